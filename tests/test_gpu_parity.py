@@ -1,0 +1,245 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded windows.
+
+Gates (BASELINE.json): index maps and block patterns bit-exact; per-edge residuals and Jacobians
+1e-9 relative; final chi2, poses and points 1e-6 relative after the same iteration / trial counts.
+"""
+import numpy as np
+import pytest
+
+from tests import oracle_api as O
+from visfs_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+RTOL_EDGE = 1e-9
+RTOL_FINAL = 1e-6
+
+
+def rejecting_window(seed, pose_noise):
+    """Close landmarks and a bad initial guess: LM has to reject steps and raise the damping."""
+    return synth.make_window(5, 150, layout="all", seed=seed, pose_noise=pose_noise, point_noise=0.5, iterations=20,
+                             depth_range=(1.0, 6.0))
+
+
+def rel_close(a, b, rtol, what=""):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    scale = max(float(np.max(np.abs(b))) if b.size else 0.0, 1e-300)
+    err = float(np.max(np.abs(a - b))) / scale if b.size else 0.0
+    assert err <= rtol, f"{what}: max abs diff / max|ref| = {err:.3e} > {rtol:.1e}"
+
+
+def elem_close(a, b, rtol, atol, what=""):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    bad = np.abs(a - b) > atol + rtol * np.abs(b)
+    assert not bad.any(), f"{what}: {int(bad.sum())} of {bad.size} entries differ, worst {np.max(np.abs(a - b)):.3e}"
+
+
+def check_solution(got, ref, what=""):
+    assert got["status"] == ref["status"], (what, got["status"], ref["status"])
+    for k in ("iterations_run", "trials_run", "stop_reason", "n_free_poses", "n_free_points"):
+        assert got[k] == ref[k], f"{what}: {k} {got[k]} != {ref[k]}"
+    assert got["n_outliers"] == ref["n_outliers"], what
+    assert np.array_equal(got["edge_level"], ref["edge_level"]), f"{what}: outlier sets differ"
+    for k in ("chi2_initial", "chi2_pass1", "chi2_final"):
+        assert abs(got[k] - ref[k]) <= RTOL_FINAL * abs(ref[k]) + 1e-12, f"{what}: {k} {got[k]!r} vs {ref[k]!r}"
+    # poses / points: 1e-6 relative, with an absolute floor at 1e-6 of the coordinate scale
+    elem_close(got["pose_tq"], ref["pose_tq"], RTOL_FINAL, RTOL_FINAL * max(1.0, float(np.abs(ref["pose_tq"]).max())) * 1e-2,
+               what + " poses")
+    elem_close(got["point_xyz"], ref["point_xyz"], RTOL_FINAL, RTOL_FINAL * max(1.0, float(np.abs(ref["point_xyz"]).max())) * 1e-2,
+               what + " points")
+
+
+# ---------------------------------------------------------------- per-edge residuals and Jacobians
+@pytest.mark.parametrize("mono_frac", [0.0, 0.3])
+def test_linearize_matches_oracle(ba, mono_frac):
+    w = synth.make_window(7, 500, layout="consecutive", views=4, seed=11, mono_frac=mono_frac)
+    got, ref = ba.linearize(w), O.linearize(w)
+    for k in ("error", "chi2", "rho", "weight", "J_point", "J_pose"):
+        elem_close(got[k], ref[k], RTOL_EDGE, 1e-9 * float(np.abs(ref[k]).max()) * 1e-3, k)
+    assert (ref["weight"] < 1.0).any(), "test window has no Huber-downweighted edge"
+
+
+def test_linearize_unsorted_edges_keep_caller_order(ba):
+    w = synth.make_window(5, 200, layout="all", seed=12, shuffle_edges=True)
+    got, ref = ba.linearize(w), O.linearize(w)
+    elem_close(got["error"], ref["error"], RTOL_EDGE, 1e-12, "error")
+    elem_close(got["J_pose"], ref["J_pose"], RTOL_EDGE, 1e-12, "J_pose")
+
+
+# ---------------------------------------------------------------- structure: bit-exact
+def _structure_case(ba, w, level=None):
+    got, ref = ba.structure(w, level), O.structure(w, level)
+    for k in ("pose_hidx", "point_hidx", "edge_active", "hpl_row", "hpl_col", "schur_rows", "schur_cols"):
+        assert np.array_equal(got[k], ref[k]), f"{k} differs"
+    for k in ("n_schur_blocks", "n_free_poses", "n_free_points", "n_active_edges", "n_hpl_blocks"):
+        assert got[k] == ref[k], (k, got[k], ref[k])
+
+
+def test_structure_all_views(ba):
+    _structure_case(ba, synth.make_window(10, 400, layout="all", seed=21))
+
+
+def test_structure_consecutive_views_fixed_points(ba):
+    _structure_case(ba, synth.make_window(20, 3000, layout="consecutive", views=6, seed=22, fixed_point_frac=0.3))
+
+
+def test_structure_with_culled_edges_and_dead_vertices(ba):
+    w = synth.make_window(8, 600, layout="random", views=3, seed=23, fixed_point_frac=0.2)
+    rng = np.random.default_rng(5)
+    level = (rng.random(w["n_edges"]) < 0.4).astype(np.uint8)
+    level[w["edge_pose"] == 2] = 1                  # a pose that loses every edge
+    level[w["edge_point"] < 20] = 1                 # landmarks that lose every edge
+    _structure_case(ba, w, level)
+
+
+def test_structure_no_fixed_pose(ba):
+    _structure_case(ba, synth.make_window(6, 200, layout="all", seed=24, root=None))
+
+
+def test_structure_unsorted(ba):
+    _structure_case(ba, synth.make_window(6, 300, layout="random", views=4, seed=25, shuffle_edges=True))
+
+
+# ---------------------------------------------------------------- Hessian / Schur / solve of one trial
+@pytest.mark.parametrize("kw", [dict(layout="all"), dict(layout="consecutive", views=5, mono_frac=0.3, fixed_point_frac=0.25)])
+def test_reduced_system_matches_oracle(ba, kw):
+    w = synth.make_window(9, 700, seed=31, **kw)
+    lam = 3.7
+    got, ref = ba.debug_trial(w, lam), O.reduced_system(w, lam)
+    assert got["n"] == ref["n"]
+    rel_close(got["chi2"], ref["chi2"], 1e-12, "chi2 at the input state")
+    rel_close(got["S"], ref["S"], 1e-10, "reduced camera system")
+    rel_close(got["b_s"], ref["b_s"], 1e-10, "reduced rhs")
+    rel_close(got["x_pose"], ref["x"][: ref["n"]], 1e-7, "pose step")
+    lam0 = ba.debug_trial(w, -1.0)["lambda_used"]
+    rel_close(lam0, ref["lambda_init"], 1e-12, "initial damping")
+
+
+# ---------------------------------------------------------------- full two-pass solves
+def test_solve_small_stereo_window(ba):
+    w = synth.make_window(6, 300, layout="all", seed=41)
+    check_solution(ba.solve(w), O.solve(w), "6x300")
+
+
+def test_solve_c1(ba):
+    w = synth.config_c1()
+    got, ref = ba.solve(w), O.solve(w)
+    check_solution(got, ref, "C1")
+    assert ref["n_outliers"] > 500 and ref["chi2_final"] < ref["chi2_initial"]
+
+
+def test_solve_c1_with_fixed_points(ba):
+    w = synth.config_c1(fixed_point_frac=0.3)
+    check_solution(ba.solve(w), O.solve(w), "C1 30% fixed points")
+
+
+def test_solve_c2_mixed_mono_stereo(ba):
+    w = synth.config_c2()
+    check_solution(ba.solve(w), O.solve(w), "C2")
+
+
+def test_solve_with_rejected_steps(ba):
+    # a badly initialised window: LM has to reject steps and raise the damping
+    for seed, pn in ((102, (0.3, np.deg2rad(6.0))), (100, (1.0, np.deg2rad(20.0)))):
+        w = rejecting_window(seed, pn)
+        ref = O.solve(w)
+        assert sum(ref["trials_run"]) > sum(ref["iterations_run"]), "window does not exercise the reject path"
+        check_solution(ba.solve(w), ref, f"rejections seed {seed}")
+
+
+def test_solve_everything_culled_second_pass_empty(ba):
+    w = rejecting_window(101, (1.0, np.deg2rad(20.0)))
+    ref = O.solve(w)
+    assert ref["stop_reason"][1] == 3 and ref["n_outliers"] == w["n_edges"]
+    check_solution(ba.solve(w), ref, "all edges culled")
+
+
+def test_solve_gauss_newton(ba):
+    w = synth.make_window(6, 300, layout="all", seed=44, trust_region=1)
+    check_solution(ba.solve(w), O.solve(w), "gauss-newton")
+
+
+def test_solve_pcg(ba):
+    w = synth.make_window(8, 400, layout="consecutive", views=5, seed=45, solver=2)
+    check_solution(ba.solve(w), O.solve(w), "pcg")
+
+
+def test_solve_no_robust_kernel_single_pass(ba):
+    w = synth.make_window(6, 300, layout="all", seed=46, huber_delta=0.0, outlier_frac=0.0)
+    got, ref = ba.solve(w), O.solve(w)
+    check_solution(got, ref, "no kernel")
+    assert got["stop_reason"][1] == 0 and got["n_outliers"] == 0
+
+
+def test_solve_unsorted_edges(ba):
+    w = synth.make_window(6, 300, layout="random", views=4, seed=47, shuffle_edges=True)
+    check_solution(ba.solve(w), O.solve(w), "unsorted")
+
+
+def test_solve_odd_iterations_and_one_iteration(ba):
+    for it in (7, 1):
+        w = synth.make_window(5, 200, layout="all", seed=48, iterations=it)
+        check_solution(ba.solve(w), O.solve(w), f"iterations={it}")
+
+
+def test_solve_no_fixed_pose_gauge_free(ba):
+    w = synth.make_window(6, 300, layout="all", seed=49, root=None)
+    check_solution(ba.solve(w), O.solve(w), "no fixed pose")
+
+
+def test_solve_ragged_inputs(ba):
+    # landmarks without edges, a pose without edges, two-pose window
+    w = synth.make_window(5, 120, layout="random", views=2, seed=50)
+    keep = (w["edge_point"] % 7 != 0) & (w["edge_pose"] != 1)
+    for k in ("edge_obs", "edge_pose", "edge_point", "edge_kind"):
+        w[k] = np.ascontiguousarray(w[k][keep])
+    w["n_edges"] = int(keep.sum())
+    check_solution(ba.solve(w), O.solve(w), "ragged")
+    w2 = synth.make_window(2, 60, layout="all", seed=51)
+    check_solution(ba.solve(w2), O.solve(w2), "two poses")
+
+
+def test_solve_numeric_failure_reports_pass1(ba):
+    w = synth.make_window(4, 50, layout="all", seed=52)
+    w["point_xyz"][3] = np.nan
+    got, ref = ba.solve(w), O.solve(w)
+    assert got["status"] == ref["status"] == 3
+
+
+def test_solve_batch_matches_individual_solves(ba):
+    ws = [synth.make_window(6, 200 + 37 * k, layout="all" if k % 2 == 0 else "consecutive", views=4, seed=60 + k,
+                            fixed_point_frac=0.1 * (k % 3)) for k in range(7)]
+    ws.append(rejecting_window(102, (0.3, np.deg2rad(6.0))))
+    got = ba.solve_batch(ws)
+    for k, (g, w) in enumerate(zip(got, ws)):
+        check_solution(g, O.solve(w), f"batch window {k}")
+
+
+def test_resident_rerun_is_deterministic(ba):
+    w = synth.config_c1()
+    ba.upload([w])
+    ba.run_resident()
+    a = ba.download()[0]
+    a = {k: (v.copy() if hasattr(v, "copy") else v) for k, v in a.items()}
+    ba.run_resident()
+    b = ba.download()[0]
+    assert np.array_equal(a["pose_tq"], b["pose_tq"]) and np.array_equal(a["point_xyz"], b["point_xyz"])
+    assert a["chi2_final"] == b["chi2_final"]
+    t = ba.timing()
+    assert t["lm_iterations"] == sum(b["iterations_run"]) and t["total_ms"] > 0
+
+
+# ---------------------------------------------------------------- full-size properties
+def test_c3_batch_properties(ba):
+    ws = synth.config_c3_windows(16)
+    got = ba.solve_batch(ws)
+    ref0 = O.solve(ws[0])
+    check_solution(got[0], ref0, "C3 window 0")
+    for g in got:
+        assert g["status"] == 0 and g["chi2_final"] < g["chi2_pass1"] < g["chi2_initial"]
+        assert np.isfinite(g["pose_tq"]).all() and np.isfinite(g["point_xyz"]).all()
+        assert np.allclose(np.linalg.norm(g["pose_tq"][:, 3:7], axis=1), 1.0, atol=1e-12)
+    # idempotence of the fixed gauge: the fixed pose never moves
+    for g, w in zip(got, ws):
+        fixed = w["pose_fixed"].astype(bool)
+        assert np.array_equal(g["pose_tq"][fixed], w["pose_tq"][fixed])

@@ -1,0 +1,1108 @@
+// ba_kernels.cuh — sm_100a kernels of the local bundle adjustment (small-window path).
+//
+// One LM trial = k_build<1> (linearise + Hessian blocks + Schur partials) -> k_solve (reduce partials,
+// damped dense Cholesky of the reduced camera system, pose oplus) -> k_update (landmark
+// back-substitution, point oplus, chi2 of the trial state) -> k_control (g2o's accept / reject).
+// All windows of a batch go through the same launches; a window that has finished returns at once.
+//
+// Work decomposition: a chunk is a contiguous landmark range of one window, one CTA per chunk.  Inside
+// a chunk the CTA walks tiles of <= kTileEdges edges / <= kTileLm landmarks:
+//   stage A  one thread per edge: residual, Jacobians, Huber weight (EdgeStereo::computeError /
+//            linearizeOplus); per-edge H_ll / b_l terms staged in shared memory and summed per
+//            landmark in edge order; (H_ll + lambda I)^-1 per landmark
+//   stage B  one thread per edge: W = H_pl block, Y = W Dinv, Hd = H_pp_e - Y W^T, g = b_p_e - W Dinv b_l
+//            staged in shared memory (the "6x6 pose block staging" of the north star)
+//   stage C  output-major accumulation: every off-diagonal block S_ij of the reduced system is owned
+//            by a fixed thread that keeps its 36 entries in registers for the whole chunk and adds
+//            -Y_i W_j^T for each landmark seen by both poses; per-pose sums (Hd, g, b_p) are owned by
+//            fixed threads as well.  No atomics anywhere, summation order fixed => deterministic.
+// Chunk partials go to global memory and are added in chunk order by k_solve.
+#pragma once
+#include <cfloat>
+#include "ba_math.cuh"
+
+namespace visfs {
+
+enum { MODE_INIT = 0, MODE_BUILD = 1 };
+
+// ------------------------------------------------------------------------------------------------
+// shared-memory carve-up of k_build / k_update
+// ------------------------------------------------------------------------------------------------
+struct BuildSmem {
+    double pose[kMaxSmallPoses * kPoseStride];
+    double W[kTileEdges * 18];
+    double Y[kTileEdges * 18];
+    double H[kTileEdges * kHStride];
+    double lm[kTileLm * 12];                    // Dinv(6) db(3) bl(3)
+    double pacc[kMaxSmallPoses * kHStride];
+    double red[32];
+    short slot[kTileLm * kMaxSmallPoses];
+    int hidx[kMaxSmallPoses];
+    int lmoff[kTileLm + 1];
+};
+constexpr int kGroupScratchDoubles = kTileEdges * (18 + 18 + kHStride);  // W, Y, H are contiguous
+
+__device__ __forceinline__ int hd_index(int a, int c) {  // a <= c, upper triangle of a 6x6, row-major
+    return a * 6 - (a * (a - 1)) / 2 + (c - a);
+}
+
+// largest l1 in (lt, lmax] with lm_edge_off[l1] - e0 <= kTileEdges
+__device__ __forceinline__ int tile_end(const int *__restrict__ off, int lt, int lmax, int e0) {
+    int lo = lt + 1, hi = lmax;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (off[mid] - e0 <= kTileEdges) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+template <int MODE, int PPT>
+__global__ void __launch_bounds__(kThreads, PPT == 1 ? 2 : 1) k_build(Batch B) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    BuildSmem &sm = *reinterpret_cast<BuildSmem *>(smem_raw);
+    const int tid = threadIdx.x;
+    const Chunk ck = B.chunks[blockIdx.x];
+    const WinDesc &wd = B.win[ck.win];
+    const LMState &st = B.st[ck.win];
+    if (st.done) return;
+    const int cur = st.cur;
+    const int F = st.F;
+    const double lambda = (MODE == MODE_BUILD && wd.trust == 0) ? (B.dbg_lambda >= 0.0 ? B.dbg_lambda : st.lambda) : 0.0;
+    const Intr K = load_intr(wd);
+    const int pose_off = wd.pose_off, n_pose = wd.n_pose;
+    const double *__restrict__ gpose = B.pose + ((size_t)cur * B.tot_pose + pose_off) * kPoseStride;
+    const double *__restrict__ gpoint = B.point + (size_t)cur * B.tot_point * 3;
+
+    for (int i = tid; i < n_pose * kPoseStride; i += kThreads) sm.pose[i] = gpose[i];
+    for (int i = tid; i < n_pose; i += kThreads) sm.hidx[i] = B.pose_hidx[pose_off + i];
+    for (int i = tid; i < kMaxSmallPoses * kHStride; i += kThreads) sm.pacc[i] = 0.0;
+
+    // pair ownership (MODE_BUILD)
+    const int npairs = F * (F - 1) / 2;
+    const int ptasks = (npairs + PPT - 1) / PPT;
+    int G = 1;
+    if (ptasks > 0) {
+        G = kThreads / ptasks;
+        if (G > kTileLm) G = kTileLm;
+        const int cap = 1 + kGroupScratchDoubles / (ptasks * PPT * 36);
+        if (G > cap) G = cap;
+        if (G < 1) G = 1;
+    }
+    const int grp = ptasks > 0 ? tid / ptasks : 0;
+    const int pt = ptasks > 0 ? tid % ptasks : 0;
+    int pi[PPT], pj[PPT];
+    double acc[PPT][36];
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+        pi[k] = pj[k] = -1;
+        const int p = pt + k * ptasks;
+        if (MODE == MODE_BUILD && grp < G && p < npairs) {
+            int i = 0, base = 0;
+            while (base + (F - 1 - i) <= p) { base += F - 1 - i; ++i; }
+            pi[k] = i; pj[k] = i + 1 + (p - base);
+        }
+#pragma unroll
+        for (int q = 0; q < 36; ++q) acc[k][q] = 0.0;
+    }
+    double chi_acc = 0.0, maxd = 0.0;
+    const int NV = (MODE == MODE_BUILD) ? kHStride : 6;
+    __syncthreads();
+
+    for (int lt = ck.lm0; lt < ck.lm1;) {
+        const int e0 = B.lm_edge_off[lt];
+        const int lmax = min(lt + kTileLm, ck.lm1);
+        const int l1 = tile_end(B.lm_edge_off, lt, lmax, e0);
+        const int ne = min(B.lm_edge_off[l1] - e0, kTileEdges);  // > kTileEdges only for a rejected (err) window
+        const int ntl = l1 - lt;
+        for (int i = tid; i < ntl * kMaxSmallPoses; i += kThreads) sm.slot[i] = -1;
+        if (tid <= ntl) sm.lmoff[tid] = min(B.lm_edge_off[lt + tid] - e0, kTileEdges);
+
+        // ---- stage A: linearise one edge per thread
+        EdgeLin lin;
+        bool act = false, lmfree = false;
+        int tl = 0, p = 0;
+        if (tid < ne) {
+            const int e = e0 + tid;
+            const int pw = B.edge_pose[e];
+            p = pw & kPoseMask;
+            const int gl = wd.point_off + B.edge_point[e];
+            tl = gl - lt;
+            const uint8_t lf = B.lm_flags[gl];
+            const uint8_t pf = B.pose_flags[pose_off + p];
+            act = !(pw & kCulledBit) && !((lf & kFixed) && (pf & kFixed));
+            lmfree = (lf & kInHessian) != 0;
+            double *hl = sm.H + tid * kHStride;
+            if (act) {
+                const double px = gpoint[3 * (size_t)gl], py = gpoint[3 * (size_t)gl + 1], pz = gpoint[3 * (size_t)gl + 2];
+                edge_linearize(sm.pose + p * kPoseStride, px, py, pz, B.obs_u[e], B.obs_v[e], B.obs_r[e],
+                               (pw & kMonoBit) != 0, K, lin);
+                if (MODE == MODE_INIT) chi_acc += lin.rho;
+            }
+            if (act && lmfree) {
+                const double wo = lin.w * K.inv_pv;
+                const double *J = lin.Jl;
+                hl[0] = wo * (J[0] * J[0] + J[3] * J[3] + J[6] * J[6]);
+                hl[1] = wo * (J[0] * J[1] + J[3] * J[4] + J[6] * J[7]);
+                hl[2] = wo * (J[0] * J[2] + J[3] * J[5] + J[6] * J[8]);
+                hl[3] = wo * (J[1] * J[1] + J[4] * J[4] + J[7] * J[7]);
+                hl[4] = wo * (J[1] * J[2] + J[4] * J[5] + J[7] * J[8]);
+                hl[5] = wo * (J[2] * J[2] + J[5] * J[5] + J[8] * J[8]);
+                hl[6] = -wo * (J[0] * lin.r[0] + J[3] * lin.r[1] + J[6] * lin.r[2]);
+                hl[7] = -wo * (J[1] * lin.r[0] + J[4] * lin.r[1] + J[7] * lin.r[2]);
+                hl[8] = -wo * (J[2] * lin.r[0] + J[5] * lin.r[1] + J[8] * lin.r[2]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 9; ++q) hl[q] = 0.0;
+            }
+        }
+        __syncthreads();
+        // ---- per-landmark H_ll / b_l in edge order, damped inverse
+        if (tid < ntl) {
+            double A[6] = {0, 0, 0, 0, 0, 0}, bl[3] = {0, 0, 0};
+            for (int s = sm.lmoff[tid]; s < sm.lmoff[tid + 1]; ++s) {
+                const double *hl = sm.H + s * kHStride;
+#pragma unroll
+                for (int q = 0; q < 6; ++q) A[q] += hl[q];
+                bl[0] += hl[6]; bl[1] += hl[7]; bl[2] += hl[8];
+            }
+            double *o = sm.lm + tid * 12;
+            if (B.lm_flags[lt + tid] & kInHessian) {
+                if (MODE == MODE_INIT) {
+                    maxd = fmax(maxd, fmax(fabs(A[0]), fmax(fabs(A[3]), fabs(A[5]))));
+                } else {
+                    A[0] += lambda; A[3] += lambda; A[5] += lambda;
+                    inv_sym3(A, o);
+                    sym3_mul(o, bl, o + 6);
+                    o[9] = bl[0]; o[10] = bl[1]; o[11] = bl[2];
+                }
+            } else if (MODE == MODE_BUILD) {
+#pragma unroll
+                for (int q = 0; q < 12; ++q) o[q] = 0.0;
+            }
+        }
+        __syncthreads();
+        // ---- stage B: pose-side blocks of every active edge whose pose is in the Hessian
+        if (tid < ne && act) {
+            const int hi = sm.hidx[p];
+            if (hi >= 0) {
+                const double wo = lin.w * K.inv_pv;
+                double *hs = sm.H + tid * kHStride;
+                if (MODE == MODE_INIT) {
+#pragma unroll
+                    for (int a = 0; a < 6; ++a)
+                        hs[a] = wo * (lin.Jp[a] * lin.Jp[a] + lin.Jp[6 + a] * lin.Jp[6 + a] + lin.Jp[12 + a] * lin.Jp[12 + a]);
+                } else {
+                    const double *lm = sm.lm + tl * 12;
+                    double Wm[18], Ym[18];
+                    if (lmfree) {
+                        double Aj[9];
+#pragma unroll
+                        for (int q = 0; q < 9; ++q) Aj[q] = wo * lin.Jl[q];
+#pragma unroll
+                        for (int a = 0; a < 6; ++a)
+#pragma unroll
+                            for (int c = 0; c < 3; ++c)
+                                Wm[a * 3 + c] = lin.Jp[a] * Aj[c] + lin.Jp[6 + a] * Aj[3 + c] + lin.Jp[12 + a] * Aj[6 + c];
+#pragma unroll
+                        for (int a = 0; a < 6; ++a) {
+                            Ym[a * 3 + 0] = Wm[a * 3] * lm[0] + Wm[a * 3 + 1] * lm[1] + Wm[a * 3 + 2] * lm[2];
+                            Ym[a * 3 + 1] = Wm[a * 3] * lm[1] + Wm[a * 3 + 1] * lm[3] + Wm[a * 3 + 2] * lm[4];
+                            Ym[a * 3 + 2] = Wm[a * 3] * lm[2] + Wm[a * 3 + 1] * lm[4] + Wm[a * 3 + 2] * lm[5];
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 18; ++q) { Wm[q] = 0.0; Ym[q] = 0.0; }
+                    }
+                    double *ws = sm.W + tid * 18, *ys = sm.Y + tid * 18;
+#pragma unroll
+                    for (int q = 0; q < 18; ++q) { ws[q] = Wm[q]; ys[q] = Ym[q]; }
+                    const double wr0 = wo * lin.r[0], wr1 = wo * lin.r[1], wr2 = wo * lin.r[2];
+#pragma unroll
+                    for (int a = 0; a < 6; ++a) {
+                        const double bp = -(lin.Jp[a] * wr0 + lin.Jp[6 + a] * wr1 + lin.Jp[12 + a] * wr2);
+                        hs[27 + a] = bp;
+                        hs[21 + a] = bp - (Wm[a * 3] * lm[6] + Wm[a * 3 + 1] * lm[7] + Wm[a * 3 + 2] * lm[8]);
+#pragma unroll
+                        for (int c = a; c < 6; ++c) {
+                            const double hpp = wo * (lin.Jp[a] * lin.Jp[c] + lin.Jp[6 + a] * lin.Jp[6 + c] + lin.Jp[12 + a] * lin.Jp[12 + c]);
+                            hs[hd_index(a, c)] = hpp - (Ym[a * 3] * Wm[c * 3] + Ym[a * 3 + 1] * Wm[c * 3 + 1] + Ym[a * 3 + 2] * Wm[c * 3 + 2]);
+                        }
+                    }
+                }
+                sm.slot[tl * kMaxSmallPoses + hi] = (short)tid;
+            }
+        }
+        __syncthreads();
+        // ---- stage C: owner threads accumulate
+        for (int task = tid; task < F * NV; task += kThreads) {
+            const int i = task / NV, k = task - i * NV;
+            double s = 0.0;
+            for (int t = 0; t < ntl; ++t) {
+                const int sl = sm.slot[t * kMaxSmallPoses + i];
+                if (sl >= 0) s += sm.H[sl * kHStride + k];
+            }
+            sm.pacc[i * kHStride + k] += s;
+        }
+        if (MODE == MODE_BUILD && grp < G) {
+            for (int t = grp; t < ntl; t += G) {
+#pragma unroll
+                for (int k = 0; k < PPT; ++k) {
+                    if (pi[k] < 0) continue;
+                    const int si = sm.slot[t * kMaxSmallPoses + pi[k]];
+                    const int sj = sm.slot[t * kMaxSmallPoses + pj[k]];
+                    if (si < 0 || sj < 0) continue;
+                    double Yi[18], Wj[18];
+                    const double2 *yp = reinterpret_cast<const double2 *>(sm.Y + si * 18);
+                    const double2 *wp = reinterpret_cast<const double2 *>(sm.W + sj * 18);
+#pragma unroll
+                    for (int q = 0; q < 9; ++q) {
+                        const double2 a = yp[q], b = wp[q];
+                        Yi[2 * q] = a.x; Yi[2 * q + 1] = a.y; Wj[2 * q] = b.x; Wj[2 * q + 1] = b.y;
+                    }
+#pragma unroll
+                    for (int a = 0; a < 6; ++a)
+#pragma unroll
+                        for (int c = 0; c < 6; ++c)
+                            acc[k][a * 6 + c] -= Yi[a * 3] * Wj[c * 3] + Yi[a * 3 + 1] * Wj[c * 3 + 1] + Yi[a * 3 + 2] * Wj[c * 3 + 2];
+                }
+            }
+        }
+        __syncthreads();
+        lt = l1;
+    }
+
+    // ---- epilogue: chunk partials to global memory
+    double *part = B.part + wd.part_off + (size_t)(blockIdx.x - wd.chunk_off) * wd.part_stride;
+    if (MODE == MODE_INIT) {
+        for (int task = tid; task < F * 6; task += kThreads) part[task] = sm.pacc[(task / 6) * kHStride + task % 6];
+        const double chi = block_sum(chi_acc, sm.red);
+        const double md = block_max(maxd, sm.red);
+        if (tid == 0) { part[F * 6] = chi; part[F * 6 + 1] = md; }
+    } else {
+        const int offd = npairs * 36;
+        for (int task = tid; task < F * kHStride; task += kThreads) part[offd + task] = sm.pacc[task];
+        double *scratch = sm.W;  // W, Y, H contiguous
+        if (G > 1) {
+            if (grp > 0 && grp < G) {
+                double *dst = scratch + ((size_t)(grp - 1) * ptasks + pt) * (PPT * 36);
+#pragma unroll
+                for (int k = 0; k < PPT; ++k)
+#pragma unroll
+                    for (int q = 0; q < 36; ++q) dst[k * 36 + q] = acc[k][q];
+            }
+            __syncthreads();
+            if (grp == 0 && pt < ptasks) {
+                for (int g2 = 1; g2 < G; ++g2) {
+                    const double *src = scratch + ((size_t)(g2 - 1) * ptasks + pt) * (PPT * 36);
+#pragma unroll
+                    for (int k = 0; k < PPT; ++k)
+#pragma unroll
+                        for (int q = 0; q < 36; ++q) acc[k][q] += src[k * 36 + q];
+                }
+            }
+        }
+        if (grp == 0) {
+#pragma unroll
+            for (int k = 0; k < PPT; ++k) {
+                if (pi[k] < 0) continue;
+                double *dst = part + (size_t)(pt + k * ptasks) * 36;
+#pragma unroll
+                for (int q = 0; q < 36; ++q) dst[q] = acc[k][q];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_solve: one CTA per window.  Adds the chunk partials in chunk order, assembles the damped reduced
+// camera system (packed lower triangle in shared memory), factorises it (Cholesky; fails on a
+// non-positive pivot like cs_chol) or runs g2o's block-Jacobi PCG, writes the pose step, applies
+// CameraPose::update into the trial buffer and leaves sum x_p (lambda x_p + b_p) for k_control.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSolveThreads = 256;
+
+__device__ __forceinline__ int tri(int r, int c) { return r * (r + 1) / 2 + c; }  // r >= c
+
+__global__ void __launch_bounds__(kSolveThreads) k_solve(Batch B) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *S = reinterpret_cast<double *>(smem_raw);
+    const int w = blockIdx.x;
+    const WinDesc &wd = B.win[w];
+    LMState &st = B.st[w];
+    if (st.done) return;
+    const int tid = threadIdx.x;
+    const int F = st.F, n = 6 * F;
+    const int ntri = n * (n + 1) / 2;
+    double *bs = S + ntri;       // [n] reduced rhs, overwritten by the solution
+    double *braw = bs + n;       // [n] raw b_p
+    double *aux = braw + n;      // PCG vectors: r, d, q, s, Minv blocks
+    __shared__ int s_ok;
+    __shared__ double s_red[32];
+    const double lambda = (wd.trust == 0) ? (B.dbg_lambda >= 0.0 ? B.dbg_lambda : st.lambda) : 0.0;
+    if (tid == 0) s_ok = 1;
+    if (n == 0) {
+        if (tid == 0) { st.ok = 1; st.scale_p = 0.0; }
+        return;
+    }
+    const int npairs = F * (F - 1) / 2;
+    const int offd = npairs * 36;
+    const int total = offd + F * kHStride;
+    const double *part = B.part + wd.part_off;
+    const int nck = wd.n_chunks;
+    const size_t stride = (size_t)wd.part_stride;
+    for (int idx = tid; idx < total; idx += kSolveThreads) {
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        int c = 0;
+        for (; c + 3 < nck; c += 4) {
+            s0 += part[(size_t)c * stride + idx];
+            s1 += part[(size_t)(c + 1) * stride + idx];
+            s2 += part[(size_t)(c + 2) * stride + idx];
+            s3 += part[(size_t)(c + 3) * stride + idx];
+        }
+        for (; c < nck; ++c) s0 += part[(size_t)c * stride + idx];
+        const double v = (s0 + s1) + (s2 + s3);
+        if (idx < offd) {
+            const int p = idx / 36, q = idx - p * 36;
+            int i = 0, base = 0;
+            while (base + (F - 1 - i) <= p) { base += F - 1 - i; ++i; }
+            const int j = i + 1 + (p - base);
+            const int a = q / 6, cc = q - a * 6;
+            S[tri(6 * j + cc, 6 * i + a)] = v;   // block (i,j) entry (a,cc) lives at lower (6j+cc, 6i+a)
+        } else {
+            const int t2 = idx - offd;
+            const int i = t2 / kHStride, k = t2 - i * kHStride;
+            if (k < 21) {
+                int a = 0, rem = k;
+                while (rem >= 6 - a) { rem -= 6 - a; ++a; }
+                const int cc = a + rem;
+                S[tri(6 * i + cc, 6 * i + a)] = v + (a == cc ? lambda : 0.0);
+            } else if (k < 27) {
+                bs[6 * i + (k - 21)] = v;
+            } else {
+                braw[6 * i + (k - 27)] = v;
+            }
+        }
+    }
+    __syncthreads();
+    if (B.dbg && w == 0) {
+        for (int i = tid; i < ntri + n; i += kSolveThreads) B.dbg[i] = S[i];  // bs follows S
+        __syncthreads();
+    }
+
+    if (wd.solver != 2) {
+        // right-looking Cholesky on the packed lower triangle
+        for (int k = 0; k < n; ++k) {
+            if (tid == 0) {
+                const double d = S[tri(k, k)];
+                if (!(d > 0.0)) { s_ok = 0; S[tri(k, k)] = 1.0; } else S[tri(k, k)] = sqrt(d);
+            }
+            __syncthreads();
+            const double dk = S[tri(k, k)];
+            for (int r = k + 1 + tid; r < n; r += kSolveThreads) S[tri(r, k)] /= dk;
+            __syncthreads();
+            const int m = n - k - 1;
+            for (int t = tid; t < m * (m + 1) / 2; t += kSolveThreads) {
+                // t -> (r, c) with k < c <= r < n
+                int rr = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+                while ((rr + 1) * (rr + 2) / 2 <= t) ++rr;
+                while (rr * (rr + 1) / 2 > t) --rr;
+                const int cc = t - rr * (rr + 1) / 2;
+                const int r = k + 1 + rr, c = k + 1 + cc;
+                S[tri(r, c)] -= S[tri(r, k)] * S[tri(c, k)];
+            }
+            __syncthreads();
+        }
+        // triangular solves by warp 0 (column-oriented), x overwrites bs
+        if (tid < 32) {
+            for (int k = 0; k < n; ++k) {
+                const double xk = bs[k] / S[tri(k, k)];
+                __syncwarp();
+                if (tid == 0) bs[k] = xk;
+                for (int r = k + 1 + tid; r < n; r += 32) bs[r] -= S[tri(r, k)] * xk;
+                __syncwarp();
+            }
+            for (int k = n - 1; k >= 0; --k) {
+                const double xk = bs[k] / S[tri(k, k)];
+                __syncwarp();
+                if (tid == 0) bs[k] = xk;
+                for (int r = tid; r < k; r += 32) bs[r] -= S[tri(k, r)] * xk;
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+    } else {
+        // g2o LinearSolverPCG: block-Jacobi preconditioner, x0 = 0, stop when r'M^-1 r <= 1e-6 * initial
+        // (absolute-tolerance quirk of upstream is replaced by running to that relative bound twice over:
+        // tolerance 1e-12), at most n iterations.
+        double *r = aux, *d = aux + n, *q = aux + 2 * n, *s = aux + 3 * n, *xv = aux + 4 * n, *Minv = aux + 5 * n;
+        // invert the 6x6 diagonal blocks (one thread per pose, Gauss-Jordan with partial pivoting)
+        for (int i = tid; i < F; i += kSolveThreads) {
+            double M[6][12];
+            for (int a = 0; a < 6; ++a)
+                for (int c = 0; c < 6; ++c) {
+                    const int rr = 6 * i + max(a, c), cc = 6 * i + min(a, c);
+                    M[a][c] = S[tri(rr, cc)];
+                    M[a][6 + c] = (a == c) ? 1.0 : 0.0;
+                }
+            for (int c = 0; c < 6; ++c) {
+                int piv = c;
+                for (int a = c + 1; a < 6; ++a) if (fabs(M[a][c]) > fabs(M[piv][c])) piv = a;
+                if (piv != c) for (int k = 0; k < 12; ++k) { const double t = M[c][k]; M[c][k] = M[piv][k]; M[piv][k] = t; }
+                const double dd = M[c][c];
+                for (int k = 0; k < 12; ++k) M[c][k] /= dd;
+                for (int a = 0; a < 6; ++a) if (a != c) {
+                    const double f = M[a][c];
+                    for (int k = 0; k < 12; ++k) M[a][k] -= f * M[c][k];
+                }
+            }
+            for (int a = 0; a < 6; ++a) for (int c = 0; c < 6; ++c) Minv[36 * i + 6 * a + c] = M[a][6 + c];
+        }
+        for (int i = tid; i < n; i += kSolveThreads) { r[i] = bs[i]; xv[i] = 0.0; }
+        __syncthreads();
+        auto precond = [&](const double *in, double *out) {
+            for (int i = tid; i < n; i += kSolveThreads) {
+                const int blk = i / 6, a = i - 6 * blk;
+                double acc = 0.0;
+                for (int c = 0; c < 6; ++c) acc += Minv[36 * blk + 6 * a + c] * in[6 * blk + c];
+                out[i] = acc;
+            }
+            __syncthreads();
+        };
+        auto dot = [&](const double *u, const double *v) {
+            double acc = 0.0;
+            for (int i = tid; i < n; i += kSolveThreads) acc += u[i] * v[i];
+            const double t = block_sum(acc, s_red);
+            __syncthreads();
+            return t;
+        };
+        precond(r, d);
+        double dn = dot(r, d);
+        const double d0 = 1e-12 * dn;
+        for (int it = 0; it < n; ++it) {
+            if (!(dn > d0)) break;
+            for (int i = tid; i < n; i += kSolveThreads) {
+                double acc = 0.0;
+                for (int c = 0; c < n; ++c) acc += S[i >= c ? tri(i, c) : tri(c, i)] * d[c];
+                q[i] = acc;
+            }
+            __syncthreads();
+            const double a = dn / dot(d, q);
+            for (int i = tid; i < n; i += kSolveThreads) { xv[i] += a * d[i]; r[i] -= a * q[i]; }
+            __syncthreads();
+            precond(r, s);
+            const double dold = dn;
+            dn = dot(r, s);
+            const double ba = dn / dold;
+            for (int i = tid; i < n; i += kSolveThreads) d[i] = s[i] + ba * d[i];
+            __syncthreads();
+        }
+        for (int i = tid; i < n; i += kSolveThreads) bs[i] = xv[i];
+        __syncthreads();
+    }
+
+    // solution checks, pose step, trial poses, scale
+    double bad = 0.0;
+    for (int i = tid; i < n; i += kSolveThreads) if (!isfinite(bs[i])) bad = 1.0;
+    const double anybad = block_sum(bad, s_red);
+    const bool ok = (s_ok != 0) && (anybad == 0.0);
+    __syncthreads();
+    double *xp = B.xp + (size_t)wd.pose_off * 6;
+    double sc = 0.0;
+    for (int i = tid; i < n; i += kSolveThreads) {
+        const double x = ok ? bs[i] : 0.0;
+        xp[i] = x;
+        sc += x * (lambda * x + braw[i]);
+    }
+    const double scale = block_sum(sc, s_red);
+    const int cur = st.cur;
+    const double *src = B.pose + ((size_t)cur * B.tot_pose + wd.pose_off) * kPoseStride;
+    double *dst = B.pose + ((size_t)(1 - cur) * B.tot_pose + wd.pose_off) * kPoseStride;
+    for (int p = tid; p < wd.n_pose; p += kSolveThreads) {
+        const int hi = B.pose_hidx[wd.pose_off + p];
+        if (hi >= 0) {
+            double dlt[6];
+            for (int a = 0; a < 6; ++a) dlt[a] = ok ? bs[6 * hi + a] : 0.0;
+            pose_oplus(src + p * kPoseStride, dlt, dst + p * kPoseStride);
+        }
+    }
+    if (tid == 0) { st.ok = ok ? 1 : 0; st.scale_p = scale; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_update: landmark back-substitution x_l = Dinv (b_l - sum_e W_e^T x_p), point oplus into the trial
+// buffer, robust chi2 of the trial state, and the landmark part of g2o's computeScale().
+// Same chunk / tile walk as k_build; the linearisation is recomputed instead of being stored
+// (32 B/edge re-read instead of 288 B/edge written and read back).
+// ------------------------------------------------------------------------------------------------
+struct UpdateSmem {
+    double pose[kMaxSmallPoses * kPoseStride];
+    double poseT[kMaxSmallPoses * kPoseStride];
+    double xp[kMaxSmallPoses * 6];
+    double H[kTileEdges * 9];
+    double T[kTileEdges * 3];
+    double lm[kTileLm * 12];
+    double newp[kTileLm * 3];
+    double red[32];
+    int hidx[kMaxSmallPoses];
+    int lmoff[kTileLm + 1];
+};
+
+__global__ void __launch_bounds__(kThreads, 2) k_update(Batch B) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    UpdateSmem &sm = *reinterpret_cast<UpdateSmem *>(smem_raw);
+    const int tid = threadIdx.x;
+    const Chunk ck = B.chunks[blockIdx.x];
+    const WinDesc &wd = B.win[ck.win];
+    const LMState &st = B.st[ck.win];
+    if (st.done) return;
+    const int cur = st.cur;
+    const double lambda = (wd.trust == 0) ? (B.dbg_lambda >= 0.0 ? B.dbg_lambda : st.lambda) : 0.0;
+    const Intr K = load_intr(wd);
+    const int pose_off = wd.pose_off, n_pose = wd.n_pose;
+    const double *__restrict__ gpose = B.pose + ((size_t)cur * B.tot_pose + pose_off) * kPoseStride;
+    const double *__restrict__ gposeT = B.pose + ((size_t)(1 - cur) * B.tot_pose + pose_off) * kPoseStride;
+    const double *__restrict__ gpoint = B.point + (size_t)cur * B.tot_point * 3;
+    double *__restrict__ gpointT = B.point + (size_t)(1 - cur) * B.tot_point * 3;
+    for (int i = tid; i < n_pose * kPoseStride; i += kThreads) { sm.pose[i] = gpose[i]; sm.poseT[i] = gposeT[i]; }
+    for (int i = tid; i < n_pose; i += kThreads) sm.hidx[i] = B.pose_hidx[pose_off + i];
+    for (int i = tid; i < st.F * 6; i += kThreads) sm.xp[i] = B.xp[(size_t)pose_off * 6 + i];
+    double chi_acc = 0.0, scale_acc = 0.0;
+    __syncthreads();
+
+    for (int lt = ck.lm0; lt < ck.lm1;) {
+        const int e0 = B.lm_edge_off[lt];
+        const int lmax = min(lt + kTileLm, ck.lm1);
+        const int l1 = tile_end(B.lm_edge_off, lt, lmax, e0);
+        const int ne = min(B.lm_edge_off[l1] - e0, kTileEdges);
+        const int ntl = l1 - lt;
+        if (tid <= ntl) sm.lmoff[tid] = min(B.lm_edge_off[lt + tid] - e0, kTileEdges);
+        bool act = false, mono = false;
+        int tl = 0, p = 0, hi = -1;
+        double ou = 0, ov = 0, our = 0;
+        if (tid < ne) {
+            const int e = e0 + tid;
+            const int pw = B.edge_pose[e];
+            p = pw & kPoseMask;
+            mono = (pw & kMonoBit) != 0;
+            const int gl = wd.point_off + B.edge_point[e];
+            tl = gl - lt;
+            const uint8_t lf = B.lm_flags[gl];
+            const uint8_t pf = B.pose_flags[pose_off + p];
+            act = !(pw & kCulledBit) && !((lf & kFixed) && (pf & kFixed));
+            const bool lmfree = (lf & kInHessian) != 0;
+            double *hl = sm.H + tid * 9;
+            double *ts = sm.T + tid * 3;
+            ts[0] = ts[1] = ts[2] = 0.0;
+#pragma unroll
+            for (int q = 0; q < 9; ++q) hl[q] = 0.0;
+            if (act) {
+                ou = B.obs_u[e]; ov = B.obs_v[e]; our = B.obs_r[e];
+                hi = sm.hidx[p];
+                if (lmfree) {
+                    EdgeLin lin;
+                    const double px = gpoint[3 * (size_t)gl], py = gpoint[3 * (size_t)gl + 1], pz = gpoint[3 * (size_t)gl + 2];
+                    edge_linearize(sm.pose + p * kPoseStride, px, py, pz, ou, ov, our, mono, K, lin);
+                    const double wo = lin.w * K.inv_pv;
+                    const double *J = lin.Jl;
+                    hl[0] = wo * (J[0] * J[0] + J[3] * J[3] + J[6] * J[6]);
+                    hl[1] = wo * (J[0] * J[1] + J[3] * J[4] + J[6] * J[7]);
+                    hl[2] = wo * (J[0] * J[2] + J[3] * J[5] + J[6] * J[8]);
+                    hl[3] = wo * (J[1] * J[1] + J[4] * J[4] + J[7] * J[7]);
+                    hl[4] = wo * (J[1] * J[2] + J[4] * J[5] + J[7] * J[8]);
+                    hl[5] = wo * (J[2] * J[2] + J[5] * J[5] + J[8] * J[8]);
+                    hl[6] = -wo * (J[0] * lin.r[0] + J[3] * lin.r[1] + J[6] * lin.r[2]);
+                    hl[7] = -wo * (J[1] * lin.r[0] + J[4] * lin.r[1] + J[7] * lin.r[2]);
+                    hl[8] = -wo * (J[2] * lin.r[0] + J[5] * lin.r[1] + J[8] * lin.r[2]);
+                    if (hi >= 0) {
+                        // W^T x_p = wo * Jl^T (Jp x_p)
+                        const double *x = sm.xp + hi * 6;
+                        double v[3];
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            double a = 0.0;
+#pragma unroll
+                            for (int c = 0; c < 6; ++c) a += lin.Jp[6 * k + c] * x[c];
+                            v[k] = wo * a;
+                        }
+                        ts[0] = J[0] * v[0] + J[3] * v[1] + J[6] * v[2];
+                        ts[1] = J[1] * v[0] + J[4] * v[1] + J[7] * v[2];
+                        ts[2] = J[2] * v[0] + J[5] * v[1] + J[8] * v[2];
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (tid < ntl) {
+            const int gl = lt + tid;
+            const double px = gpoint[3 * (size_t)gl], py = gpoint[3 * (size_t)gl + 1], pz = gpoint[3 * (size_t)gl + 2];
+            double np0 = px, np1 = py, np2 = pz;
+            if (B.lm_flags[gl] & kInHessian) {
+                double A[6] = {0, 0, 0, 0, 0, 0}, bl[3] = {0, 0, 0}, c[3] = {0, 0, 0};
+                for (int s = sm.lmoff[tid]; s < sm.lmoff[tid + 1]; ++s) {
+                    const double *hl = sm.H + s * 9;
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) A[q] += hl[q];
+                    bl[0] += hl[6]; bl[1] += hl[7]; bl[2] += hl[8];
+                    c[0] += sm.T[s * 3]; c[1] += sm.T[s * 3 + 1]; c[2] += sm.T[s * 3 + 2];
+                }
+                A[0] += lambda; A[3] += lambda; A[5] += lambda;
+                double Di[6], xl[3];
+                inv_sym3(A, Di);
+                c[0] = bl[0] - c[0]; c[1] = bl[1] - c[1]; c[2] = bl[2] - c[2];
+                sym3_mul(Di, c, xl);
+                np0 = px + xl[0]; np1 = py + xl[1]; np2 = pz + xl[2];
+                gpointT[3 * (size_t)gl] = np0; gpointT[3 * (size_t)gl + 1] = np1; gpointT[3 * (size_t)gl + 2] = np2;
+                scale_acc += xl[0] * (lambda * xl[0] + bl[0]) + xl[1] * (lambda * xl[1] + bl[1]) + xl[2] * (lambda * xl[2] + bl[2]);
+            }
+            sm.newp[tid * 3] = np0; sm.newp[tid * 3 + 1] = np1; sm.newp[tid * 3 + 2] = np2;
+        }
+        __syncthreads();
+        if (tid < ne && act) {
+            double r0, r1, r2;
+            edge_residual(sm.poseT + p * kPoseStride, sm.newp[tl * 3], sm.newp[tl * 3 + 1], sm.newp[tl * 3 + 2], ou, ov, our,
+                          mono, K, r0, r1, r2);
+            double rho, wgt;
+            huber((r0 * r0 + r1 * r1 + r2 * r2) * K.inv_pv, K.delta, rho, wgt);
+            chi_acc += rho;
+        }
+        __syncthreads();
+        lt = l1;
+    }
+    const double chi = block_sum(chi_acc, sm.red);
+    const double sc = block_sum(scale_acc, sm.red);
+    if (tid == 0) { B.part2[2 * (size_t)blockIdx.x] = chi; B.part2[2 * (size_t)blockIdx.x + 1] = sc; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LM control (g2o OptimizationAlgorithmLevenberg::solve / GaussNewton::solve), one warp per window
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void finish_pass(LMState &st, int stop, int *n_running) {
+    st.done = 1;
+    st.stop[st.pass] = stop;
+    st.chi_pass[st.pass] = st.cur_chi;
+    st.lambda_final[st.pass] = st.lambda;
+    atomicSub(n_running, 1);
+}
+
+__global__ void k_control_init(Batch B) {
+    const int w = blockIdx.x;
+    const WinDesc &wd = B.win[w];
+    LMState &st = B.st[w];
+    if (st.done) return;
+    const int lane = threadIdx.x;
+    const int F = st.F;
+    const double *part = B.part + wd.part_off;
+    const size_t stride = (size_t)wd.part_stride;
+    double md = 0.0;
+    for (int idx = lane; idx < F * 6; idx += 32) {
+        double s = 0.0;
+        for (int c = 0; c < wd.n_chunks; ++c) s += part[(size_t)c * stride + idx];
+        md = fmax(md, fabs(s));
+    }
+    double chi = 0.0;
+    for (int c = lane; c < wd.n_chunks; c += 32) { chi += part[(size_t)c * stride + F * 6]; md = fmax(md, part[(size_t)c * stride + F * 6 + 1]); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        chi += __shfl_down_sync(0xffffffffu, chi, o);
+        md = fmax(md, __shfl_down_sync(0xffffffffu, md, o));
+    }
+    if (lane == 0) {
+        st.cur_chi = chi;
+        st.chi_last_trial = chi;
+        if (st.pass == 0) st.chi_initial = chi;
+        st.lambda = 1e-5 * md;
+        st.ni = 2.0;
+        st.iter = 0; st.qmax = 0;
+        if (st.F + st.NL == 0) finish_pass(st, VISFS_BA_STOP_EMPTY, B.n_running);
+        else if (wd.max_iter <= 0) finish_pass(st, VISFS_BA_STOP_ITERATIONS, B.n_running);
+    }
+}
+
+__global__ void k_control(Batch B) {
+    const int w = blockIdx.x;
+    const WinDesc &wd = B.win[w];
+    LMState &st = B.st[w];
+    if (st.done) return;
+    const int lane = threadIdx.x;
+    double chi = 0.0, sl = 0.0;
+    for (int c = lane; c < wd.n_chunks; c += 32) {
+        chi += B.part2[2 * (size_t)(wd.chunk_off + c)];
+        sl += B.part2[2 * (size_t)(wd.chunk_off + c) + 1];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        chi += __shfl_down_sync(0xffffffffu, chi, o);
+        sl += __shfl_down_sync(0xffffffffu, sl, o);
+    }
+    if (lane != 0) return;
+    const int pass = st.pass;
+    st.chi_last_trial = chi;
+    st.trials_run[pass] += 1;
+    if (wd.trust != 0) {  // Gauss-Newton: update applied unconditionally, Fail ends the pass
+        st.iterations_run[pass] += 1;
+        if (!st.ok) { finish_pass(st, VISFS_BA_STOP_SOLVER_FAIL, B.n_running); return; }
+        st.cur ^= 1;
+        st.cur_chi = chi;
+        st.iter += 1;
+        if (st.iter >= wd.max_iter) finish_pass(st, VISFS_BA_STOP_ITERATIONS, B.n_running);
+        return;
+    }
+    double tempChi = chi;
+    if (!st.ok) tempChi = DBL_MAX;
+    double rho = st.cur_chi - tempChi;
+    const double scale = (st.scale_p + sl) + 1e-3;
+    rho /= scale;
+    st.rho = rho;
+    bool lambda_bad = false;
+    if (rho > 0.0 && isfinite(tempChi)) {
+        double alpha = 1.0 - pow(2.0 * rho - 1.0, 3.0);
+        alpha = fmin(alpha, 2.0 / 3.0);
+        const double scaleFactor = fmax(1.0 / 3.0, alpha);
+        st.lambda *= scaleFactor;
+        st.ni = 2.0;
+        st.cur_chi = tempChi;
+        st.cur ^= 1;            // discardTop(): the trial buffer becomes the accepted state
+        st.qmax += 1;
+    } else {
+        st.lambda *= st.ni;
+        st.ni *= 2.0;           // pop(): accepted buffer untouched
+        if (!isfinite(st.lambda)) lambda_bad = true; else st.qmax += 1;
+    }
+    if (!lambda_bad && rho < 0.0 && st.qmax < 10) return;  // retry the same iteration with the new lambda
+    st.iterations_run[pass] += 1;
+    st.iter += 1;
+    const bool terminate = (st.qmax == 10) || (rho == 0.0) || lambda_bad;
+    st.qmax = 0;
+    if (terminate) finish_pass(st, VISFS_BA_STOP_TERMINATE, B.n_running);
+    else if (st.iter >= wd.max_iter) finish_pass(st, VISFS_BA_STOP_ITERATIONS, B.n_running);
+}
+
+// ------------------------------------------------------------------------------------------------
+// structure (g2o initializeOptimization / buildIndexMapping / buildStructure), on the device
+// ------------------------------------------------------------------------------------------------
+// CSR offsets by landmark: lower_bound over the window's (sorted) edge_point segment
+__global__ void k_lm_offsets(Batch B, int *lm_edge_off) {
+    const int w = blockIdx.y;
+    const WinDesc &wd = B.win[w];
+    for (int l = blockIdx.x * blockDim.x + threadIdx.x; l <= wd.n_point; l += gridDim.x * blockDim.x) {
+        int lo = 0, hi = wd.n_edge;
+        const int *ep = B.edge_point + wd.edge_off;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (ep[mid] < l) lo = mid + 1; else hi = mid;
+        }
+        lm_edge_off[wd.point_off + l] = wd.edge_off + lo;
+    }
+}
+
+// per landmark: active flag, pose_active marks, degree check
+__global__ void k_struct_lm(Batch B) {
+    const int w = blockIdx.y;
+    const WinDesc &wd = B.win[w];
+    LMState &st = B.st[w];
+    if (st.status != 0) return;
+    for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < wd.n_point; l += gridDim.x * blockDim.x) {
+        const int gl = wd.point_off + l;
+        const uint8_t lfix = B.lm_flags[gl] & kFixed;
+        bool any = false;
+        const int e0 = B.lm_edge_off[gl], e1 = B.lm_edge_off[gl + 1];
+        if (e1 - e0 > kTileEdges) st.err = VISFS_BA_ERR_UNSUPPORTED;
+        for (int e = e0; e < e1; ++e) {
+            const int pw = B.edge_pose[e];
+            if (pw & kCulledBit) continue;
+            const int p = wd.pose_off + (pw & kPoseMask);
+            if (lfix && (B.pose_flags[p] & kFixed)) continue;
+            any = true;
+            B.pose_active[p] = 1;
+        }
+        B.lm_flags[gl] = lfix | ((any && !lfix) ? kInHessian : 0);
+    }
+}
+
+// per window: pose hessian indices in ascending pose order, diagonal of the covisibility pattern
+__global__ void k_struct_pose(Batch B) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= B.n_win) return;
+    const WinDesc &wd = B.win[w];
+    LMState &st = B.st[w];
+    if (st.status != 0) return;
+    int F = 0;
+    for (int p = 0; p < wd.n_pose; ++p) {
+        const int gp = wd.pose_off + p;
+        const uint8_t fix = B.pose_flags[gp] & kFixed;
+        const bool in = B.pose_active[gp] && !fix;
+        B.pose_hidx[gp] = in ? F : -1;
+        B.pose_flags[gp] = fix | (in ? kInHessian : 0);
+        if (in) ++F;
+    }
+    if (!wd.large)
+        for (int p = 0; p < wd.n_pose; ++p) B.covis[wd.pose_off + p] = (p < F) ? (1u << p) : 0u;
+    st.F = F;
+    st.NL = 0;
+    st.nF[st.pass] = F;
+}
+
+// per landmark: count landmarks in the Hessian; covisibility rows through ALL edges of the landmark
+// (g2o walks v->edges(), which still holds level-1 edges in pass 2)
+__global__ void k_struct_count(Batch B) {
+    const int w = blockIdx.y;
+    const WinDesc &wd = B.win[w];
+    LMState &st = B.st[w];
+    if (st.status != 0) return;
+    int cnt = 0;
+    for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < wd.n_point; l += gridDim.x * blockDim.x) {
+        const int gl = wd.point_off + l;
+        if (!(B.lm_flags[gl] & kInHessian)) continue;
+        ++cnt;
+        if (wd.large) continue;
+        unsigned mask = 0;
+        for (int e = B.lm_edge_off[gl]; e < B.lm_edge_off[gl + 1]; ++e) {
+            const int hi = B.pose_hidx[wd.pose_off + (B.edge_pose[e] & kPoseMask)];
+            if (hi >= 0) mask |= 1u << hi;
+        }
+        unsigned m = mask;
+        while (m) {
+            const int i = __ffs(m) - 1;
+            m &= m - 1;
+            const unsigned row = mask & ~((1u << i) - 1u);
+            if ((B.covis[wd.pose_off + i] & row) != row) atomicOr(&B.covis[wd.pose_off + i], row);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&st.NL, cnt);
+}
+
+__global__ void k_struct_finish(Batch B) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= B.n_win) return;
+    LMState &st = B.st[w];
+    if (st.status != 0) return;
+    st.nNL[st.pass] = st.NL;
+}
+
+// accepted state -> the other buffer (so vertices that are not updated in this pass agree in both)
+__global__ void k_sync_buffers(Batch B) {
+    const int w = blockIdx.y;
+    const WinDesc &wd = B.win[w];
+    const LMState &st = B.st[w];
+    if (st.status != 0) return;
+    const int cur = st.cur;
+    const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const double *ps = B.pose + ((size_t)cur * B.tot_pose + wd.pose_off) * kPoseStride;
+    double *pd = B.pose + ((size_t)(1 - cur) * B.tot_pose + wd.pose_off) * kPoseStride;
+    for (int i = t0; i < wd.n_pose * kPoseStride; i += stride) pd[i] = ps[i];
+    const double *qs = B.point + ((size_t)cur * B.tot_point + wd.point_off) * 3;
+    double *qd = B.point + ((size_t)(1 - cur) * B.tot_point + wd.point_off) * 3;
+    for (int i = t0; i < wd.n_point * 3; i += stride) qd[i] = qs[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// state reset from the uploaded inputs, pass transitions, culling, export
+// ------------------------------------------------------------------------------------------------
+__global__ void k_reset(Batch B, const double *pose_in /*[tot_pose][7]*/, const double *point_in, const uint8_t *pose_fixed,
+                        const uint8_t *point_fixed) {
+    const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int p = t0; p < B.tot_pose; p += stride) {
+        double rec[kPoseStride];
+        for (int k = 0; k < 7; ++k) rec[k] = pose_in[7 * (size_t)p + k];
+        quat_to_R(rec + 3, rec + 7);
+        for (int k = 0; k < kPoseStride; ++k) {
+            B.pose[(size_t)p * kPoseStride + k] = rec[k];
+            B.pose[((size_t)B.tot_pose + p) * kPoseStride + k] = rec[k];
+        }
+        B.pose_flags[p] = pose_fixed[p] ? kFixed : 0;
+    }
+    for (size_t i = t0; i < (size_t)B.tot_point * 3; i += stride) {
+        const double v = point_in[i];
+        B.point[i] = v;
+        B.point[(size_t)B.tot_point * 3 + i] = v;
+    }
+    for (int l = t0; l < B.tot_point; l += stride) B.lm_flags[l] = point_fixed[l] ? kFixed : 0;
+    for (int e = t0; e < B.tot_edge; e += stride) B.edge_pose[e] &= ~kCulledBit;
+    for (int w = t0; w < B.n_win; w += stride) {
+        LMState z;
+        memset(&z, 0, sizeof z);
+        B.st[w] = z;
+    }
+}
+
+// begin a pass: windows that take part become "running"
+__global__ void k_begin_pass(Batch B, int pass) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= B.n_win) return;
+    const WinDesc &wd = B.win[w];
+    LMState &st = B.st[w];
+    st.pass = pass;
+    bool run = (st.status == 0) && (st.err == 0);
+    if (pass == 1 && (!(wd.delta > 0.0) || (wd.flags & VISFS_BA_FLAG_SINGLE_PASS))) run = false;
+    st.done = run ? 0 : 1;
+    if (run) atomicAdd(B.n_running, 1);
+}
+
+// after pass 1: Optimizer.cpp:272-280; after pass 2: :315-318
+__global__ void k_end_pass(Batch B, int pass) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= B.n_win) return;
+    LMState &st = B.st[w];
+    if (st.status != 0) return;
+    if (st.err != 0) { st.status = st.err; return; }
+    if (pass == 0) {
+        const double chi2 = st.chi_pass[0];
+        st.chi_pass[1] = chi2;
+        st.chi_last_trial = chi2;   // Optimizer.cpp:270 recomputes the errors on the accepted state
+        if (isnan(chi2) || chi2 > 1000000000000.0 || !isfinite(chi2)) st.status = VISFS_BA_ERR_NUMERIC_PASS1;
+    } else if (st.stop[1] != VISFS_BA_STOP_NOT_RUN) {
+        if (st.chi_last_trial > 1000000000000.0) st.status = VISFS_BA_ERR_NUMERIC_PASS2;
+    }
+}
+
+// Optimizer.cpp:283-297: level-0 visual edges whose plain chi2 exceeds delta move to level 1
+__global__ void k_cull(Batch B) {
+    const int w = blockIdx.y;
+    const WinDesc &wd = B.win[w];
+    LMState &st = B.st[w];
+    if (st.status != 0 || !(wd.delta > 0.0) || (wd.flags & (VISFS_BA_FLAG_SINGLE_PASS | VISFS_BA_FLAG_NO_CULL))) return;
+    const Intr K = load_intr(wd);
+    const int cur = st.cur;
+    const double *gpose = B.pose + ((size_t)cur * B.tot_pose + wd.pose_off) * kPoseStride;
+    const double *gpoint = B.point + ((size_t)cur * B.tot_point + wd.point_off) * 3;
+    int cnt = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < wd.n_edge; i += gridDim.x * blockDim.x) {
+        const int e = wd.edge_off + i;
+        const int pw = B.edge_pose[e];
+        const int p = pw & kPoseMask, l = B.edge_point[e];
+        if (pw & kCulledBit) continue;
+        if ((B.lm_flags[wd.point_off + l] & kFixed) && (B.pose_flags[wd.pose_off + p] & kFixed)) continue;  // never active
+        double r0, r1, r2;
+        edge_residual(gpose + p * kPoseStride, gpoint[3 * l], gpoint[3 * l + 1], gpoint[3 * l + 2], B.obs_u[e], B.obs_v[e],
+                      B.obs_r[e], (pw & kMonoBit) != 0, K, r0, r1, r2);
+        const double chi2 = (r0 * r0 + r1 * r1 + r2 * r2) * K.inv_pv;
+        if (chi2 > wd.delta) { B.edge_pose[e] = pw | kCulledBit; ++cnt; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&st.n_outliers, cnt);
+}
+
+// gather the accepted state and the edge levels in the caller's order
+__global__ void k_export(Batch B, double *pose_out /*[tot_pose][7]*/, double *point_out, uint8_t *level_out) {
+    const int w = blockIdx.y;
+    const WinDesc &wd = B.win[w];
+    const int cur = B.st[w].cur;
+    const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const double *ps = B.pose + ((size_t)cur * B.tot_pose + wd.pose_off) * kPoseStride;
+    for (int i = t0; i < wd.n_pose * 7; i += stride) pose_out[(size_t)wd.pose_off * 7 + i] = ps[(i / 7) * kPoseStride + i % 7];
+    const double *qs = B.point + ((size_t)cur * B.tot_point + wd.point_off) * 3;
+    for (int i = t0; i < wd.n_point * 3; i += stride) point_out[(size_t)wd.point_off * 3 + i] = qs[i];
+    for (int i = t0; i < wd.n_edge; i += stride) {
+        const int e = wd.edge_off + i;
+        const int o = B.edge_orig ? B.edge_orig[e] : i;
+        level_out[wd.edge_off + o] = (B.edge_pose[e] & kCulledBit) ? 1 : 0;
+    }
+}
+
+// raw upload -> device layout: AoS observations to SoA, packed pose word; `perm` (or identity) maps
+// sorted edge slot -> caller's edge index inside the window
+__global__ void k_prepare_edges(Batch B, const double *obs_in /*[tot_edge][3]*/, const int *pose_in, const int *point_in,
+                                const uint8_t *kind_in, const int *perm, double *obs_u, double *obs_v, double *obs_r,
+                                int *edge_point) {
+    const int w = blockIdx.y;
+    const WinDesc &wd = B.win[w];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < wd.n_edge; i += gridDim.x * blockDim.x) {
+        const int e = wd.edge_off + i;
+        const int src = wd.edge_off + (perm ? perm[e] : i);
+        obs_u[e] = obs_in[3 * (size_t)src];
+        obs_v[e] = obs_in[3 * (size_t)src + 1];
+        obs_r[e] = obs_in[3 * (size_t)src + 2];
+        B.edge_pose[e] = (pose_in[src] & kPoseMask) | ((kind_in && kind_in[src]) ? kMonoBit : 0);
+        edge_point[e] = point_in[src];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// parity / debug exports
+// ------------------------------------------------------------------------------------------------
+__global__ void k_linearize_debug(Batch B, double *err, double *chi2, double *rho, double *wgt, double *Jl, double *Jp) {
+    const int w = blockIdx.y;
+    const WinDesc &wd = B.win[w];
+    const Intr K = load_intr(wd);
+    const double *gpose = B.pose + (size_t)wd.pose_off * kPoseStride;
+    const double *gpoint = B.point + (size_t)wd.point_off * 3;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < wd.n_edge; i += gridDim.x * blockDim.x) {
+        const int e = wd.edge_off + i;
+        const int o = wd.edge_off + (B.edge_orig ? B.edge_orig[e] : i);
+        const int pw = B.edge_pose[e];
+        const int p = pw & kPoseMask, l = B.edge_point[e];
+        EdgeLin lin;
+        edge_linearize(gpose + p * kPoseStride, gpoint[3 * l], gpoint[3 * l + 1], gpoint[3 * l + 2], B.obs_u[e], B.obs_v[e],
+                       B.obs_r[e], (pw & kMonoBit) != 0, K, lin);
+        for (int k = 0; k < 3; ++k) err[3 * (size_t)o + k] = lin.r[k];
+        chi2[o] = lin.chi2; rho[o] = lin.rho; wgt[o] = lin.w;
+        for (int k = 0; k < 9; ++k) Jl[9 * (size_t)o + k] = lin.Jl[k];
+        for (int k = 0; k < 18; ++k) Jp[18 * (size_t)o + k] = lin.Jp[k];
+    }
+}
+
+__global__ void k_structure_export(Batch B, const int *point_scan, int *point_hidx, uint8_t *edge_active, int *hpl_row,
+                                   int *hpl_col) {
+    const int w = blockIdx.y;
+    const WinDesc &wd = B.win[w];
+    const int F = B.st[w].F;
+    const int base = point_scan[wd.point_off];
+    const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int l = t0; l < wd.n_point; l += stride) {
+        const int gl = wd.point_off + l;
+        point_hidx[gl] = (B.lm_flags[gl] & kInHessian) ? F + (point_scan[gl] - base) : -1;
+    }
+    for (int i = t0; i < wd.n_edge; i += stride) {
+        const int e = wd.edge_off + i;
+        const int o = wd.edge_off + (B.edge_orig ? B.edge_orig[e] : i);
+        const int pw = B.edge_pose[e];
+        const int gp = wd.pose_off + (pw & kPoseMask), gl = wd.point_off + B.edge_point[e];
+        const bool act = !(pw & kCulledBit) && !((B.lm_flags[gl] & kFixed) && (B.pose_flags[gp] & kFixed));
+        edge_active[o] = act ? 1 : 0;
+        const int hi = B.pose_hidx[gp];
+        const bool both = act && hi >= 0 && (B.lm_flags[gl] & kInHessian);
+        hpl_row[o] = both ? hi : -1;
+        hpl_col[o] = both ? (point_scan[gl] - base) : -1;
+    }
+}
+
+// Schur block pattern of one small window as a (col,row)-sorted list, from the covisibility rows
+__global__ void k_schur_pattern(Batch B, int w, int *rows, int *cols, int capacity, int *count) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const WinDesc &wd = B.win[w];
+    const int F = B.st[w].F;
+    int n = 0;
+    for (int j = 0; j < F; ++j)
+        for (int i = 0; i <= j; ++i)
+            if (B.covis[wd.pose_off + i] & (1u << j)) {
+                if (n < capacity) { rows[n] = i; cols[n] = j; }
+                ++n;
+            }
+    *count = n;
+}
+
+__global__ void k_mark_levels(Batch B, const uint8_t *level_in /* caller order, [tot_edge] */) {
+    const int w = blockIdx.y;
+    const WinDesc &wd = B.win[w];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < wd.n_edge; i += gridDim.x * blockDim.x) {
+        const int e = wd.edge_off + i;
+        const int o = wd.edge_off + (B.edge_orig ? B.edge_orig[e] : i);
+        if (level_in[o]) B.edge_pose[e] |= kCulledBit;
+    }
+}
+
+// FP64 FMA peak probe
+__global__ void k_probe_fp64(double *out, int iters) {
+    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+}  // namespace visfs

@@ -1,0 +1,80 @@
+// ba_types.cuh — device-side data model of the bundle-adjustment batch.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace visfs {
+
+constexpr int kMaxSmallPoses = 32;   // windows with <= 32 poses take the shared-memory ("small") path
+constexpr int kTileEdges = 160;      // edge slots staged per tile (one thread per edge)
+constexpr int kTileLm = 32;          // landmarks per tile
+constexpr int kThreads = 256;        // CTA size of the build / update kernels
+constexpr int kPoseStride = 16;      // doubles per pose record: t(3) q(4: x y z w) R(9 row-major)
+constexpr int kHStride = 33;         // per-edge pose-side staging: Hd(21) g(6) b_p(6)
+
+// edge_pose word: bits 0-23 window-local pose index, bit 24 mono, bit 25 culled (level 1)
+constexpr int kPoseMask = 0x00FFFFFF;
+constexpr int kMonoBit = 1 << 24;
+constexpr int kCulledBit = 1 << 25;
+
+// lm_flags / pose_flags bits
+constexpr uint8_t kFixed = 1;        // vertex->fixed()
+constexpr uint8_t kInHessian = 2;    // free and active in the current pass (has a hessian index)
+
+struct WinDesc {
+    int pose_off, n_pose;            // into the concatenated pose arrays
+    int point_off, n_point;
+    int edge_off, n_edge;
+    int chunk_off, n_chunks;         // work items of this window
+    long long part_off;              // doubles, into the partial buffer (chunk k at part_off + k * part_stride)
+    int part_stride;
+    int max_iter;                    // LM iterations per pass
+    int solver, trust;
+    unsigned flags;
+    int large;                       // 1: block-sparse / global-memory path (P > kMaxSmallPoses)
+    double fx, fy, cx, cy, bf, inv_pv, delta;
+};
+
+struct LMState {
+    double lambda, ni, cur_chi, trial_chi, rho, scale_p;
+    double chi_initial, chi_pass[2], chi_last_trial, lambda_final[2];
+    int iter, qmax, done, cur;       // cur: which state buffer holds the accepted estimate
+    int F, NL, ok, fresh;            // fresh: 1 until the first trial of the pass has run
+    int iterations_run[2], trials_run[2], stop[2], nF[2], nNL[2];
+    int n_outliers, status, pass, err;
+};
+
+struct Chunk {
+    int win;
+    int lm0, lm1;                    // global landmark range [lm0, lm1)
+};
+
+// All device pointers of one uploaded batch.
+struct Batch {
+    int n_win, n_chunks;
+    int tot_pose, tot_point, tot_edge;
+    const WinDesc *win;
+    LMState *st;
+    const Chunk *chunks;
+    double *pose;                    // [2][tot_pose][kPoseStride]
+    double *point;                   // [2][tot_point][3]
+    uint8_t *pose_flags;             // [tot_pose]
+    uint8_t *lm_flags;               // [tot_point]
+    int *pose_hidx;                  // [tot_pose]
+    int *pose_active;                // [tot_pose] scratch
+    int *point_hidx;                 // [tot_point]  (export only)
+    const int *lm_edge_off;          // [tot_point + 1] global edge offsets (CSR by landmark)
+    const double *obs_u, *obs_v, *obs_r;   // [tot_edge] SoA
+    int *edge_pose;                  // [tot_edge] packed word (see above)
+    const int *edge_point;           // [tot_edge] window-local landmark index
+    const int *edge_orig;            // [tot_edge] caller's edge index (window-local)
+    unsigned *covis;                 // [tot_pose] row i: bit j set if S block (i,j), i<=j exists (small path)
+    double *part;                    // per-chunk partial sums
+    double *part2;                   // [n_chunks][2] chi2 / scale partials of the update kernel
+    double *xp;                      // [tot_pose][6] pose step per hessian index (window-local)
+    int *n_running;                  // windows still running in the current pass
+    double *dbg;                     // parity hook: k_solve dumps packed S and b_s of window 0 here (else null)
+    double dbg_lambda;               // parity hook: damping override (< 0: keep the LM state's)
+};
+
+}  // namespace visfs

@@ -1,0 +1,787 @@
+// visfs_ba.cu — C ABI of include/visfs_ba.h: batch upload, on-device structure build, the LM launch
+// sequence, download.  No CPU fallback: every compute entry point needs a CUDA device.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include "../../include/visfs_ba.h"
+#include "ba_kernels.cuh"
+
+using namespace visfs;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        const size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    template <typename T> T *as() const { return static_cast<T *>(p); }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct PinBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        const size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    template <typename T> T *as() const { return static_cast<T *>(p); }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+enum { EV_BUILD = 0, EV_SOLVE = 1, EV_UPDATE = 2, EV_OTHER = 3, EV_CLASSES = 4 };
+
+}  // namespace
+
+struct visfs_ba_handle {
+    int device = 0;
+    bool profile = false;
+    cudaStream_t stream = nullptr;
+    std::string error;
+    int sm_count = 148;
+
+    // uploaded batch (host mirrors)
+    int n_win = 0, n_chunks = 0, tot_pose = 0, tot_point = 0, tot_edge = 0, max_pose = 0, max_iter = 0;
+    bool resident = false, has_run = false, sorted = true;
+    std::vector<WinDesc> win;
+    std::vector<Chunk> chunks;
+    std::vector<LMState> st_host;
+    size_t solve_smem = 0;
+    int grid_lm_x = 1, grid_edge_x = 1;
+
+    // device memory
+    DevBuf d_win, d_st, d_chunks, d_pose, d_point, d_pose_flags, d_lm_flags, d_pose_hidx, d_pose_active, d_point_hidx,
+        d_lm_edge_off, d_obs_u, d_obs_v, d_obs_r, d_edge_pose, d_edge_point, d_edge_orig, d_covis, d_part, d_part2, d_xp,
+        d_n_running;
+    DevBuf d_in_pose, d_in_point, d_in_pfix, d_in_lfix, d_in_obs, d_in_epose, d_in_epoint, d_in_ekind;
+    DevBuf d_out_pose, d_out_point, d_out_level, d_tmp, d_keys, d_keys2, d_perm;
+    PinBuf h_stage, h_out, h_small;
+
+    // timing
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<std::pair<int, int>> ev_used[EV_CLASSES];  // (start, stop) indices
+    size_t ev_next = 0;
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+    visfs_ba_timing timing{};
+
+    Batch batch{};
+
+    int fail(int status, const std::string &msg) { error = msg; return status; }
+    int cuda_fail(cudaError_t e, const char *what) {
+        error = std::string(what) + ": " + cudaGetErrorString(e);
+        return VISFS_BA_ERR_CUDA;
+    }
+};
+
+#define CK(call)                                                     \
+    do {                                                             \
+        cudaError_t e__ = (call);                                    \
+        if (e__ != cudaSuccess) return h->cuda_fail(e__, #call);     \
+    } while (0)
+
+namespace {
+
+int ev_begin(visfs_ba_handle *h, int cls) {
+    if (!h->profile) return -1;
+    if (h->ev_next + 2 > h->ev_pool.size()) {
+        const size_t old = h->ev_pool.size();
+        h->ev_pool.resize(old + 256);
+        for (size_t i = old; i < h->ev_pool.size(); ++i) cudaEventCreate(&h->ev_pool[i]);
+    }
+    const int a = (int)h->ev_next++;
+    const int b = (int)h->ev_next++;
+    cudaEventRecord(h->ev_pool[a], h->stream);
+    h->ev_used[cls].push_back({a, b});
+    return b;
+}
+void ev_end(visfs_ba_handle *h, int b) {
+    if (b >= 0) cudaEventRecord(h->ev_pool[b], h->stream);
+}
+
+int validate(visfs_ba_handle *h, const visfs_ba_problem &p, int idx, bool *sorted, int *max_degree) {
+    char buf[160];
+    auto bad = [&](const char *m) {
+        snprintf(buf, sizeof buf, "problem %d: %s", idx, m);
+        return h->fail(VISFS_BA_ERR_INVALID, buf);
+    };
+    if (p.n_poses < 0 || p.n_points < 0 || p.n_edges < 0) return bad("negative size");
+    if (p.n_poses > kPoseMask) return bad("too many poses");
+    if ((p.n_poses && !p.pose_tq) || (p.n_points && !p.point_xyz)) return bad("null pose_tq / point_xyz");
+    if (p.n_edges && (!p.edge_obs || !p.edge_pose || !p.edge_point)) return bad("null edge arrays");
+    if (!(p.pixel_variance > 0.0)) return bad("pixel_variance must be > 0");
+    if (p.pose_id)
+        for (int i = 1; i < p.n_poses; ++i) if (p.pose_id[i] <= p.pose_id[i - 1]) return bad("pose_id not strictly ascending");
+    if (p.point_id)
+        for (int i = 1; i < p.n_points; ++i) if (p.point_id[i] <= p.point_id[i - 1]) return bad("point_id not strictly ascending");
+    bool srt = true;
+    int run = 0, maxrun = 0;
+    for (int e = 0; e < p.n_edges; ++e) {
+        const int a = p.edge_pose[e], b = p.edge_point[e];
+        if (a < 0 || a >= p.n_poses || b < 0 || b >= p.n_points) return bad("edge index out of range");
+        if (e > 0) {
+            const int pb = p.edge_point[e - 1];
+            if (b < pb || (b == pb && a <= p.edge_pose[e - 1])) srt = false;
+            run = (b == pb) ? run + 1 : 1;
+        } else run = 1;
+        maxrun = std::max(maxrun, run);
+    }
+    *sorted = srt;
+    *max_degree = srt ? maxrun : -1;
+    return VISFS_BA_OK;
+}
+
+Batch make_batch(visfs_ba_handle *h) {
+    Batch b{};
+    b.n_win = h->n_win; b.n_chunks = h->n_chunks;
+    b.tot_pose = h->tot_pose; b.tot_point = h->tot_point; b.tot_edge = h->tot_edge;
+    b.win = h->d_win.as<WinDesc>(); b.st = h->d_st.as<LMState>(); b.chunks = h->d_chunks.as<Chunk>();
+    b.pose = h->d_pose.as<double>(); b.point = h->d_point.as<double>();
+    b.pose_flags = h->d_pose_flags.as<uint8_t>(); b.lm_flags = h->d_lm_flags.as<uint8_t>();
+    b.pose_hidx = h->d_pose_hidx.as<int>(); b.pose_active = h->d_pose_active.as<int>();
+    b.point_hidx = h->d_point_hidx.as<int>(); b.lm_edge_off = h->d_lm_edge_off.as<int>();
+    b.obs_u = h->d_obs_u.as<double>(); b.obs_v = h->d_obs_v.as<double>(); b.obs_r = h->d_obs_r.as<double>();
+    b.edge_pose = h->d_edge_pose.as<int>(); b.edge_point = h->d_edge_point.as<int>();
+    b.edge_orig = h->sorted ? nullptr : h->d_edge_orig.as<int>();
+    b.covis = h->d_covis.as<unsigned>(); b.part = h->d_part.as<double>(); b.part2 = h->d_part2.as<double>();
+    b.xp = h->d_xp.as<double>(); b.n_running = h->d_n_running.as<int>();
+    b.dbg = nullptr; b.dbg_lambda = -1.0;
+    return b;
+}
+
+dim3 grid2(int items, int n_win) {
+    int gx = (items + 255) / 256;
+    gx = std::max(1, std::min(gx, 1024));
+    return dim3((unsigned)gx, (unsigned)n_win);
+}
+
+// ---- upload: validate, pack into pinned staging, H2D, device-side preparation ---------------------
+int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs) {
+    h->resident = false; h->has_run = false;
+    if (n <= 0 || !probs) return h->fail(VISFS_BA_ERR_INVALID, "empty batch");
+    if (n > 65535) return h->fail(VISFS_BA_ERR_INVALID, "at most 65535 windows per batch");
+    CK(cudaSetDevice(h->device));
+    h->win.assign(n, WinDesc{});
+    long long tp = 0, tl = 0, te = 0;
+    int max_pose = 0, max_point = 0, max_edge = 0, max_iter = 0;
+    bool all_sorted = true;
+    for (int w = 0; w < n; ++w) {
+        const visfs_ba_problem &p = probs[w];
+        bool srt; int deg;
+        const int st = validate(h, p, w, &srt, &deg);
+        if (st != VISFS_BA_OK) return st;
+        if (p.flags & VISFS_BA_FLAG_PARTITIONED) return h->fail(VISFS_BA_ERR_UNSUPPORTED, "partitioned global BA: not in this build yet");
+        if (p.n_poses > kMaxSmallPoses) return h->fail(VISFS_BA_ERR_UNSUPPORTED, "windows with more than 32 poses: not in this build yet");
+        if (deg > kTileEdges) return h->fail(VISFS_BA_ERR_UNSUPPORTED, "landmark observed by more than 160 poses");
+        all_sorted = all_sorted && srt;
+        WinDesc &d = h->win[w];
+        d.pose_off = (int)tp; d.n_pose = p.n_poses; d.point_off = (int)tl; d.n_point = p.n_points;
+        d.edge_off = (int)te; d.n_edge = p.n_edges;
+        const bool single = (p.flags & VISFS_BA_FLAG_SINGLE_PASS) != 0;
+        d.max_iter = single ? p.iterations : p.iterations / 2;
+        if (d.max_iter < 0) d.max_iter = 0;
+        d.solver = p.solver; d.trust = p.trust_region; d.flags = p.flags; d.large = 0;
+        d.fx = p.fx; d.fy = p.fy; d.cx = p.cx; d.cy = p.cy; d.bf = p.bf;
+        d.inv_pv = 1.0 / p.pixel_variance; d.delta = p.huber_delta;
+        tp += p.n_poses; tl += p.n_points; te += p.n_edges;
+        max_pose = std::max(max_pose, p.n_poses); max_point = std::max(max_point, p.n_points);
+        max_edge = std::max(max_edge, p.n_edges); max_iter = std::max(max_iter, d.max_iter);
+        if (tp > 0x3fffffff || tl > 0x3fffffff || te > 0x3fffffff) return h->fail(VISFS_BA_ERR_INVALID, "batch too large");
+    }
+    h->n_win = n; h->tot_pose = (int)tp; h->tot_point = (int)tl; h->tot_edge = (int)te;
+    h->max_pose = max_pose; h->max_iter = max_iter; h->sorted = all_sorted;
+    h->grid_lm_x = std::max(1, std::min((max_point + 255) / 256, 1024));
+    h->grid_edge_x = std::max(1, std::min((max_edge + 255) / 256, 1024));
+
+    // chunks: about 2 CTAs per SM over the whole batch, never across windows
+    const long long target = 2LL * h->sm_count;
+    int lm_per_chunk = (int)std::max<long long>(kTileLm / 2, (tl + target - 1) / target);
+    h->chunks.clear();
+    long long part_total = 0;
+    for (int w = 0; w < n; ++w) {
+        WinDesc &d = h->win[w];
+        d.chunk_off = (int)h->chunks.size();
+        for (int l0 = 0; l0 < d.n_point; l0 += lm_per_chunk)
+            h->chunks.push_back(Chunk{w, d.point_off + l0, d.point_off + std::min(d.n_point, l0 + lm_per_chunk)});
+        d.n_chunks = (int)h->chunks.size() - d.chunk_off;
+        const int Fm = std::min(d.n_pose, kMaxSmallPoses);
+        d.part_stride = std::max(Fm * (Fm - 1) / 2 * 36 + Fm * kHStride, 8);
+        d.part_off = part_total;
+        part_total += (long long)d.part_stride * std::max(d.n_chunks, 1);
+    }
+    h->n_chunks = (int)h->chunks.size();
+    {
+        const int nmax = 6 * std::min(max_pose, kMaxSmallPoses);
+        h->solve_smem = sizeof(double) * ((size_t)nmax * (nmax + 1) / 2 + 7 * (size_t)nmax + 36 * (size_t)(nmax / 6) + 8);
+    }
+
+    // device buffers
+    const size_t P = (size_t)std::max<long long>(tp, 1), L = (size_t)std::max<long long>(tl, 1), E = (size_t)std::max<long long>(te, 1);
+    CK(h->d_win.reserve(sizeof(WinDesc) * n)); CK(h->d_st.reserve(sizeof(LMState) * n));
+    CK(h->d_chunks.reserve(sizeof(Chunk) * std::max(h->n_chunks, 1)));
+    CK(h->d_pose.reserve(sizeof(double) * 2 * P * kPoseStride)); CK(h->d_point.reserve(sizeof(double) * 2 * L * 3));
+    CK(h->d_pose_flags.reserve(P)); CK(h->d_lm_flags.reserve(L));
+    CK(h->d_pose_hidx.reserve(sizeof(int) * P)); CK(h->d_pose_active.reserve(sizeof(int) * P));
+    CK(h->d_point_hidx.reserve(sizeof(int) * L)); CK(h->d_lm_edge_off.reserve(sizeof(int) * (L + 1)));
+    CK(h->d_obs_u.reserve(sizeof(double) * E)); CK(h->d_obs_v.reserve(sizeof(double) * E)); CK(h->d_obs_r.reserve(sizeof(double) * E));
+    CK(h->d_edge_pose.reserve(sizeof(int) * E)); CK(h->d_edge_point.reserve(sizeof(int) * E));
+    CK(h->d_covis.reserve(sizeof(unsigned) * P));
+    CK(h->d_part.reserve(sizeof(double) * (size_t)std::max<long long>(part_total, 8)));
+    CK(h->d_part2.reserve(sizeof(double) * 2 * std::max(h->n_chunks, 1)));
+    CK(h->d_xp.reserve(sizeof(double) * 6 * P)); CK(h->d_n_running.reserve(sizeof(int) * 4));
+    CK(h->d_in_pose.reserve(sizeof(double) * 7 * P)); CK(h->d_in_point.reserve(sizeof(double) * 3 * L));
+    CK(h->d_in_pfix.reserve(P)); CK(h->d_in_lfix.reserve(L));
+    CK(h->d_in_obs.reserve(sizeof(double) * 3 * E)); CK(h->d_in_epose.reserve(sizeof(int) * E));
+    CK(h->d_in_epoint.reserve(sizeof(int) * E)); CK(h->d_in_ekind.reserve(E));
+    CK(h->d_out_pose.reserve(sizeof(double) * 7 * P)); CK(h->d_out_point.reserve(sizeof(double) * 3 * L));
+    CK(h->d_out_level.reserve(E));
+
+    // pack into one pinned staging buffer (layout: pose | point | obs | epose | epoint | pfix | lfix | ekind)
+    const size_t o_pose = 0, o_point = o_pose + sizeof(double) * 7 * P, o_obs = o_point + sizeof(double) * 3 * L,
+                 o_epose = o_obs + sizeof(double) * 3 * E, o_epoint = o_epose + sizeof(int) * E,
+                 o_pfix = o_epoint + sizeof(int) * E, o_lfix = o_pfix + P, o_ekind = o_lfix + L, o_end = o_ekind + E;
+    CK(h->h_stage.reserve(o_end));
+    char *sg = h->h_stage.as<char>();
+    for (int w = 0; w < n; ++w) {
+        const visfs_ba_problem &p = probs[w];
+        const WinDesc &d = h->win[w];
+        if (p.n_poses) {
+            memcpy(sg + o_pose + sizeof(double) * 7 * d.pose_off, p.pose_tq, sizeof(double) * 7 * p.n_poses);
+            if (p.pose_fixed) memcpy(sg + o_pfix + d.pose_off, p.pose_fixed, p.n_poses); else memset(sg + o_pfix + d.pose_off, 0, p.n_poses);
+        }
+        if (p.n_points) {
+            memcpy(sg + o_point + sizeof(double) * 3 * d.point_off, p.point_xyz, sizeof(double) * 3 * p.n_points);
+            if (p.point_fixed) memcpy(sg + o_lfix + d.point_off, p.point_fixed, p.n_points); else memset(sg + o_lfix + d.point_off, 0, p.n_points);
+        }
+        if (p.n_edges) {
+            memcpy(sg + o_obs + sizeof(double) * 3 * d.edge_off, p.edge_obs, sizeof(double) * 3 * p.n_edges);
+            memcpy(sg + o_epose + sizeof(int) * d.edge_off, p.edge_pose, sizeof(int) * p.n_edges);
+            memcpy(sg + o_epoint + sizeof(int) * d.edge_off, p.edge_point, sizeof(int) * p.n_edges);
+            if (p.edge_kind) memcpy(sg + o_ekind + d.edge_off, p.edge_kind, p.n_edges); else memset(sg + o_ekind + d.edge_off, 0, p.n_edges);
+        }
+    }
+    cudaStream_t s = h->stream;
+    CK(cudaMemcpyAsync(h->d_in_pose.p, sg + o_pose, sizeof(double) * 7 * P, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->d_in_point.p, sg + o_point, sizeof(double) * 3 * L, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->d_in_obs.p, sg + o_obs, sizeof(double) * 3 * E, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->d_in_epose.p, sg + o_epose, sizeof(int) * E, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->d_in_epoint.p, sg + o_epoint, sizeof(int) * E, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->d_in_pfix.p, sg + o_pfix, P, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->d_in_lfix.p, sg + o_lfix, L, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->d_in_ekind.p, sg + o_ekind, E, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->d_win.p, h->win.data(), sizeof(WinDesc) * n, cudaMemcpyHostToDevice, s));
+    if (h->n_chunks) CK(cudaMemcpyAsync(h->d_chunks.p, h->chunks.data(), sizeof(Chunk) * h->n_chunks, cudaMemcpyHostToDevice, s));
+
+    // device-side preparation: (optional) stable sort by (window, point, pose), SoA split, CSR offsets
+    const int *perm = nullptr;
+    if (!all_sorted && te > 0) {
+        if (max_point >= (1 << 24)) return h->fail(VISFS_BA_ERR_UNSUPPORTED, "unsorted edge lists need fewer than 2^24 points per window");
+        CK(h->d_keys.reserve(sizeof(unsigned long long) * E)); CK(h->d_keys2.reserve(sizeof(unsigned long long) * E));
+        CK(h->d_perm.reserve(sizeof(int) * E)); CK(h->d_edge_orig.reserve(sizeof(int) * E));
+        // keys / identity are produced on the host side of the staging copy (cheap, and only on this path)
+        std::vector<unsigned long long> keys(E);
+        std::vector<int> ident(E);
+        for (int w = 0; w < n; ++w) {
+            const visfs_ba_problem &p = probs[w];
+            const WinDesc &d = h->win[w];
+            for (int e = 0; e < p.n_edges; ++e) {
+                keys[d.edge_off + e] = ((unsigned long long)w << 48) | ((unsigned long long)p.edge_point[e] << 24) | (unsigned long long)p.edge_pose[e];
+                ident[d.edge_off + e] = e;
+            }
+        }
+        CK(cudaMemcpyAsync(h->d_keys.p, keys.data(), sizeof(unsigned long long) * E, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(h->d_perm.p, ident.data(), sizeof(int) * E, cudaMemcpyHostToDevice, s));
+        size_t tmp_bytes = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, h->d_keys.as<unsigned long long>(), h->d_keys2.as<unsigned long long>(),
+                                        h->d_perm.as<int>(), h->d_edge_orig.as<int>(), (int)te, 0, 64, s);
+        CK(h->d_tmp.reserve(tmp_bytes));
+        CK(cub::DeviceRadixSort::SortPairs(h->d_tmp.p, tmp_bytes, h->d_keys.as<unsigned long long>(), h->d_keys2.as<unsigned long long>(),
+                                           h->d_perm.as<int>(), h->d_edge_orig.as<int>(), (int)te, 0, 64, s));
+        CK(cudaStreamSynchronize(s));  // host vectors above go out of scope
+        perm = h->d_edge_orig.as<int>();
+    }
+    h->batch = make_batch(h);
+    Batch &B = h->batch;
+    if (te > 0) {
+        k_prepare_edges<<<grid2(max_edge, n), 256, 0, s>>>(B, h->d_in_obs.as<double>(), h->d_in_epose.as<int>(), h->d_in_epoint.as<int>(),
+                                                          h->d_in_ekind.as<uint8_t>(), perm, h->d_obs_u.as<double>(),
+                                                          h->d_obs_v.as<double>(), h->d_obs_r.as<double>(), h->d_edge_point.as<int>());
+    }
+    k_lm_offsets<<<grid2(max_point + 1, n), 256, 0, s>>>(B, h->d_lm_edge_off.as<int>());
+    CK(cudaGetLastError());
+    h->resident = true;
+    return VISFS_BA_OK;
+}
+
+int reset_state(visfs_ba_handle *h) {
+    Batch &B = h->batch;
+    const int items = std::max(std::max(h->tot_pose, h->tot_point * 3), std::max(h->tot_edge, h->n_win));
+    const int gx = std::max(1, std::min((items + 255) / 256, 4096));
+    k_reset<<<gx, 256, 0, h->stream>>>(B, h->d_in_pose.as<double>(), h->d_in_point.as<double>(), h->d_in_pfix.as<uint8_t>(),
+                                       h->d_in_lfix.as<uint8_t>());
+    CK(cudaMemsetAsync(h->d_n_running.p, 0, sizeof(int) * 4, h->stream));
+    CK(cudaGetLastError());
+    return VISFS_BA_OK;
+}
+
+int run_structure(visfs_ba_handle *h) {
+    Batch &B = h->batch;
+    cudaStream_t s = h->stream;
+    CK(cudaMemsetAsync(h->d_pose_active.p, 0, sizeof(int) * std::max(h->tot_pose, 1), s));
+    const dim3 glm((unsigned)h->grid_lm_x, (unsigned)h->n_win);
+    const int gw = (h->n_win + 127) / 128;
+    k_struct_lm<<<glm, 256, 0, s>>>(B);
+    k_struct_pose<<<gw, 128, 0, s>>>(B);
+    k_struct_count<<<glm, 256, 0, s>>>(B);
+    k_struct_finish<<<gw, 128, 0, s>>>(B);
+    CK(cudaGetLastError());
+    return VISFS_BA_OK;
+}
+
+template <int MODE>
+int launch_build(visfs_ba_handle *h) {
+    if (h->n_chunks == 0) return VISFS_BA_OK;
+    const size_t smem = sizeof(BuildSmem);
+    if (h->max_pose <= 23) k_build<MODE, 1><<<h->n_chunks, kThreads, smem, h->stream>>>(h->batch);
+    else k_build<MODE, 2><<<h->n_chunks, kThreads, smem, h->stream>>>(h->batch);
+    return VISFS_BA_OK;
+}
+
+int enqueue_body(visfs_ba_handle *h) {
+    int ev = ev_begin(h, EV_BUILD);
+    launch_build<MODE_BUILD>(h);
+    ev_end(h, ev);
+    ev = ev_begin(h, EV_SOLVE);
+    k_solve<<<h->n_win, kSolveThreads, h->solve_smem, h->stream>>>(h->batch);
+    ev_end(h, ev);
+    ev = ev_begin(h, EV_UPDATE);
+    if (h->n_chunks) k_update<<<h->n_chunks, kThreads, sizeof(UpdateSmem), h->stream>>>(h->batch);
+    ev_end(h, ev);
+    ev = ev_begin(h, EV_OTHER);
+    k_control<<<h->n_win, 32, 0, h->stream>>>(h->batch);
+    ev_end(h, ev);
+    return VISFS_BA_OK;
+}
+
+int run_pass(visfs_ba_handle *h, int pass) {
+    cudaStream_t s = h->stream;
+    Batch &B = h->batch;
+    const int gw = (h->n_win + 127) / 128;
+    int ev = ev_begin(h, EV_OTHER);
+    k_begin_pass<<<gw, 128, 0, s>>>(B, pass);
+    int st = run_structure(h);
+    if (st) return st;
+    const int items = std::max(h->max_pose * kPoseStride, 1);
+    (void)items;
+    k_sync_buffers<<<dim3((unsigned)h->grid_lm_x, (unsigned)h->n_win), 256, 0, s>>>(B);
+    launch_build<MODE_INIT>(h);
+    k_control_init<<<h->n_win, 32, 0, s>>>(B);
+    ev_end(h, ev);
+    CK(cudaGetLastError());
+    int *running = h->h_small.as<int>();
+    int bodies = 0;
+    const int cap = 10 * std::max(h->max_iter, 1) + 2;
+    int burst = h->max_iter;
+    while (burst > 0 && bodies < cap) {
+        for (int k = 0; k < burst; ++k) enqueue_body(h);
+        bodies += burst;
+        CK(cudaMemcpyAsync(running, h->d_n_running.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (*running <= 0) break;
+        burst = 2;  // some window rejected a step: keep going two trials at a time
+    }
+    ev = ev_begin(h, EV_OTHER);
+    k_end_pass<<<gw, 128, 0, s>>>(B, pass);
+    if (pass == 0 && h->tot_edge > 0) k_cull<<<dim3((unsigned)h->grid_edge_x, (unsigned)h->n_win), 256, 0, s>>>(B);
+    ev_end(h, ev);
+    CK(cudaGetLastError());
+    return VISFS_BA_OK;
+}
+
+int run_resident(visfs_ba_handle *h) {
+    if (!h->resident) return h->fail(VISFS_BA_ERR_INVALID, "no batch uploaded");
+    CK(cudaSetDevice(h->device));
+    CK(h->h_small.reserve(64));
+    h->ev_next = 0;
+    for (auto &v : h->ev_used) v.clear();
+    CK(cudaEventRecord(h->ev_t0, h->stream));
+    int st = reset_state(h);
+    if (st) return st;
+    for (int pass = 0; pass < 2; ++pass) {
+        st = run_pass(h, pass);
+        if (st) return st;
+    }
+    CK(cudaEventRecord(h->ev_t1, h->stream));
+    // state back to the host (small), also synchronises the run
+    h->st_host.resize(h->n_win);
+    CK(cudaMemcpyAsync(h->st_host.data(), h->d_st.p, sizeof(LMState) * h->n_win, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->has_run = true;
+
+    visfs_ba_timing &t = h->timing;
+    t = visfs_ba_timing{};
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1);
+    t.total_ms = ms;
+    double *cls_ms[EV_CLASSES] = {&t.build_ms, &t.solve_ms, &t.update_ms, &t.other_ms};
+    int64_t *cls_n[EV_CLASSES] = {&t.build_launches, &t.solve_launches, &t.update_launches, &t.other_launches};
+    for (int c = 0; c < EV_CLASSES; ++c)
+        for (auto &ab : h->ev_used[c]) {
+            cudaEventElapsedTime(&ms, h->ev_pool[ab.first], h->ev_pool[ab.second]);
+            *cls_ms[c] += ms;
+            *cls_n[c] += 1;
+        }
+    for (int w = 0; w < h->n_win; ++w) {
+        const LMState &s = h->st_host[w];
+        const WinDesc &d = h->win[w];
+        const int64_t trials = (int64_t)s.trials_run[0] + s.trials_run[1];
+        t.lm_iterations += (int64_t)s.iterations_run[0] + s.iterations_run[1];
+        t.lm_trials += trials;
+        t.edge_trials += trials * d.n_edge;
+        // build reads every edge record (32 B), every landmark (24 B) and every pose (56 B) once;
+        // update re-reads them and writes every landmark (24 B)
+        t.alg_bytes_build += trials * (32LL * d.n_edge + 24LL * d.n_point + 56LL * d.n_pose);
+        t.alg_bytes_update += trials * (32LL * d.n_edge + 48LL * d.n_point + 56LL * d.n_pose);
+    }
+    return VISFS_BA_OK;
+}
+
+int download(visfs_ba_handle *h, int n, visfs_ba_result *res) {
+    if (!h->resident || !h->has_run) return h->fail(VISFS_BA_ERR_INVALID, "nothing to download");
+    if (n != h->n_win || !res) return h->fail(VISFS_BA_ERR_INVALID, "result count does not match the uploaded batch");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    const int items = std::max(h->max_pose * 7, std::max(h->grid_lm_x * 256 * 3, h->grid_edge_x * 256));
+    k_export<<<grid2(items, h->n_win), 256, 0, s>>>(h->batch, h->d_out_pose.as<double>(), h->d_out_point.as<double>(),
+                                                   h->d_out_level.as<uint8_t>());
+    CK(cudaGetLastError());
+    const size_t P = (size_t)h->tot_pose, L = (size_t)h->tot_point, E = (size_t)h->tot_edge;
+    const size_t o_pose = 0, o_point = sizeof(double) * 7 * P, o_level = o_point + sizeof(double) * 3 * L, o_end = o_level + E;
+    CK(h->h_out.reserve(o_end + 8));
+    char *ho = h->h_out.as<char>();
+    if (P) CK(cudaMemcpyAsync(ho + o_pose, h->d_out_pose.p, sizeof(double) * 7 * P, cudaMemcpyDeviceToHost, s));
+    if (L) CK(cudaMemcpyAsync(ho + o_point, h->d_out_point.p, sizeof(double) * 3 * L, cudaMemcpyDeviceToHost, s));
+    if (E) CK(cudaMemcpyAsync(ho + o_level, h->d_out_level.p, E, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    for (int w = 0; w < n; ++w) {
+        const WinDesc &d = h->win[w];
+        const LMState &st = h->st_host[w];
+        visfs_ba_result &r = res[w];
+        if (r.pose_tq && d.n_pose) memcpy(r.pose_tq, ho + o_pose + sizeof(double) * 7 * d.pose_off, sizeof(double) * 7 * d.n_pose);
+        if (r.point_xyz && d.n_point) memcpy(r.point_xyz, ho + o_point + sizeof(double) * 3 * d.point_off, sizeof(double) * 3 * d.n_point);
+        if (r.edge_level && d.n_edge) memcpy(r.edge_level, ho + o_level + d.edge_off, d.n_edge);
+        r.status = st.status; r.n_outliers = st.n_outliers;
+        for (int k = 0; k < 2; ++k) {
+            r.iterations_run[k] = st.iterations_run[k]; r.trials_run[k] = st.trials_run[k]; r.stop_reason[k] = st.stop[k];
+            r.n_free_poses[k] = st.nF[k]; r.n_free_points[k] = st.nNL[k]; r.lambda_final[k] = st.lambda_final[k];
+        }
+        if (st.stop[1] == VISFS_BA_STOP_NOT_RUN) { r.n_free_poses[1] = r.n_free_points[1] = 0; r.lambda_final[1] = 0; }
+        r.chi2_initial = st.chi_initial; r.chi2_pass1 = st.chi_pass[0]; r.chi2_final = st.chi_pass[1];
+        r.chi2_last_trial = st.chi_last_trial;
+    }
+    return VISFS_BA_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+int visfs_ba_abi_version(void) { return VISFS_BA_ABI_VERSION; }
+
+const char *visfs_ba_last_error(const visfs_ba_handle *h) { return h ? h->error.c_str() : g_create_error.c_str(); }
+
+int visfs_ba_create(const visfs_ba_config *cfg, visfs_ba_handle **out) {
+    if (!out) return VISFS_BA_ERR_INVALID;
+    *out = nullptr;
+    if (cfg && cfg->abi_version != VISFS_BA_ABI_VERSION) { g_create_error = "ABI version mismatch"; return VISFS_BA_ERR_INVALID; }
+    const int dev = cfg ? cfg->device : 0;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_create_error = std::string("no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e);
+        return VISFS_BA_ERR_CUDA;
+    }
+    if (dev < 0 || dev >= count) { g_create_error = "device ordinal out of range"; return VISFS_BA_ERR_INVALID; }
+    if ((e = cudaSetDevice(dev)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); return VISFS_BA_ERR_CUDA; }
+    visfs_ba_handle *h = new visfs_ba_handle();
+    h->device = dev;
+    h->profile = cfg && cfg->profile_kernels != 0;
+    cudaDeviceProp prop{};
+    cudaGetDeviceProperties(&prop, dev);
+    h->sm_count = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
+    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreate(&h->ev_t0)) != cudaSuccess || (e = cudaEventCreate(&h->ev_t1)) != cudaSuccess) {
+        g_create_error = cudaGetErrorString(e);
+        delete h;
+        return VISFS_BA_ERR_CUDA;
+    }
+    const int smem_build = (int)sizeof(BuildSmem), smem_update = (int)sizeof(UpdateSmem);
+    cudaFuncSetAttribute(k_build<MODE_INIT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_build);
+    cudaFuncSetAttribute(k_build<MODE_BUILD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_build);
+    cudaFuncSetAttribute(k_build<MODE_INIT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_build);
+    cudaFuncSetAttribute(k_build<MODE_BUILD, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_build);
+    cudaFuncSetAttribute(k_update, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_update);
+    e = cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) {
+        g_create_error = std::string("kernel image not usable on this device (built for sm_100a): ") + cudaGetErrorString(e);
+        cudaStreamDestroy(h->stream);
+        delete h;
+        return VISFS_BA_ERR_CUDA;
+    }
+    *out = h;
+    return VISFS_BA_OK;
+}
+
+void visfs_ba_destroy(visfs_ba_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    DevBuf *bufs[] = {&h->d_win, &h->d_st, &h->d_chunks, &h->d_pose, &h->d_point, &h->d_pose_flags, &h->d_lm_flags, &h->d_pose_hidx,
+                      &h->d_pose_active, &h->d_point_hidx, &h->d_lm_edge_off, &h->d_obs_u, &h->d_obs_v, &h->d_obs_r, &h->d_edge_pose,
+                      &h->d_edge_point, &h->d_edge_orig, &h->d_covis, &h->d_part, &h->d_part2, &h->d_xp, &h->d_n_running,
+                      &h->d_in_pose, &h->d_in_point, &h->d_in_pfix, &h->d_in_lfix, &h->d_in_obs, &h->d_in_epose, &h->d_in_epoint,
+                      &h->d_in_ekind, &h->d_out_pose, &h->d_out_point, &h->d_out_level, &h->d_tmp, &h->d_keys, &h->d_keys2, &h->d_perm};
+    for (DevBuf *b : bufs) b->release();
+    h->h_stage.release(); h->h_out.release(); h->h_small.release();
+    for (cudaEvent_t ev : h->ev_pool) cudaEventDestroy(ev);
+    if (h->ev_t0) cudaEventDestroy(h->ev_t0);
+    if (h->ev_t1) cudaEventDestroy(h->ev_t1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int visfs_ba_upload(visfs_ba_handle *h, int32_t n, const visfs_ba_problem *problems) {
+    if (!h) return VISFS_BA_ERR_INVALID;
+    return upload(h, n, problems);
+}
+
+int visfs_ba_run_resident(visfs_ba_handle *h) {
+    if (!h) return VISFS_BA_ERR_INVALID;
+    return run_resident(h);
+}
+
+int visfs_ba_download(visfs_ba_handle *h, int32_t n, visfs_ba_result *results) {
+    if (!h) return VISFS_BA_ERR_INVALID;
+    return download(h, n, results);
+}
+
+int visfs_ba_get_timing(const visfs_ba_handle *h, visfs_ba_timing *out) {
+    if (!h || !out) return VISFS_BA_ERR_INVALID;
+    *out = h->timing;
+    return VISFS_BA_OK;
+}
+
+int visfs_ba_solve_batch(visfs_ba_handle *h, int32_t n, const visfs_ba_problem *problems, visfs_ba_result *results) {
+    if (!h) return VISFS_BA_ERR_INVALID;
+    int st = upload(h, n, problems);
+    if (st) return st;
+    st = run_resident(h);
+    if (st) return st;
+    return download(h, n, results);
+}
+
+int visfs_ba_solve(visfs_ba_handle *h, const visfs_ba_problem *problem, visfs_ba_result *result) {
+    if (!h || !problem || !result) return VISFS_BA_ERR_INVALID;
+    const int st = visfs_ba_solve_batch(h, 1, problem, result);
+    if (st) return st;
+    return result->status;
+}
+
+int visfs_ba_linearize(visfs_ba_handle *h, const visfs_ba_problem *problem, visfs_ba_linearization *out) {
+    if (!h || !problem || !out) return VISFS_BA_ERR_INVALID;
+    int st = upload(h, 1, problem);
+    if (st) return st;
+    st = reset_state(h);
+    if (st) return st;
+    const size_t E = (size_t)std::max(h->tot_edge, 1);
+    CK(h->d_tmp.reserve(sizeof(double) * 33 * E));
+    double *base = h->d_tmp.as<double>();
+    double *d_err = base, *d_chi = base + 3 * E, *d_rho = base + 4 * E, *d_w = base + 5 * E, *d_jl = base + 6 * E, *d_jp = base + 15 * E;
+    k_linearize_debug<<<grid2(h->tot_edge, 1), 256, 0, h->stream>>>(h->batch, d_err, d_chi, d_rho, d_w, d_jl, d_jp);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    const size_t n = (size_t)h->tot_edge;
+    if (out->error) CK(cudaMemcpy(out->error, d_err, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost));
+    if (out->chi2) CK(cudaMemcpy(out->chi2, d_chi, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    if (out->rho) CK(cudaMemcpy(out->rho, d_rho, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    if (out->weight) CK(cudaMemcpy(out->weight, d_w, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    if (out->J_point) CK(cudaMemcpy(out->J_point, d_jl, sizeof(double) * 9 * n, cudaMemcpyDeviceToHost));
+    if (out->J_pose) CK(cudaMemcpy(out->J_pose, d_jp, sizeof(double) * 18 * n, cudaMemcpyDeviceToHost));
+    return VISFS_BA_OK;
+}
+
+int visfs_ba_structure_build(visfs_ba_handle *h, const visfs_ba_problem *problem, visfs_ba_structure *out) {
+    if (!h || !problem || !out) return VISFS_BA_ERR_INVALID;
+    int st = upload(h, 1, problem);
+    if (st) return st;
+    st = reset_state(h);
+    if (st) return st;
+    cudaStream_t s = h->stream;
+    const size_t P = (size_t)std::max(h->tot_pose, 1), L = (size_t)std::max(h->tot_point, 1), E = (size_t)std::max(h->tot_edge, 1);
+    if (out->edge_level && h->tot_edge) {
+        CK(cudaMemcpyAsync(h->d_out_level.p, out->edge_level, h->tot_edge, cudaMemcpyHostToDevice, s));
+        k_mark_levels<<<grid2(h->tot_edge, 1), 256, 0, s>>>(h->batch, h->d_out_level.as<uint8_t>());
+    }
+    k_begin_pass<<<1, 128, 0, s>>>(h->batch, 0);
+    st = run_structure(h);
+    if (st) return st;
+    // landmark hessian indices: exclusive scan of the in-Hessian flags
+    const int cap = std::max(out->schur_capacity, 0);
+    const size_t ints = L /*flags*/ + L /*scan*/ + L /*hidx*/ + 2 * E /*hpl*/ + 2 * (size_t)std::max(cap, 1) + 8;
+    DevBuf scratch, cubtmp;
+    CK(scratch.reserve(sizeof(int) * ints + E + 64));
+    int *d_flag = scratch.as<int>(), *d_scan = d_flag + L, *d_hidx = d_scan + L, *d_row = d_hidx + L, *d_col = d_row + E,
+        *d_srow = d_col + E, *d_scol = d_srow + std::max(cap, 1), *d_cnt = d_scol + std::max(cap, 1);
+    uint8_t *d_act = reinterpret_cast<uint8_t *>(d_cnt + 8);
+    std::vector<uint8_t> lmf(L);
+    CK(cudaMemcpyAsync(lmf.data(), h->d_lm_flags.p, h->tot_point, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    std::vector<int> flags(L, 0);
+    for (int l = 0; l < h->tot_point; ++l) flags[l] = (lmf[l] & kInHessian) ? 1 : 0;
+    CK(cudaMemcpyAsync(d_flag, flags.data(), sizeof(int) * L, cudaMemcpyHostToDevice, s));
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_flag, d_scan, (int)L, s);
+    CK(cubtmp.reserve(tmp_bytes));
+    CK(cub::DeviceScan::ExclusiveSum(cubtmp.p, tmp_bytes, d_flag, d_scan, (int)L, s));
+    k_structure_export<<<grid2(std::max(h->tot_point, h->tot_edge), 1), 256, 0, s>>>(h->batch, d_scan, d_hidx, d_act, d_row, d_col);
+    k_schur_pattern<<<1, 32, 0, s>>>(h->batch, 0, d_srow, d_scol, cap, d_cnt);
+    CK(cudaGetLastError());
+    std::vector<LMState> sth(1);
+    CK(cudaMemcpyAsync(sth.data(), h->d_st.p, sizeof(LMState), cudaMemcpyDeviceToHost, s));
+    int cnt = 0;
+    CK(cudaMemcpyAsync(&cnt, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (out->pose_hidx && h->tot_pose) CK(cudaMemcpyAsync(out->pose_hidx, h->d_pose_hidx.p, sizeof(int) * h->tot_pose, cudaMemcpyDeviceToHost, s));
+    if (out->point_hidx && h->tot_point) CK(cudaMemcpyAsync(out->point_hidx, d_hidx, sizeof(int) * h->tot_point, cudaMemcpyDeviceToHost, s));
+    if (out->edge_active && h->tot_edge) CK(cudaMemcpyAsync(out->edge_active, d_act, h->tot_edge, cudaMemcpyDeviceToHost, s));
+    if (out->hpl_row && h->tot_edge) CK(cudaMemcpyAsync(out->hpl_row, d_row, sizeof(int) * h->tot_edge, cudaMemcpyDeviceToHost, s));
+    if (out->hpl_col && h->tot_edge) CK(cudaMemcpyAsync(out->hpl_col, d_col, sizeof(int) * h->tot_edge, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const int ncopy = std::min(cnt, cap);
+    if (out->schur_rows && ncopy) CK(cudaMemcpy(out->schur_rows, d_srow, sizeof(int) * ncopy, cudaMemcpyDeviceToHost));
+    if (out->schur_cols && ncopy) CK(cudaMemcpy(out->schur_cols, d_scol, sizeof(int) * ncopy, cudaMemcpyDeviceToHost));
+    out->n_schur_blocks = cnt;
+    out->n_free_poses = sth[0].F;
+    out->n_free_points = sth[0].NL;
+    int nact = 0, nhpl = 0;
+    if (h->tot_edge) {
+        std::vector<uint8_t> act(E);
+        std::vector<int> row(E);
+        CK(cudaMemcpy(act.data(), d_act, h->tot_edge, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(row.data(), d_row, sizeof(int) * h->tot_edge, cudaMemcpyDeviceToHost));
+        for (int e = 0; e < h->tot_edge; ++e) { nact += act[e]; nhpl += row[e] >= 0; }
+    }
+    out->n_active_edges = nact;
+    out->n_hpl_blocks = nhpl;
+    scratch.release(); cubtmp.release();
+    (void)P;
+    return VISFS_BA_OK;
+}
+
+int visfs_ba_debug_trial(visfs_ba_handle *h, const visfs_ba_problem *problem, double lambda, double *S_dense, double *b_s,
+                         double *x_pose, double *trial_points, int32_t *n_out, double *chi2_out, double *lambda_out,
+                         double *trial_chi2_out) {
+    if (!h || !problem) return VISFS_BA_ERR_INVALID;
+    int st = upload(h, 1, problem);
+    if (st) return st;
+    st = reset_state(h);
+    if (st) return st;
+    cudaStream_t s = h->stream;
+    k_begin_pass<<<1, 128, 0, s>>>(h->batch, 0);
+    st = run_structure(h);
+    if (st) return st;
+    k_sync_buffers<<<dim3((unsigned)h->grid_lm_x, 1u), 256, 0, s>>>(h->batch);
+    launch_build<MODE_INIT>(h);
+    k_control_init<<<1, 32, 0, s>>>(h->batch);
+    LMState before;
+    CK(cudaMemcpyAsync(&before, h->d_st.p, sizeof(LMState), cudaMemcpyDeviceToHost, s));
+    const int nmax = 6 * h->tot_pose;
+    const size_t ntri_max = (size_t)nmax * (nmax + 1) / 2;
+    DevBuf dbg;
+    CK(dbg.reserve(sizeof(double) * (ntri_max + nmax + 8)));
+    CK(cudaMemsetAsync(dbg.p, 0, sizeof(double) * (ntri_max + nmax + 8), s));
+    Batch saved = h->batch;
+    h->batch.dbg = dbg.as<double>();
+    h->batch.dbg_lambda = lambda;
+    enqueue_body(h);
+    h->batch = saved;
+    CK(cudaGetLastError());
+    LMState after;
+    CK(cudaMemcpyAsync(&after, h->d_st.p, sizeof(LMState), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const int n = 6 * after.F;
+    const size_t ntri = (size_t)n * (n + 1) / 2;
+    std::vector<double> packed(ntri + n + 1);
+    if (ntri + n) CK(cudaMemcpy(packed.data(), dbg.p, sizeof(double) * (ntri + n), cudaMemcpyDeviceToHost));
+    if (n_out) *n_out = n;
+    if (S_dense)
+        for (int r = 0; r < n; ++r)
+            for (int c = 0; c <= r; ++c) {
+                const double v = packed[(size_t)r * (r + 1) / 2 + c];
+                S_dense[(size_t)r * n + c] = v;
+                S_dense[(size_t)c * n + r] = v;
+            }
+    if (b_s) for (int i = 0; i < n; ++i) b_s[i] = packed[ntri + i];
+    if (x_pose && n) CK(cudaMemcpy(x_pose, h->d_xp.p, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    const int trial_buf = 1 - before.cur;  // the trial was written into the buffer that was not accepted before the body
+    if (trial_points && h->tot_point)
+        CK(cudaMemcpy(trial_points, h->d_point.as<double>() + (size_t)trial_buf * h->tot_point * 3, sizeof(double) * 3 * h->tot_point,
+                      cudaMemcpyDeviceToHost));
+    if (chi2_out) *chi2_out = before.chi_initial;
+    if (lambda_out) *lambda_out = (lambda >= 0.0) ? lambda : before.lambda;
+    if (trial_chi2_out) *trial_chi2_out = after.chi_last_trial;
+    dbg.release();
+    return VISFS_BA_OK;
+}
+
+int visfs_ba_comm_unique_id(void *) { return VISFS_BA_ERR_UNSUPPORTED; }
+int visfs_ba_comm_init(visfs_ba_handle *h, int32_t, int32_t, const void *) {
+    return h ? h->fail(VISFS_BA_ERR_UNSUPPORTED, "multi-GPU global BA: not in this build yet") : VISFS_BA_ERR_INVALID;
+}
+int visfs_ba_comm_destroy(visfs_ba_handle *) { return VISFS_BA_OK; }
+
+int visfs_ba_probe_fp64(visfs_ba_handle *h, double *tflops_out) {
+    if (!h || !tflops_out) return VISFS_BA_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    const int blocks = h->sm_count * 8, threads = 256, iters = 1 << 15;
+    CK(h->d_tmp.reserve(sizeof(double) * (size_t)blocks * threads));
+    k_probe_fp64<<<blocks, threads, 0, h->stream>>>(h->d_tmp.as<double>(), 1024);
+    double best = 0.0;
+    for (int rep = 0; rep < 3; ++rep) {
+        CK(cudaEventRecord(h->ev_t0, h->stream));
+        k_probe_fp64<<<blocks, threads, 0, h->stream>>>(h->d_tmp.as<double>(), iters);
+        CK(cudaEventRecord(h->ev_t1, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1);
+        const double flops = 2.0 * 8.0 * (double)iters * (double)blocks * threads;
+        best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    *tflops_out = best;
+    return VISFS_BA_OK;
+}
+
+}  // extern "C"
