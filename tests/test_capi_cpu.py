@@ -1,0 +1,100 @@
+"""CPU tests of the boundary: the C-ABI library loads, exports every symbol include/visfs_ba.h declares,
+the ctypes struct layouts match the C structs, and compute calls fail loudly without a GPU."""
+import ctypes as C
+import os
+import re
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from visfs_b200 import capi, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "visfs_ba.h")
+
+
+def declared_functions():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(visfs_ba_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(built):
+    lib = capi.load_library()
+    names = declared_functions()
+    assert len(names) >= 16
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/visfs_ba.h but not exported"
+    assert sorted(capi.EXPORTS) == names
+    assert lib.visfs_ba_abi_version() == 1
+
+
+def test_struct_layouts_match_the_header(built):
+    src = r'''
+    #include <stdio.h>
+    #include "visfs_ba.h"
+    int main(void) {
+      printf("%zu %zu %zu %zu %zu %zu\n", sizeof(visfs_ba_config), sizeof(visfs_ba_problem), sizeof(visfs_ba_result),
+             sizeof(visfs_ba_linearization), sizeof(visfs_ba_structure), sizeof(visfs_ba_timing));
+      return 0; }'''
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "t.c")
+        open(c, "w").write(src)
+        exe = os.path.join(d, "t")
+        subprocess.run(["/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
+        sizes = list(map(int, subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split()))
+    assert sizes == [C.sizeof(capi.Config), C.sizeof(capi.Problem), C.sizeof(capi.Result), C.sizeof(capi.Linearization),
+                     C.sizeof(capi.Structure), C.sizeof(capi.Timing)]
+
+
+def test_no_cpu_fallback_without_a_device(built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(capi.BAError, match="no CUDA device"):
+        capi.BundleAdjuster(device=0)
+
+
+def test_missing_library_fails_loudly():
+    with pytest.raises(capi.BAError, match="missing"):
+        capi.load_library("/nonexistent/libvisfs_ba.so")
+
+
+def test_product_sources_do_not_touch_the_oracle():
+    bad = []
+    for base, _, files in os.walk(os.path.join(ROOT, "visfs_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                text = open(os.path.join(base, f), errors="ignore").read()
+                if re.search(r"oracle[/_.]|liboracle|from tests|import tests", text):
+                    bad.append(os.path.join(base, f))
+    assert not bad, f"product files reference the oracle: {bad}"
+
+
+def test_synthetic_configs_have_the_published_shapes():
+    c1 = synth.config_c1()
+    assert (c1["n_poses"], c1["n_points"], c1["n_edges"]) == (10, 2000, 20000)
+    assert c1["pose_fixed"].sum() == 1 and c1["pose_id"][c1["pose_fixed"].astype(bool)][0] == 9   # newest - 1
+    assert synth.algorithmic_bytes_per_trial(c1) == 64 * 20000 + 72 * 2000 + 112 * 10
+    c2 = synth.config_c2()
+    assert (c2["n_poses"], c2["n_points"], c2["n_edges"]) == (20, 10000, 100000)
+    assert 0.25 < c2["edge_kind"].mean() < 0.35
+    # edges are in g2o insertion order
+    key = c2["edge_point"].astype(np.int64) * 1000 + c2["edge_pose"]
+    assert np.all(np.diff(key) > 0)
+    # float rounding of the measurement (Optimizer.cpp:187-188) is part of the data
+    st = c2["edge_kind"] == 0
+    assert np.array_equal(c2["edge_obs"][st, 2], c2["edge_obs"][st, 2].astype(np.float32).astype(np.float64))
+    c4 = synth.config_c4(n_poses=100, n_points=2000)
+    assert c4["n_edges"] == 20000 and c4["edge_pose"].max() == 99
+    c5 = synth.config_c5(n_poses=40, n_points=500)
+    assert c5["n_edges"] == 5000
+
+
+def test_pose_frame_conversion_round_trip():
+    w = synth.make_window(5, 10, seed=3)
+    T = synth.camera_state_to_robot(w["pose_tq"])
+    assert np.allclose(T, w["ref_T_wr"], atol=1e-12)
+    assert np.all(w["pose_tq"][:, 6] >= 0) and np.allclose(np.linalg.norm(w["pose_tq"][:, 3:], axis=1), 1.0)

@@ -1,0 +1,45 @@
+"""GPU test of the reference-facing plugin: VISFS::Optimizer::Optimizer::localOptimize (C++17, through the
+C ABI) against the oracle plus the reference's write-back rules (Optimizer.cpp:320-358)."""
+import numpy as np
+import pytest
+
+from tests import host_io
+from tests import oracle_api as O
+from visfs_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def test_local_optimize_matches_oracle_and_write_back_rules(built, tmp_path):
+    w = synth.make_window(6, 300, layout="consecutive", views=4, seed=81, mono_frac=0.2, fixed_point_frac=0.1, first_id=5)
+    fin, fout = str(tmp_path / "w.bin"), str(tmp_path / "o.bin")
+    host_io.write_window(fin, w, feature_id_offset=40, extra_points=3)
+    got = host_io.run_solve(fin, fout)
+    ref = O.solve(w)
+    assert ref["status"] == 0
+    # poses: T_wr = T_cw^-1 * T_rc^-1
+    T_ref = synth.camera_state_to_robot(ref["pose_tq"])
+    assert sorted(got["poses"]) == list(map(int, w["pose_id"]))
+    for i, pid in enumerate(w["pose_id"]):
+        assert np.allclose(got["poses"][int(pid)], T_ref[i], rtol=1e-6, atol=1e-8)
+    # points: accepted when moved < 5 m, NaN for entries that never became a vertex
+    for l, fid in enumerate(w["point_id"]):
+        new, old = ref["point_xyz"][l], w["point_xyz"][l]
+        want = new if np.linalg.norm(old - new) < 5.0 else old
+        assert np.allclose(got["points"][int(fid) + 40], want, rtol=1e-6, atol=1e-8)
+    for k in range(3):
+        assert np.all(np.isnan(got["points"][10**6 + k]))
+    # outliers: (feature id, pose id) of culled edges, in insertion order
+    lvl = ref["edge_level"].astype(bool)
+    want = np.stack([w["point_id"][w["edge_point"][lvl]] + 40, w["pose_id"][w["edge_pose"][lvl]]], axis=1)
+    assert np.array_equal(got["outliers"], want)
+
+
+def test_local_optimize_failure_returns_empty_map(built, tmp_path):
+    w = synth.make_window(4, 50, layout="all", seed=82)
+    w["point_xyz"][3] = np.nan
+    fin, fout = str(tmp_path / "w.bin"), str(tmp_path / "o.bin")
+    host_io.write_window(fin, w)
+    got = host_io.run_solve(fin, fout)
+    assert got["poses"] == {} and len(got["outliers"]) == 0
+    assert "NANs" in got["stdout"] or "NANs" in got["stderr"]

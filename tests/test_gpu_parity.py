@@ -15,9 +15,9 @@ RTOL_EDGE = 1e-9
 RTOL_FINAL = 1e-6
 
 
-def rejecting_window(seed, pose_noise):
+def rejecting_window(seed, pose_noise, iterations=20):
     """Close landmarks and a bad initial guess: LM has to reject steps and raise the damping."""
-    return synth.make_window(5, 150, layout="all", seed=seed, pose_noise=pose_noise, point_noise=0.5, iterations=20,
+    return synth.make_window(5, 150, layout="all", seed=seed, pose_noise=pose_noise, point_noise=0.5, iterations=iterations,
                              depth_range=(1.0, 6.0))
 
 
@@ -140,8 +140,12 @@ def test_solve_c2_mixed_mono_stereo(ba):
 
 def test_solve_with_rejected_steps(ba):
     # a badly initialised window: LM has to reject steps and raise the damping
-    for seed, pn in ((102, (0.3, np.deg2rad(6.0))), (100, (1.0, np.deg2rad(20.0)))):
-        w = rejecting_window(seed, pn)
+    # (seed 100 at 20 iterations is chaotic: 17 + 15 trials from a 20 degree / 1 m initial error amplify
+    # rounding differences to 1e-3; it is run with 10 iterations, which still holds its 4-trial iteration)
+    cases = [(102, (0.3, np.deg2rad(6.0)), 20), (110, (0.3, np.deg2rad(6.0)), 20), (130, (0.3, np.deg2rad(6.0)), 20),
+             (139, (0.3, np.deg2rad(6.0)), 20), (100, (1.0, np.deg2rad(20.0)), 10)]
+    for seed, pn, iters in cases:
+        w = rejecting_window(seed, pn, iters)
         ref = O.solve(w)
         assert sum(ref["trials_run"]) > sum(ref["iterations_run"]), "window does not exercise the reject path"
         check_solution(ba.solve(w), ref, f"rejections seed {seed}")
@@ -155,7 +159,9 @@ def test_solve_everything_culled_second_pass_empty(ba):
 
 
 def test_solve_gauss_newton(ba):
-    w = synth.make_window(6, 300, layout="all", seed=44, trust_region=1)
+    # undamped steps send ill-observed landmarks to 1e13 m in any implementation (g2o included); the
+    # parity window therefore has no gross outliers and a good initial structure
+    w = synth.make_window(6, 300, layout="all", seed=44, trust_region=1, outlier_frac=0.0, point_noise=0.02)
     check_solution(ba.solve(w), O.solve(w), "gauss-newton")
 
 

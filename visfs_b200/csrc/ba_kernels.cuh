@@ -431,9 +431,8 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(Batch B) {
         }
         __syncthreads();
     } else {
-        // g2o LinearSolverPCG: block-Jacobi preconditioner, x0 = 0, stop when r'M^-1 r <= 1e-6 * initial
-        // (absolute-tolerance quirk of upstream is replaced by running to that relative bound twice over:
-        // tolerance 1e-12), at most n iterations.
+        // g2o LinearSolverPCG::solve: block-Jacobi preconditioner (inverse 6x6 diagonal blocks), x0 = 0,
+        // at most n iterations; tolerance handling below.
         double *r = aux, *d = aux + n, *q = aux + 2 * n, *s = aux + 3 * n, *xv = aux + 4 * n, *Minv = aux + 5 * n;
         // invert the 6x6 diagonal blocks (one thread per pose, Gauss-Jordan with partial pivoting)
         for (int i = tid; i < F; i += kSolveThreads) {
@@ -477,9 +476,13 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(Batch B) {
         };
         precond(r, d);
         double dn = dot(r, d);
-        const double d0 = 1e-12 * dn;
+        // upstream quirk kept: relative tolerance 1e-6 on the first solve after init(); once a solve has ended
+        // with residual > 1e-6 the bound becomes 0 and the loop runs all n iterations
+        double d0 = 1e-6 * dn;
+        const double prev_res = st.pcg_residual;
+        if (prev_res > 0.0 && prev_res > 1e-6) d0 = 0.0;
         for (int it = 0; it < n; ++it) {
-            if (!(dn > d0)) break;
+            if (dn <= d0) break;
             for (int i = tid; i < n; i += kSolveThreads) {
                 double acc = 0.0;
                 for (int c = 0; c < n; ++c) acc += S[i >= c ? tri(i, c) : tri(c, i)] * d[c];
@@ -497,6 +500,7 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(Batch B) {
             __syncthreads();
         }
         for (int i = tid; i < n; i += kSolveThreads) bs[i] = xv[i];
+        if (tid == 0) st.pcg_residual = 0.5 * dn;
         __syncthreads();
     }
 
@@ -713,6 +717,7 @@ __global__ void k_control_init(Batch B) {
         st.lambda = 1e-5 * md;
         st.ni = 2.0;
         st.iter = 0; st.qmax = 0;
+        st.pcg_residual = -1.0;
         if (st.F + st.NL == 0) finish_pass(st, VISFS_BA_STOP_EMPTY, B.n_running);
         else if (wd.max_iter <= 0) finish_pass(st, VISFS_BA_STOP_ITERATIONS, B.n_running);
     }

@@ -38,6 +38,7 @@ struct WinDesc {
 struct LMState {
     double lambda, ni, cur_chi, trial_chi, rho, scale_p;
     double chi_initial, chi_pass[2], chi_last_trial, lambda_final[2];
+    double pcg_residual;             // g2o LinearSolverPCG::_residual (reset by init() at every optimize())
     int iter, qmax, done, cur;       // cur: which state buffer holds the accepted estimate
     int F, NL, ok, fresh;            // fresh: 1 until the first trial of the pass has run
     int iterations_run[2], trials_run[2], stop[2], nF[2], nNL[2];

@@ -1,0 +1,334 @@
+// Optimizer.cpp — the reference-facing plugin: VISFS::Optimizer::Optimizer::localOptimize on the B200.
+// Follows corelib/src/Optimizer/Optimizer.cpp:58-364 (g2o branch) step by step; the numbered comments
+// are the reference's line ranges.  All arithmetic that g2o did runs behind visfs_ba_solve().
+#include "Optimizer.h"
+
+#include <cmath>
+#include <cstdio>
+#include <limits>
+
+#include "visfs_ba.h"
+
+namespace VISFS {
+namespace Optimizer {
+
+namespace {
+
+int g_device = 0;
+
+#ifndef LOG_ERROR
+// stand-alone build: the reference's Boost.Log macros (utilite/include/Log.h:38-43) become stderr lines
+void logLine(const char * level, const std::string & text) { std::fprintf(stderr, "[VISFS %s] %s\n", level, text.c_str()); }
+#define VISFS_B200_LOG(level, text) logLine(level, text)
+#else
+#define VISFS_B200_LOG(level, text) do { if (level[0] == 'E') { LOG_ERROR << text; } else { LOG_WARN << text; } } while (0)
+#endif
+
+// Eigen::Quaterniond(Matrix3d) followed by CameraPose::normalizeRotation (OptimizeTypeDefine.h:30-41)
+void rotationToQuaternion(const Eigen::Matrix3d & m, double q[4] /* x y z w */) {
+    double t = m(0, 0) + m(1, 1) + m(2, 2);
+    double x, y, z, w;
+    if (t > 0.0) {
+        t = std::sqrt(t + 1.0);
+        w = 0.5 * t;
+        t = 0.5 / t;
+        x = (m(2, 1) - m(1, 2)) * t;
+        y = (m(0, 2) - m(2, 0)) * t;
+        z = (m(1, 0) - m(0, 1)) * t;
+    } else {
+        int i = 0;
+        if (m(1, 1) > m(0, 0)) i = 1;
+        if (m(2, 2) > m(i, i)) i = 2;
+        const int j = (i + 1) % 3, k = (j + 1) % 3;
+        t = std::sqrt(m(i, i) - m(j, j) - m(k, k) + 1.0);
+        double v[3];
+        v[i] = 0.5 * t;
+        t = 0.5 / t;
+        w = (m(k, j) - m(j, k)) * t;
+        v[j] = (m(j, i) + m(i, j)) * t;
+        v[k] = (m(k, i) + m(i, k)) * t;
+        x = v[0]; y = v[1]; z = v[2];
+    }
+    if (w < 0.0) { x = -x; y = -y; z = -z; w = -w; }
+    const double n = std::sqrt(x * x + y * y + z * z + w * w);
+    q[0] = x / n; q[1] = y / n; q[2] = z / n; q[3] = w / n;
+}
+
+// CameraPose::toHomogeneousMatrix (OptimizeTypeDefine.h:74-81): Eigen toRotationMatrix of (x y z w)
+Eigen::Isometry3d stateToIsometry(const double * tq) {
+    const double x = tq[3], y = tq[4], z = tq[5], w = tq[6];
+    const double tx = 2.0 * x, ty = 2.0 * y, tz = 2.0 * z;
+    const double twx = tx * w, twy = ty * w, twz = tz * w;
+    const double txx = tx * x, txy = ty * x, txz = tz * x;
+    const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
+    Eigen::Isometry3d T;
+    Eigen::Matrix3d & R = T.linear();
+    R(0, 0) = 1.0 - (tyy + tzz); R(0, 1) = txy - twz;         R(0, 2) = txz + twy;
+    R(1, 0) = txy + twz;         R(1, 1) = 1.0 - (txx + tzz); R(1, 2) = tyz - twx;
+    R(2, 0) = txz - twy;         R(2, 1) = tyz + twx;         R(2, 2) = 1.0 - (txx + tyy);
+    T.translation() = Eigen::Vector3d(tq[0], tq[1], tq[2]);
+    return T;
+}
+
+bool isZeroTransform(const Eigen::Isometry3d & T) {
+    // t.isApprox(Isometry3d(Matrix4d::Zero())) (Optimizer.cpp:330): true only for an all-zero matrix
+    for (int i = 0; i < 3; ++i) {
+        if (T.translation()[i] != 0.0) return false;
+        for (int j = 0; j < 3; ++j) if (T.linear()(i, j) != 0.0) return false;
+    }
+    return true;
+}
+
+}  // namespace
+
+void Optimizer::setDevice(int _device) { g_device = _device; }
+
+// corelib/src/Optimizer/Optimizer.cpp:37-56
+Optimizer::Optimizer(const ParametersMap & _parameters) :
+    framework_(Parameters::defaultOptimizerFramework()),
+    solver_(Parameters::defaultOptimizerSolver()),
+    trustRegion_(Parameters::defaultOptimizerTrustRegion()),
+    iterations_(Parameters::defaultOptimizerIterations()),
+    pixelVariance_(Parameters::defaultOptimizerPixelVariance()),
+    odometryCovariance_(Parameters::defaultOptimizerOdometryCovariance()),
+    laserCovariance_(Parameters::defaultOptimizerLaserCovariance()),
+    robustKernelDelta_(Parameters::defaultOptimizerRobustKernelDelta()),
+    handle_(nullptr) {
+    Parameters::parse(_parameters, Parameters::kOptimizerFramework(), framework_);
+    Parameters::parse(_parameters, Parameters::kOptimizerSolver(), solver_);
+    Parameters::parse(_parameters, Parameters::kOptimizerTrustRegion(), trustRegion_);
+    Parameters::parse(_parameters, Parameters::kOptimizerIterations(), iterations_);
+    Parameters::parse(_parameters, Parameters::kOptimizerPixelVariance(), pixelVariance_);
+    Parameters::parse(_parameters, Parameters::kOptimizerOdometryCovariance(), odometryCovariance_);
+    Parameters::parse(_parameters, Parameters::kOptimizerLaserCovariance(), laserCovariance_);
+    Parameters::parse(_parameters, Parameters::kOptimizerRobustKernelDelta(), robustKernelDelta_);
+}
+
+Optimizer::~Optimizer() {
+    if (handle_) visfs_ba_destroy(handle_);
+}
+
+bool Optimizer::ensureHandle() {
+    if (handle_) return true;
+    visfs_ba_config cfg{};
+    cfg.abi_version = VISFS_BA_ABI_VERSION;
+    cfg.device = g_device;
+    if (visfs_ba_create(&cfg, &handle_) != VISFS_BA_OK) {
+        const char * why = visfs_ba_last_error(nullptr);
+        message_ = std::string("Optimizer: cannot create the CUDA bundle adjuster: ") + (why ? why : "");
+        VISFS_B200_LOG("ERROR", message_);
+        handle_ = nullptr;
+        return false;
+    }
+    return true;
+}
+
+// Optimizer.cpp:100-114 (poses) and :152-223 (points, visual edges) of the reference
+bool Optimizer::marshal(std::size_t _rootId,
+                        const std::map<std::size_t, Eigen::Isometry3d> & _poses,
+                        const std::vector<std::shared_ptr<GeometricCamera>> & _cameraModels,
+                        const std::map<std::size_t, std::tuple<Eigen::Vector3d, bool>> & _points3D,
+                        const std::map<std::size_t, std::map<std::size_t, FeatureBA>> & _wordReferences,
+                        detail::MarshalledWindow & m) {
+    if (_cameraModels.empty() || !_cameraModels.front()) return false;
+    const GeometricCamera & cameraModel = *_cameraModels.front();
+    const Eigen::Isometry3d Trc = cameraModel.getTansformImageToRobot();
+    m = detail::MarshalledWindow();
+
+    std::map<std::size_t, int> poseIndex;
+    for (auto iter = _poses.begin(); iter != _poses.end(); ++iter) {
+        if (iter->first > 0) {                                            // :101
+            Eigen::Isometry3d cameraPose = iter->second * Trc;           // :104  Twc = Twr * Trc
+            cameraPose = cameraPose.inverse();                            // :108  Tcw
+            double q[4];
+            rotationToQuaternion(cameraPose.linear(), q);                 // :109  CameraPose(R, t)
+            poseIndex.emplace(iter->first, static_cast<int>(m.pose_id.size()));
+            m.pose_id.push_back(static_cast<int64_t>(iter->first));
+            m.pose_fixed.push_back(iter->first == _rootId ? 1 : 0);       // :111
+            const Eigen::Vector3d & t = cameraPose.translation();
+            const double rec[7] = {t[0], t[1], t[2], q[0], q[1], q[2], q[3]};
+            m.pose_tq.insert(m.pose_tq.end(), rec, rec + 7);
+        }
+    }
+
+    const Eigen::Matrix3d K = cameraModel.eigenKdouble();                 // :176
+    double baseLine = 0.0;
+    if (_cameraModels.size() > 1) baseLine = cameraModel.getBaseLine();   // :181-183 (float -> double)
+    m.fx = K(0, 0); m.fy = K(1, 1); m.cx = K(0, 2); m.cy = K(1, 2);
+    m.bf = baseLine * m.fx;                                               // :195
+
+    for (auto iter = _wordReferences.begin(); iter != _wordReferences.end(); ++iter) {   // :156
+        const std::size_t id = iter->first;
+        auto pit = _points3D.find(id);
+        if (pit == _points3D.end()) continue;                             // :158
+        const int pointIndex = static_cast<int>(m.point_id.size());
+        const Eigen::Vector3d & pointPose = std::get<0>(pit->second);
+        m.point_id.push_back(static_cast<int64_t>(id));
+        m.point_fixed.push_back(std::get<1>(pit->second) ? 1 : 0);        // :165
+        m.point_xyz.push_back(pointPose[0]); m.point_xyz.push_back(pointPose[1]); m.point_xyz.push_back(pointPose[2]);
+        for (auto jter = iter->second.begin(); jter != iter->second.end(); ++jter) {     // :169
+            auto cit = poseIndex.find(jter->first);
+            if (cit == poseIndex.end()) continue;                         // :172
+            const FeatureBA & pt = jter->second;
+            const double depth = pt.depth;                                // :174
+            double obs[3] = {pt.kpt.pt.x, pt.kpt.pt.y, 0.0};
+            uint8_t kind = VISFS_BA_EDGE_MONO;
+            if (std::isfinite(depth) && depth > 0.0 && baseLine > 0.0) {  // :184
+                const float disparity = static_cast<float>(baseLine * K(0, 0) / depth);   // :187
+                obs[2] = pt.kpt.pt.x - disparity;                         // :188  (float - float, widened)
+                kind = VISFS_BA_EDGE_STEREO;
+            }
+            // else: the reference's mono branch is commented out (:197-208) and its live code is undefined
+            // behaviour; this build defines the mono edge as rows 0-1 of EdgeStereo.
+            m.edge_obs.insert(m.edge_obs.end(), obs, obs + 3);
+            m.edge_pose.push_back(cit->second);
+            m.edge_point.push_back(pointIndex);
+            m.edge_kind.push_back(kind);
+        }
+    }
+    return true;
+}
+
+std::map<std::size_t, Eigen::Isometry3d> Optimizer::localOptimize(
+    std::size_t _rootId,
+    const std::map<std::size_t, Eigen::Isometry3d> & _poses,
+    const std::map<std::size_t,std::tuple<std::size_t, std::size_t, Eigen::Isometry3d>> & _links,
+    const std::vector<std::shared_ptr<GeometricCamera>> & _cameraModels,
+    std::map<std::size_t, std::tuple<Eigen::Vector3d, bool>> & _points3D,
+    const std::map<std::size_t, std::map<std::size_t, FeatureBA>> & _wordReferences,
+    const std::vector<Sensor::PointCloud> & _pointClouds,
+    const std::shared_ptr<const Map::Submap2D> & _submap,
+    std::vector<std::tuple<std::size_t, std::size_t>> & _outliers) {
+
+    std::map<std::size_t, Eigen::Isometry3d> optimizedPoses;
+    message_.clear();
+    if (_cameraModels.empty()) {   // the reference asserts (:69)
+        message_ = "Optimizer: no camera model.";
+        VISFS_B200_LOG("ERROR", message_);
+        return optimizedPoses;
+    }
+    if (framework_ == CERES) {
+        message_ = "Optimizer: Optimizer/Framework=1 (ceres) is not part of the CUDA build.";
+        VISFS_B200_LOG("ERROR", message_);
+        return optimizedPoses;
+    }
+
+    if (_poses.size() >= 2 && iterations_ > 0 && _poses.begin()->first > 0) {           // :74
+        if (!_links.empty()) {        // :116-150, EdgePoseConstraint: SURVEY.md §8 f-1, not on this path yet
+            message_ = "Optimizer: odometry links are not handled by the CUDA optimiser yet.";
+            VISFS_B200_LOG("ERROR", message_);
+            return optimizedPoses;
+        }
+        if (!_pointClouds.empty() && _submap != nullptr) {   // :225-258, laser edges: SURVEY.md §8 f-4
+            message_ = "Optimizer: laser observations are not handled by the CUDA optimiser.";
+            VISFS_B200_LOG("ERROR", message_);
+            return optimizedPoses;
+        }
+        if (trustRegion_ != 0 && trustRegion_ != 1) {        // :93-97 leaves the algorithm unset
+            message_ = "Optimizer: unknown Optimizer/TrustRegion.";
+            VISFS_B200_LOG("ERROR", message_);
+            return optimizedPoses;
+        }
+        if (!ensureHandle()) return optimizedPoses;
+
+        detail::MarshalledWindow m;
+        if (!marshal(_rootId, _poses, _cameraModels, _points3D, _wordReferences, m)) return optimizedPoses;
+
+        visfs_ba_problem prob{};
+        prob.n_poses = static_cast<int32_t>(m.pose_id.size());
+        prob.n_points = static_cast<int32_t>(m.point_id.size());
+        prob.n_edges = static_cast<int32_t>(m.edge_pose.size());
+        prob.pose_tq = m.pose_tq.data(); prob.pose_id = m.pose_id.data(); prob.pose_fixed = m.pose_fixed.data();
+        prob.point_xyz = m.point_xyz.data(); prob.point_id = m.point_id.data(); prob.point_fixed = m.point_fixed.data();
+        prob.edge_obs = m.edge_obs.data(); prob.edge_pose = m.edge_pose.data(); prob.edge_point = m.edge_point.data();
+        prob.edge_kind = m.edge_kind.data();
+        prob.fx = m.fx; prob.fy = m.fy; prob.cx = m.cx; prob.cy = m.cy; prob.bf = m.bf;
+        prob.pixel_variance = pixelVariance_;                   // :153
+        prob.huber_delta = robustKernelDelta_;                  // :212-216
+        prob.iterations = iterations_;                          // :265, :311 (each pass runs iterations_/2)
+        prob.solver = solver_;                                  // :76-91
+        prob.trust_region = trustRegion_;                       // :93-97
+
+        std::vector<double> poseOut(m.pose_tq.size()), pointOut(m.point_xyz.size());
+        std::vector<uint8_t> levelOut(m.edge_pose.size());
+        visfs_ba_result res{};
+        res.pose_tq = poseOut.data(); res.point_xyz = pointOut.data(); res.edge_level = levelOut.data();
+        const int status = visfs_ba_solve(handle_, &prob, &res);
+
+        if (status == VISFS_BA_ERR_NUMERIC_PASS1) {             // :272-280
+            message_ = std::isnan(res.chi2_pass1) ? "Optimization generated NANs, aborting optimization!"
+                                                  : "g2o: Large optimization error detected in the first time optimize, aborting optimization!";
+            VISFS_B200_LOG("ERROR", message_);
+            return optimizedPoses;
+        }
+        if (status != VISFS_BA_OK && status != VISFS_BA_ERR_NUMERIC_PASS2) {   // CUDA / argument failure -> "BA failed"
+            const char * why = visfs_ba_last_error(handle_);
+            message_ = std::string("Optimizer: CUDA bundle adjustment failed: ") + (why ? why : "");
+            VISFS_B200_LOG("ERROR", message_);
+            return optimizedPoses;
+        }
+
+        // :283-309 — outliers are appended in edge insertion order, before the second-pass guard
+        if (robustKernelDelta_ > 0.0) {
+            for (std::size_t e = 0; e < levelOut.size(); ++e) {
+                if (levelOut[e]) {
+                    _outliers.emplace_back(std::make_tuple(static_cast<std::size_t>(m.point_id[m.edge_point[e]]),
+                                                           static_cast<std::size_t>(m.pose_id[m.edge_pose[e]])));
+                }
+            }
+            if (_outliers.size() > levelOut.size() / 2) {        // :305-308 (warning only)
+                message_ = "Optimizer: large outliers detect, outliers size: " + std::to_string(_outliers.size()) +
+                           ", total edges: " + std::to_string(levelOut.size());
+                VISFS_B200_LOG("WARN", message_);
+            }
+        }
+        if (status == VISFS_BA_ERR_NUMERIC_PASS2) {             // :315-318
+            message_ = "g2o: Large optimization error detected in the second time optimize, aborting optimization!";
+            VISFS_B200_LOG("ERROR", message_);
+            return optimizedPoses;
+        }
+
+        // :320-340 — poses back to T_world<-robot
+        const Eigen::Isometry3d TrcInv = _cameraModels.front()->getTansformImageToRobot().inverse();
+        for (std::size_t i = 0; i < m.pose_id.size(); ++i) {
+            Eigen::Isometry3d t = stateToIsometry(&poseOut[7 * i]);
+            t = t.inverse();
+            t = t * TrcInv;
+            if (isZeroTransform(t)) {
+                message_ = "Optimized pose " + std::to_string(m.pose_id[i]) + " is null.";
+                VISFS_B200_LOG("WARN", message_);
+                optimizedPoses.clear();
+                return optimizedPoses;
+            }
+            optimizedPoses.emplace(static_cast<std::size_t>(m.pose_id[i]), t);
+        }
+
+        // :343-358 — points: accept moves shorter than 5 m, NaN for points that never became a vertex
+        std::map<std::size_t, std::size_t> vertexOf;
+        for (std::size_t l = 0; l < m.point_id.size(); ++l) vertexOf.emplace(static_cast<std::size_t>(m.point_id[l]), l);
+        for (auto iter = _points3D.begin(); iter != _points3D.end(); ++iter) {
+            auto vit = vertexOf.find(iter->first);
+            Eigen::Vector3d oldPose = std::get<0>(iter->second);
+            const bool fixSymbol = std::get<1>(iter->second);
+            if (vit != vertexOf.end()) {
+                const double * np = &pointOut[3 * vit->second];
+                const double dx = oldPose[0] - np[0], dy = oldPose[1] - np[1], dz = oldPose[2] - np[2];
+                if (std::sqrt(dx * dx + dy * dy + dz * dz) < 5.0) {
+                    iter->second = std::make_tuple(Eigen::Vector3d(np[0], np[1], np[2]), fixSymbol);
+                }
+            } else {
+                const double nan = std::numeric_limits<double>::quiet_NaN();
+                iter->second = std::make_tuple(Eigen::Vector3d(nan, nan, nan), fixSymbol);
+            }
+        }
+    } else if (_poses.size() == 1 || iterations_ <= 0) {        // :360-361
+        optimizedPoses = _poses;
+    } else {                                                    // :362-364
+        message_ = "This method should be called at least with 1 pose!";
+        VISFS_B200_LOG("ERROR", message_);
+    }
+    return optimizedPoses;
+}
+
+}   // Optimizer
+}   // VISFS

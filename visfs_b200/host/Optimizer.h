@@ -1,0 +1,120 @@
+// Optimizer.h — C++17 mirror of the reference's BA interface
+// (corelib/include/Optimizer/Optimizer.h:17-77): same namespace, class, struct, constructor and
+// localOptimize signature, so corelib/src/Estimator.cpp:254 links against it unchanged.  The body
+// (Optimizer.cpp) marshals the window into the C ABI of include/visfs_ba.h and runs the sm_100a
+// kernels; there is no g2o, no Ceres and no CPU fallback behind it.
+#ifndef VISFS_OPTIMIZER_H
+#define VISFS_OPTIMIZER_H
+
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <set>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "visfs_compat.h"
+
+struct visfs_ba_handle;
+
+namespace VISFS {
+namespace Optimizer {
+
+struct FeatureBA {
+    cv::KeyPoint kpt;
+    float depth;
+    FeatureBA(const cv::KeyPoint & _kpt, const float _depth) {
+        kpt = _kpt;
+        depth = _depth;
+    }
+};
+
+namespace detail {
+// The window in the flat form the C ABI takes (host memory), plus the id tables needed to map results back.
+struct MarshalledWindow {
+    std::vector<double> pose_tq;        // [P][7] T_cw
+    std::vector<int64_t> pose_id;
+    std::vector<uint8_t> pose_fixed;
+    std::vector<double> point_xyz;      // [L][3]
+    std::vector<int64_t> point_id;      // feature ids that got a vertex (Optimizer.cpp:158)
+    std::vector<uint8_t> point_fixed;
+    std::vector<double> edge_obs;       // [E][3]
+    std::vector<int32_t> edge_pose, edge_point;
+    std::vector<uint8_t> edge_kind;
+    double fx = 0, fy = 0, cx = 0, cy = 0, bf = 0;
+};
+}  // namespace detail
+
+class Optimizer {
+public:
+    Optimizer(const ParametersMap & _parameters = ParametersMap());
+    ~Optimizer();
+    Optimizer(const Optimizer &) = delete;
+    Optimizer & operator=(const Optimizer &) = delete;
+
+    /** \brief Optimize the local maps (visual part of the reference's local fusion).
+     * \param[in] rootId Fixed pose.
+     * \param[in] poses Poses to optimize (T_world<-robot).
+     * \param[in] links Odometry links between poses (must be empty: SURVEY.md §8 f-1).
+     * \param[in] cameraModels Left (and right) camera model; stereo iff size() > 1.
+     * \param[in&out] points3D World points, fixed flag.
+     * \param[in] wordReferences Observations: feature id -> pose id -> key point + depth.
+     * \param[in] pointClouds Laser points (must be empty: SURVEY.md §8 f-4).
+     * \param[in] submap Laser submap (must be null).
+     * \param[out] outliers (feature id, pose id) of every edge culled after the first pass.
+     * \return optimised poses; EMPTY on failure, exactly like the reference.
+     */
+    std::map<std::size_t, Eigen::Isometry3d> localOptimize(
+        std::size_t _rootId,
+        const std::map<std::size_t, Eigen::Isometry3d> & _poses,
+        const std::map<std::size_t,std::tuple<std::size_t, std::size_t, Eigen::Isometry3d>> & _links,
+        const std::vector<std::shared_ptr<GeometricCamera>> & _cameraModels,
+        std::map<std::size_t, std::tuple<Eigen::Vector3d, bool>> & _points3D,
+        const std::map<std::size_t, std::map<std::size_t, FeatureBA>> & _wordReferences,
+        const std::vector<Sensor::PointCloud> & _pointClouds,
+        const std::shared_ptr<const Map::Submap2D> & _submap,
+        std::vector<std::tuple<std::size_t, std::size_t>> & _outliers
+    );
+
+    // Host-only half of localOptimize (Optimizer.cpp:100-223 of the reference): map-of-maps -> flat arrays.
+    // Public so that it can be tested without a GPU.
+    static bool marshal(std::size_t _rootId,
+                        const std::map<std::size_t, Eigen::Isometry3d> & _poses,
+                        const std::vector<std::shared_ptr<GeometricCamera>> & _cameraModels,
+                        const std::map<std::size_t, std::tuple<Eigen::Vector3d, bool>> & _points3D,
+                        const std::map<std::size_t, std::map<std::size_t, FeatureBA>> & _wordReferences,
+                        detail::MarshalledWindow & _out);
+
+    // Device ordinal used by every Optimizer created afterwards (default 0).
+    static void setDevice(int _device);
+
+    // Last message a LOG_ERROR / LOG_WARN of the reference would have carried.
+    const std::string & lastMessage() const { return message_; }
+
+private:
+    enum Framework {
+        G2O     =   0,      // the g2o-semantics LM, executed by the CUDA kernels
+        CERES   =   1,      // not provided by this build
+        CUDA    =   2       // alias of 0
+    };
+
+    bool ensureHandle();
+
+    int framework_;
+    int solver_;
+    int trustRegion_;
+    int iterations_;
+    double pixelVariance_;
+    double odometryCovariance_;
+    double laserCovariance_;
+    double robustKernelDelta_;
+
+    visfs_ba_handle * handle_;
+    std::string message_;
+};
+
+}   // Optimizer
+}   // VISFS
+
+#endif  // VISFS_OPTIMIZER_H

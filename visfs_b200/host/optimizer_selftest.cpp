@@ -1,0 +1,104 @@
+// optimizer_selftest.cpp — drives VISFS::Optimizer::Optimizer exactly as corelib/src/Estimator.cpp:254 does,
+// from a window file written by tests/host_io.py, and dumps what came back.
+//   optimizer_selftest marshal <in> <out>   host-only: the flat arrays handed to the C ABI (no GPU needed)
+//   optimizer_selftest solve   <in> <out>   full localOptimize on the GPU
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <vector>
+
+#include "Optimizer.h"
+
+using namespace VISFS;
+
+namespace {
+template <typename T> T rd(std::istream &is) { T v; is.read(reinterpret_cast<char *>(&v), sizeof v); return v; }
+template <typename T> void wr(std::ostream &os, const T &v) { os.write(reinterpret_cast<const char *>(&v), sizeof v); }
+template <typename T> void wrv(std::ostream &os, const std::vector<T> &v) {
+    wr<int64_t>(os, (int64_t)v.size());
+    if (!v.empty()) os.write(reinterpret_cast<const char *>(v.data()), sizeof(T) * v.size());
+}
+}  // namespace
+
+int main(int argc, char **argv) {
+    if (argc != 4) { std::fprintf(stderr, "usage: %s marshal|solve <in> <out>\n", argv[0]); return 2; }
+    const std::string mode = argv[1];
+    std::ifstream in(argv[2], std::ios::binary);
+    if (!in) { std::fprintf(stderr, "cannot open %s\n", argv[2]); return 2; }
+    const int64_t P = rd<int64_t>(in), L = rd<int64_t>(in), E = rd<int64_t>(in), rootId = rd<int64_t>(in), nCam = rd<int64_t>(in);
+    const int64_t iterations = rd<int64_t>(in), solver = rd<int64_t>(in), trust = rd<int64_t>(in);
+    const double fx = rd<double>(in), fy = rd<double>(in), cx = rd<double>(in), cy = rd<double>(in), baseline = rd<double>(in);
+    const double pixelVariance = rd<double>(in), delta = rd<double>(in);
+
+    std::map<std::size_t, Eigen::Isometry3d> poses;
+    for (int64_t i = 0; i < P; ++i) {
+        const int64_t id = rd<int64_t>(in);
+        Eigen::Isometry3d T;
+        double M[16];
+        for (double &v : M) v = rd<double>(in);
+        for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) T.linear()(r, c) = M[4 * r + c]; T.translation()[r] = M[4 * r + 3]; }
+        poses.emplace((std::size_t)id, T);
+    }
+    std::map<std::size_t, std::tuple<Eigen::Vector3d, bool>> points3D;
+    for (int64_t i = 0; i < L; ++i) {
+        const int64_t id = rd<int64_t>(in);
+        const double x = rd<double>(in), y = rd<double>(in), z = rd<double>(in);
+        const int64_t fixed = rd<int64_t>(in);
+        points3D.emplace((std::size_t)id, std::make_tuple(Eigen::Vector3d(x, y, z), fixed != 0));
+    }
+    std::map<std::size_t, std::map<std::size_t, Optimizer::FeatureBA>> wordReferences;
+    for (int64_t i = 0; i < E; ++i) {
+        const int64_t fid = rd<int64_t>(in), pid = rd<int64_t>(in);
+        const float x = rd<float>(in), y = rd<float>(in), depth = rd<float>(in);
+        (void)rd<float>(in);
+        wordReferences[(std::size_t)fid].emplace((std::size_t)pid, Optimizer::FeatureBA(cv::KeyPoint(x, y), depth));
+    }
+    std::vector<std::shared_ptr<GeometricCamera>> cameraModels;
+    for (int64_t c = 0; c < nCam; ++c)
+        cameraModels.push_back(std::make_shared<GeometricCamera>(std::vector<double>{fx, fy, cx, cy, baseline}));
+
+    std::ofstream out(argv[3], std::ios::binary);
+    if (mode == "marshal") {
+        Optimizer::detail::MarshalledWindow m;
+        const bool ok = Optimizer::Optimizer::marshal((std::size_t)rootId, poses, cameraModels, points3D, wordReferences, m);
+        wr<int64_t>(out, ok ? 1 : 0);
+        wrv(out, m.pose_tq); wrv(out, m.pose_id); wrv(out, m.pose_fixed); wrv(out, m.point_xyz); wrv(out, m.point_id);
+        wrv(out, m.point_fixed); wrv(out, m.edge_obs); wrv(out, m.edge_pose); wrv(out, m.edge_point); wrv(out, m.edge_kind);
+        const std::vector<double> intr{m.fx, m.fy, m.cx, m.cy, m.bf};
+        wrv(out, intr);
+        return 0;
+    }
+
+    ParametersMap params;
+    params["Optimizer/Iterations"] = std::to_string(iterations);
+    params["Optimizer/Solver"] = std::to_string(solver);
+    params["Optimizer/TrustRegion"] = std::to_string(trust);
+    char buf[64];
+    std::snprintf(buf, sizeof buf, "%.17g", pixelVariance); params["Optimizer/PixelVariance"] = buf;
+    std::snprintf(buf, sizeof buf, "%.17g", delta); params["Optimizer/RobustKernelDelta"] = buf;
+    Optimizer::Optimizer optimizer(params);
+    std::vector<std::tuple<std::size_t, std::size_t>> outliers;
+    const std::map<std::size_t, std::tuple<std::size_t, std::size_t, Eigen::Isometry3d>> links;
+    const std::vector<Sensor::PointCloud> pointClouds;
+    const std::shared_ptr<const Map::Submap2D> submap;
+    auto result = optimizer.localOptimize((std::size_t)rootId, poses, links, cameraModels, points3D, wordReferences,
+                                          pointClouds, submap, outliers);
+    wr<int64_t>(out, (int64_t)result.size());
+    for (auto &kv : result) {
+        wr<int64_t>(out, (int64_t)kv.first);
+        for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) wr<double>(out, kv.second.linear()(r, c)); wr<double>(out, kv.second.translation()[r]); }
+        wr<double>(out, 0.0); wr<double>(out, 0.0); wr<double>(out, 0.0); wr<double>(out, 1.0);
+    }
+    wr<int64_t>(out, (int64_t)points3D.size());
+    for (auto &kv : points3D) {
+        wr<int64_t>(out, (int64_t)kv.first);
+        const Eigen::Vector3d &p = std::get<0>(kv.second);
+        wr<double>(out, p[0]); wr<double>(out, p[1]); wr<double>(out, p[2]);
+    }
+    wr<int64_t>(out, (int64_t)outliers.size());
+    for (auto &o : outliers) { wr<int64_t>(out, (int64_t)std::get<0>(o)); wr<int64_t>(out, (int64_t)std::get<1>(o)); }
+    std::cout << "poses " << result.size() << " outliers " << outliers.size() << " message '" << optimizer.lastMessage() << "'\n";
+    return 0;
+}
