@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""Benchmark of the B200 bundle adjustment (BASELINE.json metric: BA LM iterations/s and edges/s).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle on the host cores
+
+Workload (config.workload): C3 of BASELINE.json — a batch of independent 10-key-frame / 2 000-landmark /
+20 000-stereo-edge windows (C1 windows with different seeds), `--windows` per GPU (weak scaling), each solved
+with the reference's defaults (Iterations=10 -> 5+5, Huber 8, PixelVariance 1.5, LM, direct solver).
+One step = one two-pass local BA of every window of the batch.
+
+  value  LM iterations/s over all windows and GPUs, inputs resident in HBM (visfs_ba_run_resident),
+         timed with CUDA events on the library's stream, max over ranks
+  e2e    the same through visfs_ba_solve_batch with HOST buffers: H2D + LM + D2H inside the timed region
+  roofline / fp64   build kernel (linearise + Hessian + Schur) against the measured HBM peak and an
+         FP64 FMA probe measured in the same process
+  single_window     C1 as ONE window (the latency case the >= 50x target is quoted on) and C2
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from visfs_b200 import synth  # noqa: E402
+
+METRIC = "BA LM iterations/sec"
+UNIT = "LM iterations/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def make_windows(n, rank):
+    return synth.config_c3_windows(n, seed=synth.BASE_SEED + 3 + 100000 * rank)
+
+
+def flops_per_trial(w):
+    """634 E + L (50 + 144 d + 108 d (d + 1)) with d = E / L."""
+    E, L = int(w["n_edges"]), max(int(w["n_points"]), 1)
+    d = E / L
+    return 634.0 * E + L * (50.0 + 144.0 * d + 108.0 * d * (d + 1.0))
+
+
+# ---------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    def __init__(self, device):
+        self.rows, self.proc, self.device = [], None, device
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.device),
+                 "--query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for name, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------- CPU arm
+def cpu_solve_windows(windows, threads):
+    """The oracle on the host cores: one window per thread (liboracle.so releases the GIL under ctypes)."""
+    from tests import oracle_api as O
+    O.lib(False)
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        res = list(ex.map(lambda w: O.solve_timed(w, threads=1), windows))
+    dt = time.perf_counter() - t0
+    iters = sum(sum(r["iterations_run"]) for r in res)
+    trials = sum(sum(r["trials_run"]) for r in res)
+    return dt, iters, trials, res
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    n_sample = max(cores, min(4 * cores, 64))
+    windows = make_windows(n_sample, 0)
+    for _ in range(min(args.warmup, 1)):
+        cpu_solve_windows(windows[:cores], cores)
+    tot_t, tot_it, tot_tr = 0.0, 0, 0
+    for _ in range(args.steps):
+        dt, it, tr, _ = cpu_solve_windows(windows, cores)
+        tot_t += dt; tot_it += it; tot_tr += tr
+    value = tot_it / tot_t
+    sample = (f"{n_sample} of the {args.windows * args.gpus} C1 windows per step, one window per host thread, "
+              f"oracle/ba_oracle.cpp (g2o-equivalent CPU port, -O3)")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args),
+            "edges_per_s": tot_tr * 20000 / tot_t,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(args):
+    return {"workload": f"C3: batch of {args.windows} independent C1 windows per GPU (10 key frames / 2000 landmarks / "
+                        f"20000 stereo edges each), two-pass LM 5+5 iterations, Huber 8, outlier culling",
+            "windows_per_gpu": args.windows, "poses": 10, "landmarks": 2000, "edges": 20000, "iterations": 10,
+            "cache": "inputs larger than L2 (%.0f MB of edge/point/pose records per GPU per trial)" % (args.windows * 1.43),
+            "parallelism": f"windows sharded over {args.gpus} GPU(s), no collective"}
+
+
+# ---------------------------------------------------------------------------------------------- GPU arm
+def single_window_numbers(ba, O, cores, quick):
+    """C1 and C2 as single windows: device LM time, end-to-end call time, CPU oracle time."""
+    out = {}
+    for name, w in (("c1", synth.config_c1()), ("c2", synth.config_c2())):
+        packed = ba.prepare_batch([w])
+        for _ in range(3):
+            ba.solve_packed(packed)
+        reps = 5 if quick else 20
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            ba.solve_packed(packed)
+        e2e_ms = 1e3 * (time.perf_counter() - t0) / reps
+        ba.upload([w])
+        dev = []
+        for _ in range(reps + 3):
+            ba.run_resident()
+            dev.append(ba.timing())
+        dev = dev[3:]
+        dev_ms = float(np.median([t["total_ms"] for t in dev]))
+        t = dev[-1]
+        iters = t["lm_iterations"]
+        entry = {"lm_iterations": iters, "lm_trials": t["lm_trials"], "device_ms": dev_ms, "e2e_ms": e2e_ms,
+                 "device_iters_per_s": iters / (dev_ms * 1e-3), "e2e_iters_per_s": iters / (e2e_ms * 1e-3),
+                 "kernel_ms": {k: t[k] for k in ("build_ms", "solve_ms", "update_ms", "other_ms")},
+                 "launches": t["kernel_launches"]}
+        if O is not None:
+            r1 = min((O.solve_timed(w, threads=1) for _ in range(2)), key=lambda r: r["seconds"])
+            rn = min((O.solve_timed(w, threads=cores, omp=True) for _ in range(2)), key=lambda r: r["seconds"])
+            cit = sum(r1["iterations_run"])
+            assert cit == iters, "CPU and GPU ran different iteration counts"
+            entry["cpu_1thread_iters_per_s"] = cit / r1["seconds"]
+            entry["cpu_allcores_iters_per_s"] = cit / rn["seconds"]
+            entry["speedup_e2e_vs_cpu_allcores"] = entry["e2e_iters_per_s"] / max(entry["cpu_allcores_iters_per_s"], 1e-30)
+            entry["speedup_e2e_vs_cpu_1thread"] = entry["e2e_iters_per_s"] / entry["cpu_1thread_iters_per_s"]
+        out[name] = entry
+    return out
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from visfs_b200 import capi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the bundle adjustment has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce(v, op):
+        if world == 1:
+            return v
+        t = torch.tensor([float(v)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    MAX = dist.ReduceOp.MAX if world > 1 else None
+    SUM = dist.ReduceOp.SUM if world > 1 else None
+
+    t_gen = time.perf_counter()
+    windows = make_windows(args.windows, rank)
+    log(f"[rank {rank}] generated {len(windows)} windows in {time.perf_counter() - t_gen:.1f}s")
+    ba = capi.BundleAdjuster(device=local, profile_kernels=True)
+    if args.profile_run:   # short deterministic launch sequence for ncu: upload + two device-resident solves
+        ba.upload(windows)
+        ba.run_resident()
+        ba.run_resident()
+        print(json.dumps({"profile_run": True, "timing": ba.timing()}), flush=True)
+        return 0
+    fp64_peak = ba.probe_fp64()
+    packed = ba.prepare_batch(windows)
+
+    # ---- end to end through the C ABI with host buffers (H2D + LM + D2H in the timed region)
+    for _ in range(args.warmup):
+        ba.solve_packed(packed)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ba.solve_packed(packed)
+    barrier()
+    e2e_s = reduce(time.perf_counter() - t0, MAX)
+    t_e2e = ba.timing()
+    res = packed[2]
+    iters_step = sum(r.iterations_run[0] + r.iterations_run[1] for r in res)
+    bad = sum(1 for r in res if r.status != 0)
+
+    # ---- device-resident: inputs already in HBM
+    ba.upload(windows)
+    for _ in range(args.warmup):
+        ba.run_resident()
+    barrier()
+    dev_ms, tims = 0.0, []
+    with ClockSampler(local) as clocks:
+        for _ in range(args.steps):
+            ba.run_resident()
+            t = ba.timing()
+            tims.append(t)
+            dev_ms += t["total_ms"]
+    barrier()
+    dev_s = reduce(dev_ms * 1e-3, MAX)
+    tot_iters = reduce(sum(t["lm_iterations"] for t in tims), SUM)
+    tot_trials = reduce(sum(t["lm_trials"] for t in tims), SUM)
+    tot_edge_trials = reduce(sum(t["edge_trials"] for t in tims), SUM)
+    e2e_iters = reduce(iters_step * args.steps, SUM)
+    n_bad = reduce(bad, SUM)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    build_ms = sum(t["build_ms"] for t in tims)
+    build_n = sum(t["build_launches"] for t in tims)
+    alg_build = sum(t["alg_bytes_build"] for t in tims)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = alg_build / (build_ms * 1e-3) / 1e9 if build_ms > 0 else 0.0
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "build_kernel_traffic.json"))).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    # FP64 view of the same kernel (the binding roofline per SURVEY.md §8d): Schur + Hessian flops of one trial
+    trials_rank0 = sum(t["lm_trials"] for t in tims)
+    flops_build = flops_per_trial(windows[0]) * trials_rank0 - 40.0 * 20000 * trials_rank0
+    fp64_achieved = flops_build / (build_ms * 1e-3) / 1e12 if build_ms > 0 else 0.0
+
+    line = {"metric": METRIC, "value": tot_iters / dev_s, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(args),
+            "edges_per_s": tot_edge_trials / dev_s, "lm_trials_per_s": tot_trials / dev_s,
+            "e2e": {"value": e2e_iters / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(t_e2e["h2d_bytes"]),
+                    "d2h_bytes_per_step": int(t_e2e["d2h_bytes"]), "ms_per_step": 1e3 * e2e_s / args.steps},
+            "gpu_launches": int(sum(t["kernel_launches"] for t in tims)),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "traffic": traffic, "kernel": "k_build<MODE_BUILD> (linearise + Hessian blocks + Schur partials)",
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                         "alg_bytes_per_launch": alg_build / max(build_n, 1), "avg_launch_ms": build_ms / max(build_n, 1)},
+            "fp64": {"kernel": "k_build<MODE_BUILD>", "achieved_tflops": fp64_achieved, "peak_tflops": fp64_peak,
+                     "frac": fp64_achieved / fp64_peak if fp64_peak else None,
+                     "peak_source": "visfs_ba_probe_fp64: dependent-free DFMA loop, this process, this GPU"},
+            "kernel_ms_per_step": {k: sum(t[k] for t in tims) / args.steps for k in ("build_ms", "solve_ms", "update_ms", "other_ms")},
+            "clocks": clocks.summary(), "windows_failed": int(n_bad)}
+
+    # ---- CPU baseline (rank 0, N = 1 only) and the single-window latency cases
+    if world == 1 and not args.no_cpu:
+        from tests import oracle_api as O
+        cores = os.cpu_count() or 1
+        n_sample = max(cores, min(4 * cores, 64))
+        cpu_solve_windows(windows[:cores], cores)
+        dt, it, tr, cres = cpu_solve_windows(windows[:n_sample], cores)
+        for k in range(min(4, n_sample)):   # equal iteration / trial counts, otherwise the comparison is void
+            assert cres[k]["iterations_run"] == list(res[k].iterations_run) and cres[k]["trials_run"] == list(res[k].trials_run)
+        line["cpu_baseline"] = {"value": it / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"{n_sample} of the {args.windows} windows of one step, one window per host thread, "
+                                          f"oracle/ba_oracle.cpp (g2o-equivalent CPU port; the reference's g2o path cannot be built here)"}
+        line["single_window"] = single_window_numbers(ba, O, cores, args.quick)
+    elif world == 1:
+        line["single_window"] = single_window_numbers(ba, None, 1, args.quick)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--windows", type=int, default=512, help="windows per GPU")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--profile-run", action="store_true", help="upload + two resident solves only (for ncu)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -195,6 +195,9 @@ typedef struct visfs_ba_timing {
     int64_t edge_trials;         /* sum over trials of the active edges they linearised      */
     int64_t alg_bytes_build;     /* algorithmic bytes of all build launches   */
     int64_t alg_bytes_update;    /* algorithmic bytes of all update launches                 */
+    int64_t kernel_launches;     /* kernels launched by the last visfs_ba_run_resident       */
+    int64_t h2d_bytes;           /* bytes copied host->device by the last upload             */
+    int64_t d2h_bytes;           /* bytes copied device->host by the last run + download     */
 } visfs_ba_timing;
 
 int  visfs_ba_abi_version(void);

@@ -67,7 +67,8 @@ class Timing(C.Structure):
                 ("update_ms", C.c_double), ("other_ms", C.c_double),
                 ("build_launches", C.c_int64), ("solve_launches", C.c_int64), ("update_launches", C.c_int64),
                 ("other_launches", C.c_int64), ("lm_iterations", C.c_int64), ("lm_trials", C.c_int64),
-                ("edge_trials", C.c_int64), ("alg_bytes_build", C.c_int64), ("alg_bytes_update", C.c_int64)]
+                ("edge_trials", C.c_int64), ("alg_bytes_build", C.c_int64), ("alg_bytes_update", C.c_int64),
+                ("kernel_launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
 
 
 EXPORTS = ["visfs_ba_abi_version", "visfs_ba_create", "visfs_ba_destroy", "visfs_ba_last_error", "visfs_ba_solve",

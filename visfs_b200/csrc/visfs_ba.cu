@@ -85,6 +85,7 @@ struct visfs_ba_handle {
     size_t ev_next = 0;
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
     visfs_ba_timing timing{};
+    int64_t launches = 0, h2d_bytes = 0, d2h_bytes = 0;
 
     Batch batch{};
 
@@ -293,6 +294,8 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs) {
     CK(cudaMemcpyAsync(h->d_win.p, h->win.data(), sizeof(WinDesc) * n, cudaMemcpyHostToDevice, s));
     if (h->n_chunks) CK(cudaMemcpyAsync(h->d_chunks.p, h->chunks.data(), sizeof(Chunk) * h->n_chunks, cudaMemcpyHostToDevice, s));
 
+    h->h2d_bytes = (int64_t)(sizeof(double) * 7 * P + sizeof(double) * 3 * L + sizeof(double) * 3 * E + 2 * sizeof(int) * E + P + L + E +
+                             sizeof(WinDesc) * n + sizeof(Chunk) * h->n_chunks);
     // device-side preparation: (optional) stable sort by (window, point, pose), SoA split, CSR offsets
     const int *perm = nullptr;
     if (!all_sorted && te > 0) {
@@ -342,6 +345,7 @@ int reset_state(visfs_ba_handle *h) {
                                        h->d_in_lfix.as<uint8_t>());
     CK(cudaMemsetAsync(h->d_n_running.p, 0, sizeof(int) * 4, h->stream));
     CK(cudaGetLastError());
+    h->launches += 1;
     return VISFS_BA_OK;
 }
 
@@ -356,12 +360,14 @@ int run_structure(visfs_ba_handle *h) {
     k_struct_count<<<glm, 256, 0, s>>>(B);
     k_struct_finish<<<gw, 128, 0, s>>>(B);
     CK(cudaGetLastError());
+    h->launches += 4;
     return VISFS_BA_OK;
 }
 
 template <int MODE>
 int launch_build(visfs_ba_handle *h) {
     if (h->n_chunks == 0) return VISFS_BA_OK;
+    h->launches += 1;
     const size_t smem = sizeof(BuildSmem);
     if (h->max_pose <= 23) k_build<MODE, 1><<<h->n_chunks, kThreads, smem, h->stream>>>(h->batch);
     else k_build<MODE, 2><<<h->n_chunks, kThreads, smem, h->stream>>>(h->batch);
@@ -381,6 +387,7 @@ int enqueue_body(visfs_ba_handle *h) {
     ev = ev_begin(h, EV_OTHER);
     k_control<<<h->n_win, 32, 0, h->stream>>>(h->batch);
     ev_end(h, ev);
+    h->launches += h->n_chunks ? 3 : 2;
     return VISFS_BA_OK;
 }
 
@@ -398,6 +405,7 @@ int run_pass(visfs_ba_handle *h, int pass) {
     launch_build<MODE_INIT>(h);
     k_control_init<<<h->n_win, 32, 0, s>>>(B);
     ev_end(h, ev);
+    h->launches += 3;
     CK(cudaGetLastError());
     int *running = h->h_small.as<int>();
     int bodies = 0;
@@ -415,6 +423,7 @@ int run_pass(visfs_ba_handle *h, int pass) {
     k_end_pass<<<gw, 128, 0, s>>>(B, pass);
     if (pass == 0 && h->tot_edge > 0) k_cull<<<dim3((unsigned)h->grid_edge_x, (unsigned)h->n_win), 256, 0, s>>>(B);
     ev_end(h, ev);
+    h->launches += (pass == 0 && h->tot_edge > 0) ? 2 : 1;
     CK(cudaGetLastError());
     return VISFS_BA_OK;
 }
@@ -425,6 +434,8 @@ int run_resident(visfs_ba_handle *h) {
     CK(h->h_small.reserve(64));
     h->ev_next = 0;
     for (auto &v : h->ev_used) v.clear();
+    h->launches = 0;
+    h->d2h_bytes = 0;
     CK(cudaEventRecord(h->ev_t0, h->stream));
     int st = reset_state(h);
     if (st) return st;
@@ -441,6 +452,10 @@ int run_resident(visfs_ba_handle *h) {
 
     visfs_ba_timing &t = h->timing;
     t = visfs_ba_timing{};
+    t.kernel_launches = h->launches;
+    t.h2d_bytes = h->h2d_bytes;
+    h->d2h_bytes += (int64_t)sizeof(LMState) * h->n_win;
+    t.d2h_bytes = h->d2h_bytes;
     float ms = 0;
     cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1);
     t.total_ms = ms;
@@ -484,6 +499,9 @@ int download(visfs_ba_handle *h, int n, visfs_ba_result *res) {
     if (L) CK(cudaMemcpyAsync(ho + o_point, h->d_out_point.p, sizeof(double) * 3 * L, cudaMemcpyDeviceToHost, s));
     if (E) CK(cudaMemcpyAsync(ho + o_level, h->d_out_level.p, E, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    h->d2h_bytes += (int64_t)o_end;
+    h->timing.d2h_bytes = h->d2h_bytes;
+    h->timing.kernel_launches = h->launches + 1;
     for (int w = 0; w < n; ++w) {
         const WinDesc &d = h->win[w];
         const LMState &st = h->st_host[w];
