@@ -32,6 +32,8 @@ struct WinDesc {
     int solver, trust;
     unsigned flags;
     int large;                       // 1: block-sparse / global-memory path (P > kMaxSmallPoses)
+    int layout;                      // partial-system layout written by the build kernel (see ba_solve.cuh)
+    int n_parts;                     // partial systems k_solve adds (= n_chunks / cluster size)
     double fx, fy, cx, cy, bf, inv_pv, delta;
 };
 

@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -12,6 +13,7 @@
 
 #include "../../include/visfs_ba.h"
 #include "ba_kernels.cuh"
+#include "ba_build_ws.cuh"
 
 using namespace visfs;
 
@@ -64,7 +66,8 @@ struct visfs_ba_handle {
 
     // uploaded batch (host mirrors)
     int n_win = 0, n_chunks = 0, tot_pose = 0, tot_point = 0, tot_edge = 0, max_pose = 0, max_iter = 0;
-    bool resident = false, has_run = false, sorted = true;
+    bool resident = false, has_run = false, sorted = true, use_ws = false;
+    int cluster = 1;
     std::vector<WinDesc> win;
     std::vector<Chunk> chunks;
     std::vector<LMState> st_host;
@@ -215,26 +218,49 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs) {
     h->grid_lm_x = std::max(1, std::min((max_point + 255) / 256, 1024));
     h->grid_edge_x = std::max(1, std::min((max_edge + 255) / 256, 1024));
 
-    // chunks: about 2 CTAs per SM over the whole batch, never across windows
-    const long long target = 2LL * h->sm_count;
-    int lm_per_chunk = (int)std::max<long long>(kTileLm / 2, (tl + target - 1) / target);
+    // ---- work decomposition.  A chunk is a landmark range of one window (one CTA).  The warp-specialised build
+    // kernel runs one CTA per SM, so the number of chunks is chosen to fill whole waves of `sm_count` CTAs:
+    //   one window : up to sm_count chunks of >= 16 landmarks, clusters of up to 8 CTAs sum their partials
+    //   a batch    : c chunks per window with c in 1..16 maximising n*c / (ceil(n*c / sm_count) * sm_count)
+    h->use_ws = (max_pose <= ws::kMaxPosesWs) && !getenv("VISFS_BA_NO_WS");
+    const int sms = std::max(h->sm_count, 8);
+    int per_window = 1;
+    if (n == 1) {
+        per_window = std::max(1, std::min((max_point + kTileLm / 2 - 1) / (kTileLm / 2), sms - sms % 8));
+    } else {
+        double best = -1.0;
+        for (int c = 1; c <= 16; ++c) {
+            if (c > 1 && (max_point + c - 1) / c < kTileLm / 2) break;
+            const long long tot = (long long)n * c;
+            const double eff = (double)tot / (double)(((tot + sms - 1) / sms) * sms);
+            if (eff > best + 0.03) { best = eff; per_window = c; }
+        }
+    }
+    int cl = 1;
+    if (h->use_ws && !getenv("VISFS_BA_NO_CLUSTER")) while (cl < 8 && cl * 2 <= per_window) cl *= 2;
+    h->cluster = cl;
     h->chunks.clear();
     long long part_total = 0;
     for (int w = 0; w < n; ++w) {
         WinDesc &d = h->win[w];
         d.chunk_off = (int)h->chunks.size();
+        const int lm_per_chunk = std::max(1, (d.n_point + per_window - 1) / per_window);
         for (int l0 = 0; l0 < d.n_point; l0 += lm_per_chunk)
             h->chunks.push_back(Chunk{w, d.point_off + l0, d.point_off + std::min(d.n_point, l0 + lm_per_chunk)});
+        while (((int)h->chunks.size() - d.chunk_off) % cl != 0 || (int)h->chunks.size() == d.chunk_off)
+            h->chunks.push_back(Chunk{w, d.point_off + d.n_point, d.point_off + d.n_point});   // empty padding chunk
         d.n_chunks = (int)h->chunks.size() - d.chunk_off;
+        d.layout = h->use_ws ? 1 : 0;
+        d.n_parts = h->use_ws ? d.n_chunks / cl : d.n_chunks;
         const int Fm = std::min(d.n_pose, kMaxSmallPoses);
-        d.part_stride = std::max(Fm * (Fm - 1) / 2 * 36 + Fm * kHStride, 8);
+        d.part_stride = std::max(std::max(Fm * (Fm - 1) / 2 * 36 + Fm * kHStride, ws::part_len(Fm)), 8);
         d.part_off = part_total;
         part_total += (long long)d.part_stride * std::max(d.n_chunks, 1);
     }
     h->n_chunks = (int)h->chunks.size();
     {
         const int nmax = 6 * std::min(max_pose, kMaxSmallPoses);
-        h->solve_smem = sizeof(double) * ((size_t)nmax * (nmax + 1) / 2 + 7 * (size_t)nmax + 36 * (size_t)(nmax / 6) + 8);
+        h->solve_smem = sizeof(double) * ((size_t)nmax * (nmax + 1) / 2 + 8 * (size_t)nmax + 36 * (size_t)(nmax / 6) + 8);
     }
 
     // device buffers
@@ -368,6 +394,22 @@ template <int MODE>
 int launch_build(visfs_ba_handle *h) {
     if (h->n_chunks == 0) return VISFS_BA_OK;
     h->launches += 1;
+    if (MODE == MODE_BUILD && h->use_ws) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)h->n_chunks);
+        cfg.blockDim = dim3(ws::kThreadsWs);
+        cfg.dynamicSmemBytes = sizeof(ws::Smem);
+        cfg.stream = h->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)h->cluster;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        CK(cudaLaunchKernelEx(&cfg, ws::k_build_ws, h->batch, h->cluster));
+        return VISFS_BA_OK;
+    }
     const size_t smem = sizeof(BuildSmem);
     if (h->max_pose <= 23) k_build<MODE, 1><<<h->n_chunks, kThreads, smem, h->stream>>>(h->batch);
     else k_build<MODE, 2><<<h->n_chunks, kThreads, smem, h->stream>>>(h->batch);
@@ -563,6 +605,7 @@ int visfs_ba_create(const visfs_ba_config *cfg, visfs_ba_handle **out) {
     cudaFuncSetAttribute(k_build<MODE_INIT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_build);
     cudaFuncSetAttribute(k_build<MODE_BUILD, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_build);
     cudaFuncSetAttribute(k_update, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_update);
+    cudaFuncSetAttribute(ws::k_build_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ws::Smem));
     e = cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) {
         g_create_error = std::string("kernel image not usable on this device (built for sm_100a): ") + cudaGetErrorString(e);
