@@ -37,13 +37,21 @@ def main():
         print(f"  {k:16s} gpu {got[k]}   ref {ref[k]}")
     print("  poses", d(got["pose_tq"], ref["pose_tq"]), "points", d(got["point_xyz"], ref["point_xyz"]),
           "levels equal", bool(np.array_equal(got["edge_level"], ref["edge_level"])))
-    w = synth.config_c1()
+    import os
     ba2 = capi.BundleAdjuster(0, profile_kernels=True)
-    ba2.upload([w]); ba2.run_resident(); ba2.run_resident()
-    print("C1 timing", ba2.timing())
-    ws = synth.config_c3_windows(64)
-    ba2.upload(ws); ba2.run_resident(); ba2.run_resident()
-    print("C3x64 timing", ba2.timing())
+    keys = ("total_ms", "build_ms", "solve_ms", "update_ms", "other_ms", "lm_trials", "kernel_launches")
+    for mode in ("ws", "ws-nocluster", "v1"):
+        os.environ.pop("VISFS_BA_NO_WS", None); os.environ.pop("VISFS_BA_NO_CLUSTER", None)
+        if mode == "v1":
+            os.environ["VISFS_BA_NO_WS"] = "1"
+        if mode == "ws-nocluster":
+            os.environ["VISFS_BA_NO_CLUSTER"] = "1"
+        for name, ws in (("C1", [synth.config_c1()]), ("C2", [synth.config_c2()]), ("C3x64", synth.config_c3_windows(64)),
+                         ("C3x256", synth.config_c3_windows(256))):
+            ba2.upload(ws); ba2.run_resident(); ba2.run_resident(); ba2.run_resident()
+            t = ba2.timing()
+            print(f"{mode:13s} {name:7s}", {k: (round(t[k], 3) if isinstance(t[k], float) else t[k]) for k in keys}, flush=True)
+    os.environ.pop("VISFS_BA_NO_WS", None); os.environ.pop("VISFS_BA_NO_CLUSTER", None)
 
 
 if __name__ == "__main__":

@@ -23,9 +23,9 @@ namespace ws {
 namespace cg = cooperative_groups;
 
 constexpr int kEdgeThreads = kTileEdges;      // 160
-constexpr int kPairThreads = 256;
+constexpr int kPairThreads = 224;              // 7 warps: 12 warps per CTA = 3 per SM sub-partition (16 K registers each)
 constexpr int kThreadsWs = kEdgeThreads + kPairThreads;   // 416
-constexpr int kMaxPosesWs = 22;               // F (F + 1) / 2 <= 253 block owners
+constexpr int kMaxPosesWs = 20;               // F (F + 1) / 2 <= 210 block owners
 
 enum { BAR_PROD = 1, BAR_CONS = 2, BAR_FULL = 3, BAR_EMPTY = 5 };
 
@@ -54,7 +54,7 @@ constexpr int kStageDoubles = (int)(sizeof(Stage) / sizeof(double));
 // number of doubles of one partial system in the "all pairs" layout
 __host__ __device__ __forceinline__ int part_len(int F) { return F * (F + 1) / 2 * 36 + F * kHStride; }
 
-__global__ void __maxnreg__(152) k_build_ws(Batch B, int cluster_size) {
+__global__ void __maxnreg__(168) k_build_ws(Batch B, int cluster_size) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
     const int tid = threadIdx.x;

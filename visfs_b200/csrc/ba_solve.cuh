@@ -25,11 +25,12 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(Batch B) {
     if (st.done) return;
     const int tid = threadIdx.x;
     const int F = st.F, n = 6 * F;
-    const int ntri = n * (n + 1) / 2;
-    double *bs = S + ntri;       // [n] reduced rhs, overwritten by the solution
-    double *braw = bs + n;       // [n] raw b_p
+    const int ntri = n * (n + 1) / 2;   // row n of the packed triangle (n + 1 entries) holds the reduced rhs: the
+    double *bs = S + ntri;               // factorisation's panel solves then perform the forward substitution for free
+    double *braw = bs + n + 1;   // [n] raw b_p
     double *dinv = braw + n;     // [n] 1 / L_kk
-    double *aux = dinv + n;      // PCG vectors: r, d, q, s, x, Minv blocks
+    double *zb = dinv + n;       // [8] back-substitution scratch
+    double *aux = zb + 8;        // PCG vectors: r, d, q, s, x, Minv blocks
     __shared__ int s_ok;
     __shared__ double s_red[32];
     __shared__ unsigned char tabR[kMaxSmallPoses * (kMaxSmallPoses + 1) / 2], tabC[kMaxSmallPoses * (kMaxSmallPoses + 1) / 2];
@@ -45,17 +46,18 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(Batch B) {
     const double *part = B.part + wd.part_off;
     const int nparts = wd.n_parts;
     const size_t stride = (size_t)wd.part_stride;
+    // up to 32 independent loads in flight per entry (one CTA has to pull every partial through its own SM),
+    // added in part order
     auto part_sum = [&](int idx) {
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-        int c = 0;
-        for (; c + 3 < nparts; c += 4) {
-            s0 += part[(size_t)c * stride + idx];
-            s1 += part[(size_t)(c + 1) * stride + idx];
-            s2 += part[(size_t)(c + 2) * stride + idx];
-            s3 += part[(size_t)(c + 3) * stride + idx];
+        double s = 0.0;
+        for (int c0 = 0; c0 < nparts; c0 += 32) {
+            double v[32];
+#pragma unroll
+            for (int u = 0; u < 32; ++u) v[u] = (c0 + u < nparts) ? part[(size_t)(c0 + u) * stride + idx] : 0.0;
+#pragma unroll
+            for (int u = 0; u < 32; ++u) s += v[u];
         }
-        for (; c < nparts; ++c) s0 += part[(size_t)c * stride + idx];
-        return (s0 + s1) + (s2 + s3);
+        return s;
     };
     for (int i = tid; i < ntri; i += kSolveThreads) S[i] = 0.0;
     for (int t = tid; t < F * (F + 1) / 2; t += kSolveThreads) {   // block-pair table: t -> (rr >= cc)
@@ -104,94 +106,103 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(Batch B) {
     }
 
     if (wd.solver != 2) {
-        // ---- blocked right-looking Cholesky, 6x6 blocks
+        // ---- blocked right-looking Cholesky, 6x6 blocks, on rows 0..n (row n = rhs)
         for (int kb = 0; kb < F; ++kb) {
             const int base = 6 * kb;
             // every row owner factors the diagonal block redundantly in registers (no broadcast, no extra barrier)
-            double L[21], inv[6];
+            double L00, L10, L11, L20, L21, L22, L30, L31, L32, L33, L40, L41, L42, L43, L44, L50, L51, L52, L53, L54, L55;
+            double i0, i1, i2, i3, i4, i5;
             bool okl = true;
-            if (tid < n - base) {
-#pragma unroll
-                for (int a = 0; a < 6; ++a)
-#pragma unroll
-                    for (int c = 0; c <= a; ++c) L[a * (a + 1) / 2 + c] = S[tri(base + a, base + c)];
-#pragma unroll
-                for (int c = 0; c < 6; ++c) {
-                    double d = L[c * (c + 1) / 2 + c];
-#pragma unroll
-                    for (int k = 0; k < c; ++k) d = fma(-L[c * (c + 1) / 2 + k], L[c * (c + 1) / 2 + k], d);
-                    if (!(d > 0.0)) { okl = false; d = 1.0; }
-                    const double r = rsqrt(d);
-                    inv[c] = r;
-                    L[c * (c + 1) / 2 + c] = d * r;
-#pragma unroll
-                    for (int a = c + 1; a < 6; ++a) {
-                        double v = L[a * (a + 1) / 2 + c];
-#pragma unroll
-                        for (int k = 0; k < c; ++k) v = fma(-L[a * (a + 1) / 2 + k], L[c * (c + 1) / 2 + k], v);
-                        L[a * (a + 1) / 2 + c] = v * r;
-                    }
-                }
-                if (tid >= 6) {   // panel row r: solve x L_d^T = S[r, base..base+5]
-                    const int r = base + tid;
-                    double x[6];
-#pragma unroll
-                    for (int c = 0; c < 6; ++c) x[c] = S[tri(r, base + c)];
-#pragma unroll
-                    for (int c = 0; c < 6; ++c) {
-                        double v = x[c];
-#pragma unroll
-                        for (int k = 0; k < c; ++k) v = fma(-x[k], L[c * (c + 1) / 2 + k], v);
-                        x[c] = v * inv[c];
-                    }
-#pragma unroll
-                    for (int c = 0; c < 6; ++c) S[tri(r, base + c)] = x[c];
+            if (tid <= n - base) {
+                const double *d0 = S + tri(base, base), *d1 = S + tri(base + 1, base), *d2 = S + tri(base + 2, base);
+                const double *d3 = S + tri(base + 3, base), *d4 = S + tri(base + 4, base), *d5 = S + tri(base + 5, base);
+                double d;
+#define VISFS_PIVOT(dd, inv, diag) d = (dd); if (!(d > 0.0)) { okl = false; d = 1.0; } inv = rsqrt(d); diag = d * inv;
+                VISFS_PIVOT(d0[0], i0, L00)
+                L10 = d1[0] * i0; L20 = d2[0] * i0; L30 = d3[0] * i0; L40 = d4[0] * i0; L50 = d5[0] * i0;
+                VISFS_PIVOT(fma(-L10, L10, d1[1]), i1, L11)
+                L21 = fma(-L20, L10, d2[1]) * i1; L31 = fma(-L30, L10, d3[1]) * i1; L41 = fma(-L40, L10, d4[1]) * i1; L51 = fma(-L50, L10, d5[1]) * i1;
+                VISFS_PIVOT(fma(-L21, L21, fma(-L20, L20, d2[2])), i2, L22)
+                L32 = fma(-L31, L21, fma(-L30, L20, d3[2])) * i2; L42 = fma(-L41, L21, fma(-L40, L20, d4[2])) * i2;
+                L52 = fma(-L51, L21, fma(-L50, L20, d5[2])) * i2;
+                VISFS_PIVOT(fma(-L32, L32, fma(-L31, L31, fma(-L30, L30, d3[3]))), i3, L33)
+                L43 = fma(-L42, L32, fma(-L41, L31, fma(-L40, L30, d4[3]))) * i3;
+                L53 = fma(-L52, L32, fma(-L51, L31, fma(-L50, L30, d5[3]))) * i3;
+                VISFS_PIVOT(fma(-L43, L43, fma(-L42, L42, fma(-L41, L41, fma(-L40, L40, d4[4])))), i4, L44)
+                L54 = fma(-L53, L43, fma(-L52, L42, fma(-L51, L41, fma(-L50, L40, d5[4])))) * i4;
+                VISFS_PIVOT(fma(-L54, L54, fma(-L53, L53, fma(-L52, L52, fma(-L51, L51, fma(-L50, L50, d5[5]))))), i5, L55)
+#undef VISFS_PIVOT
+                if (tid >= 6) {   // panel row r (r == n: the rhs): solve x L_d^T = S[r, base..base+5]
+                    double *xr = S + tri(base + tid, base);
+                    const double x0 = xr[0] * i0;
+                    const double x1 = fma(-x0, L10, xr[1]) * i1;
+                    const double x2 = fma(-x1, L21, fma(-x0, L20, xr[2])) * i2;
+                    const double x3 = fma(-x2, L32, fma(-x1, L31, fma(-x0, L30, xr[3]))) * i3;
+                    const double x4 = fma(-x3, L43, fma(-x2, L42, fma(-x1, L41, fma(-x0, L40, xr[4])))) * i4;
+                    const double x5 = fma(-x4, L54, fma(-x3, L53, fma(-x2, L52, fma(-x1, L51, fma(-x0, L50, xr[5]))))) * i5;
+                    xr[0] = x0; xr[1] = x1; xr[2] = x2; xr[3] = x3; xr[4] = x4; xr[5] = x5;
                 }
             }
             __syncthreads();
-            if (tid < 6) {   // the diagonal block's factor is stored only now: nobody reads that block any more
-#pragma unroll
-                for (int a = 0; a < 6; ++a)
-                    if (a == tid) {
-#pragma unroll
-                        for (int c = 0; c <= a; ++c) S[tri(base + a, base + c)] = L[a * (a + 1) / 2 + c];
-                        dinv[base + a] = inv[a];
-                    }
-                if (tid == 0 && !okl) s_ok = 0;
+            if (tid == 0) {   // the diagonal block's factor is stored only now: nobody reads that block any more
+                double *d0 = S + tri(base, base), *d1 = S + tri(base + 1, base), *d2 = S + tri(base + 2, base);
+                double *d3 = S + tri(base + 3, base), *d4 = S + tri(base + 4, base), *d5 = S + tri(base + 5, base);
+                d0[0] = L00;
+                d1[0] = L10; d1[1] = L11;
+                d2[0] = L20; d2[1] = L21; d2[2] = L22;
+                d3[0] = L30; d3[1] = L31; d3[2] = L32; d3[3] = L33;
+                d4[0] = L40; d4[1] = L41; d4[2] = L42; d4[3] = L43; d4[4] = L44;
+                d5[0] = L50; d5[1] = L51; d5[2] = L52; d5[3] = L53; d5[4] = L54; d5[5] = L55;
+                dinv[base] = i0; dinv[base + 1] = i1; dinv[base + 2] = i2; dinv[base + 3] = i3; dinv[base + 4] = i4; dinv[base + 5] = i5;
+                if (!okl) s_ok = 0;
             }
             const int m = F - kb - 1;
             const int items = m * (m + 1) / 2 * 36;
-            for (int item = tid; item < items; item += kSolveThreads) {
-                const int blk = item / 36, q = item - blk * 36;
-                const int a = q / 6, c = q - a * 6;
-                const int r = 6 * (kb + 1 + tabR[blk]) + a, cc = 6 * (kb + 1 + tabC[blk]) + c;
-                if (cc > r) continue;
+            const int extra = 6 * m;   // the rhs row against every trailing column
+            for (int item = tid; item < items + extra; item += kSolveThreads) {
+                int r, cc;
+                if (item < items) {
+                    const int blk = item / 36, q = item - blk * 36;
+                    const int a = q / 6, c = q - a * 6;
+                    r = 6 * (kb + 1 + tabR[blk]) + a; cc = 6 * (kb + 1 + tabC[blk]) + c;
+                    if (cc > r) continue;
+                } else {
+                    r = n; cc = base + 6 + (item - items);
+                }
                 const double *lr = S + tri(r, base), *lc = S + tri(cc, base);
-                double s = 0.0;
+                double sacc = 0.0;
 #pragma unroll
-                for (int k = 0; k < 6; ++k) s = fma(lr[k], lc[k], s);
-                S[tri(r, cc)] -= s;
+                for (int k = 0; k < 6; ++k) sacc = fma(lr[k], lc[k], sacc);
+                S[tri(r, cc)] -= sacc;
             }
             __syncthreads();
         }
-        // triangular solves by warp 0 (column-oriented), x overwrites bs
-        if (tid < 32) {
-            for (int k = 0; k < n; ++k) {
-                const double xk = bs[k] * dinv[k];
-                __syncwarp();
-                if (tid == 0) bs[k] = xk;
-                for (int r = k + 1 + tid; r < n; r += 32) bs[r] = fma(-S[tri(r, k)], xk, bs[r]);
-                __syncwarp();
+        // bs now holds y = L^-1 b (row n).  Back-substitution L^T x = y, one 6-block per step: six warps form the
+        // column sums over the rows below the block, thread 0 solves the 6x6 triangle.
+        for (int kb = F - 1; kb >= 0; --kb) {
+            const int base = 6 * kb;
+            const int wid = tid >> 5, lane = tid & 31;
+            if (wid < 6) {
+                double sacc = 0.0;
+                for (int r = base + 6 + lane; r < n; r += 32) sacc = fma(S[tri(r, base + wid)], bs[r], sacc);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) sacc += __shfl_down_sync(0xffffffffu, sacc, o);
+                if (lane == 0) zb[wid] = bs[base + wid] - sacc;
             }
-            for (int k = n - 1; k >= 0; --k) {
-                const double xk = bs[k] * dinv[k];
-                __syncwarp();
-                if (tid == 0) bs[k] = xk;
-                for (int r = tid; r < k; r += 32) bs[r] = fma(-S[tri(k, r)], xk, bs[r]);
-                __syncwarp();
+            __syncthreads();
+            if (tid == 0) {
+                const double *d1 = S + tri(base + 1, base), *d2 = S + tri(base + 2, base), *d3 = S + tri(base + 3, base);
+                const double *d4 = S + tri(base + 4, base), *d5 = S + tri(base + 5, base);
+                const double x5 = zb[5] * dinv[base + 5];
+                const double x4 = fma(-d5[4], x5, zb[4]) * dinv[base + 4];
+                const double x3 = fma(-d5[3], x5, fma(-d4[3], x4, zb[3])) * dinv[base + 3];
+                const double x2 = fma(-d5[2], x5, fma(-d4[2], x4, fma(-d3[2], x3, zb[2]))) * dinv[base + 2];
+                const double x1 = fma(-d5[1], x5, fma(-d4[1], x4, fma(-d3[1], x3, fma(-d2[1], x2, zb[1])))) * dinv[base + 1];
+                const double x0 = fma(-d5[0], x5, fma(-d4[0], x4, fma(-d3[0], x3, fma(-d2[0], x2, fma(-d1[0], x1, zb[0]))))) * dinv[base];
+                bs[base] = x0; bs[base + 1] = x1; bs[base + 2] = x2; bs[base + 3] = x3; bs[base + 4] = x4; bs[base + 5] = x5;
             }
+            __syncthreads();
         }
-        __syncthreads();
     } else {
         // g2o LinearSolverPCG::solve: block-Jacobi preconditioner (inverse 6x6 diagonal blocks), x0 = 0,
         // at most n iterations; tolerance handling below.

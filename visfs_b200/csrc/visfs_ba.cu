@@ -226,7 +226,7 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs) {
     const int sms = std::max(h->sm_count, 8);
     int per_window = 1;
     if (n == 1) {
-        per_window = std::max(1, std::min((max_point + kTileLm / 2 - 1) / (kTileLm / 2), sms - sms % 8));
+        per_window = std::max(1, std::min((max_point + kTileLm / 2 - 1) / (kTileLm / 2), (sms * 7 / 8) / 4 * 4));
     } else {
         double best = -1.0;
         for (int c = 1; c <= 16; ++c) {
@@ -237,7 +237,9 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs) {
         }
     }
     int cl = 1;
-    if (h->use_ws && !getenv("VISFS_BA_NO_CLUSTER")) while (cl < 8 && cl * 2 <= per_window) cl *= 2;
+    // clusters only for the single-window latency case: 4 CTAs per cluster still fit one wave (33 clusters of 4 are
+    // co-resident at 195 KB of shared memory per CTA; clusters of 8 drop that to 15) and cut k_solve's input 4x
+    if (h->use_ws && n == 1 && !getenv("VISFS_BA_NO_CLUSTER")) while (cl < 4 && cl * 2 <= per_window) cl *= 2;
     h->cluster = cl;
     h->chunks.clear();
     long long part_total = 0;
@@ -260,7 +262,7 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs) {
     h->n_chunks = (int)h->chunks.size();
     {
         const int nmax = 6 * std::min(max_pose, kMaxSmallPoses);
-        h->solve_smem = sizeof(double) * ((size_t)nmax * (nmax + 1) / 2 + 8 * (size_t)nmax + 36 * (size_t)(nmax / 6) + 8);
+        h->solve_smem = sizeof(double) * ((size_t)nmax * (nmax + 1) / 2 + 8 * (size_t)nmax + 36 * (size_t)(nmax / 6) + 32);
     }
 
     // device buffers
@@ -605,7 +607,27 @@ int visfs_ba_create(const visfs_ba_config *cfg, visfs_ba_handle **out) {
     cudaFuncSetAttribute(k_build<MODE_INIT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_build);
     cudaFuncSetAttribute(k_build<MODE_BUILD, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_build);
     cudaFuncSetAttribute(k_update, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_update);
-    cudaFuncSetAttribute(ws::k_build_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ws::Smem));
+    e = cudaFuncSetAttribute(ws::k_build_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ws::Smem));
+    if (getenv("VISFS_BA_VERBOSE")) {
+        cudaFuncAttributes fa{};
+        cudaFuncGetAttributes(&fa, ws::k_build_ws);
+        fprintf(stderr, "[visfs_ba] k_build_ws: set smem %zu -> %s; regs %d maxThreads %d static smem %zu maxDyn %d\n", sizeof(ws::Smem),
+                cudaGetErrorString(e), fa.numRegs, fa.maxThreadsPerBlock, fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes);
+        for (int cl = 1; cl <= 8; cl *= 2) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(8 * 16); cfg.blockDim = dim3(ws::kThreadsWs); cfg.dynamicSmemBytes = sizeof(ws::Smem);
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            int nc = -1;
+            cudaError_t e2 = cudaOccupancyMaxActiveClusters(&nc, ws::k_build_ws, &cfg);
+            fprintf(stderr, "[visfs_ba]   cluster %d: max active clusters %d (%s)\n", cl, nc, cudaGetErrorString(e2));
+        }
+        cudaFuncGetAttributes(&fa, k_solve);
+        fprintf(stderr, "[visfs_ba] k_solve: regs %d maxThreads %d static smem %zu\n", fa.numRegs, fa.maxThreadsPerBlock, fa.sharedSizeBytes);
+        cudaGetLastError();
+    }
     e = cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) {
         g_create_error = std::string("kernel image not usable on this device (built for sm_100a): ") + cudaGetErrorString(e);
