@@ -198,6 +198,7 @@ typedef struct visfs_ba_timing {
     int64_t kernel_launches;     /* kernels launched by the last visfs_ba_run_resident       */
     int64_t h2d_bytes;           /* bytes copied host->device by the last upload             */
     int64_t d2h_bytes;           /* bytes copied device->host by the last run + download     */
+    int64_t solve_clocks[6];     /* window 0, last trial: SM clocks at k_solve's phase boundaries */
 } visfs_ba_timing;
 
 int  visfs_ba_abi_version(void);

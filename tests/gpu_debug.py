@@ -39,8 +39,8 @@ def main():
           "levels equal", bool(np.array_equal(got["edge_level"], ref["edge_level"])))
     import os
     ba2 = capi.BundleAdjuster(0, profile_kernels=True)
-    keys = ("total_ms", "build_ms", "solve_ms", "update_ms", "other_ms", "lm_trials", "kernel_launches")
-    for mode in ("ws", "ws-nocluster", "v1"):
+    keys = ("total_ms", "build_ms", "solve_ms", "update_ms", "other_ms", "lm_trials", "kernel_launches", "solve_clocks")
+    for mode in ("ws", "ws-nocluster"):
         os.environ.pop("VISFS_BA_NO_WS", None); os.environ.pop("VISFS_BA_NO_CLUSTER", None)
         if mode == "v1":
             os.environ["VISFS_BA_NO_WS"] = "1"

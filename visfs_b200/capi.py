@@ -68,7 +68,8 @@ class Timing(C.Structure):
                 ("build_launches", C.c_int64), ("solve_launches", C.c_int64), ("update_launches", C.c_int64),
                 ("other_launches", C.c_int64), ("lm_iterations", C.c_int64), ("lm_trials", C.c_int64),
                 ("edge_trials", C.c_int64), ("alg_bytes_build", C.c_int64), ("alg_bytes_update", C.c_int64),
-                ("kernel_launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
+                ("kernel_launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+                ("solve_clocks", C.c_int64 * 6)]
 
 
 EXPORTS = ["visfs_ba_abi_version", "visfs_ba_create", "visfs_ba_destroy", "visfs_ba_last_error", "visfs_ba_solve",
@@ -286,7 +287,7 @@ class BundleAdjuster:
     def timing(self):
         t = Timing()
         self._check(self.lib.visfs_ba_get_timing(self.h, C.byref(t)))
-        return {name: getattr(t, name) for name, _ in Timing._fields_}
+        return {name: (list(getattr(t, name)) if name == "solve_clocks" else getattr(t, name)) for name, _ in Timing._fields_}
 
     def linearize(self, w):
         keep = []

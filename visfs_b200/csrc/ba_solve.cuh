@@ -35,6 +35,8 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(Batch B) {
     __shared__ double s_red[32];
     __shared__ unsigned char tabR[kMaxSmallPoses * (kMaxSmallPoses + 1) / 2], tabC[kMaxSmallPoses * (kMaxSmallPoses + 1) / 2];
     const double lambda = (wd.trust == 0) ? (B.dbg_lambda >= 0.0 ? B.dbg_lambda : st.lambda) : 0.0;
+    long long tclk[6];
+    tclk[0] = clock64();
     if (tid == 0) s_ok = 1;
     if (n == 0) {
         if (tid == 0) { st.ok = 1; st.scale_p = 0.0; }
@@ -67,6 +69,7 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(Batch B) {
         tabC[t] = (unsigned char)(t - rr * (rr + 1) / 2);
     }
     __syncthreads();
+    tclk[1] = clock64();
     // pass 1: pair blocks (each entry of S written by exactly one thread)
     for (int idx = tid; idx < offd; idx += kSolveThreads) {
         const double v = part_sum(idx);
@@ -105,6 +108,7 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(Batch B) {
         __syncthreads();
     }
 
+    tclk[2] = clock64();
     if (wd.solver != 2) {
         // ---- blocked right-looking Cholesky, 6x6 blocks, on rows 0..n (row n = rhs)
         for (int kb = 0; kb < F; ++kb) {
@@ -177,6 +181,7 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(Batch B) {
             }
             __syncthreads();
         }
+        tclk[3] = clock64();
         // bs now holds y = L^-1 b (row n).  Back-substitution L^T x = y, one 6-block per step: six warps form the
         // column sums over the rows below the block, thread 0 solves the 6x6 triangle.
         for (int kb = F - 1; kb >= 0; --kb) {
@@ -277,6 +282,7 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(Batch B) {
         __syncthreads();
     }
 
+    tclk[4] = clock64();
     // solution checks, pose step, trial poses, scale
     double bad = 0.0;
     for (int i = tid; i < n; i += kSolveThreads) if (!isfinite(bs[i])) bad = 1.0;
@@ -302,7 +308,12 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(Batch B) {
             pose_oplus(src + p * kPoseStride, dlt, dst + p * kPoseStride);
         }
     }
-    if (tid == 0) { st.ok = ok ? 1 : 0; st.scale_p = scale; }
+    if (tid == 0) {
+        st.ok = ok ? 1 : 0; st.scale_p = scale;
+        tclk[5] = clock64();
+        if (wd.solver == 2) tclk[3] = tclk[4];
+        for (int k = 0; k < 6; ++k) st.t_solve[k] = tclk[k] - tclk[0];
+    }
 }
 
 }  // namespace visfs

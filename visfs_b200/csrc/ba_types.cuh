@@ -45,6 +45,7 @@ struct LMState {
     int F, NL, ok, fresh;            // fresh: 1 until the first trial of the pass has run
     int iterations_run[2], trials_run[2], stop[2], nF[2], nNL[2];
     int n_outliers, status, pass, err;
+    long long t_solve[6];            // k_solve phase clocks of the last trial (assemble, factor, back-subst, epilogue)
 };
 
 struct Chunk {

@@ -511,6 +511,7 @@ int run_resident(visfs_ba_handle *h) {
             *cls_ms[c] += ms;
             *cls_n[c] += 1;
         }
+    for (int k = 0; k < 6; ++k) t.solve_clocks[k] = h->st_host[0].t_solve[k];
     for (int w = 0; w < h->n_win; ++w) {
         const LMState &s = h->st_host[w];
         const WinDesc &d = h->win[w];
