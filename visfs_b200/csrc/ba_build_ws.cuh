@@ -1,18 +1,21 @@
-// ba_build_ws.cuh — warp-specialised build kernel (linearise + Hessian blocks + Schur partials), F <= 22.
+// ba_build_ws.cuh — warp-specialised build kernel (linearise + Hessian blocks + Schur partials), F <= 20.
 //
-// Same arithmetic and the same tile walk as k_build<MODE_BUILD> (ba_kernels.cuh), restructured for the SM:
-//   * 5 PRODUCER warps (160 threads, one edge each): stage A (residual, Jacobians, Huber, per-landmark
-//     H_ll / b_l, damped 3x3 inverse) and stage B (W = H_pl block, Yn = -W Dinv, H_pp_e, b_p_e, g) into one
-//     of two shared-memory stages.
-//   * 8 CONSUMER warps (256 threads): stage C.  Every block (i <= j) of the reduced camera system has a fixed
+// Same arithmetic as k_build<MODE_BUILD> (ba_kernels.cuh), restructured for the SM:
+//   * 5 PRODUCER warps (160 threads, one edge each): stage A (residual, Jacobians, Huber, per-edge H_ll / b_l
+//     terms), per-landmark sums in edge order by (landmark, entry) owner threads, stage B (damped 3x3
+//     inverse, W = H_pl block, Yn = -W Dinv, H_pp_e, b_p_e, g) into one of two shared-memory stages.  The
+//     edge records and points of the NEXT tile are prefetched into registers while the current tile is
+//     computed; tile bounds come from a table built once at upload (k_fill_tiles).
+//   * 7 CONSUMER warps (224 threads): stage C.  Every block (i <= j) of the reduced camera system has a fixed
 //     owner thread that keeps its 36 entries in registers for the whole chunk and adds Yn_i W_j^T with
 //     three chained DFMAs per entry; per-pose sums (H_pp, g, b_p) have fixed owners as well.
 //   The two roles overlap on different tiles through full / empty named barriers (bar.arrive / bar.sync),
 //   so neither the 72 accumulator registers nor the linearisation temporaries are ever live in the same
 //   thread (v1 spilled 900 B / thread to L2), and the FP64 pipe is fed by both roles at once.
-//   * Thread-block clusters: when a window is split over several chunks, the CTAs of a cluster add their
-//     partial systems through distributed shared memory in rank order and write ONE partial per cluster,
-//     so k_solve reads 8x fewer partials.  No atomics; every sum has a fixed order.
+//   12 warps = 3 per SM sub-partition (16 K registers each) at 168 registers per thread.
+//   * Thread-block clusters: when ONE window is split over many chunks, the CTAs of a cluster add their
+//     partial systems through distributed shared memory in rank order and write one partial per cluster,
+//     so k_solve reads fewer partials.  No atomics; every sum has a fixed order.
 #pragma once
 #include <cooperative_groups.h>
 #include "ba_kernels.cuh"
@@ -23,8 +26,8 @@ namespace ws {
 namespace cg = cooperative_groups;
 
 constexpr int kEdgeThreads = kTileEdges;      // 160
-constexpr int kPairThreads = 224;              // 7 warps: 12 warps per CTA = 3 per SM sub-partition (16 K registers each)
-constexpr int kThreadsWs = kEdgeThreads + kPairThreads;   // 416
+constexpr int kPairThreads = 224;
+constexpr int kThreadsWs = kEdgeThreads + kPairThreads;   // 384
 constexpr int kMaxPosesWs = 20;               // F (F + 1) / 2 <= 210 block owners
 
 enum { BAR_PROD = 1, BAR_CONS = 2, BAR_FULL = 3, BAR_EMPTY = 5 };
@@ -37,9 +40,9 @@ struct Stage {
     double W[kTileEdges * 18];
     double Yn[kTileEdges * 18];
     double H[kTileEdges * kHStride];           // H_pp_e (21, upper) | g (6) | b_p (6); stage A scratch before that
-    double lm[kTileLm * 12];                   // Dinv(6) db(3) bl(3)
+    double lm[kTileLm * 12];                   // per landmark: H_ll (6) b_l (3), summed in edge order
     short slot[kTileLm * kMaxSmallPoses];
-    int ntl, next_lt, pad0, pad1;
+    int ntl, pad0, pad1, pad2;
 };
 
 struct Smem {
@@ -53,6 +56,29 @@ constexpr int kStageDoubles = (int)(sizeof(Stage) / sizeof(double));
 
 // number of doubles of one partial system in the "all pairs" layout
 __host__ __device__ __forceinline__ int part_len(int F) { return F * (F + 1) / 2 * 36 + F * kHStride; }
+
+// what a producer thread holds for its edge of one tile
+struct EdgeRec {
+    double ou, ov, our, px, py, pz;
+    int pw, gl;
+    uint8_t lf, pf;
+};
+
+__device__ __forceinline__ void load_edge_l1(const Batch &B, const WinDesc &wd, const Tile &T, int tid, EdgeRec &r) {
+    if (tid < T.ne) {
+        const int e = T.e0 + tid;
+        r.pw = B.edge_pose[e];
+        r.gl = wd.point_off + B.edge_point[e];
+        r.ou = B.obs_u[e]; r.ov = B.obs_v[e]; r.our = B.obs_r[e];
+    }
+}
+__device__ __forceinline__ void load_edge_l2(const Batch &B, const WinDesc &wd, const Tile &T, int tid, const double *gpoint, EdgeRec &r) {
+    if (tid < T.ne) {
+        r.lf = B.lm_flags[r.gl];
+        r.pf = B.pose_flags[wd.pose_off + (r.pw & kPoseMask)];
+        r.px = gpoint[3 * (size_t)r.gl]; r.py = gpoint[3 * (size_t)r.gl + 1]; r.pz = gpoint[3 * (size_t)r.gl + 2];
+    }
+}
 
 __global__ void __maxnreg__(168) k_build_ws(Batch B, int cluster_size) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -69,6 +95,8 @@ __global__ void __maxnreg__(168) k_build_ws(Batch B, int cluster_size) {
     const int pose_off = wd.pose_off, n_pose = wd.n_pose;
     const double *__restrict__ gpose = B.pose + ((size_t)cur * B.tot_pose + pose_off) * kPoseStride;
     const double *__restrict__ gpoint = B.point + (size_t)cur * B.tot_point * 3;
+    const int tile0 = B.chunk_tile_off[blockIdx.x], ntiles = B.chunk_tile_off[blockIdx.x + 1] - tile0;
+    const Tile *__restrict__ tiles = B.tiles + tile0;
 
     for (int i = tid; i < n_pose * kPoseStride; i += kThreadsWs) sm.pose[i] = gpose[i];
     for (int i = tid; i < n_pose; i += kThreadsWs) sm.hidx[i] = B.pose_hidx[pose_off + i];
@@ -93,44 +121,33 @@ __global__ void __maxnreg__(168) k_build_ws(Batch B, int cluster_size) {
 
     if (producer) {
         // ======================================================================= producers: stages A and B
-        int t = 0, cnt_prev = 0;
-        for (int lt = ck.lm0; lt < ck.lm1; ++t) {
+        EdgeRec rec, nxt;
+        Tile T, Tn;
+        if (ntiles > 0) {
+            T = tiles[0];
+            load_edge_l1(B, wd, T, tid, rec);
+            load_edge_l2(B, wd, T, tid, gpoint, rec);
+        }
+        for (int t = 0; t < ntiles; ++t) {
             Stage &S = sm.st[t & 1];
+            const bool more = t + 1 < ntiles;
+            if (more) { Tn = tiles[t + 1]; load_edge_l1(B, wd, Tn, tid, nxt); }   // prefetch, level 1
             if (t >= 2) bar_sync(BAR_EMPTY + (t & 1), kThreadsWs);
-            const int e0 = B.lm_edge_off[lt];
-            const int lmax = min(lt + kTileLm, ck.lm1);
-            int l1;
-            {   // tile end: try the previous tile's landmark count first (uniform degree), else binary search
-                const int g = min(lt + max(cnt_prev, 1), lmax);
-                const int og = B.lm_edge_off[g] - e0;
-                const int og1 = (g < lmax) ? B.lm_edge_off[g + 1] - e0 : (kTileEdges + 1);
-                l1 = (og <= kTileEdges && og1 > kTileEdges) ? g : tile_end(B.lm_edge_off, lt, lmax, e0);
-            }
-            const int ne = min(B.lm_edge_off[l1] - e0, kTileEdges);
-            const int ntl = l1 - lt;
-            cnt_prev = ntl;
+            const int ne = T.ne, ntl = T.ntl, lt = T.lt;
             for (int i = tid; i < ntl * kMaxSmallPoses; i += kEdgeThreads) S.slot[i] = -1;
-            if (tid <= ntl) sm.lmoff[tid] = min(B.lm_edge_off[lt + tid] - e0, kTileEdges);
+            if (tid <= ntl) sm.lmoff[tid] = min(B.lm_edge_off[lt + tid] - T.e0, kTileEdges);
 
             EdgeLin lin;
             bool act = false, lmfree = false;
             int tl = 0, p = 0;
             if (tid < ne) {
-                const int e = e0 + tid;
-                const int pw = B.edge_pose[e];
-                p = pw & kPoseMask;
-                const int gl = wd.point_off + B.edge_point[e];
-                tl = gl - lt;
-                const uint8_t lf = B.lm_flags[gl];
-                const uint8_t pf = B.pose_flags[pose_off + p];
-                act = !(pw & kCulledBit) && !((lf & kFixed) && (pf & kFixed));
-                lmfree = (lf & kInHessian) != 0;
+                p = rec.pw & kPoseMask;
+                tl = rec.gl - lt;
+                act = !(rec.pw & kCulledBit) && !((rec.lf & kFixed) && (rec.pf & kFixed));
+                lmfree = (rec.lf & kInHessian) != 0;
                 double *hl = S.H + tid * kHStride;
-                if (act) {
-                    const double px = gpoint[3 * (size_t)gl], py = gpoint[3 * (size_t)gl + 1], pz = gpoint[3 * (size_t)gl + 2];
-                    edge_linearize(sm.pose + p * kPoseStride, px, py, pz, B.obs_u[e], B.obs_v[e], B.obs_r[e],
-                                   (pw & kMonoBit) != 0, K, lin);
-                }
+                if (act) edge_linearize(sm.pose + p * kPoseStride, rec.px, rec.py, rec.pz, rec.ou, rec.ov, rec.our,
+                                        (rec.pw & kMonoBit) != 0, K, lin);
                 if (act && lmfree) {
                     const double wo = lin.w * K.inv_pv;
                     const double *J = lin.Jl;
@@ -148,25 +165,14 @@ __global__ void __maxnreg__(168) k_build_ws(Batch B, int cluster_size) {
                     for (int q = 0; q < 9; ++q) hl[q] = 0.0;
                 }
             }
+            if (more) load_edge_l2(B, wd, Tn, tid, gpoint, nxt);                  // prefetch, level 2
             bar_sync(BAR_PROD, kEdgeThreads);
-            if (tid < ntl) {
-                double A[6] = {0, 0, 0, 0, 0, 0}, bl[3] = {0, 0, 0};
-                for (int s = sm.lmoff[tid]; s < sm.lmoff[tid + 1]; ++s) {
-                    const double *hl = S.H + s * kHStride;
-#pragma unroll
-                    for (int q = 0; q < 6; ++q) A[q] += hl[q];
-                    bl[0] += hl[6]; bl[1] += hl[7]; bl[2] += hl[8];
-                }
-                double *o = S.lm + tid * 12;
-                if (B.lm_flags[lt + tid] & kInHessian) {
-                    A[0] += lambda; A[3] += lambda; A[5] += lambda;
-                    inv_sym3(A, o);
-                    sym3_mul(o, bl, o + 6);
-                    o[9] = bl[0]; o[10] = bl[1]; o[11] = bl[2];
-                } else {
-#pragma unroll
-                    for (int q = 0; q < 12; ++q) o[q] = 0.0;
-                }
+            // per-landmark H_ll (6) / b_l (3): one owner thread per (landmark, entry), edges added in edge order
+            for (int task = tid; task < ntl * 9; task += kEdgeThreads) {
+                const int l = task / 9, q = task - l * 9;
+                double s = 0.0;
+                for (int e = sm.lmoff[l]; e < sm.lmoff[l + 1]; ++e) s += S.H[e * kHStride + q];
+                S.lm[l * 12 + q] = s;
             }
             bar_sync(BAR_PROD, kEdgeThreads);
             if (tid < ne && act) {
@@ -175,9 +181,15 @@ __global__ void __maxnreg__(168) k_build_ws(Batch B, int cluster_size) {
                     const double wo = lin.w * K.inv_pv;
                     double *hs = S.H + tid * kHStride;
                     double *ws = S.W + tid * 18, *ys = S.Yn + tid * 18;
-                    const double *lm = S.lm + tl * 12;
-                    double Wm[18];
+                    double Wm[18], db[3] = {0.0, 0.0, 0.0};
                     if (lmfree) {
+                        // damped inverse of the landmark block, redundantly per edge (no third barrier)
+                        const double *ls = S.lm + tl * 12;
+                        double A[6] = {ls[0] + lambda, ls[1], ls[2], ls[3] + lambda, ls[4], ls[5] + lambda};
+                        const double bl[3] = {ls[6], ls[7], ls[8]};
+                        double Di[6];
+                        inv_sym3(A, Di);
+                        sym3_mul(Di, bl, db);
                         double Aj[9];
 #pragma unroll
                         for (int q = 0; q < 9; ++q) Aj[q] = wo * lin.Jl[q];
@@ -188,9 +200,9 @@ __global__ void __maxnreg__(168) k_build_ws(Batch B, int cluster_size) {
                                 Wm[a * 3 + c] = fma(lin.Jp[a], Aj[c], fma(lin.Jp[6 + a], Aj[3 + c], lin.Jp[12 + a] * Aj[6 + c]));
 #pragma unroll
                         for (int a = 0; a < 6; ++a) {
-                            ys[a * 3 + 0] = -fma(Wm[a * 3], lm[0], fma(Wm[a * 3 + 1], lm[1], Wm[a * 3 + 2] * lm[2]));
-                            ys[a * 3 + 1] = -fma(Wm[a * 3], lm[1], fma(Wm[a * 3 + 1], lm[3], Wm[a * 3 + 2] * lm[4]));
-                            ys[a * 3 + 2] = -fma(Wm[a * 3], lm[2], fma(Wm[a * 3 + 1], lm[4], Wm[a * 3 + 2] * lm[5]));
+                            ys[a * 3 + 0] = -fma(Wm[a * 3], Di[0], fma(Wm[a * 3 + 1], Di[1], Wm[a * 3 + 2] * Di[2]));
+                            ys[a * 3 + 1] = -fma(Wm[a * 3], Di[1], fma(Wm[a * 3 + 1], Di[3], Wm[a * 3 + 2] * Di[4]));
+                            ys[a * 3 + 2] = -fma(Wm[a * 3], Di[2], fma(Wm[a * 3 + 1], Di[4], Wm[a * 3 + 2] * Di[5]));
                         }
                     } else {
 #pragma unroll
@@ -203,7 +215,7 @@ __global__ void __maxnreg__(168) k_build_ws(Batch B, int cluster_size) {
                     for (int a = 0; a < 6; ++a) {
                         const double bp = -fma(lin.Jp[a], wr0, fma(lin.Jp[6 + a], wr1, lin.Jp[12 + a] * wr2));
                         hs[27 + a] = bp;
-                        hs[21 + a] = bp - fma(Wm[a * 3], lm[6], fma(Wm[a * 3 + 1], lm[7], Wm[a * 3 + 2] * lm[8]));
+                        hs[21 + a] = bp - fma(Wm[a * 3], db[0], fma(Wm[a * 3 + 1], db[1], Wm[a * 3 + 2] * db[2]));
 #pragma unroll
                         for (int c = a; c < 6; ++c)
                             hs[hd_index(a, c)] = wo * fma(lin.Jp[a], lin.Jp[c], fma(lin.Jp[6 + a], lin.Jp[6 + c], lin.Jp[12 + a] * lin.Jp[12 + c]));
@@ -211,12 +223,12 @@ __global__ void __maxnreg__(168) k_build_ws(Batch B, int cluster_size) {
                     S.slot[tl * kMaxSmallPoses + hi] = (short)tid;
                 }
             }
-            if (tid == 0) { S.ntl = ntl; S.next_lt = l1; }
+            if (tid == 0) S.ntl = ntl;
             __threadfence_block();
             bar_arrive(BAR_FULL + (t & 1), kThreadsWs);
-            lt = l1;
+            if (more) { T = Tn; rec = nxt; }
         }
-        for (int tt = max(0, t - 2); tt < t; ++tt) bar_sync(BAR_EMPTY + (tt & 1), kThreadsWs);   // join the consumers
+        for (int tt = max(0, ntiles - 2); tt < ntiles; ++tt) bar_sync(BAR_EMPTY + (tt & 1), kThreadsWs);   // join the consumers
     } else {
         // ======================================================================= consumers: stage C
         double acc[36];   // lives only in the consumer branch: never competes with the producers' registers
@@ -228,8 +240,7 @@ __global__ void __maxnreg__(168) k_build_ws(Batch B, int cluster_size) {
             while (base + (F - i) <= pt) { base += F - i; ++i; }
             pi = i; pj = i + (pt - base);
         }
-        int t = 0;
-        for (int lt = ck.lm0; lt < ck.lm1; ++t) {
+        for (int t = 0; t < ntiles; ++t) {
             const Stage &S = sm.st[t & 1];
             bar_sync(BAR_FULL + (t & 1), kThreadsWs);
             const int ntl = S.ntl;
@@ -261,9 +272,7 @@ __global__ void __maxnreg__(168) k_build_ws(Batch B, int cluster_size) {
                     }
                 }
             }
-            const int l1 = S.next_lt;
             bar_arrive(BAR_EMPTY + (t & 1), kThreadsWs);
-            lt = l1;
         }
         // groups -> one block per owner (consumer-only barriers; the stages are no longer written)
         bar_sync(BAR_CONS, kPairThreads);

@@ -317,150 +317,9 @@ __global__ void __launch_bounds__(kThreads, PPT == 1 ? 2 : 1) k_build(Batch B) {
 #include "ba_solve.cuh"
 namespace visfs {
 
-// ------------------------------------------------------------------------------------------------
-// k_update: landmark back-substitution x_l = Dinv (b_l - sum_e W_e^T x_p), point oplus into the trial
-// buffer, robust chi2 of the trial state, and the landmark part of g2o's computeScale().
-// Same chunk / tile walk as k_build; the linearisation is recomputed instead of being stored
-// (32 B/edge re-read instead of 288 B/edge written and read back).
-// ------------------------------------------------------------------------------------------------
-struct UpdateSmem {
-    double pose[kMaxSmallPoses * kPoseStride];
-    double poseT[kMaxSmallPoses * kPoseStride];
-    double xp[kMaxSmallPoses * 6];
-    double H[kTileEdges * 9];
-    double T[kTileEdges * 3];
-    double lm[kTileLm * 12];
-    double newp[kTileLm * 3];
-    double red[32];
-    int hidx[kMaxSmallPoses];
-    int lmoff[kTileLm + 1];
-};
-
-__global__ void __launch_bounds__(kThreads, 2) k_update(Batch B) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    UpdateSmem &sm = *reinterpret_cast<UpdateSmem *>(smem_raw);
-    const int tid = threadIdx.x;
-    const Chunk ck = B.chunks[blockIdx.x];
-    const WinDesc &wd = B.win[ck.win];
-    const LMState &st = B.st[ck.win];
-    if (st.done) return;
-    const int cur = st.cur;
-    const double lambda = (wd.trust == 0) ? (B.dbg_lambda >= 0.0 ? B.dbg_lambda : st.lambda) : 0.0;
-    const Intr K = load_intr(wd);
-    const int pose_off = wd.pose_off, n_pose = wd.n_pose;
-    const double *__restrict__ gpose = B.pose + ((size_t)cur * B.tot_pose + pose_off) * kPoseStride;
-    const double *__restrict__ gposeT = B.pose + ((size_t)(1 - cur) * B.tot_pose + pose_off) * kPoseStride;
-    const double *__restrict__ gpoint = B.point + (size_t)cur * B.tot_point * 3;
-    double *__restrict__ gpointT = B.point + (size_t)(1 - cur) * B.tot_point * 3;
-    for (int i = tid; i < n_pose * kPoseStride; i += kThreads) { sm.pose[i] = gpose[i]; sm.poseT[i] = gposeT[i]; }
-    for (int i = tid; i < n_pose; i += kThreads) sm.hidx[i] = B.pose_hidx[pose_off + i];
-    for (int i = tid; i < st.F * 6; i += kThreads) sm.xp[i] = B.xp[(size_t)pose_off * 6 + i];
-    double chi_acc = 0.0, scale_acc = 0.0;
-    __syncthreads();
-
-    for (int lt = ck.lm0; lt < ck.lm1;) {
-        const int e0 = B.lm_edge_off[lt];
-        const int lmax = min(lt + kTileLm, ck.lm1);
-        const int l1 = tile_end(B.lm_edge_off, lt, lmax, e0);
-        const int ne = min(B.lm_edge_off[l1] - e0, kTileEdges);
-        const int ntl = l1 - lt;
-        if (tid <= ntl) sm.lmoff[tid] = min(B.lm_edge_off[lt + tid] - e0, kTileEdges);
-        bool act = false, mono = false;
-        int tl = 0, p = 0, hi = -1;
-        double ou = 0, ov = 0, our = 0;
-        if (tid < ne) {
-            const int e = e0 + tid;
-            const int pw = B.edge_pose[e];
-            p = pw & kPoseMask;
-            mono = (pw & kMonoBit) != 0;
-            const int gl = wd.point_off + B.edge_point[e];
-            tl = gl - lt;
-            const uint8_t lf = B.lm_flags[gl];
-            const uint8_t pf = B.pose_flags[pose_off + p];
-            act = !(pw & kCulledBit) && !((lf & kFixed) && (pf & kFixed));
-            const bool lmfree = (lf & kInHessian) != 0;
-            double *hl = sm.H + tid * 9;
-            double *ts = sm.T + tid * 3;
-            ts[0] = ts[1] = ts[2] = 0.0;
-#pragma unroll
-            for (int q = 0; q < 9; ++q) hl[q] = 0.0;
-            if (act) {
-                ou = B.obs_u[e]; ov = B.obs_v[e]; our = B.obs_r[e];
-                hi = sm.hidx[p];
-                if (lmfree) {
-                    EdgeLin lin;
-                    const double px = gpoint[3 * (size_t)gl], py = gpoint[3 * (size_t)gl + 1], pz = gpoint[3 * (size_t)gl + 2];
-                    edge_linearize(sm.pose + p * kPoseStride, px, py, pz, ou, ov, our, mono, K, lin);
-                    const double wo = lin.w * K.inv_pv;
-                    const double *J = lin.Jl;
-                    hl[0] = wo * (J[0] * J[0] + J[3] * J[3] + J[6] * J[6]);
-                    hl[1] = wo * (J[0] * J[1] + J[3] * J[4] + J[6] * J[7]);
-                    hl[2] = wo * (J[0] * J[2] + J[3] * J[5] + J[6] * J[8]);
-                    hl[3] = wo * (J[1] * J[1] + J[4] * J[4] + J[7] * J[7]);
-                    hl[4] = wo * (J[1] * J[2] + J[4] * J[5] + J[7] * J[8]);
-                    hl[5] = wo * (J[2] * J[2] + J[5] * J[5] + J[8] * J[8]);
-                    hl[6] = -wo * (J[0] * lin.r[0] + J[3] * lin.r[1] + J[6] * lin.r[2]);
-                    hl[7] = -wo * (J[1] * lin.r[0] + J[4] * lin.r[1] + J[7] * lin.r[2]);
-                    hl[8] = -wo * (J[2] * lin.r[0] + J[5] * lin.r[1] + J[8] * lin.r[2]);
-                    if (hi >= 0) {
-                        // W^T x_p = wo * Jl^T (Jp x_p)
-                        const double *x = sm.xp + hi * 6;
-                        double v[3];
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) {
-                            double a = 0.0;
-#pragma unroll
-                            for (int c = 0; c < 6; ++c) a += lin.Jp[6 * k + c] * x[c];
-                            v[k] = wo * a;
-                        }
-                        ts[0] = J[0] * v[0] + J[3] * v[1] + J[6] * v[2];
-                        ts[1] = J[1] * v[0] + J[4] * v[1] + J[7] * v[2];
-                        ts[2] = J[2] * v[0] + J[5] * v[1] + J[8] * v[2];
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        if (tid < ntl) {
-            const int gl = lt + tid;
-            const double px = gpoint[3 * (size_t)gl], py = gpoint[3 * (size_t)gl + 1], pz = gpoint[3 * (size_t)gl + 2];
-            double np0 = px, np1 = py, np2 = pz;
-            if (B.lm_flags[gl] & kInHessian) {
-                double A[6] = {0, 0, 0, 0, 0, 0}, bl[3] = {0, 0, 0}, c[3] = {0, 0, 0};
-                for (int s = sm.lmoff[tid]; s < sm.lmoff[tid + 1]; ++s) {
-                    const double *hl = sm.H + s * 9;
-#pragma unroll
-                    for (int q = 0; q < 6; ++q) A[q] += hl[q];
-                    bl[0] += hl[6]; bl[1] += hl[7]; bl[2] += hl[8];
-                    c[0] += sm.T[s * 3]; c[1] += sm.T[s * 3 + 1]; c[2] += sm.T[s * 3 + 2];
-                }
-                A[0] += lambda; A[3] += lambda; A[5] += lambda;
-                double Di[6], xl[3];
-                inv_sym3(A, Di);
-                c[0] = bl[0] - c[0]; c[1] = bl[1] - c[1]; c[2] = bl[2] - c[2];
-                sym3_mul(Di, c, xl);
-                np0 = px + xl[0]; np1 = py + xl[1]; np2 = pz + xl[2];
-                gpointT[3 * (size_t)gl] = np0; gpointT[3 * (size_t)gl + 1] = np1; gpointT[3 * (size_t)gl + 2] = np2;
-                scale_acc += xl[0] * (lambda * xl[0] + bl[0]) + xl[1] * (lambda * xl[1] + bl[1]) + xl[2] * (lambda * xl[2] + bl[2]);
-            }
-            sm.newp[tid * 3] = np0; sm.newp[tid * 3 + 1] = np1; sm.newp[tid * 3 + 2] = np2;
-        }
-        __syncthreads();
-        if (tid < ne && act) {
-            double r0, r1, r2;
-            edge_residual(sm.poseT + p * kPoseStride, sm.newp[tl * 3], sm.newp[tl * 3 + 1], sm.newp[tl * 3 + 2], ou, ov, our,
-                          mono, K, r0, r1, r2);
-            double rho, wgt;
-            huber((r0 * r0 + r1 * r1 + r2 * r2) * K.inv_pv, K.delta, rho, wgt);
-            chi_acc += rho;
-        }
-        __syncthreads();
-        lt = l1;
-    }
-    const double chi = block_sum(chi_acc, sm.red);
-    const double sc = block_sum(scale_acc, sm.red);
-    if (tid == 0) { B.part2[2 * (size_t)blockIdx.x] = chi; B.part2[2 * (size_t)blockIdx.x + 1] = sc; }
-}
+}  // namespace visfs
+#include "ba_update.cuh"
+namespace visfs {
 
 // ------------------------------------------------------------------------------------------------
 // LM control (g2o OptimizationAlgorithmLevenberg::solve / GaussNewton::solve), one warp per window
@@ -583,6 +442,37 @@ __global__ void k_lm_offsets(Batch B, int *lm_edge_off) {
         }
         lm_edge_off[wd.point_off + l] = wd.edge_off + lo;
     }
+}
+
+// ---- tile table (built once per upload): tiles of <= kTileLm landmarks and <= kTileEdges edges inside every chunk
+template <bool WRITE>
+__device__ int walk_tiles(const int *__restrict__ off, int lm0, int lm1, Tile *out) {
+    int n = 0, cnt_prev = 0;
+    for (int lt = lm0; lt < lm1;) {
+        const int e0 = off[lt];
+        const int lmax = min(lt + kTileLm, lm1);
+        const int g = min(lt + max(cnt_prev, 1), lmax);   // uniform degree: same landmark count as the previous tile
+        const int og = off[g] - e0;
+        const int og1 = (g < lmax) ? off[g + 1] - e0 : (kTileEdges + 1);
+        const int l1 = (og <= kTileEdges && og1 > kTileEdges) ? g : tile_end(off, lt, lmax, e0);
+        if (WRITE) out[n] = Tile{lt, l1 - lt, e0, min(off[l1] - e0, kTileEdges)};
+        ++n;
+        cnt_prev = l1 - lt;
+        lt = l1;
+    }
+    return n;
+}
+
+__global__ void k_count_tiles(Batch B, int *ntiles) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > B.n_chunks) return;
+    ntiles[c] = (c < B.n_chunks) ? walk_tiles<false>(B.lm_edge_off, B.chunks[c].lm0, B.chunks[c].lm1, nullptr) : 0;
+}
+
+__global__ void k_fill_tiles(Batch B, const int *tile_off, Tile *tiles) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= B.n_chunks) return;
+    walk_tiles<true>(B.lm_edge_off, B.chunks[c].lm0, B.chunks[c].lm1, tiles + tile_off[c]);
 }
 
 // per landmark: active flag, pose_active marks, degree check

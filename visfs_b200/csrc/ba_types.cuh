@@ -53,6 +53,12 @@ struct Chunk {
     int lm0, lm1;                    // global landmark range [lm0, lm1)
 };
 
+// One tile of a chunk: <= kTileLm landmarks, <= kTileEdges edges (built on the device at upload, k_fill_tiles)
+struct Tile {
+    int lt, ntl;                     // first global landmark, landmark count
+    int e0, ne;                      // first global edge, edge count
+};
+
 // All device pointers of one uploaded batch.
 struct Batch {
     int n_win, n_chunks;
@@ -77,6 +83,8 @@ struct Batch {
     double *part2;                   // [n_chunks][2] chi2 / scale partials of the update kernel
     double *xp;                      // [tot_pose][6] pose step per hessian index (window-local)
     int *n_running;                  // windows still running in the current pass
+    const Tile *tiles;               // tile table, chunk c owns tiles [chunk_tile_off[c], chunk_tile_off[c + 1])
+    const int *chunk_tile_off;       // [n_chunks + 1]
     double *dbg;                     // parity hook: k_solve dumps packed S and b_s of window 0 here (else null)
     double dbg_lambda;               // parity hook: damping override (< 0: keep the LM state's)
 };

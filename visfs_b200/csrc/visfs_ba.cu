@@ -77,9 +77,9 @@ struct visfs_ba_handle {
     // device memory
     DevBuf d_win, d_st, d_chunks, d_pose, d_point, d_pose_flags, d_lm_flags, d_pose_hidx, d_pose_active, d_point_hidx,
         d_lm_edge_off, d_obs_u, d_obs_v, d_obs_r, d_edge_pose, d_edge_point, d_edge_orig, d_covis, d_part, d_part2, d_xp,
-        d_n_running;
+        d_n_running, d_tiles, d_tile_off, d_tile_cnt;
     DevBuf d_in_pose, d_in_point, d_in_pfix, d_in_lfix, d_in_obs, d_in_epose, d_in_epoint, d_in_ekind;
-    DevBuf d_out_pose, d_out_point, d_out_level, d_tmp, d_keys, d_keys2, d_perm;
+    DevBuf d_out_pose, d_out_point, d_out_level, d_tmp, d_tmp2, d_keys, d_keys2, d_perm;
     PinBuf h_stage, h_out, h_small;
 
     // timing
@@ -171,6 +171,7 @@ Batch make_batch(visfs_ba_handle *h) {
     b.covis = h->d_covis.as<unsigned>(); b.part = h->d_part.as<double>(); b.part2 = h->d_part2.as<double>();
     b.xp = h->d_xp.as<double>(); b.n_running = h->d_n_running.as<int>();
     b.dbg = nullptr; b.dbg_lambda = -1.0;
+    b.tiles = h->d_tiles.as<Tile>(); b.chunk_tile_off = h->d_tile_off.as<int>();
     return b;
 }
 
@@ -279,6 +280,9 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs) {
     CK(h->d_part.reserve(sizeof(double) * (size_t)std::max<long long>(part_total, 8)));
     CK(h->d_part2.reserve(sizeof(double) * 2 * std::max(h->n_chunks, 1)));
     CK(h->d_xp.reserve(sizeof(double) * 6 * P)); CK(h->d_n_running.reserve(sizeof(int) * 4));
+    const size_t max_tiles = 2 * E / (kTileEdges + 1) + L / kTileLm + 2 * (size_t)h->n_chunks + 8;
+    CK(h->d_tiles.reserve(sizeof(Tile) * max_tiles));
+    CK(h->d_tile_off.reserve(sizeof(int) * (h->n_chunks + 2))); CK(h->d_tile_cnt.reserve(sizeof(int) * (h->n_chunks + 2)));
     CK(h->d_in_pose.reserve(sizeof(double) * 7 * P)); CK(h->d_in_point.reserve(sizeof(double) * 3 * L));
     CK(h->d_in_pfix.reserve(P)); CK(h->d_in_lfix.reserve(L));
     CK(h->d_in_obs.reserve(sizeof(double) * 3 * E)); CK(h->d_in_epose.reserve(sizeof(int) * E));
@@ -360,6 +364,15 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs) {
                                                           h->d_obs_v.as<double>(), h->d_obs_r.as<double>(), h->d_edge_point.as<int>());
     }
     k_lm_offsets<<<grid2(max_point + 1, n), 256, 0, s>>>(B, h->d_lm_edge_off.as<int>());
+    {   // tile table: count per chunk, exclusive scan, fill (all on the stream, no host round trip)
+        const int nc1 = h->n_chunks + 1;
+        k_count_tiles<<<(nc1 + 127) / 128, 128, 0, s>>>(B, h->d_tile_cnt.as<int>());
+        size_t tmp_bytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, h->d_tile_cnt.as<int>(), h->d_tile_off.as<int>(), nc1, s);
+        CK(h->d_tmp2.reserve(tmp_bytes));
+        CK(cub::DeviceScan::ExclusiveSum(h->d_tmp2.p, tmp_bytes, h->d_tile_cnt.as<int>(), h->d_tile_off.as<int>(), nc1, s));
+        if (h->n_chunks) k_fill_tiles<<<(h->n_chunks + 127) / 128, 128, 0, s>>>(B, h->d_tile_off.as<int>(), h->d_tiles.as<Tile>());
+    }
     CK(cudaGetLastError());
     h->resident = true;
     return VISFS_BA_OK;
@@ -426,7 +439,7 @@ int enqueue_body(visfs_ba_handle *h) {
     k_solve<<<h->n_win, kSolveThreads, h->solve_smem, h->stream>>>(h->batch);
     ev_end(h, ev);
     ev = ev_begin(h, EV_UPDATE);
-    if (h->n_chunks) k_update<<<h->n_chunks, kThreads, sizeof(UpdateSmem), h->stream>>>(h->batch);
+    if (h->n_chunks) k_update<<<h->n_chunks, kUpdThreads, sizeof(UpdateSmem), h->stream>>>(h->batch);
     ev_end(h, ev);
     ev = ev_begin(h, EV_OTHER);
     k_control<<<h->n_win, 32, 0, h->stream>>>(h->batch);
@@ -648,7 +661,7 @@ void visfs_ba_destroy(visfs_ba_handle *h) {
                       &h->d_pose_active, &h->d_point_hidx, &h->d_lm_edge_off, &h->d_obs_u, &h->d_obs_v, &h->d_obs_r, &h->d_edge_pose,
                       &h->d_edge_point, &h->d_edge_orig, &h->d_covis, &h->d_part, &h->d_part2, &h->d_xp, &h->d_n_running,
                       &h->d_in_pose, &h->d_in_point, &h->d_in_pfix, &h->d_in_lfix, &h->d_in_obs, &h->d_in_epose, &h->d_in_epoint,
-                      &h->d_in_ekind, &h->d_out_pose, &h->d_out_point, &h->d_out_level, &h->d_tmp, &h->d_keys, &h->d_keys2, &h->d_perm};
+                      &h->d_in_ekind, &h->d_out_pose, &h->d_out_point, &h->d_out_level, &h->d_tmp, &h->d_tmp2, &h->d_keys, &h->d_keys2, &h->d_perm, &h->d_tiles, &h->d_tile_off, &h->d_tile_cnt};
     for (DevBuf *b : bufs) b->release();
     h->h_stage.release(); h->h_out.release(); h->h_small.release();
     for (cudaEvent_t ev : h->ev_pool) cudaEventDestroy(ev);
