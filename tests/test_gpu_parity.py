@@ -257,3 +257,16 @@ def test_c3_batch_properties(ba):
     for g, w in zip(got, ws):
         fixed = w["pose_fixed"].astype(bool)
         assert np.array_equal(g["pose_tq"][fixed], w["pose_tq"][fixed])
+
+
+def test_pipelined_batch_groups_match_oracle(ba):
+    # >= 32 windows: visfs_ba_solve_batch cuts the batch into groups with their own streams and host threads
+    ws = [synth.make_window(5 + k % 3, 150 + 11 * k, layout="all" if k % 2 == 0 else "consecutive", views=4, seed=300 + k)
+          for k in range(70)]
+    ws[33] = rejecting_window(102, (0.3, np.deg2rad(6.0)))
+    got = ba.solve_batch(ws)
+    for k in (0, 1, 17, 33, 34, 52, 69):
+        check_solution(got[k], O.solve(ws[k]), f"pipelined window {k}")
+    t = ba.timing()
+    assert t["lm_iterations"] == sum(sum(g["iterations_run"]) for g in got)
+    assert t["h2d_bytes"] > 0 and t["d2h_bytes"] > 0

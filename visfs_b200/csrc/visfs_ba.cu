@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
@@ -91,6 +92,11 @@ struct visfs_ba_handle {
     int64_t launches = 0, h2d_bytes = 0, d2h_bytes = 0;
 
     Batch batch{};
+
+    // visfs_ba_solve_batch pipeline: the batch is cut into groups, every group has its own sub-handle (stream,
+    // device buffers, pinned staging) and host thread, so packing, H2D, the LM kernels and D2H of different groups overlap
+    std::vector<visfs_ba_handle *> subs;
+    bool is_sub = false;
 
     int fail(int status, const std::string &msg) { error = msg; return status; }
     int cuda_fail(cudaError_t e, const char *what) {
@@ -655,6 +661,8 @@ int visfs_ba_create(const visfs_ba_config *cfg, visfs_ba_handle **out) {
 
 void visfs_ba_destroy(visfs_ba_handle *h) {
     if (!h) return;
+    for (visfs_ba_handle *s : h->subs) visfs_ba_destroy(s);
+    h->subs.clear();
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     DevBuf *bufs[] = {&h->d_win, &h->d_st, &h->d_chunks, &h->d_pose, &h->d_point, &h->d_pose_flags, &h->d_lm_flags, &h->d_pose_hidx,
@@ -692,13 +700,68 @@ int visfs_ba_get_timing(const visfs_ba_handle *h, visfs_ba_timing *out) {
     return VISFS_BA_OK;
 }
 
+// How many pipeline groups a batch of n windows is cut into (1 = the plain single-stream path).
+static int pick_groups(const visfs_ba_handle *h, int n, const visfs_ba_problem *problems) {
+    if (h->is_sub || n < 32) return 1;
+    for (int w = 0; w < n; ++w)
+        if (problems[w].flags & VISFS_BA_FLAG_PARTITIONED) return 1;
+    int g = 8;
+    if (const char *e = getenv("VISFS_BA_GROUPS")) g = atoi(e);
+    const int hw = (int)std::thread::hardware_concurrency();
+    if (hw > 0) g = std::min(g, hw);
+    g = std::min(g, n / 16);
+    return std::max(g, 1);
+}
+
 int visfs_ba_solve_batch(visfs_ba_handle *h, int32_t n, const visfs_ba_problem *problems, visfs_ba_result *results) {
     if (!h) return VISFS_BA_ERR_INVALID;
-    int st = upload(h, n, problems);
-    if (st) return st;
-    st = run_resident(h);
-    if (st) return st;
-    return download(h, n, results);
+    if (n <= 0 || !problems || !results) return h->fail(VISFS_BA_ERR_INVALID, "empty batch");
+    const int groups = pick_groups(h, n, problems);
+    if (groups <= 1) {
+        int st = upload(h, n, problems);
+        if (st) return st;
+        st = run_resident(h);
+        if (st) return st;
+        return download(h, n, results);
+    }
+    while ((int)h->subs.size() < groups) {
+        visfs_ba_config cfg{};
+        cfg.abi_version = VISFS_BA_ABI_VERSION; cfg.device = h->device; cfg.profile_kernels = 0;
+        visfs_ba_handle *s = nullptr;
+        const int st = visfs_ba_create(&cfg, &s);
+        if (st != VISFS_BA_OK) return h->fail(st, std::string("pipeline sub-handle: ") + g_create_error);
+        s->is_sub = true;
+        h->subs.push_back(s);
+    }
+    h->resident = false; h->has_run = false;
+    std::vector<int> status(groups, VISFS_BA_OK);
+    std::vector<std::thread> workers;
+    const int base = n / groups, rem = n % groups;
+    int off = 0;
+    for (int g = 0; g < groups; ++g) {
+        const int cnt = base + (g < rem ? 1 : 0);
+        visfs_ba_handle *s = h->subs[g];
+        workers.emplace_back([s, cnt, off, problems, results, &status, g]() {
+            int st = upload(s, cnt, problems + off);
+            if (!st) st = run_resident(s);
+            if (!st) st = download(s, cnt, results + off);
+            status[g] = st;
+        });
+        off += cnt;
+    }
+    for (auto &t : workers) t.join();
+    visfs_ba_timing &t = h->timing;
+    t = visfs_ba_timing{};
+    for (int g = 0; g < groups; ++g) {
+        const visfs_ba_timing &u = h->subs[g]->timing;
+        t.total_ms = std::max(t.total_ms, u.total_ms);
+        t.lm_iterations += u.lm_iterations; t.lm_trials += u.lm_trials; t.edge_trials += u.edge_trials;
+        t.alg_bytes_build += u.alg_bytes_build; t.alg_bytes_update += u.alg_bytes_update;
+        t.kernel_launches += u.kernel_launches; t.h2d_bytes += u.h2d_bytes; t.d2h_bytes += u.d2h_bytes;
+    }
+    for (int g = 0; g < groups; ++g)
+        if (status[g]) return h->fail(status[g], h->subs[g]->error);
+    return VISFS_BA_OK;
 }
 
 int visfs_ba_solve(visfs_ba_handle *h, const visfs_ba_problem *problem, visfs_ba_result *result) {
