@@ -1,0 +1,137 @@
+"""GPU parity tests of the large-window path (block-skyline reduced system, ba_large.cuh) and of the landmark
+partition that the multi-GPU global BA uses: CUDA through the C ABI against the CPU oracle, same gates as
+tests/test_gpu_parity.py."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from tests import oracle_api as O
+from tests.test_gpu_parity import check_solution, rel_close
+from visfs_b200 import capi, partition, synth
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def banded(seed=71, P=40, L=1500, **kw):
+    return synth.make_window(P, L, views=6, layout="consecutive", trajectory="line", seed=seed, **kw)
+
+
+def loop(seed=72, P=48, L=2000, **kw):
+    return synth.make_window(P, L, views=7, layout="consecutive", trajectory="loop", seed=seed, **kw)
+
+
+def dense(seed=73, P=36, L=1200, **kw):
+    return synth.make_window(P, L, views=8, layout="random", trajectory="orbit", seed=seed, **kw)
+
+
+def _structure_case(ba, w, level=None):
+    cap = w["n_poses"] * (w["n_poses"] + 1) // 2
+    got, ref = ba.structure(w, level, cap), O.structure(w, level, cap)
+    for k in ("pose_hidx", "point_hidx", "edge_active", "hpl_row", "hpl_col", "schur_rows", "schur_cols"):
+        assert np.array_equal(got[k], ref[k]), f"{k} differs"
+    for k in ("n_schur_blocks", "n_free_poses", "n_free_points", "n_active_edges", "n_hpl_blocks"):
+        assert got[k] == ref[k], (k, got[k], ref[k])
+
+
+@pytest.mark.parametrize("make", [banded, loop, dense])
+def test_large_structure_bit_exact(ba, make):
+    _structure_case(ba, make(fixed_point_frac=0.2))
+
+
+def test_large_structure_with_culled_edges(ba):
+    w = loop()
+    rng = np.random.default_rng(9)
+    level = (rng.random(w["n_edges"]) < 0.3).astype(np.uint8)
+    level[w["edge_pose"] == 5] = 1
+    _structure_case(ba, w, level)
+
+
+@pytest.mark.parametrize("make", [banded, loop, dense])
+def test_large_reduced_system_matches_oracle(ba, make):
+    w = make(mono_frac=0.2, fixed_point_frac=0.1)
+    lam = 2.5
+    got, ref = ba.debug_trial(w, lam), O.reduced_system(w, lam)
+    assert got["n"] == ref["n"]
+    rel_close(got["chi2"], ref["chi2"], 1e-12, "chi2 at the input state")
+    rel_close(got["S"], ref["S"], 1e-10, "reduced camera system")
+    rel_close(got["b_s"], ref["b_s"], 1e-10, "reduced rhs")
+    rel_close(got["x_pose"], ref["x"][: ref["n"]], 1e-7, "pose step")
+    lam0 = ba.debug_trial(w, -1.0)["lambda_used"]
+    rel_close(lam0, ref["lambda_init"], 1e-12, "initial damping")
+
+
+@pytest.mark.parametrize("make", [banded, loop, dense])
+def test_large_solve_matches_oracle(ba, make):
+    w = make()
+    check_solution(ba.solve(w), O.solve(w), make.__name__)
+
+
+def test_large_solve_with_fixed_points_mono_and_no_fixed_pose(ba):
+    w = loop(seed=75, mono_frac=0.3, fixed_point_frac=0.25, root=None)
+    check_solution(ba.solve(w), O.solve(w), "loop, gauge free")
+
+
+def test_large_gauss_newton_and_single_pass(ba):
+    # Gauss-Newton has no damping: use a start inside its convergence basin, otherwise rounding decides the outcome
+    w = banded(seed=77, trust_region=1, outlier_frac=0.0, pose_noise=(0.005, np.deg2rad(0.1)), point_noise=0.01)
+    check_solution(ba.solve(w), O.solve(w), "GN")
+    w = banded(seed=83, huber_delta=0.0)
+    check_solution(ba.solve(w), O.solve(w), "no kernel")
+
+
+def test_large_rejected_steps(ba):
+    w = synth.make_window(34, 400, views=6, layout="consecutive", seed=78, pose_noise=(0.3, np.deg2rad(6.0)), point_noise=0.5,
+                          iterations=20, depth_range=(1.0, 6.0))
+    ref = O.solve_timed(w)
+    assert max(ref["trials_per_iteration"]) > 1, "window does not reject any step: pick another seed"
+    check_solution(ba.solve(w), ref, "rejecting large window")
+
+
+def test_large_degree_limit_is_reported(ba):
+    w = synth.make_window(40, 30, layout="all", seed=79)    # every landmark seen by 40 poses > 32
+    with pytest.raises(capi.BAError):
+        ba.solve(w)
+
+
+def test_small_window_through_large_path(ba, monkeypatch):
+    # the same window through both code paths (VISFS_BA_FORCE_LARGE is read at upload)
+    w = synth.make_window(8, 500, layout="all", seed=80)
+    small = ba.solve(w)
+    monkeypatch.setenv("VISFS_BA_FORCE_LARGE", "1")
+    big = ba.solve(w)
+    monkeypatch.delenv("VISFS_BA_FORCE_LARGE")
+    ref = O.solve(w)
+    check_solution(small, ref, "small path")
+    check_solution(big, ref, "large path")
+
+
+def test_partitioned_single_rank_equals_unpartitioned(ba):
+    w = loop(seed=81)
+    part = partition.partition_window(w, 1, 0)
+    got = partition.merge_results(w, [part], [ba.solve(part)])
+    check_solution(got, O.solve(w), "1-rank partition")
+
+
+def test_c5_reduced_size_properties(ba):
+    w = synth.config_c5(n_poses=120, n_points=20000)
+    g = ba.solve(w)
+    assert g["status"] == 0 and g["chi2_final"] < g["chi2_pass1"] < g["chi2_initial"]
+    assert np.isfinite(g["pose_tq"]).all() and np.isfinite(g["point_xyz"]).all()
+    fixed = w["pose_fixed"].astype(bool)
+    assert np.array_equal(g["pose_tq"][fixed], w["pose_tq"][fixed])
+
+
+@pytest.mark.skipif("torch" not in sys.modules and False, reason="")
+def test_global_ba_two_ranks_nccl():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(ROOT, "tests", "global_ba_ranks.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "GLOBAL_BA_OK" in r.stdout

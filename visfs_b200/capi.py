@@ -328,6 +328,13 @@ class BundleAdjuster:
         buf = C.create_string_buffer(unique_id, COMM_ID_BYTES)
         self._check(self.lib.visfs_ba_comm_init(self.h, n_ranks, rank, buf))
 
+    def comm_init_torch(self, dist):
+        """Bootstrap the library's NCCL communicator over an initialised torch.distributed group (plumbing only)."""
+        world, rank = dist.get_world_size(), dist.get_rank()
+        box = [self.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        self.comm_init(world, rank, box[0])
+
     def comm_unique_id(self) -> bytes:
         buf = C.create_string_buffer(COMM_ID_BYTES)
         self._check(self.lib.visfs_ba_comm_unique_id(buf))

@@ -486,7 +486,7 @@ __global__ void k_struct_lm(Batch B) {
         const uint8_t lfix = B.lm_flags[gl] & kFixed;
         bool any = false;
         const int e0 = B.lm_edge_off[gl], e1 = B.lm_edge_off[gl + 1];
-        if (e1 - e0 > kTileEdges) st.err = VISFS_BA_ERR_UNSUPPORTED;
+        if (e1 - e0 > (wd.large ? kMaxDegLarge : kTileEdges)) st.err = VISFS_BA_ERR_UNSUPPORTED;
         for (int e = e0; e < e1; ++e) {
             const int pw = B.edge_pose[e];
             if (pw & kCulledBit) continue;

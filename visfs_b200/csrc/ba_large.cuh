@@ -1,0 +1,688 @@
+// ba_large.cuh — the large-window path: windows with more free poses than the shared-memory path holds
+// (P > kMaxSmallPoses) and the rank-local part of a landmark-partitioned global BA (BASELINE configs C4 / C5).
+//
+// The reduced camera system S lives in HBM / L2 as a BLOCK SKYLINE (lower triangle, 6x6 blocks): row r keeps
+// the blocks sky_first[r] .. r.  The envelope is built on the device from the edge list once per pass
+// (g2o BlockSolver::buildStructure walks the same landmark -> pose pairs) and contains the whole fill-in of
+// the Cholesky factor, so the factorisation runs in place.  For a partitioned problem every rank builds the
+// envelope of its own landmarks, the ranks agree on it with one integer MIN allreduce, and the per-trial
+// partial systems are summed with ONE ncclAllReduce over the contiguous reduce buffer
+//      red = [ skyline blocks (n_sky x 36) | reduced rhs g (6F) | raw b_p (6F) ]
+//
+//   k_build_large   one warp per landmark, one lane per edge: linearise, H_ll / b_l by shuffle reduction,
+//                   damped 3x3 inverse, W / Yn staged in the warp's shared-memory slice, then the lanes sweep the
+//                   (pose pair, entry) items of Yn_a W_b^T and add them into the skyline with red.global.add.f64
+//                   (consecutive lanes -> consecutive addresses of one block).  H_pp, g and b_p likewise.
+//   k_solve_large   one CTA: right-looking block-skyline Cholesky (the forward substitution rides along as an
+//                   extra right-hand-side row), row-oriented back-substitution, CameraPose::update.
+//   k_update_large  one warp per landmark: back-substitution of the landmark, point oplus, chi2 of the trial.
+#pragma once
+#include "ba_kernels.cuh"
+
+namespace visfs {
+namespace lg {
+
+constexpr int kWarpsL = 8;
+constexpr int kThreadsL = kWarpsL * 32;
+constexpr int kMaxDegL = kMaxDegLarge;    // landmark degree limit of the large path (one lane per edge)
+constexpr int kSolveThreadsL = 512;
+
+struct WarpStage {
+    double W[kMaxDegL * 18];
+    double Yn[kMaxDegL * 18];
+    long long base[kMaxDegL];            // sky_off[h] - sky_first[h] of the edge's pose row (block units)
+    int hi[kMaxDegL];                    // hessian index of the edge's pose, -1: not part of the Schur products
+};
+struct BuildSmemL { WarpStage w[kWarpsL]; double red[32]; };
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// element (row c, col r) of the lower block (hb, ha), ha <= hb
+__device__ __forceinline__ size_t sky_index(long long base_b, int ha, int c, int r) {
+    return (size_t)(base_b + ha) * 36 + (size_t)(c * 6 + r);
+}
+
+// ------------------------------------------------------------------------------------------------
+// structure: envelope of the reduced camera system
+// ------------------------------------------------------------------------------------------------
+__global__ void k_sky_init(Batch B) {
+    const int F = B.st[0].F;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < F; i += gridDim.x * blockDim.x) B.sky_first[i] = i;
+}
+
+// per landmark in the Hessian: every pose (hessian index) it touches through ANY edge (g2o walks v->edges(),
+// level-1 edges included) reaches back to the smallest such index
+__global__ void k_sky_first(Batch B) {
+    const WinDesc &wd = B.win[0];
+    if (B.st[0].status != 0) return;
+    for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < wd.n_point; l += gridDim.x * blockDim.x) {
+        if (!(B.lm_flags[l] & kInHessian)) continue;
+        const int e0 = B.lm_edge_off[l], e1 = B.lm_edge_off[l + 1];
+        int mn = 0x7fffffff;
+        for (int e = e0; e < e1; ++e) {
+            const int hi = B.pose_hidx[B.edge_pose[e] & kPoseMask];
+            if (hi >= 0) mn = min(mn, hi);
+        }
+        if (mn == 0x7fffffff) continue;
+        for (int e = e0; e < e1; ++e) {
+            const int hi = B.pose_hidx[B.edge_pose[e] & kPoseMask];
+            if (hi > mn && B.sky_first[hi] > mn) atomicMin(&B.sky_first[hi], mn);
+        }
+    }
+}
+
+// one CTA: row offsets (exclusive scan of the row lengths), column counts of the envelope, n_sky -> info[0]
+__global__ void k_sky_layout(Batch B, int *col_cnt, long long *info) {
+    __shared__ long long s_carry;
+    __shared__ long long s_w[32];
+    const int F = B.st[0].F;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < F; i0 += blockDim.x) {
+        const int i = i0 + tid;
+        const long long len = (i < F) ? (long long)(i - B.sky_first[i] + 1) : 0;
+        long long v = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const long long t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+        if (lane == 31) s_w[wid] = v;
+        __syncthreads();
+        long long pre = s_carry;
+        for (int k = 0; k < wid; ++k) pre += s_w[k];
+        if (i < F) B.sky_off[i] = pre + v - len;
+        __syncthreads();
+        if (tid == 0) { long long t = 0; for (int k = 0; k < nw; ++k) t += s_w[k]; s_carry += t; }
+        __syncthreads();
+    }
+    if (tid == 0) { B.sky_off[F] = s_carry; info[0] = s_carry; info[1] = F; }
+    for (int i = tid; i <= F; i += blockDim.x) col_cnt[i] = 0;
+}
+
+// column structure of the envelope: rows r > k with sky_first[r] <= k  (count, then fill after a scan)
+__global__ void k_col_count(Batch B, int *col_cnt) {
+    const int F = B.st[0].F;
+    for (int r = blockIdx.x; r < F; r += gridDim.x)
+        for (int k = B.sky_first[r] + threadIdx.x; k < r; k += blockDim.x) atomicAdd(&col_cnt[k], 1);
+}
+__global__ void k_col_scan(Batch B, const int *col_cnt) {   // one CTA
+    __shared__ int s_carry;
+    __shared__ int s_w[32];
+    const int F = B.st[0].F;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < F; i0 += blockDim.x) {
+        const int i = i0 + tid;
+        const int len = (i < F) ? col_cnt[i] : 0;
+        int v = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+        if (lane == 31) s_w[wid] = v;
+        __syncthreads();
+        int pre = s_carry;
+        for (int k = 0; k < wid; ++k) pre += s_w[k];
+        if (i < F) B.col_ptr[i] = pre + v - len;
+        __syncthreads();
+        if (tid == 0) { int t = 0; for (int k = 0; k < nw; ++k) t += s_w[k]; s_carry += t; }
+        __syncthreads();
+    }
+    if (tid == 0) B.col_ptr[F] = s_carry;
+}
+// rows of column k in ascending order: row r lands at position (number of rows r' < r with first[r'] <= k < r').
+// One thread per (r, k) pair would need a rank; instead every column is filled by one warp scanning the candidate
+// rows k+1 .. F-1 in order (ballot compaction) — F^2 / 32 warp steps in total, once per pass.
+__global__ void k_col_fill(Batch B) {
+    const int F = B.st[0].F;
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (int k = gw; k < F; k += nw) {
+        int pos = B.col_ptr[k];
+        const int end = B.col_ptr[k + 1];
+        for (int r0 = k + 1; r0 < F && pos < end; r0 += 32) {
+            const int r = r0 + lane;
+            const bool in = (r < F) && (B.sky_first[r] <= k);
+            const unsigned m = __ballot_sync(0xffffffffu, in);
+            if (in) B.col_rows[pos + __popc(m & ((1u << lane) - 1u))] = r;
+            pos += __popc(m);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_build_large<INIT>
+//   INIT : robust chi2 of the accepted state, diag(H_pp) into hdiag (atomics), max |diag H_ll|
+//   BUILD: the whole damped Schur system into the reduce buffer
+// ------------------------------------------------------------------------------------------------
+template <bool INIT>
+__global__ void __launch_bounds__(kThreadsL) k_build_large(Batch B) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    BuildSmemL &sm = *reinterpret_cast<BuildSmemL *>(smem_raw);
+    const WinDesc &wd = B.win[0];
+    const LMState &st = B.st[0];
+    if (st.done) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cur = st.cur;
+    const double lambda = (!INIT && wd.trust == 0) ? (B.dbg_lambda >= 0.0 ? B.dbg_lambda : st.lambda) : 0.0;
+    const Intr K = load_intr(wd);
+    const double *__restrict__ gpose = B.pose + (size_t)cur * B.tot_pose * kPoseStride;
+    const double *__restrict__ gpoint = B.point + (size_t)cur * B.tot_point * 3;
+    double *__restrict__ sky = B.red;
+    double *__restrict__ gvec = B.red + B.red_g_off;
+    double *__restrict__ bpvec = B.red + B.red_bp_off;
+    WarpStage &S = sm.w[warp];
+    double chi_acc = 0.0, maxd = 0.0;
+
+    for (int l = blockIdx.x * kWarpsL + warp; l < wd.n_point; l += gridDim.x * kWarpsL) {
+        const int e0 = B.lm_edge_off[l];
+        const int d = min(B.lm_edge_off[l + 1] - e0, kMaxDegL);
+        if (d <= 0) continue;
+        const uint8_t lf = B.lm_flags[l];
+        const bool lmfree = (lf & kInHessian) != 0;
+        bool act = false;
+        int hi = -1;
+        EdgeLin lin;
+        if (lane < d) {
+            const int e = e0 + lane;
+            const int pw = B.edge_pose[e];
+            const int p = pw & kPoseMask;
+            const uint8_t pf = B.pose_flags[p];
+            act = !(pw & kCulledBit) && !((lf & kFixed) && (pf & kFixed));
+            if (act) {
+                hi = B.pose_hidx[p];
+                edge_linearize(gpose + (size_t)p * kPoseStride, gpoint[3 * (size_t)l], gpoint[3 * (size_t)l + 1],
+                               gpoint[3 * (size_t)l + 2], B.obs_u[e], B.obs_v[e], B.obs_r[e], (pw & kMonoBit) != 0, K, lin);
+                if (INIT) chi_acc += lin.rho;
+            }
+        }
+        const double wo = act ? lin.w * K.inv_pv : 0.0;
+        double hl[9];
+        if (act && lmfree) {
+            const double *J = lin.Jl;
+            hl[0] = wo * fma(J[0], J[0], fma(J[3], J[3], J[6] * J[6]));
+            hl[1] = wo * fma(J[0], J[1], fma(J[3], J[4], J[6] * J[7]));
+            hl[2] = wo * fma(J[0], J[2], fma(J[3], J[5], J[6] * J[8]));
+            hl[3] = wo * fma(J[1], J[1], fma(J[4], J[4], J[7] * J[7]));
+            hl[4] = wo * fma(J[1], J[2], fma(J[4], J[5], J[7] * J[8]));
+            hl[5] = wo * fma(J[2], J[2], fma(J[5], J[5], J[8] * J[8]));
+            hl[6] = -wo * fma(J[0], lin.r[0], fma(J[3], lin.r[1], J[6] * lin.r[2]));
+            hl[7] = -wo * fma(J[1], lin.r[0], fma(J[4], lin.r[1], J[7] * lin.r[2]));
+            hl[8] = -wo * fma(J[2], lin.r[0], fma(J[5], lin.r[1], J[8] * lin.r[2]));
+        } else {
+#pragma unroll
+            for (int q = 0; q < 9; ++q) hl[q] = 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < (INIT ? 6 : 9); ++q) hl[q] = warp_sum(hl[q]);
+
+        if (INIT) {
+            if (lmfree) maxd = fmax(maxd, fmax(fabs(hl[0]), fmax(fabs(hl[3]), fabs(hl[5]))));
+            if (act && hi >= 0) {
+#pragma unroll
+                for (int a = 0; a < 6; ++a)
+                    atomicAdd(&B.hdiag[6 * (size_t)hi + a],
+                              wo * fma(lin.Jp[a], lin.Jp[a], fma(lin.Jp[6 + a], lin.Jp[6 + a], lin.Jp[12 + a] * lin.Jp[12 + a])));
+            }
+            continue;
+        }
+
+        // damped inverse of the landmark block (every lane, redundantly) and Dinv b_l
+        double Di[6], db[3] = {0.0, 0.0, 0.0};
+        if (lmfree) {
+            const double A[6] = {hl[0] + lambda, hl[1], hl[2], hl[3] + lambda, hl[4], hl[5] + lambda};
+            const double bl[3] = {hl[6], hl[7], hl[8]};
+            inv_sym3(A, Di);
+            sym3_mul(Di, bl, db);
+        }
+        int myhi = -1;
+        if (act && hi >= 0) {
+            const long long base = B.sky_off[hi] - B.sky_first[hi];
+            double Wm[18];
+            if (lmfree) {
+                double Aj[9];
+#pragma unroll
+                for (int q = 0; q < 9; ++q) Aj[q] = wo * lin.Jl[q];
+#pragma unroll
+                for (int a = 0; a < 6; ++a)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+                        Wm[a * 3 + c] = fma(lin.Jp[a], Aj[c], fma(lin.Jp[6 + a], Aj[3 + c], lin.Jp[12 + a] * Aj[6 + c]));
+                double *ws = S.W + lane * 18, *ys = S.Yn + lane * 18;
+#pragma unroll
+                for (int a = 0; a < 6; ++a) {
+                    ws[a * 3] = Wm[a * 3]; ws[a * 3 + 1] = Wm[a * 3 + 1]; ws[a * 3 + 2] = Wm[a * 3 + 2];
+                    ys[a * 3 + 0] = -fma(Wm[a * 3], Di[0], fma(Wm[a * 3 + 1], Di[1], Wm[a * 3 + 2] * Di[2]));
+                    ys[a * 3 + 1] = -fma(Wm[a * 3], Di[1], fma(Wm[a * 3 + 1], Di[3], Wm[a * 3 + 2] * Di[4]));
+                    ys[a * 3 + 2] = -fma(Wm[a * 3], Di[2], fma(Wm[a * 3 + 1], Di[4], Wm[a * 3 + 2] * Di[5]));
+                }
+                S.base[lane] = base;
+                myhi = hi;
+            } else {
+#pragma unroll
+                for (int q = 0; q < 18; ++q) Wm[q] = 0.0;
+            }
+            // per-pose sums: H_pp_e into the diagonal block (lower half), g = b_p_e - W Dinv b_l, raw b_p_e
+            const double wr0 = wo * lin.r[0], wr1 = wo * lin.r[1], wr2 = wo * lin.r[2];
+            double *dblk = sky + (size_t)(base + hi) * 36;
+#pragma unroll
+            for (int a = 0; a < 6; ++a) {
+                const double bp = -fma(lin.Jp[a], wr0, fma(lin.Jp[6 + a], wr1, lin.Jp[12 + a] * wr2));
+                atomicAdd(&bpvec[6 * (size_t)hi + a], bp);
+                atomicAdd(&gvec[6 * (size_t)hi + a], bp - fma(Wm[a * 3], db[0], fma(Wm[a * 3 + 1], db[1], Wm[a * 3 + 2] * db[2])));
+#pragma unroll
+                for (int c = a; c < 6; ++c)
+                    atomicAdd(&dblk[c * 6 + a],
+                              wo * fma(lin.Jp[a], lin.Jp[c], fma(lin.Jp[6 + a], lin.Jp[6 + c], lin.Jp[12 + a] * lin.Jp[12 + c])));
+            }
+        }
+        if (lane < d) S.hi[lane] = myhi;
+        __syncwarp();
+        if (lmfree) {
+            // Schur products: for a <= b (ascending pose => ascending hessian index) block (h_a, h_b) += Yn_a W_b^T,
+            // stored as the lower block (h_b, h_a): element (r, c) of the product sits at row c, column r
+            for (int a = 0; a < d; ++a) {
+                const int ha = S.hi[a];
+                if (ha < 0) continue;
+                const double *ya = S.Yn + a * 18;
+                const int items = (d - a) * 36;
+                for (int it = lane; it < items; it += 32) {
+                    const int bo = it / 36, q = it - bo * 36;
+                    const int b = a + bo;
+                    if (S.hi[b] < 0) continue;
+                    const int r = q / 6, c = q - r * 6;
+                    if (bo == 0 && c < r) continue;            // diagonal block: lower half only
+                    const double *wb = S.W + b * 18 + c * 3;
+                    const double v = fma(ya[r * 3], wb[0], fma(ya[r * 3 + 1], wb[1], ya[r * 3 + 2] * wb[2]));
+                    atomicAdd(&sky[sky_index(S.base[b], ha, c, r)], v);
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (INIT) {
+        const double chi = block_sum(chi_acc, sm.red);
+        const double md = block_max(maxd, sm.red);
+        if (tid == 0) {
+            B.part2[2 * (size_t)blockIdx.x] = chi;
+            B.part2[2 * (size_t)blockIdx.x + 1] = md;
+        }
+    }
+}
+
+// sum / max of the per-CTA partials in CTA order -> out[0], out[1]   (one CTA)
+__global__ void k_fold_part2(Batch B, int n, int second_is_max, double *out) {
+    __shared__ double red[32];
+    double a = 0.0, b = 0.0;
+    if (B.st[0].done) return;
+    // fixed order: thread t owns the partials t, t + blockDim, ...
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        a += B.part2[2 * (size_t)i];
+        b = second_is_max ? fmax(b, B.part2[2 * (size_t)i + 1]) : b + B.part2[2 * (size_t)i + 1];
+    }
+    const double sa = block_sum(a, red);
+    const double sb = second_is_max ? block_max(b, red) : block_sum(b, red);
+    if (threadIdx.x == 0) { out[0] = sa; out[1] = sb; }
+}
+
+// lambda init + pass bookkeeping (k_control_init of the small path): scal = {chi2, max |diag H_ll|}
+__global__ void k_control_init_large(Batch B, const double *scal) {
+    const WinDesc &wd = B.win[0];
+    LMState &st = B.st[0];
+    if (st.done) return;
+    const int F = st.F;
+    double md = 0.0;
+    for (int i = threadIdx.x; i < 6 * F; i += blockDim.x) md = fmax(md, fabs(B.hdiag[i]));
+    __shared__ double red[32];
+    md = block_max(md, red);
+    if (threadIdx.x == 0) {
+        md = fmax(md, scal[1]);
+        const double chi = scal[0];
+        st.cur_chi = chi;
+        st.chi_last_trial = chi;
+        if (st.pass == 0) st.chi_initial = chi;
+        st.lambda = 1e-5 * md;
+        st.ni = 2.0;
+        st.iter = 0; st.qmax = 0;
+        st.pcg_residual = -1.0;
+        if (st.F + st.NL == 0) finish_pass(st, VISFS_BA_STOP_EMPTY, B.n_running);
+        else if (wd.max_iter <= 0) finish_pass(st, VISFS_BA_STOP_ITERATIONS, B.n_running);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_solve_large: in-place block-skyline Cholesky of the damped reduced system + solve + pose update
+// ------------------------------------------------------------------------------------------------
+struct Chol6 {
+    double L10, L20, L21, L30, L31, L32, L40, L41, L42, L43, L50, L51, L52, L53, L54;
+    double L00, L11, L22, L33, L44, L55;
+    double i0, i1, i2, i3, i4, i5;
+    bool ok;
+};
+
+// Cholesky of a 6x6 block given by its lower half d[c*6 + a] (row c, column a), `lam` added to the diagonal
+__device__ __forceinline__ void chol6(const double *d, double lam, Chol6 &f) {
+    f.ok = true;
+    double v;
+#define VISFS_PIV(expr, inv, diag) v = (expr); if (!(v > 0.0)) { f.ok = false; v = 1.0; } inv = rsqrt(v); diag = v * inv;
+    VISFS_PIV(d[0] + lam, f.i0, f.L00)
+    f.L10 = d[6] * f.i0; f.L20 = d[12] * f.i0; f.L30 = d[18] * f.i0; f.L40 = d[24] * f.i0; f.L50 = d[30] * f.i0;
+    VISFS_PIV(fma(-f.L10, f.L10, d[7] + lam), f.i1, f.L11)
+    f.L21 = fma(-f.L20, f.L10, d[13]) * f.i1; f.L31 = fma(-f.L30, f.L10, d[19]) * f.i1;
+    f.L41 = fma(-f.L40, f.L10, d[25]) * f.i1; f.L51 = fma(-f.L50, f.L10, d[31]) * f.i1;
+    VISFS_PIV(fma(-f.L21, f.L21, fma(-f.L20, f.L20, d[14] + lam)), f.i2, f.L22)
+    f.L32 = fma(-f.L31, f.L21, fma(-f.L30, f.L20, d[20])) * f.i2;
+    f.L42 = fma(-f.L41, f.L21, fma(-f.L40, f.L20, d[26])) * f.i2;
+    f.L52 = fma(-f.L51, f.L21, fma(-f.L50, f.L20, d[32])) * f.i2;
+    VISFS_PIV(fma(-f.L32, f.L32, fma(-f.L31, f.L31, fma(-f.L30, f.L30, d[21] + lam))), f.i3, f.L33)
+    f.L43 = fma(-f.L42, f.L32, fma(-f.L41, f.L31, fma(-f.L40, f.L30, d[27]))) * f.i3;
+    f.L53 = fma(-f.L52, f.L32, fma(-f.L51, f.L31, fma(-f.L50, f.L30, d[33]))) * f.i3;
+    VISFS_PIV(fma(-f.L43, f.L43, fma(-f.L42, f.L42, fma(-f.L41, f.L41, fma(-f.L40, f.L40, d[28] + lam)))), f.i4, f.L44)
+    f.L54 = fma(-f.L53, f.L43, fma(-f.L52, f.L42, fma(-f.L51, f.L41, fma(-f.L50, f.L40, d[34])))) * f.i4;
+    VISFS_PIV(fma(-f.L54, f.L54, fma(-f.L53, f.L53, fma(-f.L52, f.L52, fma(-f.L51, f.L51, fma(-f.L50, f.L50, d[35] + lam))))),
+              f.i5, f.L55)
+#undef VISFS_PIV
+}
+
+// x L^T = v  (one row against the factor of the diagonal block), in place
+__device__ __forceinline__ void row_solve6(const Chol6 &f, double *x) {
+    const double x0 = x[0] * f.i0;
+    const double x1 = fma(-x0, f.L10, x[1]) * f.i1;
+    const double x2 = fma(-x1, f.L21, fma(-x0, f.L20, x[2])) * f.i2;
+    const double x3 = fma(-x2, f.L32, fma(-x1, f.L31, fma(-x0, f.L30, x[3]))) * f.i3;
+    const double x4 = fma(-x3, f.L43, fma(-x2, f.L42, fma(-x1, f.L41, fma(-x0, f.L40, x[4])))) * f.i4;
+    const double x5 = fma(-x4, f.L54, fma(-x3, f.L53, fma(-x2, f.L52, fma(-x1, f.L51, fma(-x0, f.L50, x[5]))))) * f.i5;
+    x[0] = x0; x[1] = x1; x[2] = x2; x[3] = x3; x[4] = x4; x[5] = x5;
+}
+
+__global__ void __launch_bounds__(kSolveThreadsL) k_solve_large(Batch B) {
+    const WinDesc &wd = B.win[0];
+    LMState &st = B.st[0];
+    if (st.done) return;
+    const int tid = threadIdx.x;
+    const int F = st.F, n = 6 * F;
+    const double lambda = (wd.trust == 0) ? (B.dbg_lambda >= 0.0 ? B.dbg_lambda : st.lambda) : 0.0;
+    __shared__ int s_ok;
+    __shared__ double s_red[32];
+    __shared__ double s_x[6];
+    if (tid == 0) s_ok = 1;
+    if (n == 0) {
+        if (tid == 0) { st.ok = 1; st.scale_p = 0.0; }
+        return;
+    }
+    double *__restrict__ sky = B.red;
+    double *__restrict__ y = B.red + B.red_g_off;          // rhs -> y -> x, in place
+    const double *__restrict__ braw = B.red + B.red_bp_off;
+    const int *__restrict__ first = B.sky_first;
+    const long long *__restrict__ off = B.sky_off;
+    __syncthreads();
+
+    // ---- factorisation, one block column per step
+    for (int k = 0; k < F; ++k) {
+        const int c0 = B.col_ptr[k], m = B.col_ptr[k + 1] - c0;
+        const int *rows = B.col_rows + c0;
+        double *dk = sky + (size_t)(off[k] + (k - first[k])) * 36;
+        Chol6 f;
+        const int ntask = 6 * m + 1;
+        if (tid < ntask) chol6(dk, lambda, f);   // every task owner factors the diagonal block redundantly
+        for (int t = tid; t < ntask; t += kSolveThreadsL) {
+            if (t < 6 * m) {                 // panel row: block L_rk, row a
+                const int r = rows[t / 6], a = t - (t / 6) * 6;
+                double *x = sky + (size_t)(off[r] + (k - first[r])) * 36 + a * 6;
+                double xv[6] = {x[0], x[1], x[2], x[3], x[4], x[5]};
+                row_solve6(f, xv);
+#pragma unroll
+                for (int q = 0; q < 6; ++q) x[q] = xv[q];
+            } else {                         // forward substitution of the rhs: y_k = L_kk^-1 b_k
+                double xv[6] = {y[6 * k], y[6 * k + 1], y[6 * k + 2], y[6 * k + 3], y[6 * k + 4], y[6 * k + 5]};
+                row_solve6(f, xv);           // (row vector times L^-T) == L^-1 applied to the column
+#pragma unroll
+                for (int q = 0; q < 6; ++q) { y[6 * k + q] = xv[q]; s_x[q] = xv[q]; }
+                if (!f.ok) s_ok = 0;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {   // store the factor of the diagonal block (lower half + inverse pivots on demand)
+            dk[0] = f.L00;
+            dk[6] = f.L10; dk[7] = f.L11;
+            dk[12] = f.L20; dk[13] = f.L21; dk[14] = f.L22;
+            dk[18] = f.L30; dk[19] = f.L31; dk[20] = f.L32; dk[21] = f.L33;
+            dk[24] = f.L40; dk[25] = f.L41; dk[26] = f.L42; dk[27] = f.L43; dk[28] = f.L44;
+            dk[30] = f.L50; dk[31] = f.L51; dk[32] = f.L52; dk[33] = f.L53; dk[34] = f.L54; dk[35] = f.L55;
+        }
+        // rhs update: b_r -= L_rk y_k, one thread per (row block, row)
+        for (int t = tid; t < 6 * m; t += kSolveThreadsL) {
+            const int r = rows[t / 6], a = t - (t / 6) * 6;
+            const double *x = sky + (size_t)(off[r] + (k - first[r])) * 36 + a * 6;
+            double s = 0.0;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) s = fma(x[q], s_x[q], s);
+            y[6 * r + a] -= s;
+        }
+        // trailing update: A_rc -= L_rk L_ck^T for r >= c in the column structure (all inside the envelope)
+        const int pairs = m * (m + 1) / 2;
+        for (int item = tid; item < pairs * 36; item += kSolveThreadsL) {
+            const int pr = item / 36, q = item - pr * 36;
+            // pr -> (ri >= ci): ri = floor((sqrt(8 pr + 1) - 1) / 2)
+            int ri = (int)((sqrt(8.0 * (double)pr + 1.0) - 1.0) * 0.5);
+            while ((ri + 1) * (ri + 2) / 2 <= pr) ++ri;
+            while (ri * (ri + 1) / 2 > pr) --ri;
+            const int ci = pr - ri * (ri + 1) / 2;
+            const int a = q / 6, c = q - a * 6;
+            if (ri == ci && c > a) continue;
+            const int r = rows[ri], cc = rows[ci];
+            const double *lr = sky + (size_t)(off[r] + (k - first[r])) * 36 + a * 6;
+            const double *lc = sky + (size_t)(off[cc] + (k - first[cc])) * 36 + c * 6;
+            double s = 0.0;
+#pragma unroll
+            for (int u = 0; u < 6; ++u) s = fma(lr[u], lc[u], s);
+            sky[(size_t)(off[r] + (cc - first[r])) * 36 + a * 6 + c] -= s;
+        }
+        __syncthreads();
+    }
+
+    // ---- back-substitution L^T x = y, row-oriented: x_r = L_rr^-T y_r, then y_c -= L_rc^T x_r for the row's blocks
+    for (int r = F - 1; r >= 0; --r) {
+        const double *dr = sky + (size_t)(off[r] + (r - first[r])) * 36;
+        if (tid == 0) {
+            double x5 = y[6 * r + 5] / dr[35];
+            double x4 = (y[6 * r + 4] - dr[34] * x5) / dr[28];
+            double x3 = (y[6 * r + 3] - dr[33] * x5 - dr[27] * x4) / dr[21];
+            double x2 = (y[6 * r + 2] - dr[32] * x5 - dr[26] * x4 - dr[20] * x3) / dr[14];
+            double x1 = (y[6 * r + 1] - dr[31] * x5 - dr[25] * x4 - dr[19] * x3 - dr[13] * x2) / dr[7];
+            double x0 = (y[6 * r] - dr[30] * x5 - dr[24] * x4 - dr[18] * x3 - dr[12] * x2 - dr[6] * x1) / dr[0];
+            y[6 * r] = x0; y[6 * r + 1] = x1; y[6 * r + 2] = x2; y[6 * r + 3] = x3; y[6 * r + 4] = x4; y[6 * r + 5] = x5;
+            s_x[0] = x0; s_x[1] = x1; s_x[2] = x2; s_x[3] = x3; s_x[4] = x4; s_x[5] = x5;
+        }
+        __syncthreads();
+        const int f0 = first[r], len = r - f0;
+        const double *rowblk = sky + (size_t)off[r] * 36;
+        for (int t = tid; t < 6 * len; t += kSolveThreadsL) {
+            const int cb = t / 6, a = t - cb * 6;        // column block f0 + cb, column a inside it
+            const double *blk = rowblk + (size_t)cb * 36;
+            double s = 0.0;
+#pragma unroll
+            for (int u = 0; u < 6; ++u) s = fma(blk[u * 6 + a], s_x[u], s);
+            y[6 * (f0 + cb) + a] -= s;
+        }
+        __syncthreads();
+    }
+
+    // ---- solution checks, pose step, trial poses, pose part of g2o's computeScale
+    double bad = 0.0;
+    for (int i = tid; i < n; i += kSolveThreadsL) if (!isfinite(y[i])) bad = 1.0;
+    const double anybad = block_sum(bad, s_red);
+    const bool ok = (s_ok != 0) && (anybad == 0.0);
+    __syncthreads();
+    double sc = 0.0;
+    for (int i = tid; i < n; i += kSolveThreadsL) {
+        const double x = ok ? y[i] : 0.0;
+        B.xp[i] = x;
+        sc += x * (lambda * x + braw[i]);
+    }
+    const double scale = block_sum(sc, s_red);
+    const int cur = st.cur;
+    const double *src = B.pose + (size_t)cur * B.tot_pose * kPoseStride;
+    double *dst = B.pose + (size_t)(1 - cur) * B.tot_pose * kPoseStride;
+    for (int p = tid; p < wd.n_pose; p += kSolveThreadsL) {
+        const int hi = B.pose_hidx[p];
+        if (hi >= 0) {
+            double dlt[6];
+            for (int a = 0; a < 6; ++a) dlt[a] = ok ? y[6 * hi + a] : 0.0;
+            pose_oplus(src + (size_t)p * kPoseStride, dlt, dst + (size_t)p * kPoseStride);
+        }
+    }
+    if (tid == 0) { st.ok = ok ? 1 : 0; st.scale_p = scale; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_update_large: landmark back-substitution, point oplus, chi2 of the trial state
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreadsL) k_update_large(Batch B) {
+    __shared__ double red[32];
+    const WinDesc &wd = B.win[0];
+    const LMState &st = B.st[0];
+    if (st.done) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cur = st.cur;
+    const double lambda = (wd.trust == 0) ? (B.dbg_lambda >= 0.0 ? B.dbg_lambda : st.lambda) : 0.0;
+    const Intr K = load_intr(wd);
+    const double *__restrict__ gpose = B.pose + (size_t)cur * B.tot_pose * kPoseStride;
+    const double *__restrict__ gposeT = B.pose + (size_t)(1 - cur) * B.tot_pose * kPoseStride;
+    const double *__restrict__ gpoint = B.point + (size_t)cur * B.tot_point * 3;
+    double *__restrict__ gpointT = B.point + (size_t)(1 - cur) * B.tot_point * 3;
+    double chi_acc = 0.0, scale_acc = 0.0;
+
+    for (int l = blockIdx.x * kWarpsL + warp; l < wd.n_point; l += gridDim.x * kWarpsL) {
+        const int e0 = B.lm_edge_off[l];
+        const int d = min(B.lm_edge_off[l + 1] - e0, kMaxDegL);
+        if (d <= 0) continue;
+        const uint8_t lf = B.lm_flags[l];
+        const bool lmfree = (lf & kInHessian) != 0;
+        const double px = gpoint[3 * (size_t)l], py = gpoint[3 * (size_t)l + 1], pz = gpoint[3 * (size_t)l + 2];
+        bool act = false, mono = false;
+        int p = 0;
+        double ou = 0, ov = 0, our = 0;
+        double hl[12];
+#pragma unroll
+        for (int q = 0; q < 12; ++q) hl[q] = 0.0;
+        if (lane < d) {
+            const int e = e0 + lane;
+            const int pw = B.edge_pose[e];
+            p = pw & kPoseMask;
+            mono = (pw & kMonoBit) != 0;
+            act = !(pw & kCulledBit) && !((lf & kFixed) && (B.pose_flags[p] & kFixed));
+            if (act) {
+                ou = B.obs_u[e]; ov = B.obs_v[e]; our = B.obs_r[e];
+                if (lmfree) {
+                    double r[3], J[9], v[3], w;
+                    const int hi = B.pose_hidx[p];
+                    edge_linearize_jx(gpose + (size_t)p * kPoseStride, px, py, pz, ou, ov, our, mono, K,
+                                      hi >= 0 ? B.xp + 6 * (size_t)hi : nullptr, r, J, v, w);
+                    const double wo = w * K.inv_pv;
+                    hl[0] = wo * fma(J[0], J[0], fma(J[3], J[3], J[6] * J[6]));
+                    hl[1] = wo * fma(J[0], J[1], fma(J[3], J[4], J[6] * J[7]));
+                    hl[2] = wo * fma(J[0], J[2], fma(J[3], J[5], J[6] * J[8]));
+                    hl[3] = wo * fma(J[1], J[1], fma(J[4], J[4], J[7] * J[7]));
+                    hl[4] = wo * fma(J[1], J[2], fma(J[4], J[5], J[7] * J[8]));
+                    hl[5] = wo * fma(J[2], J[2], fma(J[5], J[5], J[8] * J[8]));
+                    hl[6] = -wo * fma(J[0], r[0], fma(J[3], r[1], J[6] * r[2]));
+                    hl[7] = -wo * fma(J[1], r[0], fma(J[4], r[1], J[7] * r[2]));
+                    hl[8] = -wo * fma(J[2], r[0], fma(J[5], r[1], J[8] * r[2]));
+                    const double v0 = wo * v[0], v1 = wo * v[1], v2 = wo * v[2];
+                    hl[9] = fma(J[0], v0, fma(J[3], v1, J[6] * v2));
+                    hl[10] = fma(J[1], v0, fma(J[4], v1, J[7] * v2));
+                    hl[11] = fma(J[2], v0, fma(J[5], v1, J[8] * v2));
+                }
+            }
+        }
+        double np0 = px, np1 = py, np2 = pz;
+        if (lmfree) {
+#pragma unroll
+            for (int q = 0; q < 12; ++q) hl[q] = warp_sum(hl[q]);
+            const double A[6] = {hl[0] + lambda, hl[1], hl[2], hl[3] + lambda, hl[4], hl[5] + lambda};
+            const double bl[3] = {hl[6], hl[7], hl[8]};
+            const double c[3] = {bl[0] - hl[9], bl[1] - hl[10], bl[2] - hl[11]};
+            double Di[6], xl[3];
+            inv_sym3(A, Di);
+            sym3_mul(Di, c, xl);
+            np0 = px + xl[0]; np1 = py + xl[1]; np2 = pz + xl[2];
+            if (lane == 0) {
+                gpointT[3 * (size_t)l] = np0; gpointT[3 * (size_t)l + 1] = np1; gpointT[3 * (size_t)l + 2] = np2;
+                scale_acc += xl[0] * (lambda * xl[0] + bl[0]) + xl[1] * (lambda * xl[1] + bl[1]) + xl[2] * (lambda * xl[2] + bl[2]);
+            }
+        }
+        if (lane < d && act) {
+            double r0, r1, r2;
+            edge_residual(gposeT + (size_t)p * kPoseStride, np0, np1, np2, ou, ov, our, mono, K, r0, r1, r2);
+            double rho, wgt;
+            huber((r0 * r0 + r1 * r1 + r2 * r2) * K.inv_pv, K.delta, rho, wgt);
+            chi_acc += rho;
+        }
+    }
+    const double chi = block_sum(chi_acc, red);
+    const double sc = block_sum(scale_acc, red);
+    if (tid == 0) { B.part2[2 * (size_t)blockIdx.x] = chi; B.part2[2 * (size_t)blockIdx.x + 1] = sc; }
+}
+
+// small helpers for the partitioned (multi-GPU) bookkeeping
+__global__ void k_get_counts(Batch B, int *out) { if (threadIdx.x == 0 && blockIdx.x == 0) { out[0] = B.st[0].NL; out[1] = B.st[0].err; } }
+__global__ void k_set_counts(Batch B, const int *in) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        LMState &st = B.st[0];
+        st.NL = in[0];
+        st.nNL[st.pass] = in[0];
+        if (in[1] != 0 && st.err == 0) st.err = in[1];
+    }
+}
+
+// dense copy of the damped reduced system for the parity hook: out[n*n] row-major symmetric, rhs[n]
+__global__ void k_sky_to_dense(Batch B, double lambda, double *out, double *rhs) {
+    const int F = B.st[0].F, n = 6 * F;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < (size_t)n * n; idx += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(idx / n), c = (int)(idx - (size_t)r * n);
+        const int rr = max(r, c), cc = min(r, c);
+        const int rb = rr / 6, cb = cc / 6;
+        double v = 0.0;
+        if (cb >= B.sky_first[rb]) v = B.red[(size_t)(B.sky_off[rb] + (cb - B.sky_first[rb])) * 36 + (rr - 6 * rb) * 6 + (cc - 6 * cb)];
+        if (r == c) v += lambda;
+        out[idx] = v;
+    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) rhs[i] = B.red[B.red_g_off + i];
+}
+
+// Schur block pattern of the large path as (col,row)-sorted keys: emitted per landmark, sorted and made unique by the host
+__global__ void k_pattern_count(Batch B, int *cnt) {
+    const WinDesc &wd = B.win[0];
+    for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < wd.n_point; l += gridDim.x * blockDim.x) {
+        int h = 0;
+        if (B.lm_flags[l] & kInHessian)
+            for (int e = B.lm_edge_off[l]; e < B.lm_edge_off[l + 1]; ++e) h += B.pose_hidx[B.edge_pose[e] & kPoseMask] >= 0;
+        cnt[l] = h * (h + 1) / 2;
+    }
+}
+__global__ void k_pattern_emit(Batch B, const int *offs, unsigned long long *keys, int key_base) {
+    const WinDesc &wd = B.win[0];
+    const int F = B.st[0].F;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < F; i += gridDim.x * blockDim.x)
+        keys[i] = (unsigned long long)i * (unsigned long long)F + (unsigned long long)i;
+    for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < wd.n_point; l += gridDim.x * blockDim.x) {
+        if (!(B.lm_flags[l] & kInHessian)) continue;
+        int o = key_base + offs[l];
+        const int e0 = B.lm_edge_off[l], e1 = B.lm_edge_off[l + 1];
+        for (int ea = e0; ea < e1; ++ea) {
+            const int ha = B.pose_hidx[B.edge_pose[ea] & kPoseMask];
+            if (ha < 0) continue;
+            for (int eb = ea; eb < e1; ++eb) {
+                const int hb = B.pose_hidx[B.edge_pose[eb] & kPoseMask];
+                if (hb < 0) continue;
+                keys[o++] = (unsigned long long)hb * (unsigned long long)F + (unsigned long long)ha;   // (col, row)
+            }
+        }
+    }
+}
+
+}  // namespace lg
+}  // namespace visfs

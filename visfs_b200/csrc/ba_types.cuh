@@ -8,6 +8,7 @@ namespace visfs {
 constexpr int kMaxSmallPoses = 32;   // windows with <= 32 poses take the shared-memory ("small") path
 constexpr int kTileEdges = 160;      // edge slots staged per tile (one thread per edge)
 constexpr int kTileLm = 32;          // landmarks per tile
+constexpr int kMaxDegLarge = 32;     // landmark degree limit of the large-window path (one lane per edge)
 constexpr int kThreads = 256;        // CTA size of the build / update kernels
 constexpr int kPoseStride = 16;      // doubles per pose record: t(3) q(4: x y z w) R(9 row-major)
 constexpr int kHStride = 33;         // per-edge pose-side staging: Hd(21) g(6) b_p(6)
@@ -85,6 +86,14 @@ struct Batch {
     int *n_running;                  // windows still running in the current pass
     const Tile *tiles;               // tile table, chunk c owns tiles [chunk_tile_off[c], chunk_tile_off[c + 1])
     const int *chunk_tile_off;       // [n_chunks + 1]
+    // large-window path (ba_large.cuh): block-skyline reduced camera system in the reduce buffer
+    int *sky_first;                  // [F] first block column of lower row r
+    long long *sky_off;              // [F + 1] row offsets, in blocks
+    int *col_ptr;                    // [F + 1] column structure of the envelope (rows r > k with sky_first[r] <= k)
+    int *col_rows;
+    double *red;                     // [n_sky * 36 | g (6F) | b_p (6F)]  — what a partitioned run all-reduces
+    long long red_g_off, red_bp_off;
+    double *hdiag;                   // [6F] diag(H_pp) of the INIT pass (lambda init)
     double *dbg;                     // parity hook: k_solve dumps packed S and b_s of window 0 here (else null)
     double dbg_lambda;               // parity hook: damping override (< 0: keep the LM state's)
 };

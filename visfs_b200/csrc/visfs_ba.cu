@@ -15,6 +15,10 @@
 #include "../../include/visfs_ba.h"
 #include "ba_kernels.cuh"
 #include "ba_build_ws.cuh"
+#include "ba_large.cuh"
+
+#include <dlfcn.h>
+#include <nccl.h>   // types and enums only: the library is bound at run time with dlopen (no link-time dependency)
 
 using namespace visfs;
 
@@ -98,6 +102,16 @@ struct visfs_ba_handle {
     std::vector<visfs_ba_handle *> subs;
     bool is_sub = false;
 
+    // large-window path (ba_large.cuh) and the partitioned global BA
+    bool large = false, partitioned = false;
+    int grid_build_l = 1, grid_update_l = 1;
+    long long n_sky = 0;
+    DevBuf d_sky_first, d_sky_off, d_col_ptr, d_col_cnt, d_col_rows, d_red, d_hdiag, d_scal, d_info, d_cnt;
+    Batch batch_ctl{};      // same as `batch`, with part2 pointing at the folded (and all-reduced) trial sums
+    ncclComm_t comm = nullptr;
+    int comm_ranks = 1, comm_rank = 0;
+    int64_t allreduce_bytes = 0, allreduce_calls = 0;
+
     int fail(int status, const std::string &msg) { error = msg; return status; }
     int cuda_fail(cudaError_t e, const char *what) {
         error = std::string(what) + ": " + cudaGetErrorString(e);
@@ -178,6 +192,9 @@ Batch make_batch(visfs_ba_handle *h) {
     b.xp = h->d_xp.as<double>(); b.n_running = h->d_n_running.as<int>();
     b.dbg = nullptr; b.dbg_lambda = -1.0;
     b.tiles = h->d_tiles.as<Tile>(); b.chunk_tile_off = h->d_tile_off.as<int>();
+    b.sky_first = h->d_sky_first.as<int>(); b.sky_off = h->d_sky_off.as<long long>();
+    b.col_ptr = h->d_col_ptr.as<int>(); b.col_rows = h->d_col_rows.as<int>();
+    b.red = h->d_red.as<double>(); b.red_g_off = 0; b.red_bp_off = 0; b.hdiag = h->d_hdiag.as<double>();
     return b;
 }
 
@@ -196,15 +213,20 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs) {
     h->win.assign(n, WinDesc{});
     long long tp = 0, tl = 0, te = 0;
     int max_pose = 0, max_point = 0, max_edge = 0, max_iter = 0;
-    bool all_sorted = true;
+    bool all_sorted = true, any_large = false, any_part = false;
     for (int w = 0; w < n; ++w) {
         const visfs_ba_problem &p = probs[w];
         bool srt; int deg;
         const int st = validate(h, p, w, &srt, &deg);
         if (st != VISFS_BA_OK) return st;
-        if (p.flags & VISFS_BA_FLAG_PARTITIONED) return h->fail(VISFS_BA_ERR_UNSUPPORTED, "partitioned global BA: not in this build yet");
-        if (p.n_poses > kMaxSmallPoses) return h->fail(VISFS_BA_ERR_UNSUPPORTED, "windows with more than 32 poses: not in this build yet");
-        if (deg > kTileEdges) return h->fail(VISFS_BA_ERR_UNSUPPORTED, "landmark observed by more than 160 poses");
+        const bool part = (p.flags & VISFS_BA_FLAG_PARTITIONED) != 0;
+        const bool big = part || p.n_poses > kMaxSmallPoses || getenv("VISFS_BA_FORCE_LARGE");
+        if (big && n != 1)
+            return h->fail(VISFS_BA_ERR_UNSUPPORTED, "windows with more than 32 poses and partitioned problems are solved one per call");
+        any_large = any_large || big;
+        any_part = any_part || part;
+        // (the degree limit of the large path is checked on the device so that all ranks of a partitioned run agree)
+        if (!big && deg > kTileEdges) return h->fail(VISFS_BA_ERR_UNSUPPORTED, "landmark observed by more than 160 poses");
         all_sorted = all_sorted && srt;
         WinDesc &d = h->win[w];
         d.pose_off = (int)tp; d.n_pose = p.n_poses; d.point_off = (int)tl; d.n_point = p.n_points;
@@ -212,7 +234,7 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs) {
         const bool single = (p.flags & VISFS_BA_FLAG_SINGLE_PASS) != 0;
         d.max_iter = single ? p.iterations : p.iterations / 2;
         if (d.max_iter < 0) d.max_iter = 0;
-        d.solver = p.solver; d.trust = p.trust_region; d.flags = p.flags; d.large = 0;
+        d.solver = p.solver; d.trust = p.trust_region; d.flags = p.flags; d.large = big ? 1 : 0;
         d.fx = p.fx; d.fy = p.fy; d.cx = p.cx; d.cy = p.cy; d.bf = p.bf;
         d.inv_pv = 1.0 / p.pixel_variance; d.delta = p.huber_delta;
         tp += p.n_poses; tl += p.n_points; te += p.n_edges;
@@ -222,6 +244,10 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs) {
     }
     h->n_win = n; h->tot_pose = (int)tp; h->tot_point = (int)tl; h->tot_edge = (int)te;
     h->max_pose = max_pose; h->max_iter = max_iter; h->sorted = all_sorted;
+    h->large = any_large; h->partitioned = any_part;
+    if (any_part && h->comm_ranks > 1 && !h->comm) return h->fail(VISFS_BA_ERR_INVALID, "partitioned problem without visfs_ba_comm_init");
+    if (any_large && probs[0].solver == VISFS_BA_SOLVER_PCG)
+        return h->fail(VISFS_BA_ERR_UNSUPPORTED, "Optimizer/Solver=2 (PCG) is implemented for windows of up to 32 poses only");
     h->grid_lm_x = std::max(1, std::min((max_point + 255) / 256, 1024));
     h->grid_edge_x = std::max(1, std::min((max_edge + 255) / 256, 1024));
 
@@ -229,7 +255,7 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs) {
     // kernel runs one CTA per SM, so the number of chunks is chosen to fill whole waves of `sm_count` CTAs:
     //   one window : up to sm_count chunks of >= 16 landmarks, clusters of up to 8 CTAs sum their partials
     //   a batch    : c chunks per window with c in 1..16 maximising n*c / (ceil(n*c / sm_count) * sm_count)
-    h->use_ws = (max_pose <= ws::kMaxPosesWs) && !getenv("VISFS_BA_NO_WS");
+    h->use_ws = (max_pose <= ws::kMaxPosesWs) && !getenv("VISFS_BA_NO_WS") && !any_large;
     const int sms = std::max(h->sm_count, 8);
     int per_window = 1;
     if (n == 1) {
@@ -252,6 +278,10 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs) {
     long long part_total = 0;
     for (int w = 0; w < n; ++w) {
         WinDesc &d = h->win[w];
+        if (d.large) {   // the large path needs no chunk table: its kernels stride over the landmarks, k_control reads one folded partial
+            d.chunk_off = 0; d.n_chunks = 1; d.layout = 2; d.n_parts = 0; d.part_stride = 8; d.part_off = 0;
+            continue;
+        }
         d.chunk_off = (int)h->chunks.size();
         const int lm_per_chunk = std::max(1, (d.n_point + per_window - 1) / per_window);
         for (int l0 = 0; l0 < d.n_point; l0 += lm_per_chunk)
@@ -284,7 +314,17 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs) {
     CK(h->d_edge_pose.reserve(sizeof(int) * E)); CK(h->d_edge_point.reserve(sizeof(int) * E));
     CK(h->d_covis.reserve(sizeof(unsigned) * P));
     CK(h->d_part.reserve(sizeof(double) * (size_t)std::max<long long>(part_total, 8)));
-    CK(h->d_part2.reserve(sizeof(double) * 2 * std::max(h->n_chunks, 1)));
+    if (any_large) {
+        // persistent grids: 2 (build, 77 KB of shared memory per CTA) / 4 (update) CTAs per SM, warps stride over the landmarks
+        const int want = (max_point + lg::kWarpsL - 1) / lg::kWarpsL;
+        h->grid_build_l = std::max(1, std::min(want, sms * 2));
+        h->grid_update_l = std::max(1, std::min(want, sms * 4));
+        CK(h->d_sky_first.reserve(sizeof(int) * (P + 1))); CK(h->d_sky_off.reserve(sizeof(long long) * (P + 2)));
+        CK(h->d_col_ptr.reserve(sizeof(int) * (P + 2))); CK(h->d_col_cnt.reserve(sizeof(int) * (P + 2)));
+        CK(h->d_hdiag.reserve(sizeof(double) * 6 * P)); CK(h->d_scal.reserve(sizeof(double) * 8));
+        CK(h->d_info.reserve(sizeof(long long) * 4)); CK(h->d_cnt.reserve(sizeof(int) * 4));
+    }
+    CK(h->d_part2.reserve(sizeof(double) * 2 * std::max(std::max(h->n_chunks, 1), std::max(h->grid_build_l, h->grid_update_l))));
     CK(h->d_xp.reserve(sizeof(double) * 6 * P)); CK(h->d_n_running.reserve(sizeof(int) * 4));
     const size_t max_tiles = 2 * E / (kTileEdges + 1) + L / kTileLm + 2 * (size_t)h->n_chunks + 8;
     CK(h->d_tiles.reserve(sizeof(Tile) * max_tiles));
@@ -363,6 +403,8 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs) {
         perm = h->d_edge_orig.as<int>();
     }
     h->batch = make_batch(h);
+    h->batch_ctl = h->batch;
+    h->batch_ctl.part2 = h->d_scal.as<double>() + 2;
     Batch &B = h->batch;
     if (te > 0) {
         k_prepare_edges<<<grid2(max_edge, n), 256, 0, s>>>(B, h->d_in_obs.as<double>(), h->d_in_epose.as<int>(), h->d_in_epoint.as<int>(),
@@ -454,28 +496,173 @@ int enqueue_body(visfs_ba_handle *h) {
     return VISFS_BA_OK;
 }
 
+
+// ---- NCCL, bound at run time (a single-GPU user never needs the library) ---------------------------------------
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    std::string error;
+    bool load() {
+        if (lib) return true;
+        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char *nm : names) {
+            lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);   // resolves to the copy the process already holds (e.g. torch's), else the system one
+            if (lib) break;
+        }
+        if (!lib) { error = std::string("dlopen libnccl.so.2: ") + dlerror(); return false; }
+        GetUniqueId = reinterpret_cast<decltype(GetUniqueId)>(dlsym(lib, "ncclGetUniqueId"));
+        CommInitRank = reinterpret_cast<decltype(CommInitRank)>(dlsym(lib, "ncclCommInitRank"));
+        AllReduce = reinterpret_cast<decltype(AllReduce)>(dlsym(lib, "ncclAllReduce"));
+        CommDestroy = reinterpret_cast<decltype(CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
+        GetErrorString = reinterpret_cast<decltype(GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
+        if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy || !GetErrorString) {
+            error = "libnccl.so.2 lacks a required symbol";
+            lib = nullptr;
+            return false;
+        }
+        return true;
+    }
+};
+NcclApi g_nccl;
+
+int allreduce(visfs_ba_handle *h, void *buf, size_t count, ncclDataType_t dt, ncclRedOp_t op) {
+    if (!h->comm || h->comm_ranks <= 1 || !h->partitioned || count == 0) return VISFS_BA_OK;
+    const ncclResult_t r = g_nccl.AllReduce(buf, buf, count, dt, op, h->comm, h->stream);
+    if (r != ncclSuccess) return h->fail(VISFS_BA_ERR_CUDA, std::string("ncclAllReduce: ") + g_nccl.GetErrorString(r));
+    h->allreduce_calls += 1;
+    h->allreduce_bytes += (int64_t)count * (dt == ncclFloat64 ? 8 : 4);
+    return VISFS_BA_OK;
+}
+
+// ---- large-window path ---------------------------------------------------------------------------------------------
+int run_structure_large(visfs_ba_handle *h) {
+    Batch &B = h->batch;
+    cudaStream_t s = h->stream;
+    int st;
+    CK(cudaMemsetAsync(h->d_pose_active.p, 0, sizeof(int) * std::max(h->tot_pose, 1), s));
+    const dim3 glm((unsigned)h->grid_lm_x, 1u);
+    k_struct_lm<<<glm, 256, 0, s>>>(B);
+    if ((st = allreduce(h, h->d_pose_active.p, (size_t)h->tot_pose, ncclInt32, ncclMax))) return st;
+    k_struct_pose<<<1, 128, 0, s>>>(B);
+    k_struct_count<<<glm, 256, 0, s>>>(B);
+    k_struct_finish<<<1, 128, 0, s>>>(B);
+    if (h->partitioned && h->comm_ranks > 1) {   // landmarks in the Hessian: sum over ranks; device-side error: any rank
+        lg::k_get_counts<<<1, 32, 0, s>>>(B, h->d_cnt.as<int>());
+        if ((st = allreduce(h, h->d_cnt.p, 2, ncclInt32, ncclSum))) return st;
+        lg::k_set_counts<<<1, 32, 0, s>>>(B, h->d_cnt.as<int>());
+        h->launches += 2;
+    }
+    const int gp = std::max(1, std::min((h->tot_pose + 255) / 256, 64));
+    lg::k_sky_init<<<gp, 256, 0, s>>>(B);
+    lg::k_sky_first<<<glm, 256, 0, s>>>(B);
+    if ((st = allreduce(h, h->d_sky_first.p, (size_t)h->tot_pose, ncclInt32, ncclMin))) return st;
+    lg::k_sky_layout<<<1, 1024, 0, s>>>(B, h->d_col_cnt.as<int>(), h->d_info.as<long long>());
+    lg::k_col_count<<<std::max(1, std::min(h->tot_pose, 1024)), 128, 0, s>>>(B, h->d_col_cnt.as<int>());
+    lg::k_col_scan<<<1, 1024, 0, s>>>(B, h->d_col_cnt.as<int>());
+    long long *info = h->h_small.as<long long>() + 2;
+    CK(cudaMemcpyAsync(info, h->d_info.p, sizeof(long long) * 2, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    h->n_sky = info[0];
+    const long long F = info[1];
+    const size_t red_len = (size_t)h->n_sky * 36 + 12 * (size_t)F;
+    CK(h->d_red.reserve(sizeof(double) * std::max<size_t>(red_len, 8)));
+    CK(h->d_col_rows.reserve(sizeof(int) * (size_t)std::max<long long>(h->n_sky, 1)));
+    Batch *both[2] = {&h->batch, &h->batch_ctl};
+    for (Batch *b : both) {
+        b->red = h->d_red.as<double>(); b->col_rows = h->d_col_rows.as<int>();
+        b->red_g_off = h->n_sky * 36; b->red_bp_off = h->n_sky * 36 + 6 * F;
+    }
+    lg::k_col_fill<<<std::max(1, std::min((h->tot_pose + 7) / 8, 512)), 256, 0, s>>>(h->batch);
+    CK(cudaGetLastError());
+    h->launches += 11;
+    return VISFS_BA_OK;
+}
+
+size_t red_doubles(const visfs_ba_handle *h) { return (size_t)h->batch.red_bp_off + (size_t)(h->batch.red_bp_off - h->batch.red_g_off); }
+
+int enqueue_build_large(visfs_ba_handle *h) {
+    int ev = ev_begin(h, EV_BUILD);
+    CK(cudaMemsetAsync(h->d_red.p, 0, sizeof(double) * red_doubles(h), h->stream));
+    lg::k_build_large<false><<<h->grid_build_l, lg::kThreadsL, sizeof(lg::BuildSmemL), h->stream>>>(h->batch);
+    ev_end(h, ev);
+    h->launches += 1;
+    if (h->partitioned) {
+        ev = ev_begin(h, EV_OTHER);
+        const int st = allreduce(h, h->d_red.p, red_doubles(h), ncclFloat64, ncclSum);
+        ev_end(h, ev);
+        if (st) return st;
+    }
+    return VISFS_BA_OK;
+}
+
+int enqueue_rest_large(visfs_ba_handle *h) {
+    int st;
+    int ev = ev_begin(h, EV_SOLVE);
+    lg::k_solve_large<<<1, lg::kSolveThreadsL, 0, h->stream>>>(h->batch);
+    ev_end(h, ev);
+    ev = ev_begin(h, EV_UPDATE);
+    lg::k_update_large<<<h->grid_update_l, lg::kThreadsL, 0, h->stream>>>(h->batch);
+    ev_end(h, ev);
+    ev = ev_begin(h, EV_OTHER);
+    lg::k_fold_part2<<<1, 256, 0, h->stream>>>(h->batch, h->grid_update_l, 0, h->d_scal.as<double>() + 2);
+    if ((st = allreduce(h, h->d_scal.as<double>() + 2, 2, ncclFloat64, ncclSum))) return st;
+    k_control<<<1, 32, 0, h->stream>>>(h->batch_ctl);
+    ev_end(h, ev);
+    h->launches += 5;
+    return VISFS_BA_OK;
+}
+
+int enqueue_body_large(visfs_ba_handle *h) {
+    const int st = enqueue_build_large(h);
+    return st ? st : enqueue_rest_large(h);
+}
+
+int init_pass_large(visfs_ba_handle *h) {
+    cudaStream_t s = h->stream;
+    int st = run_structure_large(h);
+    if (st) return st;
+    k_sync_buffers<<<dim3((unsigned)h->grid_lm_x, 1u), 256, 0, s>>>(h->batch);
+    CK(cudaMemsetAsync(h->d_hdiag.p, 0, sizeof(double) * 6 * std::max(h->tot_pose, 1), s));
+    lg::k_build_large<true><<<h->grid_build_l, lg::kThreadsL, sizeof(lg::BuildSmemL), s>>>(h->batch);
+    lg::k_fold_part2<<<1, 256, 0, s>>>(h->batch, h->grid_build_l, 1, h->d_scal.as<double>());
+    if ((st = allreduce(h, h->d_hdiag.p, 6 * (size_t)h->tot_pose, ncclFloat64, ncclSum))) return st;
+    if ((st = allreduce(h, h->d_scal.as<double>(), 1, ncclFloat64, ncclSum))) return st;
+    if ((st = allreduce(h, h->d_scal.as<double>() + 1, 1, ncclFloat64, ncclMax))) return st;
+    lg::k_control_init_large<<<1, 256, 0, s>>>(h->batch, h->d_scal.as<double>());
+    h->launches += 4;
+    CK(cudaGetLastError());
+    return VISFS_BA_OK;
+}
+
 int run_pass(visfs_ba_handle *h, int pass) {
     cudaStream_t s = h->stream;
     Batch &B = h->batch;
     const int gw = (h->n_win + 127) / 128;
     int ev = ev_begin(h, EV_OTHER);
     k_begin_pass<<<gw, 128, 0, s>>>(B, pass);
-    int st = run_structure(h);
-    if (st) return st;
-    const int items = std::max(h->max_pose * kPoseStride, 1);
-    (void)items;
-    k_sync_buffers<<<dim3((unsigned)h->grid_lm_x, (unsigned)h->n_win), 256, 0, s>>>(B);
-    launch_build<MODE_INIT>(h);
-    k_control_init<<<h->n_win, 32, 0, s>>>(B);
+    int st;
+    if (h->large) {
+        if ((st = init_pass_large(h))) return st;
+    } else {
+        if ((st = run_structure(h))) return st;
+        k_sync_buffers<<<dim3((unsigned)h->grid_lm_x, (unsigned)h->n_win), 256, 0, s>>>(B);
+        launch_build<MODE_INIT>(h);
+        k_control_init<<<h->n_win, 32, 0, s>>>(B);
+        h->launches += 3;
+    }
     ev_end(h, ev);
-    h->launches += 3;
     CK(cudaGetLastError());
     int *running = h->h_small.as<int>();
     int bodies = 0;
     const int cap = 10 * std::max(h->max_iter, 1) + 2;
     int burst = h->max_iter;
     while (burst > 0 && bodies < cap) {
-        for (int k = 0; k < burst; ++k) enqueue_body(h);
+        for (int k = 0; k < burst; ++k)
+            if ((st = h->large ? enqueue_body_large(h) : enqueue_body(h))) return st;
         bodies += burst;
         CK(cudaMemcpyAsync(running, h->d_n_running.p, sizeof(int), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
@@ -648,6 +835,8 @@ int visfs_ba_create(const visfs_ba_config *cfg, visfs_ba_handle **out) {
         fprintf(stderr, "[visfs_ba] k_solve: regs %d maxThreads %d static smem %zu\n", fa.numRegs, fa.maxThreadsPerBlock, fa.sharedSizeBytes);
         cudaGetLastError();
     }
+    cudaFuncSetAttribute(lg::k_build_large<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(lg::BuildSmemL));
+    cudaFuncSetAttribute(lg::k_build_large<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(lg::BuildSmemL));
     e = cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) {
         g_create_error = std::string("kernel image not usable on this device (built for sm_100a): ") + cudaGetErrorString(e);
@@ -663,8 +852,14 @@ void visfs_ba_destroy(visfs_ba_handle *h) {
     if (!h) return;
     for (visfs_ba_handle *s : h->subs) visfs_ba_destroy(s);
     h->subs.clear();
+    visfs_ba_comm_destroy(h);
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    {
+        DevBuf *lb[] = {&h->d_sky_first, &h->d_sky_off, &h->d_col_ptr, &h->d_col_cnt, &h->d_col_rows, &h->d_red, &h->d_hdiag,
+                        &h->d_scal, &h->d_info, &h->d_cnt};
+        for (DevBuf *b : lb) b->release();
+    }
     DevBuf *bufs[] = {&h->d_win, &h->d_st, &h->d_chunks, &h->d_pose, &h->d_point, &h->d_pose_flags, &h->d_lm_flags, &h->d_pose_hidx,
                       &h->d_pose_active, &h->d_point_hidx, &h->d_lm_edge_off, &h->d_obs_u, &h->d_obs_v, &h->d_obs_r, &h->d_edge_pose,
                       &h->d_edge_point, &h->d_edge_orig, &h->d_covis, &h->d_part, &h->d_part2, &h->d_xp, &h->d_n_running,
@@ -807,7 +1002,8 @@ int visfs_ba_structure_build(visfs_ba_handle *h, const visfs_ba_problem *problem
         k_mark_levels<<<grid2(h->tot_edge, 1), 256, 0, s>>>(h->batch, h->d_out_level.as<uint8_t>());
     }
     k_begin_pass<<<1, 128, 0, s>>>(h->batch, 0);
-    st = run_structure(h);
+    CK(h->h_small.reserve(64));
+    st = h->large ? run_structure_large(h) : run_structure(h);
     if (st) return st;
     // landmark hessian indices: exclusive scan of the in-Hessian flags
     const int cap = std::max(out->schur_capacity, 0);
@@ -828,7 +1024,51 @@ int visfs_ba_structure_build(visfs_ba_handle *h, const visfs_ba_problem *problem
     CK(cubtmp.reserve(tmp_bytes));
     CK(cub::DeviceScan::ExclusiveSum(cubtmp.p, tmp_bytes, d_flag, d_scan, (int)L, s));
     k_structure_export<<<grid2(std::max(h->tot_point, h->tot_edge), 1), 256, 0, s>>>(h->batch, d_scan, d_hidx, d_act, d_row, d_col);
-    k_schur_pattern<<<1, 32, 0, s>>>(h->batch, 0, d_srow, d_scol, cap, d_cnt);
+    std::vector<unsigned long long> lkeys;   // large path: unique (col,row) keys, sorted
+    if (!h->large) {
+        k_schur_pattern<<<1, 32, 0, s>>>(h->batch, 0, d_srow, d_scol, cap, d_cnt);
+    } else {
+        // pattern = diagonal + every pose pair of every landmark in the Hessian: emit keys, sort, unique
+        DevBuf pc, po, kb, kb2, t2;
+        CK(pc.reserve(sizeof(int) * (L + 1))); CK(po.reserve(sizeof(int) * (L + 1)));
+        lg::k_pattern_count<<<grid2(h->tot_point, 1), 256, 0, s>>>(h->batch, pc.as<int>());
+        CK(cudaMemsetAsync(pc.as<int>() + h->tot_point, 0, sizeof(int), s));
+        size_t tb = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, pc.as<int>(), po.as<int>(), h->tot_point + 1, s);
+        CK(t2.reserve(tb));
+        CK(cub::DeviceScan::ExclusiveSum(t2.p, tb, pc.as<int>(), po.as<int>(), h->tot_point + 1, s));
+        int total = 0;
+        CK(cudaMemcpyAsync(&total, po.as<int>() + h->tot_point, sizeof(int), cudaMemcpyDeviceToHost, s));
+        LMState st0;
+        CK(cudaMemcpyAsync(&st0, h->d_st.p, sizeof(LMState), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        const size_t nk = (size_t)total + (size_t)st0.F;
+        CK(kb.reserve(sizeof(unsigned long long) * std::max<size_t>(nk, 1))); CK(kb2.reserve(sizeof(unsigned long long) * std::max<size_t>(nk, 1)));
+        lg::k_pattern_emit<<<grid2(std::max(h->tot_point, st0.F), 1), 256, 0, s>>>(h->batch, po.as<int>(), kb.as<unsigned long long>(), st0.F);
+        if (nk) {
+            tb = 0;
+            cub::DeviceRadixSort::SortKeys(nullptr, tb, kb.as<unsigned long long>(), kb2.as<unsigned long long>(), (int)nk, 0, 64, s);
+            CK(t2.reserve(tb));
+            CK(cub::DeviceRadixSort::SortKeys(t2.p, tb, kb.as<unsigned long long>(), kb2.as<unsigned long long>(), (int)nk, 0, 64, s));
+        }
+        lkeys.resize(nk);
+        if (nk) CK(cudaMemcpyAsync(lkeys.data(), kb2.p, sizeof(unsigned long long) * nk, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        lkeys.erase(std::unique(lkeys.begin(), lkeys.end()), lkeys.end());
+        const int nuniq = (int)lkeys.size();
+        std::vector<int> hr(std::max(std::min(nuniq, cap), 1)), hc(std::max(std::min(nuniq, cap), 1));
+        for (int i = 0; i < std::min(nuniq, cap); ++i) {
+            hc[i] = (int)(lkeys[i] / (unsigned long long)std::max(st0.F, 1));
+            hr[i] = (int)(lkeys[i] % (unsigned long long)std::max(st0.F, 1));
+        }
+        if (std::min(nuniq, cap) > 0) {
+            CK(cudaMemcpyAsync(d_srow, hr.data(), sizeof(int) * std::min(nuniq, cap), cudaMemcpyHostToDevice, s));
+            CK(cudaMemcpyAsync(d_scol, hc.data(), sizeof(int) * std::min(nuniq, cap), cudaMemcpyHostToDevice, s));
+        }
+        CK(cudaMemcpyAsync(d_cnt, &nuniq, sizeof(int), cudaMemcpyHostToDevice, s));
+        CK(cudaStreamSynchronize(s));
+        pc.release(); po.release(); kb.release(); kb2.release(); t2.release();
+    }
     CK(cudaGetLastError());
     std::vector<LMState> sth(1);
     CK(cudaMemcpyAsync(sth.data(), h->d_st.p, sizeof(LMState), cudaMemcpyDeviceToHost, s));
@@ -871,40 +1111,67 @@ int visfs_ba_debug_trial(visfs_ba_handle *h, const visfs_ba_problem *problem, do
     if (st) return st;
     cudaStream_t s = h->stream;
     k_begin_pass<<<1, 128, 0, s>>>(h->batch, 0);
-    st = run_structure(h);
-    if (st) return st;
-    k_sync_buffers<<<dim3((unsigned)h->grid_lm_x, 1u), 256, 0, s>>>(h->batch);
-    launch_build<MODE_INIT>(h);
-    k_control_init<<<1, 32, 0, s>>>(h->batch);
+    CK(h->h_small.reserve(64));
     LMState before;
-    CK(cudaMemcpyAsync(&before, h->d_st.p, sizeof(LMState), cudaMemcpyDeviceToHost, s));
+    DevBuf dbg;
     const int nmax = 6 * h->tot_pose;
     const size_t ntri_max = (size_t)nmax * (nmax + 1) / 2;
-    DevBuf dbg;
-    CK(dbg.reserve(sizeof(double) * (ntri_max + nmax + 8)));
-    CK(cudaMemsetAsync(dbg.p, 0, sizeof(double) * (ntri_max + nmax + 8), s));
-    Batch saved = h->batch;
-    h->batch.dbg = dbg.as<double>();
-    h->batch.dbg_lambda = lambda;
-    enqueue_body(h);
-    h->batch = saved;
+    std::vector<double> denseS, denseB;
+    if (h->large) {
+        if ((st = init_pass_large(h))) return st;
+        CK(cudaMemcpyAsync(&before, h->d_st.p, sizeof(LMState), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        const int nn = 6 * before.F;
+        h->batch.dbg_lambda = lambda; h->batch_ctl.dbg_lambda = lambda;
+        if ((st = enqueue_build_large(h))) return st;
+        CK(dbg.reserve(sizeof(double) * ((size_t)nn * nn + nn + 8)));
+        const double lam_used = (lambda >= 0.0) ? lambda : before.lambda;
+        lg::k_sky_to_dense<<<256, 256, 0, s>>>(h->batch, problem->trust_region == 0 ? lam_used : 0.0, dbg.as<double>(),
+                                               dbg.as<double>() + (size_t)nn * nn);
+        denseS.resize((size_t)nn * nn); denseB.resize(nn);
+        if (nn) {
+            CK(cudaMemcpyAsync(denseS.data(), dbg.p, sizeof(double) * (size_t)nn * nn, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(denseB.data(), dbg.as<double>() + (size_t)nn * nn, sizeof(double) * nn, cudaMemcpyDeviceToHost, s));
+        }
+        if ((st = enqueue_rest_large(h))) return st;
+        h->batch.dbg_lambda = -1.0; h->batch_ctl.dbg_lambda = -1.0;
+    } else {
+        st = run_structure(h);
+        if (st) return st;
+        k_sync_buffers<<<dim3((unsigned)h->grid_lm_x, 1u), 256, 0, s>>>(h->batch);
+        launch_build<MODE_INIT>(h);
+        k_control_init<<<1, 32, 0, s>>>(h->batch);
+        CK(cudaMemcpyAsync(&before, h->d_st.p, sizeof(LMState), cudaMemcpyDeviceToHost, s));
+        CK(dbg.reserve(sizeof(double) * (ntri_max + nmax + 8)));
+        CK(cudaMemsetAsync(dbg.p, 0, sizeof(double) * (ntri_max + nmax + 8), s));
+        Batch saved = h->batch;
+        h->batch.dbg = dbg.as<double>();
+        h->batch.dbg_lambda = lambda;
+        enqueue_body(h);
+        h->batch = saved;
+    }
     CK(cudaGetLastError());
     LMState after;
     CK(cudaMemcpyAsync(&after, h->d_st.p, sizeof(LMState), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     const int n = 6 * after.F;
     const size_t ntri = (size_t)n * (n + 1) / 2;
-    std::vector<double> packed(ntri + n + 1);
-    if (ntri + n) CK(cudaMemcpy(packed.data(), dbg.p, sizeof(double) * (ntri + n), cudaMemcpyDeviceToHost));
     if (n_out) *n_out = n;
-    if (S_dense)
-        for (int r = 0; r < n; ++r)
-            for (int c = 0; c <= r; ++c) {
-                const double v = packed[(size_t)r * (r + 1) / 2 + c];
-                S_dense[(size_t)r * n + c] = v;
-                S_dense[(size_t)c * n + r] = v;
-            }
-    if (b_s) for (int i = 0; i < n; ++i) b_s[i] = packed[ntri + i];
+    if (h->large) {
+        if (S_dense) memcpy(S_dense, denseS.data(), sizeof(double) * (size_t)n * n);
+        if (b_s) memcpy(b_s, denseB.data(), sizeof(double) * n);
+    } else {
+        std::vector<double> packed(ntri + n + 1);
+        if (ntri + n) CK(cudaMemcpy(packed.data(), dbg.p, sizeof(double) * (ntri + n), cudaMemcpyDeviceToHost));
+        if (S_dense)
+            for (int r = 0; r < n; ++r)
+                for (int c = 0; c <= r; ++c) {
+                    const double v = packed[(size_t)r * (r + 1) / 2 + c];
+                    S_dense[(size_t)r * n + c] = v;
+                    S_dense[(size_t)c * n + r] = v;
+                }
+        if (b_s) for (int i = 0; i < n; ++i) b_s[i] = packed[ntri + i];
+    }
     if (x_pose && n) CK(cudaMemcpy(x_pose, h->d_xp.p, sizeof(double) * n, cudaMemcpyDeviceToHost));
     const int trial_buf = 1 - before.cur;  // the trial was written into the buffer that was not accepted before the body
     if (trial_points && h->tot_point)
@@ -917,11 +1184,45 @@ int visfs_ba_debug_trial(visfs_ba_handle *h, const visfs_ba_problem *problem, do
     return VISFS_BA_OK;
 }
 
-int visfs_ba_comm_unique_id(void *) { return VISFS_BA_ERR_UNSUPPORTED; }
-int visfs_ba_comm_init(visfs_ba_handle *h, int32_t, int32_t, const void *) {
-    return h ? h->fail(VISFS_BA_ERR_UNSUPPORTED, "multi-GPU global BA: not in this build yet") : VISFS_BA_ERR_INVALID;
+int visfs_ba_comm_unique_id(void *id_out) {
+    if (!id_out) return VISFS_BA_ERR_INVALID;
+    if (!g_nccl.load()) { g_create_error = g_nccl.error; return VISFS_BA_ERR_CUDA; }
+    static_assert(sizeof(ncclUniqueId) <= VISFS_BA_COMM_ID_BYTES, "ncclUniqueId does not fit VISFS_BA_COMM_ID_BYTES");
+    ncclUniqueId id;
+    const ncclResult_t r = g_nccl.GetUniqueId(&id);
+    if (r != ncclSuccess) { g_create_error = g_nccl.GetErrorString(r); return VISFS_BA_ERR_CUDA; }
+    memset(id_out, 0, VISFS_BA_COMM_ID_BYTES);
+    memcpy(id_out, &id, sizeof id);
+    return VISFS_BA_OK;
 }
-int visfs_ba_comm_destroy(visfs_ba_handle *) { return VISFS_BA_OK; }
+
+int visfs_ba_comm_init(visfs_ba_handle *h, int32_t n_ranks, int32_t rank, const void *id_in) {
+    if (!h) return VISFS_BA_ERR_INVALID;
+    if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return h->fail(VISFS_BA_ERR_INVALID, "bad rank / world size");
+    if (h->comm) visfs_ba_comm_destroy(h);
+    h->comm_ranks = n_ranks; h->comm_rank = rank;
+    if (n_ranks == 1) return VISFS_BA_OK;
+    if (!id_in) return h->fail(VISFS_BA_ERR_INVALID, "null unique id");
+    if (!g_nccl.load()) return h->fail(VISFS_BA_ERR_CUDA, g_nccl.error);
+    CK(cudaSetDevice(h->device));
+    ncclUniqueId id;
+    memcpy(&id, id_in, sizeof id);
+    const ncclResult_t r = g_nccl.CommInitRank(&h->comm, n_ranks, id, rank);
+    if (r != ncclSuccess) { h->comm = nullptr; return h->fail(VISFS_BA_ERR_CUDA, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r)); }
+    return VISFS_BA_OK;
+}
+
+int visfs_ba_comm_destroy(visfs_ba_handle *h) {
+    if (!h) return VISFS_BA_ERR_INVALID;
+    if (h->comm) {
+        cudaSetDevice(h->device);
+        cudaStreamSynchronize(h->stream);
+        g_nccl.CommDestroy(h->comm);
+        h->comm = nullptr;
+    }
+    h->comm_ranks = 1; h->comm_rank = 0;
+    return VISFS_BA_OK;
+}
 
 int visfs_ba_probe_fp64(visfs_ba_handle *h, double *tflops_out) {
     if (!h || !tflops_out) return VISFS_BA_ERR_INVALID;
