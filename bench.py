@@ -188,6 +188,59 @@ def single_window_numbers(ba, O, cores, quick):
     return out
 
 
+def global_ba_numbers(ba, dist, world, rank, barrier, reduce_max, quick):
+    """BASELINE config C4: one global BA (2 000 key frames on a loop / 500 000 landmarks / 5 M edges), landmarks partitioned
+    over the ranks, reduced camera system summed with one ncclAllReduce per LM trial (strong scaling: total work fixed)."""
+    from visfs_b200 import partition
+    scale = 0.25 if quick else 1.0
+    w = synth.config_c4(n_poses=int(2000 * scale), n_points=int(500000 * scale))
+    part = partition.partition_window(w, world, rank)
+    if world > 1:
+        ba.comm_init_torch(dist)
+    ba.upload([part])
+    ba.run_resident()
+    barrier()
+    reps = 2
+    dev_ms, t = 0.0, None
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        ba.run_resident()
+        t = ba.timing()
+        dev_ms += t["total_ms"]
+    barrier()
+    wall = time.perf_counter() - t0
+    dev_s = reduce_max(dev_ms * 1e-3)
+    r = ba.download()[0]
+    out = {"workload": f"C4 global BA: {w['n_poses']} key frames on a loop, {w['n_points']} landmarks x 10 views = {w['n_edges']} "
+                       f"stereo edges, landmarks partitioned over {world} GPU(s), NCCL all-reduce of the block-skyline reduced system",
+           "scaling": "strong", "lm_iterations": int(t["lm_iterations"]), "lm_trials": int(t["lm_trials"]),
+           "ms_per_solve": 1e3 * dev_s / reps, "lm_iterations_per_s": reps * t["lm_iterations"] / dev_s,
+           "edges_per_s": reps * t["lm_trials"] * w["n_edges"] / dev_s,
+           "kernel_ms_this_rank": {k: t[k] for k in ("build_ms", "solve_ms", "update_ms", "other_ms")},
+           "wall_ms_per_solve": 1e3 * wall / reps, "status": int(r["status"]),
+           "chi2": [r["chi2_initial"], r["chi2_pass1"], r["chi2_final"]]}
+    # HBM roofline of the Jacobian + Schur pass (SURVEY.md §8d): algorithmic bytes of this rank's build launches / their time
+    if t["build_ms"] > 0:
+        out["build_GBps_this_rank"] = t["alg_bytes_build"] / (t["build_ms"] * 1e-3) / 1e9
+    return out
+
+
+def dense_window_numbers(ba, quick):
+    """BASELINE config C5: 200 key frames orbiting one scene, 200 000 landmarks x 10 random views (dense reduced system)."""
+    w = synth.config_c5(n_poses=200, n_points=50000 if quick else 200000)
+    ba.upload([w])
+    ba.run_resident()
+    ba.run_resident()
+    t = ba.timing()
+    r = ba.download()[0]
+    return {"workload": f"C5 dense window: {w['n_poses']} key frames, {w['n_points']} landmarks, {w['n_edges']} edges, one GPU",
+            "lm_iterations": int(t["lm_iterations"]), "lm_trials": int(t["lm_trials"]), "ms_per_solve": t["total_ms"],
+            "lm_iterations_per_s": t["lm_iterations"] / (t["total_ms"] * 1e-3),
+            "edges_per_s": t["lm_trials"] * w["n_edges"] / (t["total_ms"] * 1e-3),
+            "kernel_ms": {k: t[k] for k in ("build_ms", "solve_ms", "update_ms", "other_ms")}, "status": int(r["status"]),
+            "chi2": [r["chi2_initial"], r["chi2_pass1"], r["chi2_final"]]}
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -265,7 +318,16 @@ def run_gpu(args):
     e2e_iters = reduce(iters_step * args.steps, SUM)
     n_bad = reduce(bad, SUM)
 
+    # ---- global BA (C4) over all ranks: every rank takes part, rank 0 reports
+    gba = None
+    if not args.no_global:
+        try:
+            gba = global_ba_numbers(ba, dist if world > 1 else None, world, rank, barrier, lambda v: reduce(v, MAX), args.quick)
+        except Exception as exc:  # reported, never silently dropped
+            gba = {"error": repr(exc)}
+
     if rank != 0:
+        ba.close()
         if world > 1:
             dist.destroy_process_group()
         return 0
@@ -306,6 +368,10 @@ def run_gpu(args):
                      "peak_source": "visfs_ba_probe_fp64: dependent-free DFMA loop, this process, this GPU"},
             "kernel_ms_per_step": {k: sum(t[k] for t in tims) / args.steps for k in ("build_ms", "solve_ms", "update_ms", "other_ms")},
             "clocks": clocks.summary(), "windows_failed": int(n_bad)}
+    if gba is not None:
+        line["global_ba"] = gba
+    if world == 1 and not args.no_global:
+        line["dense_window"] = dense_window_numbers(ba, args.quick)
 
     # ---- CPU baseline (rank 0, N = 1 only) and the single-window latency cases
     if world == 1 and not args.no_cpu:
@@ -337,6 +403,7 @@ def main():
     ap.add_argument("--windows", type=int, default=512, help="windows per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--no-global", action="store_true", help="skip the C4 global-BA and C5 dense-window legs")
     ap.add_argument("--profile-run", action="store_true", help="upload + two resident solves only (for ncu)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
