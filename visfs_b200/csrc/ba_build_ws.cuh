@@ -46,7 +46,7 @@ struct Stage {
 };
 
 struct Smem {
-    double pose[kMaxSmallPoses * kPoseStride];
+    double pose[kMaxSmallPoses * kPoseSm];
     Stage st[2];
     double pacc[kMaxSmallPoses * kHStride];
     int hidx[kMaxSmallPoses];
@@ -98,7 +98,7 @@ __global__ void __maxnreg__(168) k_build_ws(Batch B, int cluster_size) {
     const int tile0 = B.chunk_tile_off[blockIdx.x], ntiles = B.chunk_tile_off[blockIdx.x + 1] - tile0;
     const Tile *__restrict__ tiles = B.tiles + tile0;
 
-    for (int i = tid; i < n_pose * kPoseStride; i += kThreadsWs) sm.pose[i] = gpose[i];
+    for (int i = tid; i < n_pose * kPoseStride; i += kThreadsWs) sm.pose[(i >> 4) * kPoseSm + (i & 15)] = gpose[i];
     for (int i = tid; i < n_pose; i += kThreadsWs) sm.hidx[i] = B.pose_hidx[pose_off + i];
     for (int i = tid; i < kMaxSmallPoses * kHStride; i += kThreadsWs) sm.pacc[i] = 0.0;
     __syncthreads();
@@ -146,7 +146,7 @@ __global__ void __maxnreg__(168) k_build_ws(Batch B, int cluster_size) {
                 act = !(rec.pw & kCulledBit) && !((rec.lf & kFixed) && (rec.pf & kFixed));
                 lmfree = (rec.lf & kInHessian) != 0;
                 double *hl = S.H + tid * kHStride;
-                if (act) edge_linearize(sm.pose + p * kPoseStride, rec.px, rec.py, rec.pz, rec.ou, rec.ov, rec.our,
+                if (act) edge_linearize(sm.pose + p * kPoseSm, rec.px, rec.py, rec.pz, rec.ou, rec.ov, rec.our,
                                         (rec.pw & kMonoBit) != 0, K, lin);
                 if (act && lmfree) {
                     const double wo = lin.w * K.inv_pv;

@@ -29,7 +29,7 @@ enum { MODE_INIT = 0, MODE_BUILD = 1 };
 // shared-memory carve-up of k_build / k_update
 // ------------------------------------------------------------------------------------------------
 struct BuildSmem {
-    double pose[kMaxSmallPoses * kPoseStride];
+    double pose[kMaxSmallPoses * kPoseSm];
     double W[kTileEdges * 18];
     double Y[kTileEdges * 18];
     double H[kTileEdges * kHStride];
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(kThreads, PPT == 1 ? 2 : 1) k_build(Batch B) {
     const double *__restrict__ gpose = B.pose + ((size_t)cur * B.tot_pose + pose_off) * kPoseStride;
     const double *__restrict__ gpoint = B.point + (size_t)cur * B.tot_point * 3;
 
-    for (int i = tid; i < n_pose * kPoseStride; i += kThreads) sm.pose[i] = gpose[i];
+    for (int i = tid; i < n_pose * kPoseStride; i += kThreads) sm.pose[(i >> 4) * kPoseSm + (i & 15)] = gpose[i];
     for (int i = tid; i < n_pose; i += kThreads) sm.hidx[i] = B.pose_hidx[pose_off + i];
     for (int i = tid; i < kMaxSmallPoses * kHStride; i += kThreads) sm.pacc[i] = 0.0;
 
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(kThreads, PPT == 1 ? 2 : 1) k_build(Batch B) {
             double *hl = sm.H + tid * kHStride;
             if (act) {
                 const double px = gpoint[3 * (size_t)gl], py = gpoint[3 * (size_t)gl + 1], pz = gpoint[3 * (size_t)gl + 2];
-                edge_linearize(sm.pose + p * kPoseStride, px, py, pz, B.obs_u[e], B.obs_v[e], B.obs_r[e],
+                edge_linearize(sm.pose + p * kPoseSm, px, py, pz, B.obs_u[e], B.obs_v[e], B.obs_r[e],
                                (pw & kMonoBit) != 0, K, lin);
                 if (MODE == MODE_INIT) chi_acc += lin.rho;
             }

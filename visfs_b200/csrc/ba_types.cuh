@@ -11,6 +11,7 @@ constexpr int kTileLm = 32;          // landmarks per tile
 constexpr int kMaxDegLarge = 32;     // landmark degree limit of the large-window path (one lane per edge)
 constexpr int kThreads = 256;        // CTA size of the build / update kernels
 constexpr int kPoseStride = 16;      // doubles per pose record: t(3) q(4: x y z w) R(9 row-major)
+constexpr int kPoseSm = 17;          // shared-memory stride of a pose record: odd, so lanes reading different poses hit different banks
 constexpr int kHStride = 33;         // per-edge pose-side staging: Hd(21) g(6) b_p(6)
 
 // edge_pose word: bits 0-23 window-local pose index, bit 24 mono, bit 25 culled (level 1)
@@ -86,6 +87,8 @@ struct Batch {
     int *n_running;                  // windows still running in the current pass
     const Tile *tiles;               // tile table, chunk c owns tiles [chunk_tile_off[c], chunk_tile_off[c + 1])
     const int *chunk_tile_off;       // [n_chunks + 1]
+    const Tile *wtiles;              // warp tiles of k_update (<= 32 edges, whole landmarks), same indexing
+    const int *chunk_wtile_off;      // [n_chunks + 1]
     // large-window path (ba_large.cuh): block-skyline reduced camera system in the reduce buffer
     int *sky_first;                  // [F] first block column of lower row r
     long long *sky_off;              // [F + 1] row offsets, in blocks

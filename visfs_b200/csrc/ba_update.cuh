@@ -1,9 +1,9 @@
 // ba_update.cuh — k_update: landmark back-substitution x_l = Dinv (b_l - sum_e W_e^T x_p), point oplus into the
 // trial buffer, robust chi2 of the trial state, and the landmark part of g2o's computeScale().
 // Same chunk / tile table as the build kernel; the linearisation is recomputed instead of being stored
-// (32 B/edge re-read instead of 288 B/edge written and read back).  One edge per thread; the next tile's edge
-// records and points are prefetched into registers while the current tile is computed; per-landmark sums are
-// formed by (landmark, entry) owner threads in edge order.
+// (32 B/edge re-read instead of 288 B/edge written and read back).  One edge per lane; every warp walks its own
+// warp tiles (whole landmarks, <= 32 edges) without block-level barriers; per-landmark sums are formed by
+// (landmark, entry) owner lanes in edge order.
 #pragma once
 #include "ba_math.cuh"
 
@@ -46,46 +46,92 @@ __device__ __forceinline__ void edge_linearize_jx(const double *ps, double px, d
     huber((r[0] * r[0] + r[1] * r[1] + r[2] * r[2]) * K.inv_pv, K.delta, rho, w);
 }
 
+// Warp tiles: consecutive landmarks of one chunk packed so that their edges fit one warp (<= 32 edges, <= 8 landmarks);
+// a landmark with more than 32 edges is a tile of its own and is walked in rounds.  Built once per upload
+// (k_count_wtiles / k_fill_wtiles).  Warps never wait for each other: the per-landmark sums go through the warp's own
+// shared-memory slab (summed in edge order, like g2o) and only __syncwarp orders them.
+constexpr int kWtLm = 8;
+constexpr int kUpdWarps = 8;
+constexpr int kUpdThreads = kUpdWarps * 32;
+constexpr int kHs = 13;                  // padded row length of the per-edge slab (12 values)
+
+struct UpdWarp {
+    double H[32 * kHs];                  // per edge: H_ll (6) b_l (3) W^T x_p (3)
+    double lm[kWtLm * 12];               // per landmark sums of the same
+    int lmoff[kWtLm + 1];
+    int pad;
+};
 struct UpdateSmem {
-    double pose[kMaxSmallPoses * kPoseStride];
-    double poseT[kMaxSmallPoses * kPoseStride];
+    double pose[kMaxSmallPoses * kPoseSm];
+    double poseT[kMaxSmallPoses * kPoseSm];
     double xp[kMaxSmallPoses * 6];
-    double H[kTileEdges * 12];       // per edge: H_ll (6) b_l (3) W^T x_p (3)
-    double lm[kTileLm * 12];         // per landmark sums of the same
-    double newp[kTileLm * 3];
+    UpdWarp w[kUpdWarps];
     double red[32];
     int hidx[kMaxSmallPoses];
-    int lmoff[kTileLm + 1];
 };
 
-struct UpdRec {
-    double ou, ov, our, px, py, pz;
-    int pw, gl;
-    uint8_t lf, pf;
-};
-
-__device__ __forceinline__ void upd_load_l1(const Batch &B, const WinDesc &wd, const Tile &T, int tid, UpdRec &r) {
-    if (tid < T.ne) {
-        const int e = T.e0 + tid;
-        r.pw = B.edge_pose[e];
-        r.gl = wd.point_off + B.edge_point[e];
-        r.ou = B.obs_u[e]; r.ov = B.obs_v[e]; r.our = B.obs_r[e];
+template <bool WRITE>
+__device__ int walk_wtiles(const int *__restrict__ off, int lm0, int lm1, Tile *out) {
+    int n = 0;
+    for (int lt = lm0; lt < lm1;) {
+        const int e0 = off[lt];
+        int l1 = lt;
+        while (l1 < lm1 && l1 - lt < kWtLm && off[l1 + 1] - e0 <= 32) ++l1;
+        if (l1 == lt) l1 = lt + 1;       // one landmark with more than 32 edges
+        if (off[l1] - e0 > 0) {          // landmarks without edges have nothing to update
+            if (WRITE) out[n] = Tile{lt, l1 - lt, e0, off[l1] - e0};
+            ++n;
+        }
+        lt = l1;
     }
+    return n;
 }
-__device__ __forceinline__ void upd_load_l2(const Batch &B, const WinDesc &wd, const Tile &T, int tid, const double *gpoint, UpdRec &r) {
-    if (tid < T.ne) {
-        r.lf = B.lm_flags[r.gl];
-        r.pf = B.pose_flags[wd.pose_off + (r.pw & kPoseMask)];
-        r.px = gpoint[3 * (size_t)r.gl]; r.py = gpoint[3 * (size_t)r.gl + 1]; r.pz = gpoint[3 * (size_t)r.gl + 2];
-    }
+__global__ void k_count_wtiles(Batch B, int *ntiles) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > B.n_chunks) return;
+    ntiles[c] = (c < B.n_chunks) ? walk_wtiles<false>(B.lm_edge_off, B.chunks[c].lm0, B.chunks[c].lm1, nullptr) : 0;
+}
+__global__ void k_fill_wtiles(Batch B, const int *tile_off, Tile *tiles) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= B.n_chunks) return;
+    walk_wtiles<true>(B.lm_edge_off, B.chunks[c].lm0, B.chunks[c].lm1, tiles + tile_off[c]);
 }
 
-constexpr int kUpdThreads = kTileEdges;   // 160: one edge per thread, 5 warps
+// the 12 per-edge terms of the landmark back-substitution
+__device__ __forceinline__ void upd_edge_terms(const double *ps, double px, double py, double pz, double ou, double ov, double our,
+                                               bool mono, const Intr &K, const double *xp, double *hl) {
+    double r[3], J[9], v[3], w;
+    edge_linearize_jx(ps, px, py, pz, ou, ov, our, mono, K, xp, r, J, v, w);
+    const double wo = w * K.inv_pv;
+    hl[0] = wo * fma(J[0], J[0], fma(J[3], J[3], J[6] * J[6]));
+    hl[1] = wo * fma(J[0], J[1], fma(J[3], J[4], J[6] * J[7]));
+    hl[2] = wo * fma(J[0], J[2], fma(J[3], J[5], J[6] * J[8]));
+    hl[3] = wo * fma(J[1], J[1], fma(J[4], J[4], J[7] * J[7]));
+    hl[4] = wo * fma(J[1], J[2], fma(J[4], J[5], J[7] * J[8]));
+    hl[5] = wo * fma(J[2], J[2], fma(J[5], J[5], J[8] * J[8]));
+    hl[6] = -wo * fma(J[0], r[0], fma(J[3], r[1], J[6] * r[2]));
+    hl[7] = -wo * fma(J[1], r[0], fma(J[4], r[1], J[7] * r[2]));
+    hl[8] = -wo * fma(J[2], r[0], fma(J[5], r[1], J[8] * r[2]));
+    const double v0 = wo * v[0], v1 = wo * v[1], v2 = wo * v[2];   // W^T x_p = wo * Jl^T (Jp x_p)
+    hl[9] = fma(J[0], v0, fma(J[3], v1, J[6] * v2));
+    hl[10] = fma(J[1], v0, fma(J[4], v1, J[7] * v2));
+    hl[11] = fma(J[2], v0, fma(J[5], v1, J[8] * v2));
+}
 
-__global__ void __launch_bounds__(kUpdThreads, 4) k_update(Batch B) {
+// x_l = (H_ll + lambda I)^-1 (b_l - sum W^T x_p) from the 12 landmark sums; returns the landmark's part of computeScale()
+__device__ __forceinline__ double upd_point_step(const double *ls, double lambda, double *xl) {
+    const double A[6] = {ls[0] + lambda, ls[1], ls[2], ls[3] + lambda, ls[4], ls[5] + lambda};
+    const double c[3] = {ls[6] - ls[9], ls[7] - ls[10], ls[8] - ls[11]};
+    double Di[6];
+    inv_sym3(A, Di);
+    sym3_mul(Di, c, xl);
+    return xl[0] * (lambda * xl[0] + ls[6]) + xl[1] * (lambda * xl[1] + ls[7]) + xl[2] * (lambda * xl[2] + ls[8]);
+}
+
+__global__ void __launch_bounds__(kUpdThreads, 2) k_update(Batch B) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     UpdateSmem &sm = *reinterpret_cast<UpdateSmem *>(smem_raw);
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const Chunk ck = B.chunks[blockIdx.x];
     const WinDesc &wd = B.win[ck.win];
     const LMState &st = B.st[ck.win];
@@ -98,98 +144,136 @@ __global__ void __launch_bounds__(kUpdThreads, 4) k_update(Batch B) {
     const double *__restrict__ gposeT = B.pose + ((size_t)(1 - cur) * B.tot_pose + pose_off) * kPoseStride;
     const double *__restrict__ gpoint = B.point + (size_t)cur * B.tot_point * 3;
     double *__restrict__ gpointT = B.point + (size_t)(1 - cur) * B.tot_point * 3;
-    const int tile0 = B.chunk_tile_off[blockIdx.x], ntiles = B.chunk_tile_off[blockIdx.x + 1] - tile0;
-    const Tile *__restrict__ tiles = B.tiles + tile0;
-    for (int i = tid; i < n_pose * kPoseStride; i += kUpdThreads) { sm.pose[i] = gpose[i]; sm.poseT[i] = gposeT[i]; }
+    const int tile0 = B.chunk_wtile_off[blockIdx.x], ntiles = B.chunk_wtile_off[blockIdx.x + 1] - tile0;
+    const Tile *__restrict__ tiles = B.wtiles + tile0;
+    for (int i = tid; i < n_pose * kPoseStride; i += kUpdThreads) {
+        const int j = (i >> 4) * kPoseSm + (i & 15);
+        sm.pose[j] = gpose[i]; sm.poseT[j] = gposeT[i];
+    }
     for (int i = tid; i < n_pose; i += kUpdThreads) sm.hidx[i] = B.pose_hidx[pose_off + i];
     for (int i = tid; i < st.F * 6; i += kUpdThreads) sm.xp[i] = B.xp[(size_t)pose_off * 6 + i];
-    double chi_acc = 0.0, scale_acc = 0.0;
-    UpdRec rec, nxt;
-    Tile T, Tn;
-    if (ntiles > 0) {
-        T = tiles[0];
-        upd_load_l1(B, wd, T, tid, rec);
-        upd_load_l2(B, wd, T, tid, gpoint, rec);
-    }
     __syncthreads();
+    UpdWarp &W = sm.w[warp];
+    double chi_acc = 0.0, scale_acc = 0.0;
 
-    for (int t = 0; t < ntiles; ++t) {
-        const bool more = t + 1 < ntiles;
-        if (more) { Tn = tiles[t + 1]; upd_load_l1(B, wd, Tn, tid, nxt); }
-        const int ne = T.ne, ntl = T.ntl, lt = T.lt;
-        if (tid <= ntl) sm.lmoff[tid] = min(B.lm_edge_off[lt + tid] - T.e0, kTileEdges);
-        bool act = false, mono = false;
-        int tl = 0, p = 0;
-        if (tid < ne) {
-            p = rec.pw & kPoseMask;
-            mono = (rec.pw & kMonoBit) != 0;
-            tl = rec.gl - lt;
-            act = !(rec.pw & kCulledBit) && !((rec.lf & kFixed) && (rec.pf & kFixed));
-            double *hl = sm.H + tid * 12;
-            if (act && (rec.lf & kInHessian)) {
-                double r[3], J[9], v[3], w;
-                const int hi = sm.hidx[p];
-                edge_linearize_jx(sm.pose + p * kPoseStride, rec.px, rec.py, rec.pz, rec.ou, rec.ov, rec.our, mono, K,
-                                  hi >= 0 ? sm.xp + hi * 6 : nullptr, r, J, v, w);
-                const double wo = w * K.inv_pv;
-                hl[0] = wo * fma(J[0], J[0], fma(J[3], J[3], J[6] * J[6]));
-                hl[1] = wo * fma(J[0], J[1], fma(J[3], J[4], J[6] * J[7]));
-                hl[2] = wo * fma(J[0], J[2], fma(J[3], J[5], J[6] * J[8]));
-                hl[3] = wo * fma(J[1], J[1], fma(J[4], J[4], J[7] * J[7]));
-                hl[4] = wo * fma(J[1], J[2], fma(J[4], J[5], J[7] * J[8]));
-                hl[5] = wo * fma(J[2], J[2], fma(J[5], J[5], J[8] * J[8]));
-                hl[6] = -wo * fma(J[0], r[0], fma(J[3], r[1], J[6] * r[2]));
-                hl[7] = -wo * fma(J[1], r[0], fma(J[4], r[1], J[7] * r[2]));
-                hl[8] = -wo * fma(J[2], r[0], fma(J[5], r[1], J[8] * r[2]));
-                // W^T x_p = wo * Jl^T (Jp x_p)
-                const double v0 = wo * v[0], v1 = wo * v[1], v2 = wo * v[2];
-                hl[9] = fma(J[0], v0, fma(J[3], v1, J[6] * v2));
-                hl[10] = fma(J[1], v0, fma(J[4], v1, J[7] * v2));
-                hl[11] = fma(J[2], v0, fma(J[5], v1, J[8] * v2));
-            } else {
+    for (int t = warp; t < ntiles; t += kUpdWarps) {
+        const Tile T = tiles[t];
+        if (T.ne <= 32) {
+            // ---- several whole landmarks, one edge per lane
+            if (lane <= T.ntl) W.lmoff[lane] = B.lm_edge_off[T.lt + lane] - T.e0;
+            bool act = false, mono = false, lmfree = false;
+            int tl = 0, p = 0;
+            double ou = 0, ov = 0, our = 0, px = 0, py = 0, pz = 0;
+            double hl[12];
 #pragma unroll
-                for (int q = 0; q < 12; ++q) hl[q] = 0.0;
+            for (int q = 0; q < 12; ++q) hl[q] = 0.0;
+            if (lane < T.ne) {
+                const int e = T.e0 + lane;
+                const int pw = B.edge_pose[e];
+                const int gl = wd.point_off + B.edge_point[e];
+                p = pw & kPoseMask;
+                mono = (pw & kMonoBit) != 0;
+                tl = gl - T.lt;
+                const uint8_t lf = B.lm_flags[gl];
+                lmfree = (lf & kInHessian) != 0;
+                act = !(pw & kCulledBit) && !((lf & kFixed) && (B.pose_flags[pose_off + p] & kFixed));
+                px = gpoint[3 * (size_t)gl]; py = gpoint[3 * (size_t)gl + 1]; pz = gpoint[3 * (size_t)gl + 2];
+                if (act) {
+                    ou = B.obs_u[e]; ov = B.obs_v[e]; our = B.obs_r[e];
+                    if (lmfree) {
+                        const int hi = sm.hidx[p];
+                        upd_edge_terms(sm.pose + p * kPoseSm, px, py, pz, ou, ov, our, mono, K, hi >= 0 ? sm.xp + hi * 6 : nullptr, hl);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 12; ++q) W.H[lane * kHs + q] = hl[q];
             }
-        }
-        if (more) upd_load_l2(B, wd, Tn, tid, gpoint, nxt);
-        __syncthreads();
-        for (int task = tid; task < ntl * 12; task += kUpdThreads) {
-            const int l = task / 12, q = task - l * 12;
-            double s = 0.0;
-            for (int e = sm.lmoff[l]; e < sm.lmoff[l + 1]; ++e) s += sm.H[e * 12 + q];
-            sm.lm[task] = s;
-        }
-        __syncthreads();
-        if (tid < ntl) {
-            const int gl = lt + tid;
+            __syncwarp();
+            for (int task = lane; task < T.ntl * 12; task += 32) {
+                const int l = task / 12, q = task - l * 12;
+                double s = 0.0;
+                for (int e = W.lmoff[l]; e < W.lmoff[l + 1]; ++e) s += W.H[e * kHs + q];
+                W.lm[task] = s;
+            }
+            __syncwarp();
+            if (lane < T.ne) {
+                double np0 = px, np1 = py, np2 = pz;
+                if (lmfree) {
+                    double xl[3];
+                    const double sc = upd_point_step(W.lm + tl * 12, lambda, xl);
+                    np0 = px + xl[0]; np1 = py + xl[1]; np2 = pz + xl[2];
+                    if (lane == W.lmoff[tl]) {      // first edge of the landmark: owner of the point
+                        const size_t gl = (size_t)T.lt + tl;
+                        gpointT[3 * gl] = np0; gpointT[3 * gl + 1] = np1; gpointT[3 * gl + 2] = np2;
+                        scale_acc += sc;
+                    }
+                }
+                if (act) {
+                    double r0, r1, r2, rho, wgt;
+                    edge_residual(sm.poseT + p * kPoseSm, np0, np1, np2, ou, ov, our, mono, K, r0, r1, r2);
+                    huber((r0 * r0 + r1 * r1 + r2 * r2) * K.inv_pv, K.delta, rho, wgt);
+                    chi_acc += rho;
+                }
+            }
+            __syncwarp();
+        } else {
+            // ---- one landmark with more than 32 edges: rounds of 32, sums by shuffle
+            const int gl = T.lt;
+            const uint8_t lf = B.lm_flags[gl];
+            const bool lmfree = (lf & kInHessian) != 0;
             const double px = gpoint[3 * (size_t)gl], py = gpoint[3 * (size_t)gl + 1], pz = gpoint[3 * (size_t)gl + 2];
-            double np0 = px, np1 = py, np2 = pz;
-            if (B.lm_flags[gl] & kInHessian) {
-                const double *ls = sm.lm + tid * 12;
-                double A[6] = {ls[0] + lambda, ls[1], ls[2], ls[3] + lambda, ls[4], ls[5] + lambda};
-                const double bl[3] = {ls[6], ls[7], ls[8]};
-                double c[3] = {bl[0] - ls[9], bl[1] - ls[10], bl[2] - ls[11]};
-                double Di[6], xl[3];
-                inv_sym3(A, Di);
-                sym3_mul(Di, c, xl);
-                np0 = px + xl[0]; np1 = py + xl[1]; np2 = pz + xl[2];
-                gpointT[3 * (size_t)gl] = np0; gpointT[3 * (size_t)gl + 1] = np1; gpointT[3 * (size_t)gl + 2] = np2;
-                scale_acc += xl[0] * (lambda * xl[0] + bl[0]) + xl[1] * (lambda * xl[1] + bl[1]) + xl[2] * (lambda * xl[2] + bl[2]);
+            double ls[12];
+#pragma unroll
+            for (int q = 0; q < 12; ++q) ls[q] = 0.0;
+            if (lmfree) {
+                for (int b0 = 0; b0 < T.ne; b0 += 32) {
+                    double hl[12];
+#pragma unroll
+                    for (int q = 0; q < 12; ++q) hl[q] = 0.0;
+                    if (b0 + lane < T.ne) {
+                        const int e = T.e0 + b0 + lane;
+                        const int pw = B.edge_pose[e];
+                        const int p = pw & kPoseMask;
+                        if (!(pw & kCulledBit) && !((lf & kFixed) && (B.pose_flags[pose_off + p] & kFixed))) {
+                            const int hi = sm.hidx[p];
+                            upd_edge_terms(sm.pose + p * kPoseSm, px, py, pz, B.obs_u[e], B.obs_v[e], B.obs_r[e], (pw & kMonoBit) != 0, K,
+                                           hi >= 0 ? sm.xp + hi * 6 : nullptr, hl);
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 12; ++q) {
+                        double v = hl[q];
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                        ls[q] += v;
+                    }
+                }
             }
-            sm.newp[tid * 3] = np0; sm.newp[tid * 3 + 1] = np1; sm.newp[tid * 3 + 2] = np2;
+            double np0 = px, np1 = py, np2 = pz;
+            if (lmfree) {
+                double xl[3];
+                const double sc = upd_point_step(ls, lambda, xl);
+                np0 = px + xl[0]; np1 = py + xl[1]; np2 = pz + xl[2];
+                if (lane == 0) {
+                    gpointT[3 * (size_t)gl] = np0; gpointT[3 * (size_t)gl + 1] = np1; gpointT[3 * (size_t)gl + 2] = np2;
+                    scale_acc += sc;
+                }
+            }
+            for (int b0 = 0; b0 < T.ne; b0 += 32) {
+                if (b0 + lane < T.ne) {
+                    const int e = T.e0 + b0 + lane;
+                    const int pw = B.edge_pose[e];
+                    const int p = pw & kPoseMask;
+                    if (!(pw & kCulledBit) && !((lf & kFixed) && (B.pose_flags[pose_off + p] & kFixed))) {
+                        double r0, r1, r2, rho, wgt;
+                        edge_residual(sm.poseT + p * kPoseSm, np0, np1, np2, B.obs_u[e], B.obs_v[e], B.obs_r[e], (pw & kMonoBit) != 0,
+                                      K, r0, r1, r2);
+                        huber((r0 * r0 + r1 * r1 + r2 * r2) * K.inv_pv, K.delta, rho, wgt);
+                        chi_acc += rho;
+                    }
+                }
+            }
         }
-        __syncthreads();
-        if (tid < ne && act) {
-            double r0, r1, r2;
-            edge_residual(sm.poseT + p * kPoseStride, sm.newp[tl * 3], sm.newp[tl * 3 + 1], sm.newp[tl * 3 + 2], rec.ou, rec.ov,
-                          rec.our, mono, K, r0, r1, r2);
-            double rho, wgt;
-            huber((r0 * r0 + r1 * r1 + r2 * r2) * K.inv_pv, K.delta, rho, wgt);
-            chi_acc += rho;
-        }
-        if (more) { T = Tn; rec = nxt; }
-        // (the next iteration's writes to sm.H / sm.lmoff come after every thread has passed the barrier above;
-        //  sm.newp is rewritten only after the next two barriers)
     }
     const double chi = block_sum(chi_acc, sm.red);
     const double sc = block_sum(scale_acc, sm.red);

@@ -82,7 +82,7 @@ struct visfs_ba_handle {
     // device memory
     DevBuf d_win, d_st, d_chunks, d_pose, d_point, d_pose_flags, d_lm_flags, d_pose_hidx, d_pose_active, d_point_hidx,
         d_lm_edge_off, d_obs_u, d_obs_v, d_obs_r, d_edge_pose, d_edge_point, d_edge_orig, d_covis, d_part, d_part2, d_xp,
-        d_n_running, d_tiles, d_tile_off, d_tile_cnt;
+        d_n_running, d_tiles, d_tile_off, d_tile_cnt, d_wtiles, d_wtile_off;
     DevBuf d_in_pose, d_in_point, d_in_pfix, d_in_lfix, d_in_obs, d_in_epose, d_in_epoint, d_in_ekind;
     DevBuf d_out_pose, d_out_point, d_out_level, d_tmp, d_tmp2, d_keys, d_keys2, d_perm;
     PinBuf h_stage, h_out, h_small;
@@ -192,6 +192,7 @@ Batch make_batch(visfs_ba_handle *h) {
     b.xp = h->d_xp.as<double>(); b.n_running = h->d_n_running.as<int>();
     b.dbg = nullptr; b.dbg_lambda = -1.0;
     b.tiles = h->d_tiles.as<Tile>(); b.chunk_tile_off = h->d_tile_off.as<int>();
+    b.wtiles = h->d_wtiles.as<Tile>(); b.chunk_wtile_off = h->d_wtile_off.as<int>();
     b.sky_first = h->d_sky_first.as<int>(); b.sky_off = h->d_sky_off.as<long long>();
     b.col_ptr = h->d_col_ptr.as<int>(); b.col_rows = h->d_col_rows.as<int>();
     b.red = h->d_red.as<double>(); b.red_g_off = 0; b.red_bp_off = 0; b.hdiag = h->d_hdiag.as<double>();
@@ -329,6 +330,7 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs) {
     const size_t max_tiles = 2 * E / (kTileEdges + 1) + L / kTileLm + 2 * (size_t)h->n_chunks + 8;
     CK(h->d_tiles.reserve(sizeof(Tile) * max_tiles));
     CK(h->d_tile_off.reserve(sizeof(int) * (h->n_chunks + 2))); CK(h->d_tile_cnt.reserve(sizeof(int) * (h->n_chunks + 2)));
+    CK(h->d_wtiles.reserve(sizeof(Tile) * (L + (size_t)h->n_chunks + 8))); CK(h->d_wtile_off.reserve(sizeof(int) * (h->n_chunks + 2)));
     CK(h->d_in_pose.reserve(sizeof(double) * 7 * P)); CK(h->d_in_point.reserve(sizeof(double) * 3 * L));
     CK(h->d_in_pfix.reserve(P)); CK(h->d_in_lfix.reserve(L));
     CK(h->d_in_obs.reserve(sizeof(double) * 3 * E)); CK(h->d_in_epose.reserve(sizeof(int) * E));
@@ -420,6 +422,10 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs) {
         CK(h->d_tmp2.reserve(tmp_bytes));
         CK(cub::DeviceScan::ExclusiveSum(h->d_tmp2.p, tmp_bytes, h->d_tile_cnt.as<int>(), h->d_tile_off.as<int>(), nc1, s));
         if (h->n_chunks) k_fill_tiles<<<(h->n_chunks + 127) / 128, 128, 0, s>>>(B, h->d_tile_off.as<int>(), h->d_tiles.as<Tile>());
+        // warp tiles of k_update (d_tile_cnt is reused: the scan above has consumed it)
+        k_count_wtiles<<<(nc1 + 127) / 128, 128, 0, s>>>(B, h->d_tile_cnt.as<int>());
+        CK(cub::DeviceScan::ExclusiveSum(h->d_tmp2.p, tmp_bytes, h->d_tile_cnt.as<int>(), h->d_wtile_off.as<int>(), nc1, s));
+        if (h->n_chunks) k_fill_wtiles<<<(h->n_chunks + 127) / 128, 128, 0, s>>>(B, h->d_wtile_off.as<int>(), h->d_wtiles.as<Tile>());
     }
     CK(cudaGetLastError());
     h->resident = true;
@@ -864,7 +870,7 @@ void visfs_ba_destroy(visfs_ba_handle *h) {
                       &h->d_pose_active, &h->d_point_hidx, &h->d_lm_edge_off, &h->d_obs_u, &h->d_obs_v, &h->d_obs_r, &h->d_edge_pose,
                       &h->d_edge_point, &h->d_edge_orig, &h->d_covis, &h->d_part, &h->d_part2, &h->d_xp, &h->d_n_running,
                       &h->d_in_pose, &h->d_in_point, &h->d_in_pfix, &h->d_in_lfix, &h->d_in_obs, &h->d_in_epose, &h->d_in_epoint,
-                      &h->d_in_ekind, &h->d_out_pose, &h->d_out_point, &h->d_out_level, &h->d_tmp, &h->d_tmp2, &h->d_keys, &h->d_keys2, &h->d_perm, &h->d_tiles, &h->d_tile_off, &h->d_tile_cnt};
+                      &h->d_in_ekind, &h->d_out_pose, &h->d_out_point, &h->d_out_level, &h->d_tmp, &h->d_tmp2, &h->d_keys, &h->d_keys2, &h->d_perm, &h->d_tiles, &h->d_tile_off, &h->d_tile_cnt, &h->d_wtiles, &h->d_wtile_off};
     for (DevBuf *b : bufs) b->release();
     h->h_stage.release(); h->h_out.release(); h->h_small.release();
     for (cudaEvent_t ev : h->ev_pool) cudaEventDestroy(ev);
