@@ -8,7 +8,7 @@ from visfs_b200 import capi, synth  # noqa: E402
 
 scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
 ba = capi.BundleAdjuster(0, profile_kernels=True)
-keys = ("total_ms", "build_ms", "solve_ms", "update_ms", "other_ms", "lm_iterations", "lm_trials", "kernel_launches")
+keys = ("solve_clocks", "total_ms", "build_ms", "solve_ms", "update_ms", "other_ms", "lm_iterations", "lm_trials", "kernel_launches")
 for name, make in (("C5", lambda: synth.config_c5(n_poses=200, n_points=int(200000 * scale))),
                    ("C4", lambda: synth.config_c4(n_poses=int(2000 * scale), n_points=int(500000 * scale)))):
     t0 = time.time()

@@ -17,10 +17,13 @@
 //                   extra right-hand-side row), row-oriented back-substitution, CameraPose::update.
 //   k_update_large  one warp per landmark: back-substitution of the landmark, point oplus, chi2 of the trial.
 #pragma once
+#include <cooperative_groups.h>
 #include "ba_kernels.cuh"
 
 namespace visfs {
 namespace lg {
+
+namespace cg = cooperative_groups;
 
 constexpr int kWarpsL = 8;
 constexpr int kThreadsL = kWarpsL * 32;
@@ -108,8 +111,10 @@ __global__ void k_col_count(Batch B, int *col_cnt) {
     for (int r = blockIdx.x; r < F; r += gridDim.x)
         for (int k = B.sky_first[r] + threadIdx.x; k < r; k += blockDim.x) atomicAdd(&col_cnt[k], 1);
 }
-__global__ void k_col_scan(Batch B, const int *col_cnt) {   // one CTA
+__global__ void k_col_scan(Batch B, const int *col_cnt, long long *info) {   // one CTA; info[2] = widest front
     __shared__ int s_carry;
+    __shared__ int s_max;
+    if (threadIdx.x == 0) s_max = 0;
     __shared__ int s_w[32];
     const int F = B.st[0].F;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
@@ -118,6 +123,7 @@ __global__ void k_col_scan(Batch B, const int *col_cnt) {   // one CTA
     for (int i0 = 0; i0 < F; i0 += blockDim.x) {
         const int i = i0 + tid;
         const int len = (i < F) ? col_cnt[i] : 0;
+        if (len > 0) atomicMax(&s_max, len);
         int v = len;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
@@ -130,7 +136,7 @@ __global__ void k_col_scan(Batch B, const int *col_cnt) {   // one CTA
         if (tid == 0) { int t = 0; for (int k = 0; k < nw; ++k) t += s_w[k]; s_carry += t; }
         __syncthreads();
     }
-    if (tid == 0) B.col_ptr[F] = s_carry;
+    if (tid == 0) { B.col_ptr[F] = s_carry; info[2] = s_max; }
 }
 // rows of column k in ascending order: row r lands at position (number of rows r' < r with first[r'] <= k < r').
 // One thread per (r, k) pair would need a rank; instead every column is filled by one warp scanning the candidate
@@ -397,19 +403,24 @@ __device__ __forceinline__ void row_solve6(const Chol6 &f, double *x) {
     x[0] = x0; x[1] = x1; x[2] = x2; x[3] = x3; x[4] = x4; x[5] = x5;
 }
 
-__global__ void __launch_bounds__(kSolveThreadsL) k_solve_large(Batch B) {
+// COOP = false: one CTA (banded systems: the column steps are short and __syncthreads is the cheap barrier)
+// COOP = true : cooperative launch over the whole GPU, grid.sync() between the panel and the trailing update of a column
+//               (wide fronts / dense systems: the trailing update of one column is thousands of 6x6 products);
+//               CTA 0 alone runs the back-substitution and the epilogue.
+template <bool COOP>
+__global__ void __launch_bounds__(kSolveThreadsL) k_solve_large(Batch B, int *flag) {
     const WinDesc &wd = B.win[0];
     LMState &st = B.st[0];
     if (st.done) return;
     const int tid = threadIdx.x;
+    const int gtid = COOP ? blockIdx.x * kSolveThreadsL + tid : tid;
+    const int gsize = COOP ? gridDim.x * kSolveThreadsL : kSolveThreadsL;
     const int F = st.F, n = 6 * F;
     const double lambda = (wd.trust == 0) ? (B.dbg_lambda >= 0.0 ? B.dbg_lambda : st.lambda) : 0.0;
-    __shared__ int s_ok;
     __shared__ double s_red[32];
     __shared__ double s_x[6];
-    if (tid == 0) s_ok = 1;
     if (n == 0) {
-        if (tid == 0) { st.ok = 1; st.scale_p = 0.0; }
+        if (gtid == 0) { st.ok = 1; st.scale_p = 0.0; }
         return;
     }
     double *__restrict__ sky = B.red;
@@ -417,7 +428,8 @@ __global__ void __launch_bounds__(kSolveThreadsL) k_solve_large(Batch B) {
     const double *__restrict__ braw = B.red + B.red_bp_off;
     const int *__restrict__ first = B.sky_first;
     const long long *__restrict__ off = B.sky_off;
-    __syncthreads();
+    cg::grid_group grid = cg::this_grid();
+    auto barrier = [&]() { if (COOP) grid.sync(); else __syncthreads(); };
 
     // ---- factorisation, one block column per step
     for (int k = 0; k < F; ++k) {
@@ -426,8 +438,9 @@ __global__ void __launch_bounds__(kSolveThreadsL) k_solve_large(Batch B) {
         double *dk = sky + (size_t)(off[k] + (k - first[k])) * 36;
         Chol6 f;
         const int ntask = 6 * m + 1;
-        if (tid < ntask) chol6(dk, lambda, f);   // every task owner factors the diagonal block redundantly
-        for (int t = tid; t < ntask; t += kSolveThreadsL) {
+        bool owner = false;                  // the thread that forward-substitutes the rhs also stores the diagonal factor
+        if (gtid < ntask) chol6(dk, lambda, f);   // every task owner factors the diagonal block redundantly
+        for (int t = gtid; t < ntask; t += gsize) {
             if (t < 6 * m) {                 // panel row: block L_rk, row a
                 const int r = rows[t / 6], a = t - (t / 6) * 6;
                 double *x = sky + (size_t)(off[r] + (k - first[r])) * 36 + a * 6;
@@ -439,12 +452,13 @@ __global__ void __launch_bounds__(kSolveThreadsL) k_solve_large(Batch B) {
                 double xv[6] = {y[6 * k], y[6 * k + 1], y[6 * k + 2], y[6 * k + 3], y[6 * k + 4], y[6 * k + 5]};
                 row_solve6(f, xv);           // (row vector times L^-T) == L^-1 applied to the column
 #pragma unroll
-                for (int q = 0; q < 6; ++q) { y[6 * k + q] = xv[q]; s_x[q] = xv[q]; }
-                if (!f.ok) s_ok = 0;
+                for (int q = 0; q < 6; ++q) y[6 * k + q] = xv[q];
+                if (!f.ok) *flag = 1;     // cleared by the host before the launch
+                owner = true;
             }
         }
-        __syncthreads();
-        if (tid == 0) {   // store the factor of the diagonal block (lower half + inverse pivots on demand)
+        barrier();
+        if (owner) {   // nobody reads the diagonal block again before the back-substitution
             dk[0] = f.L00;
             dk[6] = f.L10; dk[7] = f.L11;
             dk[12] = f.L20; dk[13] = f.L21; dk[14] = f.L22;
@@ -452,36 +466,44 @@ __global__ void __launch_bounds__(kSolveThreadsL) k_solve_large(Batch B) {
             dk[24] = f.L40; dk[25] = f.L41; dk[26] = f.L42; dk[27] = f.L43; dk[28] = f.L44;
             dk[30] = f.L50; dk[31] = f.L51; dk[32] = f.L52; dk[33] = f.L53; dk[34] = f.L54; dk[35] = f.L55;
         }
-        // rhs update: b_r -= L_rk y_k, one thread per (row block, row)
-        for (int t = tid; t < 6 * m; t += kSolveThreadsL) {
-            const int r = rows[t / 6], a = t - (t / 6) * 6;
-            const double *x = sky + (size_t)(off[r] + (k - first[r])) * 36 + a * 6;
-            double s = 0.0;
+        if (m > 0) {
+            const double y0 = y[6 * k], y1 = y[6 * k + 1], y2 = y[6 * k + 2], y3 = y[6 * k + 3], y4 = y[6 * k + 4], y5 = y[6 * k + 5];
+            // rhs update: b_r -= L_rk y_k, one thread per (row block, row)
+            for (int t = gtid; t < 6 * m; t += gsize) {
+                const int r = rows[t / 6], a = t - (t / 6) * 6;
+                const double *x = sky + (size_t)(off[r] + (k - first[r])) * 36 + a * 6;
+                y[6 * r + a] -= fma(x[0], y0, fma(x[1], y1, fma(x[2], y2, fma(x[3], y3, fma(x[4], y4, x[5] * y5)))));
+            }
+            // trailing update: A_rc -= L_rk L_ck^T for r >= c in the column structure (all inside the envelope);
+            // one thread per 6x6 row (6 entries): L_rk row a against the six rows of L_ck
+            const int pairs = m * (m + 1) / 2;
+            for (int item = gtid; item < pairs * 6; item += gsize) {
+                const int pr = item / 6, a = item - pr * 6;
+                int ri = (int)((sqrt(8.0 * (double)pr + 1.0) - 1.0) * 0.5);   // pr -> (ri >= ci)
+                while ((ri + 1) * (ri + 2) / 2 <= pr) ++ri;
+                while (ri * (ri + 1) / 2 > pr) --ri;
+                const int ci = pr - ri * (ri + 1) / 2;
+                const int r = rows[ri], cc = rows[ci];
+                const double *lr = sky + (size_t)(off[r] + (k - first[r])) * 36 + a * 6;
+                const double *lc = sky + (size_t)(off[cc] + (k - first[cc])) * 36;
+                double *dst = sky + (size_t)(off[r] + (cc - first[r])) * 36 + a * 6;
+                const double l0 = lr[0], l1 = lr[1], l2 = lr[2], l3 = lr[3], l4 = lr[4], l5 = lr[5];
+                double d[6];
 #pragma unroll
-            for (int q = 0; q < 6; ++q) s = fma(x[q], s_x[q], s);
-            y[6 * r + a] -= s;
-        }
-        // trailing update: A_rc -= L_rk L_ck^T for r >= c in the column structure (all inside the envelope)
-        const int pairs = m * (m + 1) / 2;
-        for (int item = tid; item < pairs * 36; item += kSolveThreadsL) {
-            const int pr = item / 36, q = item - pr * 36;
-            // pr -> (ri >= ci): ri = floor((sqrt(8 pr + 1) - 1) / 2)
-            int ri = (int)((sqrt(8.0 * (double)pr + 1.0) - 1.0) * 0.5);
-            while ((ri + 1) * (ri + 2) / 2 <= pr) ++ri;
-            while (ri * (ri + 1) / 2 > pr) --ri;
-            const int ci = pr - ri * (ri + 1) / 2;
-            const int a = q / 6, c = q - a * 6;
-            if (ri == ci && c > a) continue;
-            const int r = rows[ri], cc = rows[ci];
-            const double *lr = sky + (size_t)(off[r] + (k - first[r])) * 36 + a * 6;
-            const double *lc = sky + (size_t)(off[cc] + (k - first[cc])) * 36 + c * 6;
-            double s = 0.0;
+                for (int c = 0; c < 6; ++c) d[c] = dst[c];
 #pragma unroll
-            for (int u = 0; u < 6; ++u) s = fma(lr[u], lc[u], s);
-            sky[(size_t)(off[r] + (cc - first[r])) * 36 + a * 6 + c] -= s;
+                for (int c = 0; c < 6; ++c) {
+                    const double *w = lc + c * 6;
+                    d[c] -= fma(l0, w[0], fma(l1, w[1], fma(l2, w[2], fma(l3, w[3], fma(l4, w[4], l5 * w[5])))));
+                }
+                const int cmax = (ri == ci) ? a : 5;    // diagonal block: lower half only
+#pragma unroll
+                for (int c = 0; c < 6; ++c) if (c <= cmax) dst[c] = d[c];
+            }
         }
-        __syncthreads();
+        barrier();
     }
+    if (COOP && blockIdx.x != 0) return;
 
     // ---- back-substitution L^T x = y, row-oriented: x_r = L_rr^-T y_r, then y_c -= L_rc^T x_r for the row's blocks
     for (int r = F - 1; r >= 0; --r) {
@@ -514,7 +536,7 @@ __global__ void __launch_bounds__(kSolveThreadsL) k_solve_large(Batch B) {
     double bad = 0.0;
     for (int i = tid; i < n; i += kSolveThreadsL) if (!isfinite(y[i])) bad = 1.0;
     const double anybad = block_sum(bad, s_red);
-    const bool ok = (s_ok != 0) && (anybad == 0.0);
+    const bool ok = (*flag == 0) && (anybad == 0.0);
     __syncthreads();
     double sc = 0.0;
     for (int i = tid; i < n; i += kSolveThreadsL) {
@@ -535,6 +557,216 @@ __global__ void __launch_bounds__(kSolveThreadsL) k_solve_large(Batch B) {
         }
     }
     if (tid == 0) { st.ok = ok ? 1 : 0; st.scale_p = scale; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_solve_front: the same factorisation for NARROW fronts (banded systems with a few long rows: a trajectory with loop
+// closures).  The active front — pivot row k plus the rows of its column structure — lives in shared memory as a
+// kFrontSlots x kFrontSlots matrix of 6x6 blocks; a row occupies one slot from the column where it enters the
+// envelope until it has been the pivot (slots are planned on the host from sky_first, once per pass).  Per column:
+// entering rows are read from the skyline (their only trip through L2), panel + trailing update run entirely in shared
+// memory, finished columns of L go back to the skyline for the back-substitution.
+// ------------------------------------------------------------------------------------------------
+constexpr int kFrontSlots = 24;
+constexpr int kFrontMaxF = 3456;          // y (6F doubles) reuses the front's shared memory in the back-substitution
+
+struct FrontSmem {
+    double blk[kFrontSlots * kFrontSlots * 36];
+    double yf[kFrontSlots * 6];
+    double red[32];
+    double sx[6];
+    int col_ptr[kFrontMaxF + 2];
+    int rows[2][kFrontSlots];
+    int rslot[2][kFrontSlots];
+    int fail;
+    unsigned char slot[kFrontMaxF];
+};
+
+__global__ void __launch_bounds__(kSolveThreadsL) k_solve_front(Batch B, const unsigned char *slot_g, const int *enter_ptr,
+                                                               const int *enter_rows) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FrontSmem &sm = *reinterpret_cast<FrontSmem *>(smem_raw);
+    const WinDesc &wd = B.win[0];
+    LMState &st = B.st[0];
+    if (st.done) return;
+    const int tid = threadIdx.x;
+    const int F = st.F, n = 6 * F;
+    const double lambda = (wd.trust == 0) ? (B.dbg_lambda >= 0.0 ? B.dbg_lambda : st.lambda) : 0.0;
+    if (n == 0) {
+        if (tid == 0) { st.ok = 1; st.scale_p = 0.0; }
+        return;
+    }
+    constexpr int SL = kFrontSlots;
+    double *__restrict__ sky = B.red;
+    double *__restrict__ y = B.red + B.red_g_off;
+    const double *__restrict__ braw = B.red + B.red_bp_off;
+    const int *__restrict__ first = B.sky_first;
+    const long long *__restrict__ off = B.sky_off;
+    long long tclk[6];
+    tclk[0] = clock64();
+    for (int i = tid; i <= F; i += kSolveThreadsL) sm.col_ptr[i] = B.col_ptr[i];
+    for (int i = tid; i < F; i += kSolveThreadsL) sm.slot[i] = slot_g[i];
+    if (tid == 0) sm.fail = 0;
+    __syncthreads();
+    {   // column structure of the first pivot
+        const int m0 = sm.col_ptr[1] - sm.col_ptr[0];
+        if (tid < m0) { const int r = B.col_rows[tid]; sm.rows[0][tid] = r; sm.rslot[0][tid] = sm.slot[r]; }
+    }
+    __syncthreads();
+
+    tclk[1] = clock64();
+    for (int k = 0; k < F; ++k) {
+        const int c0 = sm.col_ptr[k], m = sm.col_ptr[k + 1] - c0;
+        const int *rows = sm.rows[k & 1], *rslot = sm.rslot[k & 1];
+        const int sk = sm.slot[k];
+        // ---- rows entering the envelope at this column: their blocks against every member of the front, and their rhs
+        const int e0 = enter_ptr[k], ne = enter_ptr[k + 1] - e0;
+        if (ne > 0) {
+            const int per = (m + 1) * 36;
+            for (int idx = tid; idx < ne * per; idx += kSolveThreadsL) {
+                const int er = idx / per, rem = idx - er * per;
+                const int qi = rem / 36, ent = rem - qi * 36;
+                const int r = enter_rows[e0 + er];
+                const int q = (qi == 0) ? k : rows[qi - 1];
+                const int hi = max(r, q), lo = min(r, q);
+                sm.blk[((int)sm.slot[hi] * SL + (int)sm.slot[lo]) * 36 + ent] = sky[(size_t)(off[hi] + (lo - first[hi])) * 36 + ent];
+            }
+            for (int idx = tid; idx < ne * 6; idx += kSolveThreadsL) {
+                const int r = enter_rows[e0 + idx / 6];
+                sm.yf[(int)sm.slot[r] * 6 + idx % 6] = y[6 * r + idx % 6];
+            }
+        }
+        __syncthreads();
+        // ---- panel: L_rk = A_rk L_kk^-T for the rows of the column structure, y_k = L_kk^-1 b_k
+        Chol6 f;
+        const int ntask = 6 * m + 1;
+        bool owner = false;
+        if (tid < ntask) chol6(sm.blk + (sk * SL + sk) * 36, lambda, f);
+        for (int t = tid; t < ntask; t += kSolveThreadsL) {
+            if (t < 6 * m) {
+                const int ri = t / 6, a = t - ri * 6;
+                const int r = rows[ri];
+                double *x = sm.blk + (rslot[ri] * SL + sk) * 36 + a * 6;
+                double xv[6] = {x[0], x[1], x[2], x[3], x[4], x[5]};
+                row_solve6(f, xv);
+                double *g = sky + (size_t)(off[r] + (k - first[r])) * 36 + a * 6;
+#pragma unroll
+                for (int q = 0; q < 6; ++q) { x[q] = xv[q]; g[q] = xv[q]; }
+            } else {
+                double xv[6];
+#pragma unroll
+                for (int q = 0; q < 6; ++q) xv[q] = sm.yf[sk * 6 + q];
+                row_solve6(f, xv);
+#pragma unroll
+                for (int q = 0; q < 6; ++q) { y[6 * k + q] = xv[q]; sm.sx[q] = xv[q]; }
+                if (!f.ok) sm.fail = 1;
+                owner = true;
+            }
+        }
+        __syncthreads();
+        if (owner) {
+            double *dk = sky + (size_t)(off[k] + (k - first[k])) * 36;
+            dk[0] = f.L00;
+            dk[6] = f.L10; dk[7] = f.L11;
+            dk[12] = f.L20; dk[13] = f.L21; dk[14] = f.L22;
+            dk[18] = f.L30; dk[19] = f.L31; dk[20] = f.L32; dk[21] = f.L33;
+            dk[24] = f.L40; dk[25] = f.L41; dk[26] = f.L42; dk[27] = f.L43; dk[28] = f.L44;
+            dk[30] = f.L50; dk[31] = f.L51; dk[32] = f.L52; dk[33] = f.L53; dk[34] = f.L54; dk[35] = f.L55;
+        }
+        // ---- rhs and trailing update of the front, all in shared memory
+        const int pairs = m * (m + 1) / 2;
+        for (int item = tid; item < pairs * 6 + 6 * m; item += kSolveThreadsL) {
+            if (item < pairs * 6) {
+                const int pr = item / 6, a = item - pr * 6;
+                int ri = (int)((sqrtf(8.0f * (float)pr + 1.0f) - 1.0f) * 0.5f);
+                while ((ri + 1) * (ri + 2) / 2 <= pr) ++ri;
+                while (ri * (ri + 1) / 2 > pr) --ri;
+                const int ci = pr - ri * (ri + 1) / 2;
+                const double *lr = sm.blk + (rslot[ri] * SL + sk) * 36 + a * 6;
+                const double *lc = sm.blk + (rslot[ci] * SL + sk) * 36;
+                double *dst = sm.blk + (rslot[ri] * SL + rslot[ci]) * 36 + a * 6;
+                const double l0 = lr[0], l1 = lr[1], l2 = lr[2], l3 = lr[3], l4 = lr[4], l5 = lr[5];
+#pragma unroll
+                for (int c = 0; c < 6; ++c) {
+                    const double *w = lc + c * 6;
+                    dst[c] -= fma(l0, w[0], fma(l1, w[1], fma(l2, w[2], fma(l3, w[3], fma(l4, w[4], l5 * w[5])))));
+                }
+            } else {
+                const int t = item - pairs * 6;
+                const int ri = t / 6, a = t - ri * 6;
+                const double *x = sm.blk + (rslot[ri] * SL + sk) * 36 + a * 6;
+                sm.yf[rslot[ri] * 6 + a] -= fma(x[0], sm.sx[0], fma(x[1], sm.sx[1], fma(x[2], sm.sx[2], fma(x[3], sm.sx[3], fma(x[4], sm.sx[4], x[5] * sm.sx[5])))));
+            }
+        }
+        // column structure of the next pivot (other buffer)
+        if (k + 1 < F) {
+            const int c1 = sm.col_ptr[k + 1], m1 = sm.col_ptr[k + 2] - c1;
+            if (tid < m1) { const int r = B.col_rows[c1 + tid]; sm.rows[(k + 1) & 1][tid] = r; sm.rslot[(k + 1) & 1][tid] = sm.slot[r]; }
+        }
+        __syncthreads();
+    }
+
+    // ---- back-substitution L^T x = y with y in shared memory (the front is no longer needed)
+    tclk[2] = clock64();
+    double *ys = sm.blk;
+    for (int i = tid; i < n; i += kSolveThreadsL) ys[i] = y[i];
+    __syncthreads();
+    for (int r = F - 1; r >= 0; --r) {
+        const double *dr = sky + (size_t)(off[r] + (r - first[r])) * 36;
+        if (tid == 0) {
+            double x5 = ys[6 * r + 5] / dr[35];
+            double x4 = (ys[6 * r + 4] - dr[34] * x5) / dr[28];
+            double x3 = (ys[6 * r + 3] - dr[33] * x5 - dr[27] * x4) / dr[21];
+            double x2 = (ys[6 * r + 2] - dr[32] * x5 - dr[26] * x4 - dr[20] * x3) / dr[14];
+            double x1 = (ys[6 * r + 1] - dr[31] * x5 - dr[25] * x4 - dr[19] * x3 - dr[13] * x2) / dr[7];
+            double x0 = (ys[6 * r] - dr[30] * x5 - dr[24] * x4 - dr[18] * x3 - dr[12] * x2 - dr[6] * x1) / dr[0];
+            ys[6 * r] = x0; ys[6 * r + 1] = x1; ys[6 * r + 2] = x2; ys[6 * r + 3] = x3; ys[6 * r + 4] = x4; ys[6 * r + 5] = x5;
+            sm.sx[0] = x0; sm.sx[1] = x1; sm.sx[2] = x2; sm.sx[3] = x3; sm.sx[4] = x4; sm.sx[5] = x5;
+        }
+        __syncthreads();
+        const int f0 = first[r], len = r - f0;
+        const double *rowblk = sky + (size_t)off[r] * 36;
+        for (int t = tid; t < 6 * len; t += kSolveThreadsL) {
+            const int cb = t / 6, a = t - cb * 6;
+            const double *blk = rowblk + (size_t)cb * 36;
+            double s = 0.0;
+#pragma unroll
+            for (int u = 0; u < 6; ++u) s = fma(blk[u * 6 + a], sm.sx[u], s);
+            ys[6 * (f0 + cb) + a] -= s;
+        }
+        __syncthreads();
+    }
+
+    tclk[3] = clock64();
+    // ---- solution checks, pose step, trial poses, pose part of g2o's computeScale
+    double bad = 0.0;
+    for (int i = tid; i < n; i += kSolveThreadsL) if (!isfinite(ys[i])) bad = 1.0;
+    const double anybad = block_sum(bad, sm.red);
+    const bool ok = (sm.fail == 0) && (anybad == 0.0);
+    __syncthreads();
+    double sc = 0.0;
+    for (int i = tid; i < n; i += kSolveThreadsL) {
+        const double x = ok ? ys[i] : 0.0;
+        B.xp[i] = x;
+        sc += x * (lambda * x + braw[i]);
+    }
+    const double scale = block_sum(sc, sm.red);
+    const int cur = st.cur;
+    const double *src = B.pose + (size_t)cur * B.tot_pose * kPoseStride;
+    double *dst = B.pose + (size_t)(1 - cur) * B.tot_pose * kPoseStride;
+    for (int p = tid; p < wd.n_pose; p += kSolveThreadsL) {
+        const int hi = B.pose_hidx[p];
+        if (hi >= 0) {
+            double dlt[6];
+            for (int a = 0; a < 6; ++a) dlt[a] = ok ? ys[6 * hi + a] : 0.0;
+            pose_oplus(src + (size_t)p * kPoseStride, dlt, dst + (size_t)p * kPoseStride);
+        }
+    }
+    if (tid == 0) {
+        st.ok = ok ? 1 : 0; st.scale_p = scale;
+        tclk[4] = tclk[5] = clock64();
+        for (int q = 0; q < 6; ++q) st.t_solve[q] = tclk[q] - tclk[0];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -106,6 +106,9 @@ struct visfs_ba_handle {
     bool large = false, partitioned = false;
     int grid_build_l = 1, grid_update_l = 1;
     long long n_sky = 0;
+    int max_front = 0, coop_grid = 0;
+    bool use_front = false;
+    DevBuf d_fslot, d_enter_ptr, d_enter_rows;
     DevBuf d_sky_first, d_sky_off, d_col_ptr, d_col_cnt, d_col_rows, d_red, d_hdiag, d_scal, d_info, d_cnt;
     Batch batch_ctl{};      // same as `batch`, with part2 pointing at the folded (and all-reduced) trial sums
     ncclComm_t comm = nullptr;
@@ -568,11 +571,12 @@ int run_structure_large(visfs_ba_handle *h) {
     if ((st = allreduce(h, h->d_sky_first.p, (size_t)h->tot_pose, ncclInt32, ncclMin))) return st;
     lg::k_sky_layout<<<1, 1024, 0, s>>>(B, h->d_col_cnt.as<int>(), h->d_info.as<long long>());
     lg::k_col_count<<<std::max(1, std::min(h->tot_pose, 1024)), 128, 0, s>>>(B, h->d_col_cnt.as<int>());
-    lg::k_col_scan<<<1, 1024, 0, s>>>(B, h->d_col_cnt.as<int>());
+    lg::k_col_scan<<<1, 1024, 0, s>>>(B, h->d_col_cnt.as<int>(), h->d_info.as<long long>());
     long long *info = h->h_small.as<long long>() + 2;
-    CK(cudaMemcpyAsync(info, h->d_info.p, sizeof(long long) * 2, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(info, h->d_info.p, sizeof(long long) * 3, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     h->n_sky = info[0];
+    h->max_front = (int)info[2];
     const long long F = info[1];
     const size_t red_len = (size_t)h->n_sky * 36 + 12 * (size_t)F;
     CK(h->d_red.reserve(sizeof(double) * std::max<size_t>(red_len, 8)));
@@ -583,6 +587,42 @@ int run_structure_large(visfs_ba_handle *h) {
         b->red_g_off = h->n_sky * 36; b->red_bp_off = h->n_sky * 36 + 6 * F;
     }
     lg::k_col_fill<<<std::max(1, std::min((h->tot_pose + 7) / 8, 512)), 256, 0, s>>>(h->batch);
+    // narrow fronts: plan the shared-memory slots of k_solve_front (a row holds a slot from the column where it enters
+    // the envelope until it has been the pivot)
+    h->use_front = false;
+    if (F > 0 && F <= lg::kFrontMaxF && h->max_front + 1 <= lg::kFrontSlots && !getenv("VISFS_BA_NO_FRONT")) {
+        std::vector<int> first((size_t)F);
+        CK(cudaMemcpyAsync(first.data(), h->d_sky_first.p, sizeof(int) * (size_t)F, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        std::vector<int> eptr((size_t)F + 1, 0), erows((size_t)F);
+        for (long long r = 0; r < F; ++r) eptr[(size_t)first[r] + 1] += 1;
+        for (long long k = 0; k < F; ++k) eptr[k + 1] += eptr[k];
+        {
+            std::vector<int> fill(eptr.begin(), eptr.end() - 1);
+            for (long long r = 0; r < F; ++r) erows[(size_t)fill[first[r]]++] = (int)r;   // ascending r inside a column
+        }
+        std::vector<unsigned char> slot((size_t)F, 0);
+        std::vector<int> free_slots;
+        for (int q = lg::kFrontSlots - 1; q >= 0; --q) free_slots.push_back(q);
+        bool ok = true;
+        for (long long k = 0; k < F && ok; ++k) {
+            for (int i = eptr[k]; i < eptr[k + 1]; ++i) {
+                if (free_slots.empty()) { ok = false; break; }
+                slot[(size_t)erows[i]] = (unsigned char)free_slots.back();
+                free_slots.pop_back();
+            }
+            free_slots.push_back(slot[(size_t)k]);
+        }
+        if (ok) {
+            CK(h->d_fslot.reserve((size_t)F)); CK(h->d_enter_ptr.reserve(sizeof(int) * ((size_t)F + 1)));
+            CK(h->d_enter_rows.reserve(sizeof(int) * (size_t)F));
+            CK(cudaMemcpyAsync(h->d_fslot.p, slot.data(), (size_t)F, cudaMemcpyHostToDevice, s));
+            CK(cudaMemcpyAsync(h->d_enter_ptr.p, eptr.data(), sizeof(int) * ((size_t)F + 1), cudaMemcpyHostToDevice, s));
+            CK(cudaMemcpyAsync(h->d_enter_rows.p, erows.data(), sizeof(int) * (size_t)F, cudaMemcpyHostToDevice, s));
+            CK(cudaStreamSynchronize(s));   // the host vectors go out of scope
+            h->use_front = true;
+        }
+    }
     CK(cudaGetLastError());
     h->launches += 11;
     return VISFS_BA_OK;
@@ -608,7 +648,19 @@ int enqueue_build_large(visfs_ba_handle *h) {
 int enqueue_rest_large(visfs_ba_handle *h) {
     int st;
     int ev = ev_begin(h, EV_SOLVE);
-    lg::k_solve_large<<<1, lg::kSolveThreadsL, 0, h->stream>>>(h->batch);
+    CK(cudaMemsetAsync(h->d_cnt.as<int>() + 2, 0, sizeof(int), h->stream));   // Cholesky failure flag
+    if (h->use_front) {
+        lg::k_solve_front<<<1, lg::kSolveThreadsL, sizeof(lg::FrontSmem), h->stream>>>(h->batch, h->d_fslot.as<unsigned char>(),
+                                                                                      h->d_enter_ptr.as<int>(), h->d_enter_rows.as<int>());
+    } else if (h->max_front > 32 && h->coop_grid > 1 && !getenv("VISFS_BA_NO_COOP")) {
+        // wide fronts (dense windows): the trailing update of a column is spread over the whole GPU
+        int *flag = h->d_cnt.as<int>() + 2;
+        void *args[] = {(void *)&h->batch, (void *)&flag};
+        CK(cudaLaunchCooperativeKernel((const void *)lg::k_solve_large<true>, dim3((unsigned)h->coop_grid), dim3(lg::kSolveThreadsL),
+                                       args, 0, h->stream));
+    } else {
+        lg::k_solve_large<false><<<1, lg::kSolveThreadsL, 0, h->stream>>>(h->batch, h->d_cnt.as<int>() + 2);
+    }
     ev_end(h, ev);
     ev = ev_begin(h, EV_UPDATE);
     lg::k_update_large<<<h->grid_update_l, lg::kThreadsL, 0, h->stream>>>(h->batch);
@@ -841,6 +893,14 @@ int visfs_ba_create(const visfs_ba_config *cfg, visfs_ba_handle **out) {
         fprintf(stderr, "[visfs_ba] k_solve: regs %d maxThreads %d static smem %zu\n", fa.numRegs, fa.maxThreadsPerBlock, fa.sharedSizeBytes);
         cudaGetLastError();
     }
+    {
+        int per_sm = 0, coop = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lg::k_solve_large<true>, lg::kSolveThreadsL, 0);
+        h->coop_grid = coop ? h->sm_count * std::max(per_sm, 0) : 0;
+        if (per_sm > 1) h->coop_grid = h->sm_count;   // one CTA per SM is enough
+    }
+    cudaFuncSetAttribute(lg::k_solve_front, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(lg::FrontSmem));
     cudaFuncSetAttribute(lg::k_build_large<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(lg::BuildSmemL));
     cudaFuncSetAttribute(lg::k_build_large<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(lg::BuildSmemL));
     e = cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -863,7 +923,7 @@ void visfs_ba_destroy(visfs_ba_handle *h) {
     cudaStreamSynchronize(h->stream);
     {
         DevBuf *lb[] = {&h->d_sky_first, &h->d_sky_off, &h->d_col_ptr, &h->d_col_cnt, &h->d_col_rows, &h->d_red, &h->d_hdiag,
-                        &h->d_scal, &h->d_info, &h->d_cnt};
+                        &h->d_scal, &h->d_info, &h->d_cnt, &h->d_fslot, &h->d_enter_ptr, &h->d_enter_rows};
         for (DevBuf *b : lb) b->release();
     }
     DevBuf *bufs[] = {&h->d_win, &h->d_st, &h->d_chunks, &h->d_pose, &h->d_point, &h->d_pose_flags, &h->d_lm_flags, &h->d_pose_hidx,
