@@ -562,28 +562,46 @@ __global__ void __launch_bounds__(kSolveThreadsL) k_solve_large(Batch B, int *fl
 // ------------------------------------------------------------------------------------------------
 // k_solve_front: the same factorisation for NARROW fronts (banded systems with a few long rows: a trajectory with loop
 // closures).  The active front — pivot row k plus the rows of its column structure — lives in shared memory as a
-// kFrontSlots x kFrontSlots matrix of 6x6 blocks; a row occupies one slot from the column where it enters the
-// envelope until it has been the pivot (slots are planned on the host from sky_first, once per pass).  Per column:
-// entering rows are read from the skyline (their only trip through L2), panel + trailing update run entirely in shared
-// memory, finished columns of L go back to the skyline for the back-substitution.
+// kFrontSlots x kFrontSlots matrix of 6x6 blocks; a row occupies one slot from the column where it enters the envelope
+// until one column after it has been the pivot.  The host plans the whole schedule from sky_first once per pass
+// (FrontPlan): slots, the rows entering at every column and the list of skyline blocks to bring in for them.  Per column
+// the panel and the trailing update run entirely in shared memory; everything the NEXT column needs from L2 (entering
+// blocks, slots, right-hand side) is loaded into registers at the start of the column and parked in shared memory at its
+// end, so no global-memory latency sits on the critical path.  Finished columns of L go back to the skyline for the
+// back-substitution, which keeps x in shared memory and prefetches one row ahead.
 // ------------------------------------------------------------------------------------------------
 constexpr int kFrontSlots = 24;
-constexpr int kFrontMaxF = 3456;          // y (6F doubles) reuses the front's shared memory in the back-substitution
+constexpr int kFrontMaxF = 2560;          // y (6F doubles) + row tables reuse the front's shared memory in the back-substitution
+constexpr int kFrontBS = 37;             // doubles per 6x6 block in shared memory: odd, so different blocks start in different banks
+constexpr int kFrontPitch = kFrontSlots + 1;   // blocks per row of the slot matrix: odd pitch * odd block size spreads a block column over the banks
+constexpr int kFrontLoaders = 96;         // threads (3 warps) that only stream the next column's data in; the rest compute
+
+struct FrontPlan {                        // device pointers of the host-built schedule
+    const unsigned char *pslot;           // [F]  slot of row r
+    const int *ent_ptr;                   // [F + 1] rows entering at column k ...
+    const int *ent_row, *ent_base;        // ... their index and sky_off - sky_first (blocks)
+    const int *ld_ptr;                    // [F + 1] skyline blocks to bring in before column k ...
+    const int *ld_src;                    // ... block index in the skyline
+    const unsigned short *ld_dst;         // ... slot_hi * kFrontPitch + slot_lo
+    const unsigned char *fr_slot;         // slots of the column structure, aligned with col_rows
+    const int *row_len, *row_off;         // [F] r - sky_first[r], sky_off[r]
+};
 
 struct FrontSmem {
-    double blk[kFrontSlots * kFrontSlots * 36];
+    double blk[kFrontSlots * kFrontPitch * kFrontBS];
     double yf[kFrontSlots * 6];
     double red[32];
     double sx[6];
     int col_ptr[kFrontMaxF + 2];
-    int rows[2][kFrontSlots];
+    int ent_ptr[kFrontMaxF + 2];
+    int ld_ptr[kFrontMaxF + 2];
+    int s_base[kFrontSlots];
     int rslot[2][kFrontSlots];
     int fail;
     unsigned char slot[kFrontMaxF];
 };
 
-__global__ void __launch_bounds__(kSolveThreadsL) k_solve_front(Batch B, const unsigned char *slot_g, const int *enter_ptr,
-                                                               const int *enter_rows) {
+__global__ void __launch_bounds__(kSolveThreadsL) k_solve_front(Batch B, FrontPlan P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FrontSmem &sm = *reinterpret_cast<FrontSmem *>(smem_raw);
     const WinDesc &wd = B.win[0];
@@ -596,60 +614,89 @@ __global__ void __launch_bounds__(kSolveThreadsL) k_solve_front(Batch B, const u
         if (tid == 0) { st.ok = 1; st.scale_p = 0.0; }
         return;
     }
-    constexpr int SL = kFrontSlots;
+    constexpr int SL = kFrontPitch, BS = kFrontBS;
+    constexpr int NC = kSolveThreadsL - kFrontLoaders;   // compute threads
+    const bool loader = tid >= NC;
+    const int ltid = tid - NC;
     double *__restrict__ sky = B.red;
     double *__restrict__ y = B.red + B.red_g_off;
     const double *__restrict__ braw = B.red + B.red_bp_off;
-    const int *__restrict__ first = B.sky_first;
-    const long long *__restrict__ off = B.sky_off;
     long long tclk[6];
     tclk[0] = clock64();
-    for (int i = tid; i <= F; i += kSolveThreadsL) sm.col_ptr[i] = B.col_ptr[i];
-    for (int i = tid; i < F; i += kSolveThreadsL) sm.slot[i] = slot_g[i];
-    if (tid == 0) sm.fail = 0;
+    for (int i = tid; i <= F; i += kSolveThreadsL) { sm.col_ptr[i] = B.col_ptr[i]; sm.ent_ptr[i] = P.ent_ptr[i]; sm.ld_ptr[i] = P.ld_ptr[i]; }
+    for (int i = tid; i < F; i += kSolveThreadsL) sm.slot[i] = P.pslot[i];
+    if (tid == 0) { sm.fail = 0; sm.col_ptr[F + 1] = B.col_ptr[F]; sm.ent_ptr[F + 1] = P.ent_ptr[F]; sm.ld_ptr[F + 1] = P.ld_ptr[F]; }
     __syncthreads();
-    {   // column structure of the first pivot
-        const int m0 = sm.col_ptr[1] - sm.col_ptr[0];
-        if (tid < m0) { const int r = B.col_rows[tid]; sm.rows[0][tid] = r; sm.rslot[0][tid] = sm.slot[r]; }
+    // what column 0 needs, without prefetch
+    {
+        const int m0 = sm.col_ptr[1], ne0 = sm.ent_ptr[1], nl0 = sm.ld_ptr[1] * 36;
+        if (tid < m0) sm.rslot[0][tid] = P.fr_slot[tid];
+        for (int i = tid; i < ne0; i += kSolveThreadsL) sm.s_base[sm.slot[P.ent_row[i]]] = P.ent_base[i];
+        for (int i = tid; i < ne0 * 6; i += kSolveThreadsL) { const int r = P.ent_row[i / 6]; sm.yf[(int)sm.slot[r] * 6 + i % 6] = y[6 * r + i % 6]; }
+        for (int i = tid; i < nl0; i += kSolveThreadsL) {
+            const int b = i / 36, ent = i - b * 36;
+            sm.blk[(int)P.ld_dst[b] * BS + ent] = sky[(size_t)P.ld_src[b] * 36 + ent];
+        }
     }
     __syncthreads();
-
     tclk[1] = clock64();
+
+    long long phA = 0, phB = 0, phL = 0;
     for (int k = 0; k < F; ++k) {
-        const int c0 = sm.col_ptr[k], m = sm.col_ptr[k + 1] - c0;
-        const int *rows = sm.rows[k & 1], *rslot = sm.rslot[k & 1];
+        const long long c_top = clock64();
+        const int m = sm.col_ptr[k + 1] - sm.col_ptr[k];
+        const int *rslot = sm.rslot[k & 1];
         const int sk = sm.slot[k];
-        // ---- rows entering the envelope at this column: their blocks against every member of the front, and their rhs
-        const int e0 = enter_ptr[k], ne = enter_ptr[k + 1] - e0;
-        if (ne > 0) {
-            const int per = (m + 1) * 36;
-            for (int idx = tid; idx < ne * per; idx += kSolveThreadsL) {
-                const int er = idx / per, rem = idx - er * per;
-                const int qi = rem / 36, ent = rem - qi * 36;
-                const int r = enter_rows[e0 + er];
-                const int q = (qi == 0) ? k : rows[qi - 1];
-                const int hi = max(r, q), lo = min(r, q);
-                sm.blk[((int)sm.slot[hi] * SL + (int)sm.slot[lo]) * 36 + ent] = sky[(size_t)(off[hi] + (lo - first[hi])) * 36 + ent];
+        if (loader) {
+            // ---- loader warps: everything column k + 1 needs from L2 goes straight into shared memory (its new rows use
+            //      slots outside the current front, so nothing the compute warps touch in this column is overwritten)
+            const int c1 = sm.col_ptr[k + 1], m1 = sm.col_ptr[k + 2] - c1;
+            const int e1 = sm.ent_ptr[k + 1], ne1 = sm.ent_ptr[k + 2] - e1;
+            const int l1 = sm.ld_ptr[k + 1], nl1 = (sm.ld_ptr[k + 2] - l1) * 36;
+            if (ltid < m1) sm.rslot[(k + 1) & 1][ltid] = P.fr_slot[c1 + ltid];
+            for (int i = ltid; i < ne1; i += kFrontLoaders) sm.s_base[sm.slot[P.ent_row[e1 + i]]] = P.ent_base[e1 + i];
+            for (int i = ltid; i < ne1 * 6; i += kFrontLoaders) {
+                const int r = P.ent_row[e1 + i / 6];
+                sm.yf[(int)sm.slot[r] * 6 + i % 6] = y[6 * r + i % 6];
             }
-            for (int idx = tid; idx < ne * 6; idx += kSolveThreadsL) {
-                const int r = enter_rows[e0 + idx / 6];
-                sm.yf[(int)sm.slot[r] * 6 + idx % 6] = y[6 * r + idx % 6];
+            int i = ltid;
+            for (; i + 3 * kFrontLoaders < nl1; i += 4 * kFrontLoaders) {   // four independent load chains per thread in flight
+                int b[4], ent[4], src[4], dst[4];
+                double v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { b[j] = (i + j * kFrontLoaders) / 36; ent[j] = (i + j * kFrontLoaders) - b[j] * 36; }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { src[j] = P.ld_src[l1 + b[j]]; dst[j] = P.ld_dst[l1 + b[j]]; }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[j] = sky[(size_t)src[j] * 36 + ent[j]];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) sm.blk[dst[j] * BS + ent[j]] = v[j];
             }
+            for (; i < nl1; i += kFrontLoaders) {
+                const int b = i / 36, ent = i - b * 36;
+                sm.blk[(int)P.ld_dst[l1 + b] * BS + ent] = sky[(size_t)P.ld_src[l1 + b] * 36 + ent];
+            }
+            phL += clock64() - c_top;
+            __syncthreads();   // (the compute warps' barrier after the panel)
+            __syncthreads();   // end of the column
+            continue;
         }
-        __syncthreads();
         // ---- panel: L_rk = A_rk L_kk^-T for the rows of the column structure, y_k = L_kk^-1 b_k
         Chol6 f;
         const int ntask = 6 * m + 1;
         bool owner = false;
-        if (tid < ntask) chol6(sm.blk + (sk * SL + sk) * 36, lambda, f);
-        for (int t = tid; t < ntask; t += kSolveThreadsL) {
+        if (tid < ntask) chol6(sm.blk + (sk * SL + sk) * BS, lambda, f);
+        for (int t = tid; t < ntask; t += NC) {
             if (t < 6 * m) {
                 const int ri = t / 6, a = t - ri * 6;
-                const int r = rows[ri];
-                double *x = sm.blk + (rslot[ri] * SL + sk) * 36 + a * 6;
+                const int rs = rslot[ri];
+                double *x = sm.blk + (rs * SL + sk) * BS + a * 6;
                 double xv[6] = {x[0], x[1], x[2], x[3], x[4], x[5]};
                 row_solve6(f, xv);
-                double *g = sky + (size_t)(off[r] + (k - first[r])) * 36 + a * 6;
+                double *g = sky + (size_t)(sm.s_base[rs] + k) * 36 + a * 6;
+#ifdef VISFS_FRONT_DEBUG
+                if (sm.s_base[rs] + k < 0 || (long long)(sm.s_base[rs] + k) * 36 >= B.red_g_off) { printf("panel oob k %d rs %d base %d\n", k, rs, sm.s_base[rs]); continue; }
+#endif
 #pragma unroll
                 for (int q = 0; q < 6; ++q) { x[q] = xv[q]; g[q] = xv[q]; }
             } else {
@@ -664,80 +711,133 @@ __global__ void __launch_bounds__(kSolveThreadsL) k_solve_front(Batch B, const u
             }
         }
         __syncthreads();
-        if (owner) {
-            double *dk = sky + (size_t)(off[k] + (k - first[k])) * 36;
-            dk[0] = f.L00;
-            dk[6] = f.L10; dk[7] = f.L11;
-            dk[12] = f.L20; dk[13] = f.L21; dk[14] = f.L22;
-            dk[18] = f.L30; dk[19] = f.L31; dk[20] = f.L32; dk[21] = f.L33;
-            dk[24] = f.L40; dk[25] = f.L41; dk[26] = f.L42; dk[27] = f.L43; dk[28] = f.L44;
-            dk[30] = f.L50; dk[31] = f.L51; dk[32] = f.L52; dk[33] = f.L53; dk[34] = f.L54; dk[35] = f.L55;
+        const long long c_mid = clock64();
+        phA += c_mid - c_top;
+        if (owner) {   // factor of the diagonal block for the back-substitution: strict lower part and RECIPROCAL pivots
+            double *dk = sky + (size_t)(sm.s_base[sk] + k) * 36;
+            dk[0] = f.i0;
+            dk[6] = f.L10; dk[7] = f.i1;
+            dk[12] = f.L20; dk[13] = f.L21; dk[14] = f.i2;
+            dk[18] = f.L30; dk[19] = f.L31; dk[20] = f.L32; dk[21] = f.i3;
+            dk[24] = f.L40; dk[25] = f.L41; dk[26] = f.L42; dk[27] = f.L43; dk[28] = f.i4;
+            dk[30] = f.L50; dk[31] = f.L51; dk[32] = f.L52; dk[33] = f.L53; dk[34] = f.L54; dk[35] = f.i5;
         }
-        // ---- rhs and trailing update of the front, all in shared memory
+        // ---- rhs and trailing update of the front, all in shared memory: one thread per half block (3 x 6 entries in registers)
         const int pairs = m * (m + 1) / 2;
-        for (int item = tid; item < pairs * 6 + 6 * m; item += kSolveThreadsL) {
-            if (item < pairs * 6) {
-                const int pr = item / 6, a = item - pr * 6;
+        for (int item = tid; item < pairs * 2 + 6 * m; item += NC) {
+            if (item < pairs * 2) {
+                const int pr = item >> 1, a0 = (item & 1) * 3;
                 int ri = (int)((sqrtf(8.0f * (float)pr + 1.0f) - 1.0f) * 0.5f);
                 while ((ri + 1) * (ri + 2) / 2 <= pr) ++ri;
                 while (ri * (ri + 1) / 2 > pr) --ri;
                 const int ci = pr - ri * (ri + 1) / 2;
-                const double *lr = sm.blk + (rslot[ri] * SL + sk) * 36 + a * 6;
-                const double *lc = sm.blk + (rslot[ci] * SL + sk) * 36;
-                double *dst = sm.blk + (rslot[ri] * SL + rslot[ci]) * 36 + a * 6;
-                const double l0 = lr[0], l1 = lr[1], l2 = lr[2], l3 = lr[3], l4 = lr[4], l5 = lr[5];
+                const double *lr = sm.blk + (rslot[ri] * SL + sk) * BS + a0 * 6;
+                const double *lc = sm.blk + (rslot[ci] * SL + sk) * BS;
+                double *dst = sm.blk + (rslot[ri] * SL + rslot[ci]) * BS + a0 * 6;
+                double L[18], acc[18];
+#pragma unroll
+                for (int q = 0; q < 18; ++q) { L[q] = lr[q]; acc[q] = dst[q]; }
 #pragma unroll
                 for (int c = 0; c < 6; ++c) {
-                    const double *w = lc + c * 6;
-                    dst[c] -= fma(l0, w[0], fma(l1, w[1], fma(l2, w[2], fma(l3, w[3], fma(l4, w[4], l5 * w[5])))));
+                    const double w0 = lc[c * 6], w1 = lc[c * 6 + 1], w2 = lc[c * 6 + 2], w3 = lc[c * 6 + 3], w4 = lc[c * 6 + 4], w5 = lc[c * 6 + 5];
+#pragma unroll
+                    for (int a = 0; a < 3; ++a)
+                        acc[a * 6 + c] -= fma(L[a * 6], w0, fma(L[a * 6 + 1], w1, fma(L[a * 6 + 2], w2, fma(L[a * 6 + 3], w3, fma(L[a * 6 + 4], w4, L[a * 6 + 5] * w5)))));
                 }
+#pragma unroll
+                for (int q = 0; q < 18; ++q) dst[q] = acc[q];
             } else {
-                const int t = item - pairs * 6;
+                const int t = item - pairs * 2;
                 const int ri = t / 6, a = t - ri * 6;
-                const double *x = sm.blk + (rslot[ri] * SL + sk) * 36 + a * 6;
+                const double *x = sm.blk + (rslot[ri] * SL + sk) * BS + a * 6;
                 sm.yf[rslot[ri] * 6 + a] -= fma(x[0], sm.sx[0], fma(x[1], sm.sx[1], fma(x[2], sm.sx[2], fma(x[3], sm.sx[3], fma(x[4], sm.sx[4], x[5] * sm.sx[5])))));
             }
         }
-        // column structure of the next pivot (other buffer)
-        if (k + 1 < F) {
-            const int c1 = sm.col_ptr[k + 1], m1 = sm.col_ptr[k + 2] - c1;
-            if (tid < m1) { const int r = B.col_rows[c1 + tid]; sm.rows[(k + 1) & 1][tid] = r; sm.rslot[(k + 1) & 1][tid] = sm.slot[r]; }
-        }
         __syncthreads();
+        phB += clock64() - c_mid;
     }
+#ifdef VISFS_FRONT_DEBUG
+    if (tid == 0 || tid == NC) printf("front tid %d: panel+barrier %lld  trailing+barrier %lld  loader busy %lld (cycles, %d columns)\n", tid, phA, phB, phL, F);
+#endif
 
-    // ---- back-substitution L^T x = y with y in shared memory (the front is no longer needed)
+    // ---- back-substitution L^T x = y: x in shared memory (the front is no longer needed), row r - 1 prefetched while
+    //      row r is applied
     tclk[2] = clock64();
     double *ys = sm.blk;
+    int *row_len = reinterpret_cast<int *>(sm.blk + 6 * kFrontMaxF);
+    int *row_off = row_len + kFrontMaxF;
     for (int i = tid; i < n; i += kSolveThreadsL) ys[i] = y[i];
+    for (int i = tid; i < F; i += kSolveThreadsL) { row_len[i] = P.row_len[i]; row_off[i] = P.row_off[i]; }
     __syncthreads();
-    for (int r = F - 1; r >= 0; --r) {
-        const double *dr = sky + (size_t)(off[r] + (r - first[r])) * 36;
+    double pf_d[21], pf_b[6];
+#pragma unroll
+    for (int q = 0; q < 21; ++q) pf_d[q] = 0.0;
+    auto prefetch_row = [&](int r) {
+        const int len = row_len[r];
+        const double *rowblk = sky + (size_t)row_off[r] * 36;
         if (tid == 0) {
-            double x5 = ys[6 * r + 5] / dr[35];
-            double x4 = (ys[6 * r + 4] - dr[34] * x5) / dr[28];
-            double x3 = (ys[6 * r + 3] - dr[33] * x5 - dr[27] * x4) / dr[21];
-            double x2 = (ys[6 * r + 2] - dr[32] * x5 - dr[26] * x4 - dr[20] * x3) / dr[14];
-            double x1 = (ys[6 * r + 1] - dr[31] * x5 - dr[25] * x4 - dr[19] * x3 - dr[13] * x2) / dr[7];
-            double x0 = (ys[6 * r] - dr[30] * x5 - dr[24] * x4 - dr[18] * x3 - dr[12] * x2 - dr[6] * x1) / dr[0];
+            const double *dr = rowblk + (size_t)len * 36;
+            int q = 0;
+#pragma unroll
+            for (int a = 0; a < 6; ++a)
+#pragma unroll
+                for (int c = 0; c <= a; ++c) pf_d[q++] = dr[a * 6 + c];
+        }
+        if (tid < 6 * len) {
+            const int cb = tid / 6, a = tid - cb * 6;
+            const double *blk = rowblk + (size_t)cb * 36;
+#pragma unroll
+            for (int u = 0; u < 6; ++u) pf_b[u] = blk[u * 6 + a];
+        }
+    };
+#ifdef VISFS_FRONT_DEBUG
+    if (tid == 0) printf("front: factor done F %d\n", F);
+#endif
+    prefetch_row(F - 1);
+    for (int r = F - 1; r >= 0; --r) {
+        double d[21], bq[6];
+#pragma unroll
+        for (int q = 0; q < 21; ++q) d[q] = pf_d[q];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) bq[q] = pf_b[q];
+        if (r > 0) prefetch_row(r - 1);
+        if (tid == 0) {   // d: packed lower triangle, row a starts at a (a + 1) / 2; diagonal entries are reciprocals
+            const double x5 = ys[6 * r + 5] * d[20];
+            const double x4 = (ys[6 * r + 4] - d[19] * x5) * d[14];
+            const double x3 = (ys[6 * r + 3] - d[18] * x5 - d[13] * x4) * d[9];
+            const double x2 = (ys[6 * r + 2] - d[17] * x5 - d[12] * x4 - d[8] * x3) * d[5];
+            const double x1 = (ys[6 * r + 1] - d[16] * x5 - d[11] * x4 - d[7] * x3 - d[4] * x2) * d[2];
+            const double x0 = (ys[6 * r] - d[15] * x5 - d[10] * x4 - d[6] * x3 - d[3] * x2 - d[1] * x1) * d[0];
             ys[6 * r] = x0; ys[6 * r + 1] = x1; ys[6 * r + 2] = x2; ys[6 * r + 3] = x3; ys[6 * r + 4] = x4; ys[6 * r + 5] = x5;
             sm.sx[0] = x0; sm.sx[1] = x1; sm.sx[2] = x2; sm.sx[3] = x3; sm.sx[4] = x4; sm.sx[5] = x5;
         }
         __syncthreads();
-        const int f0 = first[r], len = r - f0;
-        const double *rowblk = sky + (size_t)off[r] * 36;
-        for (int t = tid; t < 6 * len; t += kSolveThreadsL) {
-            const int cb = t / 6, a = t - cb * 6;
-            const double *blk = rowblk + (size_t)cb * 36;
+        const int len = row_len[r], f0 = r - len;
+        if (tid < 6 * len) {
+            const int cb = tid / 6, a = tid - cb * 6;
             double s = 0.0;
 #pragma unroll
-            for (int u = 0; u < 6; ++u) s = fma(blk[u * 6 + a], sm.sx[u], s);
+            for (int u = 0; u < 6; ++u) s = fma(bq[u], sm.sx[u], s);
             ys[6 * (f0 + cb) + a] -= s;
+        }
+        if (6 * len > kSolveThreadsL) {   // long rows (loop closures): the rest straight from L2
+            const double *rowblk = sky + (size_t)row_off[r] * 36;
+            for (int t = tid + kSolveThreadsL; t < 6 * len; t += kSolveThreadsL) {
+                const int cb = t / 6, a = t - cb * 6;
+                const double *blk = rowblk + (size_t)cb * 36;
+                double s = 0.0;
+#pragma unroll
+                for (int u = 0; u < 6; ++u) s = fma(blk[u * 6 + a], sm.sx[u], s);
+                ys[6 * (f0 + cb) + a] -= s;
+            }
         }
         __syncthreads();
     }
 
     tclk[3] = clock64();
+#ifdef VISFS_FRONT_DEBUG
+    if (tid == 0) printf("front: backsub done\n");
+#endif
     // ---- solution checks, pose step, trial poses, pose part of g2o's computeScale
     double bad = 0.0;
     for (int i = tid; i < n; i += kSolveThreadsL) if (!isfinite(ys[i])) bad = 1.0;

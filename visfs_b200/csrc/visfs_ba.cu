@@ -108,7 +108,8 @@ struct visfs_ba_handle {
     long long n_sky = 0;
     int max_front = 0, coop_grid = 0;
     bool use_front = false;
-    DevBuf d_fslot, d_enter_ptr, d_enter_rows;
+    DevBuf d_plan;
+    lg::FrontPlan front_plan{};
     DevBuf d_sky_first, d_sky_off, d_col_ptr, d_col_cnt, d_col_rows, d_red, d_hdiag, d_scal, d_info, d_cnt;
     Batch batch_ctl{};      // same as `batch`, with part2 pointing at the folded (and all-reduced) trial sums
     ncclComm_t comm = nullptr;
@@ -548,6 +549,107 @@ int allreduce(visfs_ba_handle *h, void *buf, size_t count, ncclDataType_t dt, nc
 }
 
 // ---- large-window path ---------------------------------------------------------------------------------------------
+
+// Schedule of k_solve_front (ba_large.cuh), built on the host from the envelope once per pass: which rows enter the
+// front at which column, the shared-memory slot each row holds, and the skyline blocks to bring in for the entering rows.
+// Leaves use_front = false when the front does not fit the slot matrix.
+int plan_front(visfs_ba_handle *h, int F) {
+    cudaStream_t s = h->stream;
+    std::vector<int> first((size_t)F);
+    CK(cudaMemcpyAsync(first.data(), h->d_sky_first.p, sizeof(int) * (size_t)F, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const int SL = lg::kFrontSlots;
+    std::vector<int> eptr((size_t)F + 1, 0), erow((size_t)F), ebase((size_t)F), row_len((size_t)F), row_off((size_t)F);
+    long long off = 0;
+    for (int r = 0; r < F; ++r) {
+        row_len[r] = r - first[r];
+        row_off[r] = (int)off;
+        off += row_len[r] + 1;
+        eptr[(size_t)first[r] + 1] += 1;
+    }
+    if (off != h->n_sky) return h->fail(VISFS_BA_ERR_CUDA, "front plan: envelope size differs from the device's");
+    for (int k = 0; k < F; ++k) eptr[k + 1] += eptr[k];
+    {
+        std::vector<int> fill(eptr.begin(), eptr.end() - 1);
+        for (int r = 0; r < F; ++r) {   // ascending r inside a column
+            const int i = fill[first[r]]++;
+            erow[i] = r;
+            ebase[i] = row_off[r] - first[r];
+        }
+    }
+    // column structure (rows r > k with first[r] <= k, ascending) — the same lists k_col_fill builds on the device
+    std::vector<int> cptr((size_t)F + 1, 0);
+    for (int r = 0; r < F; ++r) for (int k = first[r]; k < r; ++k) cptr[(size_t)k + 1] += 1;
+    for (int k = 0; k < F; ++k) cptr[k + 1] += cptr[k];
+    std::vector<int> crow((size_t)cptr[F]);
+    {
+        std::vector<int> fill(cptr.begin(), cptr.end() - 1);
+        for (int r = 0; r < F; ++r) for (int k = first[r]; k < r; ++k) crow[fill[k]++] = r;
+    }
+    // slots: a row takes one when it enters and gives it back one column after it was the pivot
+    std::vector<unsigned char> slot((size_t)F, 0);
+    std::vector<int> free_slots;
+    for (int q = SL - 1; q >= 0; --q) free_slots.push_back(q);
+    for (int k = 0; k < F; ++k) {
+        for (int i = eptr[k]; i < eptr[k + 1]; ++i) {
+            if (free_slots.empty()) return VISFS_BA_OK;   // front too wide: the other solvers take over
+            slot[(size_t)erow[i]] = (unsigned char)free_slots.back();
+            free_slots.pop_back();
+        }
+        if (k >= 1) free_slots.push_back(slot[(size_t)k - 1]);
+    }
+    std::vector<unsigned char> fr_slot(crow.size());
+    for (size_t i = 0; i < crow.size(); ++i) fr_slot[i] = slot[(size_t)crow[i]];
+    // skyline blocks to bring in for the rows entering at column k: against the pivot and every row of the column structure
+    std::vector<int> lptr((size_t)F + 1, 0), lsrc;
+    std::vector<unsigned short> ldst;
+    lsrc.reserve((size_t)h->n_sky); ldst.reserve((size_t)h->n_sky);
+    for (int k = 0; k < F; ++k) {
+        for (int i = eptr[k]; i < eptr[k + 1]; ++i) {
+            const int r = erow[i];
+            auto emit = [&](int q) {
+                if (first[q] == k && q > r) return;   // both enter here: emitted once, by the larger row
+                const int hi = std::max(r, q), lo = std::min(r, q);
+                lsrc.push_back(row_off[hi] + (lo - first[hi]));
+                ldst.push_back((unsigned short)(slot[(size_t)hi] * lg::kFrontPitch + slot[(size_t)lo]));
+            };
+            emit(k);
+            for (int c = cptr[k]; c < cptr[k + 1]; ++c) emit(crow[c]);
+        }
+        lptr[(size_t)k + 1] = (int)lsrc.size();
+    }
+    // one device buffer: [pslot | fr_slot | ldst | eptr | erow | ebase | lptr | lsrc | row_len | row_off]
+    auto al = [](size_t v) { return (v + 15) & ~(size_t)15; };
+    const size_t o_pslot = 0, o_fr = al(o_pslot + (size_t)F), o_ldst = al(o_fr + fr_slot.size()), o_eptr = al(o_ldst + 2 * ldst.size()),
+                 o_erow = al(o_eptr + 4 * ((size_t)F + 1)), o_ebase = al(o_erow + 4 * (size_t)F), o_lptr = al(o_ebase + 4 * (size_t)F),
+                 o_lsrc = al(o_lptr + 4 * ((size_t)F + 1)), o_rlen = al(o_lsrc + 4 * lsrc.size()), o_roff = al(o_rlen + 4 * (size_t)F),
+                 o_end = al(o_roff + 4 * (size_t)F);
+    std::vector<unsigned char> pack(o_end, 0);
+    memcpy(pack.data() + o_pslot, slot.data(), (size_t)F);
+    if (!fr_slot.empty()) memcpy(pack.data() + o_fr, fr_slot.data(), fr_slot.size());
+    if (!ldst.empty()) memcpy(pack.data() + o_ldst, ldst.data(), 2 * ldst.size());
+    memcpy(pack.data() + o_eptr, eptr.data(), 4 * ((size_t)F + 1));
+    memcpy(pack.data() + o_erow, erow.data(), 4 * (size_t)F);
+    memcpy(pack.data() + o_ebase, ebase.data(), 4 * (size_t)F);
+    memcpy(pack.data() + o_lptr, lptr.data(), 4 * ((size_t)F + 1));
+    if (!lsrc.empty()) memcpy(pack.data() + o_lsrc, lsrc.data(), 4 * lsrc.size());
+    memcpy(pack.data() + o_rlen, row_len.data(), 4 * (size_t)F);
+    memcpy(pack.data() + o_roff, row_off.data(), 4 * (size_t)F);
+    CK(h->d_plan.reserve(o_end));
+    CK(cudaMemcpyAsync(h->d_plan.p, pack.data(), o_end, cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));
+    const unsigned char *base = h->d_plan.as<unsigned char>();
+    lg::FrontPlan &P = h->front_plan;
+    P.pslot = base + o_pslot; P.fr_slot = base + o_fr;
+    P.ld_dst = reinterpret_cast<const unsigned short *>(base + o_ldst);
+    P.ent_ptr = reinterpret_cast<const int *>(base + o_eptr); P.ent_row = reinterpret_cast<const int *>(base + o_erow);
+    P.ent_base = reinterpret_cast<const int *>(base + o_ebase); P.ld_ptr = reinterpret_cast<const int *>(base + o_lptr);
+    P.ld_src = reinterpret_cast<const int *>(base + o_lsrc); P.row_len = reinterpret_cast<const int *>(base + o_rlen);
+    P.row_off = reinterpret_cast<const int *>(base + o_roff);
+    h->use_front = true;
+    return VISFS_BA_OK;
+}
+
 int run_structure_large(visfs_ba_handle *h) {
     Batch &B = h->batch;
     cudaStream_t s = h->stream;
@@ -587,41 +689,10 @@ int run_structure_large(visfs_ba_handle *h) {
         b->red_g_off = h->n_sky * 36; b->red_bp_off = h->n_sky * 36 + 6 * F;
     }
     lg::k_col_fill<<<std::max(1, std::min((h->tot_pose + 7) / 8, 512)), 256, 0, s>>>(h->batch);
-    // narrow fronts: plan the shared-memory slots of k_solve_front (a row holds a slot from the column where it enters
-    // the envelope until it has been the pivot)
     h->use_front = false;
-    if (F > 0 && F <= lg::kFrontMaxF && h->max_front + 1 <= lg::kFrontSlots && !getenv("VISFS_BA_NO_FRONT")) {
-        std::vector<int> first((size_t)F);
-        CK(cudaMemcpyAsync(first.data(), h->d_sky_first.p, sizeof(int) * (size_t)F, cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-        std::vector<int> eptr((size_t)F + 1, 0), erows((size_t)F);
-        for (long long r = 0; r < F; ++r) eptr[(size_t)first[r] + 1] += 1;
-        for (long long k = 0; k < F; ++k) eptr[k + 1] += eptr[k];
-        {
-            std::vector<int> fill(eptr.begin(), eptr.end() - 1);
-            for (long long r = 0; r < F; ++r) erows[(size_t)fill[first[r]]++] = (int)r;   // ascending r inside a column
-        }
-        std::vector<unsigned char> slot((size_t)F, 0);
-        std::vector<int> free_slots;
-        for (int q = lg::kFrontSlots - 1; q >= 0; --q) free_slots.push_back(q);
-        bool ok = true;
-        for (long long k = 0; k < F && ok; ++k) {
-            for (int i = eptr[k]; i < eptr[k + 1]; ++i) {
-                if (free_slots.empty()) { ok = false; break; }
-                slot[(size_t)erows[i]] = (unsigned char)free_slots.back();
-                free_slots.pop_back();
-            }
-            free_slots.push_back(slot[(size_t)k]);
-        }
-        if (ok) {
-            CK(h->d_fslot.reserve((size_t)F)); CK(h->d_enter_ptr.reserve(sizeof(int) * ((size_t)F + 1)));
-            CK(h->d_enter_rows.reserve(sizeof(int) * (size_t)F));
-            CK(cudaMemcpyAsync(h->d_fslot.p, slot.data(), (size_t)F, cudaMemcpyHostToDevice, s));
-            CK(cudaMemcpyAsync(h->d_enter_ptr.p, eptr.data(), sizeof(int) * ((size_t)F + 1), cudaMemcpyHostToDevice, s));
-            CK(cudaMemcpyAsync(h->d_enter_rows.p, erows.data(), sizeof(int) * (size_t)F, cudaMemcpyHostToDevice, s));
-            CK(cudaStreamSynchronize(s));   // the host vectors go out of scope
-            h->use_front = true;
-        }
+    if (F > 0 && F <= lg::kFrontMaxF && h->max_front + 2 <= lg::kFrontSlots && h->n_sky < 0x7fffffffLL / 36 && !getenv("VISFS_BA_NO_FRONT")) {
+        const int st2 = plan_front(h, (int)F);
+        if (st2) return st2;
     }
     CK(cudaGetLastError());
     h->launches += 11;
@@ -645,13 +716,21 @@ int enqueue_build_large(visfs_ba_handle *h) {
     return VISFS_BA_OK;
 }
 
+#define DBG_SYNC(what)                                                                              \
+    do {                                                                                            \
+        if (getenv("VISFS_BA_SYNC_DEBUG")) {                                                        \
+            cudaError_t e__ = cudaStreamSynchronize(h->stream);                                     \
+            if (e__ != cudaSuccess) return h->cuda_fail(e__, what);                                 \
+        }                                                                                           \
+    } while (0)
+
 int enqueue_rest_large(visfs_ba_handle *h) {
     int st;
+    DBG_SYNC("before solve (build / allreduce)");
     int ev = ev_begin(h, EV_SOLVE);
     CK(cudaMemsetAsync(h->d_cnt.as<int>() + 2, 0, sizeof(int), h->stream));   // Cholesky failure flag
     if (h->use_front) {
-        lg::k_solve_front<<<1, lg::kSolveThreadsL, sizeof(lg::FrontSmem), h->stream>>>(h->batch, h->d_fslot.as<unsigned char>(),
-                                                                                      h->d_enter_ptr.as<int>(), h->d_enter_rows.as<int>());
+        lg::k_solve_front<<<1, lg::kSolveThreadsL, sizeof(lg::FrontSmem), h->stream>>>(h->batch, h->front_plan);
     } else if (h->max_front > 32 && h->coop_grid > 1 && !getenv("VISFS_BA_NO_COOP")) {
         // wide fronts (dense windows): the trailing update of a column is spread over the whole GPU
         int *flag = h->d_cnt.as<int>() + 2;
@@ -662,6 +741,7 @@ int enqueue_rest_large(visfs_ba_handle *h) {
         lg::k_solve_large<false><<<1, lg::kSolveThreadsL, 0, h->stream>>>(h->batch, h->d_cnt.as<int>() + 2);
     }
     ev_end(h, ev);
+    DBG_SYNC("solve kernel");
     ev = ev_begin(h, EV_UPDATE);
     lg::k_update_large<<<h->grid_update_l, lg::kThreadsL, 0, h->stream>>>(h->batch);
     ev_end(h, ev);
@@ -670,6 +750,7 @@ int enqueue_rest_large(visfs_ba_handle *h) {
     if ((st = allreduce(h, h->d_scal.as<double>() + 2, 2, ncclFloat64, ncclSum))) return st;
     k_control<<<1, 32, 0, h->stream>>>(h->batch_ctl);
     ev_end(h, ev);
+    DBG_SYNC("update / fold / control");
     h->launches += 5;
     return VISFS_BA_OK;
 }
@@ -923,7 +1004,7 @@ void visfs_ba_destroy(visfs_ba_handle *h) {
     cudaStreamSynchronize(h->stream);
     {
         DevBuf *lb[] = {&h->d_sky_first, &h->d_sky_off, &h->d_col_ptr, &h->d_col_cnt, &h->d_col_rows, &h->d_red, &h->d_hdiag,
-                        &h->d_scal, &h->d_info, &h->d_cnt, &h->d_fslot, &h->d_enter_ptr, &h->d_enter_rows};
+                        &h->d_scal, &h->d_info, &h->d_cnt, &h->d_plan};
         for (DevBuf *b : lb) b->release();
     }
     DevBuf *bufs[] = {&h->d_win, &h->d_st, &h->d_chunks, &h->d_pose, &h->d_point, &h->d_pose_flags, &h->d_lm_flags, &h->d_pose_hidx,
