@@ -211,6 +211,9 @@ def global_ba_numbers(ba, dist, world, rank, barrier, reduce_max, quick):
     wall = time.perf_counter() - t0
     dev_s = reduce_max(dev_ms * 1e-3)
     r = ba.download()[0]
+    if world > 1:       # all ranks leave the communicator together, before rank 0 goes on alone
+        barrier()
+        ba.comm_destroy()
     out = {"workload": f"C4 global BA: {w['n_poses']} key frames on a loop, {w['n_points']} landmarks x 10 views = {w['n_edges']} "
                        f"stereo edges, landmarks partitioned over {world} GPU(s), NCCL all-reduce of the block-skyline reduced system",
            "scaling": "strong", "lm_iterations": int(t["lm_iterations"]), "lm_trials": int(t["lm_trials"]),
@@ -325,6 +328,10 @@ def run_gpu(args):
             gba = global_ba_numbers(ba, dist if world > 1 else None, world, rank, barrier, lambda v: reduce(v, MAX), args.quick)
         except Exception as exc:  # reported, never silently dropped
             gba = {"error": repr(exc)}
+            try:
+                ba.comm_destroy()
+            except Exception:
+                pass
 
     if rank != 0:
         ba.close()

@@ -335,6 +335,10 @@ class BundleAdjuster:
         dist.broadcast_object_list(box, src=0)
         self.comm_init(world, rank, box[0])
 
+    def comm_destroy(self):
+        """Tear the communicator down; every rank has to call this at the same point (NCCL finalises collectively)."""
+        self._check(self.lib.visfs_ba_comm_destroy(self.h))
+
     def comm_unique_id(self) -> bytes:
         buf = C.create_string_buffer(COMM_ID_BYTES)
         self._check(self.lib.visfs_ba_comm_unique_id(buf))
