@@ -119,7 +119,7 @@ def run_reference(args):
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    n_sample = max(cores, min(4 * cores, 64))
+    n_sample = max(cores, min(16 * cores, args.windows))
     windows = make_windows(n_sample, 0)
     for _ in range(min(args.warmup, 1)):
         cpu_solve_windows(windows[:cores], cores)
@@ -384,7 +384,7 @@ def run_gpu(args):
     if world == 1 and not args.no_cpu:
         from tests import oracle_api as O
         cores = os.cpu_count() or 1
-        n_sample = max(cores, min(4 * cores, 64))
+        n_sample = max(cores, min(16 * cores, args.windows))
         cpu_solve_windows(windows[:cores], cores)
         dt, it, tr, cres = cpu_solve_windows(windows[:n_sample], cores)
         for k in range(min(4, n_sample)):   # equal iteration / trial counts, otherwise the comparison is void

@@ -25,10 +25,11 @@ namespace ws {
 
 namespace cg = cooperative_groups;
 
-constexpr int kEdgeThreads = kTileEdges;      // 160
-constexpr int kPairThreads = 224;
+constexpr int kEdgeThreads = kTileEdges;      // 192
+constexpr int kPairThreads = 192;
 constexpr int kThreadsWs = kEdgeThreads + kPairThreads;   // 384
-constexpr int kMaxPosesWs = 20;               // F (F + 1) / 2 <= 210 block owners
+constexpr int kMaxFreeWs = 19;                // free poses F: F (F + 1) / 2 <= 190 block owners
+constexpr int kMaxPosesWs = 20;               // poses of a window (free + fixed)
 
 enum { BAR_PROD = 1, BAR_CONS = 2, BAR_FULL = 3, BAR_EMPTY = 5 };
 
@@ -46,13 +47,14 @@ struct Stage {
 };
 
 struct Smem {
-    double pose[kMaxSmallPoses * kPoseSm];
+    double pose[kMaxPosesWs * kPoseSm];
     Stage st[2];
-    double pacc[kMaxSmallPoses * kHStride];
+    double pacc[kMaxFreeWs * kHStride];
     int hidx[kMaxSmallPoses];
     int lmoff[kTileLm + 1];
 };
 constexpr int kStageDoubles = (int)(sizeof(Stage) / sizeof(double));
+static_assert(sizeof(Smem) <= 232448, "k_build_ws: shared memory over the 227 KB a CTA may use");
 
 // number of doubles of one partial system in the "all pairs" layout
 __host__ __device__ __forceinline__ int part_len(int F) { return F * (F + 1) / 2 * 36 + F * kHStride; }
@@ -100,7 +102,7 @@ __global__ void __maxnreg__(168) k_build_ws(Batch B, int cluster_size) {
 
     for (int i = tid; i < n_pose * kPoseStride; i += kThreadsWs) sm.pose[(i >> 4) * kPoseSm + (i & 15)] = gpose[i];
     for (int i = tid; i < n_pose; i += kThreadsWs) sm.hidx[i] = B.pose_hidx[pose_off + i];
-    for (int i = tid; i < kMaxSmallPoses * kHStride; i += kThreadsWs) sm.pacc[i] = 0.0;
+    for (int i = tid; i < kMaxFreeWs * kHStride; i += kThreadsWs) sm.pacc[i] = 0.0;
     __syncthreads();
 
     const int npairs = F * (F + 1) / 2;

@@ -28,10 +28,11 @@ enum { MODE_INIT = 0, MODE_BUILD = 1 };
 // ------------------------------------------------------------------------------------------------
 // shared-memory carve-up of k_build / k_update
 // ------------------------------------------------------------------------------------------------
-struct BuildSmem {
+template <int MODE>
+struct BuildSmemT {   // (the INIT pass stages only the per-edge H terms: without W / Y two CTAs fit one SM)
     double pose[kMaxSmallPoses * kPoseSm];
-    double W[kTileEdges * 18];
-    double Y[kTileEdges * 18];
+    double W[MODE == 1 ? kTileEdges * 18 : 2];
+    double Y[MODE == 1 ? kTileEdges * 18 : 2];
     double H[kTileEdges * kHStride];
     double lm[kTileLm * 12];                    // Dinv(6) db(3) bl(3)
     double pacc[kMaxSmallPoses * kHStride];
@@ -59,7 +60,7 @@ __device__ __forceinline__ int tile_end(const int *__restrict__ off, int lt, int
 template <int MODE, int PPT>
 __global__ void __launch_bounds__(kThreads, PPT == 1 ? 2 : 1) k_build(Batch B) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    BuildSmem &sm = *reinterpret_cast<BuildSmem *>(smem_raw);
+    BuildSmemT<MODE> &sm = *reinterpret_cast<BuildSmemT<MODE> *>(smem_raw);
     const int tid = threadIdx.x;
     const Chunk ck = B.chunks[blockIdx.x];
     const WinDesc &wd = B.win[ck.win];

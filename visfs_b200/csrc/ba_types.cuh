@@ -6,7 +6,7 @@
 namespace visfs {
 
 constexpr int kMaxSmallPoses = 32;   // windows with <= 32 poses take the shared-memory ("small") path
-constexpr int kTileEdges = 160;      // edge slots staged per tile (one thread per edge)
+constexpr int kTileEdges = 192;      // edge slots staged per tile (one thread per edge)
 constexpr int kTileLm = 32;          // landmarks per tile
 constexpr int kMaxDegLarge = 32;     // landmark degree limit of the large-window path (one lane per edge)
 constexpr int kThreads = 256;        // CTA size of the build / update kernels

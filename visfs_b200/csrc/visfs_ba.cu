@@ -217,7 +217,7 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs) {
     CK(cudaSetDevice(h->device));
     h->win.assign(n, WinDesc{});
     long long tp = 0, tl = 0, te = 0;
-    int max_pose = 0, max_point = 0, max_edge = 0, max_iter = 0;
+    int max_pose = 0, max_point = 0, max_edge = 0, max_iter = 0, max_free = 0;
     bool all_sorted = true, any_large = false, any_part = false;
     for (int w = 0; w < n; ++w) {
         const visfs_ba_problem &p = probs[w];
@@ -231,7 +231,7 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs) {
         any_large = any_large || big;
         any_part = any_part || part;
         // (the degree limit of the large path is checked on the device so that all ranks of a partitioned run agree)
-        if (!big && deg > kTileEdges) return h->fail(VISFS_BA_ERR_UNSUPPORTED, "landmark observed by more than 160 poses");
+        if (!big && deg > kTileEdges) return h->fail(VISFS_BA_ERR_UNSUPPORTED, "landmark observed by more poses than one tile holds (kTileEdges)");
         all_sorted = all_sorted && srt;
         WinDesc &d = h->win[w];
         d.pose_off = (int)tp; d.n_pose = p.n_poses; d.point_off = (int)tl; d.n_point = p.n_points;
@@ -243,6 +243,11 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs) {
         d.fx = p.fx; d.fy = p.fy; d.cx = p.cx; d.cy = p.cy; d.bf = p.bf;
         d.inv_pv = 1.0 / p.pixel_variance; d.delta = p.huber_delta;
         tp += p.n_poses; tl += p.n_points; te += p.n_edges;
+        {
+            int nfix = 0;
+            if (p.pose_fixed) for (int i = 0; i < p.n_poses; ++i) nfix += p.pose_fixed[i] != 0;
+            max_free = std::max(max_free, p.n_poses - nfix);   // upper bound of the free poses F of any pass
+        }
         max_pose = std::max(max_pose, p.n_poses); max_point = std::max(max_point, p.n_points);
         max_edge = std::max(max_edge, p.n_edges); max_iter = std::max(max_iter, d.max_iter);
         if (tp > 0x3fffffff || tl > 0x3fffffff || te > 0x3fffffff) return h->fail(VISFS_BA_ERR_INVALID, "batch too large");
@@ -260,7 +265,7 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs) {
     // kernel runs one CTA per SM, so the number of chunks is chosen to fill whole waves of `sm_count` CTAs:
     //   one window : up to sm_count chunks of >= 16 landmarks, clusters of up to 8 CTAs sum their partials
     //   a batch    : c chunks per window with c in 1..16 maximising n*c / (ceil(n*c / sm_count) * sm_count)
-    h->use_ws = (max_pose <= ws::kMaxPosesWs) && !getenv("VISFS_BA_NO_WS") && !any_large;
+    h->use_ws = (max_pose <= ws::kMaxPosesWs) && (max_free <= ws::kMaxFreeWs) && !getenv("VISFS_BA_NO_WS") && !any_large;
     const int sms = std::max(h->sm_count, 8);
     int per_window = 1;
     if (n == 1) {
@@ -483,7 +488,7 @@ int launch_build(visfs_ba_handle *h) {
         CK(cudaLaunchKernelEx(&cfg, ws::k_build_ws, h->batch, h->cluster));
         return VISFS_BA_OK;
     }
-    const size_t smem = sizeof(BuildSmem);
+    const size_t smem = sizeof(BuildSmemT<MODE>);
     if (h->max_pose <= 23) k_build<MODE, 1><<<h->n_chunks, kThreads, smem, h->stream>>>(h->batch);
     else k_build<MODE, 2><<<h->n_chunks, kThreads, smem, h->stream>>>(h->batch);
     return VISFS_BA_OK;
@@ -947,10 +952,10 @@ int visfs_ba_create(const visfs_ba_config *cfg, visfs_ba_handle **out) {
         delete h;
         return VISFS_BA_ERR_CUDA;
     }
-    const int smem_build = (int)sizeof(BuildSmem), smem_update = (int)sizeof(UpdateSmem);
-    cudaFuncSetAttribute(k_build<MODE_INIT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_build);
+    const int smem_build = (int)sizeof(BuildSmemT<MODE_BUILD>), smem_init = (int)sizeof(BuildSmemT<MODE_INIT>), smem_update = (int)sizeof(UpdateSmem);
+    cudaFuncSetAttribute(k_build<MODE_INIT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_init);
     cudaFuncSetAttribute(k_build<MODE_BUILD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_build);
-    cudaFuncSetAttribute(k_build<MODE_INIT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_build);
+    cudaFuncSetAttribute(k_build<MODE_INIT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_init);
     cudaFuncSetAttribute(k_build<MODE_BUILD, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_build);
     cudaFuncSetAttribute(k_update, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_update);
     e = cudaFuncSetAttribute(ws::k_build_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ws::Smem));
