@@ -574,7 +574,7 @@ constexpr int kFrontSlots = 24;
 constexpr int kFrontMaxF = 2560;          // y (6F doubles) + row tables reuse the front's shared memory in the back-substitution
 constexpr int kFrontBS = 37;             // doubles per 6x6 block in shared memory: odd, so different blocks start in different banks
 constexpr int kFrontPitch = kFrontSlots + 1;   // blocks per row of the slot matrix: odd pitch * odd block size spreads a block column over the banks
-constexpr int kFrontLoaders = 96;         // threads (3 warps) that only stream the next column's data in; the rest compute
+constexpr int kFrontLoaders = 128;        // threads (4 warps) that only stream the next column's data in; the rest compute
 
 struct FrontPlan {                        // device pointers of the host-built schedule
     const unsigned char *pslot;           // [F]  slot of row r
@@ -659,26 +659,18 @@ __global__ void __launch_bounds__(kSolveThreadsL) k_solve_front(Batch B, FrontPl
                 const int r = P.ent_row[e1 + i / 6];
                 sm.yf[(int)sm.slot[r] * 6 + i % 6] = y[6 * r + i % 6];
             }
-            int i = ltid;
-            for (; i + 3 * kFrontLoaders < nl1; i += 4 * kFrontLoaders) {   // four independent load chains per thread in flight
-                int b[4], ent[4], src[4], dst[4];
-                double v[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) { b[j] = (i + j * kFrontLoaders) / 36; ent[j] = (i + j * kFrontLoaders) - b[j] * 36; }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) { src[j] = P.ld_src[l1 + b[j]]; dst[j] = P.ld_dst[l1 + b[j]]; }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) v[j] = sky[(size_t)src[j] * 36 + ent[j]];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) sm.blk[dst[j] * BS + ent[j]] = v[j];
+            // one 6-entry row of a block per thread and step: one index load, then three 16-byte loads
+            const int nrow = (sm.ld_ptr[k + 2] - l1) * 6;
+            for (int i = ltid; i < nrow; i += kFrontLoaders) {
+                const int b = i / 6, a = i - b * 6;
+                const double2 *src = reinterpret_cast<const double2 *>(sky + (size_t)P.ld_src[l1 + b] * 36 + a * 6);
+                const double2 v0 = src[0], v1 = src[1], v2 = src[2];
+                double *d = sm.blk + (int)P.ld_dst[l1 + b] * BS + a * 6;
+                d[0] = v0.x; d[1] = v0.y; d[2] = v1.x; d[3] = v1.y; d[4] = v2.x; d[5] = v2.y;
             }
-            for (; i < nl1; i += kFrontLoaders) {
-                const int b = i / 36, ent = i - b * 36;
-                sm.blk[(int)P.ld_dst[l1 + b] * BS + ent] = sky[(size_t)P.ld_src[l1 + b] * 36 + ent];
-            }
+            (void)nl1;
             phL += clock64() - c_top;
-            __syncthreads();   // (the compute warps' barrier after the panel)
-            __syncthreads();   // end of the column
+            __syncthreads();   // end of the column (the barrier after the panel is the compute warps' own)
             continue;
         }
         // ---- panel: L_rk = A_rk L_kk^-T for the rows of the column structure, y_k = L_kk^-1 b_k
@@ -710,7 +702,7 @@ __global__ void __launch_bounds__(kSolveThreadsL) k_solve_front(Batch B, FrontPl
                 owner = true;
             }
         }
-        __syncthreads();
+        asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory");   // compute warps only: the loaders keep streaming
         const long long c_mid = clock64();
         phA += c_mid - c_top;
         if (owner) {   // factor of the diagonal block for the back-substitution: strict lower part and RECIPROCAL pivots
@@ -722,15 +714,16 @@ __global__ void __launch_bounds__(kSolveThreadsL) k_solve_front(Batch B, FrontPl
             dk[24] = f.L40; dk[25] = f.L41; dk[26] = f.L42; dk[27] = f.L43; dk[28] = f.i4;
             dk[30] = f.L50; dk[31] = f.L51; dk[32] = f.L52; dk[33] = f.L53; dk[34] = f.L54; dk[35] = f.i5;
         }
-        // ---- rhs and trailing update of the front, all in shared memory: one thread per half block (3 x 6 entries in registers)
+        // ---- rhs and trailing update of the front, all in shared memory: one thread per half block (3 x 6 entries).  Every
+        //      operand is loaded before the first store, so the loads pipeline; consecutive lanes share the column block,
+        //      whose rows are then broadcast loads
         const int pairs = m * (m + 1) / 2;
         for (int item = tid; item < pairs * 2 + 6 * m; item += NC) {
             if (item < pairs * 2) {
                 const int pr = item >> 1, a0 = (item & 1) * 3;
-                int ri = (int)((sqrtf(8.0f * (float)pr + 1.0f) - 1.0f) * 0.5f);
-                while ((ri + 1) * (ri + 2) / 2 <= pr) ++ri;
-                while (ri * (ri + 1) / 2 > pr) --ri;
-                const int ci = pr - ri * (ri + 1) / 2;
+                int ci = 0, base = 0;                       // pr -> (ci <= ri), column-major
+                while (base + (m - ci) <= pr) { base += m - ci; ++ci; }
+                const int ri = ci + (pr - base);
                 const double *lr = sm.blk + (rslot[ri] * SL + sk) * BS + a0 * 6;
                 const double *lc = sm.blk + (rslot[ci] * SL + sk) * BS;
                 double *dst = sm.blk + (rslot[ri] * SL + rslot[ci]) * BS + a0 * 6;
