@@ -68,6 +68,7 @@ struct UpdateSmem {
     UpdWarp w[kUpdWarps];
     double red[32];
     int hidx[kMaxSmallPoses];
+    unsigned char pflag[kMaxSmallPoses];
 };
 
 template <bool WRITE>
@@ -150,40 +151,54 @@ __global__ void __launch_bounds__(kUpdThreads, 2) k_update(Batch B) {
         const int j = (i >> 4) * kPoseSm + (i & 15);
         sm.pose[j] = gpose[i]; sm.poseT[j] = gposeT[i];
     }
-    for (int i = tid; i < n_pose; i += kUpdThreads) sm.hidx[i] = B.pose_hidx[pose_off + i];
+    for (int i = tid; i < n_pose; i += kUpdThreads) { sm.hidx[i] = B.pose_hidx[pose_off + i]; sm.pflag[i] = B.pose_flags[pose_off + i]; }
     for (int i = tid; i < st.F * 6; i += kUpdThreads) sm.xp[i] = B.xp[(size_t)pose_off * 6 + i];
     __syncthreads();
     UpdWarp &W = sm.w[warp];
     double chi_acc = 0.0, scale_acc = 0.0;
 
+    Tile Tnext{0, 0, 0, 0};
+    if (warp < ntiles) Tnext = tiles[warp];
     for (int t = warp; t < ntiles; t += kUpdWarps) {
-        const Tile T = tiles[t];
+        const Tile T = Tnext;
+        if (t + kUpdWarps < ntiles) Tnext = tiles[t + kUpdWarps];   // descriptor of the next tile: off the critical path
         if (T.ne <= 32) {
-            // ---- several whole landmarks, one edge per lane
-            if (lane <= T.ntl) W.lmoff[lane] = B.lm_edge_off[T.lt + lane] - T.e0;
+            // ---- several whole landmarks, one edge per lane.  Everything is addressed from the tile descriptor alone
+            //      (landmarks of a tile are consecutive), so all global loads of the tile are issued at once:
+            //      lane l holds CSR offset and flags of landmark l, lanes 0..3 ntl - 1 hold the tile's coordinates
+            const int off_l = (lane <= T.ntl) ? B.lm_edge_off[T.lt + lane] - T.e0 : 0x7fff;
+            const int lf_l = (lane < T.ntl) ? (int)B.lm_flags[T.lt + lane] : 0;
+            const double pt = (lane < 3 * T.ntl) ? gpoint[3 * (size_t)T.lt + lane] : 0.0;
+            int pw = 0;
+            double ou = 0, ov = 0, our = 0;
+            if (lane < T.ne) {
+                const int e = T.e0 + lane;
+                pw = B.edge_pose[e];
+                ou = B.obs_u[e]; ov = B.obs_v[e]; our = B.obs_r[e];
+            }
+            if (lane <= T.ntl) W.lmoff[lane] = off_l;
+            int tl = 0;
+#pragma unroll
+            for (int l = 1; l < kWtLm; ++l) {
+                const int v = __shfl_sync(0xffffffffu, off_l, l);
+                tl += (l < T.ntl && v <= lane) ? 1 : 0;
+            }
+            const int lf = __shfl_sync(0xffffffffu, lf_l, tl);
+            const double px = __shfl_sync(0xffffffffu, pt, 3 * tl), py = __shfl_sync(0xffffffffu, pt, 3 * tl + 1),
+                         pz = __shfl_sync(0xffffffffu, pt, 3 * tl + 2);
             bool act = false, mono = false, lmfree = false;
-            int tl = 0, p = 0;
-            double ou = 0, ov = 0, our = 0, px = 0, py = 0, pz = 0;
+            int p = 0;
             double hl[12];
 #pragma unroll
             for (int q = 0; q < 12; ++q) hl[q] = 0.0;
             if (lane < T.ne) {
-                const int e = T.e0 + lane;
-                const int pw = B.edge_pose[e];
-                const int gl = wd.point_off + B.edge_point[e];
                 p = pw & kPoseMask;
                 mono = (pw & kMonoBit) != 0;
-                tl = gl - T.lt;
-                const uint8_t lf = B.lm_flags[gl];
                 lmfree = (lf & kInHessian) != 0;
-                act = !(pw & kCulledBit) && !((lf & kFixed) && (B.pose_flags[pose_off + p] & kFixed));
-                px = gpoint[3 * (size_t)gl]; py = gpoint[3 * (size_t)gl + 1]; pz = gpoint[3 * (size_t)gl + 2];
-                if (act) {
-                    ou = B.obs_u[e]; ov = B.obs_v[e]; our = B.obs_r[e];
-                    if (lmfree) {
-                        const int hi = sm.hidx[p];
-                        upd_edge_terms(sm.pose + p * kPoseSm, px, py, pz, ou, ov, our, mono, K, hi >= 0 ? sm.xp + hi * 6 : nullptr, hl);
-                    }
+                act = !(pw & kCulledBit) && !((lf & kFixed) && (sm.pflag[p] & kFixed));
+                if (act && lmfree) {
+                    const int hi = sm.hidx[p];
+                    upd_edge_terms(sm.pose + p * kPoseSm, px, py, pz, ou, ov, our, mono, K, hi >= 0 ? sm.xp + hi * 6 : nullptr, hl);
                 }
 #pragma unroll
                 for (int q = 0; q < 12; ++q) W.H[lane * kHs + q] = hl[q];
