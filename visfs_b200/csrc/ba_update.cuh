@@ -295,4 +295,130 @@ __global__ void __launch_bounds__(kUpdThreads, 2) k_update(Batch B) {
     if (tid == 0) { B.part2[2 * (size_t)blockIdx.x] = chi; B.part2[2 * (size_t)blockIdx.x + 1] = sc; }
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_init: start of a pass — robust chi2 of the accepted state (computeActiveErrors + activeRobustChi2) and the diagonal
+// of H for OptimizationAlgorithmLevenberg::computeLambdaInit (max over poses AND landmarks).  Same warp tiles as k_update.
+// Per-pose diagonal sums stay deterministic without atomics: every warp owns a private [pose][6] table; inside a tile the
+// landmarks are added one after the other (the poses of one landmark are distinct, so the lanes of a round never collide).
+// Output per chunk (layout k_control_init reads): [F x 6 diag(H_pp) | chi2 | max |diag H_ll|].
+// ------------------------------------------------------------------------------------------------
+struct InitSmem {
+    double pose[kMaxSmallPoses * kPoseSm];
+    double pd[kUpdWarps][kMaxSmallPoses * 6];
+    double H[kUpdWarps][32 * 4];
+    double red[32];
+    int lmoff[kUpdWarps][kWtLm + 1];
+    int hidx[kMaxSmallPoses];
+    unsigned char pflag[kMaxSmallPoses];
+};
+
+__global__ void __launch_bounds__(kUpdThreads, 2) k_init(Batch B) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    InitSmem &sm = *reinterpret_cast<InitSmem *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const Chunk ck = B.chunks[blockIdx.x];
+    const WinDesc &wd = B.win[ck.win];
+    const LMState &st = B.st[ck.win];
+    if (st.done) return;
+    const int cur = st.cur, F = st.F;
+    const Intr K = load_intr(wd);
+    const int pose_off = wd.pose_off, n_pose = wd.n_pose;
+    const double *__restrict__ gpose = B.pose + ((size_t)cur * B.tot_pose + pose_off) * kPoseStride;
+    const double *__restrict__ gpoint = B.point + (size_t)cur * B.tot_point * 3;
+    const int tile0 = B.chunk_wtile_off[blockIdx.x], ntiles = B.chunk_wtile_off[blockIdx.x + 1] - tile0;
+    const Tile *__restrict__ tiles = B.wtiles + tile0;
+    for (int i = tid; i < n_pose * kPoseStride; i += kUpdThreads) sm.pose[(i >> 4) * kPoseSm + (i & 15)] = gpose[i];
+    for (int i = tid; i < n_pose; i += kUpdThreads) { sm.hidx[i] = B.pose_hidx[pose_off + i]; sm.pflag[i] = B.pose_flags[pose_off + i]; }
+    for (int i = tid; i < kUpdWarps * kMaxSmallPoses * 6; i += kUpdThreads) (&sm.pd[0][0])[i] = 0.0;
+    __syncthreads();
+    double *pd = sm.pd[warp], *Hs = sm.H[warp];
+    int *lmoff = sm.lmoff[warp];
+    double chi_acc = 0.0, maxd = 0.0;
+
+    Tile Tnext{0, 0, 0, 0};
+    if (warp < ntiles) Tnext = tiles[warp];
+    for (int t = warp; t < ntiles; t += kUpdWarps) {
+        const Tile T = Tnext;
+        if (t + kUpdWarps < ntiles) Tnext = tiles[t + kUpdWarps];
+        const int lf_l = (lane < T.ntl) ? (int)B.lm_flags[T.lt + lane] : 0;
+        const double pt = (lane < 3 * T.ntl) ? gpoint[3 * (size_t)T.lt + lane] : 0.0;
+        double hacc[3] = {0.0, 0.0, 0.0};     // long landmarks (> 32 edges): H_ll diagonal over the rounds
+        for (int b0 = 0; b0 < T.ne; b0 += 32) {
+            // (tiles of several landmarks have one round; a landmark with more than 32 edges is a tile of its own)
+            const int off_l = (lane <= T.ntl) ? B.lm_edge_off[T.lt + lane] - T.e0 - b0 : 0x7fff;
+            int pw = 0;
+            double ou = 0, ov = 0, our = 0;
+            const bool in = b0 + lane < T.ne;
+            if (in) {
+                const int e = T.e0 + b0 + lane;
+                pw = B.edge_pose[e];
+                ou = B.obs_u[e]; ov = B.obs_v[e]; our = B.obs_r[e];
+            }
+            if (lane <= T.ntl) lmoff[lane] = max(min(off_l, 32), 0);
+            int tl = 0;
+#pragma unroll
+            for (int l = 1; l < kWtLm; ++l) {
+                const int v = __shfl_sync(0xffffffffu, off_l, l);
+                tl += (l < T.ntl && v <= lane) ? 1 : 0;
+            }
+            const int lf = __shfl_sync(0xffffffffu, lf_l, tl);
+            const double px = __shfl_sync(0xffffffffu, pt, 3 * tl), py = __shfl_sync(0xffffffffu, pt, 3 * tl + 1),
+                         pz = __shfl_sync(0xffffffffu, pt, 3 * tl + 2);
+            bool act = false;
+            int hi = -1;
+            double dv[6] = {0, 0, 0, 0, 0, 0}, h3[3] = {0.0, 0.0, 0.0};
+            if (in) {
+                const int p = pw & kPoseMask;
+                act = !(pw & kCulledBit) && !((lf & kFixed) && (sm.pflag[p] & kFixed));
+                if (act) {
+                    EdgeLin lin;
+                    edge_linearize(sm.pose + p * kPoseSm, px, py, pz, ou, ov, our, (pw & kMonoBit) != 0, K, lin);
+                    chi_acc += lin.rho;
+                    const double wo = lin.w * K.inv_pv;
+                    hi = sm.hidx[p];
+                    if (lf & kInHessian) {
+                        const double *J = lin.Jl;
+                        h3[0] = wo * (J[0] * J[0] + J[3] * J[3] + J[6] * J[6]);
+                        h3[1] = wo * (J[1] * J[1] + J[4] * J[4] + J[7] * J[7]);
+                        h3[2] = wo * (J[2] * J[2] + J[5] * J[5] + J[8] * J[8]);
+                    }
+#pragma unroll
+                    for (int a = 0; a < 6; ++a)
+                        dv[a] = wo * (lin.Jp[a] * lin.Jp[a] + lin.Jp[6 + a] * lin.Jp[6 + a] + lin.Jp[12 + a] * lin.Jp[12 + a]);
+                }
+            }
+            Hs[lane * 4] = h3[0]; Hs[lane * 4 + 1] = h3[1]; Hs[lane * 4 + 2] = h3[2];
+            const int lf_task = __shfl_sync(0xffffffffu, lf_l, min(lane / 3, kWtLm - 1));   // flags of the landmark lane / 3 owns below
+            __syncwarp();
+            // diag(H_ll) per landmark in edge order
+            if (lane < T.ntl * 3) {
+                const int l = lane / 3, q = lane - l * 3;
+                double sacc = 0.0;
+                for (int e = lmoff[l]; e < lmoff[l + 1]; ++e) sacc += Hs[e * 4 + q];
+                if (T.ne > 32) { hacc[q] += sacc; sacc = hacc[q]; }
+                if (lf_task & kInHessian) maxd = fmax(maxd, fabs(sacc));
+            }
+            // diag(H_pp) per pose: one landmark per round
+            for (int l = 0; l < T.ntl; ++l) {
+                if (in && tl == l && act && hi >= 0) {
+#pragma unroll
+                    for (int a = 0; a < 6; ++a) pd[hi * 6 + a] += dv[a];
+                }
+                __syncwarp();
+            }
+        }
+    }
+    __syncthreads();
+    double *part = B.part + wd.part_off + (size_t)(blockIdx.x - wd.chunk_off) * wd.part_stride;
+    for (int task = tid; task < F * 6; task += kUpdThreads) {
+        double sacc = 0.0;
+#pragma unroll
+        for (int w = 0; w < kUpdWarps; ++w) sacc += sm.pd[w][task];
+        part[task] = sacc;
+    }
+    const double chi = block_sum(chi_acc, sm.red);
+    const double md = block_max(maxd, sm.red);
+    if (tid == 0) { part[F * 6] = chi; part[F * 6 + 1] = md; }
+}
+
 }  // namespace visfs

@@ -794,7 +794,7 @@ int run_pass(visfs_ba_handle *h, int pass) {
     } else {
         if ((st = run_structure(h))) return st;
         k_sync_buffers<<<dim3((unsigned)h->grid_lm_x, (unsigned)h->n_win), 256, 0, s>>>(B);
-        launch_build<MODE_INIT>(h);
+        if (h->n_chunks) k_init<<<h->n_chunks, kUpdThreads, sizeof(InitSmem), s>>>(B);
         k_control_init<<<h->n_win, 32, 0, s>>>(B);
         h->launches += 3;
     }
@@ -952,10 +952,8 @@ int visfs_ba_create(const visfs_ba_config *cfg, visfs_ba_handle **out) {
         delete h;
         return VISFS_BA_ERR_CUDA;
     }
-    const int smem_build = (int)sizeof(BuildSmemT<MODE_BUILD>), smem_init = (int)sizeof(BuildSmemT<MODE_INIT>), smem_update = (int)sizeof(UpdateSmem);
-    cudaFuncSetAttribute(k_build<MODE_INIT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_init);
+    const int smem_build = (int)sizeof(BuildSmemT<MODE_BUILD>), smem_update = (int)sizeof(UpdateSmem);
     cudaFuncSetAttribute(k_build<MODE_BUILD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_build);
-    cudaFuncSetAttribute(k_build<MODE_INIT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_init);
     cudaFuncSetAttribute(k_build<MODE_BUILD, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_build);
     cudaFuncSetAttribute(k_update, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_update);
     e = cudaFuncSetAttribute(ws::k_build_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ws::Smem));
@@ -1291,7 +1289,7 @@ int visfs_ba_debug_trial(visfs_ba_handle *h, const visfs_ba_problem *problem, do
         st = run_structure(h);
         if (st) return st;
         k_sync_buffers<<<dim3((unsigned)h->grid_lm_x, 1u), 256, 0, s>>>(h->batch);
-        launch_build<MODE_INIT>(h);
+        if (h->n_chunks) k_init<<<h->n_chunks, kUpdThreads, sizeof(InitSmem), s>>>(h->batch);
         k_control_init<<<1, 32, 0, s>>>(h->batch);
         CK(cudaMemcpyAsync(&before, h->d_st.p, sizeof(LMState), cudaMemcpyDeviceToHost, s));
         CK(dbg.reserve(sizeof(double) * (ntri_max + nmax + 8)));
