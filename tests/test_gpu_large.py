@@ -83,6 +83,14 @@ def test_large_gauss_newton_and_single_pass(ba):
     check_solution(ba.solve(w), O.solve(w), "no kernel")
 
 
+def test_large_solve_pcg(ba):
+    # Optimizer/Solver = 2 on the block skyline: g2o's block-Jacobi PCG, including its tolerance quirk
+    w = loop(seed=85, P=40, L=1200, solver=2, iterations=6)
+    check_solution(ba.solve(w), O.solve(w), "PCG, loop")
+    w = dense(seed=86, P=34, L=600, solver=2, iterations=4)
+    check_solution(ba.solve(w), O.solve(w), "PCG, dense")
+
+
 def test_large_rejected_steps(ba):
     w = synth.make_window(34, 400, views=6, layout="consecutive", seed=78, pose_noise=(0.3, np.deg2rad(6.0)), point_noise=0.5,
                           iterations=20, depth_range=(1.0, 6.0))

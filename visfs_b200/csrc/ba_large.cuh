@@ -863,6 +863,171 @@ __global__ void __launch_bounds__(kSolveThreadsL) k_solve_front(Batch B, FrontPl
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_solve_pcg: Optimizer/Solver = 2 on the block skyline — g2o LinearSolverPCG (block-Jacobi preconditioner = inverse 6x6
+// diagonal blocks, x0 = 0, at most n iterations, the tolerance quirk of k_solve).  Cooperative launch: one warp per block
+// row for S d (the lower part is the row's own skyline storage, the upper part the transposed blocks of its column
+// structure), dot products as per-CTA partials added in CTA order by every thread that needs them (deterministic),
+// three grid.sync() per iteration.  work = [r | d | q | s | x] (5n) + Minv (36F) + dot partials (2 x gridDim).
+// ------------------------------------------------------------------------------------------------
+constexpr int kPcgThreads = 256;
+
+__device__ __forceinline__ double grid_dot(cg::grid_group &grid, const double *u, const double *v, int n, double *partial, double *red) {
+    double acc = 0.0;
+    for (int i = blockIdx.x * kPcgThreads + threadIdx.x; i < n; i += gridDim.x * kPcgThreads) acc += u[i] * v[i];
+    const double t = block_sum(acc, red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = t;
+    grid.sync();
+    double s = 0.0;
+    for (int b = 0; b < (int)gridDim.x; ++b) s += partial[b];   // same order on every thread
+    return s;
+}
+
+__global__ void __launch_bounds__(kPcgThreads) k_solve_pcg(Batch B, double *work) {
+    const WinDesc &wd = B.win[0];
+    LMState &st = B.st[0];
+    if (st.done) return;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double s_red[32];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int gwarp = (blockIdx.x * kPcgThreads + tid) >> 5, nwarp = (gridDim.x * kPcgThreads) >> 5;
+    const int gtid = blockIdx.x * kPcgThreads + tid, gsize = gridDim.x * kPcgThreads;
+    const int F = st.F, n = 6 * F;
+    const double lambda = (wd.trust == 0) ? (B.dbg_lambda >= 0.0 ? B.dbg_lambda : st.lambda) : 0.0;
+    if (n == 0) {
+        if (gtid == 0) { st.ok = 1; st.scale_p = 0.0; }
+        return;
+    }
+    const double *__restrict__ sky = B.red;
+    const double *__restrict__ rhs = B.red + B.red_g_off;
+    const double *__restrict__ braw = B.red + B.red_bp_off;
+    const int *__restrict__ first = B.sky_first;
+    const long long *__restrict__ off = B.sky_off;
+    double *r = work, *d = work + n, *q = work + 2 * (size_t)n, *sv = work + 3 * (size_t)n, *xv = work + 4 * (size_t)n;
+    double *Minv = work + 5 * (size_t)n;
+    double *part0 = Minv + 36 * (size_t)F, *part1 = part0 + gridDim.x;
+
+    // block-Jacobi preconditioner: inverse of the damped diagonal blocks (Gauss-Jordan with partial pivoting)
+    for (int i = gtid; i < F; i += gsize) {
+        const double *blk = sky + (size_t)(off[i] + (i - first[i])) * 36;
+        double M[6][12];
+        for (int a = 0; a < 6; ++a)
+            for (int c = 0; c < 6; ++c) {
+                M[a][c] = blk[max(a, c) * 6 + min(a, c)] + (a == c ? lambda : 0.0);
+                M[a][6 + c] = (a == c) ? 1.0 : 0.0;
+            }
+        for (int c = 0; c < 6; ++c) {
+            int piv = c;
+            for (int a = c + 1; a < 6; ++a) if (fabs(M[a][c]) > fabs(M[piv][c])) piv = a;
+            if (piv != c) for (int k = 0; k < 12; ++k) { const double t = M[c][k]; M[c][k] = M[piv][k]; M[piv][k] = t; }
+            const double dd = M[c][c];
+            for (int k = 0; k < 12; ++k) M[c][k] /= dd;
+            for (int a = 0; a < 6; ++a) if (a != c) {
+                const double f = M[a][c];
+                for (int k = 0; k < 12; ++k) M[a][k] -= f * M[c][k];
+            }
+        }
+        for (int a = 0; a < 6; ++a) for (int c = 0; c < 6; ++c) Minv[36 * (size_t)i + 6 * a + c] = M[a][6 + c];
+    }
+    for (int i = gtid; i < n; i += gsize) { r[i] = rhs[i]; xv[i] = 0.0; }
+    grid.sync();
+    auto precond = [&](const double *in, double *out) {
+        for (int i = gtid; i < n; i += gsize) {
+            const int blk = i / 6, a = i - 6 * blk;
+            double acc = 0.0;
+            for (int c = 0; c < 6; ++c) acc += Minv[36 * (size_t)blk + 6 * a + c] * in[6 * blk + c];
+            out[i] = acc;
+        }
+    };
+    precond(r, d);
+    grid.sync();
+    double dn = grid_dot(grid, r, d, n, part0, s_red);
+    double d0 = 1e-6 * dn;
+    const double prev_res = st.pcg_residual;
+    if (prev_res > 0.0 && prev_res > 1e-6) d0 = 0.0;
+    for (int it = 0; it < n; ++it) {
+        if (dn <= d0) break;                       // dn is identical on every thread
+        // q = S d: one warp per block row
+        for (int row = gwarp; row < F; row += nwarp) {
+            double acc[6] = {0, 0, 0, 0, 0, 0};
+            const int f0 = first[row], len = row - f0;
+            const double *rowblk = sky + (size_t)off[row] * 36;
+            for (int ci = lane; ci <= len; ci += 32) {
+                const double *blk = rowblk + (size_t)ci * 36;
+                const double *x = d + 6 * (size_t)(f0 + ci);
+                if (ci < len) {
+#pragma unroll
+                    for (int a = 0; a < 6; ++a)
+#pragma unroll
+                        for (int u = 0; u < 6; ++u) acc[a] = fma(blk[a * 6 + u], x[u], acc[a]);
+                } else {                           // diagonal block: lower half stored, damping added here
+#pragma unroll
+                    for (int a = 0; a < 6; ++a)
+#pragma unroll
+                        for (int u = 0; u < 6; ++u)
+                            acc[a] = fma(blk[max(a, u) * 6 + min(a, u)] + (a == u ? lambda : 0.0), x[u], acc[a]);
+                }
+            }
+            const int c0 = B.col_ptr[row], m = B.col_ptr[row + 1] - c0;
+            for (int j = lane; j < m; j += 32) {
+                const int r2 = B.col_rows[c0 + j];
+                const double *blk = sky + (size_t)(off[r2] + (row - first[r2])) * 36;
+                const double *x = d + 6 * (size_t)r2;
+#pragma unroll
+                for (int a = 0; a < 6; ++a)
+#pragma unroll
+                    for (int u = 0; u < 6; ++u) acc[a] = fma(blk[u * 6 + a], x[u], acc[a]);
+            }
+#pragma unroll
+            for (int a = 0; a < 6; ++a) {
+                double v = acc[a];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0) q[6 * (size_t)row + a] = v;
+            }
+        }
+        grid.sync();
+        const double alpha = dn / grid_dot(grid, d, q, n, part1, s_red);
+        for (int i = gtid; i < n; i += gsize) { xv[i] += alpha * d[i]; r[i] -= alpha * q[i]; }
+        grid.sync();
+        precond(r, sv);
+        grid.sync();
+        const double dold = dn;
+        dn = grid_dot(grid, r, sv, n, part0, s_red);
+        const double beta = dn / dold;
+        for (int i = gtid; i < n; i += gsize) d[i] = sv[i] + beta * d[i];
+        grid.sync();
+    }
+    if (gtid == 0) st.pcg_residual = 0.5 * dn;
+    if (blockIdx.x != 0) return;
+
+    // ---- solution checks, pose step, trial poses, pose part of g2o's computeScale (CTA 0)
+    double bad = 0.0;
+    for (int i = tid; i < n; i += kPcgThreads) if (!isfinite(xv[i])) bad = 1.0;
+    const double anybad = block_sum(bad, s_red);
+    const bool ok = anybad == 0.0;
+    __syncthreads();
+    double sc = 0.0;
+    for (int i = tid; i < n; i += kPcgThreads) {
+        const double x = ok ? xv[i] : 0.0;
+        B.xp[i] = x;
+        sc += x * (lambda * x + braw[i]);
+    }
+    const double scale = block_sum(sc, s_red);
+    const int cur = st.cur;
+    const double *src = B.pose + (size_t)cur * B.tot_pose * kPoseStride;
+    double *dst = B.pose + (size_t)(1 - cur) * B.tot_pose * kPoseStride;
+    for (int p = tid; p < wd.n_pose; p += kPcgThreads) {
+        const int hi = B.pose_hidx[p];
+        if (hi >= 0) {
+            double dlt[6];
+            for (int a = 0; a < 6; ++a) dlt[a] = ok ? xv[6 * hi + a] : 0.0;
+            pose_oplus(src + (size_t)p * kPoseStride, dlt, dst + (size_t)p * kPoseStride);
+        }
+    }
+    if (tid == 0) { st.ok = ok ? 1 : 0; st.scale_p = scale; }
+}
+
+// ------------------------------------------------------------------------------------------------
 // k_update_large: landmark back-substitution, point oplus, chi2 of the trial state
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreadsL) k_update_large(Batch B) {

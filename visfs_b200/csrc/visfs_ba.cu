@@ -106,7 +106,8 @@ struct visfs_ba_handle {
     bool large = false, partitioned = false;
     int grid_build_l = 1, grid_update_l = 1;
     long long n_sky = 0;
-    int max_front = 0, coop_grid = 0;
+    int max_front = 0, coop_grid = 0, pcg_grid = 0;
+    DevBuf d_pcg;
     bool use_front = false;
     DevBuf d_plan;
     lg::FrontPlan front_plan{};
@@ -256,8 +257,8 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs) {
     h->max_pose = max_pose; h->max_iter = max_iter; h->sorted = all_sorted;
     h->large = any_large; h->partitioned = any_part;
     if (any_part && h->comm_ranks > 1 && !h->comm) return h->fail(VISFS_BA_ERR_INVALID, "partitioned problem without visfs_ba_comm_init");
-    if (any_large && probs[0].solver == VISFS_BA_SOLVER_PCG)
-        return h->fail(VISFS_BA_ERR_UNSUPPORTED, "Optimizer/Solver=2 (PCG) is implemented for windows of up to 32 poses only");
+    if (any_large && probs[0].solver == VISFS_BA_SOLVER_PCG && h->pcg_grid < 1)
+        return h->fail(VISFS_BA_ERR_UNSUPPORTED, "Optimizer/Solver=2 (PCG) on a large window needs cooperative kernel launches");
     h->grid_lm_x = std::max(1, std::min((max_point + 255) / 256, 1024));
     h->grid_edge_x = std::max(1, std::min((max_edge + 255) / 256, 1024));
 
@@ -734,7 +735,13 @@ int enqueue_rest_large(visfs_ba_handle *h) {
     DBG_SYNC("before solve (build / allreduce)");
     int ev = ev_begin(h, EV_SOLVE);
     CK(cudaMemsetAsync(h->d_cnt.as<int>() + 2, 0, sizeof(int), h->stream));   // Cholesky failure flag
-    if (h->use_front) {
+    if (h->win[0].solver == VISFS_BA_SOLVER_PCG) {
+        const size_t F = (size_t)std::max(h->tot_pose, 1);
+        CK(h->d_pcg.reserve(sizeof(double) * (5 * 6 * F + 36 * F + 2 * (size_t)h->pcg_grid + 8)));
+        double *work = h->d_pcg.as<double>();
+        void *args[] = {(void *)&h->batch, (void *)&work};
+        CK(cudaLaunchCooperativeKernel((const void *)lg::k_solve_pcg, dim3((unsigned)h->pcg_grid), dim3(lg::kPcgThreads), args, 0, h->stream));
+    } else if (h->use_front) {
         lg::k_solve_front<<<1, lg::kSolveThreadsL, sizeof(lg::FrontSmem), h->stream>>>(h->batch, h->front_plan);
     } else if (h->max_front > 32 && h->coop_grid > 1 && !getenv("VISFS_BA_NO_COOP")) {
         // wide fronts (dense windows): the trailing update of a column is spread over the whole GPU
@@ -983,6 +990,9 @@ int visfs_ba_create(const visfs_ba_config *cfg, visfs_ba_handle **out) {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lg::k_solve_large<true>, lg::kSolveThreadsL, 0);
         h->coop_grid = coop ? h->sm_count * std::max(per_sm, 0) : 0;
         if (per_sm > 1) h->coop_grid = h->sm_count;   // one CTA per SM is enough
+        int per_sm_pcg = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_pcg, lg::k_solve_pcg, lg::kPcgThreads, 0);
+        h->pcg_grid = (coop && per_sm_pcg > 0) ? h->sm_count : 0;
     }
     cudaFuncSetAttribute(lg::k_solve_front, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(lg::FrontSmem));
     cudaFuncSetAttribute(lg::k_build_large<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(lg::BuildSmemL));
@@ -1007,7 +1017,7 @@ void visfs_ba_destroy(visfs_ba_handle *h) {
     cudaStreamSynchronize(h->stream);
     {
         DevBuf *lb[] = {&h->d_sky_first, &h->d_sky_off, &h->d_col_ptr, &h->d_col_cnt, &h->d_col_rows, &h->d_red, &h->d_hdiag,
-                        &h->d_scal, &h->d_info, &h->d_cnt, &h->d_plan};
+                        &h->d_scal, &h->d_info, &h->d_cnt, &h->d_plan, &h->d_pcg};
         for (DevBuf *b : lb) b->release();
     }
     DevBuf *bufs[] = {&h->d_win, &h->d_st, &h->d_chunks, &h->d_pose, &h->d_point, &h->d_pose_flags, &h->d_lm_flags, &h->d_pose_hidx,
