@@ -24,21 +24,23 @@ __device__ __forceinline__ void edge_linearize_jx(const double *ps, double px, d
     r[0] = ou - u;
     r[1] = ov - v;
     r[2] = mono ? 0.0 : our - (u - bf * iz);
+    const double fxiz = fx * iz, fyiz = fy * iz;
+    const double bx = fxiz * (x * iz), by = fyiz * (y * iz), bb = bf * iz2;   // fx x / z^2, fy y / z^2, bf / z^2
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        const double j0 = -fx * R[k] * iz + fx * x * R[6 + k] * iz2;
-        const double j1 = -fy * R[3 + k] * iz + fy * y * R[6 + k] * iz2;
+        const double j0 = fma(bx, R[6 + k], -fxiz * R[k]);
+        const double j1 = fma(by, R[6 + k], -fyiz * R[3 + k]);
         Jl[k] = j0;
         Jl[3 + k] = j1;
-        Jl[6 + k] = mono ? 0.0 : j0 - bf * R[6 + k] * iz2;
+        Jl[6 + k] = mono ? 0.0 : fma(-bb, R[6 + k], j0);
     }
     if (xp) {
-        const double a0 = -iz * fx, a2 = x * iz2 * fx, a3 = x * y * iz2 * fx, a4 = -(1.0 + x * x * iz2) * fx, a5 = y * iz * fx;
-        const double b1 = -iz * fy, b2 = y * iz2 * fy, b3 = (1.0 + y * y * iz2) * fy, b4 = -x * y * iz2 * fy, b5 = -x * iz * fy;
+        const double a0 = -fxiz, a2 = bx, a3 = bx * y, a4 = -fma(bx, x, fx), a5 = fxiz * y;
+        const double b1 = -fyiz, b2 = by, b3 = fma(by, y, fy), b4 = -by * x, b5 = -fyiz * x;
         jx[0] = fma(a0, xp[0], fma(a2, xp[2], fma(a3, xp[3], fma(a4, xp[4], a5 * xp[5]))));
         jx[1] = fma(b1, xp[1], fma(b2, xp[2], fma(b3, xp[3], fma(b4, xp[4], b5 * xp[5]))));
-        jx[2] = mono ? 0.0
-                     : fma(a0, xp[0], fma(a2 - bf * iz2, xp[2], fma(a3 - bf * y * iz2, xp[3], fma(a4 + bf * x * iz2, xp[4], a5 * xp[5]))));
+        // row 2 = row 0 + bf / z^2 * (0, 0, -1, -y, x, 0)
+        jx[2] = mono ? 0.0 : fma(bb, fma(x, xp[4], -fma(y, xp[3], xp[2])), jx[0]);
     } else {
         jx[0] = jx[1] = jx[2] = 0.0;
     }
