@@ -43,7 +43,12 @@
  *   visfs_ba_comm_* / VISFS_BA_FLAG_PARTITIONED
  *       no reference equivalent (the reference is single process).  Global BA with the
  *       landmarks partitioned across ranks; reduced camera system summed with one
- *       ncclAllReduce per LM trial.
+ *       ncclAllReduce per LM trial (NCCL is bound with dlopen at visfs_ba_comm_init).
+ *
+ * Limits
+ *   - windows of up to 32 poses: any number per batch, landmarks with up to 192 observations;
+ *   - windows with more poses, and partitioned problems: one per call, landmarks with up to 32
+ *     observations (block-skyline path); all Optimizer/Solver values are implemented on both paths.
  *
  * Conventions
  *   - poses are T_camera<-world, stored t(3) then quaternion x,y,z,w  (CameraPose::toVector,

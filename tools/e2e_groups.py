@@ -1,0 +1,21 @@
+"""End-to-end time of visfs_ba_solve_batch (host buffers) for different pipeline group counts: VISFS_BA_GROUPS is read per call."""
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from visfs_b200 import capi, synth  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+ws = synth.config_c3_windows(n)
+ba = capi.BundleAdjuster(0)
+packed = ba.prepare_batch(ws)
+for g in (1, 2, 4, 8, 12, 16, 24):
+    os.environ["VISFS_BA_GROUPS"] = str(g)
+    for _ in range(2):
+        ba.solve_packed(packed)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        ba.solve_packed(packed)
+    dt = (time.perf_counter() - t0) / 3
+    print(f"groups {g:2d}: {1e3 * dt:7.2f} ms per batch of {n} windows", flush=True)

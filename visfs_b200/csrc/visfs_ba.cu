@@ -1060,10 +1060,15 @@ static int pick_groups(const visfs_ba_handle *h, int n, const visfs_ba_problem *
     if (h->is_sub || n < 32) return 1;
     for (int w = 0; w < n; ++w)
         if (problems[w].flags & VISFS_BA_FLAG_PARTITIONED) return 1;
-    int g = 8;
-    if (const char *e = getenv("VISFS_BA_GROUPS")) g = atoi(e);
+    int g = 16;
     const int hw = (int)std::thread::hardware_concurrency();
-    if (hw > 0) g = std::min(g, hw);
+    if (hw > 0) {
+        // one host thread per group; several ranks of one job (torchrun exports LOCAL_WORLD_SIZE) share the host cores
+        int share = hw;
+        if (const char *lws = getenv("LOCAL_WORLD_SIZE")) share = std::max(4, hw / std::max(atoi(lws), 1));
+        g = std::min(g, share);
+    }
+    if (const char *e = getenv("VISFS_BA_GROUPS")) g = atoi(e);
     g = std::min(g, n / 16);
     return std::max(g, 1);
 }
