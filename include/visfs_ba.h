@@ -16,7 +16,8 @@
  *       corelib/src/Optimizer/Optimizer.cpp:100-318 for the visual (stereo / mono)
  *       edges: vertex + edge set-up (100-114, 152-223), initializeOptimization +
  *       optimize(iterations/2) (261-265), the chi2 guards (268-280, 315-318), outlier
- *       culling by plain chi2 > delta (283-309) and the second pass (310-311).
+ *       culling by plain chi2 > delta (283-309) and the second pass (310-311); with n_links > 0
+ *       also the odometry pose-pose constraints of lines 116-150 (EdgePoseConstraint).
  *       The arithmetic it reproduces is corelib/include/Optimizer/g2o/OptimizeTypeDefine.h
  *       :16-191 (CameraPose, VertexPose, EdgeStereo) and
  *       corelib/src/Optimizer/g2o/OptimizeTypeDefine.cpp:7-14 (CameraPose::update),
@@ -48,7 +49,8 @@
  * Limits
  *   - windows of up to 32 poses: any number per batch, landmarks with up to 192 observations;
  *   - windows with more poses, and partitioned problems: one per call, landmarks with up to 32
- *     observations (block-skyline path); all Optimizer/Solver values are implemented on both paths.
+ *     observations (block-skyline path); all Optimizer/Solver values are implemented on both paths;
+ *     odometry links (n_links > 0) on the small-window path only.
  *
  * Conventions
  *   - poses are T_camera<-world, stored t(3) then quaternion x,y,z,w  (CameraPose::toVector,
@@ -74,7 +76,7 @@
 extern "C" {
 #endif
 
-#define VISFS_BA_ABI_VERSION 1
+#define VISFS_BA_ABI_VERSION 2
 
 typedef enum visfs_ba_status {
     VISFS_BA_OK = 0,
@@ -135,7 +137,14 @@ typedef struct visfs_ba_problem {
     int32_t iterations;          /* Optimizer/Iterations; each pass runs iterations / 2      */
     int32_t solver;              /* VISFS_BA_SOLVER_*                                        */
     int32_t trust_region;        /* VISFS_BA_LEVENBERG / VISFS_BA_GAUSS_NEWTON               */
-    int32_t reserved;
+    int32_t n_links;             /* odometry pose-pose constraints, 0 = none (Optimizer.cpp:116-150) */
+    /* EdgePoseConstraint (OptimizeTypeDefine.h:193-225, OptimizeTypeDefine.cpp:35-88): vertex 0 = from, vertex 1 = to,
+     * measurement T_c1c2 = T_rc^-1 * transform * T_rc (Optimizer.cpp:131-140), information = I6 / odometry_variance,
+     * no robust kernel, never culled.  Links in std::map order of their index; from != to. */
+    const int32_t *link_from;    /* [n_links] index into poses                               */
+    const int32_t *link_to;      /* [n_links] index into poses                               */
+    const double  *link_tq;      /* [n_links][7] measurement as tx ty tz qx qy qz qw         */
+    double odometry_variance;    /* Optimizer/OdometryCovariance (Parameters.h:189)          */
 } visfs_ba_problem;
 
 typedef struct visfs_ba_result {

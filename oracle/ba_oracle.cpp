@@ -137,6 +137,102 @@ inline bool inv3(const double *A, double *Ai) {  // Eigen 3x3 inverse (cofactor 
     return std::isfinite(id);
 }
 
+// ---- EdgePoseConstraint (OptimizeTypeDefine.h:193-225, OptimizeTypeDefine.cpp:35-88): odometry constraint between two
+// camera poses.  Quaternions are (x, y, z, w); products are Eigen's (Hamilton).
+inline void qmul(const double *a, const double *b, double *o) {
+    const double ax = a[0], ay = a[1], az = a[2], aw = a[3], bx = b[0], by = b[1], bz = b[2], bw = b[3];
+    o[3] = aw * bw - ax * bx - ay * by - az * bz;
+    o[0] = aw * bx + ax * bw + ay * bz - az * by;
+    o[1] = aw * by + ay * bw + az * bx - ax * bz;
+    o[2] = aw * bz + az * bw + ax * by - ay * bx;
+}
+inline void qinv(const double *q, double *o) {   // Eigen::Quaternion::inverse: conjugate / squaredNorm
+    const double n2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+    o[0] = -q[0] / n2; o[1] = -q[1] / n2; o[2] = -q[2] / n2; o[3] = q[3] / n2;
+}
+inline void matvec3(const double *R, const double *v, double *o) {
+    for (int i = 0; i < 3; ++i) o[i] = R[3 * i] * v[0] + R[3 * i + 1] * v[1] + R[3 * i + 2] * v[2];
+}
+inline void skew3(const double *v, double *S) {   // Math.h:293-300
+    S[0] = 0; S[1] = -v[2]; S[2] = v[1]; S[3] = v[2]; S[4] = 0; S[5] = -v[0]; S[6] = -v[1]; S[7] = v[0]; S[8] = 0;
+}
+inline void qpositify(const double *q, double *o) {   // Math.h:308-316
+    double s = (q[3] < 0) ? -1.0 : 1.0;
+    double t[4] = {s * q[0], s * q[1], s * q[2], s * q[3]};
+    const double n = std::sqrt(t[0] * t[0] + t[1] * t[1] + t[2] * t[2] + t[3] * t[3]);
+    for (int i = 0; i < 4; ++i) o[i] = t[i] / n;
+}
+// bottom-right 3x3 of QuaternionLeft(q) (Math.h:324-331): w I + skew(v), and of QuaternionRight(q) (:339-346): w I - skew(v);
+// the full 4x4 are [[w, -v^T], [v, w I +- skew(v)]]
+inline void qleft(const double *q, double *M /* 4x4 row-major */) {
+    double p[4]; qpositify(q, p);
+    const double x = p[0], y = p[1], z = p[2], w = p[3];
+    const double m[16] = {w, -x, -y, -z,   x, w, -z, y,   y, z, w, -x,   z, -y, x, w};
+    std::memcpy(M, m, sizeof m);
+}
+inline void qright(const double *q, double *M) {
+    double p[4]; qpositify(q, p);
+    const double x = p[0], y = p[1], z = p[2], w = p[3];
+    const double m[16] = {w, -x, -y, -z,   x, w, z, -y,   y, -z, w, x,   z, y, -x, w};
+    std::memcpy(M, m, sizeof m);
+}
+
+// EdgePoseConstraint::computeError (OptimizeTypeDefine.cpp:35-51): tq1 / tq2 = (t, q) of vertex 0 / 1, m = measurement
+inline void linkError(const double *tq1, const double *tq2, const double *m, double *e /* 6 */) {
+    double q2i[4], q12[4], R12[9], nP2[3] = {-tq2[0], -tq2[1], -tq2[2]}, rp[3];
+    qinv(tq2 + 3, q2i);
+    qmul(tq1 + 3, q2i, q12);
+    quatToR(q12, R12);
+    matvec3(R12, nP2, rp);
+    for (int i = 0; i < 3; ++i) e[i] = rp[i] + tq1[i] - m[i];
+    double mi[4], t[4];
+    qinv(m + 3, mi);
+    qmul(mi, q12, t);
+    e[3] = 2 * t[0]; e[4] = 2 * t[1]; e[5] = 2 * t[2];
+}
+
+// EdgePoseConstraint::linearizeOplus, the live "Left update" branch (OptimizeTypeDefine.cpp:53-72): 6x6 row-major each
+inline void linkJacobians(const double *tq1, const double *tq2, const double *m, double *Ji, double *Jj) {
+    std::fill(Ji, Ji + 36, 0.0); std::fill(Jj, Jj + 36, 0.0);
+    double q1i[4], q2i[4], q12[4], R1[9], R2i[9], R12[9], nP2[3] = {-tq2[0], -tq2[1], -tq2[2]};
+    qinv(tq1 + 3, q1i); qinv(tq2 + 3, q2i);
+    qmul(tq1 + 3, q2i, q12);
+    quatToR(tq1 + 3, R1); quatToR(q2i, R2i); quatToR(q12, R12);
+    // Xi
+    for (int i = 0; i < 3; ++i) Ji[6 * i + i] = 1.0;
+    double t1[3], t2[3], S[9];
+    matvec3(R2i, nP2, t1); matvec3(R1, t1, t2);          // sQ1 * (sQ2.inverse() * (-sP2))
+    skew3(t2, S);
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Ji[6 * i + 3 + j] = -S[3 * i + j];
+    double q21[4], QL[16], QR[16];
+    qmul(tq2 + 3, q1i, q21);                              // sQ2 * sQ1.inverse()
+    qleft(q21, QL); qright(m + 3, QR);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            double acc = 0;
+            for (int k = 0; k < 4; ++k) acc += QL[4 * (i + 1) + k] * QR[4 * k + (j + 1)];
+            Ji[6 * (3 + i) + 3 + j] = acc;
+        }
+    // Xj
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Jj[6 * i + j] = -R12[3 * i + j];
+    double Sn[9], R1R2i[9];
+    skew3(nP2, Sn);
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+        double acc = 0;
+        for (int k = 0; k < 3; ++k) acc += R1[3 * i + k] * R2i[3 * k + j];
+        R1R2i[3 * i + j] = acc;
+    }
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+        double acc = 0;
+        for (int k = 0; k < 3; ++k) acc += R1R2i[3 * i + k] * Sn[3 * k + j];
+        Jj[6 * i + 3 + j] = acc;
+    }
+    double mi[4], t[4], QL2[16];
+    qinv(m + 3, mi); qmul(mi, q12, t);                    // mQ12.inverse() * sQ1 * sQ2.inverse()
+    qleft(t, QL2);
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Jj[6 * (3 + i) + 3 + j] = -QL2[4 * (i + 1) + (j + 1)];
+}
+
 struct PassStats {
     int iterations = 0, trials = 0, stop = VISFS_BA_STOP_NOT_RUN, F = 0, NL = 0;
     double lambda = 0, chi2 = 0, chi2_last_trial = 0;
@@ -152,6 +248,14 @@ struct Oracle {
     double pv = 1.5, delta = 8.0;
     int solver = 0, trust = 0;
     int threads = 1;
+    // odometry links (EdgePoseConstraint, Optimizer.cpp:116-150): inserted into the graph before the visual edges
+    int NK = 0;
+    std::vector<int> lkFrom, lkTo;
+    std::vector<double> lkM;            // 7 per link
+    std::vector<uint8_t> lkAct;
+    std::vector<double> lkErr;          // 6 per link
+    double ov = 0.00005;
+    std::map<std::pair<int, int>, std::vector<double>> HppOff;   // pose-pose blocks (hi < hj) -> 6x6 row-major
 
     // structure
     std::vector<uint8_t> eact;
@@ -185,6 +289,12 @@ struct Oracle {
         el.assign(p->edge_point, p->edge_point + E);
         K = Intrinsics{p->fx, p->fy, p->cx, p->cy, p->bf};
         pv = p->pixel_variance; delta = p->huber_delta; solver = p->solver; trust = p->trust_region;
+        NK = p->n_links;
+        if (NK > 0) {
+            lkFrom.assign(p->link_from, p->link_from + NK); lkTo.assign(p->link_to, p->link_to + NK);
+            lkM.assign(p->link_tq, p->link_tq + 7 * (size_t)NK);
+            ov = p->odometry_variance;
+        }
     }
 
     void refreshR() {
@@ -204,6 +314,11 @@ struct Oracle {
             eact[e] = 1; pact[ep[e]] = 1; lact[el[e]] = 1;
             activeEdges.push_back(e);
         }
+        lkAct.assign(NK, 0);
+        for (int k = 0; k < NK; ++k) {
+            if (pfix[lkFrom[k]] && pfix[lkTo[k]]) continue;   // e->allVerticesFixed()
+            lkAct[k] = 1; pact[lkFrom[k]] = 1; pact[lkTo[k]] = 1;
+        }
         phidx.assign(P, -1); lhidx.assign(L, -1);
         F = 0;
         for (int i = 0; i < P; ++i) if (pact[i] && !pfix[i]) phidx[i] = F++;
@@ -222,6 +337,10 @@ struct Oracle {
         // pairs (i1 <= i2) reachable through ANY of its edges (v->edges(): includes level != 0).
         std::set<std::pair<int, int>> pat;
         for (int i = 0; i < F; ++i) pat.insert({i, i});
+        for (int k = 0; k < NK; ++k) {   // BlockSolver::buildStructure: H_pp off-diagonal block of a pose-pose edge
+            const int hi = phidx[lkFrom[k]], hj = phidx[lkTo[k]];
+            if (lkAct[k] && hi >= 0 && hj >= 0) pat.insert({std::max(hi, hj), std::min(hi, hj)});
+        }
         std::vector<std::vector<int>> allEdges(L);
         for (int e = 0; e < E; ++e) allEdges[el[e]].push_back(e);
         for (int l = 0; l < L; ++l) {
@@ -268,6 +387,15 @@ struct Oracle {
             rho[k] = r0;
         }
         double chi = 0.0;
+        lkErr.assign(6 * (size_t)NK, 0.0);
+        for (int k = 0; k < NK; ++k) {   // no robust kernel on these edges: rho = chi2 = e' (I / ov) e
+            if (!lkAct[k]) continue;
+            double *e = &lkErr[6 * (size_t)k];
+            linkError(&pose[7 * lkFrom[k]], &pose[7 * lkTo[k]], &lkM[7 * (size_t)k], e);
+            double c = 0;
+            for (int i = 0; i < 6; ++i) c += e[i] * e[i];
+            chi += c / ov;
+        }
         for (int k = 0; k < na; ++k) chi += rho[k];
         return chi;
     }
@@ -282,6 +410,41 @@ struct Oracle {
         const int n = 6 * F + 3 * NL;
         Hpp.assign(36 * (size_t)F, 0.0); Hll.assign(9 * (size_t)NL, 0.0);
         Hpl.assign(18 * (size_t)E, 0.0); b.assign(n, 0.0);
+        HppOff.clear();
+        for (int k = 0; k < NK; ++k) {   // BaseBinaryEdge::constructQuadraticForm with Omega = I / ov, no robust kernel
+            if (!lkAct[k]) continue;
+            double Ji[36], Jj[36];
+            linkJacobians(&pose[7 * lkFrom[k]], &pose[7 * lkTo[k]], &lkM[7 * (size_t)k], Ji, Jj);
+            const double *e = &lkErr[6 * (size_t)k];
+            const double om = 1.0 / ov;
+            const int hi = phidx[lkFrom[k]], hj = phidx[lkTo[k]];
+            auto addDiag = [&](int h, const double *J) {
+                for (int a = 0; a < 6; ++a) {
+                    for (int c = 0; c < 6; ++c) {
+                        double sacc = 0;
+                        for (int r = 0; r < 6; ++r) sacc += J[6 * r + a] * om * J[6 * r + c];
+                        Hpp[36 * (size_t)h + 6 * a + c] += sacc;
+                    }
+                    double sb = 0;
+                    for (int r = 0; r < 6; ++r) sb += J[6 * r + a] * om * e[r];
+                    b[6 * h + a] -= sb;
+                }
+            };
+            if (hi >= 0) addDiag(hi, Ji);
+            if (hj >= 0) addDiag(hj, Jj);
+            if (hi >= 0 && hj >= 0) {
+                // block (row = smaller hessian index): Ji' Omega Jj, transposed when the "to" pose comes first
+                const bool tr = hj < hi;
+                auto &blk = HppOff[{std::min(hi, hj), std::max(hi, hj)}];
+                if (blk.empty()) blk.assign(36, 0.0);
+                for (int a = 0; a < 6; ++a)
+                    for (int c = 0; c < 6; ++c) {
+                        double sacc = 0;
+                        for (int r = 0; r < 6; ++r) sacc += Ji[6 * r + a] * om * Jj[6 * r + c];
+                        if (!tr) blk[6 * a + c] += sacc; else blk[6 * c + a] += sacc;
+                    }
+            }
+        }
         auto edgeWork = [&](int e, double *HppT, double *bT) {
             const int pi = ep[e], li = el[e];
             double Jl[9], Jp[18];
@@ -477,6 +640,11 @@ struct Oracle {
                     if (a == c) v += lambda;
                     Sat(S, 6 * i + a, 6 * i + c) = v;
                 }
+        for (auto &kv : HppOff) {   // _Hschur = _Hpp: pose-pose blocks (i < j) live at lower (6j + c, 6i + a)
+            const int i = kv.first.first, j = kv.first.second;
+            for (int a = 0; a < 6; ++a)
+                for (int c = 0; c < 6; ++c) Sat(S, 6 * j + c, 6 * i + a) += kv.second[6 * a + c];
+        }
         coeff.assign(np, 0.0);
         Dinv.assign(9 * (size_t)NL, 0.0);
         auto landmarkWork = [&](int hl, std::vector<double> &St, std::vector<double> &ct) {
@@ -762,6 +930,21 @@ int oracle_structure(const visfs_ba_problem *p, visfs_ba_structure *out) {
     int nh = 0;
     for (int e = 0; e < o.E; ++e) nh += o.hplRow[e] >= 0;
     out->n_hpl_blocks = nh;
+    return VISFS_BA_OK;
+}
+
+// EdgePoseConstraint::computeError / linearizeOplus of every link at the input state (parity hook)
+int oracle_link_linearize(const visfs_ba_problem *p, double *err /* [K][6] */, double *Ji /* [K][6][6] */, double *Jj) {
+    Oracle o;
+    o.load(p);
+    for (int k = 0; k < o.NK; ++k) {
+        const double *a = &o.pose[7 * o.lkFrom[k]], *b = &o.pose[7 * o.lkTo[k]], *m = &o.lkM[7 * (size_t)k];
+        if (err) linkError(a, b, m, err + 6 * (size_t)k);
+        double J1[36], J2[36];
+        linkJacobians(a, b, m, J1, J2);
+        if (Ji) std::memcpy(Ji + 36 * (size_t)k, J1, sizeof J1);
+        if (Jj) std::memcpy(Jj + 36 * (size_t)k, J2, sizeof J2);
+    }
     return VISFS_BA_OK;
 }
 

@@ -33,6 +33,13 @@ def write_window(path, w, feature_id_offset=0, extra_points=0, n_cameras=2, pose
         for e in range(E):
             f.write(struct.pack("<2q4f", int(w["point_id"][w["edge_point"][e]]) + feature_id_offset, int(w["pose_id"][w["edge_pose"][e]]),
                                 float(w["ref_kpt"][e, 0]), float(w["ref_kpt"][e, 1]), float(w["ref_depth"][e]), 0.0))
+        K = int(w.get("n_links", 0))
+        f.write(struct.pack("<q", K))
+        if K:
+            f.write(struct.pack("<d", float(w["odometry_variance"])))
+            for k in range(K):
+                f.write(struct.pack("<2q", int(w["pose_id"][w["link_from"][k]]), int(w["pose_id"][w["link_to"][k]])))
+                f.write(np.ascontiguousarray(w["ref_link_T"][k], dtype="<f8").tobytes())
 
 
 def _rdv(buf, off, dtype):

@@ -33,6 +33,7 @@ def lib(omp=False):
         l.oracle_structure.argtypes = [C.POINTER(capi.Problem), C.POINTER(capi.Structure)]
         l.oracle_reduced_system.argtypes = [C.POINTER(capi.Problem), C.c_double, capi._dp, capi._dp, capi._dp,
                                             C.POINTER(C.c_int32), capi._dp, capi._dp]
+        l.oracle_link_linearize.argtypes = [C.POINTER(capi.Problem), capi._dp, capi._dp, capi._dp]
         _libs[name] = l
     return _libs[name]
 
@@ -100,3 +101,12 @@ def reduced_system(w, lam):
     nn = n.value
     return dict(status=st, n=nn, S=flat[: nn * nn].reshape(nn, nn).copy(), b_s=bs[:nn].copy(), x=x, chi2=chi2.value,
                 lambda_init=lam0.value)
+
+
+def link_linearize(w):
+    keep = []
+    p = capi.window_to_problem(w, keep)
+    K = int(w.get("n_links", 0))
+    err, Ji, Jj = np.zeros((K, 6)), np.zeros((K, 6, 6)), np.zeros((K, 6, 6))
+    lib().oracle_link_linearize(C.byref(p), capi._ptr(err, capi._dp), capi._ptr(Ji, capi._dp), capi._ptr(Jj, capi._dp))
+    return dict(error=err, J_from=Ji, J_to=Jj)

@@ -43,3 +43,19 @@ def test_local_optimize_failure_returns_empty_map(built, tmp_path):
     got = host_io.run_solve(fin, fout)
     assert got["poses"] == {} and len(got["outliers"]) == 0
     assert "NANs" in got["stdout"] or "NANs" in got["stderr"]
+
+
+def test_local_optimize_with_odometry_links(built, tmp_path):
+    # the deployed configuration of the reference (SensorStrategy 3): visual edges + EdgePoseConstraint between the frames
+    w = synth.make_window(6, 250, layout="all", seed=83, links="chain", first_id=3)
+    fin, fout = str(tmp_path / "w.bin"), str(tmp_path / "o.bin")
+    host_io.write_window(fin, w)
+    got = host_io.run_solve(fin, fout)
+    ref = O.solve(w)
+    assert ref["status"] == 0
+    T_ref = synth.camera_state_to_robot(ref["pose_tq"])
+    assert sorted(got["poses"]) == list(map(int, w["pose_id"]))
+    for i, pid in enumerate(w["pose_id"]):
+        assert np.allclose(got["poses"][int(pid)], T_ref[i], rtol=1e-6, atol=1e-8)
+    bare = {k: v for k, v in w.items() if not k.startswith("link") and k != "n_links"}
+    assert not np.allclose(O.solve(bare)["pose_tq"], ref["pose_tq"], atol=1e-9), "the links do not matter: test is void"

@@ -270,3 +270,48 @@ def test_pipelined_batch_groups_match_oracle(ba):
     t = ba.timing()
     assert t["lm_iterations"] == sum(sum(g["iterations_run"]) for g in got)
     assert t["h2d_bytes"] > 0 and t["d2h_bytes"] > 0
+
+
+# ---------------------------------------------------------------- odometry links (EdgePoseConstraint)
+def test_links_structure_pattern(ba):
+    w = synth.make_window(9, 300, layout="random", views=2, seed=401, links="chain")
+    _structure_case(ba, w)
+    ref = O.structure(w)
+    chain = {(i, i + 1) for i in range(ref["n_free_poses"] - 1)}
+    assert chain <= set(zip(ref["schur_rows"].tolist(), ref["schur_cols"].tolist())), "links must add their pose-pose blocks"
+
+
+@pytest.mark.parametrize("kw", [dict(layout="all"), dict(layout="consecutive", views=4, mono_frac=0.3, fixed_point_frac=0.2)])
+def test_links_reduced_system_matches_oracle(ba, kw):
+    w = synth.make_window(8, 500, seed=402, links="chain", **kw)
+    lam = 1.3
+    got, ref = ba.debug_trial(w, lam), O.reduced_system(w, lam)
+    assert got["n"] == ref["n"]
+    rel_close(got["chi2"], ref["chi2"], 1e-12, "chi2 at the input state (visual + odometry)")
+    rel_close(got["S"], ref["S"], 1e-10, "reduced camera system with pose-pose blocks")
+    rel_close(got["b_s"], ref["b_s"], 1e-10, "reduced rhs")
+    rel_close(got["x_pose"], ref["x"][: ref["n"]], 1e-7, "pose step")
+    rel_close(ba.debug_trial(w, -1.0)["lambda_used"], ref["lambda_init"], 1e-12, "initial damping")
+    bare = {k: v for k, v in w.items() if not k.startswith("link") and k != "n_links"}
+    assert abs(O.reduced_system(bare, lam)["chi2"] - ref["chi2"]) > 1e-3 * ref["chi2"], "the links do not contribute: test is void"
+
+
+def test_solve_with_odometry_links(ba):
+    w = synth.make_window(7, 400, layout="all", seed=403, links="chain")
+    check_solution(ba.solve(w), O.solve(w), "chain of links")
+    # a pose that only the links hold (it loses all its visual edges), and no fixed pose at all
+    w = synth.make_window(6, 250, layout="all", seed=404, links="chain", root=None)
+    keep = w["edge_pose"] != 2
+    for k in ("edge_obs", "edge_pose", "edge_point", "edge_kind"):
+        w[k] = np.ascontiguousarray(w[k][keep])
+    w["n_edges"] = int(keep.sum())
+    check_solution(ba.solve(w), O.solve(w), "pose held by links only")
+
+
+def test_solve_links_with_pcg_and_in_a_batch(ba):
+    a = synth.make_window(6, 300, layout="all", seed=405, links="chain", solver=2)
+    check_solution(ba.solve(a), O.solve(a), "links + PCG")
+    ws = [synth.make_window(5 + k % 3, 160 + 10 * k, layout="all", seed=410 + k, links=("chain" if k % 2 == 0 else None)) for k in range(6)]
+    got = ba.solve_batch(ws)
+    for k, (g, w) in enumerate(zip(got, ws)):
+        check_solution(g, O.solve(w), f"batch window {k}")

@@ -269,3 +269,55 @@ def test_golden_generator_reproduces_committed_fixture(name):
     assert np.allclose(again["pose_tq"], out["pose_tq"], rtol=1e-12, atol=1e-13)
     if name == "rejecting_4x50":
         assert sum(out["trials_run"]) > sum(out["iterations_run"])
+
+
+# ---------------------------------------------------------------- odometry links (EdgePoseConstraint)
+def _oplus(tq, d):
+    """CameraPose::update (OptimizeTypeDefine.cpp:7-14) in numpy."""
+    t = tq[:3] + d[:3]
+    ax, ay, az, aw = d[3] / 2, d[4] / 2, d[5] / 2, 1.0
+    bx, by, bz, bw = tq[3:7]
+    q = np.array([aw * bx + ax * bw + ay * bz - az * by, aw * by + ay * bw + az * bx - ax * bz,
+                  aw * bz + az * bw + ax * by - ay * bx, aw * bw - ax * bx - ay * by - az * bz])
+    return np.concatenate([t, q / np.linalg.norm(q)])
+
+
+def test_link_jacobians_are_the_derivatives_of_the_error_under_the_reference_oplus():
+    # unlike the visual edge's rotation columns (Appendix B-1) the live "Left update" Jacobians of EdgePoseConstraint
+    # (OptimizeTypeDefine.cpp:53-72) are exact: central differences through CameraPose::update pin the transcription
+    w = synth.make_window(5, 40, layout="all", seed=5, links="chain")
+    base = O.link_linearize(w)
+    assert np.abs(base["error"]).max() > 1e-3
+    h = 1e-6
+    for k in range(w["n_links"]):
+        for which, key in ((int(w["link_from"][k]), "J_from"), (int(w["link_to"][k]), "J_to")):
+            J = np.zeros((6, 6))
+            for a in range(6):
+                d = np.zeros(6); d[a] = h
+                wp = dict(w); wp["pose_tq"] = w["pose_tq"].copy(); wp["pose_tq"][which] = _oplus(w["pose_tq"][which], d)
+                wm = dict(w); wm["pose_tq"] = w["pose_tq"].copy(); wm["pose_tq"][which] = _oplus(w["pose_tq"][which], -d)
+                J[:, a] = (O.link_linearize(wp)["error"][k] - O.link_linearize(wm)["error"][k]) / (2 * h)
+            assert np.abs(J - base[key][k]).max() < 1e-8, (k, key)
+
+
+def test_link_error_is_zero_at_its_own_measurement_and_links_pull_the_solution():
+    w = synth.make_window(4, 60, layout="all", seed=6, links="chain", link_noise=(0.0, 0.0), pose_noise=(0.0, 0.0))
+    assert np.abs(O.link_linearize(w)["error"]).max() < 1e-12      # ground-truth poses, noise-free measurement
+    w = synth.make_window(6, 200, layout="all", seed=7, links="chain")
+    with_links = O.solve(w)
+    bare = {k: v for k, v in w.items() if not k.startswith("link") and k != "n_links"}
+    without = O.solve(bare)
+    assert with_links["status"] == 0 and with_links["chi2_initial"] > without["chi2_initial"]
+    assert not np.allclose(with_links["pose_tq"], without["pose_tq"], atol=1e-9)
+
+
+def test_links_keep_a_pose_without_visual_edges_active():
+    w = synth.make_window(5, 80, layout="all", seed=8, links="chain")
+    keep = w["edge_pose"] != 1
+    for k in ("edge_obs", "edge_pose", "edge_point", "edge_kind"):
+        w[k] = np.ascontiguousarray(w[k][keep])
+    w["n_edges"] = int(keep.sum())
+    s = O.structure(w)
+    assert s["pose_hidx"][1] >= 0
+    bare = {k: v for k, v in w.items() if not k.startswith("link") and k != "n_links"}
+    assert O.structure(bare)["pose_hidx"][1] == -1

@@ -39,7 +39,8 @@ class Problem(C.Structure):
                 ("edge_obs", _dp), ("edge_pose", _i32p), ("edge_point", _i32p), ("edge_kind", _u8p),
                 ("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double), ("bf", C.c_double),
                 ("pixel_variance", C.c_double), ("huber_delta", C.c_double),
-                ("iterations", C.c_int32), ("solver", C.c_int32), ("trust_region", C.c_int32), ("reserved", C.c_int32)]
+                ("iterations", C.c_int32), ("solver", C.c_int32), ("trust_region", C.c_int32), ("n_links", C.c_int32),
+                ("link_from", _i32p), ("link_to", _i32p), ("link_tq", _dp), ("odometry_variance", C.c_double)]
 
 
 class Result(C.Structure):
@@ -108,6 +109,12 @@ def window_to_problem(w, keep):
     for k in ("fx", "fy", "cx", "cy", "bf", "pixel_variance", "huber_delta"):
         setattr(p, k, float(w[k]))
     p.iterations, p.solver, p.trust_region = int(w["iterations"]), int(w["solver"]), int(w["trust_region"])
+    p.n_links = int(w.get("n_links", 0))
+    if p.n_links:
+        p.link_from = _ptr(arr("link_from", np.int32), _i32p)
+        p.link_to = _ptr(arr("link_to", np.int32), _i32p)
+        p.link_tq = _ptr(arr("link_tq", np.float64), _dp)
+    p.odometry_variance = float(w.get("odometry_variance", 0.00005))
     return p
 
 

@@ -343,12 +343,20 @@ __global__ void k_control_init(Batch B) {
     const double *part = B.part + wd.part_off;
     const size_t stride = (size_t)wd.part_stride;
     double md = 0.0;
+    const int *hidx = B.pose_hidx + wd.pose_off;
     for (int idx = lane; idx < F * 6; idx += 32) {
         double s = 0.0;
         for (int c = 0; c < wd.n_chunks; ++c) s += part[(size_t)c * stride + idx];
+        const int i = idx / 6, a = idx - 6 * i;
+        for (int k = 0; k < wd.n_link; ++k) {   // diag(H_pp) of the odometry links (k_link_lin ran at the accepted state)
+            const double *rec = B.link_lin + (size_t)(wd.link_off + k) * kLinkStride;
+            if (hidx[B.link_from[wd.link_off + k]] == i) s += rec[kLkHii + 7 * a];
+            if (hidx[B.link_to[wd.link_off + k]] == i) s += rec[kLkHjj + 7 * a];
+        }
         md = fmax(md, fabs(s));
     }
     double chi = 0.0;
+    for (int k = lane; k < wd.n_link; k += 32) chi += B.link_lin[(size_t)(wd.link_off + k) * kLinkStride + kLkChi];
     for (int c = lane; c < wd.n_chunks; c += 32) { chi += part[(size_t)c * stride + F * 6]; md = fmax(md, part[(size_t)c * stride + F * 6 + 1]); }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -386,6 +394,7 @@ __global__ void k_control(Batch B) {
     }
     if (lane != 0) return;
     const int pass = st.pass;
+    if (wd.n_link > 0) chi += st.link_chi_trial;
     st.chi_last_trial = chi;
     st.trials_run[pass] += 1;
     if (wd.trust != 0) {  // Gauss-Newton: update applied unconditionally, Fail ends the pass
@@ -507,6 +516,11 @@ __global__ void k_struct_pose(Batch B) {
     const WinDesc &wd = B.win[w];
     LMState &st = B.st[w];
     if (st.status != 0) return;
+    for (int k = 0; k < wd.n_link; ++k) {   // an odometry link keeps its poses active unless both ends are fixed
+        const int pf = wd.pose_off + B.link_from[wd.link_off + k], pt = wd.pose_off + B.link_to[wd.link_off + k];
+        if ((B.pose_flags[pf] & kFixed) && (B.pose_flags[pt] & kFixed)) continue;
+        B.pose_active[pf] = 1; B.pose_active[pt] = 1;
+    }
     int F = 0;
     for (int p = 0; p < wd.n_pose; ++p) {
         const int gp = wd.pose_off + p;
@@ -516,8 +530,13 @@ __global__ void k_struct_pose(Batch B) {
         B.pose_flags[gp] = fix | (in ? kInHessian : 0);
         if (in) ++F;
     }
-    if (!wd.large)
+    if (!wd.large) {
         for (int p = 0; p < wd.n_pose; ++p) B.covis[wd.pose_off + p] = (p < F) ? (1u << p) : 0u;
+        for (int k = 0; k < wd.n_link; ++k) {   // pose-pose block of the link in the Schur pattern
+            const int hi = B.pose_hidx[wd.pose_off + B.link_from[wd.link_off + k]], hj = B.pose_hidx[wd.pose_off + B.link_to[wd.link_off + k]];
+            if (hi >= 0 && hj >= 0) B.covis[wd.pose_off + min(hi, hj)] |= 1u << max(hi, hj);
+        }
+    }
     st.F = F;
     st.NL = 0;
     st.nF[st.pass] = F;

@@ -9,6 +9,7 @@
 //   0  blocks (i <  j) x 36, then per pose Hd = H_pp - Y W^T (21) g b_p   — k_build<MODE_BUILD, PPT>
 #pragma once
 #include "ba_math.cuh"
+#include "ba_link.cuh"
 
 namespace visfs {
 
@@ -103,6 +104,43 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(Batch B) {
         }
     }
     __syncthreads();
+    if (wd.n_link > 0) {
+        // ---- odometry links: H_pp blocks (diagonal and pose-pose) and gradient pieces from the records of k_link_lin.
+        //      Every diagonal entry / rhs entry has one owner thread that walks the links in order; the pose-pose blocks
+        //      of different links are different entries (atomicAdd only guards duplicate links between one pair of poses)
+        const int *hidx = B.pose_hidx + wd.pose_off;
+        const double *lin = B.link_lin + (size_t)wd.link_off * kLinkStride;
+        const int *lf = B.link_from + wd.link_off, *lt = B.link_to + wd.link_off;
+        for (int t2 = tid; t2 < F * 36; t2 += kSolveThreads) {
+            const int i = t2 / 36, q = t2 - i * 36, a = q / 6, cc = q - a * 6;
+            if (cc > a) continue;
+            double sacc = 0.0;
+            for (int k = 0; k < wd.n_link; ++k) {
+                if (hidx[lf[k]] == i) sacc += lin[(size_t)k * kLinkStride + kLkHii + q];
+                if (hidx[lt[k]] == i) sacc += lin[(size_t)k * kLinkStride + kLkHjj + q];
+            }
+            S[tri(6 * i + a, 6 * i + cc)] += sacc;
+        }
+        for (int t2 = tid; t2 < F * 6; t2 += kSolveThreads) {
+            const int i = t2 / 6, a = t2 - i * 6;
+            double sacc = 0.0;
+            for (int k = 0; k < wd.n_link; ++k) {
+                if (hidx[lf[k]] == i) sacc += lin[(size_t)k * kLinkStride + kLkBi + a];
+                if (hidx[lt[k]] == i) sacc += lin[(size_t)k * kLinkStride + kLkBj + a];
+            }
+            bs[t2] += sacc;
+            braw[t2] += sacc;
+        }
+        for (int t2 = tid; t2 < wd.n_link * 36; t2 += kSolveThreads) {
+            const int k = t2 / 36, q = t2 - k * 36, a = q / 6, cc = q - a * 6;
+            const int i = hidx[lf[k]], j = hidx[lt[k]];
+            if (i < 0 || j < 0) continue;
+            const double v = lin[(size_t)k * kLinkStride + kLkHij + q];   // (J_i' Omega J_j)(a, cc): row pose i, column pose j
+            if (i < j) atomicAdd(&S[tri(6 * j + cc, 6 * i + a)], v);
+            else atomicAdd(&S[tri(6 * i + a, 6 * j + cc)], v);
+        }
+        __syncthreads();
+    }
     if (B.dbg && w == 0) {
         for (int i = tid; i < ntri + n; i += kSolveThreads) B.dbg[i] = S[i];  // bs follows S
         __syncthreads();
@@ -308,8 +346,14 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(Batch B) {
             pose_oplus(src + p * kPoseStride, dlt, dst + p * kPoseStride);
         }
     }
+    double lchi = 0.0;
+    if (wd.n_link > 0) {   // chi2 of the links at the trial poses (this CTA has just written them)
+        __syncthreads();
+        lchi = link_chi2_block(B, wd, 1 - cur, s_red);
+    }
     if (tid == 0) {
         st.ok = ok ? 1 : 0; st.scale_p = scale;
+        st.link_chi_trial = lchi;
         tclk[5] = clock64();
         if (wd.solver == 2) tclk[3] = tclk[4];
         for (int k = 0; k < 6; ++k) st.t_solve[k] = tclk[k] - tclk[0];

@@ -36,13 +36,16 @@ struct WinDesc {
     int large;                       // 1: block-sparse / global-memory path (P > kMaxSmallPoses)
     int layout;                      // partial-system layout written by the build kernel (see ba_solve.cuh)
     int n_parts;                     // partial systems k_solve adds (= n_chunks / cluster size)
+    int link_off, n_link;            // odometry links of this window (ba_link.cuh)
     double fx, fy, cx, cy, bf, inv_pv, delta;
+    double inv_ov;                   // 1 / Optimizer/OdometryCovariance
 };
 
 struct LMState {
     double lambda, ni, cur_chi, trial_chi, rho, scale_p;
     double chi_initial, chi_pass[2], chi_last_trial, lambda_final[2];
     double pcg_residual;             // g2o LinearSolverPCG::_residual (reset by init() at every optimize())
+    double link_chi_trial;           // chi2 of the odometry links at the trial state (k_solve)
     int iter, qmax, done, cur;       // cur: which state buffer holds the accepted estimate
     int F, NL, ok, fresh;            // fresh: 1 until the first trial of the pass has run
     int iterations_run[2], trials_run[2], stop[2], nF[2], nNL[2];
@@ -97,6 +100,11 @@ struct Batch {
     double *red;                     // [n_sky * 36 | g (6F) | b_p (6F)]  — what a partitioned run all-reduces
     long long red_g_off, red_bp_off;
     double *hdiag;                   // [6F] diag(H_pp) of the INIT pass (lambda init)
+    // odometry links (ba_link.cuh)
+    int tot_link;
+    const int *link_win, *link_from, *link_to;   // [tot_link] window, window-local pose indices
+    const double *link_m;            // [tot_link][7] measurement t, q
+    double *link_lin;                // [tot_link][kLinkStride] per-trial records of k_link_lin
     double *dbg;                     // parity hook: k_solve dumps packed S and b_s of window 0 here (else null)
     double dbg_lambda;               // parity hook: damping override (< 0: keep the LM state's)
 };

@@ -70,7 +70,8 @@ struct visfs_ba_handle {
     int sm_count = 148;
 
     // uploaded batch (host mirrors)
-    int n_win = 0, n_chunks = 0, tot_pose = 0, tot_point = 0, tot_edge = 0, max_pose = 0, max_iter = 0;
+    int n_win = 0, n_chunks = 0, tot_pose = 0, tot_point = 0, tot_edge = 0, max_pose = 0, max_iter = 0, tot_link = 0;
+    DevBuf d_link_win, d_link_from, d_link_to, d_link_m, d_link_lin;
     bool resident = false, has_run = false, sorted = true, use_ws = false;
     int cluster = 1;
     std::vector<WinDesc> win;
@@ -160,6 +161,11 @@ int validate(visfs_ba_handle *h, const visfs_ba_problem &p, int idx, bool *sorte
     if ((p.n_poses && !p.pose_tq) || (p.n_points && !p.point_xyz)) return bad("null pose_tq / point_xyz");
     if (p.n_edges && (!p.edge_obs || !p.edge_pose || !p.edge_point)) return bad("null edge arrays");
     if (!(p.pixel_variance > 0.0)) return bad("pixel_variance must be > 0");
+    if (p.n_links < 0 || (p.n_links > 0 && (!p.link_from || !p.link_to || !p.link_tq))) return bad("bad odometry link arrays");
+    if (p.n_links > 0 && !(p.odometry_variance > 0.0)) return bad("odometry_variance must be > 0");
+    for (int k = 0; k < p.n_links; ++k)
+        if (p.link_from[k] < 0 || p.link_from[k] >= p.n_poses || p.link_to[k] < 0 || p.link_to[k] >= p.n_poses || p.link_from[k] == p.link_to[k])
+            return bad("odometry link index out of range (or from == to)");
     if (p.pose_id)
         for (int i = 1; i < p.n_poses; ++i) if (p.pose_id[i] <= p.pose_id[i - 1]) return bad("pose_id not strictly ascending");
     if (p.point_id)
@@ -196,6 +202,9 @@ Batch make_batch(visfs_ba_handle *h) {
     b.covis = h->d_covis.as<unsigned>(); b.part = h->d_part.as<double>(); b.part2 = h->d_part2.as<double>();
     b.xp = h->d_xp.as<double>(); b.n_running = h->d_n_running.as<int>();
     b.dbg = nullptr; b.dbg_lambda = -1.0;
+    b.tot_link = h->tot_link;
+    b.link_win = h->d_link_win.as<int>(); b.link_from = h->d_link_from.as<int>(); b.link_to = h->d_link_to.as<int>();
+    b.link_m = h->d_link_m.as<double>(); b.link_lin = h->d_link_lin.as<double>();
     b.tiles = h->d_tiles.as<Tile>(); b.chunk_tile_off = h->d_tile_off.as<int>();
     b.wtiles = h->d_wtiles.as<Tile>(); b.chunk_wtile_off = h->d_wtile_off.as<int>();
     b.sky_first = h->d_sky_first.as<int>(); b.sky_off = h->d_sky_off.as<long long>();
@@ -217,7 +226,7 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs) {
     if (n > 65535) return h->fail(VISFS_BA_ERR_INVALID, "at most 65535 windows per batch");
     CK(cudaSetDevice(h->device));
     h->win.assign(n, WinDesc{});
-    long long tp = 0, tl = 0, te = 0;
+    long long tp = 0, tl = 0, te = 0, tk = 0;
     int max_pose = 0, max_point = 0, max_edge = 0, max_iter = 0, max_free = 0;
     bool all_sorted = true, any_large = false, any_part = false;
     for (int w = 0; w < n; ++w) {
@@ -243,6 +252,9 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs) {
         d.solver = p.solver; d.trust = p.trust_region; d.flags = p.flags; d.large = big ? 1 : 0;
         d.fx = p.fx; d.fy = p.fy; d.cx = p.cx; d.cy = p.cy; d.bf = p.bf;
         d.inv_pv = 1.0 / p.pixel_variance; d.delta = p.huber_delta;
+        d.link_off = (int)tk; d.n_link = p.n_links; d.inv_ov = p.n_links > 0 ? 1.0 / p.odometry_variance : 0.0;
+        if (p.n_links > 0 && big) return h->fail(VISFS_BA_ERR_UNSUPPORTED, "odometry links are implemented for windows of up to 32 poses");
+        tk += p.n_links;
         tp += p.n_poses; tl += p.n_points; te += p.n_edges;
         {
             int nfix = 0;
@@ -253,7 +265,7 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs) {
         max_edge = std::max(max_edge, p.n_edges); max_iter = std::max(max_iter, d.max_iter);
         if (tp > 0x3fffffff || tl > 0x3fffffff || te > 0x3fffffff) return h->fail(VISFS_BA_ERR_INVALID, "batch too large");
     }
-    h->n_win = n; h->tot_pose = (int)tp; h->tot_point = (int)tl; h->tot_edge = (int)te;
+    h->n_win = n; h->tot_pose = (int)tp; h->tot_point = (int)tl; h->tot_edge = (int)te; h->tot_link = (int)tk;
     h->max_pose = max_pose; h->max_iter = max_iter; h->sorted = all_sorted;
     h->large = any_large; h->partitioned = any_part;
     if (any_part && h->comm_ranks > 1 && !h->comm) return h->fail(VISFS_BA_ERR_INVALID, "partitioned problem without visfs_ba_comm_init");
@@ -347,6 +359,27 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs) {
     CK(h->d_in_epoint.reserve(sizeof(int) * E)); CK(h->d_in_ekind.reserve(E));
     CK(h->d_out_pose.reserve(sizeof(double) * 7 * P)); CK(h->d_out_point.reserve(sizeof(double) * 3 * L));
     CK(h->d_out_level.reserve(E));
+
+    if (tk > 0) {   // odometry links: a few dozen per window, staged through pageable vectors
+        std::vector<int> lw((size_t)tk), lf((size_t)tk), lt((size_t)tk);
+        std::vector<double> lm(7 * (size_t)tk);
+        for (int w = 0; w < n; ++w) {
+            const visfs_ba_problem &p = probs[w];
+            const WinDesc &d = h->win[w];
+            for (int k = 0; k < p.n_links; ++k) {
+                lw[(size_t)d.link_off + k] = w; lf[(size_t)d.link_off + k] = p.link_from[k]; lt[(size_t)d.link_off + k] = p.link_to[k];
+                memcpy(&lm[7 * ((size_t)d.link_off + k)], p.link_tq + 7 * (size_t)k, 7 * sizeof(double));
+            }
+        }
+        CK(h->d_link_win.reserve(sizeof(int) * (size_t)tk)); CK(h->d_link_from.reserve(sizeof(int) * (size_t)tk));
+        CK(h->d_link_to.reserve(sizeof(int) * (size_t)tk)); CK(h->d_link_m.reserve(sizeof(double) * 7 * (size_t)tk));
+        CK(h->d_link_lin.reserve(sizeof(double) * kLinkStride * (size_t)tk));
+        CK(cudaMemcpyAsync(h->d_link_win.p, lw.data(), sizeof(int) * (size_t)tk, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->d_link_from.p, lf.data(), sizeof(int) * (size_t)tk, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->d_link_to.p, lt.data(), sizeof(int) * (size_t)tk, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->d_link_m.p, lm.data(), sizeof(double) * 7 * (size_t)tk, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));   // the host vectors go out of scope
+    }
 
     // pack into one pinned staging buffer (layout: pose | point | obs | epose | epoint | pfix | lfix | ekind)
     const size_t o_pose = 0, o_point = o_pose + sizeof(double) * 7 * P, o_obs = o_point + sizeof(double) * 3 * L,
@@ -500,6 +533,7 @@ int enqueue_body(visfs_ba_handle *h) {
     launch_build<MODE_BUILD>(h);
     ev_end(h, ev);
     ev = ev_begin(h, EV_SOLVE);
+    if (h->tot_link > 0) { k_link_lin<<<(h->tot_link + 63) / 64, 64, 0, h->stream>>>(h->batch); h->launches += 1; }
     k_solve<<<h->n_win, kSolveThreads, h->solve_smem, h->stream>>>(h->batch);
     ev_end(h, ev);
     ev = ev_begin(h, EV_UPDATE);
@@ -802,6 +836,7 @@ int run_pass(visfs_ba_handle *h, int pass) {
         if ((st = run_structure(h))) return st;
         k_sync_buffers<<<dim3((unsigned)h->grid_lm_x, (unsigned)h->n_win), 256, 0, s>>>(B);
         if (h->n_chunks) k_init<<<h->n_chunks, kUpdThreads, sizeof(InitSmem), s>>>(B);
+        if (h->tot_link > 0) { k_link_lin<<<(h->tot_link + 63) / 64, 64, 0, s>>>(B); h->launches += 1; }
         k_control_init<<<h->n_win, 32, 0, s>>>(B);
         h->launches += 3;
     }
@@ -1024,7 +1059,8 @@ void visfs_ba_destroy(visfs_ba_handle *h) {
                       &h->d_pose_active, &h->d_point_hidx, &h->d_lm_edge_off, &h->d_obs_u, &h->d_obs_v, &h->d_obs_r, &h->d_edge_pose,
                       &h->d_edge_point, &h->d_edge_orig, &h->d_covis, &h->d_part, &h->d_part2, &h->d_xp, &h->d_n_running,
                       &h->d_in_pose, &h->d_in_point, &h->d_in_pfix, &h->d_in_lfix, &h->d_in_obs, &h->d_in_epose, &h->d_in_epoint,
-                      &h->d_in_ekind, &h->d_out_pose, &h->d_out_point, &h->d_out_level, &h->d_tmp, &h->d_tmp2, &h->d_keys, &h->d_keys2, &h->d_perm, &h->d_tiles, &h->d_tile_off, &h->d_tile_cnt, &h->d_wtiles, &h->d_wtile_off};
+                      &h->d_in_ekind, &h->d_out_pose, &h->d_out_point, &h->d_out_level, &h->d_tmp, &h->d_tmp2, &h->d_keys, &h->d_keys2, &h->d_perm, &h->d_tiles, &h->d_tile_off, &h->d_tile_cnt, &h->d_wtiles, &h->d_wtile_off,
+                      &h->d_link_win, &h->d_link_from, &h->d_link_to, &h->d_link_m, &h->d_link_lin};
     for (DevBuf *b : bufs) b->release();
     h->h_stage.release(); h->h_out.release(); h->h_small.release();
     for (cudaEvent_t ev : h->ev_pool) cudaEventDestroy(ev);
@@ -1305,6 +1341,7 @@ int visfs_ba_debug_trial(visfs_ba_handle *h, const visfs_ba_problem *problem, do
         if (st) return st;
         k_sync_buffers<<<dim3((unsigned)h->grid_lm_x, 1u), 256, 0, s>>>(h->batch);
         if (h->n_chunks) k_init<<<h->n_chunks, kUpdThreads, sizeof(InitSmem), s>>>(h->batch);
+        if (h->tot_link > 0) k_link_lin<<<(h->tot_link + 63) / 64, 64, 0, s>>>(h->batch);
         k_control_init<<<1, 32, 0, s>>>(h->batch);
         CK(cudaMemcpyAsync(&before, h->d_st.p, sizeof(LMState), cudaMemcpyDeviceToHost, s));
         CK(dbg.reserve(sizeof(double) * (ntri_max + nmax + 8)));

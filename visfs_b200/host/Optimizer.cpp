@@ -3,6 +3,7 @@
 // are the reference's line ranges.  All arithmetic that g2o did runs behind visfs_ba_solve().
 #include "Optimizer.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <limits>
@@ -214,11 +215,6 @@ std::map<std::size_t, Eigen::Isometry3d> Optimizer::localOptimize(
     }
 
     if (_poses.size() >= 2 && iterations_ > 0 && _poses.begin()->first > 0) {           // :74
-        if (!_links.empty()) {        // :116-150, EdgePoseConstraint: SURVEY.md §8 f-1, not on this path yet
-            message_ = "Optimizer: odometry links are not handled by the CUDA optimiser yet.";
-            VISFS_B200_LOG("ERROR", message_);
-            return optimizedPoses;
-        }
         if (!_pointClouds.empty() && _submap != nullptr) {   // :225-258, laser edges: SURVEY.md §8 f-4
             message_ = "Optimizer: laser observations are not handled by the CUDA optimiser.";
             VISFS_B200_LOG("ERROR", message_);
@@ -248,6 +244,34 @@ std::map<std::size_t, Eigen::Isometry3d> Optimizer::localOptimize(
         prob.iterations = iterations_;                          // :265, :311 (each pass runs iterations_/2)
         prob.solver = solver_;                                  // :76-91
         prob.trust_region = trustRegion_;                       // :93-97
+
+        // :116-150 — odometry constraints (EdgePoseConstraint) between poses of the window
+        std::vector<int32_t> linkFrom, linkTo;
+        std::vector<double> linkTq;
+        {
+            const Eigen::Isometry3d Tri = _cameraModels.front()->getTansformImageToRobot();
+            const Eigen::Isometry3d TriInv = Tri.inverse();
+            auto indexOf = [&](std::size_t id) -> int {
+                auto it = std::lower_bound(m.pose_id.begin(), m.pose_id.end(), static_cast<int64_t>(id));
+                return (it != m.pose_id.end() && *it == static_cast<int64_t>(id)) ? static_cast<int>(it - m.pose_id.begin()) : -1;
+            };
+            for (auto iter = _links.begin(); iter != _links.end(); ++iter) {
+                const std::size_t fromId = std::get<0>(iter->second), toId = std::get<1>(iter->second);
+                if (!(fromId > 0 && toId > 0) || fromId == toId) continue;               // :126-129
+                const int a = indexOf(fromId), b = indexOf(toId);
+                if (a < 0 || b < 0) continue;                                            // uContains(_poses, ...)
+                const Eigen::Isometry3d Tc1c2 = TriInv * std::get<2>(iter->second) * Tri;   // :133
+                double q[4];
+                rotationToQuaternion(Tc1c2.linear(), q);                                 // g2o::SE3Quat(R, t): w >= 0, unit
+                const Eigen::Vector3d & t = Tc1c2.translation();
+                const double rec[7] = {t[0], t[1], t[2], q[0], q[1], q[2], q[3]};
+                linkFrom.push_back(a); linkTo.push_back(b);
+                linkTq.insert(linkTq.end(), rec, rec + 7);
+            }
+        }
+        prob.n_links = static_cast<int32_t>(linkFrom.size());
+        prob.link_from = linkFrom.data(); prob.link_to = linkTo.data(); prob.link_tq = linkTq.data();
+        prob.odometry_variance = odometryCovariance_;           // :120
 
         std::vector<double> poseOut(m.pose_tq.size()), pointOut(m.point_xyz.size());
         std::vector<uint8_t> levelOut(m.edge_pose.size());

@@ -56,7 +56,7 @@ public:
     /** \brief Optimize the local maps (visual part of the reference's local fusion).
      * \param[in] rootId Fixed pose.
      * \param[in] poses Poses to optimize (T_world<-robot).
-     * \param[in] links Odometry links between poses (must be empty: SURVEY.md §8 f-1).
+     * \param[in] links Odometry links between poses (EdgePoseConstraint, Optimizer.cpp:116-150).
      * \param[in] cameraModels Left (and right) camera model; stereo iff size() > 1.
      * \param[in&out] points3D World points, fixed flag.
      * \param[in] wordReferences Observations: feature id -> pose id -> key point + depth.

@@ -55,6 +55,23 @@ int main(int argc, char **argv) {
         (void)rd<float>(in);
         wordReferences[(std::size_t)fid].emplace((std::size_t)pid, Optimizer::FeatureBA(cv::KeyPoint(x, y), depth));
     }
+    // optional trailer: odometry links (count, odometry covariance, then from id, to id, 4x4 robot-frame transform)
+    std::map<std::size_t, std::tuple<std::size_t, std::size_t, Eigen::Isometry3d>> links;
+    double odometryCovariance = 0.00005;
+    {
+        const int64_t nLinks = rd<int64_t>(in);
+        if (in && nLinks > 0) {
+            odometryCovariance = rd<double>(in);
+            for (int64_t i = 0; i < nLinks; ++i) {
+                const int64_t from = rd<int64_t>(in), to = rd<int64_t>(in);
+                Eigen::Isometry3d T;
+                double M[16];
+                for (double &v : M) v = rd<double>(in);
+                for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) T.linear()(r, c) = M[4 * r + c]; T.translation()[r] = M[4 * r + 3]; }
+                links.emplace((std::size_t)i, std::make_tuple((std::size_t)from, (std::size_t)to, T));
+            }
+        }
+    }
     std::vector<std::shared_ptr<GeometricCamera>> cameraModels;
     for (int64_t c = 0; c < nCam; ++c)
         cameraModels.push_back(std::make_shared<GeometricCamera>(std::vector<double>{fx, fy, cx, cy, baseline}));
@@ -78,9 +95,9 @@ int main(int argc, char **argv) {
     char buf[64];
     std::snprintf(buf, sizeof buf, "%.17g", pixelVariance); params["Optimizer/PixelVariance"] = buf;
     std::snprintf(buf, sizeof buf, "%.17g", delta); params["Optimizer/RobustKernelDelta"] = buf;
+    std::snprintf(buf, sizeof buf, "%.17g", odometryCovariance); params["Optimizer/OdometryCovariance"] = buf;
     Optimizer::Optimizer optimizer(params);
     std::vector<std::tuple<std::size_t, std::size_t>> outliers;
-    const std::map<std::size_t, std::tuple<std::size_t, std::size_t, Eigen::Isometry3d>> links;
     const std::vector<Sensor::PointCloud> pointClouds;
     const std::shared_ptr<const Map::Submap2D> submap;
     auto result = optimizer.localOptimize((std::size_t)rootId, poses, links, cameraModels, points3D, wordReferences,

@@ -172,9 +172,13 @@ def make_window(n_poses=10, n_points=2000, views=10, *, seed=BASE_SEED, layout="
                 mono_frac=0.0, fixed_point_frac=0.0, outlier_frac=0.05, pixel_noise=0.7,
                 pose_noise=(0.02, np.deg2rad(0.5)), point_noise=0.05, iterations=10, solver=0,
                 trust_region=0, huber_delta=8.0, pixel_variance=1.5, first_id=1, root="second_newest",
-                depth_range=(2.0, 10.0), shuffle_edges=False):
+                depth_range=(2.0, 10.0), shuffle_edges=False, links=None, odometry_variance=0.00005,
+                link_noise=(0.003, np.deg2rad(0.05))):
     """Build one window.  Returns a dict of numpy arrays in C-ABI form plus the reference-form
     inputs under the keys ``ref_*``.
+
+    links: None, or "chain": an odometry constraint (EdgePoseConstraint, Optimizer.cpp:116-150) between every pair of
+    consecutive frames, measurement = ground-truth relative camera motion T_c1c2 plus noise.
 
     layout: "all" (every point seen by every frame; views ignored), "consecutive" (each point
     seen by `views` consecutive frames, wrapping on a loop trajectory), "random" (`views` random
@@ -267,7 +271,30 @@ def make_window(n_poses=10, n_points=2000, views=10, *, seed=BASE_SEED, layout="
         perm = rng.permutation(E)
         e_point, e_pose, obs, kind, kpt, depth = e_point[perm], e_pose[perm], obs[perm], kind[perm], kpt[perm], depth[perm]
 
+    link_kw = {}
+    if links == "chain" and P > 1:
+        # T_c1c2 = T_c1w * T_c2w^-1 from the ground truth, perturbed
+        Tcw = np.zeros((P, 4, 4)); Tcw[:, 3, 3] = 1.0
+        Tcw[:, :3, :3] = R_cw; Tcw[:, :3, 3] = t_cw
+        lf = np.arange(0, P - 1, dtype=np.int32); lt = lf + 1
+        rel = Tcw[lf] @ np.linalg.inv(Tcw[lt])
+        rel[:, :3, 3] += rng.normal(0, link_noise[0], (P - 1, 3))
+        rel[:, :3, :3] = small_rot(rng.normal(0, link_noise[1], (P - 1, 3))) @ rel[:, :3, :3]
+        # what the reference is handed is the robot-frame motion T_r1r2; Optimizer.cpp:133 turns it into
+        # T_c1c2 = T_rc^-1 * T_r1r2 * T_rc, which is the measurement of the C ABI
+        T_rc = np.eye(4); T_rc[:3, :3] = R_ROBOT_FROM_IMAGE
+        ref_T = T_rc @ rel @ np.linalg.inv(T_rc)
+        meas = np.linalg.inv(T_rc) @ ref_T @ T_rc
+        ltq = np.zeros((P - 1, 7))
+        ltq[:, :3] = meas[:, :3, 3]
+        ltq[:, 3:7] = quat_from_R(meas[:, :3, :3])
+        link_kw = dict(n_links=P - 1, link_from=lf, link_to=lt, link_tq=np.ascontiguousarray(ltq),
+                       odometry_variance=float(odometry_variance), ref_link_T=ref_T)
+    elif links is not None:
+        raise ValueError(links)
+
     return dict(
+        **link_kw,
         n_poses=P, n_points=L, n_edges=E,
         pose_tq=np.ascontiguousarray(robot_to_camera_state(T_init)), pose_id=pose_id, pose_fixed=pose_fixed,
         point_xyz=np.ascontiguousarray(pts_init), point_id=np.arange(L, dtype=np.int64), point_fixed=point_fixed,
