@@ -81,10 +81,19 @@ struct visfs_ba_handle {
     int grid_lm_x = 1, grid_edge_x = 1;
 
     // device memory
-    DevBuf d_win, d_st, d_chunks, d_pose, d_point, d_pose_flags, d_lm_flags, d_pose_hidx, d_pose_active, d_point_hidx,
+    DevBuf d_st, d_pose, d_point, d_pose_flags, d_lm_flags, d_pose_hidx, d_pose_active, d_point_hidx,
         d_lm_edge_off, d_obs_u, d_obs_v, d_obs_r, d_edge_pose, d_edge_point, d_edge_orig, d_covis, d_part, d_part2, d_xp,
         d_n_running, d_tiles, d_tile_off, d_tile_cnt, d_wtiles, d_wtile_off;
-    DevBuf d_in_pose, d_in_point, d_in_pfix, d_in_lfix, d_in_obs, d_in_epose, d_in_epoint, d_in_ekind;
+    // the caller's arrays, window and chunk descriptors: ONE device buffer with the layout of the pinned staging buffer,
+    // filled by ONE H2D copy (a single-window call is latency-bound: ten small copies cost ~50 us)
+    DevBuf d_in;
+    struct InPtrs {
+        double *pose = nullptr, *point = nullptr, *obs = nullptr;
+        int *epose = nullptr, *epoint = nullptr;
+        uint8_t *pfix = nullptr, *lfix = nullptr, *ekind = nullptr;
+        WinDesc *win = nullptr;
+        Chunk *chunks = nullptr;
+    } in;
     DevBuf d_out_pose, d_out_point, d_out_level, d_tmp, d_tmp2, d_keys, d_keys2, d_perm;
     PinBuf h_stage, h_out, h_small;
 
@@ -191,7 +200,7 @@ Batch make_batch(visfs_ba_handle *h) {
     Batch b{};
     b.n_win = h->n_win; b.n_chunks = h->n_chunks;
     b.tot_pose = h->tot_pose; b.tot_point = h->tot_point; b.tot_edge = h->tot_edge;
-    b.win = h->d_win.as<WinDesc>(); b.st = h->d_st.as<LMState>(); b.chunks = h->d_chunks.as<Chunk>();
+    b.win = h->in.win; b.st = h->d_st.as<LMState>(); b.chunks = h->in.chunks;
     b.pose = h->d_pose.as<double>(); b.point = h->d_point.as<double>();
     b.pose_flags = h->d_pose_flags.as<uint8_t>(); b.lm_flags = h->d_lm_flags.as<uint8_t>();
     b.pose_hidx = h->d_pose_hidx.as<int>(); b.pose_active = h->d_pose_active.as<int>();
@@ -327,8 +336,7 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs) {
 
     // device buffers
     const size_t P = (size_t)std::max<long long>(tp, 1), L = (size_t)std::max<long long>(tl, 1), E = (size_t)std::max<long long>(te, 1);
-    CK(h->d_win.reserve(sizeof(WinDesc) * n)); CK(h->d_st.reserve(sizeof(LMState) * n));
-    CK(h->d_chunks.reserve(sizeof(Chunk) * std::max(h->n_chunks, 1)));
+    CK(h->d_st.reserve(sizeof(LMState) * n));
     CK(h->d_pose.reserve(sizeof(double) * 2 * P * kPoseStride)); CK(h->d_point.reserve(sizeof(double) * 2 * L * 3));
     CK(h->d_pose_flags.reserve(P)); CK(h->d_lm_flags.reserve(L));
     CK(h->d_pose_hidx.reserve(sizeof(int) * P)); CK(h->d_pose_active.reserve(sizeof(int) * P));
@@ -353,12 +361,7 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs) {
     CK(h->d_tiles.reserve(sizeof(Tile) * max_tiles));
     CK(h->d_tile_off.reserve(sizeof(int) * (h->n_chunks + 2))); CK(h->d_tile_cnt.reserve(sizeof(int) * (h->n_chunks + 2)));
     CK(h->d_wtiles.reserve(sizeof(Tile) * (L + (size_t)h->n_chunks + 8))); CK(h->d_wtile_off.reserve(sizeof(int) * (h->n_chunks + 2)));
-    CK(h->d_in_pose.reserve(sizeof(double) * 7 * P)); CK(h->d_in_point.reserve(sizeof(double) * 3 * L));
-    CK(h->d_in_pfix.reserve(P)); CK(h->d_in_lfix.reserve(L));
-    CK(h->d_in_obs.reserve(sizeof(double) * 3 * E)); CK(h->d_in_epose.reserve(sizeof(int) * E));
-    CK(h->d_in_epoint.reserve(sizeof(int) * E)); CK(h->d_in_ekind.reserve(E));
-    CK(h->d_out_pose.reserve(sizeof(double) * 7 * P)); CK(h->d_out_point.reserve(sizeof(double) * 3 * L));
-    CK(h->d_out_level.reserve(E));
+    CK(h->d_out_level.reserve(E));   // (visfs_ba_structure_build stages the caller's edge levels here)
 
     if (tk > 0) {   // odometry links: a few dozen per window, staged through pageable vectors
         std::vector<int> lw((size_t)tk), lf((size_t)tk), lt((size_t)tk);
@@ -382,10 +385,21 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs) {
     }
 
     // pack into one pinned staging buffer (layout: pose | point | obs | epose | epoint | pfix | lfix | ekind)
+    auto al16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
     const size_t o_pose = 0, o_point = o_pose + sizeof(double) * 7 * P, o_obs = o_point + sizeof(double) * 3 * L,
                  o_epose = o_obs + sizeof(double) * 3 * E, o_epoint = o_epose + sizeof(int) * E,
-                 o_pfix = o_epoint + sizeof(int) * E, o_lfix = o_pfix + P, o_ekind = o_lfix + L, o_end = o_ekind + E;
+                 o_pfix = o_epoint + sizeof(int) * E, o_lfix = o_pfix + P, o_ekind = o_lfix + L, o_win = al16(o_ekind + E),
+                 o_chunks = al16(o_win + sizeof(WinDesc) * n), o_end = al16(o_chunks + sizeof(Chunk) * std::max(h->n_chunks, 1));
     CK(h->h_stage.reserve(o_end));
+    CK(h->d_in.reserve(o_end));
+    {
+        char *db = h->d_in.as<char>();
+        h->in.pose = reinterpret_cast<double *>(db + o_pose); h->in.point = reinterpret_cast<double *>(db + o_point);
+        h->in.obs = reinterpret_cast<double *>(db + o_obs); h->in.epose = reinterpret_cast<int *>(db + o_epose);
+        h->in.epoint = reinterpret_cast<int *>(db + o_epoint); h->in.pfix = reinterpret_cast<uint8_t *>(db + o_pfix);
+        h->in.lfix = reinterpret_cast<uint8_t *>(db + o_lfix); h->in.ekind = reinterpret_cast<uint8_t *>(db + o_ekind);
+        h->in.win = reinterpret_cast<WinDesc *>(db + o_win); h->in.chunks = reinterpret_cast<Chunk *>(db + o_chunks);
+    }
     char *sg = h->h_stage.as<char>();
     for (int w = 0; w < n; ++w) {
         const visfs_ba_problem &p = probs[w];
@@ -406,19 +420,11 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs) {
         }
     }
     cudaStream_t s = h->stream;
-    CK(cudaMemcpyAsync(h->d_in_pose.p, sg + o_pose, sizeof(double) * 7 * P, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(h->d_in_point.p, sg + o_point, sizeof(double) * 3 * L, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(h->d_in_obs.p, sg + o_obs, sizeof(double) * 3 * E, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(h->d_in_epose.p, sg + o_epose, sizeof(int) * E, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(h->d_in_epoint.p, sg + o_epoint, sizeof(int) * E, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(h->d_in_pfix.p, sg + o_pfix, P, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(h->d_in_lfix.p, sg + o_lfix, L, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(h->d_in_ekind.p, sg + o_ekind, E, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(h->d_win.p, h->win.data(), sizeof(WinDesc) * n, cudaMemcpyHostToDevice, s));
-    if (h->n_chunks) CK(cudaMemcpyAsync(h->d_chunks.p, h->chunks.data(), sizeof(Chunk) * h->n_chunks, cudaMemcpyHostToDevice, s));
+    memcpy(sg + o_win, h->win.data(), sizeof(WinDesc) * n);
+    if (h->n_chunks) memcpy(sg + o_chunks, h->chunks.data(), sizeof(Chunk) * h->n_chunks);
+    CK(cudaMemcpyAsync(h->d_in.p, sg, o_end, cudaMemcpyHostToDevice, s));
 
-    h->h2d_bytes = (int64_t)(sizeof(double) * 7 * P + sizeof(double) * 3 * L + sizeof(double) * 3 * E + 2 * sizeof(int) * E + P + L + E +
-                             sizeof(WinDesc) * n + sizeof(Chunk) * h->n_chunks);
+    h->h2d_bytes = (int64_t)o_end + (int64_t)tk * (3 * (int64_t)sizeof(int) + 7 * (int64_t)sizeof(double));
     // device-side preparation: (optional) stable sort by (window, point, pose), SoA split, CSR offsets
     const int *perm = nullptr;
     if (!all_sorted && te > 0) {
@@ -452,8 +458,8 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs) {
     h->batch_ctl.part2 = h->d_scal.as<double>() + 2;
     Batch &B = h->batch;
     if (te > 0) {
-        k_prepare_edges<<<grid2(max_edge, n), 256, 0, s>>>(B, h->d_in_obs.as<double>(), h->d_in_epose.as<int>(), h->d_in_epoint.as<int>(),
-                                                          h->d_in_ekind.as<uint8_t>(), perm, h->d_obs_u.as<double>(),
+        k_prepare_edges<<<grid2(max_edge, n), 256, 0, s>>>(B, h->in.obs, h->in.epose, h->in.epoint,
+                                                          h->in.ekind, perm, h->d_obs_u.as<double>(),
                                                           h->d_obs_v.as<double>(), h->d_obs_r.as<double>(), h->d_edge_point.as<int>());
     }
     k_lm_offsets<<<grid2(max_point + 1, n), 256, 0, s>>>(B, h->d_lm_edge_off.as<int>());
@@ -479,8 +485,7 @@ int reset_state(visfs_ba_handle *h) {
     Batch &B = h->batch;
     const int items = std::max(std::max(h->tot_pose, h->tot_point * 3), std::max(h->tot_edge, h->n_win));
     const int gx = std::max(1, std::min((items + 255) / 256, 4096));
-    k_reset<<<gx, 256, 0, h->stream>>>(B, h->d_in_pose.as<double>(), h->d_in_point.as<double>(), h->d_in_pfix.as<uint8_t>(),
-                                       h->d_in_lfix.as<uint8_t>());
+    k_reset<<<gx, 256, 0, h->stream>>>(B, h->in.pose, h->in.point, h->in.pfix, h->in.lfix);
     CK(cudaMemsetAsync(h->d_n_running.p, 0, sizeof(int) * 4, h->stream));
     CK(cudaGetLastError());
     h->launches += 1;
@@ -925,16 +930,16 @@ int download(visfs_ba_handle *h, int n, visfs_ba_result *res) {
     CK(cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
     const int items = std::max(h->max_pose * 7, std::max(h->grid_lm_x * 256 * 3, h->grid_edge_x * 256));
-    k_export<<<grid2(items, h->n_win), 256, 0, s>>>(h->batch, h->d_out_pose.as<double>(), h->d_out_point.as<double>(),
-                                                   h->d_out_level.as<uint8_t>());
-    CK(cudaGetLastError());
     const size_t P = (size_t)h->tot_pose, L = (size_t)h->tot_point, E = (size_t)h->tot_edge;
     const size_t o_pose = 0, o_point = sizeof(double) * 7 * P, o_level = o_point + sizeof(double) * 3 * L, o_end = o_level + E;
+    CK(h->d_out_pose.reserve(o_end + 8));      // one output buffer [pose | point | level], one D2H copy
+    char *dout = h->d_out_pose.as<char>();
+    k_export<<<grid2(items, h->n_win), 256, 0, s>>>(h->batch, reinterpret_cast<double *>(dout + o_pose), reinterpret_cast<double *>(dout + o_point),
+                                                   reinterpret_cast<uint8_t *>(dout + o_level));
+    CK(cudaGetLastError());
     CK(h->h_out.reserve(o_end + 8));
     char *ho = h->h_out.as<char>();
-    if (P) CK(cudaMemcpyAsync(ho + o_pose, h->d_out_pose.p, sizeof(double) * 7 * P, cudaMemcpyDeviceToHost, s));
-    if (L) CK(cudaMemcpyAsync(ho + o_point, h->d_out_point.p, sizeof(double) * 3 * L, cudaMemcpyDeviceToHost, s));
-    if (E) CK(cudaMemcpyAsync(ho + o_level, h->d_out_level.p, E, cudaMemcpyDeviceToHost, s));
+    if (o_end) CK(cudaMemcpyAsync(ho, dout, o_end, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     h->d2h_bytes += (int64_t)o_end;
     h->timing.d2h_bytes = h->d2h_bytes;
@@ -1055,11 +1060,10 @@ void visfs_ba_destroy(visfs_ba_handle *h) {
                         &h->d_scal, &h->d_info, &h->d_cnt, &h->d_plan, &h->d_pcg};
         for (DevBuf *b : lb) b->release();
     }
-    DevBuf *bufs[] = {&h->d_win, &h->d_st, &h->d_chunks, &h->d_pose, &h->d_point, &h->d_pose_flags, &h->d_lm_flags, &h->d_pose_hidx,
+    DevBuf *bufs[] = {&h->d_in, &h->d_st, &h->d_pose, &h->d_point, &h->d_pose_flags, &h->d_lm_flags, &h->d_pose_hidx,
                       &h->d_pose_active, &h->d_point_hidx, &h->d_lm_edge_off, &h->d_obs_u, &h->d_obs_v, &h->d_obs_r, &h->d_edge_pose,
                       &h->d_edge_point, &h->d_edge_orig, &h->d_covis, &h->d_part, &h->d_part2, &h->d_xp, &h->d_n_running,
-                      &h->d_in_pose, &h->d_in_point, &h->d_in_pfix, &h->d_in_lfix, &h->d_in_obs, &h->d_in_epose, &h->d_in_epoint,
-                      &h->d_in_ekind, &h->d_out_pose, &h->d_out_point, &h->d_out_level, &h->d_tmp, &h->d_tmp2, &h->d_keys, &h->d_keys2, &h->d_perm, &h->d_tiles, &h->d_tile_off, &h->d_tile_cnt, &h->d_wtiles, &h->d_wtile_off,
+                      &h->d_out_pose, &h->d_out_point, &h->d_out_level, &h->d_tmp, &h->d_tmp2, &h->d_keys, &h->d_keys2, &h->d_perm, &h->d_tiles, &h->d_tile_off, &h->d_tile_cnt, &h->d_wtiles, &h->d_wtile_off,
                       &h->d_link_win, &h->d_link_from, &h->d_link_to, &h->d_link_m, &h->d_link_lin};
     for (DevBuf *b : bufs) b->release();
     h->h_stage.release(); h->h_out.release(); h->h_small.release();
