@@ -17,6 +17,27 @@ constexpr int kSolveThreads = 256;
 
 __device__ __forceinline__ int tri(int r, int c) { return r * (r + 1) / 2 + c; }  // r >= c
 
+// Single-window latency: k_solve is one CTA and would pull every partial system through one SM (C2: 1.9 MB, 37 us).
+// This kernel folds them into the first partial with many CTAs, in part order (deterministic), so k_solve reads one.
+__global__ void k_reduce_parts(Batch B) {
+    const int w = blockIdx.y;
+    const WinDesc &wd = B.win[w];
+    if (B.st[w].done || wd.n_parts <= 1) return;
+    double *part = B.part + wd.part_off;
+    const size_t stride = (size_t)wd.part_stride;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < wd.part_stride; idx += gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int c0 = 0; c0 < wd.n_parts; c0 += 16) {
+            double v[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) v[u] = (c0 + u < wd.n_parts) ? part[(size_t)(c0 + u) * stride + idx] : 0.0;
+#pragma unroll
+            for (int u = 0; u < 16; ++u) s += v[u];
+        }
+        part[idx] = s;
+    }
+}
+
 __global__ void __launch_bounds__(kSolveThreads) k_solve(Batch B) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *S = reinterpret_cast<double *>(smem_raw);
@@ -47,7 +68,7 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(Batch B) {
     const int npairs = all_pairs ? F * (F + 1) / 2 : F * (F - 1) / 2;
     const int offd = npairs * 36;
     const double *part = B.part + wd.part_off;
-    const int nparts = wd.n_parts;
+    const int nparts = B.parts_reduced ? 1 : wd.n_parts;
     const size_t stride = (size_t)wd.part_stride;
     // up to 32 independent loads in flight per entry (one CTA has to pull every partial through its own SM),
     // added in part order
@@ -198,24 +219,45 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(Batch B) {
                 dinv[base] = i0; dinv[base + 1] = i1; dinv[base + 2] = i2; dinv[base + 3] = i3; dinv[base + 4] = i4; dinv[base + 5] = i5;
                 if (!okl) s_ok = 0;
             }
+            // trailing update, one thread per half block (3 x 6 entries in registers, all operands loaded before the first
+            // store so the shared-memory loads pipeline); the rhs row against every trailing column rides along
             const int m = F - kb - 1;
-            const int items = m * (m + 1) / 2 * 36;
-            const int extra = 6 * m;   // the rhs row against every trailing column
-            for (int item = tid; item < items + extra; item += kSolveThreads) {
-                int r, cc;
-                if (item < items) {
-                    const int blk = item / 36, q = item - blk * 36;
-                    const int a = q / 6, c = q - a * 6;
-                    r = 6 * (kb + 1 + tabR[blk]) + a; cc = 6 * (kb + 1 + tabC[blk]) + c;
-                    if (cc > r) continue;
-                } else {
-                    r = n; cc = base + 6 + (item - items);
-                }
-                const double *lr = S + tri(r, base), *lc = S + tri(cc, base);
-                double sacc = 0.0;
+            const int halves = m * (m + 1);
+            const int extra = 6 * m;
+            for (int item = tid; item < halves + extra; item += kSolveThreads) {
+                if (item < halves) {
+                    const int blk = item >> 1, a0 = (item & 1) * 3;
+                    const int r0 = 6 * (kb + 1 + tabR[blk]) + a0, c0 = 6 * (kb + 1 + tabC[blk]);
+                    double L[18], acc[18];
 #pragma unroll
-                for (int k = 0; k < 6; ++k) sacc = fma(lr[k], lc[k], sacc);
-                S[tri(r, cc)] -= sacc;
+                    for (int a = 0; a < 3; ++a) {
+                        const double *lr = S + tri(r0 + a, base);
+                        const double *dst = S + tri(r0 + a, c0);
+#pragma unroll
+                        for (int k = 0; k < 6; ++k) { L[a * 6 + k] = lr[k]; acc[a * 6 + k] = (c0 + k <= r0 + a) ? dst[k] : 0.0; }
+                    }
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) {
+                        const double *lc = S + tri(c0 + c, base);
+                        const double w0 = lc[0], w1 = lc[1], w2 = lc[2], w3 = lc[3], w4 = lc[4], w5 = lc[5];
+#pragma unroll
+                        for (int a = 0; a < 3; ++a)
+                            acc[a * 6 + c] -= fma(L[a * 6], w0, fma(L[a * 6 + 1], w1, fma(L[a * 6 + 2], w2, fma(L[a * 6 + 3], w3, fma(L[a * 6 + 4], w4, L[a * 6 + 5] * w5)))));
+                    }
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        double *dst = S + tri(r0 + a, c0);
+#pragma unroll
+                        for (int k = 0; k < 6; ++k) if (c0 + k <= r0 + a) dst[k] = acc[a * 6 + k];   // diagonal block: lower half only
+                    }
+                } else {
+                    const int cc = base + 6 + (item - halves);
+                    const double *lr = S + tri(n, base), *lc = S + tri(cc, base);
+                    double sacc = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) sacc = fma(lr[k], lc[k], sacc);
+                    S[tri(n, cc)] -= sacc;
+                }
             }
             __syncthreads();
         }

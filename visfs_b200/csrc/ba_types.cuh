@@ -105,6 +105,7 @@ struct Batch {
     const int *link_win, *link_from, *link_to;   // [tot_link] window, window-local pose indices
     const double *link_m;            // [tot_link][7] measurement t, q
     double *link_lin;                // [tot_link][kLinkStride] per-trial records of k_link_lin
+    int parts_reduced;               // 1: k_reduce_parts has folded all partial systems of a window into its first one
     double *dbg;                     // parity hook: k_solve dumps packed S and b_s of window 0 here (else null)
     double dbg_lambda;               // parity hook: damping override (< 0: keep the LM state's)
 };

@@ -78,7 +78,7 @@ struct visfs_ba_handle {
     std::vector<Chunk> chunks;
     std::vector<LMState> st_host;
     size_t solve_smem = 0;
-    int grid_lm_x = 1, grid_edge_x = 1;
+    int grid_lm_x = 1, grid_edge_x = 1, reduce_grid = 1;
 
     // device memory
     DevBuf d_st, d_pose, d_point, d_pose_flags, d_lm_flags, d_pose_hidx, d_pose_active, d_point_hidx,
@@ -292,6 +292,7 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs) {
     int per_window = 1;
     if (n == 1) {
         per_window = std::max(1, std::min((max_point + kTileLm / 2 - 1) / (kTileLm / 2), (sms * 7 / 8) / 4 * 4));
+        if (const char *e = getenv("VISFS_BA_CHUNKS")) per_window = std::max(1, atoi(e));   // experiments
     } else {
         double best = -1.0;
         for (int c = 1; c <= 16; ++c) {
@@ -304,7 +305,9 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs) {
     int cl = 1;
     // clusters only for the single-window latency case: 4 CTAs per cluster still fit one wave (33 clusters of 4 are
     // co-resident at 195 KB of shared memory per CTA; clusters of 8 drop that to 15) and cut k_solve's input 4x
-    if (h->use_ws && n == 1 && !getenv("VISFS_BA_NO_CLUSTER")) while (cl < 4 && cl * 2 <= per_window) cl *= 2;
+    int cl_max = 4;
+    if (const char *e = getenv("VISFS_BA_CLUSTER")) cl_max = std::max(1, std::min(atoi(e), 8));
+    if (h->use_ws && n == 1 && !getenv("VISFS_BA_NO_CLUSTER")) while (cl < cl_max && cl * 2 <= per_window) cl *= 2;
     h->cluster = cl;
     h->chunks.clear();
     long long part_total = 0;
@@ -454,6 +457,18 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs) {
         perm = h->d_edge_orig.as<int>();
     }
     h->batch = make_batch(h);
+    {   // few windows with many partial systems each: fold them with a wide kernel before the one-CTA k_solve
+        int max_parts = 0, max_stride = 0;
+        long long volume = 0;   // doubles one k_solve CTA would have to pull through its SM
+        for (const WinDesc &d : h->win) {
+            if (d.large) continue;
+            max_parts = std::max(max_parts, d.n_parts); max_stride = std::max(max_stride, d.part_stride);
+            volume = std::max(volume, (long long)d.n_parts * d.part_stride);
+        }
+        // worth an extra launch (~3 us) from about 0.8 MB per window (C2: 1.9 MB, C1: 0.5 MB)
+        h->batch.parts_reduced = (n <= 8 && max_parts >= 4 && volume >= 100000 && !getenv("VISFS_BA_NO_REDUCE")) ? 1 : 0;
+        h->reduce_grid = std::max(1, std::min((max_stride + 255) / 256, 64));
+    }
     h->batch_ctl = h->batch;
     h->batch_ctl.part2 = h->d_scal.as<double>() + 2;
     Batch &B = h->batch;
@@ -539,6 +554,10 @@ int enqueue_body(visfs_ba_handle *h) {
     ev_end(h, ev);
     ev = ev_begin(h, EV_SOLVE);
     if (h->tot_link > 0) { k_link_lin<<<(h->tot_link + 63) / 64, 64, 0, h->stream>>>(h->batch); h->launches += 1; }
+    if (h->batch.parts_reduced) {
+        k_reduce_parts<<<dim3((unsigned)h->reduce_grid, (unsigned)h->n_win), 256, 0, h->stream>>>(h->batch);
+        h->launches += 1;
+    }
     k_solve<<<h->n_win, kSolveThreads, h->solve_smem, h->stream>>>(h->batch);
     ev_end(h, ev);
     ev = ev_begin(h, EV_UPDATE);
