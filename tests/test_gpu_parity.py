@@ -315,3 +315,23 @@ def test_solve_links_with_pcg_and_in_a_batch(ba):
     got = ba.solve_batch(ws)
     for k, (g, w) in enumerate(zip(got, ws)):
         check_solution(g, O.solve(w), f"batch window {k}")
+
+
+# ---------------------------------------------------------------- empty inputs
+def test_empty_and_degenerate_windows(ba):
+    # no edges at all: nothing is active, both passes stop as "empty", the state comes back untouched
+    w = synth.make_window(4, 30, layout="all", seed=501)
+    for k in ("edge_obs", "edge_pose", "edge_point", "edge_kind"):
+        w[k] = np.ascontiguousarray(w[k][:0])
+    w["n_edges"] = 0
+    got, ref = ba.solve(w), O.solve(w)
+    check_solution(got, ref, "no edges")
+    assert np.array_equal(got["pose_tq"], w["pose_tq"]) and np.array_equal(got["point_xyz"], w["point_xyz"])
+    # every vertex fixed: edges exist but none is active
+    w = synth.make_window(3, 20, layout="all", seed=502, fixed_point_frac=1.0)
+    w["pose_fixed"][:] = 1
+    check_solution(ba.solve(w), O.solve(w), "everything fixed")
+    # a batch that mixes an empty window with ordinary ones
+    ws = [synth.make_window(5, 100, layout="all", seed=503), dict(w), synth.make_window(4, 80, layout="all", seed=504)]
+    for g, x in zip(ba.solve_batch(ws), ws):
+        check_solution(g, O.solve(x), "mixed batch")
