@@ -379,7 +379,10 @@ def run_gpu(args):
     if gba is not None:
         line["global_ba"] = gba
     if world == 1 and not args.no_global:
-        line["dense_window"] = dense_window_numbers(ba, args.quick)
+        try:
+            line["dense_window"] = dense_window_numbers(ba, args.quick)
+        except Exception as exc:  # reported, never silently dropped
+            line["dense_window"] = {"error": repr(exc)}
 
     # ---- CPU baseline (rank 0, N = 1 only) and the single-window latency cases
     if world == 1 and not args.no_cpu:
