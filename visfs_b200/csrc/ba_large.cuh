@@ -318,6 +318,289 @@ __global__ void __launch_bounds__(kThreadsL) k_build_large(Batch B) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_build_large_run: the same build for landmarks of degree <= 10, with the atomics taken out of the inner loop.
+// The landmarks are walked in the order of their first pose (lm_order, sorted on the device once per pass), every warp
+// takes a contiguous piece of that order, and consecutive landmarks that touch the SAME poses form a run: the Schur
+// products of a run are accumulated in registers (a lane owns up to two pose pairs, 2 x 36 accumulators), the per-pose
+// sums in the warp's shared-memory slab, and only the end of a run goes to the skyline with red.global.add.f64.  In a map
+// whose landmarks are seen by consecutive frames a run is a few hundred landmarks long (C4: ~250).
+// ------------------------------------------------------------------------------------------------
+constexpr int kRunDeg = 10;                          // landmark degree limit of this kernel: d (d + 1) / 2 <= 64 pose pairs
+struct RunWarp {
+    double W[kRunDeg * 18];
+    double Yn[kRunDeg * 18];
+    double PA[kRunDeg * kHStride];                   // per edge slot: H_pp (21, upper) | g (6) | b_p (6), summed over the run
+    long long base[kRunDeg];
+    int hi[kRunDeg];
+    int pad[2];
+};
+struct RunSmem { RunWarp w[kWarpsL]; };
+
+__global__ void __launch_bounds__(kThreadsL, 1) k_build_large_run(Batch B, const int4 *__restrict__ lm_rec) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RunSmem &sm = *reinterpret_cast<RunSmem *>(smem_raw);
+    const WinDesc &wd = B.win[0];
+    const LMState &st = B.st[0];
+    if (st.done) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cur = st.cur;
+    const double lambda = (wd.trust == 0) ? (B.dbg_lambda >= 0.0 ? B.dbg_lambda : st.lambda) : 0.0;
+    const Intr K = load_intr(wd);
+    const double *__restrict__ gpose = B.pose + (size_t)cur * B.tot_pose * kPoseStride;
+    const double *__restrict__ gpoint = B.point + (size_t)cur * B.tot_point * 3;
+    double *__restrict__ sky = B.red;
+    double *__restrict__ gvec = B.red + B.red_g_off;
+    double *__restrict__ bpvec = B.red + B.red_bp_off;
+    RunWarp &S = sm.w[warp];
+
+    // this warp's piece of the order
+    const int nwarp = gridDim.x * kWarpsL, gw = blockIdx.x * kWarpsL + warp;
+    const int per = (wd.n_point + nwarp - 1) / nwarp;
+    const int i0 = min(gw * per, wd.n_point), i1 = min(i0 + per, wd.n_point);
+
+    double acc0[36], acc1[36];
+#pragma unroll
+    for (int q = 0; q < 36; ++q) { acc0[q] = 0.0; acc1[q] = 0.0; }
+    int run_d = -1, run_sig = -3, run_free = 0, run_len = 0;   // run_sig: this lane's entry of the signature
+    int pa0 = -1, pb0 = -1, pa1 = -1, pb1 = -1;                // edge slots (a <= b) of the two pairs this lane owns
+
+    auto flush = [&]() {
+        if (run_len > 0) {
+            if (run_free) {
+                // pairs: product block (h_a, h_b) -> lower block (h_b, h_a), element (r, c) at row c, column r
+                if (pa0 >= 0 && S.hi[pa0] >= 0 && S.hi[pb0] >= 0) {
+                    double *blk = sky + (size_t)(S.base[pb0] + S.hi[pa0]) * 36;
+#pragma unroll
+                    for (int r = 0; r < 6; ++r)
+#pragma unroll
+                        for (int c = 0; c < 6; ++c) if (pa0 != pb0 || c >= r) atomicAdd(&blk[c * 6 + r], acc0[r * 6 + c]);
+                }
+                if (pa1 >= 0 && S.hi[pa1] >= 0 && S.hi[pb1] >= 0) {
+                    double *blk = sky + (size_t)(S.base[pb1] + S.hi[pa1]) * 36;
+#pragma unroll
+                    for (int r = 0; r < 6; ++r)
+#pragma unroll
+                        for (int c = 0; c < 6; ++c) if (pa1 != pb1 || c >= r) atomicAdd(&blk[c * 6 + r], acc1[r * 6 + c]);
+                }
+            }
+            // per-pose sums of this lane's edge slot
+            if (lane < run_d && run_sig >= 0) {
+                const double *pa = S.PA + lane * kHStride;
+                double *dblk = sky + (size_t)(S.base[lane] + run_sig) * 36;
+#pragma unroll
+                for (int a = 0; a < 6; ++a) {
+                    atomicAdd(&gvec[6 * (size_t)run_sig + a], pa[21 + a]);
+                    atomicAdd(&bpvec[6 * (size_t)run_sig + a], pa[27 + a]);
+#pragma unroll
+                    for (int c = a; c < 6; ++c) atomicAdd(&dblk[c * 6 + a], pa[hd_index(a, c)]);
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 36; ++q) { acc0[q] = 0.0; acc1[q] = 0.0; }
+        run_len = 0;
+        __syncwarp();
+    };
+
+    // software pipeline: the sorted records are read 32 at a time (lane j holds landmark blk0 + j), the edge records and the
+    // point of landmark idx + 1 are requested while landmark idx is computed — their addresses come from the record block,
+    // not from a chain of dependent loads
+    int4 rblk = make_int4(0, 0, 0, 0);
+    int blk0 = i0 - 32;
+    int n_pw = 0;
+    double n_ou = 0.0, n_ov = 0.0, n_our = 0.0, n_pt = 0.0;   // next landmark: edge record of this lane, point coordinate (lanes 0..2)
+    auto request = [&](int idx) {
+        if (idx >= i1) return;
+        if (idx >= blk0 + 32) { blk0 = idx; rblk = (idx + lane < i1) ? lm_rec[idx + lane] : make_int4(0, 0, 0, 0); }
+        const int j = idx - blk0;
+        const int l = __shfl_sync(0xffffffffu, rblk.x, j), e0 = __shfl_sync(0xffffffffu, rblk.y, j), d = __shfl_sync(0xffffffffu, rblk.z, j);
+        if (lane < d) {
+            const int e = e0 + lane;
+            n_pw = B.edge_pose[e];
+            n_ou = B.obs_u[e]; n_ov = B.obs_v[e]; n_our = B.obs_r[e];
+        }
+        if (lane < 3) n_pt = gpoint[3 * (size_t)l + lane];
+    };
+    request(i0);
+    for (int idx = i0; idx < i1; ++idx) {
+        const int j = idx - blk0;
+        const int l = __shfl_sync(0xffffffffu, rblk.x, j), d = __shfl_sync(0xffffffffu, rblk.z, j);
+        const uint8_t lf = (uint8_t)__shfl_sync(0xffffffffu, rblk.w, j);
+        (void)l;
+        const int pw = n_pw;
+        const double ou = n_ou, ov = n_ov, our = n_our;
+        const double px = __shfl_sync(0xffffffffu, n_pt, 0), py = __shfl_sync(0xffffffffu, n_pt, 1), pz = __shfl_sync(0xffffffffu, n_pt, 2);
+        request(idx + 1);
+        if (d <= 0) continue;
+        const bool lmfree = (lf & kInHessian) != 0;
+        bool act = false;
+        int hi = -1;
+        EdgeLin lin;
+        if (lane < d) {
+            const int p = pw & kPoseMask;
+            act = !(pw & kCulledBit) && !((lf & kFixed) && (B.pose_flags[p] & kFixed));
+            if (act) {
+                hi = B.pose_hidx[p];
+                edge_linearize(gpose + (size_t)p * kPoseStride, px, py, pz, ou, ov, our, (pw & kMonoBit) != 0, K, lin);
+            }
+        }
+        const int sig = (lane < d) ? ((act && hi >= 0) ? hi : -1) : -2;
+        // same poses as the running run?
+        const bool same = (d == run_d) && (lmfree == (run_free != 0)) && __all_sync(0xffffffffu, sig == run_sig);
+        if (!same) {
+            flush();
+            run_d = d; run_sig = sig; run_free = lmfree ? 1 : 0;
+            if (lane < d) {
+                S.hi[lane] = sig;
+                S.base[lane] = (sig >= 0) ? (B.sky_off[sig] - B.sky_first[sig]) : 0;
+#pragma unroll
+                for (int q = 0; q < kHStride; ++q) S.PA[lane * kHStride + q] = 0.0;
+            }
+            // pair p (row-major over a <= b < d) -> (a, b) for p = lane and lane + 32
+            const int np = d * (d + 1) / 2;
+            pa0 = pb0 = pa1 = pb1 = -1;
+            {
+                int p = lane, a = 0;
+                if (p < np) { while (p >= d - a) { p -= d - a; ++a; } pa0 = a; pb0 = a + p; }
+                p = lane + 32; a = 0;
+                if (p < np) { while (p >= d - a) { p -= d - a; ++a; } pa1 = a; pb1 = a + p; }
+            }
+            __syncwarp();
+        }
+        run_len += 1;
+
+        const double wo = act ? lin.w * K.inv_pv : 0.0;
+        double hl[9];
+        if (act && lmfree) {
+            const double *J = lin.Jl;
+            hl[0] = wo * fma(J[0], J[0], fma(J[3], J[3], J[6] * J[6]));
+            hl[1] = wo * fma(J[0], J[1], fma(J[3], J[4], J[6] * J[7]));
+            hl[2] = wo * fma(J[0], J[2], fma(J[3], J[5], J[6] * J[8]));
+            hl[3] = wo * fma(J[1], J[1], fma(J[4], J[4], J[7] * J[7]));
+            hl[4] = wo * fma(J[1], J[2], fma(J[4], J[5], J[7] * J[8]));
+            hl[5] = wo * fma(J[2], J[2], fma(J[5], J[5], J[8] * J[8]));
+            hl[6] = -wo * fma(J[0], lin.r[0], fma(J[3], lin.r[1], J[6] * lin.r[2]));
+            hl[7] = -wo * fma(J[1], lin.r[0], fma(J[4], lin.r[1], J[7] * lin.r[2]));
+            hl[8] = -wo * fma(J[2], lin.r[0], fma(J[5], lin.r[1], J[8] * lin.r[2]));
+        } else {
+#pragma unroll
+            for (int q = 0; q < 9; ++q) hl[q] = 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 9; ++q) hl[q] = warp_sum(hl[q]);
+        double Di[6], db[3] = {0.0, 0.0, 0.0};
+        if (lmfree) {
+            const double A[6] = {hl[0] + lambda, hl[1], hl[2], hl[3] + lambda, hl[4], hl[5] + lambda};
+            const double bl[3] = {hl[6], hl[7], hl[8]};
+            inv_sym3(A, Di);
+            sym3_mul(Di, bl, db);
+        }
+        if (sig >= 0) {
+            double Wm[18];
+            double *ws = S.W + lane * 18, *ys = S.Yn + lane * 18;
+            if (lmfree) {
+                double Aj[9];
+#pragma unroll
+                for (int q = 0; q < 9; ++q) Aj[q] = wo * lin.Jl[q];
+#pragma unroll
+                for (int a = 0; a < 6; ++a)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+                        Wm[a * 3 + c] = fma(lin.Jp[a], Aj[c], fma(lin.Jp[6 + a], Aj[3 + c], lin.Jp[12 + a] * Aj[6 + c]));
+#pragma unroll
+                for (int a = 0; a < 6; ++a) {
+                    ws[a * 3] = Wm[a * 3]; ws[a * 3 + 1] = Wm[a * 3 + 1]; ws[a * 3 + 2] = Wm[a * 3 + 2];
+                    ys[a * 3 + 0] = -fma(Wm[a * 3], Di[0], fma(Wm[a * 3 + 1], Di[1], Wm[a * 3 + 2] * Di[2]));
+                    ys[a * 3 + 1] = -fma(Wm[a * 3], Di[1], fma(Wm[a * 3 + 1], Di[3], Wm[a * 3 + 2] * Di[4]));
+                    ys[a * 3 + 2] = -fma(Wm[a * 3], Di[2], fma(Wm[a * 3 + 1], Di[4], Wm[a * 3 + 2] * Di[5]));
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 18; ++q) Wm[q] = 0.0;
+            }
+            const double wr0 = wo * lin.r[0], wr1 = wo * lin.r[1], wr2 = wo * lin.r[2];
+            double *pa = S.PA + lane * kHStride;
+#pragma unroll
+            for (int a = 0; a < 6; ++a) {
+                const double bp = -fma(lin.Jp[a], wr0, fma(lin.Jp[6 + a], wr1, lin.Jp[12 + a] * wr2));
+                pa[27 + a] += bp;
+                pa[21 + a] += bp - fma(Wm[a * 3], db[0], fma(Wm[a * 3 + 1], db[1], Wm[a * 3 + 2] * db[2]));
+#pragma unroll
+                for (int c = a; c < 6; ++c)
+                    pa[hd_index(a, c)] += wo * fma(lin.Jp[a], lin.Jp[c], fma(lin.Jp[6 + a], lin.Jp[6 + c], lin.Jp[12 + a] * lin.Jp[12 + c]));
+            }
+        }
+        __syncwarp();
+        if (lmfree) {
+            if (pa0 >= 0 && S.hi[pa0] >= 0 && S.hi[pb0] >= 0) {
+                const double *ya = S.Yn + pa0 * 18, *wb = S.W + pb0 * 18;
+                double Wj[18];
+#pragma unroll
+                for (int q = 0; q < 18; ++q) Wj[q] = wb[q];
+#pragma unroll
+                for (int r = 0; r < 6; ++r) {
+                    const double y0 = ya[r * 3], y1 = ya[r * 3 + 1], y2 = ya[r * 3 + 2];
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) acc0[r * 6 + c] = fma(y0, Wj[c * 3], fma(y1, Wj[c * 3 + 1], fma(y2, Wj[c * 3 + 2], acc0[r * 6 + c])));
+                }
+            }
+            if (pa1 >= 0 && S.hi[pa1] >= 0 && S.hi[pb1] >= 0) {
+                const double *ya = S.Yn + pa1 * 18, *wb = S.W + pb1 * 18;
+                double Wj[18];
+#pragma unroll
+                for (int q = 0; q < 18; ++q) Wj[q] = wb[q];
+#pragma unroll
+                for (int r = 0; r < 6; ++r) {
+                    const double y0 = ya[r * 3], y1 = ya[r * 3 + 1], y2 = ya[r * 3 + 2];
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) acc1[r * 6 + c] = fma(y0, Wj[c * 3], fma(y1, Wj[c * 3 + 1], fma(y2, Wj[c * 3 + 2], acc1[r * 6 + c])));
+                }
+            }
+        }
+        __syncwarp();
+    }
+    flush();
+}
+
+// first pose (smallest hessian index) of every landmark in the Hessian, the sort key of k_build_large_run's order
+__global__ void k_lm_first(Batch B, int *key, int *idx) {
+    const WinDesc &wd = B.win[0];
+    for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < wd.n_point; l += gridDim.x * blockDim.x) {
+        int mn = 0x7fffffff;
+        for (int e = B.lm_edge_off[l]; e < B.lm_edge_off[l + 1]; ++e) {
+            const int hi = B.pose_hidx[B.edge_pose[e] & kPoseMask];
+            if (hi >= 0) mn = min(mn, hi);
+        }
+        key[l] = mn;
+        idx[l] = l;
+    }
+}
+
+// sorted landmark records for k_build_large_run: rec[idx] = (landmark, first edge, degree, flags) so that the kernel reads
+// them contiguously, and the number of runs (landmarks whose pose list differs from their predecessor's in the order)
+__global__ void k_run_prep(Batch B, const int *__restrict__ order, int4 *rec, int *n_runs) {
+    const WinDesc &wd = B.win[0];
+    int cnt = 0;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < wd.n_point; idx += gridDim.x * blockDim.x) {
+        const int l = order[idx];
+        const int e0 = B.lm_edge_off[l], d = B.lm_edge_off[l + 1] - e0;
+        rec[idx] = make_int4(l, e0, d, (int)B.lm_flags[l]);
+        bool boundary = (idx == 0);
+        if (!boundary) {
+            const int lp = order[idx - 1];
+            const int p0 = B.lm_edge_off[lp], dp = B.lm_edge_off[lp + 1] - p0;
+            boundary = (dp != d) || ((B.lm_flags[lp] ^ B.lm_flags[l]) & kInHessian);
+            for (int k = 0; k < d && !boundary; ++k)
+                boundary = ((B.edge_pose[e0 + k] ^ B.edge_pose[p0 + k]) & (kPoseMask | kCulledBit)) != 0;
+        }
+        cnt += boundary ? 1 : 0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(n_runs, cnt);
+}
+
 // sum / max of the per-CTA partials in CTA order -> out[0], out[1]   (one CTA)
 __global__ void k_fold_part2(Batch B, int n, int second_is_max, double *out) {
     __shared__ double red[32];

@@ -117,6 +117,9 @@ struct visfs_ba_handle {
     int grid_build_l = 1, grid_update_l = 1;
     long long n_sky = 0;
     int max_front = 0, coop_grid = 0, pcg_grid = 0;
+    int max_deg = -1;                 // largest landmark degree of the uploaded batch (-1: unknown, unsorted edge list)
+    bool use_run = false;             // k_build_large_run: landmarks walked in the order of their first pose
+    DevBuf d_lm_key, d_lm_key2, d_lm_idx, d_lm_order, d_sort_tmp, d_lm_rec;
     DevBuf d_pcg;
     bool use_front = false;
     DevBuf d_plan;
@@ -238,6 +241,7 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs) {
     long long tp = 0, tl = 0, te = 0, tk = 0;
     int max_pose = 0, max_point = 0, max_edge = 0, max_iter = 0, max_free = 0;
     bool all_sorted = true, any_large = false, any_part = false;
+    int max_deg_seen = 0;
     for (int w = 0; w < n; ++w) {
         const visfs_ba_problem &p = probs[w];
         bool srt; int deg;
@@ -252,6 +256,7 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs) {
         // (the degree limit of the large path is checked on the device so that all ranks of a partitioned run agree)
         if (!big && deg > kTileEdges) return h->fail(VISFS_BA_ERR_UNSUPPORTED, "landmark observed by more poses than one tile holds (kTileEdges)");
         all_sorted = all_sorted && srt;
+        max_deg_seen = (deg < 0 || max_deg_seen < 0) ? -1 : std::max(max_deg_seen, deg);
         WinDesc &d = h->win[w];
         d.pose_off = (int)tp; d.n_pose = p.n_poses; d.point_off = (int)tl; d.n_point = p.n_points;
         d.edge_off = (int)te; d.n_edge = p.n_edges;
@@ -277,6 +282,7 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs) {
     h->n_win = n; h->tot_pose = (int)tp; h->tot_point = (int)tl; h->tot_edge = (int)te; h->tot_link = (int)tk;
     h->max_pose = max_pose; h->max_iter = max_iter; h->sorted = all_sorted;
     h->large = any_large; h->partitioned = any_part;
+    h->max_deg = max_deg_seen;
     if (any_part && h->comm_ranks > 1 && !h->comm) return h->fail(VISFS_BA_ERR_INVALID, "partitioned problem without visfs_ba_comm_init");
     if (any_large && probs[0].solver == VISFS_BA_SOLVER_PCG && h->pcg_grid < 1)
         return h->fail(VISFS_BA_ERR_UNSUPPORTED, "Optimizer/Solver=2 (PCG) on a large window needs cooperative kernel launches");
@@ -731,6 +737,24 @@ int run_structure_large(visfs_ba_handle *h) {
         lg::k_set_counts<<<1, 32, 0, s>>>(B, h->d_cnt.as<int>());
         h->launches += 2;
     }
+    // landmarks in the order of their first pose for the run-aggregating build kernel (degree <= 10 only)
+    h->use_run = h->max_deg >= 0 && h->max_deg <= lg::kRunDeg && h->tot_point > 0 && !getenv("VISFS_BA_NO_RUN");
+    if (h->use_run) {
+        const size_t L = (size_t)h->tot_point;
+        CK(h->d_lm_key.reserve(sizeof(int) * L)); CK(h->d_lm_key2.reserve(sizeof(int) * L));
+        CK(h->d_lm_idx.reserve(sizeof(int) * L)); CK(h->d_lm_order.reserve(sizeof(int) * L));
+        lg::k_lm_first<<<glm, 256, 0, s>>>(B, h->d_lm_key.as<int>(), h->d_lm_idx.as<int>());
+        size_t tb = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tb, h->d_lm_key.as<int>(), h->d_lm_key2.as<int>(), h->d_lm_idx.as<int>(),
+                                        h->d_lm_order.as<int>(), (int)L, 0, 32, s);
+        CK(h->d_sort_tmp.reserve(tb));
+        CK(cub::DeviceRadixSort::SortPairs(h->d_sort_tmp.p, tb, h->d_lm_key.as<int>(), h->d_lm_key2.as<int>(), h->d_lm_idx.as<int>(),
+                                           h->d_lm_order.as<int>(), (int)L, 0, 32, s));
+        CK(h->d_lm_rec.reserve(sizeof(int4) * L));
+        CK(cudaMemsetAsync(h->d_info.as<long long>() + 3, 0, sizeof(long long), s));
+        lg::k_run_prep<<<glm, 256, 0, s>>>(B, h->d_lm_order.as<int>(), h->d_lm_rec.as<int4>(), reinterpret_cast<int *>(h->d_info.as<long long>() + 3));
+        h->launches += 3;
+    }
     const int gp = std::max(1, std::min((h->tot_pose + 255) / 256, 64));
     lg::k_sky_init<<<gp, 256, 0, s>>>(B);
     lg::k_sky_first<<<glm, 256, 0, s>>>(B);
@@ -739,10 +763,14 @@ int run_structure_large(visfs_ba_handle *h) {
     lg::k_col_count<<<std::max(1, std::min(h->tot_pose, 1024)), 128, 0, s>>>(B, h->d_col_cnt.as<int>());
     lg::k_col_scan<<<1, 1024, 0, s>>>(B, h->d_col_cnt.as<int>(), h->d_info.as<long long>());
     long long *info = h->h_small.as<long long>() + 2;
-    CK(cudaMemcpyAsync(info, h->d_info.p, sizeof(long long) * 3, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(info, h->d_info.p, sizeof(long long) * 4, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     h->n_sky = info[0];
     h->max_front = (int)info[2];
+    if (h->use_run) {   // worth it only when landmarks that touch the same poses follow each other: runs of >= 4 on average
+        const long long n_runs = (long long)(int)(info[3] & 0xffffffffLL);
+        if (n_runs * 4 > h->tot_point) h->use_run = false;
+    }
     const long long F = info[1];
     const size_t red_len = (size_t)h->n_sky * 36 + 12 * (size_t)F;
     CK(h->d_red.reserve(sizeof(double) * std::max<size_t>(red_len, 8)));
@@ -768,7 +796,11 @@ size_t red_doubles(const visfs_ba_handle *h) { return (size_t)h->batch.red_bp_of
 int enqueue_build_large(visfs_ba_handle *h) {
     int ev = ev_begin(h, EV_BUILD);
     CK(cudaMemsetAsync(h->d_red.p, 0, sizeof(double) * red_doubles(h), h->stream));
-    lg::k_build_large<false><<<h->grid_build_l, lg::kThreadsL, sizeof(lg::BuildSmemL), h->stream>>>(h->batch);
+    if (h->use_run)
+        lg::k_build_large_run<<<std::max(1, std::min(h->sm_count, (h->tot_point + 63) / 64)), lg::kThreadsL, sizeof(lg::RunSmem), h->stream>>>(
+            h->batch, h->d_lm_rec.as<int4>());
+    else
+        lg::k_build_large<false><<<h->grid_build_l, lg::kThreadsL, sizeof(lg::BuildSmemL), h->stream>>>(h->batch);
     ev_end(h, ev);
     h->launches += 1;
     if (h->partitioned) {
@@ -1076,7 +1108,8 @@ void visfs_ba_destroy(visfs_ba_handle *h) {
     cudaStreamSynchronize(h->stream);
     {
         DevBuf *lb[] = {&h->d_sky_first, &h->d_sky_off, &h->d_col_ptr, &h->d_col_cnt, &h->d_col_rows, &h->d_red, &h->d_hdiag,
-                        &h->d_scal, &h->d_info, &h->d_cnt, &h->d_plan, &h->d_pcg};
+                        &h->d_scal, &h->d_info, &h->d_cnt, &h->d_plan, &h->d_pcg, &h->d_lm_key, &h->d_lm_key2, &h->d_lm_idx,
+                        &h->d_lm_order, &h->d_sort_tmp, &h->d_lm_rec};
         for (DevBuf *b : lb) b->release();
     }
     DevBuf *bufs[] = {&h->d_in, &h->d_st, &h->d_pose, &h->d_point, &h->d_pose_flags, &h->d_lm_flags, &h->d_pose_hidx,
