@@ -49,8 +49,8 @@
  * Limits
  *   - windows of up to 32 poses: any number per batch, landmarks with up to 192 observations;
  *   - windows with more poses, and partitioned problems: one per call, landmarks with up to 32
- *     observations (block-skyline path); all Optimizer/Solver values are implemented on both paths;
- *     odometry links (n_links > 0) on the small-window path only.
+ *     observations (block-skyline path); all Optimizer/Solver values and odometry links (n_links > 0) are implemented
+ *     on both paths.  In a partitioned run every rank passes ALL links.
  *
  * Conventions
  *   - poses are T_camera<-world, stored t(3) then quaternion x,y,z,w  (CameraPose::toVector,

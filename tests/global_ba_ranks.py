@@ -25,7 +25,8 @@ def main():
     ba = capi.BundleAdjuster(device=local)
     ba.comm_init_torch(dist)
 
-    w = synth.make_window(48, 3000, views=7, layout="consecutive", trajectory="loop", seed=91, mono_frac=0.2, fixed_point_frac=0.1)
+    w = synth.make_window(48, 3000, views=7, layout="consecutive", trajectory="loop", seed=91, mono_frac=0.2, fixed_point_frac=0.1,
+                          links="chain")
     part = partition.partition_window(w, world, rank)
     res = ba.solve(part)
     # gather the per-rank results on rank 0

@@ -91,6 +91,20 @@ def test_large_solve_pcg(ba):
     check_solution(ba.solve(w), O.solve(w), "PCG, dense")
 
 
+def test_large_with_odometry_links(ba):
+    w = loop(seed=87, P=40, L=900, links="chain")
+    _structure_case(ba, w)
+    lam = 0.9
+    got, ref = ba.debug_trial(w, lam), O.reduced_system(w, lam)
+    rel_close(got["chi2"], ref["chi2"], 1e-12, "chi2 with links")
+    rel_close(got["S"], ref["S"], 1e-10, "reduced camera system with pose-pose blocks")
+    rel_close(got["b_s"], ref["b_s"], 1e-10, "reduced rhs")
+    rel_close(ba.debug_trial(w, -1.0)["lambda_used"], ref["lambda_init"], 1e-12, "initial damping")
+    check_solution(ba.solve(w), O.solve(w), "large window with links")
+    part = partition.partition_window(w, 1, 0)
+    check_solution(partition.merge_results(w, [part], [ba.solve(part)]), O.solve(w), "1-rank partition with links")
+
+
 def test_large_rejected_steps(ba):
     w = synth.make_window(34, 400, views=6, layout="consecutive", seed=78, pose_noise=(0.3, np.deg2rad(6.0)), point_noise=0.5,
                           iterations=20, depth_range=(1.0, 6.0))

@@ -1146,6 +1146,76 @@ __global__ void __launch_bounds__(kSolveThreadsL) k_solve_front(Batch B, FrontPl
 }
 
 // ------------------------------------------------------------------------------------------------
+// odometry links on the block skyline (ba_link.cuh): envelope, Hessian / gradient pieces, chi2
+// ------------------------------------------------------------------------------------------------
+__global__ void k_sky_links(Batch B) {   // a link couples its two poses: the later row reaches back to the earlier one
+    if (B.st[0].status != 0) return;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < B.tot_link; k += gridDim.x * blockDim.x) {
+        const int hi = B.pose_hidx[B.link_from[k]], hj = B.pose_hidx[B.link_to[k]];
+        if (hi >= 0 && hj >= 0 && hi != hj) atomicMin(&B.sky_first[max(hi, hj)], min(hi, hj));
+    }
+}
+
+// records of k_link_lin -> skyline blocks, reduced rhs and raw b_p (one thread per link; called on ONE rank of a
+// partitioned run, before the all-reduce)
+__global__ void k_link_add_large(Batch B) {
+    if (B.st[0].done) return;
+    double *sky = B.red, *gvec = B.red + B.red_g_off, *bpvec = B.red + B.red_bp_off;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < B.tot_link; k += gridDim.x * blockDim.x) {
+        const double *rec = B.link_lin + (size_t)k * kLinkStride;
+        const int hi = B.pose_hidx[B.link_from[k]], hj = B.pose_hidx[B.link_to[k]];
+        for (int side = 0; side < 2; ++side) {
+            const int h = side ? hj : hi;
+            if (h < 0) continue;
+            const double *H = rec + (side ? kLkHjj : kLkHii), *b = rec + (side ? kLkBj : kLkBi);
+            double *dblk = sky + (size_t)(B.sky_off[h] + (h - B.sky_first[h])) * 36;
+            for (int a = 0; a < 6; ++a) {
+                atomicAdd(&gvec[6 * (size_t)h + a], b[a]);
+                atomicAdd(&bpvec[6 * (size_t)h + a], b[a]);
+                for (int c = 0; c <= a; ++c) atomicAdd(&dblk[a * 6 + c], H[a * 6 + c]);   // lower half
+            }
+        }
+        if (hi >= 0 && hj >= 0) {
+            // H_ij = J_i' Omega J_j (row pose i, column pose j); lower block (max, min): rows of the later pose
+            const int hr = max(hi, hj), hc = min(hi, hj);
+            double *blk = sky + (size_t)(B.sky_off[hr] + (hc - B.sky_first[hr])) * 36;
+            for (int a = 0; a < 6; ++a)
+                for (int c = 0; c < 6; ++c) {
+                    const double v = rec[kLkHij + a * 6 + c];
+                    if (hj > hi) atomicAdd(&blk[c * 6 + a], v); else atomicAdd(&blk[a * 6 + c], v);
+                }
+        }
+    }
+}
+
+// start of a pass: link part of diag(H_pp) and of chi2 (one CTA; ONE rank of a partitioned run, before the all-reduce)
+__global__ void k_link_init_large(Batch B, double *scal) {
+    if (B.st[0].done) return;
+    __shared__ double red[32];
+    double chi = 0.0;
+    for (int k = threadIdx.x; k < B.tot_link; k += blockDim.x) {
+        const double *rec = B.link_lin + (size_t)k * kLinkStride;
+        chi += rec[kLkChi];
+        const int hi = B.pose_hidx[B.link_from[k]], hj = B.pose_hidx[B.link_to[k]];
+        for (int a = 0; a < 6; ++a) {
+            if (hi >= 0) atomicAdd(&B.hdiag[6 * (size_t)hi + a], rec[kLkHii + 7 * a]);
+            if (hj >= 0) atomicAdd(&B.hdiag[6 * (size_t)hj + a], rec[kLkHjj + 7 * a]);
+        }
+    }
+    const double t = block_sum(chi, red);
+    if (threadIdx.x == 0) scal[0] += t;
+}
+
+// chi2 of the links at the trial poses (after a large-path solve kernel has written them); one CTA
+__global__ void k_link_chi_large(Batch B) {
+    __shared__ double red[32];
+    LMState &st = B.st[0];
+    if (st.done) return;
+    const double c = link_chi2_block(B, B.win[0], 1 - st.cur, red);
+    if (threadIdx.x == 0) st.link_chi_trial = c;
+}
+
+// ------------------------------------------------------------------------------------------------
 // k_solve_pcg: Optimizer/Solver = 2 on the block skyline — g2o LinearSolverPCG (block-Jacobi preconditioner = inverse 6x6
 // diagonal blocks, x0 = 0, at most n iterations, the tolerance quirk of k_solve).  Cooperative launch: one warp per block
 // row for S d (the lower part is the row's own skyline storage, the upper part the transposed blocks of its column

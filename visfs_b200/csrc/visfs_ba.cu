@@ -267,7 +267,6 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs) {
         d.fx = p.fx; d.fy = p.fy; d.cx = p.cx; d.cy = p.cy; d.bf = p.bf;
         d.inv_pv = 1.0 / p.pixel_variance; d.delta = p.huber_delta;
         d.link_off = (int)tk; d.n_link = p.n_links; d.inv_ov = p.n_links > 0 ? 1.0 / p.odometry_variance : 0.0;
-        if (p.n_links > 0 && big) return h->fail(VISFS_BA_ERR_UNSUPPORTED, "odometry links are implemented for windows of up to 32 poses");
         tk += p.n_links;
         tp += p.n_poses; tl += p.n_points; te += p.n_edges;
         {
@@ -758,6 +757,7 @@ int run_structure_large(visfs_ba_handle *h) {
     const int gp = std::max(1, std::min((h->tot_pose + 255) / 256, 64));
     lg::k_sky_init<<<gp, 256, 0, s>>>(B);
     lg::k_sky_first<<<glm, 256, 0, s>>>(B);
+    if (h->tot_link > 0) lg::k_sky_links<<<(h->tot_link + 127) / 128, 128, 0, s>>>(B);
     if ((st = allreduce(h, h->d_sky_first.p, (size_t)h->tot_pose, ncclInt32, ncclMin))) return st;
     lg::k_sky_layout<<<1, 1024, 0, s>>>(B, h->d_col_cnt.as<int>(), h->d_info.as<long long>());
     lg::k_col_count<<<std::max(1, std::min(h->tot_pose, 1024)), 128, 0, s>>>(B, h->d_col_cnt.as<int>());
@@ -801,6 +801,11 @@ int enqueue_build_large(visfs_ba_handle *h) {
             h->batch, h->d_lm_rec.as<int4>());
     else
         lg::k_build_large<false><<<h->grid_build_l, lg::kThreadsL, sizeof(lg::BuildSmemL), h->stream>>>(h->batch);
+    if (h->tot_link > 0) {   // odometry links: every rank evaluates them (identical poses), ONE rank adds them to the sums
+        k_link_lin<<<(h->tot_link + 63) / 64, 64, 0, h->stream>>>(h->batch);
+        if (!h->partitioned || h->comm_rank == 0) lg::k_link_add_large<<<(h->tot_link + 63) / 64, 64, 0, h->stream>>>(h->batch);
+        h->launches += 2;
+    }
     ev_end(h, ev);
     h->launches += 1;
     if (h->partitioned) {
@@ -842,6 +847,7 @@ int enqueue_rest_large(visfs_ba_handle *h) {
     } else {
         lg::k_solve_large<false><<<1, lg::kSolveThreadsL, 0, h->stream>>>(h->batch, h->d_cnt.as<int>() + 2);
     }
+    if (h->tot_link > 0) { lg::k_link_chi_large<<<1, 128, 0, h->stream>>>(h->batch); h->launches += 1; }
     ev_end(h, ev);
     DBG_SYNC("solve kernel");
     ev = ev_begin(h, EV_UPDATE);
@@ -870,6 +876,11 @@ int init_pass_large(visfs_ba_handle *h) {
     CK(cudaMemsetAsync(h->d_hdiag.p, 0, sizeof(double) * 6 * std::max(h->tot_pose, 1), s));
     lg::k_build_large<true><<<h->grid_build_l, lg::kThreadsL, sizeof(lg::BuildSmemL), s>>>(h->batch);
     lg::k_fold_part2<<<1, 256, 0, s>>>(h->batch, h->grid_build_l, 1, h->d_scal.as<double>());
+    if (h->tot_link > 0) {
+        k_link_lin<<<(h->tot_link + 63) / 64, 64, 0, s>>>(h->batch);
+        if (!h->partitioned || h->comm_rank == 0) lg::k_link_init_large<<<1, 128, 0, s>>>(h->batch, h->d_scal.as<double>());
+        h->launches += 2;
+    }
     if ((st = allreduce(h, h->d_hdiag.p, 6 * (size_t)h->tot_pose, ncclFloat64, ncclSum))) return st;
     if ((st = allreduce(h, h->d_scal.as<double>(), 1, ncclFloat64, ncclSum))) return st;
     if ((st = allreduce(h, h->d_scal.as<double>() + 1, 1, ncclFloat64, ncclMax))) return st;
@@ -1311,6 +1322,16 @@ int visfs_ba_structure_build(visfs_ba_handle *h, const visfs_ba_problem *problem
         lkeys.resize(nk);
         if (nk) CK(cudaMemcpyAsync(lkeys.data(), kb2.p, sizeof(unsigned long long) * nk, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
+        if (problem->n_links > 0 && st0.F > 0) {   // pose-pose blocks of the odometry links
+            std::vector<int> hidx((size_t)h->tot_pose);
+            CK(cudaMemcpy(hidx.data(), h->d_pose_hidx.p, sizeof(int) * (size_t)h->tot_pose, cudaMemcpyDeviceToHost));
+            for (int k = 0; k < problem->n_links; ++k) {
+                const int hi = hidx[(size_t)problem->link_from[k]], hj = hidx[(size_t)problem->link_to[k]];
+                if (hi >= 0 && hj >= 0)
+                    lkeys.push_back((unsigned long long)std::max(hi, hj) * (unsigned long long)st0.F + (unsigned long long)std::min(hi, hj));
+            }
+            std::sort(lkeys.begin(), lkeys.end());
+        }
         lkeys.erase(std::unique(lkeys.begin(), lkeys.end()), lkeys.end());
         const int nuniq = (int)lkeys.size();
         std::vector<int> hr(std::max(std::min(nuniq, cap), 1)), hc(std::max(std::min(nuniq, cap), 1));

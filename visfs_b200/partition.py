@@ -30,6 +30,7 @@ def partition_window(w: dict, n_ranks: int, rank: int) -> dict:
     out["edge_point"] = np.ascontiguousarray(ep[keep] - l0).astype(np.int32)
     out["edge_kind"] = np.ascontiguousarray(w["edge_kind"][keep])
     out["n_edges"] = int(keep.sum())
+    # odometry links are pose-pose constraints: every rank passes all of them, the library adds them on one rank only
     out["flags"] = int(w.get("flags", 0)) | FLAG_PARTITIONED
     out["part_range"] = (l0, l1)
     out["part_edge_index"] = np.nonzero(keep)[0]
