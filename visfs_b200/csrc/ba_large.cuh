@@ -1384,7 +1384,13 @@ __global__ void __launch_bounds__(kPcgThreads) k_solve_pcg(Batch B, double *work
 // k_update_large: landmark back-substitution, point oplus, chi2 of the trial state
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreadsL) k_update_large(Batch B) {
+    // Several whole landmarks per warp step, one edge per lane (the warp tiles of the small-window k_update, formed on
+    // the fly): the warp takes the next landmarks of its block whose edges fit 32 lanes (<= 8 landmarks).  Per-landmark
+    // sums go through the warp's shared-memory slab in edge order.
     __shared__ double red[32];
+    __shared__ double s_H[kWarpsL][32 * kHs];
+    __shared__ double s_lm[kWarpsL][kWtLm * 12];
+    __shared__ int s_off[kWarpsL][kWtLm + 1];
     const WinDesc &wd = B.win[0];
     const LMState &st = B.st[0];
     if (st.done) return;
@@ -1396,74 +1402,92 @@ __global__ void __launch_bounds__(kThreadsL) k_update_large(Batch B) {
     const double *__restrict__ gposeT = B.pose + (size_t)(1 - cur) * B.tot_pose * kPoseStride;
     const double *__restrict__ gpoint = B.point + (size_t)cur * B.tot_point * 3;
     double *__restrict__ gpointT = B.point + (size_t)(1 - cur) * B.tot_point * 3;
+    double *Hs = s_H[warp], *Ls = s_lm[warp];
+    int *lmoff = s_off[warp];
     double chi_acc = 0.0, scale_acc = 0.0;
 
-    for (int l = blockIdx.x * kWarpsL + warp; l < wd.n_point; l += gridDim.x * kWarpsL) {
-        const int e0 = B.lm_edge_off[l];
-        const int d = min(B.lm_edge_off[l + 1] - e0, kMaxDegL);
-        if (d <= 0) continue;
-        const uint8_t lf = B.lm_flags[l];
-        const bool lmfree = (lf & kInHessian) != 0;
-        const double px = gpoint[3 * (size_t)l], py = gpoint[3 * (size_t)l + 1], pz = gpoint[3 * (size_t)l + 2];
-        bool act = false, mono = false;
-        int p = 0;
+    // contiguous block of landmarks per warp
+    const int nwarp = gridDim.x * kWarpsL, gw = blockIdx.x * kWarpsL + warp;
+    const int per = (wd.n_point + nwarp - 1) / nwarp;
+    const int l_end = min((gw + 1) * per, wd.n_point);
+    for (int lt = min(gw * per, wd.n_point); lt < l_end;) {
+        // landmarks lt .. lt + ntl - 1: as many as fit 32 edges (at least one; kMaxDegL bounds a single landmark)
+        const int navail = min(kWtLm, l_end - lt);
+        const int off_abs = (lane <= navail) ? B.lm_edge_off[lt + lane] : 0x7fffffff;
+        const int e0 = __shfl_sync(0xffffffffu, off_abs, 0);
+        const int off_l = (lane <= navail) ? off_abs - e0 : 0x7fff;
+        int ntl = 1;
+#pragma unroll
+        for (int l = 2; l <= kWtLm; ++l) {
+            const int v = __shfl_sync(0xffffffffu, off_l, l);
+            ntl += (l <= navail && v <= 32) ? 1 : 0;
+        }
+        const int ne = min(__shfl_sync(0xffffffffu, off_l, ntl), 32);
+        const int lf_l = (lane < ntl) ? (int)B.lm_flags[lt + lane] : 0;
+        const double pt = (lane < 3 * ntl) ? gpoint[3 * (size_t)lt + lane] : 0.0;
+        int pw = 0;
         double ou = 0, ov = 0, our = 0;
+        if (lane < ne) {
+            const int e = e0 + lane;
+            pw = B.edge_pose[e];
+            ou = B.obs_u[e]; ov = B.obs_v[e]; our = B.obs_r[e];
+        }
+        if (lane <= ntl) lmoff[lane] = min(off_l, 32);
+        int tl = 0;
+#pragma unroll
+        for (int l = 1; l < kWtLm; ++l) {
+            const int v = __shfl_sync(0xffffffffu, off_l, l);
+            tl += (l < ntl && v <= lane) ? 1 : 0;
+        }
+        const int lf = __shfl_sync(0xffffffffu, lf_l, tl);
+        const double px = __shfl_sync(0xffffffffu, pt, 3 * tl), py = __shfl_sync(0xffffffffu, pt, 3 * tl + 1),
+                     pz = __shfl_sync(0xffffffffu, pt, 3 * tl + 2);
+        bool act = false, mono = false, lmfree = false;
+        int p = 0;
         double hl[12];
 #pragma unroll
         for (int q = 0; q < 12; ++q) hl[q] = 0.0;
-        if (lane < d) {
-            const int e = e0 + lane;
-            const int pw = B.edge_pose[e];
+        if (lane < ne) {
             p = pw & kPoseMask;
             mono = (pw & kMonoBit) != 0;
+            lmfree = (lf & kInHessian) != 0;
             act = !(pw & kCulledBit) && !((lf & kFixed) && (B.pose_flags[p] & kFixed));
-            if (act) {
-                ou = B.obs_u[e]; ov = B.obs_v[e]; our = B.obs_r[e];
-                if (lmfree) {
-                    double r[3], J[9], v[3], w;
-                    const int hi = B.pose_hidx[p];
-                    edge_linearize_jx(gpose + (size_t)p * kPoseStride, px, py, pz, ou, ov, our, mono, K,
-                                      hi >= 0 ? B.xp + 6 * (size_t)hi : nullptr, r, J, v, w);
-                    const double wo = w * K.inv_pv;
-                    hl[0] = wo * fma(J[0], J[0], fma(J[3], J[3], J[6] * J[6]));
-                    hl[1] = wo * fma(J[0], J[1], fma(J[3], J[4], J[6] * J[7]));
-                    hl[2] = wo * fma(J[0], J[2], fma(J[3], J[5], J[6] * J[8]));
-                    hl[3] = wo * fma(J[1], J[1], fma(J[4], J[4], J[7] * J[7]));
-                    hl[4] = wo * fma(J[1], J[2], fma(J[4], J[5], J[7] * J[8]));
-                    hl[5] = wo * fma(J[2], J[2], fma(J[5], J[5], J[8] * J[8]));
-                    hl[6] = -wo * fma(J[0], r[0], fma(J[3], r[1], J[6] * r[2]));
-                    hl[7] = -wo * fma(J[1], r[0], fma(J[4], r[1], J[7] * r[2]));
-                    hl[8] = -wo * fma(J[2], r[0], fma(J[5], r[1], J[8] * r[2]));
-                    const double v0 = wo * v[0], v1 = wo * v[1], v2 = wo * v[2];
-                    hl[9] = fma(J[0], v0, fma(J[3], v1, J[6] * v2));
-                    hl[10] = fma(J[1], v0, fma(J[4], v1, J[7] * v2));
-                    hl[11] = fma(J[2], v0, fma(J[5], v1, J[8] * v2));
+            if (act && lmfree) {
+                const int hi = B.pose_hidx[p];
+                upd_edge_terms(gpose + (size_t)p * kPoseStride, px, py, pz, ou, ov, our, mono, K, hi >= 0 ? B.xp + 6 * (size_t)hi : nullptr, hl);
+            }
+#pragma unroll
+            for (int q = 0; q < 12; ++q) Hs[lane * kHs + q] = hl[q];
+        }
+        __syncwarp();
+        for (int task = lane; task < ntl * 12; task += 32) {
+            const int l = task / 12, q = task - l * 12;
+            double sacc = 0.0;
+            for (int e = lmoff[l]; e < lmoff[l + 1]; ++e) sacc += Hs[e * kHs + q];
+            Ls[task] = sacc;
+        }
+        __syncwarp();
+        if (lane < ne) {
+            double np0 = px, np1 = py, np2 = pz;
+            if (lmfree) {
+                double xl[3];
+                const double sc = upd_point_step(Ls + tl * 12, lambda, xl);
+                np0 = px + xl[0]; np1 = py + xl[1]; np2 = pz + xl[2];
+                if (lane == lmoff[tl]) {      // first edge of the landmark: owner of the point
+                    const size_t gl = (size_t)lt + tl;
+                    gpointT[3 * gl] = np0; gpointT[3 * gl + 1] = np1; gpointT[3 * gl + 2] = np2;
+                    scale_acc += sc;
                 }
             }
-        }
-        double np0 = px, np1 = py, np2 = pz;
-        if (lmfree) {
-#pragma unroll
-            for (int q = 0; q < 12; ++q) hl[q] = warp_sum(hl[q]);
-            const double A[6] = {hl[0] + lambda, hl[1], hl[2], hl[3] + lambda, hl[4], hl[5] + lambda};
-            const double bl[3] = {hl[6], hl[7], hl[8]};
-            const double c[3] = {bl[0] - hl[9], bl[1] - hl[10], bl[2] - hl[11]};
-            double Di[6], xl[3];
-            inv_sym3(A, Di);
-            sym3_mul(Di, c, xl);
-            np0 = px + xl[0]; np1 = py + xl[1]; np2 = pz + xl[2];
-            if (lane == 0) {
-                gpointT[3 * (size_t)l] = np0; gpointT[3 * (size_t)l + 1] = np1; gpointT[3 * (size_t)l + 2] = np2;
-                scale_acc += xl[0] * (lambda * xl[0] + bl[0]) + xl[1] * (lambda * xl[1] + bl[1]) + xl[2] * (lambda * xl[2] + bl[2]);
+            if (act) {
+                double r0, r1, r2, rho, wgt;
+                edge_residual(gposeT + (size_t)p * kPoseStride, np0, np1, np2, ou, ov, our, mono, K, r0, r1, r2);
+                huber((r0 * r0 + r1 * r1 + r2 * r2) * K.inv_pv, K.delta, rho, wgt);
+                chi_acc += rho;
             }
         }
-        if (lane < d && act) {
-            double r0, r1, r2;
-            edge_residual(gposeT + (size_t)p * kPoseStride, np0, np1, np2, ou, ov, our, mono, K, r0, r1, r2);
-            double rho, wgt;
-            huber((r0 * r0 + r1 * r1 + r2 * r2) * K.inv_pv, K.delta, rho, wgt);
-            chi_acc += rho;
-        }
+        __syncwarp();
+        lt += ntl;
     }
     const double chi = block_sum(chi_acc, red);
     const double sc = block_sum(scale_acc, red);
