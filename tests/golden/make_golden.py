@@ -95,6 +95,38 @@ def pose_oplus(tq, d):
     return out
 
 
+def q_mul(a, b):   # Eigen (Hamilton) product, (x, y, z, w)
+    ax, ay, az, aw = a
+    bx, by, bz, bw = b
+    return np.array([aw * bx + ax * bw + ay * bz - az * by, aw * by + ay * bw + az * bx - ax * bz,
+                     aw * bz + az * bw + ax * by - ay * bx, aw * bw - ax * bx - ay * by - az * bz])
+
+
+def q_inv(q):
+    return np.array([-q[0], -q[1], -q[2], q[3]]) / float(np.sum(q * q))
+
+
+def link_error(tq1, tq2, m):
+    """EdgePoseConstraint::computeError (OptimizeTypeDefine.cpp:35-51), written from the source independently of the oracle."""
+    q12 = q_mul(tq1[3:7], q_inv(tq2[3:7]))
+    e_t = quat_R(q12) @ (-tq2[:3]) + tq1[:3] - m[:3]
+    e_r = 2.0 * q_mul(q_inv(m[3:7]), q12)[:3]
+    return np.concatenate([e_t, e_r])
+
+
+def link_jacobians_numeric(tq1, tq2, m, h=1e-4):
+    """d error / d (oplus increment) of both poses by 4th-order central differences through pose_oplus — NOT the reference's
+    closed forms: agreement of the full LM with the oracle then also checks that those closed forms are the derivatives."""
+    def col(which, a):
+        def f(s):
+            d = np.zeros(6); d[a] = s
+            return link_error(pose_oplus(tq1, d), tq2, m) if which == 0 else link_error(tq1, pose_oplus(tq2, d), m)
+        return (-f(2 * h) + 8 * f(h) - 8 * f(-h) + f(-2 * h)) / (12 * h)
+    Ji = np.stack([col(0, a) for a in range(6)], axis=1)
+    Jj = np.stack([col(1, a) for a in range(6)], axis=1)
+    return Ji, Jj
+
+
 def optimize_pass(w, pose, point, level, max_iter):
     """One g2o optimize(max_iter) with dense normal equations.  Returns the accepted state and statistics."""
     pfix, lfix = w["pose_fixed"].astype(bool), w["point_fixed"].astype(bool)
@@ -105,6 +137,12 @@ def optimize_pass(w, pose, point, level, max_iter):
     pact, lact = np.zeros(P, bool), np.zeros(L, bool)
     pact[ep[e_idx]] = True
     lact[el[e_idx]] = True
+    K = int(w.get("n_links", 0))
+    links = [(int(w["link_from"][k]), int(w["link_to"][k]), np.asarray(w["link_tq"][k], float)) for k in range(K)]
+    links = [(i, j, m) for (i, j, m) in links if not (pfix[i] and pfix[j])]          # e->allVerticesFixed()
+    for i, j, _ in links:
+        pact[i] = pact[j] = True
+    om_link = 1.0 / float(w.get("odometry_variance", 1.0))
     phi = np.full(P, -1)
     free_p = np.nonzero(pact & ~pfix)[0]
     phi[free_p] = np.arange(len(free_p))
@@ -119,7 +157,8 @@ def optimize_pass(w, pose, point, level, max_iter):
     def chi_of(ps, pt):
         err, _, _ = edge_terms(w, ps, pt, e_idx)
         rho, _ = robust(np.sum(err * err, axis=1) / pv, delta)
-        return float(np.sum(rho)), err
+        chi_links = sum(om_link * float(np.sum(link_error(ps[i], ps[j], m) ** 2)) for i, j, m in links)   # no robust kernel
+        return float(np.sum(rho)) + chi_links, err
 
     stats = dict(iterations=0, trials=0, stop=1, F=F, NL=NL, lam=0.0)
     chi_now, _ = chi_of(pose, point)
@@ -150,6 +189,19 @@ def optimize_pass(w, pose, point, level, max_iter):
             wo = wgt[k] / pv
             H[np.ix_(c, c)] += wo * J.T @ J
             b[c] -= wo * J.T @ err[k]
+        for i, j, m in links:
+            e = link_error(pose[i], pose[j], m)
+            Ji, Jj = link_jacobians_numeric(pose[i], pose[j], m)
+            cols, blocks = [], []
+            if phi[i] >= 0:
+                cols.append(np.arange(6) + 6 * phi[i]); blocks.append(Ji)
+            if phi[j] >= 0:
+                cols.append(np.arange(6) + 6 * phi[j]); blocks.append(Jj)
+            if cols:
+                J = np.concatenate(blocks, axis=1)
+                c = np.concatenate(cols)
+                H[np.ix_(c, c)] += om_link * J.T @ J
+                b[c] -= om_link * J.T @ e
         if w["trust_region"] == 1:
             try:
                 x = np.linalg.solve(H, b)
@@ -235,6 +287,7 @@ def dense_lm(w):
     return out
 
 
+LINK_KEYS = ("n_links", "link_from", "link_to", "link_tq", "odometry_variance")
 INPUT_KEYS = ("n_poses", "n_points", "n_edges", "pose_tq", "pose_id", "pose_fixed", "point_xyz", "point_id", "point_fixed",
               "edge_obs", "edge_pose", "edge_point", "edge_kind", "fx", "fy", "cx", "cy", "bf", "pixel_variance",
               "huber_delta", "iterations", "solver", "trust_region", "flags")
@@ -247,19 +300,23 @@ CASES = {
                            iterations=12, depth_range=(1.0, 6.0)),
     "gauss_newton_4x40": dict(n_poses=4, n_points=40, layout="all", seed=9004, trust_region=1, outlier_frac=0.0, point_noise=0.02),
     "no_fixed_pose_3x30": dict(n_poses=3, n_points=30, layout="all", seed=9005, root=None),
+    "odometry_links_5x50": dict(n_poses=5, n_points=50, layout="consecutive", views=3, seed=9006, links="chain", mono_frac=0.2),
 }
 
 
-def main():
+def main(only=None):
     for name, kw in CASES.items():
+        if only and name not in only:
+            continue
         w = synth.make_window(**kw)
         out = dense_lm(w)
         path = os.path.join(HERE, name + ".npz")
-        np.savez_compressed(path, **{"in_" + k: np.asarray(w[k]) for k in INPUT_KEYS},
+        keys = INPUT_KEYS + (LINK_KEYS if w.get("n_links", 0) else ())
+        np.savez_compressed(path, **{"in_" + k: np.asarray(w[k]) for k in keys},
                             **{"out_" + k: np.asarray(v) for k, v in out.items()})
         print(name, "chi2", out["chi2_pass1"], "->", out["chi2_final"], "iters", out["iterations_run"], "trials", out["trials_run"],
               "outliers", out["n_outliers"], "bytes", os.path.getsize(path))
 
 
 if __name__ == "__main__":
-    main()
+    main(sys.argv[1:])
