@@ -157,3 +157,61 @@ def test_global_ba_two_ranks_nccl():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "GLOBAL_BA_OK" in r.stdout
+
+
+# ---------------------------------------------------------------- BASELINE configs C4 / C5 at full size
+# The multi-threaded oracle finishes these in well under a minute, so the full sizes are checked against it directly
+# (decisions exact, state to rounding) on top of the size-independent properties.
+#
+# C4 note: the reference pairs an exponential-map Jacobian (OptimizeTypeDefine.h:157-176, rotation columns built from the
+# camera-frame point) with a decoupled update (CameraPose::update, OptimizeTypeDefine.cpp:7-14: t += dt, q = dq * q).  The
+# two differ by [t_cw]x, so far from the world origin (the 48 m loop of C4) the LM gain ratio turns negative, lambda climbs
+# and pass 1 hardly moves; most edges then sit above chi2 > delta and are culled.  That is the reference's behaviour, the
+# oracle restates it and the CUDA path reproduces it decision for decision — hence no "few outliers" assertion here.
+def _check_properties(w, g):
+    assert g["status"] == 0 and g["chi2_final"] < g["chi2_initial"]
+    assert np.isfinite(g["pose_tq"]).all() and np.isfinite(g["point_xyz"]).all()
+    assert np.allclose(np.linalg.norm(g["pose_tq"][:, 3:7], axis=1), 1.0, atol=1e-12)
+    fixed = w["pose_fixed"].astype(bool)
+    assert np.array_equal(g["pose_tq"][fixed], w["pose_tq"][fixed])          # the gauge pose never moves
+    assert g["n_outliers"] == int(g["edge_level"].sum())
+    assert g["n_outliers"] >= 0.04 * w["n_edges"]                            # the planted +-20 px outliers are among the culled
+
+
+def _check_against_oracle(w, g):
+    o = O.solve(w, threads=O.threads(), omp=True)
+    assert g["status"] == o["status"] == 0
+    for k in (0, 1):
+        # once lambda has run away (C4 note above) the steps are below 1e-12 of the state and the sign of the gain ratio is
+        # rounding noise: whether such a pass ends on its 9th or 10th null trial is not a decision worth comparing, the
+        # accepted state below is
+        if max(g["lambda_final"][k], o["lambda_final"][k]) > 1e12:
+            continue
+        assert g["iterations_run"][k] == o["iterations_run"][k] and g["trials_run"][k] == o["trials_run"][k]
+        assert g["stop_reason"][k] == o["stop_reason"][k]
+    assert g["n_outliers"] == o["n_outliers"] and np.array_equal(g["edge_level"], o["edge_level"])
+    for k in ("chi2_initial", "chi2_pass1", "chi2_final"):
+        assert abs(g[k] - o[k]) <= 1e-6 * abs(o[k]), k
+    np.testing.assert_allclose(g["pose_tq"], o["pose_tq"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(g["point_xyz"], o["point_xyz"], rtol=1e-6, atol=1e-6)
+
+
+def test_c4_full_size_oracle_parity_and_partition_invariance(ba):
+    w = synth.config_c4()                      # 2 000 key frames on a loop / 500 000 landmarks / 5 M edges
+    g = ba.solve(w)
+    _check_properties(w, g)
+    _check_against_oracle(w, g)
+    # the same problem handed over as a 1-rank landmark partition takes the same code path: same decisions, same answer
+    part = partition.partition_window(w, 1, 0)
+    p = partition.merge_results(w, [part], [ba.solve(part)])
+    assert p["iterations_run"] == g["iterations_run"] and p["trials_run"] == g["trials_run"]
+    assert np.array_equal(p["edge_level"], g["edge_level"])
+    assert np.allclose(p["pose_tq"], g["pose_tq"], rtol=1e-7, atol=1e-9)     # (red.global.add: summation order is not fixed)
+    assert abs(p["chi2_final"] - g["chi2_final"]) <= 1e-7 * g["chi2_final"]
+
+
+def test_c5_full_size_oracle_parity(ba):
+    w = synth.config_c5()                      # 200 key frames / 200 000 landmarks / 2 M edges, dense reduced system
+    g = ba.solve(w)
+    _check_properties(w, g)
+    _check_against_oracle(w, g)
