@@ -248,6 +248,14 @@ int visfs_ba_comm_unique_id(void *id_out /* VISFS_BA_COMM_ID_BYTES */);
 int visfs_ba_comm_init(visfs_ba_handle *h, int32_t n_ranks, int32_t rank, const void *id);
 int visfs_ba_comm_destroy(visfs_ba_handle *h);
 
+/* Page-locked host memory.  Arrays of a visfs_ba_problem / visfs_ba_result that live in page-locked memory (allocated
+ * here, or by cudaHostAlloc / cudaHostRegister / torch pin_memory) are moved by DMA straight between the caller's arrays
+ * and the device; pageable arrays go through the library's own page-locked staging buffer (one more host copy).  Either
+ * way the caller's arrays must not change while a call that reads them is running.  visfs_ba_host_alloc returns NULL on
+ * failure; the memory is portable across the devices of the process. */
+void *visfs_ba_host_alloc(size_t bytes);
+void  visfs_ba_host_free(void *p);
+
 /* FP64 FMA peak probe used by bench.py for the second roofline (returns TFLOP/s) */
 int visfs_ba_probe_fp64(visfs_ba_handle *h, double *tflops_out);
 

@@ -272,6 +272,33 @@ def test_pipelined_batch_groups_match_oracle(ba):
     assert t["h2d_bytes"] > 0 and t["d2h_bytes"] > 0
 
 
+def test_page_locked_caller_arrays_take_the_direct_dma_path(ba):
+    # arrays in visfs_ba_host_alloc memory are DMA'd without staging: bit-identical results to the pageable (staged) route,
+    # for one window, a small batch and a pipelined batch; window sizes straddle the 32 KB direct-copy threshold
+    ws = [synth.make_window(5 + k % 3, 120 + 60 * k, layout="all" if k % 2 == 0 else "consecutive", views=4, seed=700 + k,
+                            mono_frac=0.2 if k % 3 == 0 else 0.0, fixed_point_frac=0.1) for k in range(40)]
+    for sub in (ws[:1], ws[5:12], ws):
+        staged = ba.solve_batch(sub)
+        packed = ba.prepare_batch(sub, pinned=True)
+        ba.solve_packed(packed)
+        direct = ba.packed_results(packed)
+        for a, b in zip(staged, direct):
+            assert a["status"] == b["status"] and a["trials_run"] == b["trials_run"] and a["chi2_final"] == b["chi2_final"]
+            assert np.array_equal(a["pose_tq"], b["pose_tq"]) and np.array_equal(a["point_xyz"], b["point_xyz"])
+            assert np.array_equal(a["edge_level"], b["edge_level"])
+    check_solution(direct[39], O.solve(ws[39]), "page-locked window 39")
+    # the resident API: upload returns only after the caller's arrays have been read
+    packed = ba.prepare_batch(ws[5:12], pinned=True)
+    n, probs, res, outs, keep = packed
+    ba._check(ba.lib.visfs_ba_upload(ba.h, n, probs))
+    for k in range(n):                               # scribbling over the inputs now must not matter
+        np.ctypeslib.as_array(probs[k].edge_obs, shape=(probs[k].n_edges * 3,))[:] = 0.0
+    ba.run_resident()
+    ba._check(ba.lib.visfs_ba_download(ba.h, n, res))
+    for a, b in zip(ba.solve_batch(ws[5:12]), ba.packed_results(packed)):
+        assert a["chi2_final"] == b["chi2_final"] and np.array_equal(a["pose_tq"], b["pose_tq"])
+
+
 # ---------------------------------------------------------------- odometry links (EdgePoseConstraint)
 def test_links_structure_pattern(ba):
     w = synth.make_window(9, 300, layout="random", views=2, seed=401, links="chain")

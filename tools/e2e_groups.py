@@ -1,4 +1,4 @@
-"""End-to-end time of visfs_ba_solve_batch (host buffers) for different pipeline group counts: VISFS_BA_GROUPS is read per call."""
+"""End-to-end time of visfs_ba_solve_batch (host buffers) for different pipeline group counts and size ramps: VISFS_BA_GROUPS / VISFS_BA_RAMP are read per call."""
 import os
 import sys
 import time
@@ -10,12 +10,13 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 ws = synth.config_c3_windows(n)
 ba = capi.BundleAdjuster(0)
 packed = ba.prepare_batch(ws)
-for g in (1, 2, 4, 8, 12, 16, 24):
+for ramp, g in ((1.0, 16), (1.0, 32), (1.1, 16), (1.22, 8), (1.22, 16), (1.22, 24), (1.3, 16)):
+    os.environ["VISFS_BA_RAMP"] = str(ramp)
     os.environ["VISFS_BA_GROUPS"] = str(g)
     for _ in range(2):
         ba.solve_packed(packed)
     t0 = time.perf_counter()
-    for _ in range(3):
+    for _ in range(4):
         ba.solve_packed(packed)
-    dt = (time.perf_counter() - t0) / 3
-    print(f"groups {g:2d}: {1e3 * dt:7.2f} ms per batch of {n} windows", flush=True)
+    dt = (time.perf_counter() - t0) / 4
+    print(f"ramp {ramp:4.2f} groups {g:2d}: {1e3 * dt:7.2f} ms per batch of {n} windows", flush=True)

@@ -76,7 +76,8 @@ class Timing(C.Structure):
 EXPORTS = ["visfs_ba_abi_version", "visfs_ba_create", "visfs_ba_destroy", "visfs_ba_last_error", "visfs_ba_solve",
            "visfs_ba_solve_batch", "visfs_ba_linearize", "visfs_ba_structure_build", "visfs_ba_upload",
            "visfs_ba_run_resident", "visfs_ba_download", "visfs_ba_get_timing", "visfs_ba_comm_unique_id",
-           "visfs_ba_comm_init", "visfs_ba_comm_destroy", "visfs_ba_probe_fp64", "visfs_ba_debug_trial"]
+           "visfs_ba_comm_init", "visfs_ba_comm_destroy", "visfs_ba_probe_fp64", "visfs_ba_debug_trial",
+           "visfs_ba_host_alloc", "visfs_ba_host_free"]
 
 
 def _ptr(a, typ):
@@ -206,7 +207,49 @@ def load_library(path=LIB_PATH):
     lib.visfs_ba_probe_fp64.argtypes = [C.c_void_p, _dp]
     lib.visfs_ba_debug_trial.argtypes = [C.c_void_p, C.POINTER(Problem), C.c_double, _dp, _dp, _dp, _dp,
                                          C.POINTER(C.c_int32), _dp, _dp, _dp]
+    lib.visfs_ba_host_alloc.argtypes = [C.c_size_t]
+    lib.visfs_ba_host_alloc.restype = C.c_void_p
+    lib.visfs_ba_host_free.argtypes = [C.c_void_p]
+    lib.visfs_ba_host_free.restype = None
     return lib
+
+
+class PinnedArena:
+    """Page-locked host memory from visfs_ba_host_alloc, handed out as numpy arrays (64-byte aligned).  Arrays placed
+    here are moved by DMA straight between the caller's memory and the device (include/visfs_ba.h)."""
+
+    def __init__(self, lib, nbytes):
+        self.lib, self.nbytes, self.used = lib, int(nbytes), 0
+        self.ptr = lib.visfs_ba_host_alloc(self.nbytes)
+        if not self.ptr:
+            raise BAError(f"visfs_ba_host_alloc({nbytes}) failed")
+        self.buf = np.ctypeslib.as_array((C.c_uint8 * self.nbytes).from_address(self.ptr))
+
+    @staticmethod
+    def size_of(a):
+        return (int(a.nbytes) + 63) & ~63
+
+    def place(self, a):
+        """Copy `a` into the arena; returns the page-locked array."""
+        n = int(a.nbytes)
+        if self.used + n > self.nbytes:
+            raise BAError("pinned arena exhausted")
+        out = self.buf[self.used:self.used + n].view(a.dtype).reshape(a.shape)
+        out[...] = a
+        self.used += (n + 63) & ~63
+        return out
+
+    def close(self):
+        if getattr(self, "ptr", None):
+            self.buf = None
+            self.lib.visfs_ba_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class BundleAdjuster:
@@ -254,11 +297,24 @@ class BundleAdjuster:
                     allow=(OK, ERR_NUMERIC_PASS1, ERR_NUMERIC_PASS2))
         return result_to_dict(r, out)
 
-    def _pack(self, windows):
+    def _pack(self, windows, pinned=False):
         keep = []
         n = len(windows)
-        probs = (Problem * n)(*[window_to_problem(w, keep) for w in windows])
         outs = [ResultArrays(w) for w in windows]
+        if pinned:
+            # every input and output array moves into one page-locked arena (freed with the packed batch)
+            keys = ("pose_tq", "pose_fixed", "point_xyz", "point_fixed", "edge_obs", "edge_pose", "edge_point", "edge_kind")
+            cast = dict(pose_tq=np.float64, pose_fixed=np.uint8, point_xyz=np.float64, point_fixed=np.uint8,
+                        edge_obs=np.float64, edge_pose=np.int32, edge_point=np.int32, edge_kind=np.uint8)
+            arrs = [{k: np.ascontiguousarray(w[k], dtype=cast[k]) for k in keys if w.get(k) is not None} for w in windows]
+            total = sum(PinnedArena.size_of(a) for d in arrs for a in d.values())
+            total += sum(PinnedArena.size_of(a) for o in outs for a in (o.pose_tq, o.point_xyz, o.edge_level))
+            arena = PinnedArena(self.lib, total + 64)
+            windows = [dict(w, **{k: arena.place(a) for k, a in d.items()}) for w, d in zip(windows, arrs)]
+            for o in outs:
+                o.pose_tq, o.point_xyz, o.edge_level = arena.place(o.pose_tq), arena.place(o.point_xyz), arena.place(o.edge_level)
+            keep.append(arena)
+        probs = (Problem * n)(*[window_to_problem(w, keep) for w in windows])
         res = (Result * n)()
         for r, o in zip(res, outs):
             o.bind(r)
@@ -269,9 +325,14 @@ class BundleAdjuster:
         self._check(self.lib.visfs_ba_solve_batch(self.h, n, probs, res))
         return [result_to_dict(r, o) for r, o in zip(res, outs)]
 
-    def prepare_batch(self, windows):
-        """Marshal once; returns an opaque packed batch for repeated solve_packed() calls."""
-        return self._pack(windows)
+    def prepare_batch(self, windows, pinned=False):
+        """Marshal once; returns an opaque packed batch for repeated solve_packed() calls.  pinned=True places every
+        array in page-locked memory (visfs_ba_host_alloc): no staging copy on either side of the call."""
+        return self._pack(windows, pinned)
+
+    def packed_results(self, packed):
+        n, probs, res, outs, keep = packed
+        return [result_to_dict(r, o) for r, o in zip(res, outs)]
 
     def solve_packed(self, packed):
         n, probs, res, outs, keep = packed

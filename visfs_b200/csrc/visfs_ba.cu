@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <chrono>
 #include <thread>
 #include <vector>
 
@@ -104,6 +105,7 @@ struct visfs_ba_handle {
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
     visfs_ba_timing timing{};
     int64_t launches = 0, h2d_bytes = 0, d2h_bytes = 0;
+    int direct_h2d = 0;   // pieces of the last upload DMA'd straight from the caller's page-locked arrays
 
     Batch batch{};
 
@@ -162,6 +164,13 @@ void ev_end(visfs_ba_handle *h, int b) {
     if (b >= 0) cudaEventRecord(h->ev_pool[b], h->stream);
 }
 
+// page-locked host memory (cudaHostAlloc, cudaHostRegister, visfs_ba_host_alloc): DMA source / target without staging
+bool host_is_pinned(const void *p) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
 int validate(visfs_ba_handle *h, const visfs_ba_problem &p, int idx, bool *sorted, int *max_degree) {
     char buf[160];
     auto bad = [&](const char *m) {
@@ -182,17 +191,22 @@ int validate(visfs_ba_handle *h, const visfs_ba_problem &p, int idx, bool *sorte
         for (int i = 1; i < p.n_poses; ++i) if (p.pose_id[i] <= p.pose_id[i - 1]) return bad("pose_id not strictly ascending");
     if (p.point_id)
         for (int i = 1; i < p.n_points; ++i) if (p.point_id[i] <= p.point_id[i - 1]) return bad("point_id not strictly ascending");
-    bool srt = true;
-    int run = 0, maxrun = 0;
-    for (int e = 0; e < p.n_edges; ++e) {
-        const int a = p.edge_pose[e], b = p.edge_point[e];
-        if (a < 0 || a >= p.n_poses || b < 0 || b >= p.n_points) return bad("edge index out of range");
-        if (e > 0) {
-            const int pb = p.edge_point[e - 1];
-            if (b < pb || (b == pb && a <= p.edge_pose[e - 1])) srt = false;
-            run = (b == pb) ? run + 1 : 1;
-        } else run = 1;
-        maxrun = std::max(maxrun, run);
+    // three branch-light sweeps (the first two vectorise): bounds, order, longest run of one landmark
+    const int *ep = p.edge_pose, *el = p.edge_point;
+    const unsigned nP = (unsigned)p.n_poses, nL = (unsigned)p.n_points;
+    unsigned oob = 0;
+    for (int e = 0; e < p.n_edges; ++e) oob |= (unsigned)((unsigned)ep[e] >= nP) | (unsigned)((unsigned)el[e] >= nL);
+    if (oob) return bad("edge index out of range");
+    unsigned unsorted = 0;
+    for (int e = 1; e < p.n_edges; ++e)
+        unsorted |= (unsigned)(el[e] < el[e - 1]) | ((unsigned)(el[e] == el[e - 1]) & (unsigned)(ep[e] <= ep[e - 1]));
+    const bool srt = unsorted == 0;
+    int maxrun = p.n_edges > 0 ? 1 : 0;
+    if (srt) {
+        int start = 0;
+        for (int e = 1; e < p.n_edges; ++e)
+            if (el[e] != el[e - 1]) { maxrun = std::max(maxrun, e - start); start = e; }
+        maxrun = std::max(maxrun, p.n_edges - start);
     }
     *sorted = srt;
     *max_degree = srt ? maxrun : -1;
@@ -409,28 +423,54 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs) {
         h->in.win = reinterpret_cast<WinDesc *>(db + o_win); h->in.chunks = reinterpret_cast<Chunk *>(db + o_chunks);
     }
     char *sg = h->h_stage.as<char>();
-    for (int w = 0; w < n; ++w) {
-        const visfs_ba_problem &p = probs[w];
-        const WinDesc &d = h->win[w];
-        if (p.n_poses) {
-            memcpy(sg + o_pose + sizeof(double) * 7 * d.pose_off, p.pose_tq, sizeof(double) * 7 * p.n_poses);
-            if (p.pose_fixed) memcpy(sg + o_pfix + d.pose_off, p.pose_fixed, p.n_poses); else memset(sg + o_pfix + d.pose_off, 0, p.n_poses);
-        }
-        if (p.n_points) {
-            memcpy(sg + o_point + sizeof(double) * 3 * d.point_off, p.point_xyz, sizeof(double) * 3 * p.n_points);
-            if (p.point_fixed) memcpy(sg + o_lfix + d.point_off, p.point_fixed, p.n_points); else memset(sg + o_lfix + d.point_off, 0, p.n_points);
-        }
-        if (p.n_edges) {
-            memcpy(sg + o_obs + sizeof(double) * 3 * d.edge_off, p.edge_obs, sizeof(double) * 3 * p.n_edges);
-            memcpy(sg + o_epose + sizeof(int) * d.edge_off, p.edge_pose, sizeof(int) * p.n_edges);
-            memcpy(sg + o_epoint + sizeof(int) * d.edge_off, p.edge_point, sizeof(int) * p.n_edges);
-            if (p.edge_kind) memcpy(sg + o_ekind + d.edge_off, p.edge_kind, p.n_edges); else memset(sg + o_ekind + d.edge_off, 0, p.n_edges);
-        }
-    }
     cudaStream_t s = h->stream;
-    memcpy(sg + o_win, h->win.data(), sizeof(WinDesc) * n);
-    if (h->n_chunks) memcpy(sg + o_chunks, h->chunks.data(), sizeof(Chunk) * h->n_chunks);
-    CK(cudaMemcpyAsync(h->d_in.p, sg, o_end, cudaMemcpyHostToDevice, s));
+    {
+        // Every piece (one array of one window) either is DMA'd from the caller's memory (page-locked source, worth its
+        // own copy) or is packed into the staging buffer; adjacent staged pieces leave as one copy.
+        char *db = h->d_in.as<char>();
+        // (the groups of a pipelined batch keep the staging route: one large DMA transfer per group moves at 45 GB/s, the
+        //  many array-sized ones of the direct route at 20 GB/s, and their packing runs on all host cores anyway)
+        const bool allow_direct = !getenv("VISFS_BA_NO_DIRECT") && (!h->is_sub || getenv("VISFS_BA_DIRECT_GROUPS"));
+        constexpr size_t kDirectMin = 32 * 1024;
+        size_t run_lo = 0, run_hi = 0;
+        int direct = 0;
+        cudaError_t cerr = cudaSuccess;
+        auto flush = [&]() {
+            if (run_hi > run_lo && cerr == cudaSuccess) cerr = cudaMemcpyAsync(db + run_lo, sg + run_lo, run_hi - run_lo, cudaMemcpyHostToDevice, s);
+            run_lo = run_hi = 0;
+        };
+        auto stage_at = [&](size_t off, size_t bytes) -> char * {   // reserve [off, off + bytes) of the staging buffer in the current run
+            if (off != run_hi || run_hi == run_lo) { flush(); run_lo = off; }
+            run_hi = off + bytes;
+            return sg + off;
+        };
+        auto put = [&](size_t off, const void *src, size_t bytes) {
+            if (!bytes) return;
+            if (allow_direct && bytes >= kDirectMin && host_is_pinned(src)) {
+                if (cerr == cudaSuccess) cerr = cudaMemcpyAsync(db + off, src, bytes, cudaMemcpyHostToDevice, s);
+                ++direct;
+            } else {
+                memcpy(stage_at(off, bytes), src, bytes);
+            }
+        };
+        auto put_flags = [&](size_t off, const uint8_t *src, size_t bytes) {   // optional byte arrays: absent = zeros
+            if (!bytes) return;
+            if (src) memcpy(stage_at(off, bytes), src, bytes); else memset(stage_at(off, bytes), 0, bytes);
+        };
+        for (int w = 0; w < n; ++w) put(o_pose + sizeof(double) * 7 * h->win[w].pose_off, probs[w].pose_tq, sizeof(double) * 7 * probs[w].n_poses);
+        for (int w = 0; w < n; ++w) put(o_point + sizeof(double) * 3 * h->win[w].point_off, probs[w].point_xyz, sizeof(double) * 3 * probs[w].n_points);
+        for (int w = 0; w < n; ++w) put(o_obs + sizeof(double) * 3 * h->win[w].edge_off, probs[w].edge_obs, sizeof(double) * 3 * probs[w].n_edges);
+        for (int w = 0; w < n; ++w) put(o_epose + sizeof(int) * h->win[w].edge_off, probs[w].edge_pose, sizeof(int) * probs[w].n_edges);
+        for (int w = 0; w < n; ++w) put(o_epoint + sizeof(int) * h->win[w].edge_off, probs[w].edge_point, sizeof(int) * probs[w].n_edges);
+        for (int w = 0; w < n; ++w) put_flags(o_pfix + h->win[w].pose_off, probs[w].pose_fixed, probs[w].n_poses);
+        for (int w = 0; w < n; ++w) put_flags(o_lfix + h->win[w].point_off, probs[w].point_fixed, probs[w].n_points);
+        for (int w = 0; w < n; ++w) put_flags(o_ekind + h->win[w].edge_off, probs[w].edge_kind, probs[w].n_edges);
+        memcpy(stage_at(o_win, sizeof(WinDesc) * n), h->win.data(), sizeof(WinDesc) * n);
+        if (h->n_chunks) memcpy(stage_at(o_chunks, sizeof(Chunk) * h->n_chunks), h->chunks.data(), sizeof(Chunk) * h->n_chunks);
+        flush();
+        CK(cerr);
+        h->direct_h2d = direct;
+    }
 
     h->h2d_bytes = (int64_t)o_end + (int64_t)tk * (3 * (int64_t)sizeof(int) + 7 * (int64_t)sizeof(double));
     // device-side preparation: (optional) stable sort by (window, point, pose), SoA split, CSR offsets
@@ -1001,7 +1041,26 @@ int download(visfs_ba_handle *h, int n, visfs_ba_result *res) {
     CK(cudaGetLastError());
     CK(h->h_out.reserve(o_end + 8));
     char *ho = h->h_out.as<char>();
-    if (o_end) CK(cudaMemcpyAsync(ho, dout, o_end, cudaMemcpyDeviceToHost, s));
+    // results go straight into page-locked caller arrays when every window offers them for its landmarks and edge levels
+    bool direct = !getenv("VISFS_BA_NO_DIRECT") && n > 0 && (!h->is_sub || getenv("VISFS_BA_DIRECT_GROUPS"));
+    for (int w = 0; w < n && direct; ++w) {
+        const WinDesc &d = h->win[w];
+        const visfs_ba_result &r = res[w];
+        if (d.n_point && r.point_xyz && !host_is_pinned(r.point_xyz)) direct = false;
+        if (d.n_edge && r.edge_level && !host_is_pinned(r.edge_level)) direct = false;
+    }
+    if (direct) {
+        if (o_point) CK(cudaMemcpyAsync(ho, dout, o_point, cudaMemcpyDeviceToHost, s));   // poses: small, staged
+        for (int w = 0; w < n; ++w) {
+            const WinDesc &d = h->win[w];
+            const visfs_ba_result &r = res[w];
+            if (r.point_xyz && d.n_point)
+                CK(cudaMemcpyAsync(r.point_xyz, dout + o_point + sizeof(double) * 3 * d.point_off, sizeof(double) * 3 * d.n_point, cudaMemcpyDeviceToHost, s));
+            if (r.edge_level && d.n_edge) CK(cudaMemcpyAsync(r.edge_level, dout + o_level + d.edge_off, d.n_edge, cudaMemcpyDeviceToHost, s));
+        }
+    } else if (o_end) {
+        CK(cudaMemcpyAsync(ho, dout, o_end, cudaMemcpyDeviceToHost, s));
+    }
     CK(cudaStreamSynchronize(s));
     h->d2h_bytes += (int64_t)o_end;
     h->timing.d2h_bytes = h->d2h_bytes;
@@ -1011,8 +1070,10 @@ int download(visfs_ba_handle *h, int n, visfs_ba_result *res) {
         const LMState &st = h->st_host[w];
         visfs_ba_result &r = res[w];
         if (r.pose_tq && d.n_pose) memcpy(r.pose_tq, ho + o_pose + sizeof(double) * 7 * d.pose_off, sizeof(double) * 7 * d.n_pose);
-        if (r.point_xyz && d.n_point) memcpy(r.point_xyz, ho + o_point + sizeof(double) * 3 * d.point_off, sizeof(double) * 3 * d.n_point);
-        if (r.edge_level && d.n_edge) memcpy(r.edge_level, ho + o_level + d.edge_off, d.n_edge);
+        if (!direct) {
+            if (r.point_xyz && d.n_point) memcpy(r.point_xyz, ho + o_point + sizeof(double) * 3 * d.point_off, sizeof(double) * 3 * d.n_point);
+            if (r.edge_level && d.n_edge) memcpy(r.edge_level, ho + o_level + d.edge_off, d.n_edge);
+        }
         r.status = st.status; r.n_outliers = st.n_outliers;
         for (int k = 0; k < 2; ++k) {
             r.iterations_run[k] = st.iterations_run[k]; r.trials_run[k] = st.trials_run[k]; r.stop_reason[k] = st.stop[k];
@@ -1139,7 +1200,11 @@ void visfs_ba_destroy(visfs_ba_handle *h) {
 
 int visfs_ba_upload(visfs_ba_handle *h, int32_t n, const visfs_ba_problem *problems) {
     if (!h) return VISFS_BA_ERR_INVALID;
-    return upload(h, n, problems);
+    const int st = upload(h, n, problems);
+    // copies that read the caller's page-locked arrays directly must have finished when this returns
+    if (st == VISFS_BA_OK && h->direct_h2d > 0 && cudaStreamSynchronize(h->stream) != cudaSuccess)
+        return h->fail(VISFS_BA_ERR_CUDA, "upload: copy from page-locked caller memory failed");
+    return st;
 }
 
 int visfs_ba_run_resident(visfs_ba_handle *h) {
@@ -1199,15 +1264,44 @@ int visfs_ba_solve_batch(visfs_ba_handle *h, int32_t n, const visfs_ba_problem *
     h->resident = false; h->has_run = false;
     std::vector<int> status(groups, VISFS_BA_OK);
     std::vector<std::thread> workers;
-    const int base = n / groups, rem = n % groups;
+    const auto t_call = std::chrono::steady_clock::now();
+    const bool trace = getenv("VISFS_BA_TRACE") != nullptr;
+    // Group sizes grow geometrically (x 1.22 per group).  Every group's host thread starts packing at once, so a small first
+    // group puts the GPU to work early; more important, groups of unequal size do not run in lock-step: the latency-bound
+    // phases of one (k_solve, control) overlap the throughput-bound ones of another (k_build_ws).  Measured on C3 x 512 with
+    // 16 groups: 33.0 ms uniform -> 27.8 ms; with the packing removed entirely uniform groups still take 30.7 ms.
+    std::vector<int> sizes(groups, 0);
+    {
+        double ramp = 1.22;
+        if (const char *e = getenv("VISFS_BA_RAMP")) ramp = std::max(1.0, atof(e));
+        std::vector<double> wgt(groups);
+        double tot = 0.0;
+        int flat = groups;
+        if (const char *e = getenv("VISFS_BA_RAMP_FLAT")) flat = std::max(1, atoi(e));
+        for (int g = 0; g < groups; ++g) { wgt[g] = std::pow(ramp, std::min(g, flat)); tot += wgt[g]; }
+        int given = 0;
+        for (int g = 0; g < groups; ++g) { sizes[g] = std::max(1, (int)std::floor(n * wgt[g] / tot)); given += sizes[g]; }
+        for (int g = groups - 1; given != n; g = (g + groups - 1) % groups) {   // hand the rounding remainder to the large end
+            if (given < n) { ++sizes[g]; ++given; }
+            else if (sizes[g] > 1) { --sizes[g]; --given; }
+        }
+    }
     int off = 0;
     for (int g = 0; g < groups; ++g) {
-        const int cnt = base + (g < rem ? 1 : 0);
+        const int cnt = sizes[g];
         visfs_ba_handle *s = h->subs[g];
-        workers.emplace_back([s, cnt, off, problems, results, &status, g]() {
+        workers.emplace_back([s, cnt, off, problems, results, &status, g, t_call, trace]() {
+            auto ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count(); };
+            const double t0 = ms();
             int st = upload(s, cnt, problems + off);
+            const double t1 = ms();
+            if (trace) { cudaStreamSynchronize(s->stream); }
+            const double t1b = ms();
             if (!st) st = run_resident(s);
+            const double t2 = ms();
             if (!st) st = download(s, cnt, results + off);
+            const double t3 = ms();
+            if (trace) fprintf(stderr, "[visfs_ba] group %2d: start %.2f upload-issued %.2f h2d-done %.2f run-done %.2f download-done %.2f ms\n", g, t0, t1, t1b, t2, t3);
             status[g] = st;
         });
         off += cnt;
@@ -1501,6 +1595,16 @@ int visfs_ba_comm_destroy(visfs_ba_handle *h) {
     }
     h->comm_ranks = 1; h->comm_rank = 0;
     return VISFS_BA_OK;
+}
+
+void *visfs_ba_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+void visfs_ba_host_free(void *p) {
+    if (p) cudaFreeHost(p);
 }
 
 int visfs_ba_probe_fp64(visfs_ba_handle *h, double *tflops_out) {
