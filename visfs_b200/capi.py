@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(ROOT, "visfs_b200", "csrc", "libvisfs_ba.so")
+LIB_PATH = os.environ.get("VISFS_BA_LIB") or os.path.join(ROOT, "visfs_b200", "csrc", "libvisfs_ba.so")   # (override: A/B runs of tools/)
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NUMERIC_PASS1, ERR_NUMERIC_PASS2, ERR_UNSUPPORTED = range(6)
 EDGE_STEREO, EDGE_MONO = 0, 1

@@ -1,14 +1,15 @@
 // ba_build_ws.cuh — warp-specialised build kernel (linearise + Hessian blocks + Schur partials), F <= 20.
 //
 // Same arithmetic as k_build<MODE_BUILD> (ba_kernels.cuh), restructured for the SM:
-//   * 5 PRODUCER warps (160 threads, one edge each): stage A (residual, Jacobians, Huber, per-edge H_ll / b_l
-//     terms), per-landmark sums in edge order by (landmark, entry) owner threads, stage B (damped 3x3
-//     inverse, W = H_pl block, Yn = -W Dinv, H_pp_e, b_p_e, g) into one of two shared-memory stages.  The
-//     edge records and points of the NEXT tile are prefetched into registers while the current tile is
-//     computed; tile bounds come from a table built once at upload (k_fill_tiles).
-//   * 7 CONSUMER warps (224 threads): stage C.  Every block (i <= j) of the reduced camera system has a fixed
-//     owner thread that keeps its 36 entries in registers for the whole chunk and adds Yn_i W_j^T with
-//     three chained DFMAs per entry; per-pose sums (H_pp, g, b_p) have fixed owners as well.
+//   * 6 PRODUCER warps (192 threads, one edge each): stage A (residual, Jacobians, Huber, per-edge H_ll / b_l
+//     terms, W = H_pl block, H_pp_e, b_p_e) and the per-landmark sums in edge order by (landmark, entry) owner
+//     threads, into one of two shared-memory stages.  The edge records and points of the NEXT tile are
+//     prefetched into registers while the current tile is computed; tile bounds come from a table built once
+//     at upload (k_fill_tiles).
+//   * 6 CONSUMER warps (192 threads): stage B, one edge per thread (damped 3x3 inverse, Yn = -W Dinv, g), then
+//     stage C: every block (i <= j) of the reduced camera system has a fixed owner thread that keeps its 36
+//     entries in registers for the whole chunk and adds Yn_i W_j^T with three chained DFMAs per entry;
+//     per-pose sums (H_pp, g, b_p) have fixed owners as well.
 //   The two roles overlap on different tiles through full / empty named barriers (bar.arrive / bar.sync),
 //   so neither the 72 accumulator registers nor the linearisation temporaries are ever live in the same
 //   thread (v1 spilled 900 B / thread to L2), and the FP64 pipe is fed by both roles at once.
@@ -43,6 +44,7 @@ struct Stage {
     double H[kTileEdges * kHStride];           // H_pp_e (21, upper) | g (6) | b_p (6); stage A scratch before that
     double lm[kTileLm * 12];                   // per landmark: H_ll (6) b_l (3), summed in edge order
     short slot[kTileLm * kMaxSmallPoses];
+    short emeta[kTileEdges];                   // per edge: -1 = contributes nothing, else tile-local landmark | landmark-in-Hessian << 6
     int ntl, pad0, pad1, pad2;
 };
 
@@ -81,6 +83,44 @@ __device__ __forceinline__ void load_edge_l2(const Batch &B, const WinDesc &wd, 
         r.px = gpoint[3 * (size_t)r.gl]; r.py = gpoint[3 * (size_t)r.gl + 1]; r.pz = gpoint[3 * (size_t)r.gl + 2];
     }
 }
+
+// stage B of one edge: damped inverse of its landmark block (redundantly per edge), Yn = -W Dinv over the scratch stage A
+// left in the Yn row, g = b_p_e - W Dinv b_l.  Needs the landmark sums of the tile (S.lm).
+__device__ __forceinline__ void stage_b_edge(Stage &S, int e, double lambda) {
+    const int meta = S.emeta[e];
+    if (meta < 0) return;
+    double *ys = S.Yn + e * 18;
+    double *hs = S.H + e * kHStride;
+    if (meta & 64) {
+        const double *ls = S.lm + (meta & 63) * 12;
+        double A[6] = {ls[0] + lambda, ls[1], ls[2], ls[3] + lambda, ls[4], ls[5] + lambda};
+        const double bl[3] = {ls[6], ls[7], ls[8]};
+        double Di[6], db[3];
+        inv_sym3(A, Di);
+        sym3_mul(Di, bl, db);
+        const double *wsrc = S.W + e * 18;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            const double w0 = wsrc[a * 3], w1 = wsrc[a * 3 + 1], w2 = wsrc[a * 3 + 2];
+            ys[a * 3 + 0] = -fma(w0, Di[0], fma(w1, Di[1], w2 * Di[2]));
+            ys[a * 3 + 1] = -fma(w0, Di[1], fma(w1, Di[3], w2 * Di[4]));
+            ys[a * 3 + 2] = -fma(w0, Di[2], fma(w1, Di[4], w2 * Di[5]));
+            hs[21 + a] = hs[27 + a] - fma(w0, db[0], fma(w1, db[1], w2 * db[2]));
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 18; ++q) ys[q] = 0.0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) hs[21 + a] = hs[27 + a];
+    }
+}
+
+// Of every 4 edges of a tile, how many get their stage B from the producers (after one more producer barrier) instead of
+// the consumers.  Measured on C3 x 512 (ms per step): 0 -> 22.7, 1 -> 23.7, 2 -> 23.7; the old all-producer design 23.1.
+#ifndef VISFS_WS_PROD_SHARE
+#define VISFS_WS_PROD_SHARE 0
+#endif
+constexpr int kProdShare = VISFS_WS_PROD_SHARE;
 
 __global__ void __maxnreg__(168) k_build_ws(Batch B, int cluster_size) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -139,19 +179,23 @@ __global__ void __maxnreg__(168) k_build_ws(Batch B, int cluster_size) {
             for (int i = tid; i < ntl * kMaxSmallPoses; i += kEdgeThreads) S.slot[i] = -1;
             if (tid <= ntl) sm.lmoff[tid] = min(B.lm_edge_off[lt + tid] - T.e0, kTileEdges);
 
-            EdgeLin lin;
-            bool act = false, lmfree = false;
-            int tl = 0, p = 0;
+            // stage A, everything that needs this edge only: residual, Jacobians, Huber weight; the H_ll / b_l terms go to
+            // the (still unused) Yn rows as scratch, W, H_pp_e and b_p_e to their final place.  Nothing of the
+            // linearisation stays live across the barrier; the landmark-level half (damped inverse, Yn, g) is done by the
+            // consumers, who would otherwise wait for this stage.
+            short meta = -1;
+            int slot_idx = -1;
             if (tid < ne) {
-                p = rec.pw & kPoseMask;
-                tl = rec.gl - lt;
-                act = !(rec.pw & kCulledBit) && !((rec.lf & kFixed) && (rec.pf & kFixed));
-                lmfree = (rec.lf & kInHessian) != 0;
-                double *hl = S.H + tid * kHStride;
+                const int p = rec.pw & kPoseMask;
+                const int tl = rec.gl - lt;
+                const bool act = !(rec.pw & kCulledBit) && !((rec.lf & kFixed) && (rec.pf & kFixed));
+                const bool lmfree = (rec.lf & kInHessian) != 0;
+                double *hl = S.Yn + tid * 18;
+                EdgeLin lin;
                 if (act) edge_linearize(sm.pose + p * kPoseSm, rec.px, rec.py, rec.pz, rec.ou, rec.ov, rec.our,
                                         (rec.pw & kMonoBit) != 0, K, lin);
+                const double wo = act ? lin.w * K.inv_pv : 0.0;
                 if (act && lmfree) {
-                    const double wo = lin.w * K.inv_pv;
                     const double *J = lin.Jl;
                     hl[0] = wo * fma(J[0], J[0], fma(J[3], J[3], J[6] * J[6]));
                     hl[1] = wo * fma(J[0], J[1], fma(J[3], J[4], J[6] * J[7]));
@@ -166,32 +210,11 @@ __global__ void __maxnreg__(168) k_build_ws(Batch B, int cluster_size) {
 #pragma unroll
                     for (int q = 0; q < 9; ++q) hl[q] = 0.0;
                 }
-            }
-            if (more) load_edge_l2(B, wd, Tn, tid, gpoint, nxt);                  // prefetch, level 2
-            bar_sync(BAR_PROD, kEdgeThreads);
-            // per-landmark H_ll (6) / b_l (3): one owner thread per (landmark, entry), edges added in edge order
-            for (int task = tid; task < ntl * 9; task += kEdgeThreads) {
-                const int l = task / 9, q = task - l * 9;
-                double s = 0.0;
-                for (int e = sm.lmoff[l]; e < sm.lmoff[l + 1]; ++e) s += S.H[e * kHStride + q];
-                S.lm[l * 12 + q] = s;
-            }
-            bar_sync(BAR_PROD, kEdgeThreads);
-            if (tid < ne && act) {
-                const int hi = sm.hidx[p];
+                const int hi = act ? sm.hidx[p] : -1;
                 if (hi >= 0) {
-                    const double wo = lin.w * K.inv_pv;
                     double *hs = S.H + tid * kHStride;
-                    double *ws = S.W + tid * 18, *ys = S.Yn + tid * 18;
-                    double Wm[18], db[3] = {0.0, 0.0, 0.0};
+                    double *ws = S.W + tid * 18;
                     if (lmfree) {
-                        // damped inverse of the landmark block, redundantly per edge (no third barrier)
-                        const double *ls = S.lm + tl * 12;
-                        double A[6] = {ls[0] + lambda, ls[1], ls[2], ls[3] + lambda, ls[4], ls[5] + lambda};
-                        const double bl[3] = {ls[6], ls[7], ls[8]};
-                        double Di[6];
-                        inv_sym3(A, Di);
-                        sym3_mul(Di, bl, db);
                         double Aj[9];
 #pragma unroll
                         for (int q = 0; q < 9; ++q) Aj[q] = wo * lin.Jl[q];
@@ -199,31 +222,37 @@ __global__ void __maxnreg__(168) k_build_ws(Batch B, int cluster_size) {
                         for (int a = 0; a < 6; ++a)
 #pragma unroll
                             for (int c = 0; c < 3; ++c)
-                                Wm[a * 3 + c] = fma(lin.Jp[a], Aj[c], fma(lin.Jp[6 + a], Aj[3 + c], lin.Jp[12 + a] * Aj[6 + c]));
-#pragma unroll
-                        for (int a = 0; a < 6; ++a) {
-                            ys[a * 3 + 0] = -fma(Wm[a * 3], Di[0], fma(Wm[a * 3 + 1], Di[1], Wm[a * 3 + 2] * Di[2]));
-                            ys[a * 3 + 1] = -fma(Wm[a * 3], Di[1], fma(Wm[a * 3 + 1], Di[3], Wm[a * 3 + 2] * Di[4]));
-                            ys[a * 3 + 2] = -fma(Wm[a * 3], Di[2], fma(Wm[a * 3 + 1], Di[4], Wm[a * 3 + 2] * Di[5]));
-                        }
+                                ws[a * 3 + c] = fma(lin.Jp[a], Aj[c], fma(lin.Jp[6 + a], Aj[3 + c], lin.Jp[12 + a] * Aj[6 + c]));
                     } else {
 #pragma unroll
-                        for (int q = 0; q < 18; ++q) { Wm[q] = 0.0; ys[q] = 0.0; }
+                        for (int q = 0; q < 18; ++q) ws[q] = 0.0;
                     }
-#pragma unroll
-                    for (int q = 0; q < 18; ++q) ws[q] = Wm[q];
                     const double wr0 = wo * lin.r[0], wr1 = wo * lin.r[1], wr2 = wo * lin.r[2];
 #pragma unroll
                     for (int a = 0; a < 6; ++a) {
-                        const double bp = -fma(lin.Jp[a], wr0, fma(lin.Jp[6 + a], wr1, lin.Jp[12 + a] * wr2));
-                        hs[27 + a] = bp;
-                        hs[21 + a] = bp - fma(Wm[a * 3], db[0], fma(Wm[a * 3 + 1], db[1], Wm[a * 3 + 2] * db[2]));
+                        hs[27 + a] = -fma(lin.Jp[a], wr0, fma(lin.Jp[6 + a], wr1, lin.Jp[12 + a] * wr2));
 #pragma unroll
                         for (int c = a; c < 6; ++c)
                             hs[hd_index(a, c)] = wo * fma(lin.Jp[a], lin.Jp[c], fma(lin.Jp[6 + a], lin.Jp[6 + c], lin.Jp[12 + a] * lin.Jp[12 + c]));
                     }
-                    S.slot[tl * kMaxSmallPoses + hi] = (short)tid;
+                    slot_idx = tl * kMaxSmallPoses + hi;
+                    meta = (short)(tl | (lmfree ? 64 : 0));
                 }
+            }
+            S.emeta[tid] = meta;
+            if (more) load_edge_l2(B, wd, Tn, tid, gpoint, nxt);                  // prefetch, level 2
+            bar_sync(BAR_PROD, kEdgeThreads);
+            if (slot_idx >= 0) S.slot[slot_idx] = (short)tid;   // (after the barrier: other threads cleared the table above)
+            // per-landmark H_ll (6) / b_l (3): one owner thread per (landmark, entry), edges added in edge order
+            for (int task = tid; task < ntl * 9; task += kEdgeThreads) {
+                const int l = task / 9, q = task - l * 9;
+                double s = 0.0;
+                for (int e = sm.lmoff[l]; e < sm.lmoff[l + 1]; ++e) s += S.Yn[e * 18 + q];
+                S.lm[l * 12 + q] = s;
+            }
+            if (kProdShare > 0) {
+                bar_sync(BAR_PROD, kEdgeThreads);
+                if ((tid & 3) < kProdShare) stage_b_edge(S, tid, lambda);
             }
             if (tid == 0) S.ntl = ntl;
             __threadfence_block();
@@ -243,9 +272,11 @@ __global__ void __maxnreg__(168) k_build_ws(Batch B, int cluster_size) {
             pi = i; pj = i + (pt - base);
         }
         for (int t = 0; t < ntiles; ++t) {
-            const Stage &S = sm.st[t & 1];
+            Stage &S = sm.st[t & 1];
             bar_sync(BAR_FULL + (t & 1), kThreadsWs);
             const int ntl = S.ntl;
+            if ((ctid & 3) >= kProdShare) stage_b_edge(S, ctid, lambda);
+            bar_sync(BAR_CONS, kPairThreads);
             for (int task = ctid; task < F * kHStride; task += kPairThreads) {
                 const int i = task / kHStride, k = task - i * kHStride;
                 double s = 0.0;
