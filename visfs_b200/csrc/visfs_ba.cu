@@ -105,6 +105,7 @@ struct visfs_ba_handle {
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
     visfs_ba_timing timing{};
     int64_t launches = 0, h2d_bytes = 0, d2h_bytes = 0;
+    bool direct_groups = false;   // sub-handle of a pipelined batch whose groups DMA page-locked caller arrays directly
     int direct_h2d = 0;   // pieces of the last upload DMA'd straight from the caller's page-locked arrays
 
     Batch batch{};
@@ -428,9 +429,9 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs) {
         // Every piece (one array of one window) either is DMA'd from the caller's memory (page-locked source, worth its
         // own copy) or is packed into the staging buffer; adjacent staged pieces leave as one copy.
         char *db = h->d_in.as<char>();
-        // (the groups of a pipelined batch keep the staging route: one large DMA transfer per group moves at 45 GB/s, the
-        //  many array-sized ones of the direct route at 20 GB/s, and their packing runs on all host cores anyway)
-        const bool allow_direct = !getenv("VISFS_BA_NO_DIRECT") && (!h->is_sub || getenv("VISFS_BA_DIRECT_GROUPS"));
+        // (the groups of a pipelined batch keep the staging route when the rank has 16 host cores for the packing: one large
+        //  DMA transfer per group moves at 45 GB/s, the many array-sized ones of the direct route at 20 GB/s; see pick_groups)
+        const bool allow_direct = !getenv("VISFS_BA_NO_DIRECT") && (!h->is_sub || h->direct_groups);
         constexpr size_t kDirectMin = 32 * 1024;
         size_t run_lo = 0, run_hi = 0;
         int direct = 0;
@@ -1042,7 +1043,7 @@ int download(visfs_ba_handle *h, int n, visfs_ba_result *res) {
     CK(h->h_out.reserve(o_end + 8));
     char *ho = h->h_out.as<char>();
     // results go straight into page-locked caller arrays when every window offers them for its landmarks and edge levels
-    bool direct = !getenv("VISFS_BA_NO_DIRECT") && n > 0 && (!h->is_sub || getenv("VISFS_BA_DIRECT_GROUPS"));
+    bool direct = !getenv("VISFS_BA_NO_DIRECT") && n > 0 && (!h->is_sub || h->direct_groups);
     for (int w = 0; w < n && direct; ++w) {
         const WinDesc &d = h->win[w];
         const visfs_ba_result &r = res[w];
@@ -1224,17 +1225,30 @@ int visfs_ba_get_timing(const visfs_ba_handle *h, visfs_ba_timing *out) {
 }
 
 // How many pipeline groups a batch of n windows is cut into (1 = the plain single-stream path).
-static int pick_groups(const visfs_ba_handle *h, int n, const visfs_ba_problem *problems) {
+// How a batch is pipelined: the number of groups, and whether the groups DMA page-locked caller arrays directly.
+// One host thread per group; several ranks of one job (torchrun exports LOCAL_WORLD_SIZE) share the host cores.
+// Measured on C3 x 512 with page-locked inputs, ms per batch (staging route / direct route, best group count of each):
+//   16 cores 27.9 (16 groups) / 28.7 (8)   8 cores 30.3 (8) / 28.8 (8)   4 cores 41.3 (8) / 30.1 (8)   2 cores 55.3 (8) / 37.3 (8)
+// so with fewer than 16 cores for this rank the packing threads are the bottleneck and the direct route wins.
+static int pick_groups(const visfs_ba_handle *h, int n, const visfs_ba_problem *problems, bool *direct) {
+    *direct = false;
     if (h->is_sub || n < 32) return 1;
     for (int w = 0; w < n; ++w)
         if (problems[w].flags & VISFS_BA_FLAG_PARTITIONED) return 1;
-    int g = 16;
+    int share = 16;
     const int hw = (int)std::thread::hardware_concurrency();
     if (hw > 0) {
-        // one host thread per group; several ranks of one job (torchrun exports LOCAL_WORLD_SIZE) share the host cores
-        int share = hw;
-        if (const char *lws = getenv("LOCAL_WORLD_SIZE")) share = std::max(4, hw / std::max(atoi(lws), 1));
-        g = std::min(g, share);
+        share = hw;
+        if (const char *lws = getenv("LOCAL_WORLD_SIZE")) share = std::max(1, hw / std::max(atoi(lws), 1));
+    }
+    const bool pinned = problems[0].n_edges > 0 && problems[n - 1].n_edges > 0 && host_is_pinned(problems[0].edge_obs) &&
+                        host_is_pinned(problems[n - 1].edge_obs);
+    int g;
+    if (getenv("VISFS_BA_DIRECT_GROUPS") || (pinned && share < 16 && !getenv("VISFS_BA_NO_DIRECT"))) {
+        *direct = true;
+        g = 8;
+    } else {
+        g = std::min(16, std::max(4, share));
     }
     if (const char *e = getenv("VISFS_BA_GROUPS")) g = atoi(e);
     g = std::min(g, n / 16);
@@ -1244,7 +1258,8 @@ static int pick_groups(const visfs_ba_handle *h, int n, const visfs_ba_problem *
 int visfs_ba_solve_batch(visfs_ba_handle *h, int32_t n, const visfs_ba_problem *problems, visfs_ba_result *results) {
     if (!h) return VISFS_BA_ERR_INVALID;
     if (n <= 0 || !problems || !results) return h->fail(VISFS_BA_ERR_INVALID, "empty batch");
-    const int groups = pick_groups(h, n, problems);
+    bool direct_groups = false;
+    const int groups = pick_groups(h, n, problems, &direct_groups);
     if (groups <= 1) {
         int st = upload(h, n, problems);
         if (st) return st;
@@ -1261,6 +1276,7 @@ int visfs_ba_solve_batch(visfs_ba_handle *h, int32_t n, const visfs_ba_problem *
         s->is_sub = true;
         h->subs.push_back(s);
     }
+    for (visfs_ba_handle *s : h->subs) s->direct_groups = direct_groups;
     h->resident = false; h->has_run = false;
     std::vector<int> status(groups, VISFS_BA_OK);
     std::vector<std::thread> workers;
