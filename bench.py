@@ -184,6 +184,18 @@ def single_window_numbers(ba, O, cores, quick):
             entry["cpu_allcores_iters_per_s"] = cit / rn["seconds"]
             entry["speedup_e2e_vs_cpu_allcores"] = entry["e2e_iters_per_s"] / max(entry["cpu_allcores_iters_per_s"], 1e-30)
             entry["speedup_e2e_vs_cpu_1thread"] = entry["e2e_iters_per_s"] / entry["cpu_1thread_iters_per_s"]
+        try:   # the same window through the reference-facing C++ class (std::map in, std::map out): VISFS::Optimizer::Optimizer
+            import tempfile
+            from tests import host_io
+            if os.path.exists(host_io.EXE):
+                with tempfile.TemporaryDirectory() as td:
+                    fin = os.path.join(td, "w.bin")
+                    host_io.write_window(fin, w)
+                    th = host_io.run_time(fin, os.path.join(td, "o.bin"))
+                entry["local_optimize_ms"] = th["local_optimize_ms_mean"]
+                entry["local_optimize_marshal_ms"] = th["marshal_ms"]
+        except Exception as e:   # the C++ mirror is optional for the bench line
+            entry["local_optimize_error"] = str(e)[:200]
         out[name] = entry
     return out
 

@@ -79,3 +79,10 @@ def run_solve(in_path, out_path):
     n = struct.unpack_from("<q", buf, off)[0]; off += 8
     outliers = np.frombuffer(buf, dtype="<i8", count=2 * n, offset=off).reshape(n, 2).copy()
     return dict(poses=poses, points=points, outliers=outliers, stdout=p.stdout, stderr=p.stderr)
+
+
+def run_time(in_path, out_path):
+    """localOptimize 20 times through the C++ mirror: {'local_optimize_ms_mean', 'local_optimize_ms_best', 'marshal_ms', ...}."""
+    import json
+    p = subprocess.run([EXE, "time", in_path, out_path], check=True, capture_output=True, text=True)
+    return json.loads(p.stdout.strip().splitlines()[-1])

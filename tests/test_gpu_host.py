@@ -59,3 +59,14 @@ def test_local_optimize_with_odometry_links(built, tmp_path):
         assert np.allclose(got["poses"][int(pid)], T_ref[i], rtol=1e-6, atol=1e-8)
     bare = {k: v for k, v in w.items() if not k.startswith("link") and k != "n_links"}
     assert not np.allclose(O.solve(bare)["pose_tq"], ref["pose_tq"], atol=1e-9), "the links do not matter: test is void"
+
+
+def test_local_optimize_repeated_calls_reuse_their_buffers(built, tmp_path):
+    # the Optimizer keeps its (page-locked) marshalling buffers from call to call: 23 calls on one object must all
+    # succeed, and a C1-sized call has to stay in the low milliseconds (maps in, maps out)
+    w = synth.config_c1()
+    fin, fout = str(tmp_path / "w.bin"), str(tmp_path / "o.bin")
+    host_io.write_window(fin, w)
+    t = host_io.run_time(fin, fout)
+    assert t["poses"] == 10 and t["edges"] == 20000
+    assert 0.0 < t["marshal_ms"] < t["local_optimize_ms_best"] < 50.0

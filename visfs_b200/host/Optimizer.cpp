@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstdio>
 #include <limits>
 
@@ -124,6 +125,19 @@ bool Optimizer::ensureHandle() {
     return true;
 }
 
+namespace detail {
+void * hostAlloc(std::size_t _bytes, bool * _pinned) {
+    void * p = visfs_ba_host_alloc(_bytes);      // NULL without a CUDA device
+    *_pinned = p != nullptr;
+    if (!p) p = std::malloc(_bytes ? _bytes : 1);
+    return p;
+}
+void hostFree(void * _p, bool _pinned) {
+    if (!_p) return;
+    if (_pinned) visfs_ba_host_free(_p); else std::free(_p);
+}
+}   // detail
+
 // Optimizer.cpp:100-114 (poses) and :152-223 (points, visual edges) of the reference
 bool Optimizer::marshal(std::size_t _rootId,
                         const std::map<std::size_t, Eigen::Isometry3d> & _poses,
@@ -134,7 +148,7 @@ bool Optimizer::marshal(std::size_t _rootId,
     if (_cameraModels.empty() || !_cameraModels.front()) return false;
     const GeometricCamera & cameraModel = *_cameraModels.front();
     const Eigen::Isometry3d Trc = cameraModel.getTansformImageToRobot();
-    m = detail::MarshalledWindow();
+    m.clear();
 
     std::map<std::size_t, int> poseIndex;
     for (auto iter = _poses.begin(); iter != _poses.end(); ++iter) {
@@ -148,7 +162,7 @@ bool Optimizer::marshal(std::size_t _rootId,
             m.pose_fixed.push_back(iter->first == _rootId ? 1 : 0);       // :111
             const Eigen::Vector3d & t = cameraPose.translation();
             const double rec[7] = {t[0], t[1], t[2], q[0], q[1], q[2], q[3]};
-            m.pose_tq.insert(m.pose_tq.end(), rec, rec + 7);
+            m.pose_tq.append(rec, rec + 7);
         }
     }
 
@@ -181,7 +195,7 @@ bool Optimizer::marshal(std::size_t _rootId,
             }
             // else: the reference's mono branch is commented out (:197-208) and its live code is undefined
             // behaviour; this build defines the mono edge as rows 0-1 of EdgeStereo.
-            m.edge_obs.insert(m.edge_obs.end(), obs, obs + 3);
+            m.edge_obs.append(obs, obs + 3);
             m.edge_pose.push_back(cit->second);
             m.edge_point.push_back(pointIndex);
             m.edge_kind.push_back(kind);
@@ -227,7 +241,7 @@ std::map<std::size_t, Eigen::Isometry3d> Optimizer::localOptimize(
         }
         if (!ensureHandle()) return optimizedPoses;
 
-        detail::MarshalledWindow m;
+        detail::MarshalledWindow & m = window_;
         if (!marshal(_rootId, _poses, _cameraModels, _points3D, _wordReferences, m)) return optimizedPoses;
 
         visfs_ba_problem prob{};
@@ -273,8 +287,10 @@ std::map<std::size_t, Eigen::Isometry3d> Optimizer::localOptimize(
         prob.link_from = linkFrom.data(); prob.link_to = linkTo.data(); prob.link_tq = linkTq.data();
         prob.odometry_variance = odometryCovariance_;           // :120
 
-        std::vector<double> poseOut(m.pose_tq.size()), pointOut(m.point_xyz.size());
-        std::vector<uint8_t> levelOut(m.edge_pose.size());
+        detail::HostArray<double> & poseOut = poseOut_;
+        detail::HostArray<double> & pointOut = pointOut_;
+        detail::HostArray<uint8_t> & levelOut = levelOut_;
+        poseOut.resize(m.pose_tq.size()); pointOut.resize(m.point_xyz.size()); levelOut.resize(m.edge_pose.size());
         visfs_ba_result res{};
         res.pose_tq = poseOut.data(); res.point_xyz = pointOut.data(); res.edge_level = levelOut.data();
         const int status = visfs_ba_solve(handle_, &prob, &res);
@@ -328,14 +344,15 @@ std::map<std::size_t, Eigen::Isometry3d> Optimizer::localOptimize(
         }
 
         // :343-358 — points: accept moves shorter than 5 m, NaN for points that never became a vertex
-        std::map<std::size_t, std::size_t> vertexOf;
-        for (std::size_t l = 0; l < m.point_id.size(); ++l) vertexOf.emplace(static_cast<std::size_t>(m.point_id[l]), l);
+        // (point_id ascends like _points3D's keys: one merge walk instead of a lookup table)
+        std::size_t l = 0;
         for (auto iter = _points3D.begin(); iter != _points3D.end(); ++iter) {
-            auto vit = vertexOf.find(iter->first);
-            Eigen::Vector3d oldPose = std::get<0>(iter->second);
+            while (l < m.point_id.size() && static_cast<std::size_t>(m.point_id[l]) < iter->first) ++l;
+            const bool hasVertex = l < m.point_id.size() && static_cast<std::size_t>(m.point_id[l]) == iter->first;
+            const Eigen::Vector3d oldPose = std::get<0>(iter->second);
             const bool fixSymbol = std::get<1>(iter->second);
-            if (vit != vertexOf.end()) {
-                const double * np = &pointOut[3 * vit->second];
+            if (hasVertex) {
+                const double * np = &pointOut[3 * l];
                 const double dx = oldPose[0] - np[0], dy = oldPose[1] - np[1], dz = oldPose[2] - np[2];
                 if (std::sqrt(dx * dx + dy * dy + dz * dz) < 5.0) {
                     iter->second = std::make_tuple(Eigen::Vector3d(np[0], np[1], np[2]), fixSymbol);

@@ -6,6 +6,7 @@
 #ifndef VISFS_OPTIMIZER_H
 #define VISFS_OPTIMIZER_H
 
+#include <cstddef>
 #include <cstdint>
 #include <map>
 #include <memory>
@@ -31,18 +32,69 @@ struct FeatureBA {
 };
 
 namespace detail {
+// Growable host array in page-locked memory (visfs_ba_host_alloc), so that the C ABI moves it by DMA without a staging
+// copy; plain malloc when there is no CUDA device (the marshalling itself needs none).  Kept across calls by Optimizer.
+void * hostAlloc(std::size_t _bytes, bool * _pinned);
+void hostFree(void * _p, bool _pinned);
+
+template <typename T>
+class HostArray {
+public:
+    HostArray() = default;
+    ~HostArray() { hostFree(p_, pinned_); }
+    HostArray(const HostArray &) = delete;
+    HostArray & operator=(const HostArray &) = delete;
+
+    void clear() { n_ = 0; }
+    std::size_t size() const { return n_; }
+    bool empty() const { return n_ == 0; }
+    T * data() { return p_; }
+    const T * data() const { return p_; }
+    T & operator[](std::size_t _i) { return p_[_i]; }
+    const T & operator[](std::size_t _i) const { return p_[_i]; }
+    const T * begin() const { return p_; }
+    const T * end() const { return p_ + n_; }
+    void push_back(const T & _v) { if (n_ == cap_) grow(n_ + 1); p_[n_++] = _v; }
+    void append(const T * _b, const T * _e) {
+        const std::size_t k = static_cast<std::size_t>(_e - _b);
+        if (n_ + k > cap_) grow(n_ + k);
+        for (std::size_t i = 0; i < k; ++i) p_[n_ + i] = _b[i];
+        n_ += k;
+    }
+    void resize(std::size_t _n) { if (_n > cap_) grow(_n); n_ = _n; }
+
+private:
+    void grow(std::size_t _need) {
+        std::size_t cap = cap_ ? 2 * cap_ : 4096;
+        if (cap < _need) cap = _need;
+        bool pinned = false;
+        T * q = static_cast<T *>(hostAlloc(cap * sizeof(T), &pinned));
+        for (std::size_t i = 0; i < n_; ++i) q[i] = p_[i];
+        hostFree(p_, pinned_);
+        p_ = q; cap_ = cap; pinned_ = pinned;
+    }
+    T * p_ = nullptr;
+    std::size_t n_ = 0, cap_ = 0;
+    bool pinned_ = false;
+};
+
 // The window in the flat form the C ABI takes (host memory), plus the id tables needed to map results back.
 struct MarshalledWindow {
-    std::vector<double> pose_tq;        // [P][7] T_cw
-    std::vector<int64_t> pose_id;
-    std::vector<uint8_t> pose_fixed;
-    std::vector<double> point_xyz;      // [L][3]
-    std::vector<int64_t> point_id;      // feature ids that got a vertex (Optimizer.cpp:158)
-    std::vector<uint8_t> point_fixed;
-    std::vector<double> edge_obs;       // [E][3]
-    std::vector<int32_t> edge_pose, edge_point;
-    std::vector<uint8_t> edge_kind;
+    HostArray<double> pose_tq;          // [P][7] T_cw
+    HostArray<int64_t> pose_id;
+    HostArray<uint8_t> pose_fixed;
+    HostArray<double> point_xyz;        // [L][3]
+    HostArray<int64_t> point_id;        // feature ids that got a vertex (Optimizer.cpp:158), ascending
+    HostArray<uint8_t> point_fixed;
+    HostArray<double> edge_obs;         // [E][3]
+    HostArray<int32_t> edge_pose, edge_point;
+    HostArray<uint8_t> edge_kind;
     double fx = 0, fy = 0, cx = 0, cy = 0, bf = 0;
+    void clear() {
+        pose_tq.clear(); pose_id.clear(); pose_fixed.clear(); point_xyz.clear(); point_id.clear(); point_fixed.clear();
+        edge_obs.clear(); edge_pose.clear(); edge_point.clear(); edge_kind.clear();
+        fx = fy = cx = cy = bf = 0;
+    }
 };
 }  // namespace detail
 
@@ -112,6 +164,11 @@ private:
 
     visfs_ba_handle * handle_;
     std::string message_;
+
+    // marshalling and result buffers, reused from call to call (results never depend on earlier calls)
+    detail::MarshalledWindow window_;
+    detail::HostArray<double> poseOut_, pointOut_;
+    detail::HostArray<uint8_t> levelOut_;
 };
 
 }   // Optimizer

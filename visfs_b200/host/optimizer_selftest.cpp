@@ -2,8 +2,11 @@
 // from a window file written by tests/host_io.py, and dumps what came back.
 //   optimizer_selftest marshal <in> <out>   host-only: the flat arrays handed to the C ABI (no GPU needed)
 //   optimizer_selftest solve   <in> <out>   full localOptimize on the GPU
+//   optimizer_selftest time    <in> <out>   the same 20 times: wall time per call and the marshalling share
 #include <cstdint>
 #include <cstdio>
+#include <algorithm>
+#include <chrono>
 #include <cstring>
 #include <fstream>
 #include <iostream>
@@ -20,10 +23,14 @@ template <typename T> void wrv(std::ostream &os, const std::vector<T> &v) {
     wr<int64_t>(os, (int64_t)v.size());
     if (!v.empty()) os.write(reinterpret_cast<const char *>(v.data()), sizeof(T) * v.size());
 }
+template <typename T> void wrv(std::ostream &os, const Optimizer::detail::HostArray<T> &v) {
+    wr<int64_t>(os, (int64_t)v.size());
+    if (!v.empty()) os.write(reinterpret_cast<const char *>(v.data()), sizeof(T) * v.size());
+}
 }  // namespace
 
 int main(int argc, char **argv) {
-    if (argc != 4) { std::fprintf(stderr, "usage: %s marshal|solve <in> <out>\n", argv[0]); return 2; }
+    if (argc != 4) { std::fprintf(stderr, "usage: %s marshal|solve|time <in> <out>\n", argv[0]); return 2; }
     const std::string mode = argv[1];
     std::ifstream in(argv[2], std::ios::binary);
     if (!in) { std::fprintf(stderr, "cannot open %s\n", argv[2]); return 2; }
@@ -100,6 +107,31 @@ int main(int argc, char **argv) {
     std::vector<std::tuple<std::size_t, std::size_t>> outliers;
     const std::vector<Sensor::PointCloud> pointClouds;
     const std::shared_ptr<const Map::Submap2D> submap;
+    if (mode == "time") {
+        // what Estimator::process pays per key frame: the whole call, maps in, maps out
+        const auto pointsIn = points3D;
+        double best = 1e30, sum = 0.0, marshalMs = 0.0;
+        const int reps = 20;
+        for (int r = 0; r < reps + 3; ++r) {
+            points3D = pointsIn; outliers.clear();
+            const auto t0 = std::chrono::steady_clock::now();
+            auto res = optimizer.localOptimize((std::size_t)rootId, poses, links, cameraModels, points3D, wordReferences,
+                                               pointClouds, submap, outliers);
+            const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            if (res.size() != poses.size()) { std::fprintf(stderr, "localOptimize failed: %s\n", optimizer.lastMessage().c_str()); return 1; }
+            if (r >= 3) { best = std::min(best, ms); sum += ms; }
+        }
+        {
+            Optimizer::detail::MarshalledWindow m;
+            Optimizer::Optimizer::marshal((std::size_t)rootId, poses, cameraModels, points3D, wordReferences, m);   // sizes the arrays
+            const auto t0 = std::chrono::steady_clock::now();
+            for (int r = 0; r < reps; ++r) Optimizer::Optimizer::marshal((std::size_t)rootId, poses, cameraModels, points3D, wordReferences, m);
+            marshalMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() / reps;
+        }
+        std::printf("{\"poses\": %lld, \"points\": %lld, \"edges\": %lld, \"local_optimize_ms_mean\": %.4f, \"local_optimize_ms_best\": %.4f, \"marshal_ms\": %.4f}\n",
+                    (long long)P, (long long)L, (long long)E, sum / reps, best, marshalMs);
+        return 0;
+    }
     auto result = optimizer.localOptimize((std::size_t)rootId, poses, links, cameraModels, points3D, wordReferences,
                                           pointClouds, submap, outliers);
     wr<int64_t>(out, (int64_t)result.size());
