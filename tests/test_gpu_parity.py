@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from tests import oracle_api as O
-from visfs_b200 import synth
+from visfs_b200 import capi, synth
 
 pytestmark = pytest.mark.gpu
 
@@ -297,6 +297,45 @@ def test_page_locked_caller_arrays_take_the_direct_dma_path(ba):
     ba._check(ba.lib.visfs_ba_download(ba.h, n, res))
     for a, b in zip(ba.solve_batch(ws[5:12]), ba.packed_results(packed)):
         assert a["chi2_final"] == b["chi2_final"] and np.array_equal(a["pose_tq"], b["pose_tq"])
+
+
+def test_malformed_problems_are_rejected_with_a_message_and_the_handle_survives(ba):
+    # the host-side validation is load-bearing (an out-of-range index would be an illegal address on the device): every
+    # malformed input comes back as a status + message, nothing is launched, and the handle solves the next window
+    good = synth.make_window(5, 120, layout="all", seed=910)
+
+    def bad(match, **changes):
+        w = dict(good)
+        for k, v in changes.items():
+            w[k] = v(good[k].copy()) if callable(v) else v
+        with pytest.raises(capi.BAError, match=match):
+            ba.solve(w)
+
+    def poke(i, val):
+        def f(a):
+            a[i] = val
+            return a
+        return f
+
+    bad("edge index out of range", edge_pose=poke(7, 5))
+    bad("edge index out of range", edge_pose=poke(0, -1))
+    bad("edge index out of range", edge_point=poke(3, 120))
+    bad("pixel_variance", pixel_variance=0.0)
+    bad("pose_id not strictly ascending", pose_id=poke(2, int(good["pose_id"][1])))
+    bad("point_id not strictly ascending", point_id=poke(10, int(good["point_id"][9])))
+    linked = synth.make_window(5, 120, layout="all", seed=910, links="chain")
+    w = dict(linked); w["link_to"] = linked["link_to"].copy(); w["link_to"][1] = 9
+    with pytest.raises(capi.BAError, match="odometry link index out of range"):
+        ba.solve(w)
+    w = dict(linked); w["odometry_variance"] = 0.0
+    with pytest.raises(capi.BAError, match="odometry_variance"):
+        ba.solve(w)
+    # a batch with one bad window is refused as a whole, naming the window
+    ws = [synth.make_window(5, 100 + k, layout="all", seed=920 + k) for k in range(40)]
+    ws[37] = dict(ws[37]); ws[37]["edge_point"] = ws[37]["edge_point"].copy(); ws[37]["edge_point"][5] = 10**6
+    with pytest.raises(capi.BAError, match="problem 37: edge index out of range"):
+        ba.solve_batch(ws)
+    check_solution(ba.solve(good), O.solve(good), "after the rejected inputs")
 
 
 # ---------------------------------------------------------------- odometry links (EdgePoseConstraint)

@@ -105,6 +105,7 @@ struct visfs_ba_handle {
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
     visfs_ba_timing timing{};
     int64_t launches = 0, h2d_bytes = 0, d2h_bytes = 0;
+    int idx_base = 0;             // sub-handle of a pipelined batch: index of its first window in the caller's batch (messages)
     bool direct_groups = false;   // sub-handle of a pipelined batch whose groups DMA page-locked caller arrays directly
     int direct_h2d = 0;   // pieces of the last upload DMA'd straight from the caller's page-locked arrays
 
@@ -175,7 +176,7 @@ bool host_is_pinned(const void *p) {
 int validate(visfs_ba_handle *h, const visfs_ba_problem &p, int idx, bool *sorted, int *max_degree) {
     char buf[160];
     auto bad = [&](const char *m) {
-        snprintf(buf, sizeof buf, "problem %d: %s", idx, m);
+        snprintf(buf, sizeof buf, "problem %d: %s", h->idx_base + idx, m);
         return h->fail(VISFS_BA_ERR_INVALID, buf);
     };
     if (p.n_poses < 0 || p.n_points < 0 || p.n_edges < 0) return bad("negative size");
@@ -1306,6 +1307,7 @@ int visfs_ba_solve_batch(visfs_ba_handle *h, int32_t n, const visfs_ba_problem *
     for (int g = 0; g < groups; ++g) {
         const int cnt = sizes[g];
         visfs_ba_handle *s = h->subs[g];
+        s->idx_base = off;
         workers.emplace_back([s, cnt, off, problems, results, &status, g, t_call, trace]() {
             auto ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count(); };
             const double t0 = ms();
