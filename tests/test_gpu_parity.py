@@ -401,3 +401,40 @@ def test_empty_and_degenerate_windows(ba):
     ws = [synth.make_window(5, 100, layout="all", seed=503), dict(w), synth.make_window(4, 80, layout="all", seed=504)]
     for g, x in zip(ba.solve_batch(ws), ws):
         check_solution(g, O.solve(x), "mixed batch")
+
+
+# ---------------------------------------------------------------- seeded sweep over window shapes and options
+def _sweep_windows():
+    rng = np.random.default_rng(20261018)
+    ws = []
+    for k in range(36):
+        P = int(rng.integers(2, 33))                      # crosses the warp-specialised (<= 20 poses) / fallback build boundary
+        layout = ("all", "consecutive", "random")[k % 3] if P <= 20 else ("consecutive", "random")[k % 2]
+        views = int(rng.integers(2, min(P, 12) + 1))
+        L = int(rng.integers(40, 400))
+        kw = dict(layout=layout, views=views, seed=5000 + k, mono_frac=float(rng.choice([0.0, 0.0, 0.25, 1.0])),
+                  fixed_point_frac=float(rng.choice([0.0, 0.0, 0.15])), outlier_frac=float(rng.choice([0.0, 0.05, 0.15])),
+                  root=rng.choice(["second_newest", "first", None]), shuffle_edges=bool(rng.integers(0, 4) == 0),
+                  iterations=int(rng.choice([10, 10, 6, 7])), solver=int(rng.choice([0, 0, 0, 2])),
+                  trust_region=int(rng.choice([0, 0, 0, 1])), huber_delta=float(rng.choice([8.0, 8.0, 3.0])),
+                  links="chain" if k % 4 == 1 else None)
+        if kw["trust_region"] == 1:                        # undamped Gauss-Newton: start inside its basin
+            kw.update(outlier_frac=0.0, pose_noise=(0.004, np.deg2rad(0.1)), point_noise=0.01)
+        if kw["root"] is None or kw["mono_frac"] == 1.0:   # gauge / scale only held by damping: keep LM
+            kw.update(trust_region=0)
+        ws.append(synth.make_window(P, L, **kw))
+    return ws
+
+
+def test_seeded_sweep_of_window_shapes_and_options(ba):
+    ws = _sweep_windows()
+    small = [w for w in ws if w["n_poses"] <= 32]
+    got = ba.solve_batch(small)                            # one heterogeneous batch (pipelined: >= 32 windows)
+    bad = []
+    for k, (w, g) in enumerate(zip(small, got)):
+        r = O.solve(w)
+        try:
+            check_solution(g, r, f"sweep window {k}")
+        except AssertionError as e:
+            bad.append(str(e)[:300])
+    assert not bad, "\n".join(bad)
