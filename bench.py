@@ -55,10 +55,67 @@ def flops_per_trial(w):
 
 # ---------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
+    """SM clock and clock-event reasons of one GPU, sampled every few ms DURING the timed region by an in-process NVML
+    thread (the timed calls are ctypes calls that release the GIL); falls back to an `nvidia-smi -lms` child process."""
+    NAMES = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
     def __init__(self, device):
-        self.rows, self.proc, self.device = [], None, device
+        self.device, self.sm, self.mx, self.reasons = device, [], [], set()
+        self.proc = self.thread = self.nv = self.handle = None
+        self.stop = threading.Event()
+        try:   # NVML is initialised here, outside the timed region
+            self.handle = self._nvml_handle()
+            self.mx.append(float(self.nv.nvmlDeviceGetMaxClockInfo(self.handle, self.nv.NVML_CLOCK_SM)))
+            self.nv.nvmlDeviceGetClockInfo(self.handle, self.nv.NVML_CLOCK_SM)
+        except Exception:
+            self.handle = None
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        self.nv = pynvml
+        try:
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.device).uuid)
+            return pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:
+            return pynvml.nvmlDeviceGetHandleByIndex(self.device)
+
+    def _sample(self):
+        nv, h = self.nv, self.handle
+        reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        try:
+            self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+            bits = int(reasons_fn(h))
+            for bit, name in self.NAMES.items():
+                if bits & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def _poll(self):
+        while True:
+            self._sample()
+            if self.stop.wait(0.004):
+                break
+
+    def _read_smi(self):
+        for line in self.proc.stdout:
+            r = [c.strip() for c in line.split(",")]
+            try:
+                self.sm.append(float(r[0])); self.mx.append(float(r[1]))
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(name)
+            except Exception:
+                pass
 
     def __enter__(self):
+        self.t_enter = time.perf_counter()
+        if self.handle is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return self
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.device),
@@ -66,18 +123,20 @@ class ClockSampler:
                  "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
                  "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "100"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread = threading.Thread(target=self._read_smi, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
         return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
     def __exit__(self, *exc):
-        if self.proc:
+        if self.handle is not None:
+            self._sample()          # (the GPU is still at its loaded clocks right after the last synchronise; an NVML call
+            self.stop.set()         #  of the polling thread occasionally blocks for tens of ms under load)
+            self.thread.join(timeout=1.0)
+            if os.environ.get("VISFS_BENCH_DEBUG"):
+                print(f"[clocks] {len(self.sm)} samples in {time.perf_counter() - self.t_enter:.3f} s", file=sys.stderr)
+        elif self.proc:
             time.sleep(0.15)
             self.proc.terminate()
             try:
@@ -86,18 +145,9 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-                for name, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            except Exception:
-                pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm),
+                "source": "nvml, 4 ms period, during the timed region" if self.handle is not None else "nvidia-smi -lms 100"}
 
 
 # ---------------------------------------------------------------------------------------------- CPU arm
@@ -315,11 +365,12 @@ def run_gpu(args):
 
     # ---- device-resident: inputs already in HBM
     ba.upload(windows)
+    clocks = ClockSampler(local)
     for _ in range(args.warmup):
         ba.run_resident()
     barrier()
     dev_ms, tims = 0.0, []
-    with ClockSampler(local) as clocks:
+    with clocks:
         for _ in range(args.steps):
             ba.run_resident()
             t = ba.timing()
