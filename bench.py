@@ -204,7 +204,7 @@ def single_window_numbers(ba, O, cores, quick):
     """C1 and C2 as single windows: device LM time, end-to-end call time, CPU oracle time."""
     out = {}
     for name, w in (("c1", synth.config_c1()), ("c2", synth.config_c2())):
-        packed = ba.prepare_batch([w], pinned=True)
+        packed = ba.prepare_batch([w], pinned=True, float_obs=True)
         for _ in range(3):
             ba.solve_packed(packed)
         reps = 5 if quick else 20
@@ -347,7 +347,7 @@ def run_gpu(args):
         print(json.dumps({"profile_run": True, "timing": ba.timing()}), flush=True)
         return 0
     fp64_peak = ba.probe_fp64()
-    packed = ba.prepare_batch(windows, pinned=True)
+    packed = ba.prepare_batch(windows, pinned=True, float_obs=True)
 
     # ---- end to end through the C ABI with host buffers (H2D + LM + D2H in the timed region)
     for _ in range(args.warmup):

@@ -76,7 +76,7 @@
 extern "C" {
 #endif
 
-#define VISFS_BA_ABI_VERSION 2
+#define VISFS_BA_ABI_VERSION 3
 
 typedef enum visfs_ba_status {
     VISFS_BA_OK = 0,
@@ -145,6 +145,11 @@ typedef struct visfs_ba_problem {
     const int32_t *link_to;      /* [n_links] index into poses                               */
     const double  *link_tq;      /* [n_links][7] measurement as tx ty tz qx qy qz qw         */
     double odometry_variance;    /* Optimizer/OdometryCovariance (Parameters.h:189)          */
+    /* Optional: the observations as floats, used INSTEAD of edge_obs when not NULL (edge_obs may then be NULL).  The
+     * reference's observations are floats widened to double (cv::KeyPoint and FeatureBA::depth are float, and u_right
+     * = x - disparity is a float subtraction, Optimizer.cpp:187-188), so this form loses nothing and moves 12 instead of
+     * 24 bytes per edge over PCIe; the device widens them back. */
+    const float   *edge_obs_f32; /* [E][3]  u, v, u_right                                    */
 } visfs_ba_problem;
 
 typedef struct visfs_ba_result {

@@ -280,7 +280,8 @@ struct Oracle {
         P = p->n_poses; L = p->n_points; E = p->n_edges;
         pose.assign(p->pose_tq, p->pose_tq + 7 * (size_t)P);
         point.assign(p->point_xyz, p->point_xyz + 3 * (size_t)L);
-        obs.assign(p->edge_obs, p->edge_obs + 3 * (size_t)E);
+        if (p->edge_obs_f32) { obs.resize(3 * (size_t)E); for (size_t i = 0; i < obs.size(); ++i) obs[i] = (double)p->edge_obs_f32[i]; }
+        else obs.assign(p->edge_obs, p->edge_obs + 3 * (size_t)E);
         pfix.assign(P, 0); lfix.assign(L, 0); kind.assign(E, 0); level.assign(E, 0);
         if (p->pose_fixed) pfix.assign(p->pose_fixed, p->pose_fixed + P);
         if (p->point_fixed) lfix.assign(p->point_fixed, p->point_fixed + L);

@@ -299,6 +299,31 @@ def test_page_locked_caller_arrays_take_the_direct_dma_path(ba):
         assert a["chi2_final"] == b["chi2_final"] and np.array_equal(a["pose_tq"], b["pose_tq"])
 
 
+def test_float_observations_travel_as_floats_and_change_nothing(ba):
+    # edge_obs_f32: 12 instead of 24 bytes per edge over PCIe; bit-identical results for one window, a pipelined batch and a
+    # batch that mixes both forms (the float windows are then widened while packing)
+    ws = [synth.make_window(5 + k % 3, 150 + 20 * k, layout="all" if k % 2 == 0 else "consecutive", views=4, seed=800 + k,
+                            mono_frac=0.2 if k % 3 == 0 else 0.0) for k in range(40)]
+    fw = [capi.with_float_observations(w) for w in ws]
+    ref = ba.solve_batch(ws)
+    bytes_double = ba.timing()["h2d_bytes"]
+    got = ba.solve_batch(fw)
+    bytes_float = ba.timing()["h2d_bytes"]
+    n_edges = sum(w["n_edges"] for w in ws)
+    assert bytes_double - bytes_float >= 12 * n_edges - 4096
+    mixed = ba.solve_batch([fw[k] if k % 2 else ws[k] for k in range(40)])
+    pairs = [(g, ref[k]) for k in range(40) for g in (got[k], mixed[k])]
+    pairs.append((ba.solve(fw[7]), ba.solve(ws[7])))       # (a single window is cut into chunks differently from a batch)
+    for g, r in pairs:
+        assert g["trials_run"] == r["trials_run"] and g["chi2_final"] == r["chi2_final"]
+        assert np.array_equal(g["pose_tq"], r["pose_tq"]) and np.array_equal(g["point_xyz"], r["point_xyz"])
+        assert np.array_equal(g["edge_level"], r["edge_level"])
+    packed = ba.prepare_batch(ws, pinned=True, float_obs=True)       # page-locked floats: the direct DMA route
+    ba.solve_packed(packed)
+    for a, b in zip(ba.packed_results(packed), ref):
+        assert a["chi2_final"] == b["chi2_final"] and np.array_equal(a["pose_tq"], b["pose_tq"])
+
+
 def test_malformed_problems_are_rejected_with_a_message_and_the_handle_survives(ba):
     # the host-side validation is load-bearing (an out-of-range index would be an illegal address on the device): every
     # malformed input comes back as a status + message, nothing is launched, and the handle solves the next window

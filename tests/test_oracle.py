@@ -321,3 +321,16 @@ def test_links_keep_a_pose_without_visual_edges_active():
     assert s["pose_hidx"][1] >= 0
     bare = {k: v for k, v in w.items() if not k.startswith("link") and k != "n_links"}
     assert O.structure(bare)["pose_hidx"][1] == -1
+
+
+def test_float_observations_are_the_same_problem():
+    # edge_obs_f32 (include/visfs_ba.h): the reference's observations are floats widened to double, so handing them over as
+    # floats is exact — the oracle must return bit-identical results
+    from visfs_b200 import capi
+    w = synth.make_window(6, 200, layout="consecutive", views=4, seed=77, mono_frac=0.2)
+    a, b = O.solve(w), O.solve(capi.with_float_observations(w))
+    assert a["trials_run"] == b["trials_run"] and a["chi2_final"] == b["chi2_final"]
+    assert np.array_equal(a["pose_tq"], b["pose_tq"]) and np.array_equal(a["edge_level"], b["edge_level"])
+    w2 = dict(w); w2["edge_obs"] = w["edge_obs"] + 1e-9
+    with pytest.raises(ValueError):
+        capi.with_float_observations(w2)

@@ -40,7 +40,8 @@ class Problem(C.Structure):
                 ("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double), ("bf", C.c_double),
                 ("pixel_variance", C.c_double), ("huber_delta", C.c_double),
                 ("iterations", C.c_int32), ("solver", C.c_int32), ("trust_region", C.c_int32), ("n_links", C.c_int32),
-                ("link_from", _i32p), ("link_to", _i32p), ("link_tq", _dp), ("odometry_variance", C.c_double)]
+                ("link_from", _i32p), ("link_to", _i32p), ("link_tq", _dp), ("odometry_variance", C.c_double),
+                ("edge_obs_f32", C.POINTER(C.c_float))]
 
 
 class Result(C.Structure):
@@ -84,6 +85,17 @@ def _ptr(a, typ):
     return None if a is None else a.ctypes.data_as(typ)
 
 
+def with_float_observations(w):
+    """The same window with its observations as floats (edge_obs_f32).  Exact for windows whose observations come from float
+    key points and depths, which is what the reference has (synth.marshal_observations); refuses to round otherwise."""
+    f = np.ascontiguousarray(w["edge_obs"], dtype=np.float32)
+    if not np.array_equal(f.astype(np.float64), np.asarray(w["edge_obs"], dtype=np.float64)):
+        raise ValueError("edge_obs is not representable in float32")
+    out = dict(w)
+    out["edge_obs_f32"] = f
+    return out
+
+
 def window_to_problem(w, keep):
     """Fill a Problem from a window dict (visfs_b200.synth.make_window).  `keep` is a list that
     receives the contiguous arrays so they outlive the call."""
@@ -103,7 +115,10 @@ def window_to_problem(w, keep):
     p.point_xyz = _ptr(arr("point_xyz", np.float64), _dp)
     p.point_id = _ptr(arr("point_id", np.int64), _i64p)
     p.point_fixed = _ptr(arr("point_fixed", np.uint8), _u8p)
-    p.edge_obs = _ptr(arr("edge_obs", np.float64), _dp)
+    if w.get("edge_obs_f32") is not None:    # observations as floats (include/visfs_ba.h): used instead of edge_obs
+        p.edge_obs_f32 = _ptr(arr("edge_obs_f32", np.float32), C.POINTER(C.c_float))
+    else:
+        p.edge_obs = _ptr(arr("edge_obs", np.float64), _dp)
     p.edge_pose = _ptr(arr("edge_pose", np.int32), _i32p)
     p.edge_point = _ptr(arr("edge_point", np.int32), _i32p)
     p.edge_kind = _ptr(arr("edge_kind", np.uint8), _u8p)
@@ -303,10 +318,11 @@ class BundleAdjuster:
         outs = [ResultArrays(w) for w in windows]
         if pinned:
             # every input and output array moves into one page-locked arena (freed with the packed batch)
-            keys = ("pose_tq", "pose_fixed", "point_xyz", "point_fixed", "edge_obs", "edge_pose", "edge_point", "edge_kind")
+            keys = ("pose_tq", "pose_fixed", "point_xyz", "point_fixed", "edge_obs", "edge_obs_f32", "edge_pose", "edge_point", "edge_kind")
             cast = dict(pose_tq=np.float64, pose_fixed=np.uint8, point_xyz=np.float64, point_fixed=np.uint8,
-                        edge_obs=np.float64, edge_pose=np.int32, edge_point=np.int32, edge_kind=np.uint8)
-            arrs = [{k: np.ascontiguousarray(w[k], dtype=cast[k]) for k in keys if w.get(k) is not None} for w in windows]
+                        edge_obs=np.float64, edge_obs_f32=np.float32, edge_pose=np.int32, edge_point=np.int32, edge_kind=np.uint8)
+            arrs = [{k: np.ascontiguousarray(w[k], dtype=cast[k]) for k in keys
+                     if w.get(k) is not None and not (k == "edge_obs" and w.get("edge_obs_f32") is not None)} for w in windows]
             total = sum(PinnedArena.size_of(a) for d in arrs for a in d.values())
             total += sum(PinnedArena.size_of(a) for o in outs for a in (o.pose_tq, o.point_xyz, o.edge_level))
             arena = PinnedArena(self.lib, total + 64)
@@ -325,9 +341,11 @@ class BundleAdjuster:
         self._check(self.lib.visfs_ba_solve_batch(self.h, n, probs, res))
         return [result_to_dict(r, o) for r, o in zip(res, outs)]
 
-    def prepare_batch(self, windows, pinned=False):
+    def prepare_batch(self, windows, pinned=False, float_obs=False):
         """Marshal once; returns an opaque packed batch for repeated solve_packed() calls.  pinned=True places every
         array in page-locked memory (visfs_ba_host_alloc): no staging copy on either side of the call."""
+        if float_obs:
+            windows = [with_float_observations(w) for w in windows]
         return self._pack(windows, pinned)
 
     def packed_results(self, packed):

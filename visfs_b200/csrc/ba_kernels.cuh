@@ -704,7 +704,8 @@ __global__ void k_export(Batch B, double *pose_out /*[tot_pose][7]*/, double *po
 
 // raw upload -> device layout: AoS observations to SoA, packed pose word; `perm` (or identity) maps
 // sorted edge slot -> caller's edge index inside the window
-__global__ void k_prepare_edges(Batch B, const double *obs_in /*[tot_edge][3]*/, const int *pose_in, const int *point_in,
+__global__ void k_prepare_edges(Batch B, const double *obs_in /*[tot_edge][3], or null*/, const float *obs_in_f32 /*the same as floats*/,
+                                const int *pose_in, const int *point_in,
                                 const uint8_t *kind_in, const int *perm, double *obs_u, double *obs_v, double *obs_r,
                                 int *edge_point) {
     const int w = blockIdx.y;
@@ -712,9 +713,15 @@ __global__ void k_prepare_edges(Batch B, const double *obs_in /*[tot_edge][3]*/,
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < wd.n_edge; i += gridDim.x * blockDim.x) {
         const int e = wd.edge_off + i;
         const int src = wd.edge_off + (perm ? perm[e] : i);
-        obs_u[e] = obs_in[3 * (size_t)src];
-        obs_v[e] = obs_in[3 * (size_t)src + 1];
-        obs_r[e] = obs_in[3 * (size_t)src + 2];
+        if (obs_in_f32) {
+            obs_u[e] = (double)obs_in_f32[3 * (size_t)src];
+            obs_v[e] = (double)obs_in_f32[3 * (size_t)src + 1];
+            obs_r[e] = (double)obs_in_f32[3 * (size_t)src + 2];
+        } else {
+            obs_u[e] = obs_in[3 * (size_t)src];
+            obs_v[e] = obs_in[3 * (size_t)src + 1];
+            obs_r[e] = obs_in[3 * (size_t)src + 2];
+        }
         B.edge_pose[e] = (pose_in[src] & kPoseMask) | ((kind_in && kind_in[src]) ? kMonoBit : 0);
         edge_point[e] = point_in[src];
     }

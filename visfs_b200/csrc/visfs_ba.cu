@@ -182,7 +182,7 @@ int validate(visfs_ba_handle *h, const visfs_ba_problem &p, int idx, bool *sorte
     if (p.n_poses < 0 || p.n_points < 0 || p.n_edges < 0) return bad("negative size");
     if (p.n_poses > kPoseMask) return bad("too many poses");
     if ((p.n_poses && !p.pose_tq) || (p.n_points && !p.point_xyz)) return bad("null pose_tq / point_xyz");
-    if (p.n_edges && (!p.edge_obs || !p.edge_pose || !p.edge_point)) return bad("null edge arrays");
+    if (p.n_edges && ((!p.edge_obs && !p.edge_obs_f32) || !p.edge_pose || !p.edge_point)) return bad("null edge arrays");
     if (!(p.pixel_variance > 0.0)) return bad("pixel_variance must be > 0");
     if (p.n_links < 0 || (p.n_links > 0 && (!p.link_from || !p.link_to || !p.link_tq))) return bad("bad odometry link arrays");
     if (p.n_links > 0 && !(p.odometry_variance > 0.0)) return bad("odometry_variance must be > 0");
@@ -410,8 +410,12 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs) {
 
     // pack into one pinned staging buffer (layout: pose | point | obs | epose | epoint | pfix | lfix | ekind)
     auto al16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
+    // observations travel as floats when every window offers them that way (edge_obs_f32), else as doubles
+    bool obs_f32 = te > 0;
+    for (int w = 0; w < n; ++w) if (probs[w].n_edges > 0 && !probs[w].edge_obs_f32) obs_f32 = false;
+    const size_t obs_elem = obs_f32 ? sizeof(float) : sizeof(double);
     const size_t o_pose = 0, o_point = o_pose + sizeof(double) * 7 * P, o_obs = o_point + sizeof(double) * 3 * L,
-                 o_epose = o_obs + sizeof(double) * 3 * E, o_epoint = o_epose + sizeof(int) * E,
+                 o_epose = o_obs + obs_elem * 3 * E, o_epoint = o_epose + sizeof(int) * E,
                  o_pfix = o_epoint + sizeof(int) * E, o_lfix = o_pfix + P, o_ekind = o_lfix + L, o_win = al16(o_ekind + E),
                  o_chunks = al16(o_win + sizeof(WinDesc) * n), o_end = al16(o_chunks + sizeof(Chunk) * std::max(h->n_chunks, 1));
     CK(h->h_stage.reserve(o_end));
@@ -461,7 +465,16 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs) {
         };
         for (int w = 0; w < n; ++w) put(o_pose + sizeof(double) * 7 * h->win[w].pose_off, probs[w].pose_tq, sizeof(double) * 7 * probs[w].n_poses);
         for (int w = 0; w < n; ++w) put(o_point + sizeof(double) * 3 * h->win[w].point_off, probs[w].point_xyz, sizeof(double) * 3 * probs[w].n_points);
-        for (int w = 0; w < n; ++w) put(o_obs + sizeof(double) * 3 * h->win[w].edge_off, probs[w].edge_obs, sizeof(double) * 3 * probs[w].n_edges);
+        for (int w = 0; w < n; ++w) {
+            const visfs_ba_problem &p = probs[w];
+            const size_t at = o_obs + obs_elem * 3 * h->win[w].edge_off;
+            if (obs_f32) put(at, p.edge_obs_f32, sizeof(float) * 3 * p.n_edges);
+            else if (!p.edge_obs_f32) put(at, p.edge_obs, sizeof(double) * 3 * p.n_edges);
+            else if (p.n_edges) {   // a float window in a batch that travels as doubles: widened while packing
+                double *dst = reinterpret_cast<double *>(stage_at(at, sizeof(double) * 3 * p.n_edges));
+                for (size_t i = 0; i < 3 * (size_t)p.n_edges; ++i) dst[i] = (double)p.edge_obs_f32[i];
+            }
+        }
         for (int w = 0; w < n; ++w) put(o_epose + sizeof(int) * h->win[w].edge_off, probs[w].edge_pose, sizeof(int) * probs[w].n_edges);
         for (int w = 0; w < n; ++w) put(o_epoint + sizeof(int) * h->win[w].edge_off, probs[w].edge_point, sizeof(int) * probs[w].n_edges);
         for (int w = 0; w < n; ++w) put_flags(o_pfix + h->win[w].pose_off, probs[w].pose_fixed, probs[w].n_poses);
@@ -520,7 +533,7 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs) {
     h->batch_ctl.part2 = h->d_scal.as<double>() + 2;
     Batch &B = h->batch;
     if (te > 0) {
-        k_prepare_edges<<<grid2(max_edge, n), 256, 0, s>>>(B, h->in.obs, h->in.epose, h->in.epoint,
+        k_prepare_edges<<<grid2(max_edge, n), 256, 0, s>>>(B, obs_f32 ? nullptr : h->in.obs, obs_f32 ? reinterpret_cast<const float *>(h->in.obs) : nullptr, h->in.epose, h->in.epoint,
                                                           h->in.ekind, perm, h->d_obs_u.as<double>(),
                                                           h->d_obs_v.as<double>(), h->d_obs_r.as<double>(), h->d_edge_point.as<int>());
     }
@@ -1242,8 +1255,9 @@ static int pick_groups(const visfs_ba_handle *h, int n, const visfs_ba_problem *
         share = hw;
         if (const char *lws = getenv("LOCAL_WORLD_SIZE")) share = std::max(1, hw / std::max(atoi(lws), 1));
     }
-    const bool pinned = problems[0].n_edges > 0 && problems[n - 1].n_edges > 0 && host_is_pinned(problems[0].edge_obs) &&
-                        host_is_pinned(problems[n - 1].edge_obs);
+    auto obs_of = [](const visfs_ba_problem &p) -> const void * { return p.edge_obs_f32 ? (const void *)p.edge_obs_f32 : (const void *)p.edge_obs; };
+    const bool pinned = problems[0].n_edges > 0 && problems[n - 1].n_edges > 0 && host_is_pinned(obs_of(problems[0])) &&
+                        host_is_pinned(obs_of(problems[n - 1]));
     int g;
     if (getenv("VISFS_BA_DIRECT_GROUPS") || (pinned && share < 16 && !getenv("VISFS_BA_NO_DIRECT"))) {
         *direct = true;

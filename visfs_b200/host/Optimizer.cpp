@@ -186,11 +186,11 @@ bool Optimizer::marshal(std::size_t _rootId,
             if (cit == poseIndex.end()) continue;                         // :172
             const FeatureBA & pt = jter->second;
             const double depth = pt.depth;                                // :174
-            double obs[3] = {pt.kpt.pt.x, pt.kpt.pt.y, 0.0};
+            float obs[3] = {pt.kpt.pt.x, pt.kpt.pt.y, 0.0f};
             uint8_t kind = VISFS_BA_EDGE_MONO;
             if (std::isfinite(depth) && depth > 0.0 && baseLine > 0.0) {  // :184
                 const float disparity = static_cast<float>(baseLine * K(0, 0) / depth);   // :187
-                obs[2] = pt.kpt.pt.x - disparity;                         // :188  (float - float, widened)
+                obs[2] = pt.kpt.pt.x - disparity;                         // :188  (float - float; the device widens it)
                 kind = VISFS_BA_EDGE_STEREO;
             }
             // else: the reference's mono branch is commented out (:197-208) and its live code is undefined
@@ -250,7 +250,8 @@ std::map<std::size_t, Eigen::Isometry3d> Optimizer::localOptimize(
         prob.n_edges = static_cast<int32_t>(m.edge_pose.size());
         prob.pose_tq = m.pose_tq.data(); prob.pose_id = m.pose_id.data(); prob.pose_fixed = m.pose_fixed.data();
         prob.point_xyz = m.point_xyz.data(); prob.point_id = m.point_id.data(); prob.point_fixed = m.point_fixed.data();
-        prob.edge_obs = m.edge_obs.data(); prob.edge_pose = m.edge_pose.data(); prob.edge_point = m.edge_point.data();
+        prob.edge_obs = nullptr; prob.edge_obs_f32 = m.edge_obs.data();   // 12 instead of 24 bytes per edge over PCIe, nothing lost
+        prob.edge_pose = m.edge_pose.data(); prob.edge_point = m.edge_point.data();
         prob.edge_kind = m.edge_kind.data();
         prob.fx = m.fx; prob.fy = m.fy; prob.cx = m.cx; prob.cy = m.cy; prob.bf = m.bf;
         prob.pixel_variance = pixelVariance_;                   // :153

@@ -86,7 +86,7 @@ struct MarshalledWindow {
     HostArray<double> point_xyz;        // [L][3]
     HostArray<int64_t> point_id;        // feature ids that got a vertex (Optimizer.cpp:158), ascending
     HostArray<uint8_t> point_fixed;
-    HostArray<double> edge_obs;         // [E][3]
+    HostArray<float> edge_obs;          // [E][3] u, v, u_right: floats, as the reference builds them (Optimizer.cpp:187-188)
     HostArray<int32_t> edge_pose, edge_point;
     HostArray<uint8_t> edge_kind;
     double fx = 0, fy = 0, cx = 0, cy = 0, bf = 0;

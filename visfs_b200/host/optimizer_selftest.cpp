@@ -89,7 +89,9 @@ int main(int argc, char **argv) {
         const bool ok = Optimizer::Optimizer::marshal((std::size_t)rootId, poses, cameraModels, points3D, wordReferences, m);
         wr<int64_t>(out, ok ? 1 : 0);
         wrv(out, m.pose_tq); wrv(out, m.pose_id); wrv(out, m.pose_fixed); wrv(out, m.point_xyz); wrv(out, m.point_id);
-        wrv(out, m.point_fixed); wrv(out, m.edge_obs); wrv(out, m.edge_pose); wrv(out, m.edge_point); wrv(out, m.edge_kind);
+        wrv(out, m.point_fixed);
+        { std::vector<double> wide(m.edge_obs.begin(), m.edge_obs.end()); wrv(out, wide); }   // (floats, dumped widened)
+        wrv(out, m.edge_pose); wrv(out, m.edge_point); wrv(out, m.edge_kind);
         const std::vector<double> intr{m.fx, m.fy, m.cx, m.cy, m.bf};
         wrv(out, intr);
         return 0;
