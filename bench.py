@@ -430,11 +430,11 @@ def run_gpu(args):
                     "d2h_bytes_per_step": int(t_e2e["d2h_bytes"]), "ms_per_step": 1e3 * e2e_s / args.steps},
             "gpu_launches": int(sum(t["kernel_launches"] for t in tims)),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": traffic, "kernel": "k_build<MODE_BUILD> (linearise + Hessian blocks + Schur partials)",
+                         "traffic": traffic, "kernel": "ws::k_build_ws (linearise + Hessian blocks + Schur partials; k_build<MODE_BUILD> is its fallback for 20-32 poses)",
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                          "alg_bytes_per_launch": alg_build / max(build_n, 1), "avg_launch_ms": build_ms / max(build_n, 1),
                          "note": "the kernel sits right of the FP64 ridge (28 flop/B): the binding roofline is the FP64 pipe, see the fp64 object"},
-            "fp64": {"kernel": "k_build<MODE_BUILD>", "achieved_tflops": fp64_achieved, "peak_tflops": fp64_peak,
+            "fp64": {"kernel": "ws::k_build_ws", "achieved_tflops": fp64_achieved, "peak_tflops": fp64_peak,
                      "frac": fp64_achieved / fp64_peak if fp64_peak else None,
                      "peak_source": "visfs_ba_probe_fp64: dependent-free DFMA loop, this process, this GPU"},
             "kernel_ms_per_step": {k: sum(t[k] for t in tims) / args.steps for k in ("build_ms", "solve_ms", "update_ms", "other_ms")},

@@ -10,7 +10,7 @@ from visfs_b200 import capi, synth  # noqa: E402
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 ws = synth.config_c3_windows(n)
 ba = capi.BundleAdjuster(0)
-packed = ba.prepare_batch(ws, pinned=True)
+packed = ba.prepare_batch(ws, pinned=True, float_obs=True)
 for direct in (False, True):
     if direct:
         os.environ["VISFS_BA_DIRECT_GROUPS"] = "1"
