@@ -9,14 +9,16 @@ from visfs_b200 import capi, synth  # noqa: E402
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 ws = synth.config_c3_windows(n)
 ba = capi.BundleAdjuster(0)
-packed = ba.prepare_batch(ws)
-for ramp, g in ((1.0, 16), (1.0, 32), (1.1, 16), (1.22, 8), (1.22, 16), (1.22, 24), (1.3, 16)):
-    os.environ["VISFS_BA_RAMP"] = str(ramp)
-    os.environ["VISFS_BA_GROUPS"] = str(g)
-    for _ in range(2):
-        ba.solve_packed(packed)
-    t0 = time.perf_counter()
-    for _ in range(4):
-        ba.solve_packed(packed)
-    dt = (time.perf_counter() - t0) / 4
-    print(f"ramp {ramp:4.2f} groups {g:2d}: {1e3 * dt:7.2f} ms per batch of {n} windows", flush=True)
+packed = ba.prepare_batch(ws, pinned=True, float_obs=True)
+for rep in range(2):
+    for ramp, flat, g in ((1.22, 99, 16), (1.22, 12, 16), (1.22, 10, 20), (1.22, 10, 24), (1.3, 8, 20), (1.15, 99, 16), (1.22, 99, 20)):
+        os.environ["VISFS_BA_RAMP"] = str(ramp)
+        os.environ["VISFS_BA_RAMP_FLAT"] = str(flat)
+        os.environ["VISFS_BA_GROUPS"] = str(g)
+        for _ in range(2):
+            ba.solve_packed(packed)
+        t0 = time.perf_counter()
+        for _ in range(6):
+            ba.solve_packed(packed)
+        dt = (time.perf_counter() - t0) / 6
+        print(f"ramp {ramp:4.2f} flat {flat:2d} groups {g:2d}: {1e3 * dt:7.2f} ms per batch of {n} windows", flush=True)
