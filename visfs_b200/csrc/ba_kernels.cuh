@@ -544,7 +544,8 @@ __global__ void k_struct_pose(Batch B) {
 
 // per landmark: count landmarks in the Hessian; covisibility rows through ALL edges of the landmark
 // (g2o walks v->edges(), which still holds level-1 edges in pass 2)
-__global__ void k_struct_count(Batch B) {
+// (want_covis: only visfs_ba_structure_build exports the pattern; the solve paths treat every pose pair as a block)
+__global__ void k_struct_count(Batch B, int want_covis) {
     const int w = blockIdx.y;
     const WinDesc &wd = B.win[w];
     LMState &st = B.st[w];
@@ -554,7 +555,7 @@ __global__ void k_struct_count(Batch B) {
         const int gl = wd.point_off + l;
         if (!(B.lm_flags[gl] & kInHessian)) continue;
         ++cnt;
-        if (wd.large) continue;
+        if (wd.large || !want_covis) continue;
         unsigned mask = 0;
         for (int e = B.lm_edge_off[gl]; e < B.lm_edge_off[gl + 1]; ++e) {
             const int hi = B.pose_hidx[wd.pose_off + (B.edge_pose[e] & kPoseMask)];

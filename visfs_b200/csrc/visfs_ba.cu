@@ -567,7 +567,7 @@ int reset_state(visfs_ba_handle *h) {
     return VISFS_BA_OK;
 }
 
-int run_structure(visfs_ba_handle *h) {
+int run_structure(visfs_ba_handle *h, bool want_covis = false) {
     Batch &B = h->batch;
     cudaStream_t s = h->stream;
     CK(cudaMemsetAsync(h->d_pose_active.p, 0, sizeof(int) * std::max(h->tot_pose, 1), s));
@@ -575,7 +575,7 @@ int run_structure(visfs_ba_handle *h) {
     const int gw = (h->n_win + 127) / 128;
     k_struct_lm<<<glm, 256, 0, s>>>(B);
     k_struct_pose<<<gw, 128, 0, s>>>(B);
-    k_struct_count<<<glm, 256, 0, s>>>(B);
+    k_struct_count<<<glm, 256, 0, s>>>(B, want_covis ? 1 : 0);
     k_struct_finish<<<gw, 128, 0, s>>>(B);
     CK(cudaGetLastError());
     h->launches += 4;
@@ -783,7 +783,7 @@ int run_structure_large(visfs_ba_handle *h) {
     k_struct_lm<<<glm, 256, 0, s>>>(B);
     if ((st = allreduce(h, h->d_pose_active.p, (size_t)h->tot_pose, ncclInt32, ncclMax))) return st;
     k_struct_pose<<<1, 128, 0, s>>>(B);
-    k_struct_count<<<glm, 256, 0, s>>>(B);
+    k_struct_count<<<glm, 256, 0, s>>>(B, 0);
     k_struct_finish<<<1, 128, 0, s>>>(B);
     if (h->partitioned && h->comm_ranks > 1) {   // landmarks in the Hessian: sum over ranks; device-side error: any rank
         lg::k_get_counts<<<1, 32, 0, s>>>(B, h->d_cnt.as<int>());
@@ -1397,7 +1397,7 @@ int visfs_ba_structure_build(visfs_ba_handle *h, const visfs_ba_problem *problem
     }
     k_begin_pass<<<1, 128, 0, s>>>(h->batch, 0);
     CK(h->h_small.reserve(64));
-    st = h->large ? run_structure_large(h) : run_structure(h);
+    st = h->large ? run_structure_large(h) : run_structure(h, true);
     if (st) return st;
     // landmark hessian indices: exclusive scan of the in-Hessian flags
     const int cap = std::max(out->schur_capacity, 0);
