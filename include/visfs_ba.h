@@ -55,11 +55,15 @@
  * Conventions
  *   - poses are T_camera<-world, stored t(3) then quaternion x,y,z,w  (CameraPose::toVector,
  *     OptimizeTypeDefine.h:57-67); `pose_id` strictly ascending (std::map order of
- *     Optimizer.cpp:100).
+ *     Optimizer.cpp:100).  Like the CameraPose constructor (OptimizeTypeDefine.h:36-41) the library forces
+ *     w >= 0 and unit norm on every input quaternion, and like g2o::SE3Quat on every odometry measurement
+ *     (link_tq): the sign of a quaternion the caller passes never changes a result.
  *   - points are world-frame xyz; `point_id` strictly ascending (Optimizer.cpp:156).
  *   - edges in g2o insertion order: grouped by point, ascending pose inside a point
  *     (Optimizer.cpp:156-169).  Unsorted edge lists are accepted and stably sorted on
  *     the device by (point, pose); all per-edge outputs are in the CALLER's edge order.
+ *     At most ONE edge per (point, pose) pair — the reference's std::map<pose id, FeatureBA> per feature
+ *     (Optimizer.h:52) cannot hold two; a duplicate is rejected with VISFS_BA_ERR_INVALID.
  *   - edge_obs = (u, v, u_right) as built at Optimizer.cpp:187-188; u_right is ignored
  *     for mono edges (edge_kind == VISFS_BA_EDGE_MONO).
  *   - every function returns a visfs_ba_status; on error visfs_ba_last_error() has text.
@@ -240,6 +244,16 @@ int visfs_ba_structure_build(visfs_ba_handle *h, const visfs_ba_problem *problem
 int visfs_ba_debug_trial(visfs_ba_handle *h, const visfs_ba_problem *problem, double lambda, double *S_dense,
                          double *b_s, double *x_pose, double *trial_points, int32_t *n_out, double *chi2_out,
                          double *lambda_out, double *trial_chi2_out);
+
+/* parity / debug: the device functions of the product path on caller-supplied operands, so that tests can hold them to
+ * the reference's own compiled code (oracle/_ref).  CameraPose::update + deltaQ (OptimizeTypeDefine.cpp:7-14,
+ * Math.h:277-287) of n poses: tq_in [n][7], delta [n][6] -> tq_out [n][7]. */
+int visfs_ba_debug_pose_oplus(visfs_ba_handle *h, int32_t n, const double *tq_in, const double *delta, double *tq_out);
+/* EdgePoseConstraint::computeError / linearizeOplus (OptimizeTypeDefine.cpp:35-72) of n (from, to, measurement) triples,
+ * each [n][7]; the measurement is used as given (the solve path normalises it like g2o::SE3Quat first).
+ * err [n][6], J_from / J_to [n][6][6] row-major. */
+int visfs_ba_debug_link_linearize(visfs_ba_handle *h, int32_t n, const double *from_tq, const double *to_tq,
+                                  const double *meas_tq, double *err, double *J_from, double *J_to);
 
 /* resident-window API: upload once, run the device LM any number of times, download */
 int visfs_ba_upload(visfs_ba_handle *h, int32_t n, const visfs_ba_problem *problems);

@@ -4,9 +4,13 @@
 // It is used by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
 // leg as the checker and as the timed CPU baseline ("g2o-equivalent port").
 //
-// PARITY UNPINNED: the reference ships no golden vectors, known-answer tests or fixtures for
-// this path and neither g2o nor Eigen is available in the build container,
-// so this file cannot be validated against a run of the reference itself.  It follows
+// PARITY, WHAT IS PINNED AND WHAT IS NOT.  The reference ships no golden vectors, known-answer tests or fixtures
+// for this path, and g2o / Eigen are absent from the build container, so Optimizer.cpp itself
+// cannot be built here.  Since round 2 the reference's OWN per-edge / per-vertex arithmetic IS executed here: its
+// unmodified OptimizeTypeDefine.{h,cpp} + Math.h compile against a minimal Eigen / g2o-base-class stand-in
+// (oracle/ref_stub, oracle/ref_shim.cpp -> oracle/_ref/libvisfs_ref.so), and tests/test_ref_pin.py holds this file to
+// it: rows (1)-(3) below and EdgePoseConstraint are REFERENCE-PINNED.  Rows (4)-(5) — g2o's optimiser semantics and the
+// driver protocol of Optimizer.cpp — remain a restatement: PARITY UNPINNED for those.  It follows
 //   (1) corelib/include/Optimizer/g2o/OptimizeTypeDefine.h:16-191 — CameraPose, VertexPose, EdgeStereo
 //   (2) corelib/src/Optimizer/g2o/OptimizeTypeDefine.cpp:7-14     — CameraPose::update
 //   (3) utilite/include/Math.h:277-287                            — deltaQ
@@ -276,9 +280,18 @@ struct Oracle {
     std::vector<double> Hpp, Hll, Hpl, b, x, S, bs, Dinv, coeff;
     std::vector<double> diagBackupP, diagBackupL;
 
+    // CameraPose::normalizeRotation (OptimizeTypeDefine.h:36-41), run by the CameraPose constructors of Optimizer.cpp:109;
+    // g2o::SE3Quat::normalizeRotation does the same to an odometry measurement (Optimizer.cpp:140): w >= 0, unit norm.
+    static void normalizeRotation(double *q /* x y z w */) {
+        if (q[3] < 0) for (int i = 0; i < 4; ++i) q[i] *= -1;
+        const double n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+        for (int i = 0; i < 4; ++i) q[i] /= n;
+    }
+
     void load(const visfs_ba_problem *p) {
         P = p->n_poses; L = p->n_points; E = p->n_edges;
         pose.assign(p->pose_tq, p->pose_tq + 7 * (size_t)P);
+        for (int i = 0; i < P; ++i) normalizeRotation(&pose[7 * (size_t)i + 3]);
         point.assign(p->point_xyz, p->point_xyz + 3 * (size_t)L);
         if (p->edge_obs_f32) { obs.resize(3 * (size_t)E); for (size_t i = 0; i < obs.size(); ++i) obs[i] = (double)p->edge_obs_f32[i]; }
         else obs.assign(p->edge_obs, p->edge_obs + 3 * (size_t)E);
@@ -294,6 +307,7 @@ struct Oracle {
         if (NK > 0) {
             lkFrom.assign(p->link_from, p->link_from + NK); lkTo.assign(p->link_to, p->link_to + NK);
             lkM.assign(p->link_tq, p->link_tq + 7 * (size_t)NK);
+            for (int k = 0; k < NK; ++k) normalizeRotation(&lkM[7 * (size_t)k + 3]);
             ov = p->odometry_variance;
         }
     }
@@ -945,6 +959,17 @@ int oracle_link_linearize(const visfs_ba_problem *p, double *err /* [K][6] */, d
         linkJacobians(a, b, m, J1, J2);
         if (Ji) std::memcpy(Ji + 36 * (size_t)k, J1, sizeof J1);
         if (Jj) std::memcpy(Jj + 36 * (size_t)k, J2, sizeof J2);
+    }
+    return VISFS_BA_OK;
+}
+
+// CameraPose::update of n poses (parity hook against the reference's own compiled code, oracle/ref_shim.cpp)
+int oracle_pose_oplus(int n, const double *tq_in /* [n][7] */, const double *delta /* [n][6] */, double *tq_out) {
+    for (int i = 0; i < n; ++i) {
+        double tq[7];
+        std::memcpy(tq, tq_in + 7 * (size_t)i, sizeof tq);
+        poseOplus(tq, delta + 6 * (size_t)i);
+        std::memcpy(tq_out + 7 * (size_t)i, tq, sizeof tq);
     }
     return VISFS_BA_OK;
 }

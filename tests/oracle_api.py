@@ -34,6 +34,7 @@ def lib(omp=False):
         l.oracle_reduced_system.argtypes = [C.POINTER(capi.Problem), C.c_double, capi._dp, capi._dp, capi._dp,
                                             C.POINTER(C.c_int32), capi._dp, capi._dp]
         l.oracle_link_linearize.argtypes = [C.POINTER(capi.Problem), capi._dp, capi._dp, capi._dp]
+        l.oracle_pose_oplus.argtypes = [C.c_int, capi._dp, capi._dp, capi._dp]
         _libs[name] = l
     return _libs[name]
 
@@ -110,3 +111,12 @@ def link_linearize(w):
     err, Ji, Jj = np.zeros((K, 6)), np.zeros((K, 6, 6)), np.zeros((K, 6, 6))
     lib().oracle_link_linearize(C.byref(p), capi._ptr(err, capi._dp), capi._ptr(Ji, capi._dp), capi._ptr(Jj, capi._dp))
     return dict(error=err, J_from=Ji, J_to=Jj)
+
+
+def pose_oplus(tq, delta):
+    """CameraPose::update of every row (the oracle's restatement of OptimizeTypeDefine.cpp:7-14)."""
+    tq = np.ascontiguousarray(tq, dtype=np.float64)
+    delta = np.ascontiguousarray(delta, dtype=np.float64)
+    out = np.zeros_like(tq)
+    lib().oracle_pose_oplus(len(tq), capi._ptr(tq, capi._dp), capi._ptr(delta, capi._dp), capi._ptr(out, capi._dp))
+    return out

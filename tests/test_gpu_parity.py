@@ -346,6 +346,13 @@ def test_malformed_problems_are_rejected_with_a_message_and_the_handle_survives(
     bad("edge index out of range", edge_pose=poke(0, -1))
     bad("edge index out of range", edge_point=poke(3, 120))
     bad("pixel_variance", pixel_variance=0.0)
+    # one observation per (point, pose): a repeated edge in a sorted list, and in an unsorted one (found after
+    # the device sort), is refused instead of racing in the per-pose accumulators
+    bad("duplicate", edge_pose=poke(1, int(good["edge_pose"][0])))
+    perm = np.random.default_rng(3).permutation(int(good["n_edges"]))
+    dup = {k: good[k][perm].copy() for k in ("edge_obs", "edge_pose", "edge_point", "edge_kind")}
+    dup["edge_pose"][5], dup["edge_point"][5] = dup["edge_pose"][400], dup["edge_point"][400]
+    bad("duplicate", **dup)
     bad("pose_id not strictly ascending", pose_id=poke(2, int(good["pose_id"][1])))
     bad("point_id not strictly ascending", point_id=poke(10, int(good["point_id"][9])))
     linked = synth.make_window(5, 120, layout="all", seed=910, links="chain")

@@ -78,7 +78,7 @@ EXPORTS = ["visfs_ba_abi_version", "visfs_ba_create", "visfs_ba_destroy", "visfs
            "visfs_ba_solve_batch", "visfs_ba_linearize", "visfs_ba_structure_build", "visfs_ba_upload",
            "visfs_ba_run_resident", "visfs_ba_download", "visfs_ba_get_timing", "visfs_ba_comm_unique_id",
            "visfs_ba_comm_init", "visfs_ba_comm_destroy", "visfs_ba_probe_fp64", "visfs_ba_debug_trial",
-           "visfs_ba_host_alloc", "visfs_ba_host_free"]
+           "visfs_ba_host_alloc", "visfs_ba_host_free", "visfs_ba_debug_pose_oplus", "visfs_ba_debug_link_linearize"]
 
 
 def _ptr(a, typ):
@@ -222,6 +222,8 @@ def load_library(path=LIB_PATH):
     lib.visfs_ba_probe_fp64.argtypes = [C.c_void_p, _dp]
     lib.visfs_ba_debug_trial.argtypes = [C.c_void_p, C.POINTER(Problem), C.c_double, _dp, _dp, _dp, _dp,
                                          C.POINTER(C.c_int32), _dp, _dp, _dp]
+    lib.visfs_ba_debug_pose_oplus.argtypes = [C.c_void_p, C.c_int32, _dp, _dp, _dp]
+    lib.visfs_ba_debug_link_linearize.argtypes = [C.c_void_p, C.c_int32, _dp, _dp, _dp, _dp, _dp, _dp]
     lib.visfs_ba_host_alloc.argtypes = [C.c_size_t]
     lib.visfs_ba_host_alloc.restype = C.c_void_p
     lib.visfs_ba_host_free.argtypes = [C.c_void_p]
@@ -404,6 +406,21 @@ class BundleAdjuster:
         nn = n.value
         return dict(n=nn, S=S[: nn * nn].reshape(nn, nn).copy(), b_s=bs[:nn].copy(), x_pose=xp[:nn].copy(), trial_points=tp,
                     chi2=chi2.value, lambda_used=lam_out.value, trial_chi2=tchi.value)
+
+    def debug_pose_oplus(self, tq, delta):
+        tq = np.ascontiguousarray(tq, dtype=np.float64)
+        delta = np.ascontiguousarray(delta, dtype=np.float64)
+        out = np.zeros_like(tq)
+        self._check(self.lib.visfs_ba_debug_pose_oplus(self.h, len(tq), _ptr(tq, _dp), _ptr(delta, _dp), _ptr(out, _dp)))
+        return out
+
+    def debug_link_linearize(self, from_tq, to_tq, meas_tq):
+        a, b, m = (np.ascontiguousarray(x, dtype=np.float64) for x in (from_tq, to_tq, meas_tq))
+        n = len(a)
+        err, Ji, Jj = np.zeros((n, 6)), np.zeros((n, 6, 6)), np.zeros((n, 6, 6))
+        self._check(self.lib.visfs_ba_debug_link_linearize(self.h, n, _ptr(a, _dp), _ptr(b, _dp), _ptr(m, _dp), _ptr(err, _dp),
+                                                           _ptr(Ji, _dp), _ptr(Jj, _dp)))
+        return dict(error=err, J_from=Ji, J_to=Jj)
 
     def probe_fp64(self):
         v = C.c_double()

@@ -371,9 +371,16 @@ __global__ void k_control_init(Batch B) {
         st.ni = 2.0;
         st.iter = 0; st.qmax = 0;
         st.pcg_residual = -1.0;
-        if (st.F + st.NL == 0) finish_pass(st, VISFS_BA_STOP_EMPTY, B.n_running);
+        if (st.err != 0) finish_pass(st, VISFS_BA_STOP_NOT_RUN, B.n_running);   // rejected by the structure kernels: no trial runs
+        else if (st.F + st.NL == 0) finish_pass(st, VISFS_BA_STOP_EMPTY, B.n_running);
         else if (wd.max_iter <= 0) finish_pass(st, VISFS_BA_STOP_ITERATIONS, B.n_running);
     }
+}
+
+// adjacent equal keys of the sorted (window, point, pose) list = duplicate edges
+__global__ void k_dup_keys(const unsigned long long *keys, int n, int *flag) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x + 1; i < n; i += gridDim.x * blockDim.x)
+        if (keys[i] == keys[i - 1]) *flag = 1;
 }
 
 __global__ void k_control(Batch B) {
@@ -607,6 +614,10 @@ __global__ void k_reset(Batch B, const double *pose_in /*[tot_pose][7]*/, const 
     for (int p = t0; p < B.tot_pose; p += stride) {
         double rec[kPoseStride];
         for (int k = 0; k < 7; ++k) rec[k] = pose_in[7 * (size_t)p + k];
+        // CameraPose::normalizeRotation (OptimizeTypeDefine.h:36-41), run by the constructor at Optimizer.cpp:109
+        if (rec[6] < 0.0) for (int k = 3; k < 7; ++k) rec[k] = -rec[k];
+        const double qn = sqrt(rec[3] * rec[3] + rec[4] * rec[4] + rec[5] * rec[5] + rec[6] * rec[6]);
+        for (int k = 3; k < 7; ++k) rec[k] /= qn;
         quat_to_R(rec + 3, rec + 7);
         for (int k = 0; k < kPoseStride; ++k) {
             B.pose[(size_t)p * kPoseStride + k] = rec[k];

@@ -636,7 +636,8 @@ __global__ void k_control_init_large(Batch B, const double *scal) {
         st.ni = 2.0;
         st.iter = 0; st.qmax = 0;
         st.pcg_residual = -1.0;
-        if (st.F + st.NL == 0) finish_pass(st, VISFS_BA_STOP_EMPTY, B.n_running);
+        if (st.err != 0) finish_pass(st, VISFS_BA_STOP_NOT_RUN, B.n_running);
+        else if (st.F + st.NL == 0) finish_pass(st, VISFS_BA_STOP_EMPTY, B.n_running);
         else if (wd.max_iter <= 0) finish_pass(st, VISFS_BA_STOP_ITERATIONS, B.n_running);
     }
 }

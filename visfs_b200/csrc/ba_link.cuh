@@ -161,4 +161,26 @@ __device__ __forceinline__ double link_chi2_block(const Batch &B, const WinDesc 
     return block_sum(acc, scratch);
 }
 
+
+// parity hooks (visfs_ba_debug_pose_oplus / visfs_ba_debug_link_linearize): the device functions of the product path on
+// caller-supplied operands, checked against the reference's own compiled code (tests/test_gpu_ref_pin.py)
+__global__ void k_debug_pose_oplus(int n, const double *tq_in, const double *delta, double *tq_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double src[7], rec[kPoseStride];
+    for (int k = 0; k < 7; ++k) src[k] = tq_in[7 * (size_t)i + k];
+    pose_oplus(src, delta + 6 * (size_t)i, rec);
+    for (int k = 0; k < 7; ++k) tq_out[7 * (size_t)i + k] = rec[k];
+}
+
+__global__ void k_debug_link(int n, const double *from_tq, const double *to_tq, const double *meas_tq, double *err, double *Ji, double *Jj) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    double e[6], A[36], Bm[36];
+    link_error(from_tq + 7 * (size_t)k, to_tq + 7 * (size_t)k, meas_tq + 7 * (size_t)k, e);
+    link_jacobians(from_tq + 7 * (size_t)k, to_tq + 7 * (size_t)k, meas_tq + 7 * (size_t)k, A, Bm);
+    for (int i = 0; i < 6; ++i) err[6 * (size_t)k + i] = e[i];
+    for (int i = 0; i < 36; ++i) { Ji[36 * (size_t)k + i] = A[i]; Jj[36 * (size_t)k + i] = Bm[i]; }
+}
+
 }  // namespace visfs

@@ -41,6 +41,10 @@ struct DevBuf {
     }
     template <typename T> T *as() const { return static_cast<T *>(p); }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }   // locals of the debug / structure entry points are freed on every early return
 };
 
 struct PinBuf {
@@ -57,6 +61,10 @@ struct PinBuf {
     }
     template <typename T> T *as() const { return static_cast<T *>(p); }
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    PinBuf() = default;
+    PinBuf(const PinBuf &) = delete;
+    PinBuf &operator=(const PinBuf &) = delete;
+    ~PinBuf() { release(); }
 };
 
 enum { EV_BUILD = 0, EV_SOLVE = 1, EV_UPDATE = 2, EV_OTHER = 3, EV_CLASSES = 4 };
@@ -199,9 +207,14 @@ int validate(visfs_ba_handle *h, const visfs_ba_problem &p, int idx, bool *sorte
     unsigned oob = 0;
     for (int e = 0; e < p.n_edges; ++e) oob |= (unsigned)((unsigned)ep[e] >= nP) | (unsigned)((unsigned)el[e] >= nL);
     if (oob) return bad("edge index out of range");
-    unsigned unsorted = 0;
-    for (int e = 1; e < p.n_edges; ++e)
-        unsorted |= (unsigned)(el[e] < el[e - 1]) | ((unsigned)(el[e] == el[e - 1]) & (unsigned)(ep[e] <= ep[e - 1]));
+    unsigned unsorted = 0, dup = 0;
+    for (int e = 1; e < p.n_edges; ++e) {
+        unsorted |= (unsigned)(el[e] < el[e - 1]) | ((unsigned)(el[e] == el[e - 1]) & (unsigned)(ep[e] < ep[e - 1]));
+        dup |= (unsigned)(el[e] == el[e - 1]) & (unsigned)(ep[e] == ep[e - 1]);
+    }
+    // one observation per (point, pose): the reference's std::map<pid, FeatureBA> per feature cannot hold two
+    // (Optimizer.h:52), and the kernels give every pose of a landmark its own accumulator
+    if (dup) return bad("duplicate (point, pose) edge");
     const bool srt = unsorted == 0;
     int maxrun = p.n_edges > 0 ? 1 : 0;
     if (srt) {
@@ -395,7 +408,12 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs) {
             const WinDesc &d = h->win[w];
             for (int k = 0; k < p.n_links; ++k) {
                 lw[(size_t)d.link_off + k] = w; lf[(size_t)d.link_off + k] = p.link_from[k]; lt[(size_t)d.link_off + k] = p.link_to[k];
-                memcpy(&lm[7 * ((size_t)d.link_off + k)], p.link_tq + 7 * (size_t)k, 7 * sizeof(double));
+                double *m = &lm[7 * ((size_t)d.link_off + k)];
+                memcpy(m, p.link_tq + 7 * (size_t)k, 7 * sizeof(double));
+                // g2o::SE3Quat::normalizeRotation, run by the constructor the measurement goes through at Optimizer.cpp:140
+                if (m[6] < 0.0) for (int i = 3; i < 7; ++i) m[i] = -m[i];
+                const double qn = std::sqrt(m[3] * m[3] + m[4] * m[4] + m[5] * m[5] + m[6] * m[6]);
+                for (int i = 3; i < 7; ++i) m[i] /= qn;
             }
         }
         CK(h->d_link_win.reserve(sizeof(int) * (size_t)tk)); CK(h->d_link_from.reserve(sizeof(int) * (size_t)tk));
@@ -513,7 +531,13 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs) {
         CK(h->d_tmp.reserve(tmp_bytes));
         CK(cub::DeviceRadixSort::SortPairs(h->d_tmp.p, tmp_bytes, h->d_keys.as<unsigned long long>(), h->d_keys2.as<unsigned long long>(),
                                            h->d_perm.as<int>(), h->d_edge_orig.as<int>(), (int)te, 0, 64, s));
+        // duplicates of an unsorted list are adjacent after the sort
+        CK(cudaMemsetAsync(h->d_n_running.as<int>() + 1, 0, sizeof(int), s));
+        k_dup_keys<<<std::max(1, std::min(((int)te + 255) / 256, 1024)), 256, 0, s>>>(h->d_keys2.as<unsigned long long>(), (int)te, h->d_n_running.as<int>() + 1);
+        int n_dup = 0;
+        CK(cudaMemcpyAsync(&n_dup, h->d_n_running.as<int>() + 1, sizeof(int), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));  // host vectors above go out of scope
+        if (n_dup) return h->fail(VISFS_BA_ERR_INVALID, "duplicate (point, pose) edge in an unsorted edge list");
         perm = h->d_edge_orig.as<int>();
     }
     h->batch = make_batch(h);
@@ -1097,6 +1121,13 @@ int download(visfs_ba_handle *h, int n, visfs_ba_result *res) {
         if (st.stop[1] == VISFS_BA_STOP_NOT_RUN) { r.n_free_poses[1] = r.n_free_points[1] = 0; r.lambda_final[1] = 0; }
         r.chi2_initial = st.chi_initial; r.chi2_pass1 = st.chi_pass[0]; r.chi2_final = st.chi_pass[1];
         r.chi2_last_trial = st.chi_last_trial;
+        if (st.status == VISFS_BA_ERR_UNSUPPORTED || st.status == VISFS_BA_ERR_INVALID || st.status == VISFS_BA_ERR_CUDA) {
+            char buf[200];   // failures found on the device (k_struct_lm's degree check, ...): leave text for visfs_ba_last_error
+            snprintf(buf, sizeof buf, "problem %d: rejected on the device with status %d (%s)", h->idx_base + w, st.status,
+                     st.status == VISFS_BA_ERR_UNSUPPORTED ? "a landmark is observed by more poses than the kernels hold: 192 per small window, 32 per large window"
+                                                           : "device-side check");
+            h->error = buf;
+        }
     }
     return VISFS_BA_OK;
 }
@@ -1471,8 +1502,7 @@ int visfs_ba_structure_build(visfs_ba_handle *h, const visfs_ba_problem *problem
         }
         CK(cudaMemcpyAsync(d_cnt, &nuniq, sizeof(int), cudaMemcpyHostToDevice, s));
         CK(cudaStreamSynchronize(s));
-        pc.release(); po.release(); kb.release(); kb2.release(); t2.release();
-    }
+        }
     CK(cudaGetLastError());
     std::vector<LMState> sth(1);
     CK(cudaMemcpyAsync(sth.data(), h->d_st.p, sizeof(LMState), cudaMemcpyDeviceToHost, s));
@@ -1518,6 +1548,10 @@ int visfs_ba_debug_trial(visfs_ba_handle *h, const visfs_ba_problem *problem, do
     CK(h->h_small.reserve(64));
     LMState before;
     DevBuf dbg;
+    struct DbgGuard {   // the damping / capture overrides never outlive this call, whichever way it returns
+        visfs_ba_handle *h;
+        ~DbgGuard() { h->batch.dbg = nullptr; h->batch.dbg_lambda = -1.0; h->batch_ctl.dbg = nullptr; h->batch_ctl.dbg_lambda = -1.0; }
+    } dbg_guard{h};
     const int nmax = 6 * h->tot_pose;
     const size_t ntri_max = (size_t)nmax * (nmax + 1) / 2;
     std::vector<double> denseS, denseB;
@@ -1586,6 +1620,43 @@ int visfs_ba_debug_trial(visfs_ba_handle *h, const visfs_ba_problem *problem, do
     if (lambda_out) *lambda_out = (lambda >= 0.0) ? lambda : before.lambda;
     if (trial_chi2_out) *trial_chi2_out = after.chi_last_trial;
     dbg.release();
+    return VISFS_BA_OK;
+}
+
+int visfs_ba_debug_pose_oplus(visfs_ba_handle *h, int32_t n, const double *tq_in, const double *delta, double *tq_out) {
+    if (!h) return VISFS_BA_ERR_INVALID;
+    if (n <= 0 || !tq_in || !delta || !tq_out) return h->fail(VISFS_BA_ERR_INVALID, "debug_pose_oplus: bad arguments");
+    CK(cudaSetDevice(h->device));
+    DevBuf buf;
+    CK(buf.reserve(sizeof(double) * 20 * (size_t)n));
+    double *d_in = buf.as<double>(), *d_delta = d_in + 7 * (size_t)n, *d_out = d_delta + 6 * (size_t)n;
+    CK(cudaMemcpyAsync(d_in, tq_in, sizeof(double) * 7 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_delta, delta, sizeof(double) * 6 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    k_debug_pose_oplus<<<(n + 63) / 64, 64, 0, h->stream>>>(n, d_in, d_delta, d_out);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(tq_out, d_out, sizeof(double) * 7 * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return VISFS_BA_OK;
+}
+
+int visfs_ba_debug_link_linearize(visfs_ba_handle *h, int32_t n, const double *from_tq, const double *to_tq, const double *meas_tq,
+                                  double *err, double *J_from, double *J_to) {
+    if (!h) return VISFS_BA_ERR_INVALID;
+    if (n <= 0 || !from_tq || !to_tq || !meas_tq || !err || !J_from || !J_to) return h->fail(VISFS_BA_ERR_INVALID, "debug_link_linearize: bad arguments");
+    CK(cudaSetDevice(h->device));
+    DevBuf buf;
+    const size_t N = (size_t)n;
+    CK(buf.reserve(sizeof(double) * (21 + 6 + 72) * N));
+    double *d_a = buf.as<double>(), *d_b = d_a + 7 * N, *d_m = d_b + 7 * N, *d_e = d_m + 7 * N, *d_ji = d_e + 6 * N, *d_jj = d_ji + 36 * N;
+    CK(cudaMemcpyAsync(d_a, from_tq, sizeof(double) * 7 * N, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_b, to_tq, sizeof(double) * 7 * N, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_m, meas_tq, sizeof(double) * 7 * N, cudaMemcpyHostToDevice, h->stream));
+    k_debug_link<<<(n + 63) / 64, 64, 0, h->stream>>>(n, d_a, d_b, d_m, d_e, d_ji, d_jj);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(err, d_e, sizeof(double) * 6 * N, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(J_from, d_ji, sizeof(double) * 36 * N, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(J_to, d_jj, sizeof(double) * 36 * N, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
     return VISFS_BA_OK;
 }
 

@@ -63,11 +63,13 @@ Eigen::Isometry3d stateToIsometry(const double * tq) {
     const double twx = tx * w, twy = ty * w, twz = tz * w;
     const double txx = tx * x, txy = ty * x, txz = tz * x;
     const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
-    Eigen::Isometry3d T;
-    Eigen::Matrix3d & R = T.linear();
+    // (with real Eigen Transform::linear() returns a Block by value, so it cannot bind to a Matrix3d &: build R locally)
+    Eigen::Matrix3d R;
     R(0, 0) = 1.0 - (tyy + tzz); R(0, 1) = txy - twz;         R(0, 2) = txz + twy;
     R(1, 0) = txy + twz;         R(1, 1) = 1.0 - (txx + tzz); R(1, 2) = tyz - twx;
     R(2, 0) = txz - twy;         R(2, 1) = tyz + twx;         R(2, 2) = 1.0 - (txx + tyy);
+    Eigen::Isometry3d T = Eigen::Isometry3d::Identity();
+    T.linear() = R;
     T.translation() = Eigen::Vector3d(tq[0], tq[1], tq[2]);
     return T;
 }
