@@ -1056,11 +1056,13 @@ int run_resident(visfs_ba_handle *h) {
         const int64_t trials = (int64_t)s.trials_run[0] + s.trials_run[1];
         t.lm_iterations += (int64_t)s.iterations_run[0] + s.iterations_run[1];
         t.lm_trials += trials;
-        t.edge_trials += trials * d.n_edge;
-        // build reads every edge record (32 B), every landmark (24 B) and every pose (56 B) once;
+        // edges a trial linearises: all of the window in pass 1, those that survived the cull (Optimizer.cpp:283-297) in pass 2
+        const int64_t edge_trials = (int64_t)s.trials_run[0] * d.n_edge + (int64_t)s.trials_run[1] * std::max(0, d.n_edge - s.n_outliers);
+        t.edge_trials += edge_trials;
+        // build reads every active edge record (32 B), every landmark (24 B) and every pose (56 B) once;
         // update re-reads them and writes every landmark (24 B)
-        t.alg_bytes_build += trials * (32LL * d.n_edge + 24LL * d.n_point + 56LL * d.n_pose);
-        t.alg_bytes_update += trials * (32LL * d.n_edge + 48LL * d.n_point + 56LL * d.n_pose);
+        t.alg_bytes_build += 32LL * edge_trials + trials * (24LL * d.n_point + 56LL * d.n_pose);
+        t.alg_bytes_update += 32LL * edge_trials + trials * (48LL * d.n_point + 56LL * d.n_pose);
     }
     return VISFS_BA_OK;
 }
