@@ -1,0 +1,391 @@
+// ba_dense.cuh — dense FP64 Cholesky of the reduced camera system on the tensor pipe (north_star item 3: "a dense FP64
+// Cholesky on tensor cores only when the window makes it a dense contraction"; BASELINE config C5: 200 key frames that all
+// share landmarks, S = 1194 x 1194 dense).  Replaces, for such windows, what g2o's direct linear solvers do after
+// BlockSolver::solve has formed S (selected at corelib/src/Optimizer/Optimizer.cpp:76-91).
+//
+// Layout: one dense row-major matrix D [NP][LD] in HBM / L2 (C5: 12.5 MB), rows 0..n-1 = lower triangle of the damped S,
+// row n = the reduced right-hand side (the forward substitution rides along as one more row), everything else zero padding
+// (so that no tile needs an edge guard).  The block skyline the build kernels produced is left untouched.
+//
+//   k_dense_fill     skyline blocks + lambda -> D
+//   k_dense_chol     cooperative launch, one CTA per SM: blocked right-looking Cholesky, panels of kNB = 48 columns
+//        phase A     every CTA factors the 48 x 48 diagonal block in shared memory (left-looking over 6 x 6 register blocks)
+//                    together with ITS rows of the panel (row r below the block belongs to CTA (r - base) mod G): the
+//                    triangular solve of a row is done by the thread that owns the row, nothing is broadcast.  CTA c < 48
+//                    also carries the unit row e_c, which comes out as row c of L_kk^-T
+//        grid.sync
+//        phase B     trailing update D[r][c] -= P_r . P_c on 32 x 32 tiles, one warp per tile, K = 48 in twelve
+//                    mma.sync.aligned.m8n8k4.f64 steps (DMMA), fragments double-buffered straight from L2, results sent
+//                    with red.global.add.f64 (one writer per entry and panel)
+//        grid.sync
+//        back-substitution, right-looking and spread over the grid: x_panel = L_kk^-T y_panel (a 48 x 48 product, every
+//                    CTA for itself), then every column of y left of the panel is updated by its owner thread; one
+//                    grid.sync per panel
+//   k_dense_back     solution checks, CameraPose::update of the trial poses, pose part of g2o's computeScale — the epilogue
+//                    of the other solvers
+#pragma once
+#include <cooperative_groups.h>
+#include "ba_large.cuh"
+
+namespace visfs {
+namespace dn {
+
+namespace cg = cooperative_groups;
+
+constexpr int kNB = 48;                 // panel width (a multiple of the 6 x 6 pose blocks)
+constexpr int kThreadsD = 256;
+constexpr int kTP = kNB + 1;            // shared-memory pitch of the panel matrix (odd: rows land in different banks)
+constexpr int kMaxOwn = 200;            // rows of a panel one CTA may own (row owner = one thread)
+constexpr int kBackThreads = 1024;
+
+struct DenseMat {
+    double *D;       // [NP][LD]
+    int n, LD, NP;
+    int *flag;       // set to 1 on a non-positive pivot (cleared by the host before the launch)
+    double *Linvt;   // [panels][kNB][kNB] L_kk^-T of every diagonal block (a by-product of the panel solve)
+    double *x;       // [n] solution
+    long long *prof; // optional (VISFS_BA_DENSE_PROF): globaltimer stamps of CTA 0 at the phase boundaries, 5 per panel
+};
+
+__device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+
+__host__ __device__ inline int dense_pad(int n) { return ((n + 1 + 31) / 32) * 32 + 32; }
+
+// skyline (+ lambda on the diagonal) -> dense lower triangle, rhs -> row n.  D has been zeroed by the caller.
+__global__ void k_dense_fill(Batch B, DenseMat M) {
+    const WinDesc &wd = B.win[0];
+    const LMState &st = B.st[0];
+    if (st.done) return;
+    const int F = st.F, n = 6 * F;
+    const double lambda = (wd.trust == 0) ? (B.dbg_lambda >= 0.0 ? B.dbg_lambda : st.lambda) : 0.0;
+    const double *__restrict__ sky = B.red;
+    for (int r = blockIdx.x; r < F; r += gridDim.x) {
+        const int f0 = B.sky_first[r], len = r - f0 + 1;
+        const double *src = sky + (size_t)B.sky_off[r] * 36;
+        for (int idx = threadIdx.x; idx < len * 36; idx += blockDim.x) {
+            const int cb = idx / 36, e = idx - cb * 36, a = e / 6, c = e - a * 6;   // block (r, f0 + cb), entry (row a, col c)
+            const int row = 6 * r + a, col = 6 * (f0 + cb) + c;
+            if (col > row) continue;
+            M.D[(size_t)row * M.LD + col] = src[idx] + (row == col ? lambda : 0.0);
+        }
+    }
+    const double *g = B.red + B.red_g_off;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) M.D[(size_t)n * M.LD + i] = g[i];
+}
+
+// Cholesky of the 6 x 6 block whose lower half sits at d[c * ld + a] (row c, column a <= c)
+__device__ __forceinline__ void chol6_ld(const double *d, int ld, lg::Chol6 &f) {
+    f.ok = true;
+    double v;
+#define VISFS_PIV(expr, inv, diag) v = (expr); if (!(v > 0.0)) { f.ok = false; v = 1.0; } inv = rsqrt(v); diag = v * inv;
+    const double *d1 = d + ld, *d2 = d + 2 * ld, *d3 = d + 3 * ld, *d4 = d + 4 * ld, *d5 = d + 5 * ld;
+    VISFS_PIV(d[0], f.i0, f.L00)
+    f.L10 = d1[0] * f.i0; f.L20 = d2[0] * f.i0; f.L30 = d3[0] * f.i0; f.L40 = d4[0] * f.i0; f.L50 = d5[0] * f.i0;
+    VISFS_PIV(fma(-f.L10, f.L10, d1[1]), f.i1, f.L11)
+    f.L21 = fma(-f.L20, f.L10, d2[1]) * f.i1; f.L31 = fma(-f.L30, f.L10, d3[1]) * f.i1;
+    f.L41 = fma(-f.L40, f.L10, d4[1]) * f.i1; f.L51 = fma(-f.L50, f.L10, d5[1]) * f.i1;
+    VISFS_PIV(fma(-f.L21, f.L21, fma(-f.L20, f.L20, d2[2])), f.i2, f.L22)
+    f.L32 = fma(-f.L31, f.L21, fma(-f.L30, f.L20, d3[2])) * f.i2;
+    f.L42 = fma(-f.L41, f.L21, fma(-f.L40, f.L20, d4[2])) * f.i2;
+    f.L52 = fma(-f.L51, f.L21, fma(-f.L50, f.L20, d5[2])) * f.i2;
+    VISFS_PIV(fma(-f.L32, f.L32, fma(-f.L31, f.L31, fma(-f.L30, f.L30, d3[3]))), f.i3, f.L33)
+    f.L43 = fma(-f.L42, f.L32, fma(-f.L41, f.L31, fma(-f.L40, f.L30, d4[3]))) * f.i3;
+    f.L53 = fma(-f.L52, f.L32, fma(-f.L51, f.L31, fma(-f.L50, f.L30, d5[3]))) * f.i3;
+    VISFS_PIV(fma(-f.L43, f.L43, fma(-f.L42, f.L42, fma(-f.L41, f.L41, fma(-f.L40, f.L40, d4[4])))), f.i4, f.L44)
+    f.L54 = fma(-f.L53, f.L43, fma(-f.L52, f.L42, fma(-f.L51, f.L41, fma(-f.L50, f.L40, d5[4])))) * f.i4;
+    VISFS_PIV(fma(-f.L54, f.L54, fma(-f.L53, f.L53, fma(-f.L52, f.L52, fma(-f.L51, f.L51, fma(-f.L50, f.L50, d5[5]))))), f.i5, f.L55)
+#undef VISFS_PIV
+}
+
+// D (8x8) += A (8x4, row) * B (4x8, col), FP64 tensor pipe.  Lane l holds A[l >> 2][l & 3], B[l & 3][l >> 2] and
+// C[l >> 2][2 (l & 3) .. + 1].
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(kThreadsD) k_dense_chol(Batch B, DenseMat M) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *T = reinterpret_cast<double *>(smem_raw);   // [(kNB + own rows + 1)][kTP]
+    if (B.st[0].done) return;
+    cg::grid_group grid = cg::this_grid();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = gridDim.x, c_id = blockIdx.x;
+    const int n = M.n, LD = M.LD;
+    double *__restrict__ D = M.D;
+    const int own_max = (n + 1 + G - 1) / G + 1;
+    double *S6 = T + (size_t)(kNB + own_max) * kTP;      // [rows][6] partial sums of the helper warps
+
+    for (int k0 = 0; k0 < n; k0 += kNB) {
+        const int nb = min(kNB, n - k0);
+        const int base = k0 + nb;                  // first row below the diagonal block
+        const int m = n + 1 - base;                // rows below it (the rhs row n included)
+        const int nr = (m > c_id) ? (m - c_id + G - 1) / G : 0;   // this CTA's rows: base + c_id + G q
+        // CTA c < nb also carries the unit row e_c: after the panel solve it holds row c of L_kk^-T, which turns the
+        // back-substitution's triangular solves into plain 48 x 48 products
+        const bool unit_row = c_id < nb;
+        const int rows_all = nb + nr + (unit_row ? 1 : 0);
+        long long *pr = (M.prof && c_id == 0 && tid == 0) ? M.prof + 5 * (k0 / kNB) : nullptr;
+        if (pr) pr[0] = gtime();
+        // ---- phase A: diagonal block + own rows into shared memory (all loads of a thread in flight before the first store)
+        {
+            double v[9], w[2];
+            const int own_items = nr * nb;
+#pragma unroll
+            for (int u = 0; u < 9; ++u) {
+                const int idx = tid + u * kThreadsD, i = idx / nb, j = idx - i * nb;
+                v[u] = (idx < nb * nb) ? D[(size_t)(k0 + i) * LD + k0 + j] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {       // (the common case: at most 512 entries of own rows, in the same batch of loads)
+                const int idx = tid + u * kThreadsD, q = idx / nb, j = idx - q * nb;
+                w[u] = (idx < own_items) ? D[(size_t)(base + c_id + G * q) * LD + k0 + j] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 9; ++u) {
+                const int idx = tid + u * kThreadsD, i = idx / nb, j = idx - i * nb;
+                if (idx < nb * nb && j <= i) T[i * kTP + j] = v[u];
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int idx = tid + u * kThreadsD, q = idx / nb, j = idx - q * nb;
+                if (idx < own_items) T[(nb + q) * kTP + j] = w[u];
+            }
+            for (int idx = tid + 2 * kThreadsD; idx < own_items; idx += kThreadsD) {
+                const int q = idx / nb, j = idx - q * nb;
+                T[(nb + q) * kTP + j] = D[(size_t)(base + c_id + G * q) * LD + k0 + j];
+            }
+            if (unit_row && tid < nb) T[(nb + nr) * kTP + tid] = (tid == c_id) ? 1.0 : 0.0;
+        }
+        __syncthreads();
+        // Left-looking over the 6 x 6 block columns of the panel.  Row owners (thread t owns row b0 + t of the rows at and
+        // below the block) bring their six entries of block column b0 up to date, factor the diagonal block redundantly in
+        // registers and solve their own row: nothing is broadcast.  While they run the dependent chain of the factorisation
+        // the other warps pre-compute, for the NEXT block column, the part of its update that only needs finished columns.
+        const bool helpers = rows_all <= 64;       // row owners fit warps 0-1: warps 2-7 are free to help
+        for (int b0 = 0; b0 < nb; b0 += 6) {
+            if (b0 > 0) {
+                const int i = b0 + tid;
+                if (i < rows_all) {
+                    double u[6];
+                    const int q0 = helpers ? b0 - 6 : 0;
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) u[c] = helpers ? S6[i * 6 + c] : 0.0;
+                    const double *ri = T + i * kTP, *p0 = T + b0 * kTP;
+                    for (int q = q0; q < b0; ++q) {
+                        const double v = ri[q];
+#pragma unroll
+                        for (int c = 0; c < 6; ++c) u[c] = fma(v, p0[c * kTP + q], u[c]);
+                    }
+                    double *x = T + i * kTP + b0;
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) x[c] -= u[c];
+                }
+                __syncthreads();
+            }
+            if (M.prof && c_id == 0 && tid == 0 && k0 == 0) M.prof[2500 + 2 * (b0 / 6)] = gtime();
+            lg::Chol6 f;
+            const int i = b0 + 6 + tid;
+            const bool solver = i < rows_all;                              // owner of a row below the block
+            if (solver || tid == 0) chol6_ld(T + b0 * kTP + b0, kTP, f);   // every row owner factors the block redundantly
+            if (solver) {
+                double *x = T + i * kTP + b0;
+                double xv[6] = {x[0], x[1], x[2], x[3], x[4], x[5]};
+                lg::row_solve6(f, xv);
+#pragma unroll
+                for (int q = 0; q < 6; ++q) x[q] = xv[q];
+            } else if (helpers && tid >= 64 && b0 + 6 < nb && b0 > 0) {
+                // helper warps: S6[i][c] = sum_{q < b0} T[i][q] T[b0 + 6 + c][q] for the rows at and below the next block
+                const int nrow = rows_all - b0 - 6;
+                for (int item = tid - 64; item < nrow * 6; item += kThreadsD - 64) {
+                    const int c = item / nrow, ir = b0 + 6 + (item - c * nrow);
+                    const double *ri = T + ir * kTP, *pc = T + (b0 + 6 + c) * kTP;
+                    double s0 = 0.0, s1 = 0.0;
+                    int q = 0;
+                    for (; q + 1 < b0; q += 2) { s0 = fma(ri[q], pc[q], s0); s1 = fma(ri[q + 1], pc[q + 1], s1); }
+                    if (q < b0) s0 = fma(ri[q], pc[q], s0);
+                    S6[ir * 6 + c] = s0 + s1;
+                }
+            } else if (helpers && tid >= 64 && b0 == 0) {
+                for (int item = tid - 64; item < rows_all * 6; item += kThreadsD - 64) S6[item] = 0.0;
+            }
+            __syncthreads();
+            if (M.prof && c_id == 0 && tid == 0 && k0 == 0) M.prof[2501 + 2 * (b0 / 6)] = gtime();
+            if (tid == 0) {   // the factor of the diagonal block is stored only now: nobody reads the original any more
+                double *d0 = T + b0 * kTP + b0, *d1 = d0 + kTP, *d2 = d1 + kTP, *d3 = d2 + kTP, *d4 = d3 + kTP, *d5 = d4 + kTP;
+                d0[0] = f.L00;
+                d1[0] = f.L10; d1[1] = f.L11;
+                d2[0] = f.L20; d2[1] = f.L21; d2[2] = f.L22;
+                d3[0] = f.L30; d3[1] = f.L31; d3[2] = f.L32; d3[3] = f.L33;
+                d4[0] = f.L40; d4[1] = f.L41; d4[2] = f.L42; d4[3] = f.L43; d4[4] = f.L44;
+                d5[0] = f.L50; d5[1] = f.L51; d5[2] = f.L52; d5[3] = f.L53; d5[4] = f.L54; d5[5] = f.L55;
+                if (!f.ok && c_id == 0) *M.flag = 1;
+            }
+        }
+        __syncthreads();
+        if (M.prof && c_id == 0 && tid == 0 && k0 == 0) M.prof[2520] = gtime();
+        // own rows of the panel back, and from CTA c < nb row c of L_kk^-T (the factor of the diagonal block itself is not
+        // needed again: the back-substitution works with its inverse)
+        for (int idx = tid; idx < nr * nb; idx += kThreadsD) {
+            const int q = idx / nb, j = idx - q * nb;
+            D[(size_t)(base + c_id + G * q) * LD + k0 + j] = T[(nb + q) * kTP + j];
+        }
+        if (unit_row && tid < nb) M.Linvt[((size_t)(k0 / kNB) * kNB + c_id) * kNB + tid] = T[(nb + nr) * kTP + tid];
+        if (pr) pr[1] = gtime();
+        __threadfence();
+        grid.sync();
+        if (pr) pr[2] = gtime();
+        if (base >= n) break;                      // last panel: nothing is left to update (the same decision in every CTA)
+
+        // ---- phase B: D[r][c] -= sum_k P[r][k] P[c][k] over the trailing lower triangle, 32 x 32 tiles, one warp each,
+        //      tiles dealt round-robin over the CTAs first (every SM gets work), fragments double-buffered (the loads of
+        //      the next 16 columns are in flight while the tensor pipe works on the current ones), results sent with
+        //      red.global.add (every entry has exactly one writer per panel: deterministic, and no load to wait for)
+        const int nt = (m + 31) >> 5;
+        const int ntiles = nt * (nt + 1) / 2;
+        const int gl = lane >> 2, tl = lane & 3;
+        for (int tile = c_id + G * warp; tile < ntiles; tile += G * (kThreadsD / 32)) {
+            int ti = (int)((sqrt(8.0 * (double)tile + 1.0) - 1.0) * 0.5);
+            while ((ti + 1) * (ti + 2) / 2 <= tile) ++ti;
+            while (ti * (ti + 1) / 2 > tile) --ti;
+            const int tj = tile - ti * (ti + 1) / 2;
+            const int r0 = base + 32 * ti, c0 = base + 32 * tj;
+            const double *pa = D + (size_t)(r0 + gl) * LD + k0 + tl;
+            const double *pb = D + (size_t)(c0 + gl) * LD + k0 + tl;
+            double acc[4][4][2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+            double fa0[4][4], fb0[4][4], fa1[4][4], fb1[4][4];
+#define VISFS_LOAD(fa, fb, kk)                                                                        \
+            _Pragma("unroll") for (int s_ = 0; s_ < 4; ++s_) {                                         \
+                const bool in_ = (kk) + 4 * s_ + tl < nb; /* (the last panel may be narrower than 48) */ \
+                _Pragma("unroll") for (int i_ = 0; i_ < 4; ++i_) {                                     \
+                    fa[s_][i_] = in_ ? pa[(size_t)(8 * i_) * LD + (kk) + 4 * s_] : 0.0;                \
+                    fb[s_][i_] = in_ ? pb[(size_t)(8 * i_) * LD + (kk) + 4 * s_] : 0.0;                \
+                }                                                                                     \
+            }
+#define VISFS_MMA(fa, fb)                                                                             \
+            _Pragma("unroll") for (int s_ = 0; s_ < 4; ++s_)                                           \
+                _Pragma("unroll") for (int i_ = 0; i_ < 4; ++i_)                                       \
+                    _Pragma("unroll") for (int j_ = 0; j_ < 4; ++j_) dmma884(acc[i_][j_][0], acc[i_][j_][1], fa[s_][i_], fb[s_][j_]);
+            VISFS_LOAD(fa0, fb0, 0)
+#pragma unroll 1
+            for (int kk = 0; kk < nb; kk += 32) {
+                const bool more1 = kk + 16 < nb, more2 = kk + 32 < nb;
+                if (more1) { VISFS_LOAD(fa1, fb1, kk + 16) }
+                VISFS_MMA(fa0, fb0)
+                if (more1) {
+                    if (more2) { VISFS_LOAD(fa0, fb0, kk + 32) }
+                    VISFS_MMA(fa1, fb1)
+                }
+            }
+#undef VISFS_LOAD
+#undef VISFS_MMA
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    double *p = D + (size_t)(r0 + 8 * i + gl) * LD + c0 + 8 * j + 2 * tl;
+                    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(-acc[i][j][0]) : "memory");
+                    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p + 1), "d"(-acc[i][j][1]) : "memory");
+                }
+        }
+        if (pr) pr[3] = gtime();
+        __threadfence();
+        grid.sync();
+        if (pr) pr[4] = gtime();
+    }
+
+    // ---- back-substitution L^T x = y (y = row n of D), right-looking and spread over the grid: every CTA forms
+    //      x_panel = L_kk^-T y_panel itself (a 48 x 48 product), then column c < k0 of y is brought up to date by ITS owner
+    //      thread (48 independent loads of L[panel rows][c]); one grid.sync per panel, no partial sums to exchange
+    long long tb = (M.prof && c_id == 0 && tid == 0) ? gtime() : 0;
+    double *Ls = T, *ys = T + kNB * kTP, *xs = ys + kNB;
+    const int npan = (n + kNB - 1) / kNB;
+    double *__restrict__ yrow = D + (size_t)n * LD;
+    for (int p = npan - 1; p >= 0; --p) {
+        const int k0 = p * kNB, nb = min(kNB, n - k0);
+        {
+            double v[9];
+#pragma unroll
+            for (int u = 0; u < 9; ++u) {
+                const int idx = tid + u * kThreadsD;
+                v[u] = (idx < nb * kNB) ? M.Linvt[(size_t)p * kNB * kNB + idx] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 9; ++u) {
+                const int idx = tid + u * kThreadsD, i = idx / kNB, j = idx - i * kNB;
+                if (idx < nb * kNB) Ls[i * kTP + j] = v[u];
+            }
+            if (tid < nb) ys[tid] = yrow[k0 + tid];
+        }
+        __syncthreads();
+        {   // x_i = sum_{j >= i} (L^-T)[i][j] y_j, four lanes per row
+            const int i = tid >> 2, part = tid & 3;
+            double sacc = 0.0;
+            if (i < nb) for (int j = i + part; j < nb; j += 4) sacc = fma(Ls[i * kTP + j], ys[j], sacc);
+            sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+            sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+            if (i < nb && part == 0) { xs[i] = sacc; if (c_id == 0) M.x[k0 + i] = sacc; }
+        }
+        __syncthreads();
+        for (int c = c_id * kThreadsD + tid; c < k0; c += G * kThreadsD) {
+            const double *col = D + (size_t)k0 * LD + c;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            for (int r = 0; r < nb; r += 6) {      // nb is a multiple of 6
+                const double v0 = col[(size_t)r * LD], v1 = col[(size_t)(r + 1) * LD], v2 = col[(size_t)(r + 2) * LD];
+                const double v3 = col[(size_t)(r + 3) * LD], v4 = col[(size_t)(r + 4) * LD], v5 = col[(size_t)(r + 5) * LD];
+                s0 = fma(v0, xs[r], s0); s1 = fma(v1, xs[r + 1], s1); s2 = fma(v2, xs[r + 2], s2);
+                s3 = fma(v3, xs[r + 3], s3); s0 = fma(v4, xs[r + 4], s0); s1 = fma(v5, xs[r + 5], s1);
+            }
+            yrow[c] -= (s0 + s1) + (s2 + s3);
+        }
+        if (p > 0) { __threadfence(); grid.sync(); }
+    }
+    if (M.prof && c_id == 0 && tid == 0) M.prof[2530] = gtime() - tb;
+}
+
+// the epilogue shared with the other direct solvers: solution checks, pose step, trial poses, pose part of computeScale
+__global__ void __launch_bounds__(kBackThreads) k_dense_back(Batch B, DenseMat M) {
+    __shared__ double s_red[32];
+    const WinDesc &wd = B.win[0];
+    LMState &st = B.st[0];
+    if (st.done) return;
+    const int tid = threadIdx.x;
+    const int n = M.n;
+    const double *__restrict__ x = M.x;
+    const double lambda = (wd.trust == 0) ? (B.dbg_lambda >= 0.0 ? B.dbg_lambda : st.lambda) : 0.0;
+    if (n == 0) {
+        if (tid == 0) { st.ok = 1; st.scale_p = 0.0; }
+        return;
+    }
+    const double *__restrict__ braw = B.red + B.red_bp_off;
+    double bad = 0.0;
+    for (int i = tid; i < n; i += kBackThreads) if (!isfinite(x[i])) bad = 1.0;
+    const double anybad = block_sum(bad, s_red);
+    const bool ok = (*M.flag == 0) && (anybad == 0.0);
+    __syncthreads();
+    double sc = 0.0;
+    for (int i = tid; i < n; i += kBackThreads) {
+        const double xi = ok ? x[i] : 0.0;
+        B.xp[i] = xi;
+        sc += xi * (lambda * xi + braw[i]);
+    }
+    const double scale = block_sum(sc, s_red);
+    const int cur = st.cur;
+    const double *src = B.pose + (size_t)cur * B.tot_pose * kPoseStride;
+    double *dst = B.pose + (size_t)(1 - cur) * B.tot_pose * kPoseStride;
+    for (int p = tid; p < wd.n_pose; p += kBackThreads) {
+        const int hi = B.pose_hidx[p];
+        if (hi >= 0) {
+            double dlt[6];
+            for (int a = 0; a < 6; ++a) dlt[a] = ok ? x[6 * hi + a] : 0.0;
+            pose_oplus(src + (size_t)p * kPoseStride, dlt, dst + (size_t)p * kPoseStride);
+        }
+    }
+    if (tid == 0) { st.ok = ok ? 1 : 0; st.scale_p = scale; }
+}
+
+}  // namespace dn
+}  // namespace visfs

@@ -17,6 +17,7 @@
 #include "ba_kernels.cuh"
 #include "ba_build_ws.cuh"
 #include "ba_large.cuh"
+#include "ba_dense.cuh"
 
 #include <dlfcn.h>
 #include <nccl.h>   // types and enums only: the library is bound at run time with dlopen (no link-time dependency)
@@ -134,6 +135,11 @@ struct visfs_ba_handle {
     DevBuf d_lm_key, d_lm_key2, d_lm_idx, d_lm_order, d_sort_tmp, d_lm_rec;
     DevBuf d_pcg;
     bool use_front = false;
+    bool use_dense = false;           // dense DMMA Cholesky (ba_dense.cuh): wide fronts whose envelope is mostly full
+    int dense_grid = 0;               // CTAs of the cooperative k_dense_chol launch (0: cooperative launches unavailable)
+    size_t dense_smem = 0;
+    DevBuf d_dense, d_dense_prof;
+    dn::DenseMat dense{};
     DevBuf d_plan;
     lg::FrontPlan front_plan{};
     DevBuf d_sky_first, d_sky_off, d_col_ptr, d_col_cnt, d_col_rows, d_red, d_hdiag, d_scal, d_info, d_cnt;
@@ -860,8 +866,32 @@ int run_structure_large(visfs_ba_handle *h) {
         b->red_g_off = h->n_sky * 36; b->red_bp_off = h->n_sky * 36 + 6 * F;
     }
     lg::k_col_fill<<<std::max(1, std::min((h->tot_pose + 7) / 8, 512)), 256, 0, s>>>(h->batch);
+    h->use_dense = false;
+    if (F > 0 && h->max_front > 32 && h->dense_grid > 0 && !getenv("VISFS_BA_NO_DENSE")) {
+        // dense contraction: the envelope holds at least a quarter of the full lower triangle (C5: all of it) and D fits easily
+        const int n = 6 * (int)F, NP = dn::dense_pad(n);
+        const int own = (n + 1 + h->dense_grid - 1) / h->dense_grid;
+        const size_t smem_chol = sizeof(double) * ((size_t)(dn::kNB + own + 1) * dn::kTP + (size_t)(dn::kNB + own + 1) * 6 + 2 * dn::kNB);
+        const int npan = (n + dn::kNB - 1) / dn::kNB;
+        if (h->n_sky * 4 >= F * (F + 1) / 2 && (size_t)NP * NP * sizeof(double) <= ((size_t)1 << 30) && own + 1 <= dn::kMaxOwn &&
+            smem_chol <= 200 * 1024) {
+            const size_t extra = (size_t)npan * dn::kNB * dn::kNB + (size_t)n + 64;
+            CK(h->d_dense.reserve(sizeof(double) * ((size_t)NP * NP + extra)));
+            h->dense.D = h->d_dense.as<double>(); h->dense.n = n; h->dense.LD = NP; h->dense.NP = NP;
+            h->dense.Linvt = h->dense.D + (size_t)NP * NP; h->dense.x = h->dense.Linvt + (size_t)npan * dn::kNB * dn::kNB;
+            h->dense.flag = h->d_cnt.as<int>() + 2;
+            h->dense.prof = nullptr;
+            if (getenv("VISFS_BA_DENSE_PROF")) {   // phase timing of the last k_dense_chol launch, printed by run_resident
+                CK(h->d_dense_prof.reserve(sizeof(long long) * 2600));
+                CK(cudaMemsetAsync(h->d_dense_prof.p, 0, sizeof(long long) * 2600, s));
+                h->dense.prof = h->d_dense_prof.as<long long>();
+            }
+            h->dense_smem = smem_chol;
+            h->use_dense = true;
+        }
+    }
     h->use_front = false;
-    if (F > 0 && F <= lg::kFrontMaxF && h->max_front + 2 <= lg::kFrontSlots && h->n_sky < 0x7fffffffLL / 36 && !getenv("VISFS_BA_NO_FRONT")) {
+    if (!h->use_dense && F > 0 && F <= lg::kFrontMaxF && h->max_front + 2 <= lg::kFrontSlots && h->n_sky < 0x7fffffffLL / 36 && !getenv("VISFS_BA_NO_FRONT")) {
         const int st2 = plan_front(h, (int)F);
         if (st2) return st2;
     }
@@ -915,6 +945,15 @@ int enqueue_rest_large(visfs_ba_handle *h) {
         double *work = h->d_pcg.as<double>();
         void *args[] = {(void *)&h->batch, (void *)&work};
         CK(cudaLaunchCooperativeKernel((const void *)lg::k_solve_pcg, dim3((unsigned)h->pcg_grid), dim3(lg::kPcgThreads), args, 0, h->stream));
+    } else if (h->use_dense) {
+        // dense window: blocked Cholesky with the trailing updates on the FP64 tensor pipe (ba_dense.cuh)
+        const dn::DenseMat &M = h->dense;
+        CK(cudaMemsetAsync(M.D, 0, sizeof(double) * (size_t)M.NP * M.LD, h->stream));
+        dn::k_dense_fill<<<std::max(1, std::min(M.n / 6, 4 * h->sm_count)), 256, 0, h->stream>>>(h->batch, M);
+        void *args[] = {(void *)&h->batch, (void *)&h->dense};
+        CK(cudaLaunchCooperativeKernel((const void *)dn::k_dense_chol, dim3((unsigned)h->dense_grid), dim3(dn::kThreadsD), args, h->dense_smem, h->stream));
+        dn::k_dense_back<<<1, dn::kBackThreads, 0, h->stream>>>(h->batch, M);
+        h->launches += 2;
     } else if (h->use_front) {
         lg::k_solve_front<<<1, lg::kSolveThreadsL, sizeof(lg::FrontSmem), h->stream>>>(h->batch, h->front_plan);
     } else if (h->max_front > 32 && h->coop_grid > 1 && !getenv("VISFS_BA_NO_COOP")) {
@@ -1031,6 +1070,18 @@ int run_resident(visfs_ba_handle *h) {
     CK(cudaMemcpyAsync(h->st_host.data(), h->d_st.p, sizeof(LMState) * h->n_win, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->has_run = true;
+    if (h->use_dense && h->dense.prof) {
+        const int np = std::min(512, (h->dense.n + dn::kNB - 1) / dn::kNB);
+        std::vector<long long> pr(2600);
+        cudaMemcpy(pr.data(), h->dense.prof, sizeof(long long) * pr.size(), cudaMemcpyDeviceToHost);
+        double a = 0, s1 = 0, b = 0, s2 = 0;
+        for (int k = 0; k + 1 < np; ++k) { a += pr[5 * k + 1] - pr[5 * k]; s1 += pr[5 * k + 2] - pr[5 * k + 1]; b += pr[5 * k + 3] - pr[5 * k + 2]; s2 += pr[5 * k + 4] - pr[5 * k + 3]; }
+        fprintf(stderr, "[visfs_ba] k_dense_chol (last launch, CTA 0, %d panels): phase A %.1f us, sync %.1f us, phase B %.1f us, sync %.1f us, total %.1f us\n",
+                np, a * 1e-3, s1 * 1e-3, b * 1e-3, s2 * 1e-3, (pr[5 * (np - 1) + 1] - pr[0]) * 1e-3);
+        fprintf(stderr, "[visfs_ba]   panel 0: load %.2f us;", (pr[2500] - pr[0]) * 1e-3);
+        for (int b = 0; b < 8; ++b) fprintf(stderr, " [left %.2f chol+solve %.2f]", b ? (pr[2500 + 2 * b] - pr[2499 + 2 * b]) * 1e-3 : 0.0, (pr[2501 + 2 * b] - pr[2500 + 2 * b]) * 1e-3);
+        fprintf(stderr, " store %.2f us\n[visfs_ba]   back-substitution (inside k_dense_chol): %.1f us\n", (pr[1] - pr[2520]) * 1e-3, pr[2530] * 1e-3);
+    }
 
     visfs_ba_timing &t = h->timing;
     t = visfs_ba_timing{};
@@ -1205,6 +1256,14 @@ int visfs_ba_create(const visfs_ba_config *cfg, visfs_ba_handle **out) {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_pcg, lg::k_solve_pcg, lg::kPcgThreads, 0);
         h->pcg_grid = (coop && per_sm_pcg > 0) ? h->sm_count : 0;
     }
+    {
+        int coop = 0, per_sm = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        cudaFuncSetAttribute(dn::k_dense_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(dn::k_dense_back, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dn::k_dense_chol, dn::kThreadsD, 200 * 1024);
+        h->dense_grid = (coop && per_sm > 0) ? h->sm_count : 0;
+    }
     cudaFuncSetAttribute(lg::k_solve_front, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(lg::FrontSmem));
     cudaFuncSetAttribute(lg::k_build_large<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(lg::BuildSmemL));
     cudaFuncSetAttribute(lg::k_build_large<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(lg::BuildSmemL));
@@ -1229,7 +1288,7 @@ void visfs_ba_destroy(visfs_ba_handle *h) {
     {
         DevBuf *lb[] = {&h->d_sky_first, &h->d_sky_off, &h->d_col_ptr, &h->d_col_cnt, &h->d_col_rows, &h->d_red, &h->d_hdiag,
                         &h->d_scal, &h->d_info, &h->d_cnt, &h->d_plan, &h->d_pcg, &h->d_lm_key, &h->d_lm_key2, &h->d_lm_idx,
-                        &h->d_lm_order, &h->d_sort_tmp, &h->d_lm_rec};
+                        &h->d_lm_order, &h->d_sort_tmp, &h->d_lm_rec, &h->d_dense, &h->d_dense_prof};
         for (DevBuf *b : lb) b->release();
     }
     DevBuf *bufs[] = {&h->d_in, &h->d_st, &h->d_pose, &h->d_point, &h->d_pose_flags, &h->d_lm_flags, &h->d_pose_hidx,
