@@ -105,6 +105,26 @@ def test_large_with_odometry_links(ba):
     check_solution(partition.merge_results(w, [part], [ba.solve(part)]), O.solve(w), "1-rank partition with links")
 
 
+def test_multifrontal_band_solver_matches_oracle(ba, monkeypatch):
+    # ba_mf.cuh: nested dissection of the key-frame chain, dense fronts, DMMA corner updates.  It is chosen from 256 free poses
+    # up; VISFS_BA_MF_MIN (read at the start of every pass) brings it down to windows the oracle checks in a second.
+    monkeypatch.setenv("VISFS_BA_MF_MIN", "8")
+    cases = [("loop with closure rows", loop(seed=171, P=96, L=2500)),
+             ("plain band", banded(seed=172, P=150, L=3000)),
+             ("narrow band, gauge free, mono + fixed points", synth.make_window(70, 1500, views=3, layout="consecutive", seed=173, mono_frac=0.3,
+                                                                               fixed_point_frac=0.2, root=None)),
+             ("10 views like C4", synth.make_window(260, 6000, views=10, layout="consecutive", trajectory="loop", seed=174)),
+             ("band with odometry links", loop(seed=175, P=64, L=1500, links="chain"))]
+    for name, w in cases:
+        lam = 0.7
+        got, ref = ba.debug_trial(w, lam), O.reduced_system(w, lam)
+        rel_close(got["x_pose"], ref["x"][: ref["n"]], 1e-7, name + ": pose step of one damped trial")
+        check_solution(ba.solve(w), O.solve(w), name)
+    # the same windows through the one-CTA frontal solver give the same answer: both are exercised
+    monkeypatch.setenv("VISFS_BA_NO_MF", "1")
+    check_solution(ba.solve(cases[0][1]), O.solve(cases[0][1]), "frontal solver")
+
+
 def test_large_rejected_steps(ba):
     w = synth.make_window(34, 400, views=6, layout="consecutive", seed=78, pose_noise=(0.3, np.deg2rad(6.0)), point_noise=0.5,
                           iterations=20, depth_range=(1.0, 6.0))

@@ -8,17 +8,17 @@
 // (so that no tile needs an edge guard).  The block skyline the build kernels produced is left untouched.
 //
 //   k_dense_fill     skyline blocks + lambda -> D
-//   k_dense_chol     cooperative launch, one CTA per SM: blocked right-looking Cholesky, panels of kNB = 48 columns
-//        phase A     every CTA factors the 48 x 48 diagonal block in shared memory (left-looking over 6 x 6 register blocks)
+//   k_dense_chol     cooperative launch, one CTA per SM: blocked right-looking Cholesky, panels of kNB = 54 columns
+//        phase A     every CTA factors the 54 x 54 diagonal block in shared memory (left-looking over 6 x 6 register blocks)
 //                    together with ITS rows of the panel (row r below the block belongs to CTA (r - base) mod G): the
-//                    triangular solve of a row is done by the thread that owns the row, nothing is broadcast.  CTA c < 48
+//                    triangular solve of a row is done by the thread that owns the row, nothing is broadcast.  CTA c < 54
 //                    also carries the unit row e_c, which comes out as row c of L_kk^-T
 //        grid.sync
-//        phase B     trailing update D[r][c] -= P_r . P_c on 32 x 32 tiles, one warp per tile, K = 48 in twelve
+//        phase B     trailing update D[r][c] -= P_r . P_c on 32 x 32 tiles, one warp per tile, K = 54 in fourteen
 //                    mma.sync.aligned.m8n8k4.f64 steps (DMMA), fragments double-buffered straight from L2, results sent
 //                    with red.global.add.f64 (one writer per entry and panel)
 //        grid.sync
-//        back-substitution, right-looking and spread over the grid: x_panel = L_kk^-T y_panel (a 48 x 48 product, every
+//        back-substitution, right-looking and spread over the grid: x_panel = L_kk^-T y_panel (a 54 x 54 product, every
 //                    CTA for itself), then every column of y left of the panel is updated by its owner thread; one
 //                    grid.sync per panel
 //   k_dense_back     solution checks, CameraPose::update of the trial poses, pose part of g2o's computeScale — the epilogue
@@ -32,7 +32,7 @@ namespace dn {
 
 namespace cg = cooperative_groups;
 
-constexpr int kNB = 48;                 // panel width (a multiple of the 6 x 6 pose blocks)
+constexpr int kNB = 54;                 // panel width: nine 6 x 6 pose blocks (= the separator width of the multifrontal solver for a 10-view band)
 constexpr int kThreadsD = 256;
 constexpr int kTP = kNB + 1;            // shared-memory pitch of the panel matrix (odd: rows land in different banks)
 constexpr int kMaxOwn = 200;            // rows of a panel one CTA may own (row owner = one thread)
@@ -103,12 +103,250 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Building blocks shared by the dense solver below (one matrix, all CTAs of a cooperative grid) and by the multifrontal
+// solver of ba_mf.cuh (many small fronts, one CTA each: SINGLE).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kDiagLoads = (kNB * kNB + kThreadsD - 1) / kThreadsD;
+
+__device__ __forceinline__ double ld_l2(const double *p) { return __ldcg(p); }   // D is written by other CTAs / by red.global: read it at L2
+
+// Phase A of one panel: columns [k0, k0 + nb) of D.  The diagonal block and the CTA's rows of the panel go to shared
+// memory T, are factored / solved there (left-looking over 6 x 6 register blocks, row owner = thread, nothing is
+// broadcast) and the rows go back to D.  Rows: q-th own row = base + c_id + G q, q < nr.  `nunit` unit rows e_u ride along
+// (u = unit0 + 0 .. nunit-1): after the solve they hold rows of L_kk^-T, stored to linvt[u][0..nb).
+__device__ __forceinline__ void panel_factor(double *__restrict__ D, int LD, int k0, int nb, int base, int nr, int c_id, int G,
+                                             int unit0, int nunit, double *__restrict__ linvt, int *flag, bool report,
+                                             double *T, double *S6) {
+    const int tid = threadIdx.x;
+    const int rows_all = nb + nr + nunit;
+    {
+        double v[kDiagLoads], w[2];
+        const int own_items = nr * nb;
+#pragma unroll
+        for (int u = 0; u < kDiagLoads; ++u) {
+            const int idx = tid + u * kThreadsD, i = idx / nb, j = idx - i * nb;
+            v[u] = (idx < nb * nb) ? ld_l2(D + (size_t)(k0 + i) * LD + k0 + j) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {       // (the common case: at most 512 entries of own rows, in the same batch of loads)
+            const int idx = tid + u * kThreadsD, q = idx / nb, j = idx - q * nb;
+            w[u] = (idx < own_items) ? ld_l2(D + (size_t)(base + c_id + G * q) * LD + k0 + j) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < kDiagLoads; ++u) {
+            const int idx = tid + u * kThreadsD, i = idx / nb, j = idx - i * nb;
+            if (idx < nb * nb && j <= i) T[i * kTP + j] = v[u];
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int idx = tid + u * kThreadsD, q = idx / nb, j = idx - q * nb;
+            if (idx < own_items) T[(nb + q) * kTP + j] = w[u];
+        }
+        for (int i0 = 2 * kThreadsD; i0 < own_items; i0 += 8 * kThreadsD) {
+            double z[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int idx = i0 + tid + u * kThreadsD, q = idx / nb, j = idx - q * nb;
+                z[u] = (idx < own_items) ? ld_l2(D + (size_t)(base + c_id + G * q) * LD + k0 + j) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int idx = i0 + tid + u * kThreadsD, q = idx / nb, j = idx - q * nb;
+                if (idx < own_items) T[(nb + q) * kTP + j] = z[u];
+            }
+        }
+        for (int idx = tid; idx < nunit * nb; idx += kThreadsD) {
+            const int u = idx / nb, j = idx - u * nb;
+            T[(nb + nr + u) * kTP + j] = (j == unit0 + u) ? 1.0 : 0.0;
+        }
+    }
+    __syncthreads();
+    // While the row owners run the dependent chain of a block's factorisation the other warps pre-compute, for the NEXT
+    // block column, the part of its update that only needs finished columns (possible when the owners fit warps 0-1).
+    const bool helpers = rows_all <= 64;
+    for (int b0 = 0; b0 < nb; b0 += 6) {
+        if (b0 > 0) {
+            for (int i = b0 + tid; i < rows_all; i += kThreadsD) {
+                double u[6];
+                const int q0 = helpers ? b0 - 6 : 0;
+#pragma unroll
+                for (int c = 0; c < 6; ++c) u[c] = helpers ? S6[i * 6 + c] : 0.0;
+                const double *ri = T + i * kTP, *p0 = T + b0 * kTP;
+                for (int q = q0; q < b0; ++q) {
+                    const double v = ri[q];
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) u[c] = fma(v, p0[c * kTP + q], u[c]);
+                }
+                double *x = T + i * kTP + b0;
+#pragma unroll
+                for (int c = 0; c < 6; ++c) x[c] -= u[c];
+            }
+            __syncthreads();
+        }
+        lg::Chol6 f;
+        const bool solver = b0 + 6 + tid < rows_all;                   // owner of (at least) one row below the block
+        if (solver || tid == 0) chol6_ld(T + b0 * kTP + b0, kTP, f);   // every row owner factors the block redundantly
+        if (solver) {
+            for (int i = b0 + 6 + tid; i < rows_all; i += kThreadsD) {
+                double *x = T + i * kTP + b0;
+                double xv[6] = {x[0], x[1], x[2], x[3], x[4], x[5]};
+                lg::row_solve6(f, xv);
+#pragma unroll
+                for (int q = 0; q < 6; ++q) x[q] = xv[q];
+            }
+        } else if (helpers && tid >= 64 && b0 + 6 < nb && b0 > 0) {
+            // helper warps: S6[i][c] = sum_{q < b0} T[i][q] T[b0 + 6 + c][q] for the rows at and below the next block
+            const int nrow = rows_all - b0 - 6;
+            for (int item = tid - 64; item < nrow * 6; item += kThreadsD - 64) {
+                const int c = item / nrow, ir = b0 + 6 + (item - c * nrow);
+                const double *ri = T + ir * kTP, *pc = T + (b0 + 6 + c) * kTP;
+                double s0 = 0.0, s1 = 0.0;
+                int q = 0;
+                for (; q + 1 < b0; q += 2) { s0 = fma(ri[q], pc[q], s0); s1 = fma(ri[q + 1], pc[q + 1], s1); }
+                if (q < b0) s0 = fma(ri[q], pc[q], s0);
+                S6[ir * 6 + c] = s0 + s1;
+            }
+        } else if (helpers && tid >= 64 && b0 == 0) {
+            for (int item = tid - 64; item < rows_all * 6; item += kThreadsD - 64) S6[item] = 0.0;
+        }
+        __syncthreads();
+        if (tid == 0) {   // the factor of the diagonal block is stored only now: nobody reads the original any more
+            double *d0 = T + b0 * kTP + b0, *d1 = d0 + kTP, *d2 = d1 + kTP, *d3 = d2 + kTP, *d4 = d3 + kTP, *d5 = d4 + kTP;
+            d0[0] = f.L00;
+            d1[0] = f.L10; d1[1] = f.L11;
+            d2[0] = f.L20; d2[1] = f.L21; d2[2] = f.L22;
+            d3[0] = f.L30; d3[1] = f.L31; d3[2] = f.L32; d3[3] = f.L33;
+            d4[0] = f.L40; d4[1] = f.L41; d4[2] = f.L42; d4[3] = f.L43; d4[4] = f.L44;
+            d5[0] = f.L50; d5[1] = f.L51; d5[2] = f.L52; d5[3] = f.L53; d5[4] = f.L54; d5[5] = f.L55;
+            if (!f.ok && report) *flag = 1;
+        }
+    }
+    __syncthreads();
+    // own rows of the panel back, and the rows of L_kk^-T (the factor of the diagonal block itself is not needed again:
+    // the back-substitution works with its inverse)
+    for (int idx = tid; idx < nr * nb; idx += kThreadsD) {
+        const int q = idx / nb, j = idx - q * nb;
+        D[(size_t)(base + c_id + G * q) * LD + k0 + j] = T[(nb + q) * kTP + j];
+    }
+    for (int idx = tid; idx < nunit * nb; idx += kThreadsD) {
+        const int u = idx / nb, j = idx - u * nb;
+        linvt[(size_t)(unit0 + u) * kNB + j] = T[(nb + nr + u) * kTP + j];
+    }
+}
+
+// Phase B of one panel: D[r][c] -= sum_k P[r][k] P[c][k] over the lower triangle of rows / columns [base, base + m), 32 x 32
+// tiles, one warp each; tile t of the sequence t0, t0 + tstep, ... is this warp's.  Fragments double-buffered (the loads of
+// the next 16 columns are in flight while the tensor pipe works on the current ones), results sent with red.global.add
+// (every entry has exactly one writer per panel: deterministic, and no load to wait for).
+__device__ __forceinline__ void trailing_update(double *__restrict__ D, int LD, int k0, int nb, int base, int m, int t0, int tstep) {
+    const int lane = threadIdx.x & 31;
+    const int nt = (m + 31) >> 5;
+    const int ntiles = nt * (nt + 1) / 2;
+    const int gl = lane >> 2, tl = lane & 3;
+    for (int tile = t0; tile < ntiles; tile += tstep) {
+        int ti = (int)((sqrt(8.0 * (double)tile + 1.0) - 1.0) * 0.5);
+        while ((ti + 1) * (ti + 2) / 2 <= tile) ++ti;
+        while (ti * (ti + 1) / 2 > tile) --ti;
+        const int tj = tile - ti * (ti + 1) / 2;
+        const int r0 = base + 32 * ti, c0 = base + 32 * tj;
+        const double *pa = D + (size_t)(r0 + gl) * LD + k0 + tl;
+        const double *pb = D + (size_t)(c0 + gl) * LD + k0 + tl;
+        double acc[4][4][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+        double fa0[4][4], fb0[4][4], fa1[4][4], fb1[4][4];
+#define VISFS_LOAD(fa, fb, kk)                                                                        \
+        _Pragma("unroll") for (int s_ = 0; s_ < 4; ++s_) {                                             \
+            const bool in_ = (kk) + 4 * s_ + tl < nb; /* (a panel may be narrower than kNB) */         \
+            _Pragma("unroll") for (int i_ = 0; i_ < 4; ++i_) {                                         \
+                fa[s_][i_] = in_ ? ld_l2(pa + (size_t)(8 * i_) * LD + (kk) + 4 * s_) : 0.0;            \
+                fb[s_][i_] = in_ ? ld_l2(pb + (size_t)(8 * i_) * LD + (kk) + 4 * s_) : 0.0;            \
+            }                                                                                         \
+        }
+#define VISFS_MMA(fa, fb)                                                                             \
+        _Pragma("unroll") for (int s_ = 0; s_ < 4; ++s_)                                               \
+            _Pragma("unroll") for (int i_ = 0; i_ < 4; ++i_)                                           \
+                _Pragma("unroll") for (int j_ = 0; j_ < 4; ++j_) dmma884(acc[i_][j_][0], acc[i_][j_][1], fa[s_][i_], fb[s_][j_]);
+        VISFS_LOAD(fa0, fb0, 0)
+#pragma unroll 1
+        for (int kk = 0; kk < nb; kk += 32) {
+            const bool more1 = kk + 16 < nb, more2 = kk + 32 < nb;
+            if (more1) { VISFS_LOAD(fa1, fb1, kk + 16) }
+            VISFS_MMA(fa0, fb0)
+            if (more1) {
+                if (more2) { VISFS_LOAD(fa0, fb0, kk + 32) }
+                VISFS_MMA(fa1, fb1)
+            }
+        }
+#undef VISFS_LOAD
+#undef VISFS_MMA
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                double *p = D + (size_t)(r0 + 8 * i + gl) * LD + c0 + 8 * j + 2 * tl;
+                asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(-acc[i][j][0]) : "memory");
+                asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p + 1), "d"(-acc[i][j][1]) : "memory");
+            }
+    }
+}
+
+// Back-substitution step of one panel: x_panel = L_kk^-T y_panel (Ls / ys / xs in shared memory, four lanes per row).
+// Leaves xs valid for all threads (ends with a barrier).  `lin` = the panel's L_kk^-T [kNB][kNB] in global memory.
+__device__ __forceinline__ void back_panel_x(const double *__restrict__ lin, const double *__restrict__ yrow, int k0, int nb,
+                                             double *Ls, double *ys, double *xs) {
+    const int tid = threadIdx.x;
+    {
+        double v[kDiagLoads];
+#pragma unroll
+        for (int u = 0; u < kDiagLoads; ++u) {
+            const int idx = tid + u * kThreadsD;
+            v[u] = (idx < nb * kNB) ? ld_l2(lin + idx) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < kDiagLoads; ++u) {
+            const int idx = tid + u * kThreadsD, i = idx / kNB, j = idx - i * kNB;
+            if (idx < nb * kNB) Ls[i * kTP + j] = v[u];
+        }
+        if (tid < nb) ys[tid] = ld_l2(yrow + k0 + tid);
+    }
+    __syncthreads();
+    {   // x_i = sum_{j >= i} (L^-T)[i][j] y_j
+        const int i = tid >> 2, part = tid & 3;
+        double sacc = 0.0;
+        if (i < nb) for (int j = i + part; j < nb; j += 4) sacc = fma(Ls[i * kTP + j], ys[j], sacc);
+        sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+        sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+        if (i < nb && part == 0) xs[i] = sacc;
+    }
+    __syncthreads();
+}
+
+// y_c -= sum_{r < nrow} D[row0 + r][c] xv[r] for the columns c = c0, c0 + cstep, ... < cend (column c has ONE owner thread)
+__device__ __forceinline__ void back_update_cols(double *__restrict__ D, int LD, double *__restrict__ yrow, int row0, int nrow,
+                                                 const double *xv, int c0, int cstep, int cend) {
+    for (int c = c0; c < cend; c += cstep) {
+        const double *col = D + (size_t)row0 * LD + c;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+        for (int r = 0; r < nrow; r += 6) {      // nrow is a multiple of 6
+            const double v0 = ld_l2(col + (size_t)r * LD), v1 = ld_l2(col + (size_t)(r + 1) * LD), v2 = ld_l2(col + (size_t)(r + 2) * LD);
+            const double v3 = ld_l2(col + (size_t)(r + 3) * LD), v4 = ld_l2(col + (size_t)(r + 4) * LD), v5 = ld_l2(col + (size_t)(r + 5) * LD);
+            s0 = fma(v0, xv[r], s0); s1 = fma(v1, xv[r + 1], s1); s2 = fma(v2, xv[r + 2], s2);
+            s0 = fma(v3, xv[r + 3], s0); s1 = fma(v4, xv[r + 4], s1); s2 = fma(v5, xv[r + 5], s2);
+        }
+        yrow[c] -= (s0 + s1) + s2;
+    }
+}
+
 __global__ void __launch_bounds__(kThreadsD) k_dense_chol(Batch B, DenseMat M) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *T = reinterpret_cast<double *>(smem_raw);   // [(kNB + own rows + 1)][kTP]
     if (B.st[0].done) return;
     cg::grid_group grid = cg::this_grid();
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5;
     const int G = gridDim.x, c_id = blockIdx.x;
     const int n = M.n, LD = M.LD;
     double *__restrict__ D = M.D;
@@ -120,177 +358,19 @@ __global__ void __launch_bounds__(kThreadsD) k_dense_chol(Batch B, DenseMat M) {
         const int base = k0 + nb;                  // first row below the diagonal block
         const int m = n + 1 - base;                // rows below it (the rhs row n included)
         const int nr = (m > c_id) ? (m - c_id + G - 1) / G : 0;   // this CTA's rows: base + c_id + G q
-        // CTA c < nb also carries the unit row e_c: after the panel solve it holds row c of L_kk^-T, which turns the
-        // back-substitution's triangular solves into plain 48 x 48 products
-        const bool unit_row = c_id < nb;
-        const int rows_all = nb + nr + (unit_row ? 1 : 0);
         long long *pr = (M.prof && c_id == 0 && tid == 0) ? M.prof + 5 * (k0 / kNB) : nullptr;
         if (pr) pr[0] = gtime();
-        // ---- phase A: diagonal block + own rows into shared memory (all loads of a thread in flight before the first store)
-        {
-            double v[9], w[2];
-            const int own_items = nr * nb;
-#pragma unroll
-            for (int u = 0; u < 9; ++u) {
-                const int idx = tid + u * kThreadsD, i = idx / nb, j = idx - i * nb;
-                v[u] = (idx < nb * nb) ? D[(size_t)(k0 + i) * LD + k0 + j] : 0.0;
-            }
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {       // (the common case: at most 512 entries of own rows, in the same batch of loads)
-                const int idx = tid + u * kThreadsD, q = idx / nb, j = idx - q * nb;
-                w[u] = (idx < own_items) ? D[(size_t)(base + c_id + G * q) * LD + k0 + j] : 0.0;
-            }
-#pragma unroll
-            for (int u = 0; u < 9; ++u) {
-                const int idx = tid + u * kThreadsD, i = idx / nb, j = idx - i * nb;
-                if (idx < nb * nb && j <= i) T[i * kTP + j] = v[u];
-            }
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int idx = tid + u * kThreadsD, q = idx / nb, j = idx - q * nb;
-                if (idx < own_items) T[(nb + q) * kTP + j] = w[u];
-            }
-            for (int idx = tid + 2 * kThreadsD; idx < own_items; idx += kThreadsD) {
-                const int q = idx / nb, j = idx - q * nb;
-                T[(nb + q) * kTP + j] = D[(size_t)(base + c_id + G * q) * LD + k0 + j];
-            }
-            if (unit_row && tid < nb) T[(nb + nr) * kTP + tid] = (tid == c_id) ? 1.0 : 0.0;
-        }
-        __syncthreads();
-        // Left-looking over the 6 x 6 block columns of the panel.  Row owners (thread t owns row b0 + t of the rows at and
-        // below the block) bring their six entries of block column b0 up to date, factor the diagonal block redundantly in
-        // registers and solve their own row: nothing is broadcast.  While they run the dependent chain of the factorisation
-        // the other warps pre-compute, for the NEXT block column, the part of its update that only needs finished columns.
-        const bool helpers = rows_all <= 64;       // row owners fit warps 0-1: warps 2-7 are free to help
-        for (int b0 = 0; b0 < nb; b0 += 6) {
-            if (b0 > 0) {
-                const int i = b0 + tid;
-                if (i < rows_all) {
-                    double u[6];
-                    const int q0 = helpers ? b0 - 6 : 0;
-#pragma unroll
-                    for (int c = 0; c < 6; ++c) u[c] = helpers ? S6[i * 6 + c] : 0.0;
-                    const double *ri = T + i * kTP, *p0 = T + b0 * kTP;
-                    for (int q = q0; q < b0; ++q) {
-                        const double v = ri[q];
-#pragma unroll
-                        for (int c = 0; c < 6; ++c) u[c] = fma(v, p0[c * kTP + q], u[c]);
-                    }
-                    double *x = T + i * kTP + b0;
-#pragma unroll
-                    for (int c = 0; c < 6; ++c) x[c] -= u[c];
-                }
-                __syncthreads();
-            }
-            if (M.prof && c_id == 0 && tid == 0 && k0 == 0) M.prof[2500 + 2 * (b0 / 6)] = gtime();
-            lg::Chol6 f;
-            const int i = b0 + 6 + tid;
-            const bool solver = i < rows_all;                              // owner of a row below the block
-            if (solver || tid == 0) chol6_ld(T + b0 * kTP + b0, kTP, f);   // every row owner factors the block redundantly
-            if (solver) {
-                double *x = T + i * kTP + b0;
-                double xv[6] = {x[0], x[1], x[2], x[3], x[4], x[5]};
-                lg::row_solve6(f, xv);
-#pragma unroll
-                for (int q = 0; q < 6; ++q) x[q] = xv[q];
-            } else if (helpers && tid >= 64 && b0 + 6 < nb && b0 > 0) {
-                // helper warps: S6[i][c] = sum_{q < b0} T[i][q] T[b0 + 6 + c][q] for the rows at and below the next block
-                const int nrow = rows_all - b0 - 6;
-                for (int item = tid - 64; item < nrow * 6; item += kThreadsD - 64) {
-                    const int c = item / nrow, ir = b0 + 6 + (item - c * nrow);
-                    const double *ri = T + ir * kTP, *pc = T + (b0 + 6 + c) * kTP;
-                    double s0 = 0.0, s1 = 0.0;
-                    int q = 0;
-                    for (; q + 1 < b0; q += 2) { s0 = fma(ri[q], pc[q], s0); s1 = fma(ri[q + 1], pc[q + 1], s1); }
-                    if (q < b0) s0 = fma(ri[q], pc[q], s0);
-                    S6[ir * 6 + c] = s0 + s1;
-                }
-            } else if (helpers && tid >= 64 && b0 == 0) {
-                for (int item = tid - 64; item < rows_all * 6; item += kThreadsD - 64) S6[item] = 0.0;
-            }
-            __syncthreads();
-            if (M.prof && c_id == 0 && tid == 0 && k0 == 0) M.prof[2501 + 2 * (b0 / 6)] = gtime();
-            if (tid == 0) {   // the factor of the diagonal block is stored only now: nobody reads the original any more
-                double *d0 = T + b0 * kTP + b0, *d1 = d0 + kTP, *d2 = d1 + kTP, *d3 = d2 + kTP, *d4 = d3 + kTP, *d5 = d4 + kTP;
-                d0[0] = f.L00;
-                d1[0] = f.L10; d1[1] = f.L11;
-                d2[0] = f.L20; d2[1] = f.L21; d2[2] = f.L22;
-                d3[0] = f.L30; d3[1] = f.L31; d3[2] = f.L32; d3[3] = f.L33;
-                d4[0] = f.L40; d4[1] = f.L41; d4[2] = f.L42; d4[3] = f.L43; d4[4] = f.L44;
-                d5[0] = f.L50; d5[1] = f.L51; d5[2] = f.L52; d5[3] = f.L53; d5[4] = f.L54; d5[5] = f.L55;
-                if (!f.ok && c_id == 0) *M.flag = 1;
-            }
-        }
-        __syncthreads();
-        if (M.prof && c_id == 0 && tid == 0 && k0 == 0) M.prof[2520] = gtime();
-        // own rows of the panel back, and from CTA c < nb row c of L_kk^-T (the factor of the diagonal block itself is not
-        // needed again: the back-substitution works with its inverse)
-        for (int idx = tid; idx < nr * nb; idx += kThreadsD) {
-            const int q = idx / nb, j = idx - q * nb;
-            D[(size_t)(base + c_id + G * q) * LD + k0 + j] = T[(nb + q) * kTP + j];
-        }
-        if (unit_row && tid < nb) M.Linvt[((size_t)(k0 / kNB) * kNB + c_id) * kNB + tid] = T[(nb + nr) * kTP + tid];
+        // CTA c < nb also carries the unit row e_c: after the panel solve it holds row c of L_kk^-T, which turns the
+        // back-substitution's triangular solves into plain products
+        panel_factor(D, LD, k0, nb, base, nr, c_id, G, c_id, (c_id < nb) ? 1 : 0, M.Linvt + (size_t)(k0 / kNB) * kNB * kNB, M.flag,
+                     c_id == 0, T, S6);
         if (pr) pr[1] = gtime();
         __threadfence();
         grid.sync();
         if (pr) pr[2] = gtime();
         if (base >= n) break;                      // last panel: nothing is left to update (the same decision in every CTA)
-
-        // ---- phase B: D[r][c] -= sum_k P[r][k] P[c][k] over the trailing lower triangle, 32 x 32 tiles, one warp each,
-        //      tiles dealt round-robin over the CTAs first (every SM gets work), fragments double-buffered (the loads of
-        //      the next 16 columns are in flight while the tensor pipe works on the current ones), results sent with
-        //      red.global.add (every entry has exactly one writer per panel: deterministic, and no load to wait for)
-        const int nt = (m + 31) >> 5;
-        const int ntiles = nt * (nt + 1) / 2;
-        const int gl = lane >> 2, tl = lane & 3;
-        for (int tile = c_id + G * warp; tile < ntiles; tile += G * (kThreadsD / 32)) {
-            int ti = (int)((sqrt(8.0 * (double)tile + 1.0) - 1.0) * 0.5);
-            while ((ti + 1) * (ti + 2) / 2 <= tile) ++ti;
-            while (ti * (ti + 1) / 2 > tile) --ti;
-            const int tj = tile - ti * (ti + 1) / 2;
-            const int r0 = base + 32 * ti, c0 = base + 32 * tj;
-            const double *pa = D + (size_t)(r0 + gl) * LD + k0 + tl;
-            const double *pb = D + (size_t)(c0 + gl) * LD + k0 + tl;
-            double acc[4][4][2];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
-            double fa0[4][4], fb0[4][4], fa1[4][4], fb1[4][4];
-#define VISFS_LOAD(fa, fb, kk)                                                                        \
-            _Pragma("unroll") for (int s_ = 0; s_ < 4; ++s_) {                                         \
-                const bool in_ = (kk) + 4 * s_ + tl < nb; /* (the last panel may be narrower than 48) */ \
-                _Pragma("unroll") for (int i_ = 0; i_ < 4; ++i_) {                                     \
-                    fa[s_][i_] = in_ ? pa[(size_t)(8 * i_) * LD + (kk) + 4 * s_] : 0.0;                \
-                    fb[s_][i_] = in_ ? pb[(size_t)(8 * i_) * LD + (kk) + 4 * s_] : 0.0;                \
-                }                                                                                     \
-            }
-#define VISFS_MMA(fa, fb)                                                                             \
-            _Pragma("unroll") for (int s_ = 0; s_ < 4; ++s_)                                           \
-                _Pragma("unroll") for (int i_ = 0; i_ < 4; ++i_)                                       \
-                    _Pragma("unroll") for (int j_ = 0; j_ < 4; ++j_) dmma884(acc[i_][j_][0], acc[i_][j_][1], fa[s_][i_], fb[s_][j_]);
-            VISFS_LOAD(fa0, fb0, 0)
-#pragma unroll 1
-            for (int kk = 0; kk < nb; kk += 32) {
-                const bool more1 = kk + 16 < nb, more2 = kk + 32 < nb;
-                if (more1) { VISFS_LOAD(fa1, fb1, kk + 16) }
-                VISFS_MMA(fa0, fb0)
-                if (more1) {
-                    if (more2) { VISFS_LOAD(fa0, fb0, kk + 32) }
-                    VISFS_MMA(fa1, fb1)
-                }
-            }
-#undef VISFS_LOAD
-#undef VISFS_MMA
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    double *p = D + (size_t)(r0 + 8 * i + gl) * LD + c0 + 8 * j + 2 * tl;
-                    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(-acc[i][j][0]) : "memory");
-                    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p + 1), "d"(-acc[i][j][1]) : "memory");
-                }
-        }
+        // tiles dealt round-robin over the CTAs first (every SM gets work)
+        trailing_update(D, LD, k0, nb, base, m, c_id + G * warp, G * (kThreadsD / 32));
         if (pr) pr[3] = gtime();
         __threadfence();
         grid.sync();
@@ -298,49 +378,17 @@ __global__ void __launch_bounds__(kThreadsD) k_dense_chol(Batch B, DenseMat M) {
     }
 
     // ---- back-substitution L^T x = y (y = row n of D), right-looking and spread over the grid: every CTA forms
-    //      x_panel = L_kk^-T y_panel itself (a 48 x 48 product), then column c < k0 of y is brought up to date by ITS owner
-    //      thread (48 independent loads of L[panel rows][c]); one grid.sync per panel, no partial sums to exchange
+    //      x_panel = L_kk^-T y_panel itself, then column c < k0 of y is brought up to date by ITS owner thread (independent
+    //      loads of L[panel rows][c]); one grid.sync per panel, no partial sums to exchange
     long long tb = (M.prof && c_id == 0 && tid == 0) ? gtime() : 0;
     double *Ls = T, *ys = T + kNB * kTP, *xs = ys + kNB;
     const int npan = (n + kNB - 1) / kNB;
     double *__restrict__ yrow = D + (size_t)n * LD;
     for (int p = npan - 1; p >= 0; --p) {
         const int k0 = p * kNB, nb = min(kNB, n - k0);
-        {
-            double v[9];
-#pragma unroll
-            for (int u = 0; u < 9; ++u) {
-                const int idx = tid + u * kThreadsD;
-                v[u] = (idx < nb * kNB) ? M.Linvt[(size_t)p * kNB * kNB + idx] : 0.0;
-            }
-#pragma unroll
-            for (int u = 0; u < 9; ++u) {
-                const int idx = tid + u * kThreadsD, i = idx / kNB, j = idx - i * kNB;
-                if (idx < nb * kNB) Ls[i * kTP + j] = v[u];
-            }
-            if (tid < nb) ys[tid] = yrow[k0 + tid];
-        }
-        __syncthreads();
-        {   // x_i = sum_{j >= i} (L^-T)[i][j] y_j, four lanes per row
-            const int i = tid >> 2, part = tid & 3;
-            double sacc = 0.0;
-            if (i < nb) for (int j = i + part; j < nb; j += 4) sacc = fma(Ls[i * kTP + j], ys[j], sacc);
-            sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
-            sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
-            if (i < nb && part == 0) { xs[i] = sacc; if (c_id == 0) M.x[k0 + i] = sacc; }
-        }
-        __syncthreads();
-        for (int c = c_id * kThreadsD + tid; c < k0; c += G * kThreadsD) {
-            const double *col = D + (size_t)k0 * LD + c;
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-            for (int r = 0; r < nb; r += 6) {      // nb is a multiple of 6
-                const double v0 = col[(size_t)r * LD], v1 = col[(size_t)(r + 1) * LD], v2 = col[(size_t)(r + 2) * LD];
-                const double v3 = col[(size_t)(r + 3) * LD], v4 = col[(size_t)(r + 4) * LD], v5 = col[(size_t)(r + 5) * LD];
-                s0 = fma(v0, xs[r], s0); s1 = fma(v1, xs[r + 1], s1); s2 = fma(v2, xs[r + 2], s2);
-                s3 = fma(v3, xs[r + 3], s3); s0 = fma(v4, xs[r + 4], s0); s1 = fma(v5, xs[r + 5], s1);
-            }
-            yrow[c] -= (s0 + s1) + (s2 + s3);
-        }
+        back_panel_x(M.Linvt + (size_t)p * kNB * kNB, yrow, k0, nb, Ls, ys, xs);
+        if (c_id == 0 && tid < nb) M.x[k0 + tid] = xs[tid];
+        back_update_cols(D, LD, yrow, k0, nb, xs, c_id * kThreadsD + tid, G * kThreadsD, k0);
         if (p > 0) { __threadfence(); grid.sync(); }
     }
     if (M.prof && c_id == 0 && tid == 0) M.prof[2530] = gtime() - tb;

@@ -1,6 +1,7 @@
 // visfs_ba.cu — C ABI of include/visfs_ba.h: batch upload, on-device structure build, the LM launch
 // sequence, download.  No CPU fallback: every compute entry point needs a CUDA device.
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -18,6 +19,7 @@
 #include "ba_build_ws.cuh"
 #include "ba_large.cuh"
 #include "ba_dense.cuh"
+#include "ba_mf.cuh"
 
 #include <dlfcn.h>
 #include <nccl.h>   // types and enums only: the library is bound at run time with dlopen (no link-time dependency)
@@ -140,6 +142,11 @@ struct visfs_ba_handle {
     size_t dense_smem = 0;
     DevBuf d_dense, d_dense_prof;
     dn::DenseMat dense{};
+    int st_F_hint = 0;                // free poses of the current pass (host copy)
+    bool use_mf = false;              // multifrontal nested-dissection Cholesky (ba_mf.cuh): long banded systems
+    DevBuf d_mf_meta, d_mf_fronts;
+    mf::Plan mf_plan{};
+    std::vector<int> mf_level_off;    // problems of level l: [mf_level_off[l], mf_level_off[l + 1])
     DevBuf d_plan;
     lg::FrontPlan front_plan{};
     DevBuf d_sky_first, d_sky_off, d_col_ptr, d_col_cnt, d_col_rows, d_red, d_hdiag, d_scal, d_info, d_cnt;
@@ -804,6 +811,139 @@ int plan_front(visfs_ba_handle *h, int F) {
     return VISFS_BA_OK;
 }
 
+
+// Plan of the multifrontal solver (ba_mf.cuh), built on the host from the envelope once per pass.  Rows whose envelope is
+// longer than mf::kMaxBand blocks are "arrows" (loop closures): they are eliminated last and sit in every front's boundary.
+// The remaining rows form a band of half-width w <= mf::kMaxBand; the chain is cut by nested dissection into leaves of
+// <= 9 poses and separators of w poses.  Leaves use_mf = false when the structure does not fit (the other solvers take over).
+int plan_mf(visfs_ba_handle *h, int F) {
+    cudaStream_t s = h->stream;
+    h->use_mf = false;
+    std::vector<int> first((size_t)F);
+    CK(cudaMemcpyAsync(first.data(), h->d_sky_first.p, sizeof(int) * (size_t)F, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    std::vector<int> comp, arrows, before((size_t)F + 1, 0);   // before[r] = non-arrow rows with index < r
+    for (int r = 0; r < F; ++r) {
+        const bool arrow = r - first[r] > mf::kMaxBand;
+        before[(size_t)r + 1] = before[r] + (arrow ? 0 : 1);
+        (arrow ? arrows : comp).push_back(r);
+    }
+    if ((int)arrows.size() > mf::kMaxArrow) return VISFS_BA_OK;
+    const int N = (int)comp.size();
+    int w = 1;
+    for (int q = 0; q < N; ++q) w = std::max(w, q - before[first[comp[q]]]);
+    if (w > mf::kMaxBand || N < 4 * w) return VISFS_BA_OK;
+
+    struct Node { int lo, hi, e0, e1, level, parent; std::vector<int> kids; };
+    std::vector<Node> nodes;
+    // recursive bisection of the compressed range [lo, hi): returns the node that eliminates its separator (or the leaf)
+    std::vector<std::array<int, 3>> stack;   // (lo, hi, parent) — children are created after their parent, levels fixed below
+    struct Rec { static int build(std::vector<Node> &nodes, int lo, int hi, int w) {
+        const int L = hi - lo;
+        Node nd{lo, hi, lo, hi, 0, -1, {}};
+        if (L <= 9 || L <= w + 1) { nodes.push_back(nd); return (int)nodes.size() - 1; }
+        const int m = lo + (L - w) / 2;
+        nd.e0 = m; nd.e1 = m + w;
+        int k0 = -1, k1 = -1;
+        if (m > lo) k0 = build(nodes, lo, m, w);
+        if (hi > m + w) k1 = build(nodes, m + w, hi, w);
+        nd.level = 1 + std::max(k0 >= 0 ? nodes[k0].level : -1, k1 >= 0 ? nodes[k1].level : -1);
+        if (k0 >= 0) nd.kids.push_back(k0);
+        if (k1 >= 0) nd.kids.push_back(k1);
+        nodes.push_back(nd);
+        const int id = (int)nodes.size() - 1;
+        for (int k : nodes[id].kids) nodes[k].parent = id;
+        return id;
+    } };
+    int top = Rec::build(nodes, 0, N, w);
+    if (!arrows.empty()) {
+        Node nd{0, N, -1, -1, nodes[top].level + 1, -1, {top}};   // e0 = -1: eliminates the arrows
+        nodes.push_back(nd);
+        nodes[top].parent = (int)nodes.size() - 1;
+        top = (int)nodes.size() - 1;
+    }
+    // problems in level order (children before parents; ascending node index inside a level keeps the order deterministic)
+    const int n_nodes = (int)nodes.size();
+    std::vector<int> order(n_nodes), newid(n_nodes);
+    for (int i = 0; i < n_nodes; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return nodes[a].level < nodes[b].level; });
+    for (int i = 0; i < n_nodes; ++i) newid[order[i]] = i;
+    const int n_level = nodes[top].level + 1;
+    h->mf_level_off.assign((size_t)n_level + 1, 0);
+    for (int i = 0; i < n_nodes; ++i) h->mf_level_off[(size_t)nodes[order[i]].level + 1] += 1;
+    for (int l = 0; l < n_level; ++l) h->mf_level_off[l + 1] += h->mf_level_off[l];
+
+    std::vector<mf::Prob> prob(n_nodes);
+    std::vector<int> idx, child, pmap;
+    std::vector<std::vector<int>> local(n_nodes);   // per node: hessian indices of its local blocks
+    long long d_len = 0, linv_len = 0;
+    for (int i = 0; i < n_nodes; ++i) {
+        const Node &nd = nodes[order[i]];
+        std::vector<int> &loc = local[order[i]];
+        int ne = 0;
+        if (nd.e0 < 0) { loc = arrows; ne = (int)arrows.size(); }
+        else {
+            for (int q = nd.e0; q < nd.e1; ++q) loc.push_back(comp[q]);
+            ne = nd.e1 - nd.e0;
+            for (int q = std::max(0, nd.lo - w); q < nd.lo; ++q) loc.push_back(comp[q]);
+            for (int q = nd.hi; q < std::min(N, nd.hi + w); ++q) loc.push_back(comp[q]);
+            for (int a : arrows) loc.push_back(a);
+        }
+        mf::Prob &p = prob[i];
+        p.ne = ne; p.nb = (int)loc.size() - ne;
+        if (p.ne > 2 * mf::kMaxBand || p.nb > 2 * mf::kMaxBand + mf::kMaxArrow || p.ne < 1) return VISFS_BA_OK;
+        const int n_t = 6 * (p.ne + p.nb);
+        p.LD = (n_t + 32 + 7) / 8 * 8;
+        p.d_off = d_len; d_len += ((long long)p.LD * p.LD + 15) / 16 * 16;
+        p.linv_off = linv_len; linv_len += (long long)((6 * p.ne + dn::kNB - 1) / dn::kNB) * dn::kNB * dn::kNB;
+        p.idx_off = (int)idx.size();
+        idx.insert(idx.end(), loc.begin(), loc.end());
+        p.child_off = (int)child.size(); p.n_child = (int)nd.kids.size();
+        std::vector<int> kids;
+        for (int k : nd.kids) kids.push_back(newid[k]);
+        std::sort(kids.begin(), kids.end());
+        child.insert(child.end(), kids.begin(), kids.end());
+        p.map_off = 0;
+    }
+    // boundary of a child -> position in its parent's front
+    std::vector<int> where((size_t)F, -1);
+    for (int i = 0; i < n_nodes; ++i) {
+        const Node &nd = nodes[order[i]];
+        if (nd.parent < 0) continue;
+        const std::vector<int> &ploc = local[nd.parent];
+        for (size_t k = 0; k < ploc.size(); ++k) where[(size_t)ploc[k]] = (int)k;
+        prob[i].map_off = (int)pmap.size();
+        const std::vector<int> &loc = local[order[i]];
+        for (int b = prob[i].ne; b < (int)loc.size(); ++b) {
+            if (where[(size_t)loc[b]] < 0) return h->fail(VISFS_BA_ERR_CUDA, "multifrontal plan: a boundary block is missing from the parent's front");
+            pmap.push_back(where[(size_t)loc[b]]);
+        }
+        for (size_t k = 0; k < ploc.size(); ++k) where[(size_t)ploc[k]] = -1;
+    }
+    if (d_len * (long long)sizeof(double) > ((long long)3 << 30)) return VISFS_BA_OK;
+    // one metadata buffer: [prob | idx | child | pmap]
+    auto al = [](size_t v) { return (v + 15) & ~(size_t)15; };
+    const size_t o_prob = 0, o_idx = al(sizeof(mf::Prob) * prob.size()), o_child = al(o_idx + 4 * idx.size()),
+                 o_pmap = al(o_child + 4 * std::max<size_t>(child.size(), 1)), o_end = al(o_pmap + 4 * std::max<size_t>(pmap.size(), 1));
+    std::vector<unsigned char> pack(o_end, 0);
+    memcpy(pack.data() + o_prob, prob.data(), sizeof(mf::Prob) * prob.size());
+    memcpy(pack.data() + o_idx, idx.data(), 4 * idx.size());
+    if (!child.empty()) memcpy(pack.data() + o_child, child.data(), 4 * child.size());
+    if (!pmap.empty()) memcpy(pack.data() + o_pmap, pmap.data(), 4 * pmap.size());
+    CK(h->d_mf_meta.reserve(o_end));
+    CK(cudaMemcpyAsync(h->d_mf_meta.p, pack.data(), o_end, cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));
+    CK(h->d_mf_fronts.reserve(sizeof(double) * (size_t)(d_len + linv_len + 6 * (long long)F + 64)));
+    const unsigned char *mb = h->d_mf_meta.as<unsigned char>();
+    mf::Plan &P = h->mf_plan;
+    P.prob = reinterpret_cast<const mf::Prob *>(mb + o_prob); P.idx = reinterpret_cast<const int *>(mb + o_idx);
+    P.child = reinterpret_cast<const int *>(mb + o_child); P.pmap = reinterpret_cast<const int *>(mb + o_pmap);
+    P.fronts = h->d_mf_fronts.as<double>(); P.linvt = P.fronts + d_len; P.x = P.linvt + linv_len;
+    P.flag = h->d_cnt.as<int>() + 2;
+    h->use_mf = true;
+    return VISFS_BA_OK;
+}
+
 int run_structure_large(visfs_ba_handle *h) {
     Batch &B = h->batch;
     cudaStream_t s = h->stream;
@@ -857,6 +997,7 @@ int run_structure_large(visfs_ba_handle *h) {
         if (n_runs * 4 > h->tot_point) h->use_run = false;
     }
     const long long F = info[1];
+    h->st_F_hint = (int)F;
     const size_t red_len = (size_t)h->n_sky * 36 + 12 * (size_t)F;
     CK(h->d_red.reserve(sizeof(double) * std::max<size_t>(red_len, 8)));
     CK(h->d_col_rows.reserve(sizeof(int) * (size_t)std::max<long long>(h->n_sky, 1)));
@@ -890,8 +1031,17 @@ int run_structure_large(visfs_ba_handle *h) {
             h->use_dense = true;
         }
     }
+    h->use_mf = false;
+    {
+        int mf_min = 256;   // below that the one-CTA frontal solver is as fast
+        if (const char *e = getenv("VISFS_BA_MF_MIN")) mf_min = atoi(e);
+        if (!h->use_dense && F >= mf_min && !getenv("VISFS_BA_NO_MF")) {
+            const int st2 = plan_mf(h, (int)F);
+            if (st2) return st2;
+        }
+    }
     h->use_front = false;
-    if (!h->use_dense && F > 0 && F <= lg::kFrontMaxF && h->max_front + 2 <= lg::kFrontSlots && h->n_sky < 0x7fffffffLL / 36 && !getenv("VISFS_BA_NO_FRONT")) {
+    if (!h->use_dense && !h->use_mf && F > 0 && F <= lg::kFrontMaxF && h->max_front + 2 <= lg::kFrontSlots && h->n_sky < 0x7fffffffLL / 36 && !getenv("VISFS_BA_NO_FRONT")) {
         const int st2 = plan_front(h, (int)F);
         if (st2) return st2;
     }
@@ -954,6 +1104,19 @@ int enqueue_rest_large(visfs_ba_handle *h) {
         CK(cudaLaunchCooperativeKernel((const void *)dn::k_dense_chol, dim3((unsigned)h->dense_grid), dim3(dn::kThreadsD), args, h->dense_smem, h->stream));
         dn::k_dense_back<<<1, dn::kBackThreads, 0, h->stream>>>(h->batch, M);
         h->launches += 2;
+    } else if (h->use_mf) {
+        // long banded system: nested-dissection multifrontal Cholesky, one launch per tree level (ba_mf.cuh)
+        const size_t smem_f = sizeof(double) * ((size_t)mf::kMaxRows * dn::kTP + (size_t)mf::kMaxRows * 6);
+        const size_t smem_b = sizeof(double) * ((size_t)dn::kNB * dn::kTP + 2 * dn::kNB + 6 * (2 * mf::kMaxBand + mf::kMaxArrow));
+        const int nl = (int)h->mf_level_off.size() - 1;
+        for (int l = 0; l < nl; ++l)
+            mf::k_mf_factor<<<h->mf_level_off[l + 1] - h->mf_level_off[l], dn::kThreadsD, smem_f, h->stream>>>(h->batch, h->mf_plan, h->mf_level_off[l]);
+        for (int l = nl - 1; l >= 0; --l)
+            mf::k_mf_back<<<h->mf_level_off[l + 1] - h->mf_level_off[l], dn::kThreadsD, smem_b, h->stream>>>(h->batch, h->mf_plan, h->mf_level_off[l]);
+        dn::DenseMat M{};
+        M.n = 6 * h->st_F_hint; M.x = h->mf_plan.x; M.flag = h->mf_plan.flag;
+        dn::k_dense_back<<<1, dn::kBackThreads, 0, h->stream>>>(h->batch, M);
+        h->launches += 2 * nl;
     } else if (h->use_front) {
         lg::k_solve_front<<<1, lg::kSolveThreadsL, sizeof(lg::FrontSmem), h->stream>>>(h->batch, h->front_plan);
     } else if (h->max_front > 32 && h->coop_grid > 1 && !getenv("VISFS_BA_NO_COOP")) {
@@ -1078,9 +1241,7 @@ int run_resident(visfs_ba_handle *h) {
         for (int k = 0; k + 1 < np; ++k) { a += pr[5 * k + 1] - pr[5 * k]; s1 += pr[5 * k + 2] - pr[5 * k + 1]; b += pr[5 * k + 3] - pr[5 * k + 2]; s2 += pr[5 * k + 4] - pr[5 * k + 3]; }
         fprintf(stderr, "[visfs_ba] k_dense_chol (last launch, CTA 0, %d panels): phase A %.1f us, sync %.1f us, phase B %.1f us, sync %.1f us, total %.1f us\n",
                 np, a * 1e-3, s1 * 1e-3, b * 1e-3, s2 * 1e-3, (pr[5 * (np - 1) + 1] - pr[0]) * 1e-3);
-        fprintf(stderr, "[visfs_ba]   panel 0: load %.2f us;", (pr[2500] - pr[0]) * 1e-3);
-        for (int b = 0; b < 8; ++b) fprintf(stderr, " [left %.2f chol+solve %.2f]", b ? (pr[2500 + 2 * b] - pr[2499 + 2 * b]) * 1e-3 : 0.0, (pr[2501 + 2 * b] - pr[2500 + 2 * b]) * 1e-3);
-        fprintf(stderr, " store %.2f us\n[visfs_ba]   back-substitution (inside k_dense_chol): %.1f us\n", (pr[1] - pr[2520]) * 1e-3, pr[2530] * 1e-3);
+        fprintf(stderr, "[visfs_ba]   back-substitution (inside k_dense_chol): %.1f us\n", pr[2530] * 1e-3);
     }
 
     visfs_ba_timing &t = h->timing;
@@ -1261,6 +1422,7 @@ int visfs_ba_create(const visfs_ba_config *cfg, visfs_ba_handle **out) {
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
         cudaFuncSetAttribute(dn::k_dense_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(dn::k_dense_back, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(mf::k_mf_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dn::k_dense_chol, dn::kThreadsD, 200 * 1024);
         h->dense_grid = (coop && per_sm > 0) ? h->sm_count : 0;
     }
@@ -1288,7 +1450,7 @@ void visfs_ba_destroy(visfs_ba_handle *h) {
     {
         DevBuf *lb[] = {&h->d_sky_first, &h->d_sky_off, &h->d_col_ptr, &h->d_col_cnt, &h->d_col_rows, &h->d_red, &h->d_hdiag,
                         &h->d_scal, &h->d_info, &h->d_cnt, &h->d_plan, &h->d_pcg, &h->d_lm_key, &h->d_lm_key2, &h->d_lm_idx,
-                        &h->d_lm_order, &h->d_sort_tmp, &h->d_lm_rec, &h->d_dense, &h->d_dense_prof};
+                        &h->d_lm_order, &h->d_sort_tmp, &h->d_lm_rec, &h->d_dense, &h->d_dense_prof, &h->d_mf_meta, &h->d_mf_fronts};
         for (DevBuf *b : lb) b->release();
     }
     DevBuf *bufs[] = {&h->d_in, &h->d_st, &h->d_pose, &h->d_point, &h->d_pose_flags, &h->d_lm_flags, &h->d_pose_hidx,
