@@ -58,50 +58,83 @@ __global__ void __launch_bounds__(dn::kThreadsD) k_mf_factor(Batch B, Plan P, in
     const int *__restrict__ idx = P.idx + pb.idx_off;
     const double lambda = (wd.trust == 0) ? (B.dbg_lambda >= 0.0 ? B.dbg_lambda : st.lambda) : 0.0;
 
+    // index tables of the front in shared memory (the assembly below is bound by dependent global loads otherwise)
+    __shared__ int s_idx[kMaxFrontBlocks], s_first[kMaxFrontBlocks], s_map[kMaxFrontBlocks];
+    __shared__ long long s_off[kMaxFrontBlocks];
+    const int nloc = ne + nbd;
+    if (tid < nloc) {
+        const int r = idx[tid];
+        s_idx[tid] = r; s_first[tid] = B.sky_first[r]; s_off[tid] = B.sky_off[r];
+    }
     // ---- zero the part of the front the tiles can touch
-    for (int i = tid; i < (n_t + 32) * LD; i += dn::kThreadsD) D[i] = 0.0;
+    {
+        double2 *z = reinterpret_cast<double2 *>(D);
+        const int cnt = (n_t + 32) * LD / 2;                    // LD is a multiple of 8
+        for (int i = tid; i < cnt; i += dn::kThreadsD) z[i] = make_double2(0.0, 0.0);
+    }
     __threadfence();
     __syncthreads();
-    // ---- entries of S: block (local i, local j) for j eliminated here, i >= j
+    // ---- entries of S: block (local i, local j) for j eliminated here, i >= j; one item = one 6-entry row of a block
     {
         const double *__restrict__ sky = B.red;
-        const int nloc = ne + nbd;
-        for (int item = tid; item < nloc * ne * 36; item += dn::kThreadsD) {
-            const int i = item / (ne * 36), rem = item - i * (ne * 36), j = rem / 36, e = rem - j * 36;
+        for (int item = tid; item < nloc * ne * 6; item += dn::kThreadsD) {
+            const int i = item / (ne * 6), rem = item - i * (ne * 6), j = rem / 6, a = rem - j * 6;
             if (i < j) continue;
-            const int a = e / 6, c = e - a * 6;                 // entry (6 i + a, 6 j + c) of the front
-            if (i == j && c > a) continue;
-            const int ri = idx[i], cj = idx[j];
-            const int hb = max(ri, cj), ha = min(ri, cj);
-            if (ha < B.sky_first[hb]) continue;                 // outside the envelope: structurally zero
-            const double *blk = sky + (size_t)(B.sky_off[hb] + (ha - B.sky_first[hb])) * 36;
-            const double v = (ri >= cj) ? blk[a * 6 + c] : blk[c * 6 + a];
-            D[(size_t)(6 * i + a) * LD + 6 * j + c] = v + ((i == j && a == c) ? lambda : 0.0);
+            const int ri = s_idx[i], cj = s_idx[j];
+            const bool lower = ri >= cj;                        // the block is stored with the larger hessian index as its row
+            const int hb = lower ? i : j, ha_idx = lower ? cj : ri;
+            if (ha_idx < s_first[hb]) continue;                 // outside the envelope: structurally zero
+            const double *blk = sky + (size_t)(s_off[hb] + (ha_idx - s_first[hb])) * 36;
+            double v[6];
+            if (lower) {
+                const double2 *p2 = reinterpret_cast<const double2 *>(blk + a * 6);
+                const double2 v0 = p2[0], v1 = p2[1], v2 = p2[2];
+                v[0] = v0.x; v[1] = v0.y; v[2] = v1.x; v[3] = v1.y; v[4] = v2.x; v[5] = v2.y;
+            } else {
+#pragma unroll
+                for (int c = 0; c < 6; ++c) v[c] = blk[c * 6 + a];
+            }
+            double *dst = D + (size_t)(6 * i + a) * LD + 6 * j;
+#pragma unroll
+            for (int c = 0; c < 6; ++c)
+                if (i != j || c <= a) dst[c] = v[c] + ((i == j && a == c) ? lambda : 0.0);
         }
         const double *g = B.red + B.red_g_off;
-        for (int t = tid; t < n_e; t += dn::kThreadsD) D[(size_t)n_t * LD + t] = g[6 * idx[t / 6] + t % 6];
+        for (int t = tid; t < n_e; t += dn::kThreadsD) D[(size_t)n_t * LD + t] = g[6 * s_idx[t / 6] + t % 6];
     }
     __syncthreads();
-    // ---- extend-add: the children's boundary corners (and the boundary part of their rhs rows), child by child
+    // ---- extend-add: the children's boundary corners (and the boundary part of their rhs rows), child by child;
+    //      one item = one 6-entry row of a corner block, every entry of the parent has one writer per child
     for (int k = 0; k < pb.n_child; ++k) {
         const Prob ch = P.prob[P.child[pb.child_off + k]];
         const double *__restrict__ Dc = P.fronts + ch.d_off;
-        const int *__restrict__ map = P.pmap + ch.map_off;
         const int ce = 6 * ch.ne, ct = 6 * (ch.ne + ch.nb), cLD = ch.LD;
-        for (int item = tid; item < (ch.nb + 1) * ch.nb * 36; item += dn::kThreadsD) {
-            const int bi = item / (ch.nb * 36), rem = item - bi * (ch.nb * 36), bj = rem / 36, e = rem - bj * 36;
-            const int a = e / 6, c = e - a * 6;
-            if (bi == ch.nb) {                                  // the child's rhs row, boundary columns
-                if (a != 0) continue;
-                const double v = dn::ld_l2(Dc + (size_t)ct * cLD + ce + 6 * bj + c);
-                D[(size_t)n_t * LD + 6 * map[bj] + c] += v;
+        if (tid < ch.nb) s_map[tid] = P.pmap[ch.map_off + tid];
+        __syncthreads();
+        for (int item = tid; item < (ch.nb * 6 + 1) * ch.nb; item += dn::kThreadsD) {
+            const int row = item / ch.nb, bj = item - row * ch.nb;      // row: 6 bi + a, or ch.nb * 6 = the child's rhs row
+            const int bi = row / 6, a = row - bi * 6;
+            const bool rhs = bi == ch.nb;
+            if (!rhs && bj > bi) continue;
+            const double2 *p2 = reinterpret_cast<const double2 *>(Dc + (size_t)(rhs ? ct : ce + row) * cLD + ce + 6 * bj);
+            const double2 v0 = __ldcg(p2), v1 = __ldcg(p2 + 1), v2 = __ldcg(p2 + 2);
+            const double v[6] = {v0.x, v0.y, v1.x, v1.y, v2.x, v2.y};
+            const int pj = s_map[bj];
+            if (rhs) {
+                double *dst = D + (size_t)n_t * LD + 6 * pj;
+#pragma unroll
+                for (int c = 0; c < 6; ++c) dst[c] += v[c];
                 continue;
             }
-            if (bj > bi || (bi == bj && c > a)) continue;
-            const double v = dn::ld_l2(Dc + (size_t)(ce + 6 * bi + a) * cLD + ce + 6 * bj + c);
-            const int pi = map[bi], pj = map[bj];
-            if (pi >= pj) D[(size_t)(6 * pi + a) * LD + 6 * pj + c] += v;
-            else D[(size_t)(6 * pj + c) * LD + 6 * pi + a] += v;
+            const int pi = s_map[bi];
+            if (pi >= pj) {
+                double *dst = D + (size_t)(6 * pi + a) * LD + 6 * pj;
+#pragma unroll
+                for (int c = 0; c < 6; ++c) if (bi != bj || c <= a) dst[c] += v[c];
+            } else {
+#pragma unroll
+                for (int c = 0; c < 6; ++c) D[(size_t)(6 * pj + c) * LD + 6 * pi + a] += v[c];
+            }
         }
         __syncthreads();
     }
