@@ -80,7 +80,7 @@
 extern "C" {
 #endif
 
-#define VISFS_BA_ABI_VERSION 3
+#define VISFS_BA_ABI_VERSION 4
 
 typedef enum visfs_ba_status {
     VISFS_BA_OK = 0,
@@ -260,6 +260,69 @@ int visfs_ba_upload(visfs_ba_handle *h, int32_t n, const visfs_ba_problem *probl
 int visfs_ba_run_resident(visfs_ba_handle *h);
 int visfs_ba_download(visfs_ba_handle *h, int32_t n, visfs_ba_result *results);
 int visfs_ba_get_timing(const visfs_ba_handle *h, visfs_ba_timing *out);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Resident local map.  The reference re-marshals a window that changed by ONE frame on every
+ * call: LocalMap keeps the signatures and features (corelib/src/LocalMap.cpp), Estimator::process turns them into fresh
+ * std::maps and hands them to localOptimize (corelib/src/Estimator.cpp:216-254), then feeds the result back
+ * (Estimator.cpp:391-395 -> LocalMap::updateLocalMap).  A visfs_ba_window keeps the same state in HBM and takes the same
+ * DELTAS; a solve moves one small table to the device and the poses / outlier list back.
+ *
+ *   visfs_ba_window_set_points          a feature enters the map or changes (LocalMap::insertSignature "add new feature",
+ *                                       LocalMap.cpp:61-80; Feature::setFeaturePose / STABLE, :84-88, :170-183)
+ *   visfs_ba_window_insert_frame        LocalMap::insertSignature (LocalMap.cpp:48-131): the signature's pose as T_cw and
+ *                                       its observations, as built at Optimizer.cpp:184-195 (u, v, u_right as floats)
+ *   visfs_ba_window_remove_frame        LocalMap::removeSignature (LocalMap.cpp:133-168)
+ *   visfs_ba_window_remove_points       features_.erase (LocalMap.cpp:158-160)
+ *   visfs_ba_window_remove_observations LocalMap::updateLocalMap's outlier handling (LocalMap.cpp:203-226)
+ *   visfs_ba_window_set_poses           Signature::setPose (LocalMap.cpp:170-176; Estimator.cpp:393 overrides the newest)
+ *   visfs_ba_window_solve               LocalMap::getSignaturePoses + getFeaturePosesAndObservations (LocalMap.cpp:228-236,
+ *                                       274-294: features observed more than once, fixed iff STABLE) + localOptimize
+ *                                       (Optimizer.cpp:58-364) + the write-back of Optimizer.cpp:320-358 into the resident
+ *                                       state (points move only when displaced by less than 5 m)
+ * Ids are the reference's signature / feature ids.  One observation per (feature, frame).  Results are identical to
+ * visfs_ba_solve on the window the reference would have built (tests/test_gpu_window.py). */
+typedef struct visfs_ba_window visfs_ba_window;
+
+typedef struct visfs_ba_window_config {
+    int32_t max_frames;          /* frames resident at once (LocalMap/MapSize + 1), <= 32                   */
+    int32_t max_points;          /* features resident at once                                                */
+    int32_t max_observations;    /* capacity of the observation pool (dead entries are compacted when full)  */
+    int32_t reserved0;
+    double fx, fy, cx, cy, bf;   /* as visfs_ba_problem                                                      */
+    double pixel_variance, huber_delta;
+    int32_t iterations, solver, trust_region, reserved1;
+} visfs_ba_window_config;
+
+typedef struct visfs_ba_window_result {
+    /* caller-allocated outputs, any may be NULL */
+    int64_t *frame_id;           /* [max_frames] ids of the frames of the window, ascending                  */
+    double  *pose_tq;            /* [max_frames][7] optimised T_cw in the same order                         */
+    int64_t *outlier_point_id;   /* [outlier_capacity] culled observations (Optimizer.cpp:283-297), sorted   */
+    int64_t *outlier_frame_id;   /* [outlier_capacity]   by (point, frame)                                   */
+    int32_t outlier_capacity;
+    /* filled by the library */
+    int32_t n_frames, n_points, n_edges;   /* the window that was solved                                     */
+    int32_t n_outliers;                    /* may exceed outlier_capacity (lists truncated)                  */
+    int32_t status;
+    int32_t iterations_run[2], trials_run[2], stop_reason[2];
+    double chi2_initial, chi2_pass1, chi2_final;
+    int64_t h2d_bytes, d2h_bytes;          /* moved by this solve                                            */
+} visfs_ba_window_result;
+
+int  visfs_ba_window_create(visfs_ba_handle *h, const visfs_ba_window_config *cfg, visfs_ba_window **out);
+void visfs_ba_window_destroy(visfs_ba_window *w);
+int  visfs_ba_window_set_points(visfs_ba_window *w, int32_t n, const int64_t *point_id, const double *xyz, const uint8_t *fixed);
+int  visfs_ba_window_insert_frame(visfs_ba_window *w, int64_t frame_id, const double *pose_tq, int32_t n_obs,
+                                  const int64_t *point_id, const float *obs_uvr /* [n_obs][3] */, const uint8_t *kind /* or NULL */);
+int  visfs_ba_window_remove_frame(visfs_ba_window *w, int64_t frame_id);
+int  visfs_ba_window_remove_points(visfs_ba_window *w, int32_t n, const int64_t *point_id);
+int  visfs_ba_window_remove_observations(visfs_ba_window *w, int32_t n, const int64_t *point_id, const int64_t *frame_id);
+int  visfs_ba_window_set_poses(visfs_ba_window *w, int32_t n, const int64_t *frame_id, const double *pose_tq);
+/* root_frame_id: the fixed pose (Estimator.cpp:252: newest id - 1); a value that is not in the window fixes none */
+int  visfs_ba_window_solve(visfs_ba_window *w, int64_t root_frame_id, visfs_ba_window_result *result);
+int  visfs_ba_window_get_points(visfs_ba_window *w, int32_t n, const int64_t *point_id, double *xyz_out);
+int64_t visfs_ba_window_h2d_bytes_total(const visfs_ba_window *w);   /* every byte the window ever sent to the device */
 
 /* multi-GPU global BA: one handle per rank; id from rank 0 is broadcast by the caller */
 #define VISFS_BA_COMM_ID_BYTES 128

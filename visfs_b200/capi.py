@@ -64,6 +64,23 @@ class Structure(C.Structure):
                 ("n_free_points", C.c_int32), ("n_active_edges", C.c_int32), ("n_hpl_blocks", C.c_int32)]
 
 
+class WindowConfig(C.Structure):
+    _fields_ = [("max_frames", C.c_int32), ("max_points", C.c_int32), ("max_observations", C.c_int32), ("reserved0", C.c_int32),
+                ("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double), ("bf", C.c_double),
+                ("pixel_variance", C.c_double), ("huber_delta", C.c_double),
+                ("iterations", C.c_int32), ("solver", C.c_int32), ("trust_region", C.c_int32), ("reserved1", C.c_int32)]
+
+
+class WindowResult(C.Structure):
+    _fields_ = [("frame_id", _i64p), ("pose_tq", _dp), ("outlier_point_id", _i64p), ("outlier_frame_id", _i64p),
+                ("outlier_capacity", C.c_int32),
+                ("n_frames", C.c_int32), ("n_points", C.c_int32), ("n_edges", C.c_int32), ("n_outliers", C.c_int32),
+                ("status", C.c_int32), ("iterations_run", C.c_int32 * 2), ("trials_run", C.c_int32 * 2),
+                ("stop_reason", C.c_int32 * 2),
+                ("chi2_initial", C.c_double), ("chi2_pass1", C.c_double), ("chi2_final", C.c_double),
+                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
+
+
 class Timing(C.Structure):
     _fields_ = [("total_ms", C.c_double), ("build_ms", C.c_double), ("solve_ms", C.c_double),
                 ("update_ms", C.c_double), ("other_ms", C.c_double),
@@ -78,7 +95,10 @@ EXPORTS = ["visfs_ba_abi_version", "visfs_ba_create", "visfs_ba_destroy", "visfs
            "visfs_ba_solve_batch", "visfs_ba_linearize", "visfs_ba_structure_build", "visfs_ba_upload",
            "visfs_ba_run_resident", "visfs_ba_download", "visfs_ba_get_timing", "visfs_ba_comm_unique_id",
            "visfs_ba_comm_init", "visfs_ba_comm_destroy", "visfs_ba_probe_fp64", "visfs_ba_debug_trial",
-           "visfs_ba_host_alloc", "visfs_ba_host_free", "visfs_ba_debug_pose_oplus", "visfs_ba_debug_link_linearize"]
+           "visfs_ba_host_alloc", "visfs_ba_host_free", "visfs_ba_debug_pose_oplus", "visfs_ba_debug_link_linearize",
+           "visfs_ba_window_create", "visfs_ba_window_destroy", "visfs_ba_window_set_points", "visfs_ba_window_insert_frame",
+           "visfs_ba_window_remove_frame", "visfs_ba_window_remove_points", "visfs_ba_window_remove_observations",
+           "visfs_ba_window_set_poses", "visfs_ba_window_solve", "visfs_ba_window_get_points", "visfs_ba_window_h2d_bytes_total"]
 
 
 def _ptr(a, typ):
@@ -224,6 +244,19 @@ def load_library(path=LIB_PATH):
                                          C.POINTER(C.c_int32), _dp, _dp, _dp]
     lib.visfs_ba_debug_pose_oplus.argtypes = [C.c_void_p, C.c_int32, _dp, _dp, _dp]
     lib.visfs_ba_debug_link_linearize.argtypes = [C.c_void_p, C.c_int32, _dp, _dp, _dp, _dp, _dp, _dp]
+    lib.visfs_ba_window_create.argtypes = [C.c_void_p, C.POINTER(WindowConfig), C.POINTER(C.c_void_p)]
+    lib.visfs_ba_window_destroy.argtypes = [C.c_void_p]
+    lib.visfs_ba_window_destroy.restype = None
+    lib.visfs_ba_window_set_points.argtypes = [C.c_void_p, C.c_int32, _i64p, _dp, _u8p]
+    lib.visfs_ba_window_insert_frame.argtypes = [C.c_void_p, C.c_int64, _dp, C.c_int32, _i64p, C.POINTER(C.c_float), _u8p]
+    lib.visfs_ba_window_remove_frame.argtypes = [C.c_void_p, C.c_int64]
+    lib.visfs_ba_window_remove_points.argtypes = [C.c_void_p, C.c_int32, _i64p]
+    lib.visfs_ba_window_remove_observations.argtypes = [C.c_void_p, C.c_int32, _i64p, _i64p]
+    lib.visfs_ba_window_set_poses.argtypes = [C.c_void_p, C.c_int32, _i64p, _dp]
+    lib.visfs_ba_window_solve.argtypes = [C.c_void_p, C.c_int64, C.POINTER(WindowResult)]
+    lib.visfs_ba_window_get_points.argtypes = [C.c_void_p, C.c_int32, _i64p, _dp]
+    lib.visfs_ba_window_h2d_bytes_total.argtypes = [C.c_void_p]
+    lib.visfs_ba_window_h2d_bytes_total.restype = C.c_int64
     lib.visfs_ba_host_alloc.argtypes = [C.c_size_t]
     lib.visfs_ba_host_alloc.restype = C.c_void_p
     lib.visfs_ba_host_free.argtypes = [C.c_void_p]
@@ -446,3 +479,76 @@ class BundleAdjuster:
         buf = C.create_string_buffer(COMM_ID_BYTES)
         self._check(self.lib.visfs_ba_comm_unique_id(buf))
         return buf.raw
+
+
+class ResidentWindow:
+    """visfs_ba_window_*: the local map kept in HBM and fed with LocalMap's deltas (include/visfs_ba.h)."""
+
+    def __init__(self, ba: BundleAdjuster, max_frames, max_points, max_observations, *, fx, fy, cx, cy, bf, pixel_variance=1.5,
+                 huber_delta=8.0, iterations=10, solver=0, trust_region=0):
+        self.ba, self.lib = ba, ba.lib
+        self.cfg = WindowConfig(max_frames=max_frames, max_points=max_points, max_observations=max_observations, fx=fx, fy=fy, cx=cx,
+                                cy=cy, bf=bf, pixel_variance=pixel_variance, huber_delta=huber_delta, iterations=iterations,
+                                solver=solver, trust_region=trust_region)
+        self.w = C.c_void_p()
+        ba._check(self.lib.visfs_ba_window_create(ba.h, C.byref(self.cfg), C.byref(self.w)))
+
+    def close(self):
+        if self.w:
+            self.lib.visfs_ba_window_destroy(self.w)
+            self.w = C.c_void_p()
+
+    def set_points(self, ids, xyz, fixed=None):
+        ids = np.ascontiguousarray(ids, dtype=np.int64)
+        xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+        fixed = None if fixed is None else np.ascontiguousarray(fixed, dtype=np.uint8)
+        self.ba._check(self.lib.visfs_ba_window_set_points(self.w, len(ids), _ptr(ids, _i64p), _ptr(xyz, _dp), _ptr(fixed, _u8p)))
+
+    def insert_frame(self, frame_id, pose_tq, point_ids, obs, kind=None):
+        tq = np.ascontiguousarray(pose_tq, dtype=np.float64)
+        ids = np.ascontiguousarray(point_ids, dtype=np.int64)
+        ob = np.ascontiguousarray(obs, dtype=np.float32)
+        kd = None if kind is None else np.ascontiguousarray(kind, dtype=np.uint8)
+        self.ba._check(self.lib.visfs_ba_window_insert_frame(self.w, int(frame_id), _ptr(tq, _dp), len(ids), _ptr(ids, _i64p),
+                                                             _ptr(ob, C.POINTER(C.c_float)), _ptr(kd, _u8p)))
+
+    def remove_frame(self, frame_id):
+        self.ba._check(self.lib.visfs_ba_window_remove_frame(self.w, int(frame_id)))
+
+    def remove_points(self, ids):
+        ids = np.ascontiguousarray(ids, dtype=np.int64)
+        self.ba._check(self.lib.visfs_ba_window_remove_points(self.w, len(ids), _ptr(ids, _i64p)))
+
+    def remove_observations(self, point_ids, frame_ids):
+        a = np.ascontiguousarray(point_ids, dtype=np.int64)
+        b = np.ascontiguousarray(frame_ids, dtype=np.int64)
+        self.ba._check(self.lib.visfs_ba_window_remove_observations(self.w, len(a), _ptr(a, _i64p), _ptr(b, _i64p)))
+
+    def set_poses(self, frame_ids, pose_tq):
+        a = np.ascontiguousarray(frame_ids, dtype=np.int64)
+        tq = np.ascontiguousarray(pose_tq, dtype=np.float64)
+        self.ba._check(self.lib.visfs_ba_window_set_poses(self.w, len(a), _ptr(a, _i64p), _ptr(tq, _dp)))
+
+    def get_points(self, ids):
+        ids = np.ascontiguousarray(ids, dtype=np.int64)
+        out = np.zeros((len(ids), 3))
+        self.ba._check(self.lib.visfs_ba_window_get_points(self.w, len(ids), _ptr(ids, _i64p), _ptr(out, _dp)))
+        return out
+
+    def solve(self, root_frame_id):
+        F, cap = self.cfg.max_frames, self.cfg.max_observations
+        fid, tq = np.zeros(F, dtype=np.int64), np.zeros((F, 7))
+        op, of = np.zeros(cap, dtype=np.int64), np.zeros(cap, dtype=np.int64)
+        r = WindowResult(frame_id=_ptr(fid, _i64p), pose_tq=_ptr(tq, _dp), outlier_point_id=_ptr(op, _i64p),
+                         outlier_frame_id=_ptr(of, _i64p), outlier_capacity=cap)
+        self.ba._check(self.lib.visfs_ba_window_solve(self.w, int(root_frame_id), C.byref(r)),
+                       allow=(OK, ERR_NUMERIC_PASS1, ERR_NUMERIC_PASS2))
+        n, k = r.n_frames, min(r.n_outliers, cap)
+        return dict(frame_id=fid[:n].copy(), pose_tq=tq[:n].copy(), outliers=list(zip(op[:k].tolist(), of[:k].tolist())),
+                    n_frames=n, n_points=r.n_points, n_edges=r.n_edges, n_outliers=r.n_outliers, status=r.status,
+                    iterations_run=list(r.iterations_run), trials_run=list(r.trials_run), stop_reason=list(r.stop_reason),
+                    chi2_initial=r.chi2_initial, chi2_pass1=r.chi2_pass1, chi2_final=r.chi2_final,
+                    h2d_bytes=r.h2d_bytes, d2h_bytes=r.d2h_bytes)
+
+    def h2d_bytes_total(self):
+        return int(self.lib.visfs_ba_window_h2d_bytes_total(self.w))

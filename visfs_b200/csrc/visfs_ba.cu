@@ -7,6 +7,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <functional>
+#include <map>
+#include <unordered_map>
 #include <chrono>
 #include <thread>
 #include <vector>
@@ -20,6 +23,7 @@
 #include "ba_large.cuh"
 #include "ba_dense.cuh"
 #include "ba_mf.cuh"
+#include "ba_window.cuh"
 
 #include <dlfcn.h>
 #include <nccl.h>   // types and enums only: the library is bound at run time with dlopen (no link-time dependency)
@@ -273,8 +277,15 @@ dim3 grid2(int items, int n_win) {
     return dim3((unsigned)gx, (unsigned)n_win);
 }
 
+// inputs that are already on the device (resident local map, visfs_ba_window_solve): sizes come with the problem structs,
+// the arrays are written into the staging layout by `emit` (kernels on h->stream) instead of being packed and copied
+struct DevInput {
+    int max_degree = 0, n_fixed = 0;
+    std::function<int(visfs_ba_handle *)> emit;
+};
+
 // ---- upload: validate, pack into pinned staging, H2D, device-side preparation ---------------------
-int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs) {
+int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs, const DevInput *dev = nullptr) {
     h->resident = false; h->has_run = false;
     if (n <= 0 || !probs) return h->fail(VISFS_BA_ERR_INVALID, "empty batch");
     if (n > 65535) return h->fail(VISFS_BA_ERR_INVALID, "at most 65535 windows per batch");
@@ -286,9 +297,11 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs) {
     int max_deg_seen = 0;
     for (int w = 0; w < n; ++w) {
         const visfs_ba_problem &p = probs[w];
-        bool srt; int deg;
-        const int st = validate(h, p, w, &srt, &deg);
-        if (st != VISFS_BA_OK) return st;
+        bool srt = true; int deg = dev ? dev->max_degree : 0;
+        if (!dev) {
+            const int st = validate(h, p, w, &srt, &deg);
+            if (st != VISFS_BA_OK) return st;
+        }
         const bool part = (p.flags & VISFS_BA_FLAG_PARTITIONED) != 0;
         const bool big = part || p.n_poses > kMaxSmallPoses || getenv("VISFS_BA_FORCE_LARGE");
         if (big && n != 1)
@@ -312,7 +325,7 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs) {
         tk += p.n_links;
         tp += p.n_poses; tl += p.n_points; te += p.n_edges;
         {
-            int nfix = 0;
+            int nfix = dev ? dev->n_fixed : 0;
             if (p.pose_fixed) for (int i = 0; i < p.n_poses; ++i) nfix += p.pose_fixed[i] != 0;
             max_free = std::max(max_free, p.n_poses - nfix);   // upper bound of the free poses F of any pass
         }
@@ -443,7 +456,7 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs) {
     auto al16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
     // observations travel as floats when every window offers them that way (edge_obs_f32), else as doubles
     bool obs_f32 = te > 0;
-    for (int w = 0; w < n; ++w) if (probs[w].n_edges > 0 && !probs[w].edge_obs_f32) obs_f32 = false;
+    for (int w = 0; w < n; ++w) if (probs[w].n_edges > 0 && !probs[w].edge_obs_f32 && !dev) obs_f32 = false;
     const size_t obs_elem = obs_f32 ? sizeof(float) : sizeof(double);
     const size_t o_pose = 0, o_point = o_pose + sizeof(double) * 7 * P, o_obs = o_point + sizeof(double) * 3 * L,
                  o_epose = o_obs + obs_elem * 3 * E, o_epoint = o_epose + sizeof(int) * E,
@@ -494,6 +507,7 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs) {
             if (!bytes) return;
             if (src) memcpy(stage_at(off, bytes), src, bytes); else memset(stage_at(off, bytes), 0, bytes);
         };
+        if (!dev) {
         for (int w = 0; w < n; ++w) put(o_pose + sizeof(double) * 7 * h->win[w].pose_off, probs[w].pose_tq, sizeof(double) * 7 * probs[w].n_poses);
         for (int w = 0; w < n; ++w) put(o_point + sizeof(double) * 3 * h->win[w].point_off, probs[w].point_xyz, sizeof(double) * 3 * probs[w].n_points);
         for (int w = 0; w < n; ++w) {
@@ -511,14 +525,16 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs) {
         for (int w = 0; w < n; ++w) put_flags(o_pfix + h->win[w].pose_off, probs[w].pose_fixed, probs[w].n_poses);
         for (int w = 0; w < n; ++w) put_flags(o_lfix + h->win[w].point_off, probs[w].point_fixed, probs[w].n_points);
         for (int w = 0; w < n; ++w) put_flags(o_ekind + h->win[w].edge_off, probs[w].edge_kind, probs[w].n_edges);
+        }
         memcpy(stage_at(o_win, sizeof(WinDesc) * n), h->win.data(), sizeof(WinDesc) * n);
         if (h->n_chunks) memcpy(stage_at(o_chunks, sizeof(Chunk) * h->n_chunks), h->chunks.data(), sizeof(Chunk) * h->n_chunks);
         flush();
         CK(cerr);
         h->direct_h2d = direct;
+        if (dev) { const int st = dev->emit(h); if (st) return st; }
     }
 
-    h->h2d_bytes = (int64_t)o_end + (int64_t)tk * (3 * (int64_t)sizeof(int) + 7 * (int64_t)sizeof(double));
+    h->h2d_bytes = (dev ? (int64_t)(o_end - o_win) : (int64_t)o_end) + (int64_t)tk * (3 * (int64_t)sizeof(int) + 7 * (int64_t)sizeof(double));
     // device-side preparation: (optional) stable sort by (window, point, pose), SoA split, CSR offsets
     const int *perm = nullptr;
     if (!all_sorted && te > 0) {
@@ -1348,6 +1364,73 @@ int download(visfs_ba_handle *h, int n, visfs_ba_result *res) {
 
 }  // namespace
 
+
+// ================================================================================================
+// resident local map (visfs_ba_window_*, ba_window.cuh)
+// ================================================================================================
+struct visfs_ba_window {
+    visfs_ba_handle *h = nullptr;
+    visfs_ba_window_config cfg{};
+    // host mirror of the structure (ids, slots, which observation lives where); the numbers live on the device only
+    std::map<int64_t, int> frame_slot;                 // signature id -> slot, ascending ids = pose order
+    std::vector<int> free_frames;
+    std::unordered_map<int64_t, int> point_slot;
+    std::map<int64_t, int> point_order;                // ascending feature id -> slot (std::map order of Optimizer.cpp:156)
+    std::vector<int> free_points;
+    bool order_dirty = true;
+    struct Ob { int pslot, fslot; float o[3]; uint8_t kind, dead; };
+    std::vector<Ob> pool;                              // mirror of the device pool (for compaction and duplicate checks)
+    std::unordered_map<uint64_t, int> ob_index;        // (feature slot, frame slot) -> pool index of the live observation
+    std::vector<std::vector<int>> frame_obs, point_obs;   // pool indices per slot
+    std::vector<int64_t> point_id_of_slot, frame_id_of_slot;
+    int64_t h2d_total = 0;
+    // device
+    DevBuf d_frame_tq, d_frame_pose, d_pose_slot, d_point_xyz, d_point_fixed, d_point_id, d_order, d_ob_point, d_ob_frame, d_ob_obs,
+        d_ob_kind, d_ob_dead, d_cnt, d_act, d_rank, d_rank_of_slot, d_slot_of_rank, d_key, d_key2, d_val, d_val2, d_counters, d_scan_tmp,
+        d_sort_tmp, d_pose_out, d_outliers, d_list;
+    PinBuf h_small;
+    static uint64_t okey(int pslot, int fslot) { return ((uint64_t)(uint32_t)pslot << 8) | (uint32_t)fslot; }
+};
+
+namespace {
+
+int win_fail(visfs_ba_window *w, int st, const std::string &msg) { return w->h->fail(st, "window: " + msg); }
+
+// the device pool is append-only; when it is full the live observations are re-packed from the host mirror
+int win_compact(visfs_ba_window *w) {
+    visfs_ba_handle *h = w->h;
+    std::vector<visfs_ba_window::Ob> live;
+    live.reserve(w->pool.size());
+    for (const auto &o : w->pool) if (!o.dead) live.push_back(o);
+    w->pool.swap(live);
+    w->ob_index.clear();
+    for (auto &v : w->frame_obs) v.clear();
+    for (auto &v : w->point_obs) v.clear();
+    const size_t n = w->pool.size();
+    std::vector<int> op(n), of(n);
+    std::vector<float> oo(3 * n);
+    std::vector<uint8_t> ok(n);
+    for (size_t i = 0; i < n; ++i) {
+        const auto &o = w->pool[i];
+        op[i] = o.pslot; of[i] = o.fslot; oo[3 * i] = o.o[0]; oo[3 * i + 1] = o.o[1]; oo[3 * i + 2] = o.o[2]; ok[i] = o.kind;
+        w->ob_index[visfs_ba_window::okey(o.pslot, o.fslot)] = (int)i;
+        w->frame_obs[(size_t)o.fslot].push_back((int)i); w->point_obs[(size_t)o.pslot].push_back((int)i);
+    }
+    cudaStream_t s = h->stream;
+    if (n) {
+        CK(cudaMemcpyAsync(w->d_ob_point.p, op.data(), 4 * n, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(w->d_ob_frame.p, of.data(), 4 * n, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(w->d_ob_obs.p, oo.data(), 12 * n, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(w->d_ob_kind.p, ok.data(), n, cudaMemcpyHostToDevice, s));
+    }
+    CK(cudaMemsetAsync(w->d_ob_dead.p, 0, (size_t)w->cfg.max_observations, s));
+    CK(cudaStreamSynchronize(s));
+    w->h2d_total += (int64_t)(21 * n);
+    return VISFS_BA_OK;
+}
+
+}  // namespace
+
 // ================================================================================================
 // C ABI
 // ================================================================================================
@@ -1921,6 +2004,355 @@ int visfs_ba_comm_destroy(visfs_ba_handle *h) {
     }
     h->comm_ranks = 1; h->comm_rank = 0;
     return VISFS_BA_OK;
+}
+
+
+// ---- resident local map -----------------------------------------------------------------------------------------
+int visfs_ba_window_create(visfs_ba_handle *h, const visfs_ba_window_config *cfg, visfs_ba_window **out) {
+    if (!h || !out) return VISFS_BA_ERR_INVALID;
+    *out = nullptr;
+    if (!cfg || cfg->max_frames < 2 || cfg->max_frames > kMaxSmallPoses || cfg->max_points < 1 || cfg->max_observations < 1 ||
+        !(cfg->pixel_variance > 0.0))
+        return h->fail(VISFS_BA_ERR_INVALID, "window: bad configuration (2..32 frames, positive capacities, pixel_variance > 0)");
+    CK(cudaSetDevice(h->device));
+    visfs_ba_window *w = new visfs_ba_window();
+    w->h = h; w->cfg = *cfg;
+    const size_t F = (size_t)cfg->max_frames, L = (size_t)cfg->max_points, E = (size_t)cfg->max_observations;
+    for (int i = (int)F - 1; i >= 0; --i) w->free_frames.push_back(i);
+    for (int i = (int)L - 1; i >= 0; --i) w->free_points.push_back(i);
+    w->frame_obs.resize(F); w->point_obs.resize(L);
+    w->point_id_of_slot.assign(L, -1); w->frame_id_of_slot.assign(F, -1);
+    cudaError_t e = cudaSuccess;
+    auto R = [&](DevBuf &b, size_t bytes) { if (e == cudaSuccess) e = b.reserve(bytes); };
+    R(w->d_frame_tq, 56 * F); R(w->d_frame_pose, 4 * F); R(w->d_pose_slot, 4 * F); R(w->d_point_xyz, 24 * L); R(w->d_point_fixed, L);
+    R(w->d_point_id, 8 * L); R(w->d_order, 4 * L); R(w->d_ob_point, 4 * E); R(w->d_ob_frame, 4 * E); R(w->d_ob_obs, 12 * E);
+    R(w->d_ob_kind, E); R(w->d_ob_dead, E); R(w->d_cnt, 4 * L); R(w->d_act, 4 * L); R(w->d_rank, 4 * L); R(w->d_rank_of_slot, 4 * L);
+    R(w->d_slot_of_rank, 4 * L); R(w->d_key, 8 * E); R(w->d_key2, 8 * E); R(w->d_val, 4 * E); R(w->d_val2, 4 * E); R(w->d_counters, 16);
+    R(w->d_pose_out, 56 * F); R(w->d_outliers, 8 * E); R(w->d_list, 4 * E);
+    if (e == cudaSuccess) e = w->h_small.reserve(4096 + 56 * F + 8 * E);
+    if (e == cudaSuccess) e = cudaMemsetAsync(w->d_ob_dead.p, 0, E, h->stream);
+    if (e != cudaSuccess) { const int st = h->cuda_fail(e, "window allocation"); delete w; return st; }
+    *out = w;
+    return VISFS_BA_OK;
+}
+
+void visfs_ba_window_destroy(visfs_ba_window *w) {
+    if (!w) return;
+    cudaSetDevice(w->h->device);
+    cudaStreamSynchronize(w->h->stream);
+    delete w;
+}
+
+int64_t visfs_ba_window_h2d_bytes_total(const visfs_ba_window *w) { return w ? w->h2d_total : 0; }
+
+int visfs_ba_window_set_points(visfs_ba_window *w, int32_t n, const int64_t *point_id, const double *xyz, const uint8_t *fixed) {
+    if (!w) return VISFS_BA_ERR_INVALID;
+    visfs_ba_handle *h = w->h;
+    if (n < 0 || (n > 0 && (!point_id || !xyz))) return win_fail(w, VISFS_BA_ERR_INVALID, "set_points: null arrays");
+    CK(cudaSetDevice(h->device));
+    int fresh = 0;
+    for (int i = 0; i < n; ++i) fresh += w->point_slot.find(point_id[i]) == w->point_slot.end();
+    if (fresh > (int)w->free_points.size()) return win_fail(w, VISFS_BA_ERR_INVALID, "set_points: more features than max_points");
+    cudaStream_t s = h->stream;
+    for (int i = 0; i < n; ++i) {
+        int slot;
+        auto it = w->point_slot.find(point_id[i]);
+        if (it == w->point_slot.end()) {
+            slot = w->free_points.back(); w->free_points.pop_back();
+            w->point_slot.emplace(point_id[i], slot); w->point_order.emplace(point_id[i], slot);
+            w->point_id_of_slot[(size_t)slot] = point_id[i];
+            w->order_dirty = true;
+            CK(cudaMemcpyAsync(w->d_point_id.as<long long>() + slot, point_id + i, 8, cudaMemcpyHostToDevice, s));
+            w->h2d_total += 8;
+        } else slot = it->second;
+        const uint8_t fx = fixed ? fixed[i] : 0;
+        CK(cudaMemcpyAsync(w->d_point_xyz.as<double>() + 3 * (size_t)slot, xyz + 3 * (size_t)i, 24, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(w->d_point_fixed.as<uint8_t>() + slot, &fx, 1, cudaMemcpyHostToDevice, s));
+        w->h2d_total += 25;
+    }
+    CK(cudaStreamSynchronize(s));   // the caller's arrays (and `fx`) may go away
+    return VISFS_BA_OK;
+}
+
+int visfs_ba_window_insert_frame(visfs_ba_window *w, int64_t frame_id, const double *pose_tq, int32_t n_obs, const int64_t *point_id,
+                                 const float *obs_uvr, const uint8_t *kind) {
+    if (!w) return VISFS_BA_ERR_INVALID;
+    visfs_ba_handle *h = w->h;
+    if (!pose_tq || n_obs < 0 || (n_obs > 0 && (!point_id || !obs_uvr))) return win_fail(w, VISFS_BA_ERR_INVALID, "insert_frame: null arrays");
+    if (w->frame_slot.count(frame_id)) return win_fail(w, VISFS_BA_ERR_INVALID, "insert_frame: the frame is already in the window");
+    if (w->free_frames.empty()) return win_fail(w, VISFS_BA_ERR_INVALID, "insert_frame: window full (remove a frame first, LocalMap::removeSignature)");
+    CK(cudaSetDevice(h->device));
+    const int fslot = w->free_frames.back();
+    // validate before anything changes
+    std::vector<int> pslots((size_t)n_obs);
+    {
+        std::unordered_map<int, int> seen;
+        for (int i = 0; i < n_obs; ++i) {
+            auto it = w->point_slot.find(point_id[i]);
+            if (it == w->point_slot.end()) return win_fail(w, VISFS_BA_ERR_INVALID, "insert_frame: observation of a feature that was never set (visfs_ba_window_set_points)");
+            pslots[(size_t)i] = it->second;
+            if (!seen.emplace(it->second, i).second) return win_fail(w, VISFS_BA_ERR_INVALID, "insert_frame: two observations of one feature in one frame");
+        }
+    }
+    if ((int)w->pool.size() + n_obs > w->cfg.max_observations) {
+        const int st = win_compact(w);
+        if (st) return st;
+        if ((int)w->pool.size() + n_obs > w->cfg.max_observations) return win_fail(w, VISFS_BA_ERR_INVALID, "insert_frame: observation pool full (max_observations)");
+    }
+    w->free_frames.pop_back();
+    w->frame_slot.emplace(frame_id, fslot);
+    w->frame_id_of_slot[(size_t)fslot] = frame_id;
+    cudaStream_t s = h->stream;
+    const size_t at = w->pool.size(), n = (size_t)n_obs;
+    std::vector<int> of(n, fslot);
+    std::vector<uint8_t> ok(n, 0);
+    for (size_t i = 0; i < n; ++i) {
+        visfs_ba_window::Ob o{pslots[i], fslot, {obs_uvr[3 * i], obs_uvr[3 * i + 1], obs_uvr[3 * i + 2]}, (uint8_t)(kind ? kind[i] : 0), 0};
+        ok[i] = o.kind;
+        w->ob_index[visfs_ba_window::okey(o.pslot, fslot)] = (int)(at + i);
+        w->frame_obs[(size_t)fslot].push_back((int)(at + i)); w->point_obs[(size_t)o.pslot].push_back((int)(at + i));
+        w->pool.push_back(o);
+    }
+    CK(cudaMemcpyAsync(w->d_frame_tq.as<double>() + 7 * (size_t)fslot, pose_tq, 56, cudaMemcpyHostToDevice, s));
+    if (n) {
+        CK(cudaMemcpyAsync(w->d_ob_point.as<int>() + at, pslots.data(), 4 * n, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(w->d_ob_frame.as<int>() + at, of.data(), 4 * n, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(w->d_ob_obs.as<float>() + 3 * at, obs_uvr, 12 * n, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(w->d_ob_kind.as<uint8_t>() + at, ok.data(), n, cudaMemcpyHostToDevice, s));
+    }
+    CK(cudaStreamSynchronize(s));
+    w->h2d_total += 56 + (int64_t)(21 * n);
+    return VISFS_BA_OK;
+}
+
+int visfs_ba_window_remove_frame(visfs_ba_window *w, int64_t frame_id) {
+    if (!w) return VISFS_BA_ERR_INVALID;
+    visfs_ba_handle *h = w->h;
+    auto it = w->frame_slot.find(frame_id);
+    if (it == w->frame_slot.end()) return win_fail(w, VISFS_BA_ERR_INVALID, "remove_frame: no such frame");
+    CK(cudaSetDevice(h->device));
+    const int fslot = it->second;
+    for (int i : w->frame_obs[(size_t)fslot]) {
+        auto &o = w->pool[(size_t)i];
+        if (!o.dead) { o.dead = 1; w->ob_index.erase(visfs_ba_window::okey(o.pslot, o.fslot)); }
+    }
+    w->frame_obs[(size_t)fslot].clear();
+    if (!w->pool.empty())
+        wn::k_win_kill_frame<<<std::max(1, std::min(((int)w->pool.size() + 255) / 256, 256)), 256, 0, h->stream>>>(w->d_ob_frame.as<int>(), w->d_ob_dead.as<uint8_t>(), (int)w->pool.size(), fslot);
+    CK(cudaGetLastError());
+    w->frame_slot.erase(it);
+    w->frame_id_of_slot[(size_t)fslot] = -1;
+    w->free_frames.push_back(fslot);
+    return VISFS_BA_OK;
+}
+
+static int win_kill(visfs_ba_window *w, const std::vector<int> &list) {
+    visfs_ba_handle *h = w->h;
+    if (list.empty()) return VISFS_BA_OK;
+    CK(cudaMemcpyAsync(w->d_list.p, list.data(), 4 * list.size(), cudaMemcpyHostToDevice, h->stream));
+    wn::k_win_kill_list<<<std::max(1, std::min(((int)list.size() + 255) / 256, 64)), 256, 0, h->stream>>>(w->d_ob_dead.as<uint8_t>(), w->d_list.as<int>(), (int)list.size());
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    w->h2d_total += (int64_t)(4 * list.size());
+    return VISFS_BA_OK;
+}
+
+int visfs_ba_window_remove_points(visfs_ba_window *w, int32_t n, const int64_t *point_id) {
+    if (!w) return VISFS_BA_ERR_INVALID;
+    if (n < 0 || (n > 0 && !point_id)) return win_fail(w, VISFS_BA_ERR_INVALID, "remove_points: null array");
+    if (cudaSetDevice(w->h->device) != cudaSuccess) return VISFS_BA_ERR_CUDA;
+    std::vector<int> list;
+    for (int k = 0; k < n; ++k) {
+        auto it = w->point_slot.find(point_id[k]);
+        if (it == w->point_slot.end()) return win_fail(w, VISFS_BA_ERR_INVALID, "remove_points: no such feature");
+        const int slot = it->second;
+        for (int i : w->point_obs[(size_t)slot]) {
+            auto &o = w->pool[(size_t)i];
+            if (!o.dead) { o.dead = 1; w->ob_index.erase(visfs_ba_window::okey(o.pslot, o.fslot)); list.push_back(i); }
+        }
+        w->point_obs[(size_t)slot].clear();
+        w->point_order.erase(point_id[k]);
+        w->point_slot.erase(it);
+        w->point_id_of_slot[(size_t)slot] = -1;
+        w->free_points.push_back(slot);
+        w->order_dirty = true;
+    }
+    return win_kill(w, list);
+}
+
+int visfs_ba_window_remove_observations(visfs_ba_window *w, int32_t n, const int64_t *point_id, const int64_t *frame_id) {
+    if (!w) return VISFS_BA_ERR_INVALID;
+    if (n < 0 || (n > 0 && (!point_id || !frame_id))) return win_fail(w, VISFS_BA_ERR_INVALID, "remove_observations: null arrays");
+    if (cudaSetDevice(w->h->device) != cudaSuccess) return VISFS_BA_ERR_CUDA;
+    std::vector<int> list;
+    for (int k = 0; k < n; ++k) {
+        auto ip = w->point_slot.find(point_id[k]);
+        auto jf = w->frame_slot.find(frame_id[k]);
+        if (ip == w->point_slot.end() || jf == w->frame_slot.end()) continue;      // LocalMap.cpp:219-224 logs and goes on
+        auto io = w->ob_index.find(visfs_ba_window::okey(ip->second, jf->second));
+        if (io == w->ob_index.end()) continue;
+        w->pool[(size_t)io->second].dead = 1;
+        list.push_back(io->second);
+        w->ob_index.erase(io);
+    }
+    return win_kill(w, list);
+}
+
+int visfs_ba_window_set_poses(visfs_ba_window *w, int32_t n, const int64_t *frame_id, const double *pose_tq) {
+    if (!w) return VISFS_BA_ERR_INVALID;
+    visfs_ba_handle *h = w->h;
+    if (n < 0 || (n > 0 && (!frame_id || !pose_tq))) return win_fail(w, VISFS_BA_ERR_INVALID, "set_poses: null arrays");
+    CK(cudaSetDevice(h->device));
+    for (int k = 0; k < n; ++k) {
+        auto it = w->frame_slot.find(frame_id[k]);
+        if (it == w->frame_slot.end()) return win_fail(w, VISFS_BA_ERR_INVALID, "set_poses: no such frame");
+        CK(cudaMemcpyAsync(w->d_frame_tq.as<double>() + 7 * (size_t)it->second, pose_tq + 7 * (size_t)k, 56, cudaMemcpyHostToDevice, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    w->h2d_total += 56 * (int64_t)n;
+    return VISFS_BA_OK;
+}
+
+int visfs_ba_window_get_points(visfs_ba_window *w, int32_t n, const int64_t *point_id, double *xyz_out) {
+    if (!w) return VISFS_BA_ERR_INVALID;
+    visfs_ba_handle *h = w->h;
+    if (n < 0 || (n > 0 && (!point_id || !xyz_out))) return win_fail(w, VISFS_BA_ERR_INVALID, "get_points: null arrays");
+    CK(cudaSetDevice(h->device));
+    for (int k = 0; k < n; ++k) {
+        auto it = w->point_slot.find(point_id[k]);
+        if (it == w->point_slot.end()) return win_fail(w, VISFS_BA_ERR_INVALID, "get_points: no such feature");
+        CK(cudaMemcpyAsync(xyz_out + 3 * (size_t)k, w->d_point_xyz.as<double>() + 3 * (size_t)it->second, 24, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return VISFS_BA_OK;
+}
+
+int visfs_ba_window_solve(visfs_ba_window *w, int64_t root_frame_id, visfs_ba_window_result *res) {
+    if (!w || !res) return VISFS_BA_ERR_INVALID;
+    visfs_ba_handle *h = w->h;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    const int P = (int)w->frame_slot.size(), n_pool = (int)w->pool.size(), n_order = (int)w->point_order.size();
+    const int maxF = w->cfg.max_frames;
+    int64_t h2d = 0;
+    // ---- the one table a solve sends: frame slot -> pose index (ascending signature id), pose index -> slot
+    int *tab = w->h_small.as<int>();
+    int root_pose = -1;
+    for (int i = 0; i < maxF; ++i) tab[i] = -1;
+    {
+        int k = 0;
+        for (const auto &kv : w->frame_slot) {
+            tab[kv.second] = k; tab[maxF + k] = kv.second;
+            if (kv.first == root_frame_id) root_pose = k;
+            if (res->frame_id) res->frame_id[k] = kv.first;
+            ++k;
+        }
+    }
+    CK(cudaMemcpyAsync(w->d_frame_pose.p, tab, 4 * (size_t)maxF, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(w->d_pose_slot.p, tab + maxF, 4 * (size_t)std::max(P, 1), cudaMemcpyHostToDevice, s));
+    h2d += 4 * (maxF + P);
+    std::vector<int> order;
+    if (w->order_dirty) {   // only when a feature entered or left since the last solve
+        order.reserve((size_t)n_order);
+        for (const auto &kv : w->point_order) order.push_back(kv.second);
+        if (n_order) CK(cudaMemcpyAsync(w->d_order.p, order.data(), 4 * (size_t)n_order, cudaMemcpyHostToDevice, s));
+        h2d += 4 * n_order;
+    }
+    wn::Win W{};
+    W.frame_tq = w->d_frame_tq.as<double>(); W.frame_pose = w->d_frame_pose.as<int>(); W.pose_slot = w->d_pose_slot.as<int>();
+    W.point_xyz = w->d_point_xyz.as<double>(); W.point_fixed = w->d_point_fixed.as<uint8_t>(); W.point_id = w->d_point_id.as<long long>();
+    W.order = w->d_order.as<int>(); W.n_order = n_order;
+    W.ob_point = w->d_ob_point.as<int>(); W.ob_frame = w->d_ob_frame.as<int>(); W.ob_obs = w->d_ob_obs.as<float>();
+    W.ob_kind = w->d_ob_kind.as<uint8_t>(); W.ob_dead = w->d_ob_dead.as<uint8_t>(); W.n_pool = n_pool;
+    W.cnt = w->d_cnt.as<int>(); W.act = w->d_act.as<int>(); W.rank = w->d_rank.as<int>();
+    W.rank_of_slot = w->d_rank_of_slot.as<int>(); W.slot_of_rank = w->d_slot_of_rank.as<int>();
+    W.key = w->d_key.as<unsigned long long>(); W.key_sorted = w->d_key2.as<unsigned long long>();
+    W.val = w->d_val.as<int>(); W.val_sorted = w->d_val2.as<int>(); W.counters = w->d_counters.as<int>();
+    int L = 0, E = 0;
+    if (n_pool > 0 && n_order > 0 && P > 0) {
+        const int gp = std::max(1, std::min((n_pool + 255) / 256, 1024)), go = std::max(1, std::min((n_order + 255) / 256, 1024));
+        CK(cudaMemsetAsync(w->d_cnt.p, 0, 4 * (size_t)w->cfg.max_points, s));
+        CK(cudaMemsetAsync(w->d_counters.p, 0, 16, s));
+        wn::k_win_count<<<gp, 256, 0, s>>>(W);
+        wn::k_win_act<<<go, 256, 0, s>>>(W);
+        size_t tb = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, W.act, W.rank, n_order, s);
+        CK(w->d_scan_tmp.reserve(tb));
+        CK(cub::DeviceScan::ExclusiveSum(w->d_scan_tmp.p, tb, W.act, W.rank, n_order, s));
+        wn::k_win_rank<<<go, 256, 0, s>>>(W);
+        wn::k_win_keys<<<gp, 256, 0, s>>>(W);
+        tb = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tb, W.key, W.key_sorted, W.val, W.val_sorted, n_pool, 0, 64, s);
+        CK(w->d_sort_tmp.reserve(tb));
+        CK(cub::DeviceRadixSort::SortPairs(w->d_sort_tmp.p, tb, W.key, W.key_sorted, W.val, W.val_sorted, n_pool, 0, 64, s));
+        int *cnt_h = w->h_small.as<int>() + 2 * maxF;
+        CK(cudaMemcpyAsync(cnt_h, w->d_counters.p, 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        L = cnt_h[0]; E = cnt_h[1];
+        h->launches = 0;
+    } else {
+        CK(cudaStreamSynchronize(s));
+    }
+    w->order_dirty = false;
+    // ---- the window as one problem whose arrays are already on the device
+    visfs_ba_problem pb{};
+    pb.n_poses = P; pb.n_points = L; pb.n_edges = E;
+    pb.fx = w->cfg.fx; pb.fy = w->cfg.fy; pb.cx = w->cfg.cx; pb.cy = w->cfg.cy; pb.bf = w->cfg.bf;
+    pb.pixel_variance = w->cfg.pixel_variance; pb.huber_delta = w->cfg.huber_delta;
+    pb.iterations = w->cfg.iterations; pb.solver = w->cfg.solver; pb.trust_region = w->cfg.trust_region;
+    DevInput dev;
+    dev.max_degree = std::max(P, 1); dev.n_fixed = root_pose >= 0 ? 1 : 0;
+    dev.emit = [&](visfs_ba_handle *hh) -> int {
+        const int items = std::max(std::max(P * 7, L), E);
+        wn::k_win_emit<<<std::max(1, std::min((items + 255) / 256, 1024)), 256, 0, hh->stream>>>(
+            W, P, L, E, root_pose, hh->in.pose, hh->in.point, reinterpret_cast<float *>(hh->in.obs), hh->in.epose, hh->in.epoint, hh->in.pfix,
+            hh->in.lfix, hh->in.ekind);
+        return cudaGetLastError() == cudaSuccess ? VISFS_BA_OK : VISFS_BA_ERR_CUDA;
+    };
+    *res = visfs_ba_window_result{res->frame_id, res->pose_tq, res->outlier_point_id, res->outlier_frame_id, res->outlier_capacity};
+    res->n_frames = P; res->n_points = L; res->n_edges = E;
+    if (P == 0) return win_fail(w, VISFS_BA_ERR_INVALID, "solve: the window holds no frame");
+    int st = upload(h, 1, &pb, &dev);
+    if (st) return st;
+    h2d += h->h2d_bytes;
+    st = run_resident(h);
+    if (st) return st;
+    // ---- results: poses back, write-back into the resident state, outlier list
+    const int cap = std::max(0, std::min(res->outlier_capacity, w->cfg.max_observations));
+    const int items = std::max(std::max(P * 7, L), E);
+    wn::k_win_finish<<<std::max(1, std::min((items + 255) / 256, 1024)), 256, 0, s>>>(W, h->batch, P, L, E, 1, w->d_pose_out.as<double>(),
+                                                                                     w->d_outliers.as<int>(), cap);
+    CK(cudaGetLastError());
+    double *pose_h = reinterpret_cast<double *>(w->h_small.as<char>() + 4096);
+    int *out_h = reinterpret_cast<int *>(w->h_small.as<char>() + 4096 + 56 * (size_t)maxF);
+    int *cnt_h = w->h_small.as<int>() + 2 * maxF;
+    CK(cudaMemcpyAsync(pose_h, w->d_pose_out.p, 56 * (size_t)P, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(cnt_h, w->d_counters.p, 12, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const int n_out = (E > 0) ? cnt_h[2] : 0;
+    const int n_copy = std::min(n_out, cap);
+    if (n_copy > 0) {
+        CK(cudaMemcpyAsync(out_h, w->d_outliers.p, 8 * (size_t)n_copy, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    if (res->pose_tq) memcpy(res->pose_tq, pose_h, 56 * (size_t)P);
+    {   // (feature id, signature id) pairs, sorted: the order of Optimizer.cpp:283-297 (features ascending, frames ascending)
+        std::vector<std::pair<int64_t, int64_t>> outl((size_t)n_copy);
+        for (int k = 0; k < n_copy; ++k) outl[(size_t)k] = {w->point_id_of_slot[(size_t)out_h[2 * k]], w->frame_id_of_slot[(size_t)out_h[2 * k + 1]]};
+        std::sort(outl.begin(), outl.end());
+        for (int k = 0; k < n_copy; ++k) {
+            if (res->outlier_point_id) res->outlier_point_id[k] = outl[(size_t)k].first;
+            if (res->outlier_frame_id) res->outlier_frame_id[k] = outl[(size_t)k].second;
+        }
+    }
+    const LMState &ls = h->st_host[0];
+    res->n_outliers = n_out; res->status = ls.status;
+    for (int k = 0; k < 2; ++k) { res->iterations_run[k] = ls.iterations_run[k]; res->trials_run[k] = ls.trials_run[k]; res->stop_reason[k] = ls.stop[k]; }
+    res->chi2_initial = ls.chi_initial; res->chi2_pass1 = ls.chi_pass[0]; res->chi2_final = ls.chi_pass[1];
+    res->h2d_bytes = h2d;
+    res->d2h_bytes = 56 * (int64_t)P + 8 * (int64_t)n_copy + 20 + (int64_t)sizeof(LMState);
+    w->h2d_total += h2d;
+    return ls.status;
 }
 
 void *visfs_ba_host_alloc(size_t bytes) {
