@@ -213,7 +213,9 @@ def workload_config(args):
 def single_window_numbers(ba, O, cores, quick):
     """C1 and C2 as single windows: device LM time, end-to-end call time, CPU oracle time."""
     out = {}
-    for name, w in (("c1", synth.config_c1()), ("c2", synth.config_c2())):
+    # c0: the window the reference actually runs (corelib/include/Parameters.h:148,161: LocalMap/MapSize 5 + 1 frames,
+    # Tracker/MaxFeature 300 -> <= 1 800 edges); c1 / c2: BASELINE.json configs[0] / configs[1]
+    for name, w in (("c0", synth.make_window(6, 300, layout="all", seed=synth.BASE_SEED + 10)), ("c1", synth.config_c1()), ("c2", synth.config_c2())):
         packed = ba.prepare_batch([w], pinned=True, float_obs=True)
         for _ in range(3):
             ba.solve_packed(packed)
@@ -258,6 +260,68 @@ def single_window_numbers(ba, O, cores, quick):
             entry["local_optimize_error"] = str(e)[:200]
         out[name] = entry
     return out
+
+
+def resident_window_numbers(ba, quick):
+    """per-frame cost of the reference's real window (6 frames, ~300 features per frame) when the local
+    map stays in HBM and only LocalMap's deltas travel (visfs_ba_window_*), against handing the whole window over every frame
+    (visfs_ba_solve with page-locked float buffers).  Same sequence, same results (tests/test_gpu_window.py)."""
+    from visfs_b200 import capi
+    n_frames, views = (16 if quick else 40), 6
+    seq = synth.make_window(n_frames, 50 * n_frames, views=views, layout="consecutive", seed=synth.BASE_SEED + 11)
+    first_seen = np.full(seq["n_points"], 10**9)
+    np.minimum.at(first_seen, seq["edge_point"], seq["edge_pose"])
+    win = capi.ResidentWindow(ba, views + 1, 4096, 32768, fx=seq["fx"], fy=seq["fy"], cx=seq["cx"], cy=seq["cy"], bf=seq["bf"],
+                              pixel_variance=seq["pixel_variance"], huber_delta=seq["huber_delta"], iterations=seq["iterations"])
+    frames, obs = [], {}
+    t_res, t_full, h2d_res, h2d_full, edges, solves = 0.0, 0.0, 0, 0, 0, 0
+    for f in range(n_frames):
+        fid = int(seq["pose_id"][f])
+        sel = np.nonzero(seq["edge_pose"] == f)[0]
+        new = np.unique(seq["edge_point"][sel][first_seen[seq["edge_point"][sel]] == f])
+        pid = seq["point_id"][seq["edge_point"][sel]]
+        ob32 = seq["edge_obs"][sel].astype(np.float32)
+        before = win.h2d_bytes_total()
+        t0 = time.perf_counter()
+        if len(new):
+            win.set_points(seq["point_id"][new], seq["point_xyz"][new])
+        win.insert_frame(fid, seq["pose_tq"][f], pid, ob32, seq["edge_kind"][sel])
+        frames.append(f)
+        if len(frames) > views:
+            old = frames.pop(0)
+            win.remove_frame(int(seq["pose_id"][old]))
+        r = win.solve(fid - 1) if len(frames) >= 2 else None
+        if r is not None and r["outliers"]:
+            win.remove_observations([k[0] for k in r["outliers"]], [k[1] for k in r["outliers"]])
+        dt = time.perf_counter() - t0
+        if r is None or len(frames) < views:
+            continue
+        t_res += dt; h2d_res += win.h2d_bytes_total() - before; edges += r["n_edges"]; solves += 1
+        # the same window handed over whole (the plain C-ABI call the C++ shim makes), marshalled before the clock starts
+        keep = np.isin(seq["edge_pose"], frames)
+        lm = np.unique(seq["edge_point"][keep])
+        remap = -np.ones(seq["n_points"], dtype=np.int64); remap[lm] = np.arange(len(lm))
+        fmap = -np.ones(seq["n_poses"], dtype=np.int64); fmap[frames] = np.arange(len(frames))
+        w = dict(seq)
+        w.update(n_poses=len(frames), n_points=len(lm), n_edges=int(keep.sum()), pose_tq=seq["pose_tq"][frames], pose_id=seq["pose_id"][frames],
+                 pose_fixed=(seq["pose_id"][frames] == fid - 1).astype(np.uint8), point_xyz=seq["point_xyz"][lm], point_id=seq["point_id"][lm],
+                 point_fixed=seq["point_fixed"][lm], edge_obs=seq["edge_obs"][keep], edge_pose=fmap[seq["edge_pose"][keep]].astype(np.int32),
+                 edge_point=remap[seq["edge_point"][keep]].astype(np.int32), edge_kind=seq["edge_kind"][keep])
+        for k in ("link_from", "link_to", "link_tq", "n_links"):
+            w.pop(k, None)
+        packed = ba.prepare_batch([w], pinned=True, float_obs=True)
+        ba.solve_packed(packed)
+        t1 = time.perf_counter()
+        ba.solve_packed(packed)
+        t_full += time.perf_counter() - t1
+        h2d_full += int(ba.timing()["h2d_bytes"])
+    win.close()
+    n = max(solves, 1)
+    return {"workload": f"{n_frames}-frame sequence through a {views}-frame local map, ~{edges // n} edges per solve, root = newest - 1",
+            "solves": solves, "per_frame_ms_resident": 1e3 * t_res / n, "per_frame_ms_full_call": 1e3 * t_full / n,
+            "h2d_bytes_per_frame_resident": h2d_res // n, "h2d_bytes_per_frame_full_call": h2d_full // n,
+            "note": "resident: set_points + insert_frame + remove_frame + solve + remove_observations per frame (ctypes calls included); "
+                    "full call: one visfs_ba_solve on a pre-marshalled page-locked window (no marshalling in the clock)"}
 
 
 def global_ba_numbers(ba, dist, world, rank, local, barrier, reduce_max, reduce_min, quick, use_oracle):
@@ -555,6 +619,11 @@ def run_gpu(args):
         line["single_window"] = single_window_numbers(ba, O, cores, args.quick)
     elif world == 1:
         line["single_window"] = single_window_numbers(ba, None, 1, args.quick)
+    if world == 1:
+        try:
+            line["resident_window"] = resident_window_numbers(ba, args.quick)
+        except Exception as exc:  # reported, never silently dropped
+            line["resident_window"] = {"error": repr(exc)[:300]}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -318,13 +318,6 @@ __global__ void __launch_bounds__(kThreads, PPT == 1 ? 2 : 1) k_build(Batch B) {
 #include "ba_solve.cuh"
 namespace visfs {
 
-}  // namespace visfs
-#include "ba_update.cuh"
-namespace visfs {
-
-// ------------------------------------------------------------------------------------------------
-// LM control (g2o OptimizationAlgorithmLevenberg::solve / GaussNewton::solve), one warp per window
-// ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void finish_pass(LMState &st, int stop, int *n_running) {
     st.done = 1;
     st.stop[st.pass] = stop;
@@ -333,66 +326,15 @@ __device__ __forceinline__ void finish_pass(LMState &st, int stop, int *n_runnin
     atomicSub(n_running, 1);
 }
 
-__global__ void k_control_init(Batch B) {
-    const int w = blockIdx.x;
+// One LM decision of window w (g2o OptimizationAlgorithmLevenberg::solve after the trial has been evaluated), run by one warp:
+// as the kernel k_control (large windows), or by the last CTA of k_update that finishes the window's trial (small windows).
+__device__ __forceinline__ void control_step(const Batch &B, int w, int lane) {
     const WinDesc &wd = B.win[w];
     LMState &st = B.st[w];
-    if (st.done) return;
-    const int lane = threadIdx.x;
-    const int F = st.F;
-    const double *part = B.part + wd.part_off;
-    const size_t stride = (size_t)wd.part_stride;
-    double md = 0.0;
-    const int *hidx = B.pose_hidx + wd.pose_off;
-    for (int idx = lane; idx < F * 6; idx += 32) {
-        double s = 0.0;
-        for (int c = 0; c < wd.n_chunks; ++c) s += part[(size_t)c * stride + idx];
-        const int i = idx / 6, a = idx - 6 * i;
-        for (int k = 0; k < wd.n_link; ++k) {   // diag(H_pp) of the odometry links (k_link_lin ran at the accepted state)
-            const double *rec = B.link_lin + (size_t)(wd.link_off + k) * kLinkStride;
-            if (hidx[B.link_from[wd.link_off + k]] == i) s += rec[kLkHii + 7 * a];
-            if (hidx[B.link_to[wd.link_off + k]] == i) s += rec[kLkHjj + 7 * a];
-        }
-        md = fmax(md, fabs(s));
-    }
-    double chi = 0.0;
-    for (int k = lane; k < wd.n_link; k += 32) chi += B.link_lin[(size_t)(wd.link_off + k) * kLinkStride + kLkChi];
-    for (int c = lane; c < wd.n_chunks; c += 32) { chi += part[(size_t)c * stride + F * 6]; md = fmax(md, part[(size_t)c * stride + F * 6 + 1]); }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        chi += __shfl_down_sync(0xffffffffu, chi, o);
-        md = fmax(md, __shfl_down_sync(0xffffffffu, md, o));
-    }
-    if (lane == 0) {
-        st.cur_chi = chi;
-        st.chi_last_trial = chi;
-        if (st.pass == 0) st.chi_initial = chi;
-        st.lambda = 1e-5 * md;
-        st.ni = 2.0;
-        st.iter = 0; st.qmax = 0;
-        st.pcg_residual = -1.0;
-        if (st.err != 0) finish_pass(st, VISFS_BA_STOP_NOT_RUN, B.n_running);   // rejected by the structure kernels: no trial runs
-        else if (st.F + st.NL == 0) finish_pass(st, VISFS_BA_STOP_EMPTY, B.n_running);
-        else if (wd.max_iter <= 0) finish_pass(st, VISFS_BA_STOP_ITERATIONS, B.n_running);
-    }
-}
-
-// adjacent equal keys of the sorted (window, point, pose) list = duplicate edges
-__global__ void k_dup_keys(const unsigned long long *keys, int n, int *flag) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x + 1; i < n; i += gridDim.x * blockDim.x)
-        if (keys[i] == keys[i - 1]) *flag = 1;
-}
-
-__global__ void k_control(Batch B) {
-    const int w = blockIdx.x;
-    const WinDesc &wd = B.win[w];
-    LMState &st = B.st[w];
-    if (st.done) return;
-    const int lane = threadIdx.x;
     double chi = 0.0, sl = 0.0;
-    for (int c = lane; c < wd.n_chunks; c += 32) {
-        chi += B.part2[2 * (size_t)(wd.chunk_off + c)];
-        sl += B.part2[2 * (size_t)(wd.chunk_off + c) + 1];
+    for (int c = lane; c < wd.n_chunks; c += 32) {   // (read at L2: written by other CTAs of the same launch)
+        chi += __ldcg(&B.part2[2 * (size_t)(wd.chunk_off + c)]);
+        sl += __ldcg(&B.part2[2 * (size_t)(wd.chunk_off + c) + 1]);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -441,6 +383,92 @@ __global__ void k_control(Batch B) {
     st.qmax = 0;
     if (terminate) finish_pass(st, VISFS_BA_STOP_TERMINATE, B.n_running);
     else if (st.iter >= wd.max_iter) finish_pass(st, VISFS_BA_STOP_ITERATIONS, B.n_running);
+}
+
+}  // namespace visfs
+#include "ba_update.cuh"
+namespace visfs {
+
+// ------------------------------------------------------------------------------------------------
+// LM control (g2o OptimizationAlgorithmLevenberg::solve / GaussNewton::solve), one warp per window
+// ------------------------------------------------------------------------------------------------
+
+constexpr int kCtlInitThreads = 256;
+
+// One CTA per window.  The partial sums of k_init (per chunk: diag(H_pp) [6F], chi2, max |diag H_ll|) are folded with many
+// independent loads in flight: item (entry, group) adds the chunks c = group, group + ng, ...
+__global__ void __launch_bounds__(kCtlInitThreads) k_control_init(Batch B) {
+    const int w = blockIdx.x;
+    const WinDesc &wd = B.win[w];
+    LMState &st = B.st[w];
+    if (st.done) return;
+    __shared__ double s_part[kCtlInitThreads];
+    __shared__ double s_red[32];
+    const int tid = threadIdx.x;
+    const int F = st.F;
+    const int ne = F * 6 + 2;                       // entries per chunk: diag(H_pp), chi2, max |diag H_ll|
+    const double *part = B.part + wd.part_off;
+    const size_t stride = (size_t)wd.part_stride;
+    const int ng = max(1, min(8, kCtlInitThreads / ne));
+    double md = 0.0, chi = 0.0;
+    if (tid < ne * ng) {
+        const int ent = tid % ne, g = tid / ne;
+        const bool is_max = ent == F * 6 + 1;
+        double acc = 0.0;
+        int c = g;
+        for (; c + 7 * ng < wd.n_chunks; c += 8 * ng) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = part[(size_t)(c + u * ng) * stride + ent];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc = is_max ? fmax(acc, v[u]) : acc + v[u];
+        }
+        for (; c < wd.n_chunks; c += ng) { const double v = part[(size_t)c * stride + ent]; acc = is_max ? fmax(acc, v) : acc + v; }
+        s_part[tid] = acc;
+    }
+    __syncthreads();
+    if (tid < ne) {
+        const bool is_max = tid == F * 6 + 1;
+        double acc = s_part[tid];
+        for (int g = 1; g < ng; ++g) acc = is_max ? fmax(acc, s_part[g * ne + tid]) : acc + s_part[g * ne + tid];
+        if (tid < F * 6) {
+            const int i = tid / 6, a = tid - 6 * i;
+            const int *hidx = B.pose_hidx + wd.pose_off;
+            for (int k = 0; k < wd.n_link; ++k) {   // diag(H_pp) of the odometry links (k_link_lin ran at the accepted state)
+                const double *rec = B.link_lin + (size_t)(wd.link_off + k) * kLinkStride;
+                if (hidx[B.link_from[wd.link_off + k]] == i) acc += rec[kLkHii + 7 * a];
+                if (hidx[B.link_to[wd.link_off + k]] == i) acc += rec[kLkHjj + 7 * a];
+            }
+            md = fabs(acc);
+        } else if (is_max) md = acc;
+        else chi = acc;
+    }
+    for (int k = tid; k < wd.n_link; k += kCtlInitThreads) chi += B.link_lin[(size_t)(wd.link_off + k) * kLinkStride + kLkChi];
+    chi = block_sum(chi, s_red);
+    md = block_max(md, s_red);
+    if (tid == 0) {
+        st.cur_chi = chi;
+        st.chi_last_trial = chi;
+        if (st.pass == 0) st.chi_initial = chi;
+        st.lambda = 1e-5 * md;
+        st.ni = 2.0;
+        st.iter = 0; st.qmax = 0;
+        st.pcg_residual = -1.0;
+        if (st.err != 0) finish_pass(st, VISFS_BA_STOP_NOT_RUN, B.n_running);   // rejected by the structure kernels: no trial runs
+        else if (st.F + st.NL == 0) finish_pass(st, VISFS_BA_STOP_EMPTY, B.n_running);
+        else if (wd.max_iter <= 0) finish_pass(st, VISFS_BA_STOP_ITERATIONS, B.n_running);
+    }
+}
+
+// adjacent equal keys of the sorted (window, point, pose) list = duplicate edges
+__global__ void k_dup_keys(const unsigned long long *keys, int n, int *flag) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x + 1; i < n; i += gridDim.x * blockDim.x)
+        if (keys[i] == keys[i - 1]) *flag = 1;
+}
+
+__global__ void k_control(Batch B) {
+    if (B.st[blockIdx.x].done) return;
+    control_step(B, blockIdx.x, threadIdx.x);
 }
 
 // ------------------------------------------------------------------------------------------------

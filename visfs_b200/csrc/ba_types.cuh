@@ -88,6 +88,7 @@ struct Batch {
     double *part2;                   // [n_chunks][2] chi2 / scale partials of the update kernel
     double *xp;                      // [tot_pose][6] pose step per hessian index (window-local)
     int *n_running;                  // windows still running in the current pass
+    int *ctl_count;                  // [n_win] CTAs of k_update that have finished this trial: the last one runs the LM controller
     const Tile *tiles;               // tile table, chunk c owns tiles [chunk_tile_off[c], chunk_tile_off[c + 1])
     const int *chunk_tile_off;       // [n_chunks + 1]
     const Tile *wtiles;              // warp tiles of k_update (<= 32 edges, whole landmarks), same indexing

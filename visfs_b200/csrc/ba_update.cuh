@@ -294,7 +294,20 @@ __global__ void __launch_bounds__(kUpdThreads, 2) k_update(Batch B) {
     }
     const double chi = block_sum(chi_acc, sm.red);
     const double sc = block_sum(scale_acc, sm.red);
-    if (tid == 0) { B.part2[2 * (size_t)blockIdx.x] = chi; B.part2[2 * (size_t)blockIdx.x + 1] = sc; }
+    // The CTA that finishes a window's trial last runs the LM controller (one launch less per trial).  Nobody reads the LM
+    // state of the window any more at that point: every other CTA of the window has taken its ticket at its very end.
+    __shared__ int s_last;
+    if (tid == 0) {
+        B.part2[2 * (size_t)blockIdx.x] = chi; B.part2[2 * (size_t)blockIdx.x + 1] = sc;
+        __threadfence();
+        s_last = atomicAdd(&B.ctl_count[ck.win], 1) == wd.n_chunks - 1;
+    }
+    __syncthreads();
+    if (s_last && warp == 0) {
+        __threadfence();
+        if (lane == 0) B.ctl_count[ck.win] = 0;
+        control_step(B, ck.win, lane);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

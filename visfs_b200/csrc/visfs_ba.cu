@@ -99,7 +99,7 @@ struct visfs_ba_handle {
     // device memory
     DevBuf d_st, d_pose, d_point, d_pose_flags, d_lm_flags, d_pose_hidx, d_pose_active, d_point_hidx,
         d_lm_edge_off, d_obs_u, d_obs_v, d_obs_r, d_edge_pose, d_edge_point, d_edge_orig, d_covis, d_part, d_part2, d_xp,
-        d_n_running, d_tiles, d_tile_off, d_tile_cnt, d_wtiles, d_wtile_off;
+        d_n_running, d_ctl_count, d_tiles, d_tile_off, d_tile_cnt, d_wtiles, d_wtile_off;
     // the caller's arrays, window and chunk descriptors: ONE device buffer with the layout of the pinned staging buffer,
     // filled by ONE H2D copy (a single-window call is latency-bound: ten small copies cost ~50 us)
     DevBuf d_in;
@@ -258,7 +258,7 @@ Batch make_batch(visfs_ba_handle *h) {
     b.edge_pose = h->d_edge_pose.as<int>(); b.edge_point = h->d_edge_point.as<int>();
     b.edge_orig = h->sorted ? nullptr : h->d_edge_orig.as<int>();
     b.covis = h->d_covis.as<unsigned>(); b.part = h->d_part.as<double>(); b.part2 = h->d_part2.as<double>();
-    b.xp = h->d_xp.as<double>(); b.n_running = h->d_n_running.as<int>();
+    b.xp = h->d_xp.as<double>(); b.n_running = h->d_n_running.as<int>(); b.ctl_count = h->d_ctl_count.as<int>();
     b.dbg = nullptr; b.dbg_lambda = -1.0;
     b.tot_link = h->tot_link;
     b.link_win = h->d_link_win.as<int>(); b.link_from = h->d_link_from.as<int>(); b.link_to = h->d_link_to.as<int>();
@@ -419,7 +419,7 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs, const DevIn
         CK(h->d_info.reserve(sizeof(long long) * 4)); CK(h->d_cnt.reserve(sizeof(int) * 4));
     }
     CK(h->d_part2.reserve(sizeof(double) * 2 * std::max(std::max(h->n_chunks, 1), std::max(h->grid_build_l, h->grid_update_l))));
-    CK(h->d_xp.reserve(sizeof(double) * 6 * P)); CK(h->d_n_running.reserve(sizeof(int) * 4));
+    CK(h->d_xp.reserve(sizeof(double) * 6 * P)); CK(h->d_n_running.reserve(sizeof(int) * 4)); CK(h->d_ctl_count.reserve(sizeof(int) * (size_t)n));
     const size_t max_tiles = 2 * E / (kTileEdges + 1) + L / kTileLm + 2 * (size_t)h->n_chunks + 8;
     CK(h->d_tiles.reserve(sizeof(Tile) * max_tiles));
     CK(h->d_tile_off.reserve(sizeof(int) * (h->n_chunks + 2))); CK(h->d_tile_cnt.reserve(sizeof(int) * (h->n_chunks + 2)));
@@ -579,7 +579,7 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs, const DevIn
             volume = std::max(volume, (long long)d.n_parts * d.part_stride);
         }
         // worth an extra launch (~3 us) from about 0.8 MB per window (C2: 1.9 MB, C1: 0.5 MB)
-        h->batch.parts_reduced = (n <= 8 && max_parts >= 4 && volume >= 100000 && !getenv("VISFS_BA_NO_REDUCE")) ? 1 : 0;
+        h->batch.parts_reduced = (n <= 8 && max_parts >= 4 && volume >= (getenv("VISFS_BA_REDUCE_MIN") ? atoll(getenv("VISFS_BA_REDUCE_MIN")) : 100000) && !getenv("VISFS_BA_NO_REDUCE")) ? 1 : 0;
         h->reduce_grid = std::max(1, std::min((max_stride + 255) / 256, 64));
     }
     h->batch_ctl = h->batch;
@@ -615,6 +615,7 @@ int reset_state(visfs_ba_handle *h) {
     const int gx = std::max(1, std::min((items + 255) / 256, 4096));
     k_reset<<<gx, 256, 0, h->stream>>>(B, h->in.pose, h->in.point, h->in.pfix, h->in.lfix);
     CK(cudaMemsetAsync(h->d_n_running.p, 0, sizeof(int) * 4, h->stream));
+    CK(cudaMemsetAsync(h->d_ctl_count.p, 0, sizeof(int) * (size_t)std::max(h->n_win, 1), h->stream));
     CK(cudaGetLastError());
     h->launches += 1;
     return VISFS_BA_OK;
@@ -674,12 +675,10 @@ int enqueue_body(visfs_ba_handle *h) {
     k_solve<<<h->n_win, kSolveThreads, h->solve_smem, h->stream>>>(h->batch);
     ev_end(h, ev);
     ev = ev_begin(h, EV_UPDATE);
-    if (h->n_chunks) k_update<<<h->n_chunks, kUpdThreads, sizeof(UpdateSmem), h->stream>>>(h->batch);
+    if (h->n_chunks) k_update<<<h->n_chunks, kUpdThreads, sizeof(UpdateSmem), h->stream>>>(h->batch);   // (its last CTA per window runs the LM controller)
+    else k_control<<<h->n_win, 32, 0, h->stream>>>(h->batch);
     ev_end(h, ev);
-    ev = ev_begin(h, EV_OTHER);
-    k_control<<<h->n_win, 32, 0, h->stream>>>(h->batch);
-    ev_end(h, ev);
-    h->launches += h->n_chunks ? 3 : 2;
+    h->launches += 3;
     return VISFS_BA_OK;
 }
 
@@ -1201,7 +1200,7 @@ int run_pass(visfs_ba_handle *h, int pass) {
         k_sync_buffers<<<dim3((unsigned)h->grid_lm_x, (unsigned)h->n_win), 256, 0, s>>>(B);
         if (h->n_chunks) k_init<<<h->n_chunks, kUpdThreads, sizeof(InitSmem), s>>>(B);
         if (h->tot_link > 0) { k_link_lin<<<(h->tot_link + 63) / 64, 64, 0, s>>>(B); h->launches += 1; }
-        k_control_init<<<h->n_win, 32, 0, s>>>(B);
+        k_control_init<<<h->n_win, kCtlInitThreads, 0, s>>>(B);
         h->launches += 3;
     }
     ev_end(h, ev);
@@ -1538,7 +1537,7 @@ void visfs_ba_destroy(visfs_ba_handle *h) {
     }
     DevBuf *bufs[] = {&h->d_in, &h->d_st, &h->d_pose, &h->d_point, &h->d_pose_flags, &h->d_lm_flags, &h->d_pose_hidx,
                       &h->d_pose_active, &h->d_point_hidx, &h->d_lm_edge_off, &h->d_obs_u, &h->d_obs_v, &h->d_obs_r, &h->d_edge_pose,
-                      &h->d_edge_point, &h->d_edge_orig, &h->d_covis, &h->d_part, &h->d_part2, &h->d_xp, &h->d_n_running,
+                      &h->d_edge_point, &h->d_edge_orig, &h->d_covis, &h->d_part, &h->d_part2, &h->d_xp, &h->d_n_running, &h->d_ctl_count,
                       &h->d_out_pose, &h->d_out_point, &h->d_out_level, &h->d_tmp, &h->d_tmp2, &h->d_keys, &h->d_keys2, &h->d_perm, &h->d_tiles, &h->d_tile_off, &h->d_tile_cnt, &h->d_wtiles, &h->d_wtile_off,
                       &h->d_link_win, &h->d_link_from, &h->d_link_to, &h->d_link_m, &h->d_link_lin};
     for (DevBuf *b : bufs) b->release();
@@ -1885,7 +1884,7 @@ int visfs_ba_debug_trial(visfs_ba_handle *h, const visfs_ba_problem *problem, do
         k_sync_buffers<<<dim3((unsigned)h->grid_lm_x, 1u), 256, 0, s>>>(h->batch);
         if (h->n_chunks) k_init<<<h->n_chunks, kUpdThreads, sizeof(InitSmem), s>>>(h->batch);
         if (h->tot_link > 0) k_link_lin<<<(h->tot_link + 63) / 64, 64, 0, s>>>(h->batch);
-        k_control_init<<<1, 32, 0, s>>>(h->batch);
+        k_control_init<<<1, kCtlInitThreads, 0, s>>>(h->batch);
         CK(cudaMemcpyAsync(&before, h->d_st.p, sizeof(LMState), cudaMemcpyDeviceToHost, s));
         CK(dbg.reserve(sizeof(double) * (ntri_max + nmax + 8)));
         CK(cudaMemsetAsync(dbg.p, 0, sizeof(double) * (ntri_max + nmax + 8), s));
