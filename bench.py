@@ -273,26 +273,46 @@ def resident_window_numbers(ba, quick):
     np.minimum.at(first_seen, seq["edge_point"], seq["edge_pose"])
     win = capi.ResidentWindow(ba, views + 1, 4096, 32768, fx=seq["fx"], fy=seq["fy"], cx=seq["cx"], cy=seq["cy"], bf=seq["bf"],
                               pixel_variance=seq["pixel_variance"], huber_delta=seq["huber_delta"], iterations=seq["iterations"])
-    frames, obs = [], {}
-    t_res, t_full, h2d_res, h2d_full, edges, solves = 0.0, 0.0, 0, 0, 0, 0
+    # every array a frame hands over is converted BEFORE the clock starts (the harness' numpy work is not the product's)
+    import ctypes as C
+    lib, W = ba.lib, win.w
+    I64, F64, F32, U8 = capi._i64p, capi._dp, C.POINTER(C.c_float), capi._u8p
+    per_frame = []
     for f in range(n_frames):
-        fid = int(seq["pose_id"][f])
         sel = np.nonzero(seq["edge_pose"] == f)[0]
         new = np.unique(seq["edge_point"][sel][first_seen[seq["edge_point"][sel]] == f])
-        pid = seq["point_id"][seq["edge_point"][sel]]
-        ob32 = seq["edge_obs"][sel].astype(np.float32)
+        per_frame.append(dict(
+            fid=int(seq["pose_id"][f]), tq=np.ascontiguousarray(seq["pose_tq"][f]),
+            new_id=np.ascontiguousarray(seq["point_id"][new], dtype=np.int64), new_xyz=np.ascontiguousarray(seq["point_xyz"][new]),
+            pid=np.ascontiguousarray(seq["point_id"][seq["edge_point"][sel]], dtype=np.int64),
+            ob=np.ascontiguousarray(seq["edge_obs"][sel], dtype=np.float32), kind=np.ascontiguousarray(seq["edge_kind"][sel], dtype=np.uint8)))
+    cap = 32768
+    r_fid, r_tq = np.zeros(views + 1, dtype=np.int64), np.zeros((views + 1, 7))
+    r_op, r_of = np.zeros(cap, dtype=np.int64), np.zeros(cap, dtype=np.int64)
+    res = capi.WindowResult(frame_id=capi._ptr(r_fid, I64), pose_tq=capi._ptr(r_tq, F64), outlier_point_id=capi._ptr(r_op, I64),
+                            outlier_frame_id=capi._ptr(r_of, I64), outlier_capacity=cap)
+    frames = []
+    t_res, t_full, h2d_res, h2d_full, edges, solves = 0.0, 0.0, 0, 0, 0, 0
+    for f in range(n_frames):
+        d = per_frame[f]
+        fid = d["fid"]
         before = win.h2d_bytes_total()
         t0 = time.perf_counter()
-        if len(new):
-            win.set_points(seq["point_id"][new], seq["point_xyz"][new])
-        win.insert_frame(fid, seq["pose_tq"][f], pid, ob32, seq["edge_kind"][sel])
+        if len(d["new_id"]):
+            ba._check(lib.visfs_ba_window_set_points(W, len(d["new_id"]), capi._ptr(d["new_id"], I64), capi._ptr(d["new_xyz"], F64), None))
+        ba._check(lib.visfs_ba_window_insert_frame(W, fid, capi._ptr(d["tq"], F64), len(d["pid"]), capi._ptr(d["pid"], I64),
+                                                   capi._ptr(d["ob"], F32), capi._ptr(d["kind"], U8)))
         frames.append(f)
         if len(frames) > views:
             old = frames.pop(0)
-            win.remove_frame(int(seq["pose_id"][old]))
-        r = win.solve(fid - 1) if len(frames) >= 2 else None
-        if r is not None and r["outliers"]:
-            win.remove_observations([k[0] for k in r["outliers"]], [k[1] for k in r["outliers"]])
+            ba._check(lib.visfs_ba_window_remove_frame(W, int(seq["pose_id"][old])))
+        r = None
+        if len(frames) >= 2:
+            ba._check(lib.visfs_ba_window_solve(W, fid - 1, C.byref(res)), allow=(0, 3, 4))
+            r = {"n_edges": res.n_edges}
+            k = min(res.n_outliers, cap)
+            if k:
+                ba._check(lib.visfs_ba_window_remove_observations(W, k, capi._ptr(r_op, I64), capi._ptr(r_of, I64)))
         dt = time.perf_counter() - t0
         if r is None or len(frames) < views:
             continue
@@ -320,8 +340,10 @@ def resident_window_numbers(ba, quick):
     return {"workload": f"{n_frames}-frame sequence through a {views}-frame local map, ~{edges // n} edges per solve, root = newest - 1",
             "solves": solves, "per_frame_ms_resident": 1e3 * t_res / n, "per_frame_ms_full_call": 1e3 * t_full / n,
             "h2d_bytes_per_frame_resident": h2d_res // n, "h2d_bytes_per_frame_full_call": h2d_full // n,
-            "note": "resident: set_points + insert_frame + remove_frame + solve + remove_observations per frame (ctypes calls included); "
-                    "full call: one visfs_ba_solve on a pre-marshalled page-locked window (no marshalling in the clock)"}
+            "note": "resident: set_points + insert_frame + remove_frame + solve + remove_observations per frame; full call: one visfs_ba_solve "
+                    "on a pre-marshalled page-locked window.  Neither clock contains host marshalling: the reference's std::map walk that the "
+                    "resident map makes unnecessary is single_window.*.local_optimize_marshal_ms.  At this size both are bound by the ~58 "
+                    "launches of the two-pass LM, the resident path adds ~10 short launches that build the window on the device"}
 
 
 def global_ba_numbers(ba, dist, world, rank, local, barrier, reduce_max, reduce_min, quick, use_oracle):

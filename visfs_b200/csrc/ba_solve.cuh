@@ -92,40 +92,26 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(Batch B) {
     }
     __syncthreads();
     tclk[1] = clock64();
-    // pass 1: pair blocks (each entry of S written by exactly one thread).  All partial sums of a thread are requested before
-    // the first one is used: the phase is bound by the latency of dependent L2 loads otherwise.
-    for (int i0 = 0; i0 < offd; i0 += 4 * kSolveThreads) {
-        double vv[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) { const int idx = i0 + tid + u * kSolveThreads; vv[u] = (idx < offd) ? part_sum(idx) : 0.0; }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int idx = i0 + tid + u * kSolveThreads;
-            if (idx >= offd) continue;
-            const double v = vv[u];
-            const int p = idx / 36, q = idx - p * 36;
-            int i = 0, base = 0, j;
-            if (all_pairs) {
-                while (base + (F - i) <= p) { base += F - i; ++i; }
-                j = i + (p - base);
-            } else {
-                while (base + (F - 1 - i) <= p) { base += F - 1 - i; ++i; }
-                j = i + 1 + (p - base);
-            }
-            const int a = q / 6, cc = q - a * 6;
-            if (i < j) S[tri(6 * j + cc, 6 * i + a)] = v;          // block (i,j) entry (a,cc) lives at lower (6j+cc, 6i+a)
-            else if (a >= cc) S[tri(6 * i + a, 6 * i + cc)] = v;   // diagonal block: lower half only
+    // pass 1: pair blocks (each entry of S written by exactly one thread)
+    for (int idx = tid; idx < offd; idx += kSolveThreads) {
+        const double v = part_sum(idx);
+        const int p = idx / 36, q = idx - p * 36;
+        int i = 0, base = 0, j;
+        if (all_pairs) {
+            while (base + (F - i) <= p) { base += F - i; ++i; }
+            j = i + (p - base);
+        } else {
+            while (base + (F - 1 - i) <= p) { base += F - 1 - i; ++i; }
+            j = i + 1 + (p - base);
         }
+        const int a = q / 6, cc = q - a * 6;
+        if (i < j) S[tri(6 * j + cc, 6 * i + a)] = v;          // block (i,j) entry (a,cc) lives at lower (6j+cc, 6i+a)
+        else if (a >= cc) S[tri(6 * i + a, 6 * i + cc)] = v;   // diagonal block: lower half only
     }
-    // pass 2: per-pose sums (requested before the barrier as well: they do not touch S)
-    double pv[2];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) { const int t2 = tid + u * kSolveThreads; pv[u] = (t2 < F * kHStride) ? part_sum(offd + t2) : 0.0; }
     __syncthreads();
-#pragma unroll
-    for (int u = 0; u < 2; ++u)
-    for (int t2 = tid + u * kSolveThreads; t2 < F * kHStride; t2 += 2 * kSolveThreads) {
-        const double v = (t2 < 2 * kSolveThreads) ? pv[u] : part_sum(offd + t2);
+    // pass 2: per-pose sums
+    for (int t2 = tid; t2 < F * kHStride; t2 += kSolveThreads) {
+        const double v = part_sum(offd + t2);
         const int i = t2 / kHStride, k = t2 - i * kHStride;
         if (k < 21) {
             int a = 0, rem = k;

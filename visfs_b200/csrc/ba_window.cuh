@@ -37,7 +37,7 @@ struct Win {
     int *act, *rank;             // [n_order] takes part / dense index (exclusive scan of act)
     int *rank_of_slot;           // [max_points] dense index or -1
     int *slot_of_rank;           // [max_points]
-    unsigned long long *key, *key_sorted;
+    unsigned *key, *key_sorted;  // (feature index * 32 + pose index), 0xffffffff = not part of this solve
     int *val, *val_sorted;
     int *counters;               // [0] features in the window, [1] edges, [2] outliers
 };
@@ -64,10 +64,10 @@ __global__ void k_win_rank(Win W) {
 __global__ void k_win_keys(Win W) {
     int n = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < W.n_pool; i += gridDim.x * blockDim.x) {
-        unsigned long long k = ~0ull;
+        unsigned k = 0xffffffffu;
         if (!W.ob_dead[i]) {
             const int p = W.frame_pose[W.ob_frame[i]], r = W.rank_of_slot[W.ob_point[i]];
-            if (p >= 0 && r >= 0) { k = ((unsigned long long)r << 24) | (unsigned long long)p; ++n; }
+            if (p >= 0 && r >= 0) { k = ((unsigned)r << 5) | (unsigned)p; ++n; }      // at most 32 frames (kMaxSmallPoses)
         }
         W.key[i] = k;
         W.val[i] = i;
@@ -128,6 +128,17 @@ __global__ void k_win_finish(Win W, Batch B, int P, int L, int E, int write_back
 __global__ void k_win_kill_frame(int *ob_frame, uint8_t *ob_dead, int n_pool, int fslot) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pool; i += gridDim.x * blockDim.x)
         if (ob_frame[i] == fslot) ob_dead[i] = 1;
+}
+
+// deltas arrive packed in one staging copy: scatter them into the tables
+__global__ void k_win_scatter_points(int n, const int *slot, const double *xyz, const uint8_t *fixed, const long long *id, double *point_xyz,
+                                     uint8_t *point_fixed, long long *point_id) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int s = slot[i];
+        point_xyz[3 * s] = xyz[3 * i]; point_xyz[3 * s + 1] = xyz[3 * i + 1]; point_xyz[3 * s + 2] = xyz[3 * i + 2];
+        point_fixed[s] = fixed[i];
+        point_id[s] = id[i];
+    }
 }
 
 __global__ void k_win_kill_list(uint8_t *ob_dead, const int *list, int n) {

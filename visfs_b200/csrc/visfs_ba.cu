@@ -1387,7 +1387,15 @@ struct visfs_ba_window {
     DevBuf d_frame_tq, d_frame_pose, d_pose_slot, d_point_xyz, d_point_fixed, d_point_id, d_order, d_ob_point, d_ob_frame, d_ob_obs,
         d_ob_kind, d_ob_dead, d_cnt, d_act, d_rank, d_rank_of_slot, d_slot_of_rank, d_key, d_key2, d_val, d_val2, d_counters, d_scan_tmp,
         d_sort_tmp, d_pose_out, d_outliers, d_list;
-    PinBuf h_small;
+    PinBuf h_small, h_stage;
+    DevBuf d_stage;
+    cudaEvent_t stage_done = nullptr;              // the last asynchronous copy out of h_stage
+    // page-locked staging for a delta: waits until the previous delta has left, returns the buffer
+    char *stage(size_t bytes) {
+        if (stage_done) cudaEventSynchronize(stage_done);
+        if (h_stage.reserve(bytes) != cudaSuccess || d_stage.reserve(bytes) != cudaSuccess) return nullptr;
+        return h_stage.as<char>();
+    }
     static uint64_t okey(int pslot, int fslot) { return ((uint64_t)(uint32_t)pslot << 8) | (uint32_t)fslot; }
 };
 
@@ -2026,9 +2034,10 @@ int visfs_ba_window_create(visfs_ba_handle *h, const visfs_ba_window_config *cfg
     R(w->d_frame_tq, 56 * F); R(w->d_frame_pose, 4 * F); R(w->d_pose_slot, 4 * F); R(w->d_point_xyz, 24 * L); R(w->d_point_fixed, L);
     R(w->d_point_id, 8 * L); R(w->d_order, 4 * L); R(w->d_ob_point, 4 * E); R(w->d_ob_frame, 4 * E); R(w->d_ob_obs, 12 * E);
     R(w->d_ob_kind, E); R(w->d_ob_dead, E); R(w->d_cnt, 4 * L); R(w->d_act, 4 * L); R(w->d_rank, 4 * L); R(w->d_rank_of_slot, 4 * L);
-    R(w->d_slot_of_rank, 4 * L); R(w->d_key, 8 * E); R(w->d_key2, 8 * E); R(w->d_val, 4 * E); R(w->d_val2, 4 * E); R(w->d_counters, 16);
+    R(w->d_slot_of_rank, 4 * L); R(w->d_key, 4 * E); R(w->d_key2, 4 * E); R(w->d_val, 4 * E); R(w->d_val2, 4 * E); R(w->d_counters, 16);
     R(w->d_pose_out, 56 * F); R(w->d_outliers, 8 * E); R(w->d_list, 4 * E);
     if (e == cudaSuccess) e = w->h_small.reserve(4096 + 56 * F + 8 * E);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&w->stage_done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMemsetAsync(w->d_ob_dead.p, 0, E, h->stream);
     if (e != cudaSuccess) { const int st = h->cuda_fail(e, "window allocation"); delete w; return st; }
     *out = w;
@@ -2039,6 +2048,7 @@ void visfs_ba_window_destroy(visfs_ba_window *w) {
     if (!w) return;
     cudaSetDevice(w->h->device);
     cudaStreamSynchronize(w->h->stream);
+    if (w->stage_done) cudaEventDestroy(w->stage_done);
     delete w;
 }
 
@@ -2048,28 +2058,38 @@ int visfs_ba_window_set_points(visfs_ba_window *w, int32_t n, const int64_t *poi
     if (!w) return VISFS_BA_ERR_INVALID;
     visfs_ba_handle *h = w->h;
     if (n < 0 || (n > 0 && (!point_id || !xyz))) return win_fail(w, VISFS_BA_ERR_INVALID, "set_points: null arrays");
+    if (n == 0) return VISFS_BA_OK;
     CK(cudaSetDevice(h->device));
     int fresh = 0;
     for (int i = 0; i < n; ++i) fresh += w->point_slot.find(point_id[i]) == w->point_slot.end();
     if (fresh > (int)w->free_points.size()) return win_fail(w, VISFS_BA_ERR_INVALID, "set_points: more features than max_points");
-    cudaStream_t s = h->stream;
+    // one packed delta [slot | xyz | id | fixed] -> one copy -> scatter on the device
+    const size_t N = (size_t)n, o_slot = 0, o_xyz = (4 * N + 15) & ~(size_t)15, o_id = o_xyz + 24 * N, o_fix = o_id + 8 * N, bytes = o_fix + N;
+    char *sg = w->stage(bytes);
+    if (!sg) return win_fail(w, VISFS_BA_ERR_CUDA, "set_points: staging allocation failed");
+    int *slots = reinterpret_cast<int *>(sg + o_slot);
     for (int i = 0; i < n; ++i) {
-        int slot;
         auto it = w->point_slot.find(point_id[i]);
         if (it == w->point_slot.end()) {
-            slot = w->free_points.back(); w->free_points.pop_back();
+            const int slot = w->free_points.back(); w->free_points.pop_back();
             w->point_slot.emplace(point_id[i], slot); w->point_order.emplace(point_id[i], slot);
             w->point_id_of_slot[(size_t)slot] = point_id[i];
             w->order_dirty = true;
-            CK(cudaMemcpyAsync(w->d_point_id.as<long long>() + slot, point_id + i, 8, cudaMemcpyHostToDevice, s));
-            w->h2d_total += 8;
-        } else slot = it->second;
-        const uint8_t fx = fixed ? fixed[i] : 0;
-        CK(cudaMemcpyAsync(w->d_point_xyz.as<double>() + 3 * (size_t)slot, xyz + 3 * (size_t)i, 24, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(w->d_point_fixed.as<uint8_t>() + slot, &fx, 1, cudaMemcpyHostToDevice, s));
-        w->h2d_total += 25;
+            slots[i] = slot;
+        } else slots[i] = it->second;
+        sg[o_fix + (size_t)i] = (char)(fixed ? fixed[i] : 0);
     }
-    CK(cudaStreamSynchronize(s));   // the caller's arrays (and `fx`) may go away
+    memcpy(sg + o_xyz, xyz, 24 * N);
+    memcpy(sg + o_id, point_id, 8 * N);
+    cudaStream_t s = h->stream;
+    char *dg = w->d_stage.as<char>();
+    CK(cudaMemcpyAsync(dg, sg, bytes, cudaMemcpyHostToDevice, s));
+    wn::k_win_scatter_points<<<std::max(1, std::min((n + 127) / 128, 64)), 128, 0, s>>>(
+        n, reinterpret_cast<const int *>(dg + o_slot), reinterpret_cast<const double *>(dg + o_xyz), reinterpret_cast<const uint8_t *>(dg + o_fix),
+        reinterpret_cast<const long long *>(dg + o_id), w->d_point_xyz.as<double>(), w->d_point_fixed.as<uint8_t>(), w->d_point_id.as<long long>());
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(w->stage_done, s));
+    w->h2d_total += (int64_t)bytes;
     return VISFS_BA_OK;
 }
 
@@ -2103,23 +2123,29 @@ int visfs_ba_window_insert_frame(visfs_ba_window *w, int64_t frame_id, const dou
     w->frame_id_of_slot[(size_t)fslot] = frame_id;
     cudaStream_t s = h->stream;
     const size_t at = w->pool.size(), n = (size_t)n_obs;
-    std::vector<int> of(n, fslot);
-    std::vector<uint8_t> ok(n, 0);
+    // one packed delta [pose | feature slots | frame slots | observations | kinds] -> one copy, the pieces are contiguous appends
+    const size_t o_pose = 0, o_ps = 64, o_fs = o_ps + 4 * n, o_obs = o_fs + 4 * n, o_kind = o_obs + 12 * n, bytes = o_kind + n;
+    char *sg = w->stage(bytes);
+    if (!sg) return win_fail(w, VISFS_BA_ERR_CUDA, "insert_frame: staging allocation failed");
+    memcpy(sg + o_pose, pose_tq, 56);
     for (size_t i = 0; i < n; ++i) {
         visfs_ba_window::Ob o{pslots[i], fslot, {obs_uvr[3 * i], obs_uvr[3 * i + 1], obs_uvr[3 * i + 2]}, (uint8_t)(kind ? kind[i] : 0), 0};
-        ok[i] = o.kind;
+        reinterpret_cast<int *>(sg + o_ps)[i] = o.pslot;
+        reinterpret_cast<int *>(sg + o_fs)[i] = fslot;
+        sg[o_kind + i] = (char)o.kind;
         w->ob_index[visfs_ba_window::okey(o.pslot, fslot)] = (int)(at + i);
         w->frame_obs[(size_t)fslot].push_back((int)(at + i)); w->point_obs[(size_t)o.pslot].push_back((int)(at + i));
         w->pool.push_back(o);
     }
-    CK(cudaMemcpyAsync(w->d_frame_tq.as<double>() + 7 * (size_t)fslot, pose_tq, 56, cudaMemcpyHostToDevice, s));
+    if (n) memcpy(sg + o_obs, obs_uvr, 12 * n);
+    CK(cudaMemcpyAsync(w->d_frame_tq.as<double>() + 7 * (size_t)fslot, sg + o_pose, 56, cudaMemcpyHostToDevice, s));
     if (n) {
-        CK(cudaMemcpyAsync(w->d_ob_point.as<int>() + at, pslots.data(), 4 * n, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(w->d_ob_frame.as<int>() + at, of.data(), 4 * n, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(w->d_ob_obs.as<float>() + 3 * at, obs_uvr, 12 * n, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(w->d_ob_kind.as<uint8_t>() + at, ok.data(), n, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(w->d_ob_point.as<int>() + at, sg + o_ps, 4 * n, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(w->d_ob_frame.as<int>() + at, sg + o_fs, 4 * n, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(w->d_ob_obs.as<float>() + 3 * at, sg + o_obs, 12 * n, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(w->d_ob_kind.as<uint8_t>() + at, sg + o_kind, n, cudaMemcpyHostToDevice, s));
     }
-    CK(cudaStreamSynchronize(s));
+    CK(cudaEventRecord(w->stage_done, s));
     w->h2d_total += 56 + (int64_t)(21 * n);
     return VISFS_BA_OK;
 }
@@ -2148,10 +2174,13 @@ int visfs_ba_window_remove_frame(visfs_ba_window *w, int64_t frame_id) {
 static int win_kill(visfs_ba_window *w, const std::vector<int> &list) {
     visfs_ba_handle *h = w->h;
     if (list.empty()) return VISFS_BA_OK;
-    CK(cudaMemcpyAsync(w->d_list.p, list.data(), 4 * list.size(), cudaMemcpyHostToDevice, h->stream));
+    char *sg = w->stage(4 * list.size());
+    if (!sg) return win_fail(w, VISFS_BA_ERR_CUDA, "staging allocation failed");
+    memcpy(sg, list.data(), 4 * list.size());
+    CK(cudaMemcpyAsync(w->d_list.p, sg, 4 * list.size(), cudaMemcpyHostToDevice, h->stream));
     wn::k_win_kill_list<<<std::max(1, std::min(((int)list.size() + 255) / 256, 64)), 256, 0, h->stream>>>(w->d_ob_dead.as<uint8_t>(), w->d_list.as<int>(), (int)list.size());
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaEventRecord(w->stage_done, h->stream));
     w->h2d_total += (int64_t)(4 * list.size());
     return VISFS_BA_OK;
 }
@@ -2265,7 +2294,7 @@ int visfs_ba_window_solve(visfs_ba_window *w, int64_t root_frame_id, visfs_ba_wi
     W.ob_kind = w->d_ob_kind.as<uint8_t>(); W.ob_dead = w->d_ob_dead.as<uint8_t>(); W.n_pool = n_pool;
     W.cnt = w->d_cnt.as<int>(); W.act = w->d_act.as<int>(); W.rank = w->d_rank.as<int>();
     W.rank_of_slot = w->d_rank_of_slot.as<int>(); W.slot_of_rank = w->d_slot_of_rank.as<int>();
-    W.key = w->d_key.as<unsigned long long>(); W.key_sorted = w->d_key2.as<unsigned long long>();
+    W.key = w->d_key.as<unsigned>(); W.key_sorted = w->d_key2.as<unsigned>();
     W.val = w->d_val.as<int>(); W.val_sorted = w->d_val2.as<int>(); W.counters = w->d_counters.as<int>();
     int L = 0, E = 0;
     if (n_pool > 0 && n_order > 0 && P > 0) {
@@ -2280,10 +2309,10 @@ int visfs_ba_window_solve(visfs_ba_window *w, int64_t root_frame_id, visfs_ba_wi
         CK(cub::DeviceScan::ExclusiveSum(w->d_scan_tmp.p, tb, W.act, W.rank, n_order, s));
         wn::k_win_rank<<<go, 256, 0, s>>>(W);
         wn::k_win_keys<<<gp, 256, 0, s>>>(W);
-        tb = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, tb, W.key, W.key_sorted, W.val, W.val_sorted, n_pool, 0, 64, s);
+        tb = 0;   // (all 32 bits: the keys of observations that take no part are 0xffffffff and must sort last)
+        cub::DeviceRadixSort::SortPairs(nullptr, tb, W.key, W.key_sorted, W.val, W.val_sorted, n_pool, 0, 32, s);
         CK(w->d_sort_tmp.reserve(tb));
-        CK(cub::DeviceRadixSort::SortPairs(w->d_sort_tmp.p, tb, W.key, W.key_sorted, W.val, W.val_sorted, n_pool, 0, 64, s));
+        CK(cub::DeviceRadixSort::SortPairs(w->d_sort_tmp.p, tb, W.key, W.key_sorted, W.val, W.val_sorted, n_pool, 0, 32, s));
         int *cnt_h = w->h_small.as<int>() + 2 * maxF;
         CK(cudaMemcpyAsync(cnt_h, w->d_counters.p, 8, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
