@@ -294,6 +294,49 @@ __device__ __forceinline__ void trailing_update(double *__restrict__ D, int LD, 
     }
 }
 
+// The same update for a front that ONE CTA owns: the solved panel rows are still in shared memory (T rows nb .. nb + m - 1 are
+// the rows base .. base + m - 1 of D), so the fragments come from there instead of L2.
+__device__ __forceinline__ void trailing_update_smem(double *__restrict__ D, int LD, const double *T, int nb, int base, int m, int t0, int tstep) {
+    const int lane = threadIdx.x & 31;
+    const int nt = (m + 31) >> 5;
+    const int ntiles = nt * (nt + 1) / 2;
+    const int gl = lane >> 2, tl = lane & 3;
+    for (int tile = t0; tile < ntiles; tile += tstep) {
+        int ti = (int)((sqrt(8.0 * (double)tile + 1.0) - 1.0) * 0.5);
+        while ((ti + 1) * (ti + 2) / 2 <= tile) ++ti;
+        while (ti * (ti + 1) / 2 > tile) --ti;
+        const int tj = tile - ti * (ti + 1) / 2;
+        const int xr = 32 * ti + gl, xc = 32 * tj + gl;          // rows relative to base
+        double acc[4][4][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+#pragma unroll 2
+        for (int kk = 0; kk < nb; kk += 4) {
+            const bool in = kk + tl < nb;
+            double a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                a[i] = (in && xr + 8 * i < m) ? T[(nb + xr + 8 * i) * kTP + kk + tl] : 0.0;
+                b[i] = (in && xc + 8 * i < m) ? T[(nb + xc + 8 * i) * kTP + kk + tl] : 0.0;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                double *p = D + (size_t)(base + xr + 8 * i) * LD + base + 32 * tj + 8 * j + 2 * tl;
+                asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(-acc[i][j][0]) : "memory");
+                asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p + 1), "d"(-acc[i][j][1]) : "memory");
+            }
+    }
+}
+
 // Back-substitution step of one panel: x_panel = L_kk^-T y_panel (Ls / ys / xs in shared memory, four lanes per row).
 // Leaves xs valid for all threads (ends with a barrier).  `lin` = the panel's L_kk^-T [kNB][kNB] in global memory.
 __device__ __forceinline__ void back_panel_x(const double *__restrict__ lin, const double *__restrict__ yrow, int k0, int nb,

@@ -148,7 +148,7 @@ struct visfs_ba_handle {
     dn::DenseMat dense{};
     int st_F_hint = 0;                // free poses of the current pass (host copy)
     bool use_mf = false;              // multifrontal nested-dissection Cholesky (ba_mf.cuh): long banded systems
-    DevBuf d_mf_meta, d_mf_fronts;
+    DevBuf d_mf_meta, d_mf_fronts, d_mf_touch;
     mf::Plan mf_plan{};
     std::vector<int> mf_level_off;    // problems of level l: [mf_level_off[l], mf_level_off[l + 1])
     DevBuf d_plan;
@@ -848,14 +848,32 @@ int plan_mf(visfs_ba_handle *h, int F) {
     int w = 1;
     for (int q = 0; q < N; ++q) w = std::max(w, q - before[first[comp[q]]]);
     if (w > mf::kMaxBand || N < 4 * w) return VISFS_BA_OK;
+    // which columns every arrow really couples with (device: the landmarks' pose lists; every rank of a partitioned run
+    // sees its own landmarks only, so the maps are merged with an integer MAX all-reduce)
+    const int n_arrow = (int)arrows.size();
+    std::vector<int> touch((size_t)n_arrow * F, 0);
+    if (n_arrow > 0) {
+        std::vector<int> arrow_of((size_t)F, -1);
+        for (int a = 0; a < n_arrow; ++a) arrow_of[(size_t)arrows[a]] = a;
+        CK(h->d_mf_touch.reserve(sizeof(int) * ((size_t)F + (size_t)n_arrow * F)));
+        int *d_arrow_of = h->d_mf_touch.as<int>(), *d_touch = d_arrow_of + F;
+        CK(cudaMemcpyAsync(d_arrow_of, arrow_of.data(), sizeof(int) * (size_t)F, cudaMemcpyHostToDevice, s));
+        CK(cudaMemsetAsync(d_touch, 0, sizeof(int) * (size_t)n_arrow * F, s));
+        mf::k_arrow_touch<<<std::max(1, std::min((h->tot_point + 255) / 256, 1024)), 256, 0, s>>>(h->batch, d_arrow_of, d_touch, F);
+        CK(cudaGetLastError());
+        const int st_ar = allreduce(h, d_touch, (size_t)n_arrow * F, ncclInt32, ncclMax);
+        if (st_ar) return st_ar;
+        CK(cudaMemcpyAsync(touch.data(), d_touch, sizeof(int) * (size_t)n_arrow * F, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    }
 
-    struct Node { int lo, hi, e0, e1, level, parent; std::vector<int> kids; };
+    struct Node { int lo, hi, e0, e1, level, parent; std::vector<int> kids; unsigned reach = 0; };   // reach: arrows coupled with the subtree
     std::vector<Node> nodes;
     // recursive bisection of the compressed range [lo, hi): returns the node that eliminates its separator (or the leaf)
     std::vector<std::array<int, 3>> stack;   // (lo, hi, parent) — children are created after their parent, levels fixed below
     struct Rec { static int build(std::vector<Node> &nodes, int lo, int hi, int w) {
         const int L = hi - lo;
-        Node nd{lo, hi, lo, hi, 0, -1, {}};
+        Node nd{lo, hi, lo, hi, 0, -1, {}, 0};
         if (L <= 9 || L <= w + 1) { nodes.push_back(nd); return (int)nodes.size() - 1; }
         const int m = lo + (L - w) / 2;
         nd.e0 = m; nd.e1 = m + w;
@@ -872,10 +890,20 @@ int plan_mf(visfs_ba_handle *h, int F) {
     } };
     int top = Rec::build(nodes, 0, N, w);
     if (!arrows.empty()) {
-        Node nd{0, N, -1, -1, nodes[top].level + 1, -1, {top}};   // e0 = -1: eliminates the arrows
+        Node nd{0, N, -1, -1, nodes[top].level + 1, -1, {top}, 0};   // e0 = -1: eliminates the arrows
         nodes.push_back(nd);
         nodes[top].parent = (int)nodes.size() - 1;
         top = (int)nodes.size() - 1;
+    }
+    // arrows a front can reach: those coupled with a column it eliminates, and whatever its children reach (children have
+    // smaller node indices than their parents: one ascending sweep)
+    for (size_t i = 0; i < nodes.size(); ++i) {
+        Node &nd = nodes[i];
+        if (nd.e0 >= 0)
+            for (int a = 0; a < n_arrow; ++a)
+                for (int q = nd.e0; q < nd.e1 && !(nd.reach >> a & 1u); ++q)
+                    if (touch[(size_t)a * F + comp[q]]) nd.reach |= 1u << a;
+        for (int k : nd.kids) nd.reach |= nodes[(size_t)k].reach;
     }
     // problems in level order (children before parents; ascending node index inside a level keeps the order deterministic)
     const int n_nodes = (int)nodes.size();
@@ -902,7 +930,7 @@ int plan_mf(visfs_ba_handle *h, int F) {
             ne = nd.e1 - nd.e0;
             for (int q = std::max(0, nd.lo - w); q < nd.lo; ++q) loc.push_back(comp[q]);
             for (int q = nd.hi; q < std::min(N, nd.hi + w); ++q) loc.push_back(comp[q]);
-            for (int a : arrows) loc.push_back(a);
+            for (int a = 0; a < n_arrow; ++a) if (nd.reach >> a & 1u) loc.push_back(arrows[a]);
         }
         mf::Prob &p = prob[i];
         p.ne = ne; p.nb = (int)loc.size() - ne;
@@ -955,6 +983,12 @@ int plan_mf(visfs_ba_handle *h, int F) {
     P.child = reinterpret_cast<const int *>(mb + o_child); P.pmap = reinterpret_cast<const int *>(mb + o_pmap);
     P.fronts = h->d_mf_fronts.as<double>(); P.linvt = P.fronts + d_len; P.x = P.linvt + linv_len;
     P.flag = h->d_cnt.as<int>() + 2;
+    P.prof = nullptr;
+    if (getenv("VISFS_BA_DENSE_PROF")) {
+        CK(h->d_dense_prof.reserve(sizeof(long long) * 2600));
+        CK(cudaMemsetAsync(h->d_dense_prof.p, 0, sizeof(long long) * 2600, s));
+        P.prof = h->d_dense_prof.as<long long>();
+    }
     h->use_mf = true;
     return VISFS_BA_OK;
 }
@@ -1125,7 +1159,7 @@ int enqueue_rest_large(visfs_ba_handle *h) {
         const size_t smem_b = sizeof(double) * ((size_t)dn::kNB * dn::kTP + 2 * dn::kNB + 6 * (2 * mf::kMaxBand + mf::kMaxArrow));
         const int nl = (int)h->mf_level_off.size() - 1;
         for (int l = 0; l < nl; ++l)
-            mf::k_mf_factor<<<h->mf_level_off[l + 1] - h->mf_level_off[l], dn::kThreadsD, smem_f, h->stream>>>(h->batch, h->mf_plan, h->mf_level_off[l]);
+            mf::k_mf_factor<<<h->mf_level_off[l + 1] - h->mf_level_off[l], dn::kThreadsD, smem_f, h->stream>>>(h->batch, h->mf_plan, h->mf_level_off[l], l);
         for (int l = nl - 1; l >= 0; --l)
             mf::k_mf_back<<<h->mf_level_off[l + 1] - h->mf_level_off[l], dn::kThreadsD, smem_b, h->stream>>>(h->batch, h->mf_plan, h->mf_level_off[l]);
         dn::DenseMat M{};
@@ -1248,6 +1282,17 @@ int run_resident(visfs_ba_handle *h) {
     CK(cudaMemcpyAsync(h->st_host.data(), h->d_st.p, sizeof(LMState) * h->n_win, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->has_run = true;
+    if (h->use_mf && h->mf_plan.prof) {
+        std::vector<long long> pr(2600);
+        cudaMemcpy(pr.data(), h->mf_plan.prof, sizeof(long long) * pr.size(), cudaMemcpyDeviceToHost);
+        const int nl = (int)h->mf_level_off.size() - 1;
+        for (int l = 0; l < nl; ++l) {
+            const long long *q = pr.data() + 8 * l;
+            fprintf(stderr, "[visfs_ba] mf level %d (%d fronts, CTA 0): tables %.1f  gather assembly %.1f  fence %.1f  panel %.1f  corner update %.1f  rest %.1f  total %.1f us\n", l,
+                    h->mf_level_off[l + 1] - h->mf_level_off[l], (q[1] - q[0]) * 1e-3, (q[2] - q[1]) * 1e-3, (q[3] - q[2]) * 1e-3, (q[4] - q[3]) * 1e-3,
+                    (q[5] - q[4]) * 1e-3, (q[6] - q[5]) * 1e-3, (q[6] - q[0]) * 1e-3);
+        }
+    }
     if (h->use_dense && h->dense.prof) {
         const int np = std::min(512, (h->dense.n + dn::kNB - 1) / dn::kNB);
         std::vector<long long> pr(2600);
@@ -1540,7 +1585,7 @@ void visfs_ba_destroy(visfs_ba_handle *h) {
     {
         DevBuf *lb[] = {&h->d_sky_first, &h->d_sky_off, &h->d_col_ptr, &h->d_col_cnt, &h->d_col_rows, &h->d_red, &h->d_hdiag,
                         &h->d_scal, &h->d_info, &h->d_cnt, &h->d_plan, &h->d_pcg, &h->d_lm_key, &h->d_lm_key2, &h->d_lm_idx,
-                        &h->d_lm_order, &h->d_sort_tmp, &h->d_lm_rec, &h->d_dense, &h->d_dense_prof, &h->d_mf_meta, &h->d_mf_fronts};
+                        &h->d_lm_order, &h->d_sort_tmp, &h->d_lm_rec, &h->d_dense, &h->d_dense_prof, &h->d_mf_meta, &h->d_mf_fronts, &h->d_mf_touch};
         for (DevBuf *b : lb) b->release();
     }
     DevBuf *bufs[] = {&h->d_in, &h->d_st, &h->d_pose, &h->d_point, &h->d_pose_flags, &h->d_lm_flags, &h->d_pose_hidx,
