@@ -568,7 +568,9 @@ def run_gpu(args):
     achieved = alg_build / (build_ms * 1e-3) / 1e9 if build_ms > 0 else 0.0
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "build_kernel_traffic.json"))).get("dram_bytes_per_launch")
+        tj = json.load(open(os.path.join(ROOT, "profiles", "build_kernel_traffic.json")))
+        # (one ncu --set full capture on the 4096-window batch, stored per window: a launch of this run holds len(windows))
+        traffic = tj["dram_bytes_per_window"] * len(windows) if "dram_bytes_per_window" in tj else tj.get("dram_bytes_per_launch")
     except Exception:
         pass
     # FP64 view of the same kernel (the binding roofline per SURVEY.md §8d): Schur + Hessian flops of one trial

@@ -62,8 +62,9 @@ def run_marshal(in_path, out_path):
     return out
 
 
-def run_solve(in_path, out_path):
-    p = subprocess.run([EXE, "solve", in_path, out_path], check=True, capture_output=True, text=True)
+def run_solve(in_path, out_path, mode="solve"):
+    """mode "solve": VISFS::Optimizer::Optimizer::localOptimize; "resident": the same window through ResidentLocalMap."""
+    p = subprocess.run([EXE, mode, in_path, out_path], check=True, capture_output=True, text=True)
     buf = open(out_path, "rb").read()
     off = 0
     n = struct.unpack_from("<q", buf, off)[0]; off += 8

@@ -70,3 +70,20 @@ def test_local_optimize_repeated_calls_reuse_their_buffers(built, tmp_path):
     t = host_io.run_time(fin, fout)
     assert t["poses"] == 10 and t["edges"] == 20000
     assert 0.0 < t["marshal_ms"] < t["local_optimize_ms_best"] < 50.0
+
+
+def test_resident_local_map_class_equals_local_optimize(built, tmp_path):
+    # VISFS::Optimizer::ResidentLocalMap: the same window fed signature by signature as LocalMap's deltas,
+    # then one localOptimize on the resident map, must return what Optimizer::localOptimize returns for the maps the reference
+    # would have built: poses, culled (feature, signature) pairs, and the points after the 5 m write-back rule
+    w = synth.make_window(6, 300, layout="consecutive", views=4, seed=84, mono_frac=0.2, fixed_point_frac=0.1, first_id=5)
+    fin, f1, f2 = str(tmp_path / "w.bin"), str(tmp_path / "o1.bin"), str(tmp_path / "o2.bin")
+    host_io.write_window(fin, w, feature_id_offset=40)
+    a = host_io.run_solve(fin, f1, mode="solve")
+    b = host_io.run_solve(fin, f2, mode="resident")
+    assert sorted(a["poses"]) == sorted(b["poses"]) == list(map(int, w["pose_id"]))
+    for pid in a["poses"]:
+        assert np.allclose(a["poses"][pid], b["poses"][pid], rtol=1e-9, atol=1e-11)
+    assert np.array_equal(a["outliers"], b["outliers"]) and len(a["outliers"]) > 0
+    for fid in a["points"]:
+        assert np.allclose(a["points"][fid], b["points"][fid], rtol=1e-9, atol=1e-11)

@@ -374,5 +374,150 @@ std::map<std::size_t, Eigen::Isometry3d> Optimizer::localOptimize(
     return optimizedPoses;
 }
 
+// ================================================================================================
+// ResidentLocalMap: LocalMap's deltas -> visfs_ba_window_* (include/visfs_ba.h)
+// ================================================================================================
+ResidentLocalMap::ResidentLocalMap(const ParametersMap & _parameters, const std::vector<std::shared_ptr<GeometricCamera>> & _cameraModels,
+                                   int _maxSignatures, int _maxFeatures) :
+    handle_(nullptr), window_(nullptr), fx_(0.0), baseLine_(0.0), maxSignatures_(_maxSignatures),
+    maxObservations_(4 * _maxSignatures * _maxFeatures) {
+    // the same parameters, with the same defaults, as Optimizer (corelib/src/Optimizer/Optimizer.cpp:37-56)
+    int solver = Parameters::defaultOptimizerSolver(), trust = Parameters::defaultOptimizerTrustRegion(), iterations = Parameters::defaultOptimizerIterations();
+    double pixelVariance = Parameters::defaultOptimizerPixelVariance(), delta = Parameters::defaultOptimizerRobustKernelDelta();
+    Parameters::parse(_parameters, Parameters::kOptimizerSolver(), solver);
+    Parameters::parse(_parameters, Parameters::kOptimizerTrustRegion(), trust);
+    Parameters::parse(_parameters, Parameters::kOptimizerIterations(), iterations);
+    Parameters::parse(_parameters, Parameters::kOptimizerPixelVariance(), pixelVariance);
+    Parameters::parse(_parameters, Parameters::kOptimizerRobustKernelDelta(), delta);
+    if (_cameraModels.empty() || !_cameraModels.front()) { fail("ResidentLocalMap: no camera model"); return; }
+    const GeometricCamera & cameraModel = *_cameraModels.front();
+    Trc_ = cameraModel.getTansformImageToRobot();
+    const Eigen::Matrix3d K = cameraModel.eigenKdouble();                       // Optimizer.cpp:176
+    if (_cameraModels.size() > 1) baseLine_ = cameraModel.getBaseLine();        // :181-183
+    fx_ = K(0, 0);
+    visfs_ba_config cfg{};
+    cfg.abi_version = VISFS_BA_ABI_VERSION;
+    cfg.device = g_device;
+    if (visfs_ba_create(&cfg, &handle_) != VISFS_BA_OK) { handle_ = nullptr; fail("ResidentLocalMap: cannot create the CUDA bundle adjuster"); return; }
+    visfs_ba_window_config wc{};
+    wc.max_frames = _maxSignatures + 1; wc.max_points = _maxFeatures; wc.max_observations = maxObservations_;
+    wc.fx = K(0, 0); wc.fy = K(1, 1); wc.cx = K(0, 2); wc.cy = K(1, 2); wc.bf = baseLine_ * wc.fx;   // :191-195
+    wc.pixel_variance = pixelVariance; wc.huber_delta = delta;
+    wc.iterations = iterations; wc.solver = solver; wc.trust_region = trust;
+    if (visfs_ba_window_create(handle_, &wc, &window_) != VISFS_BA_OK) { window_ = nullptr; fail("ResidentLocalMap: cannot create the resident window"); }
+}
+
+ResidentLocalMap::~ResidentLocalMap() {
+    if (window_) visfs_ba_window_destroy(window_);
+    if (handle_) visfs_ba_destroy(handle_);
+}
+
+bool ResidentLocalMap::fail(const char * _what) {
+    const char * why = handle_ ? visfs_ba_last_error(handle_) : visfs_ba_last_error(nullptr);
+    message_ = std::string(_what) + ": " + (why ? why : "");
+    VISFS_B200_LOG("ERROR", message_);
+    return false;
+}
+
+namespace {
+// Optimizer.cpp:102-109: T_cw = (T_wr * T_rc)^-1 as CameraPose(R, t)
+void cameraState(const Eigen::Isometry3d & _Twr, const Eigen::Isometry3d & _Trc, double _tq[7]) {
+    Eigen::Isometry3d cameraPose = _Twr * _Trc;
+    cameraPose = cameraPose.inverse();
+    double q[4];
+    rotationToQuaternion(cameraPose.linear(), q);
+    const Eigen::Vector3d & t = cameraPose.translation();
+    _tq[0] = t[0]; _tq[1] = t[1]; _tq[2] = t[2]; _tq[3] = q[0]; _tq[4] = q[1]; _tq[5] = q[2]; _tq[6] = q[3];
+}
+}   // namespace
+
+bool ResidentLocalMap::setFeature(std::size_t _featureId, const Eigen::Vector3d & _pose, bool _stable) {
+    if (!window_) return false;
+    const int64_t id = static_cast<int64_t>(_featureId);
+    const double xyz[3] = {_pose[0], _pose[1], _pose[2]};
+    const uint8_t fixed = _stable ? 1 : 0;                                      // LocalMap.cpp:278: fixed iff STABLE
+    return visfs_ba_window_set_points(window_, 1, &id, xyz, &fixed) == VISFS_BA_OK || fail("ResidentLocalMap::setFeature");
+}
+
+bool ResidentLocalMap::insertSignature(std::size_t _id, const Eigen::Isometry3d & _pose, const std::map<std::size_t, FeatureBA> & _observations) {
+    if (!window_) return false;
+    double tq[7];
+    cameraState(_pose, Trc_, tq);
+    ids_.clear(); obs_.clear(); kinds_.clear();
+    for (auto iter = _observations.begin(); iter != _observations.end(); ++iter) {
+        const FeatureBA & pt = iter->second;
+        const double depth = pt.depth;                                          // Optimizer.cpp:174
+        float obs[3] = {pt.kpt.pt.x, pt.kpt.pt.y, 0.0f};
+        uint8_t kind = VISFS_BA_EDGE_MONO;
+        if (std::isfinite(depth) && depth > 0.0 && baseLine_ > 0.0) {          // :184
+            const float disparity = static_cast<float>(baseLine_ * fx_ / depth);   // :187
+            obs[2] = pt.kpt.pt.x - disparity;                                   // :188
+            kind = VISFS_BA_EDGE_STEREO;
+        }
+        ids_.push_back(static_cast<int64_t>(iter->first));
+        obs_.insert(obs_.end(), obs, obs + 3);
+        kinds_.push_back(kind);
+    }
+    return visfs_ba_window_insert_frame(window_, static_cast<int64_t>(_id), tq, static_cast<int32_t>(ids_.size()), ids_.data(), obs_.data(),
+                                        kinds_.data()) == VISFS_BA_OK || fail("ResidentLocalMap::insertSignature");
+}
+
+bool ResidentLocalMap::removeSignature(std::size_t _id) {
+    return window_ && (visfs_ba_window_remove_frame(window_, static_cast<int64_t>(_id)) == VISFS_BA_OK || fail("ResidentLocalMap::removeSignature"));
+}
+
+bool ResidentLocalMap::removeFeature(std::size_t _featureId) {
+    const int64_t id = static_cast<int64_t>(_featureId);
+    return window_ && (visfs_ba_window_remove_points(window_, 1, &id) == VISFS_BA_OK || fail("ResidentLocalMap::removeFeature"));
+}
+
+bool ResidentLocalMap::removeObservation(std::size_t _featureId, std::size_t _signatureId) {
+    const int64_t f = static_cast<int64_t>(_featureId), s = static_cast<int64_t>(_signatureId);
+    return window_ && (visfs_ba_window_remove_observations(window_, 1, &f, &s) == VISFS_BA_OK || fail("ResidentLocalMap::removeObservation"));
+}
+
+bool ResidentLocalMap::setSignaturePose(std::size_t _id, const Eigen::Isometry3d & _pose) {
+    if (!window_) return false;
+    double tq[7];
+    cameraState(_pose, Trc_, tq);
+    const int64_t id = static_cast<int64_t>(_id);
+    return visfs_ba_window_set_poses(window_, 1, &id, tq) == VISFS_BA_OK || fail("ResidentLocalMap::setSignaturePose");
+}
+
+bool ResidentLocalMap::getFeaturePose(std::size_t _featureId, Eigen::Vector3d & _pose) {
+    if (!window_) return false;
+    const int64_t id = static_cast<int64_t>(_featureId);
+    double xyz[3];
+    if (visfs_ba_window_get_points(window_, 1, &id, xyz) != VISFS_BA_OK) return fail("ResidentLocalMap::getFeaturePose");
+    _pose = Eigen::Vector3d(xyz[0], xyz[1], xyz[2]);
+    return true;
+}
+
+std::map<std::size_t, Eigen::Isometry3d> ResidentLocalMap::localOptimize(std::size_t _rootId, std::vector<std::tuple<std::size_t, std::size_t>> & _outliers) {
+    std::map<std::size_t, Eigen::Isometry3d> optimizedPoses;
+    if (!window_) return optimizedPoses;
+    const std::size_t F = static_cast<std::size_t>(maxSignatures_ + 1);
+    ids_.assign(F, 0); poses_.assign(7 * F, 0.0);
+    outlierPoint_.resize(static_cast<std::size_t>(maxObservations_)); outlierFrame_.resize(static_cast<std::size_t>(maxObservations_));
+    visfs_ba_window_result res{};
+    res.frame_id = ids_.data(); res.pose_tq = poses_.data();
+    res.outlier_point_id = outlierPoint_.data(); res.outlier_frame_id = outlierFrame_.data(); res.outlier_capacity = maxObservations_;
+    const int st = visfs_ba_window_solve(window_, static_cast<int64_t>(_rootId), &res);
+    // the culled observations are reported before the second-pass guard, like the reference (Optimizer.cpp:283-318)
+    if (st == VISFS_BA_OK || st == VISFS_BA_ERR_NUMERIC_PASS2)
+        for (int k = 0; k < std::min(res.n_outliers, res.outlier_capacity); ++k)
+            _outliers.emplace_back(static_cast<std::size_t>(outlierPoint_[static_cast<std::size_t>(k)]), static_cast<std::size_t>(outlierFrame_[static_cast<std::size_t>(k)]));
+    if (st != VISFS_BA_OK) { fail("ResidentLocalMap::localOptimize"); return optimizedPoses; }
+    const Eigen::Isometry3d Tcr = Trc_.inverse();
+    for (int k = 0; k < res.n_frames; ++k) {                                    // Optimizer.cpp:320-340
+        Eigen::Isometry3d t = stateToIsometry(poses_.data() + 7 * static_cast<std::size_t>(k));
+        t = t.inverse();
+        t = t * Tcr;
+        if (isZeroTransform(t)) { optimizedPoses.clear(); return optimizedPoses; }
+        optimizedPoses.emplace(static_cast<std::size_t>(ids_[static_cast<std::size_t>(k)]), t);
+    }
+    return optimizedPoses;
+}
+
 }   // Optimizer
 }   // VISFS

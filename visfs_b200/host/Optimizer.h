@@ -18,6 +18,7 @@
 #include "visfs_compat.h"
 
 struct visfs_ba_handle;
+struct visfs_ba_window;
 
 namespace VISFS {
 namespace Optimizer {
@@ -169,6 +170,54 @@ private:
     detail::MarshalledWindow window_;
     detail::HostArray<double> poseOut_, pointOut_;
     detail::HostArray<uint8_t> levelOut_;
+};
+
+/** \brief The bundle-adjustment side of VISFS::LocalMap (corelib/src/LocalMap.cpp) kept resident on the GPU.
+ *
+ * The reference rebuilds poses / points3D / wordReferences from LocalMap on every frame (Estimator.cpp:216-254) although the
+ * map changed by one signature.  This class takes the same changes as LocalMap does, as deltas:
+ *   LocalMap::insertSignature  (LocalMap.cpp:48-131)  ->  setFeature() for the features it creates, insertSignature()
+ *   LocalMap::removeSignature  (LocalMap.cpp:133-168) ->  removeSignature(), removeFeature() for the features it erases
+ *   LocalMap::updateLocalMap   (LocalMap.cpp:170-226) ->  nothing for poses / feature poses (the solve already wrote them into
+ *                                                         the resident state), removeObservation() for every outlier,
+ *                                                         setSignaturePose() where the caller overrides a pose (Estimator.cpp:393)
+ * and localOptimize() replaces getSignaturePoses + getFeaturePosesAndObservations + Optimizer::localOptimize.  Results are
+ * those of Optimizer::localOptimize on the maps the reference would have built.  Odometry links and laser data are not part
+ * of the resident state yet (use Optimizer::localOptimize for those configurations).
+ */
+class ResidentLocalMap {
+public:
+    ResidentLocalMap(const ParametersMap & _parameters, const std::vector<std::shared_ptr<GeometricCamera>> & _cameraModels,
+                     int _maxSignatures = 6, int _maxFeatures = 4096);
+    ~ResidentLocalMap();
+    ResidentLocalMap(const ResidentLocalMap &) = delete;
+    ResidentLocalMap & operator=(const ResidentLocalMap &) = delete;
+
+    bool setFeature(std::size_t _featureId, const Eigen::Vector3d & _pose, bool _stable);
+    bool insertSignature(std::size_t _id, const Eigen::Isometry3d & _pose, const std::map<std::size_t, FeatureBA> & _observations);
+    bool removeSignature(std::size_t _id);
+    bool removeFeature(std::size_t _featureId);
+    bool removeObservation(std::size_t _featureId, std::size_t _signatureId);
+    bool setSignaturePose(std::size_t _id, const Eigen::Isometry3d & _pose);
+    bool getFeaturePose(std::size_t _featureId, Eigen::Vector3d & _pose);
+
+    /** \brief Optimizer::localOptimize on the resident map.  \return optimised poses (T_world<-robot); EMPTY on failure. */
+    std::map<std::size_t, Eigen::Isometry3d> localOptimize(std::size_t _rootId, std::vector<std::tuple<std::size_t, std::size_t>> & _outliers);
+
+    const std::string & lastMessage() const { return message_; }
+
+private:
+    bool fail(const char * _what);
+    visfs_ba_handle * handle_;
+    visfs_ba_window * window_;
+    Eigen::Isometry3d Trc_;
+    double fx_, baseLine_;
+    int maxSignatures_, maxObservations_;
+    std::string message_;
+    std::vector<int64_t> ids_, outlierPoint_, outlierFrame_;
+    std::vector<double> poses_;
+    std::vector<float> obs_;
+    std::vector<uint8_t> kinds_;
 };
 
 }   // Optimizer

@@ -3,6 +3,8 @@
 //   optimizer_selftest marshal <in> <out>   host-only: the flat arrays handed to the C ABI (no GPU needed)
 //   optimizer_selftest solve   <in> <out>   full localOptimize on the GPU
 //   optimizer_selftest time    <in> <out>   the same 20 times: wall time per call and the marshalling share
+//   optimizer_selftest resident <in> <out>  the same window fed to VISFS::Optimizer::ResidentLocalMap signature by signature
+//                                           (LocalMap's deltas), then ONE localOptimize on the resident map: same output file
 #include <cstdint>
 #include <cstdio>
 #include <algorithm>
@@ -30,7 +32,7 @@ template <typename T> void wrv(std::ostream &os, const Optimizer::detail::HostAr
 }  // namespace
 
 int main(int argc, char **argv) {
-    if (argc != 4) { std::fprintf(stderr, "usage: %s marshal|solve|time <in> <out>\n", argv[0]); return 2; }
+    if (argc != 4) { std::fprintf(stderr, "usage: %s marshal|solve|time|resident <in> <out>\n", argv[0]); return 2; }
     const std::string mode = argv[1];
     std::ifstream in(argv[2], std::ios::binary);
     if (!in) { std::fprintf(stderr, "cannot open %s\n", argv[2]); return 2; }
@@ -105,6 +107,39 @@ int main(int argc, char **argv) {
     std::snprintf(buf, sizeof buf, "%.17g", pixelVariance); params["Optimizer/PixelVariance"] = buf;
     std::snprintf(buf, sizeof buf, "%.17g", delta); params["Optimizer/RobustKernelDelta"] = buf;
     std::snprintf(buf, sizeof buf, "%.17g", odometryCovariance); params["Optimizer/OdometryCovariance"] = buf;
+    if (mode == "resident") {
+        Optimizer::ResidentLocalMap map(params, cameraModels, (int)std::max<int64_t>(P, 2), (int)std::max<int64_t>(L, 1));
+        bool ok = true;
+        for (auto &kv : points3D) ok = ok && map.setFeature(kv.first, std::get<0>(kv.second), std::get<1>(kv.second));
+        for (auto &pk : poses) {   // ascending signature id, each with its observations (LocalMap::insertSignature)
+            std::map<std::size_t, Optimizer::FeatureBA> obs;
+            for (auto &fk : wordReferences) {
+                auto it = fk.second.find(pk.first);
+                if (it != fk.second.end() && points3D.count(fk.first)) obs.emplace(fk.first, it->second);
+            }
+            ok = ok && map.insertSignature(pk.first, pk.second, obs);
+        }
+        if (!ok) { std::fprintf(stderr, "ResidentLocalMap: %s\n", map.lastMessage().c_str()); return 1; }
+        std::vector<std::tuple<std::size_t, std::size_t>> outliers;
+        auto result = map.localOptimize((std::size_t)rootId, outliers);
+        wr<int64_t>(out, (int64_t)result.size());
+        for (auto &kv : result) {
+            wr<int64_t>(out, (int64_t)kv.first);
+            for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) wr<double>(out, kv.second.linear()(r, c)); wr<double>(out, kv.second.translation()[r]); }
+            wr<double>(out, 0.0); wr<double>(out, 0.0); wr<double>(out, 0.0); wr<double>(out, 1.0);
+        }
+        wr<int64_t>(out, (int64_t)points3D.size());
+        for (auto &kv : points3D) {
+            Eigen::Vector3d p;
+            map.getFeaturePose(kv.first, p);
+            wr<int64_t>(out, (int64_t)kv.first);
+            wr<double>(out, p[0]); wr<double>(out, p[1]); wr<double>(out, p[2]);
+        }
+        wr<int64_t>(out, (int64_t)outliers.size());
+        for (auto &o : outliers) { wr<int64_t>(out, (int64_t)std::get<0>(o)); wr<int64_t>(out, (int64_t)std::get<1>(o)); }
+        std::cout << "poses " << result.size() << " outliers " << outliers.size() << " message '" << map.lastMessage() << "'\n";
+        return 0;
+    }
     Optimizer::Optimizer optimizer(params);
     std::vector<std::tuple<std::size_t, std::size_t>> outliers;
     const std::vector<Sensor::PointCloud> pointClouds;
