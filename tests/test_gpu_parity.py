@@ -472,3 +472,25 @@ def test_seeded_sweep_of_window_shapes_and_options(ba):
         except AssertionError as e:
             bad.append(str(e)[:300])
     assert not bad, "\n".join(bad)
+
+
+# ---------------------------------------------------------------- the opt-in tensor-pipe build kernel (k_build_ds)
+def test_tensor_pipe_build_variant_matches_oracle(ba, monkeypatch):
+    """VISFS_BA_USE_DS=1 routes windows of <= 10 poses through k_build_ds (Schur products as DMMA); same gates."""
+    monkeypatch.setenv("VISFS_BA_USE_DS", "1")
+    cases = {
+        "C1": synth.config_c1(),
+        "C1 30% fixed points": synth.config_c1(fixed_point_frac=0.3),
+        "consecutive views": synth.make_window(8, 500, layout="consecutive", views=3, seed=77),
+        "rejected steps": rejecting_window(5, 0.08),
+        "chain of links": synth.make_window(7, 400, layout="all", seed=403, links="chain"),
+        "no fixed pose": synth.make_window(5, 200, layout="all", seed=12, root=None),
+    }
+    for what, w in cases.items():
+        check_solution(ba.solve(w), O.solve(w), "ds " + what)
+    ws = synth.config_c3_windows(24)
+    got = ba.solve_batch(ws)
+    monkeypatch.delenv("VISFS_BA_USE_DS")
+    ref = ba.solve_batch(ws)
+    for g, r in zip(got, ref):
+        check_solution(g, r, "ds batch vs default batch")

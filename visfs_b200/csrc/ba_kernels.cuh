@@ -48,11 +48,11 @@ __device__ __forceinline__ int hd_index(int a, int c) {  // a <= c, upper triang
 }
 
 // largest l1 in (lt, lmax] with lm_edge_off[l1] - e0 <= kTileEdges
-__device__ __forceinline__ int tile_end(const int *__restrict__ off, int lt, int lmax, int e0) {
+__device__ __forceinline__ int tile_end(const int *__restrict__ off, int lt, int lmax, int e0, int max_edges = kTileEdges) {
     int lo = lt + 1, hi = lmax;
     while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
-        if (off[mid] - e0 <= kTileEdges) lo = mid; else hi = mid - 1;
+        if (off[mid] - e0 <= max_edges) lo = mid; else hi = mid - 1;
     }
     return lo;
 }
@@ -490,17 +490,18 @@ __global__ void k_lm_offsets(Batch B, int *lm_edge_off) {
 }
 
 // ---- tile table (built once per upload): tiles of <= kTileLm landmarks and <= kTileEdges edges inside every chunk
+// (max_lm, max_edges: kTileLm / kTileEdges for k_build_ws, 16 / 160 for the tensor-pipe kernel k_build_ds)
 template <bool WRITE>
-__device__ int walk_tiles(const int *__restrict__ off, int lm0, int lm1, Tile *out) {
+__device__ int walk_tiles(const int *__restrict__ off, int lm0, int lm1, Tile *out, int max_lm, int max_edges) {
     int n = 0, cnt_prev = 0;
     for (int lt = lm0; lt < lm1;) {
         const int e0 = off[lt];
-        const int lmax = min(lt + kTileLm, lm1);
+        const int lmax = min(lt + max_lm, lm1);
         const int g = min(lt + max(cnt_prev, 1), lmax);   // uniform degree: same landmark count as the previous tile
         const int og = off[g] - e0;
-        const int og1 = (g < lmax) ? off[g + 1] - e0 : (kTileEdges + 1);
-        const int l1 = (og <= kTileEdges && og1 > kTileEdges) ? g : tile_end(off, lt, lmax, e0);
-        if (WRITE) out[n] = Tile{lt, l1 - lt, e0, min(off[l1] - e0, kTileEdges)};
+        const int og1 = (g < lmax) ? off[g + 1] - e0 : (max_edges + 1);
+        const int l1 = (og <= max_edges && og1 > max_edges) ? g : tile_end(off, lt, lmax, e0, max_edges);
+        if (WRITE) out[n] = Tile{lt, l1 - lt, e0, min(off[l1] - e0, max_edges)};
         ++n;
         cnt_prev = l1 - lt;
         lt = l1;
@@ -508,16 +509,16 @@ __device__ int walk_tiles(const int *__restrict__ off, int lm0, int lm1, Tile *o
     return n;
 }
 
-__global__ void k_count_tiles(Batch B, int *ntiles) {
+__global__ void k_count_tiles(Batch B, int *ntiles, int max_lm, int max_edges) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c > B.n_chunks) return;
-    ntiles[c] = (c < B.n_chunks) ? walk_tiles<false>(B.lm_edge_off, B.chunks[c].lm0, B.chunks[c].lm1, nullptr) : 0;
+    ntiles[c] = (c < B.n_chunks) ? walk_tiles<false>(B.lm_edge_off, B.chunks[c].lm0, B.chunks[c].lm1, nullptr, max_lm, max_edges) : 0;
 }
 
-__global__ void k_fill_tiles(Batch B, const int *tile_off, Tile *tiles) {
+__global__ void k_fill_tiles(Batch B, const int *tile_off, Tile *tiles, int max_lm, int max_edges) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= B.n_chunks) return;
-    walk_tiles<true>(B.lm_edge_off, B.chunks[c].lm0, B.chunks[c].lm1, tiles + tile_off[c]);
+    walk_tiles<true>(B.lm_edge_off, B.chunks[c].lm0, B.chunks[c].lm1, tiles + tile_off[c], max_lm, max_edges);
 }
 
 // per landmark: active flag, pose_active marks, degree check

@@ -20,6 +20,7 @@
 #include "../../include/visfs_ba.h"
 #include "ba_kernels.cuh"
 #include "ba_build_ws.cuh"
+#include "ba_build_ds.cuh"
 #include "ba_large.cuh"
 #include "ba_dense.cuh"
 #include "ba_mf.cuh"
@@ -89,6 +90,8 @@ struct visfs_ba_handle {
     int n_win = 0, n_chunks = 0, tot_pose = 0, tot_point = 0, tot_edge = 0, max_pose = 0, max_iter = 0, tot_link = 0;
     DevBuf d_link_win, d_link_from, d_link_to, d_link_m, d_link_lin;
     bool resident = false, has_run = false, sorted = true, use_ws = false;
+    bool use_ds = false;              // k_build_ds (Schur products on the FP64 tensor pipe): windows of <= 10 poses; opt-in
+                                      // (VISFS_BA_USE_DS=1) -- measured 19 % slower per C3 step than k_build_ws, DESIGN.md §5
     int cluster = 1;
     std::vector<WinDesc> win;
     std::vector<Chunk> chunks;
@@ -173,6 +176,17 @@ struct visfs_ba_handle {
     } while (0)
 
 namespace {
+
+// VISFS_BA_LAUNCH_DEBUG: name the launch that failed (the error would otherwise surface at the end of the pass)
+#define LAUNCH_CHECK(what)                                                                                     \
+    do {                                                                                                       \
+        static const bool dbg__ = getenv("VISFS_BA_LAUNCH_DEBUG") != nullptr;                                  \
+        if (dbg__) {                                                                                           \
+            cudaError_t e__ = cudaGetLastError();                                                              \
+            if (e__ == cudaSuccess) e__ = cudaStreamSynchronize(h->stream);                                    \
+            if (e__ != cudaSuccess) return h->cuda_fail(e__, what);                                            \
+        }                                                                                                      \
+    } while (0)
 
 int ev_begin(visfs_ba_handle *h, int cls) {
     if (!h->profile) return -1;
@@ -348,6 +362,7 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs, const DevIn
     //   one window : up to sm_count chunks of >= 16 landmarks, clusters of up to 8 CTAs sum their partials
     //   a batch    : c chunks per window with c in 1..16 maximising n*c / (ceil(n*c / sm_count) * sm_count)
     h->use_ws = (max_pose <= ws::kMaxPosesWs) && (max_free <= ws::kMaxFreeWs) && !getenv("VISFS_BA_NO_WS") && !any_large;
+    h->use_ds = h->use_ws && max_pose <= ds::kMaxPosesDs && getenv("VISFS_BA_USE_DS") != nullptr;
     const int sms = std::max(h->sm_count, 8);
     int per_window = 1;
     if (n == 1) {
@@ -420,7 +435,7 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs, const DevIn
     }
     CK(h->d_part2.reserve(sizeof(double) * 2 * std::max(std::max(h->n_chunks, 1), std::max(h->grid_build_l, h->grid_update_l))));
     CK(h->d_xp.reserve(sizeof(double) * 6 * P)); CK(h->d_n_running.reserve(sizeof(int) * 4)); CK(h->d_ctl_count.reserve(sizeof(int) * (size_t)n));
-    const size_t max_tiles = 2 * E / (kTileEdges + 1) + L / kTileLm + 2 * (size_t)h->n_chunks + 8;
+    const size_t max_tiles = 2 * E / (ds::kEdges + 1) + L / ds::kLm + 2 * (size_t)h->n_chunks + 8;   // (bound for either tile shape)
     CK(h->d_tiles.reserve(sizeof(Tile) * max_tiles));
     CK(h->d_tile_off.reserve(sizeof(int) * (h->n_chunks + 2))); CK(h->d_tile_cnt.reserve(sizeof(int) * (h->n_chunks + 2)));
     CK(h->d_wtiles.reserve(sizeof(Tile) * (L + (size_t)h->n_chunks + 8))); CK(h->d_wtile_off.reserve(sizeof(int) * (h->n_chunks + 2)));
@@ -590,19 +605,23 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs, const DevIn
                                                           h->in.ekind, perm, h->d_obs_u.as<double>(),
                                                           h->d_obs_v.as<double>(), h->d_obs_r.as<double>(), h->d_edge_point.as<int>());
     }
+    LAUNCH_CHECK("k_prepare_edges");
     k_lm_offsets<<<grid2(max_point + 1, n), 256, 0, s>>>(B, h->d_lm_edge_off.as<int>());
+    LAUNCH_CHECK("k_lm_offsets");
     {   // tile table: count per chunk, exclusive scan, fill (all on the stream, no host round trip)
         const int nc1 = h->n_chunks + 1;
-        k_count_tiles<<<(nc1 + 127) / 128, 128, 0, s>>>(B, h->d_tile_cnt.as<int>());
+        const int tile_lm = h->use_ds ? ds::kLm : kTileLm, tile_edges = h->use_ds ? ds::kEdges : kTileEdges;
+        k_count_tiles<<<(nc1 + 127) / 128, 128, 0, s>>>(B, h->d_tile_cnt.as<int>(), tile_lm, tile_edges);
         size_t tmp_bytes = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, h->d_tile_cnt.as<int>(), h->d_tile_off.as<int>(), nc1, s);
         CK(h->d_tmp2.reserve(tmp_bytes));
         CK(cub::DeviceScan::ExclusiveSum(h->d_tmp2.p, tmp_bytes, h->d_tile_cnt.as<int>(), h->d_tile_off.as<int>(), nc1, s));
-        if (h->n_chunks) k_fill_tiles<<<(h->n_chunks + 127) / 128, 128, 0, s>>>(B, h->d_tile_off.as<int>(), h->d_tiles.as<Tile>());
+        if (h->n_chunks) k_fill_tiles<<<(h->n_chunks + 127) / 128, 128, 0, s>>>(B, h->d_tile_off.as<int>(), h->d_tiles.as<Tile>(), tile_lm, tile_edges);
         // warp tiles of k_update (d_tile_cnt is reused: the scan above has consumed it)
         k_count_wtiles<<<(nc1 + 127) / 128, 128, 0, s>>>(B, h->d_tile_cnt.as<int>());
         CK(cub::DeviceScan::ExclusiveSum(h->d_tmp2.p, tmp_bytes, h->d_tile_cnt.as<int>(), h->d_wtile_off.as<int>(), nc1, s));
         if (h->n_chunks) k_fill_wtiles<<<(h->n_chunks + 127) / 128, 128, 0, s>>>(B, h->d_wtile_off.as<int>(), h->d_wtiles.as<Tile>());
+        LAUNCH_CHECK("tile tables");
     }
     CK(cudaGetLastError());
     h->resident = true;
@@ -614,6 +633,7 @@ int reset_state(visfs_ba_handle *h) {
     const int items = std::max(std::max(h->tot_pose, h->tot_point * 3), std::max(h->tot_edge, h->n_win));
     const int gx = std::max(1, std::min((items + 255) / 256, 4096));
     k_reset<<<gx, 256, 0, h->stream>>>(B, h->in.pose, h->in.point, h->in.pfix, h->in.lfix);
+    LAUNCH_CHECK("k_reset");
     CK(cudaMemsetAsync(h->d_n_running.p, 0, sizeof(int) * 4, h->stream));
     CK(cudaMemsetAsync(h->d_ctl_count.p, 0, sizeof(int) * (size_t)std::max(h->n_win, 1), h->stream));
     CK(cudaGetLastError());
@@ -631,6 +651,7 @@ int run_structure(visfs_ba_handle *h, bool want_covis = false) {
     k_struct_pose<<<gw, 128, 0, s>>>(B);
     k_struct_count<<<glm, 256, 0, s>>>(B, want_covis ? 1 : 0);
     k_struct_finish<<<gw, 128, 0, s>>>(B);
+    LAUNCH_CHECK("k_struct_*");
     CK(cudaGetLastError());
     h->launches += 4;
     return VISFS_BA_OK;
@@ -643,8 +664,8 @@ int launch_build(visfs_ba_handle *h) {
     if (MODE == MODE_BUILD && h->use_ws) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)h->n_chunks);
-        cfg.blockDim = dim3(ws::kThreadsWs);
-        cfg.dynamicSmemBytes = sizeof(ws::Smem);
+        cfg.blockDim = dim3(h->use_ds ? ds::kThreadsDs : ws::kThreadsWs);
+        cfg.dynamicSmemBytes = h->use_ds ? sizeof(ds::Smem) : sizeof(ws::Smem);
         cfg.stream = h->stream;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -653,7 +674,8 @@ int launch_build(visfs_ba_handle *h) {
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        CK(cudaLaunchKernelEx(&cfg, ws::k_build_ws, h->batch, h->cluster));
+        if (h->use_ds) CK(cudaLaunchKernelEx(&cfg, ds::k_build_ds, h->batch, h->cluster));
+        else CK(cudaLaunchKernelEx(&cfg, ws::k_build_ws, h->batch, h->cluster));
         return VISFS_BA_OK;
     }
     const size_t smem = sizeof(BuildSmemT<MODE>);
@@ -664,7 +686,8 @@ int launch_build(visfs_ba_handle *h) {
 
 int enqueue_body(visfs_ba_handle *h) {
     int ev = ev_begin(h, EV_BUILD);
-    launch_build<MODE_BUILD>(h);
+    { const int st = launch_build<MODE_BUILD>(h); if (st) return st; }
+    LAUNCH_CHECK(h->use_ds ? "k_build_ds" : (h->use_ws ? "k_build_ws" : "k_build"));
     ev_end(h, ev);
     ev = ev_begin(h, EV_SOLVE);
     if (h->tot_link > 0) { k_link_lin<<<(h->tot_link + 63) / 64, 64, 0, h->stream>>>(h->batch); h->launches += 1; }
@@ -673,10 +696,12 @@ int enqueue_body(visfs_ba_handle *h) {
         h->launches += 1;
     }
     k_solve<<<h->n_win, kSolveThreads, h->solve_smem, h->stream>>>(h->batch);
+    LAUNCH_CHECK("k_solve");
     ev_end(h, ev);
     ev = ev_begin(h, EV_UPDATE);
     if (h->n_chunks) k_update<<<h->n_chunks, kUpdThreads, sizeof(UpdateSmem), h->stream>>>(h->batch);   // (its last CTA per window runs the LM controller)
     else k_control<<<h->n_win, 32, 0, h->stream>>>(h->batch);
+    LAUNCH_CHECK("k_update");
     ev_end(h, ev);
     h->launches += 3;
     return VISFS_BA_OK;
@@ -1232,9 +1257,12 @@ int run_pass(visfs_ba_handle *h, int pass) {
     } else {
         if ((st = run_structure(h))) return st;
         k_sync_buffers<<<dim3((unsigned)h->grid_lm_x, (unsigned)h->n_win), 256, 0, s>>>(B);
+        LAUNCH_CHECK("structure kernels");
         if (h->n_chunks) k_init<<<h->n_chunks, kUpdThreads, sizeof(InitSmem), s>>>(B);
+        LAUNCH_CHECK("k_init");
         if (h->tot_link > 0) { k_link_lin<<<(h->tot_link + 63) / 64, 64, 0, s>>>(B); h->launches += 1; }
         k_control_init<<<h->n_win, kCtlInitThreads, 0, s>>>(B);
+        LAUNCH_CHECK("k_control_init");
         h->launches += 3;
     }
     ev_end(h, ev);
@@ -1522,6 +1550,7 @@ int visfs_ba_create(const visfs_ba_config *cfg, visfs_ba_handle **out) {
     cudaFuncSetAttribute(k_build<MODE_BUILD, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_build);
     cudaFuncSetAttribute(k_update, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_update);
     e = cudaFuncSetAttribute(ws::k_build_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ws::Smem));
+    cudaFuncSetAttribute(ds::k_build_ds, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ds::Smem));
     if (getenv("VISFS_BA_VERBOSE")) {
         cudaFuncAttributes fa{};
         cudaFuncGetAttributes(&fa, ws::k_build_ws);
@@ -1537,6 +1566,15 @@ int visfs_ba_create(const visfs_ba_config *cfg, visfs_ba_handle **out) {
             int nc = -1;
             cudaError_t e2 = cudaOccupancyMaxActiveClusters(&nc, ws::k_build_ws, &cfg);
             fprintf(stderr, "[visfs_ba]   cluster %d: max active clusters %d (%s)\n", cl, nc, cudaGetErrorString(e2));
+        }
+        {
+            cudaFuncAttributes fd{};
+            cudaError_t e3 = cudaFuncSetAttribute(ds::k_build_ds, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ds::Smem));
+            cudaFuncGetAttributes(&fd, ds::k_build_ds);
+            int nb = -1;
+            cudaError_t e4 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ds::k_build_ds, ds::kThreadsDs, sizeof(ds::Smem));
+            fprintf(stderr, "[visfs_ba] k_build_ds: set smem %zu -> %s; regs %d maxThreads %d static smem %zu maxDyn %d; blocks/SM %d (%s)\n", sizeof(ds::Smem),
+                    cudaGetErrorString(e3), fd.numRegs, fd.maxThreadsPerBlock, fd.sharedSizeBytes, fd.maxDynamicSharedSizeBytes, nb, cudaGetErrorString(e4));
         }
         cudaFuncGetAttributes(&fa, k_solve);
         fprintf(stderr, "[visfs_ba] k_solve: regs %d maxThreads %d static smem %zu\n", fa.numRegs, fa.maxThreadsPerBlock, fa.sharedSizeBytes);
@@ -1935,9 +1973,12 @@ int visfs_ba_debug_trial(visfs_ba_handle *h, const visfs_ba_problem *problem, do
         st = run_structure(h);
         if (st) return st;
         k_sync_buffers<<<dim3((unsigned)h->grid_lm_x, 1u), 256, 0, s>>>(h->batch);
+        LAUNCH_CHECK("k_sync_buffers");
         if (h->n_chunks) k_init<<<h->n_chunks, kUpdThreads, sizeof(InitSmem), s>>>(h->batch);
+        LAUNCH_CHECK("k_init");
         if (h->tot_link > 0) k_link_lin<<<(h->tot_link + 63) / 64, 64, 0, s>>>(h->batch);
         k_control_init<<<1, kCtlInitThreads, 0, s>>>(h->batch);
+        LAUNCH_CHECK("k_control_init");
         CK(cudaMemcpyAsync(&before, h->d_st.p, sizeof(LMState), cudaMemcpyDeviceToHost, s));
         CK(dbg.reserve(sizeof(double) * (ntri_max + nmax + 8)));
         CK(cudaMemsetAsync(dbg.p, 0, sizeof(double) * (ntri_max + nmax + 8), s));
