@@ -125,6 +125,29 @@ def test_multifrontal_band_solver_matches_oracle(ba, monkeypatch):
     check_solution(ba.solve(cases[0][1]), O.solve(cases[0][1]), "frontal solver")
 
 
+def test_band_chunks_build_matches_oracle(ba, monkeypatch):
+    # ba_band.cuh: the large build through ws::k_build_band + k_band_gather (no atomics).  Chosen for maps of >= 4096
+    # landmarks with band structure; VISFS_BA_BAND_FORCE brings it to windows the oracle checks in a second, including maps where
+    # only some chunks qualify (loop closure, random views) and lg::k_build_large_run takes the rest.
+    monkeypatch.setenv("VISFS_BA_BAND_FORCE", "1")
+    cases = [("plain band", banded(seed=181, P=80, L=2500, mono_frac=0.2, fixed_point_frac=0.1)),
+             ("loop: closure landmarks outside the chunks", loop(seed=182, P=64, L=2500)),
+             ("random views: most chunks do not qualify", dense(seed=183)),
+             ("10 views like C4", synth.make_window(260, 6000, views=10, layout="consecutive", trajectory="loop", seed=184)),
+             ("gauge free, mono + fixed points", synth.make_window(70, 1500, views=3, layout="consecutive", seed=185, mono_frac=0.3,
+                                                                   fixed_point_frac=0.2, root=None)),
+             ("band with odometry links", loop(seed=186, P=48, L=1200, links="chain"))]
+    for name, w in cases:
+        lam = 1.3
+        got, ref = ba.debug_trial(w, lam), O.reduced_system(w, lam)
+        rel_close(got["chi2"], ref["chi2"], 1e-12, name + ": chi2")
+        rel_close(got["S"], ref["S"], 1e-10, name + ": reduced camera system")
+        rel_close(got["b_s"], ref["b_s"], 1e-10, name + ": reduced rhs")
+        check_solution(ba.solve(w), O.solve(w), name)
+    part = partition.partition_window(cases[3][1], 1, 0)
+    check_solution(partition.merge_results(cases[3][1], [part], [ba.solve(part)]), O.solve(cases[3][1]), "1-rank partition, band chunks")
+
+
 def test_large_rejected_steps(ba):
     w = synth.make_window(34, 400, views=6, layout="consecutive", seed=78, pose_noise=(0.3, np.deg2rad(6.0)), point_noise=0.5,
                           iterations=20, depth_range=(1.0, 6.0))

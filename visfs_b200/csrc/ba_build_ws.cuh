@@ -61,14 +61,51 @@ static_assert(sizeof(Smem) <= 232448, "k_build_ws: shared memory over the 227 KB
 // number of doubles of one partial system in the "all pairs" layout
 __host__ __device__ __forceinline__ int part_len(int F) { return F * (F + 1) / 2 * 36 + F * kHStride; }
 
+// ---- band chunks (ba_band.cuh): the same kernel on pieces of a LARGE window.  The landmarks are taken in the order of
+// their first pose; a band chunk is a contiguous piece of that order whose landmarks touch <= kBandPoses poses in all, so
+// inside the chunk the poses are numbered 0 .. n_pose - 1 and everything above applies.  Its partial system goes to the
+// chunk's own slot of `part` and k_band_gather adds the slots into the block skyline in a fixed order (no atomics).
+constexpr int kBandPoses = 19;                 // poses of a band chunk, free or fixed (<= kMaxFreeWs block owners per row)
+constexpr int kBandPartStride = 7472;          // doubles per chunk slot >= part_len(19) = 7467
+struct BandChunk {
+    int lm0, lm1;                              // landmark range in the sorted order
+    int n_pose, F;                             // poses the chunk touches / the free ones among them; n_pose < 0: not a band chunk
+};
+struct Band {
+    const BandChunk *chunk;
+    const int *chunk_pose;                     // [n_chunk][kBandPoses] global pose index, ascending
+    const int *sorted_off;                     // [L + 1] edge offsets of the landmarks in the sorted order
+    // per-pass copies of the edge records in the sorted order, so that the kernel's prefetch has no dependent address:
+    const int *s_pw;                           // [E] pose word (mono / culled bits) with the CHUNK-LOCAL pose index
+    const int *s_gl;                           // [E] landmark
+    const int *s_sl;                           // [E] sorted landmark index
+    const double *s_ou, *s_ov, *s_our;         // [E] observation
+    const int4 *lm_rec;                        // [L] sorted landmark -> (landmark, first edge, degree, flags)
+    const Tile *tiles;
+    const int *chunk_tile_off;
+    double *part;                              // [n_chunk][kBandPartStride]
+    int n_chunk;
+};
+
 // what a producer thread holds for its edge of one tile
 struct EdgeRec {
     double ou, ov, our, px, py, pz;
-    int pw, gl;
+    int pw, gl, sl;                            // sl: sorted landmark index (band chunks only)
     uint8_t lf, pf;
 };
 
-__device__ __forceinline__ void load_edge_l1(const Batch &B, const WinDesc &wd, const Tile &T, int tid, EdgeRec &r) {
+template <bool BAND>
+__device__ __forceinline__ void load_edge_l1_t(const Batch &B, const WinDesc &wd, const Band &bd, const Tile &T, int tid, EdgeRec &r) {
+    if (BAND) {
+        if (tid < T.ne) {
+            const int k = T.e0 + tid;
+            r.sl = bd.s_sl[k];
+            r.pw = bd.s_pw[k];
+            r.gl = bd.s_gl[k];
+            r.ou = bd.s_ou[k]; r.ov = bd.s_ov[k]; r.our = bd.s_our[k];
+        }
+        return;
+    }
     if (tid < T.ne) {
         const int e = T.e0 + tid;
         r.pw = B.edge_pose[e];
@@ -76,12 +113,20 @@ __device__ __forceinline__ void load_edge_l1(const Batch &B, const WinDesc &wd, 
         r.ou = B.obs_u[e]; r.ov = B.obs_v[e]; r.our = B.obs_r[e];
     }
 }
-__device__ __forceinline__ void load_edge_l2(const Batch &B, const WinDesc &wd, const Tile &T, int tid, const double *gpoint, EdgeRec &r) {
+template <bool BAND>
+__device__ __forceinline__ void load_edge_l2_t(const Batch &B, const WinDesc &wd, const int *__restrict__ cpose, const Tile &T, int tid,
+                                               const double *gpoint, EdgeRec &r) {
     if (tid < T.ne) {
         r.lf = B.lm_flags[r.gl];
-        r.pf = B.pose_flags[wd.pose_off + (r.pw & kPoseMask)];
+        r.pf = B.pose_flags[wd.pose_off + (BAND ? cpose[r.pw & kPoseMask] : (r.pw & kPoseMask))];
         r.px = gpoint[3 * (size_t)r.gl]; r.py = gpoint[3 * (size_t)r.gl + 1]; r.pz = gpoint[3 * (size_t)r.gl + 2];
     }
+}
+__device__ __forceinline__ void load_edge_l1(const Batch &B, const WinDesc &wd, const Tile &T, int tid, EdgeRec &r) {
+    load_edge_l1_t<false>(B, wd, Band{}, T, tid, r);
+}
+__device__ __forceinline__ void load_edge_l2(const Batch &B, const WinDesc &wd, const Tile &T, int tid, const double *gpoint, EdgeRec &r) {
+    load_edge_l2_t<false>(B, wd, nullptr, T, tid, gpoint, r);
 }
 
 // stage B of one edge: damped inverse of its landmark block (redundantly per edge), Yn = -W Dinv over the scratch stage A
@@ -122,26 +167,41 @@ __device__ __forceinline__ void stage_b_edge(Stage &S, int e, double lambda) {
 #endif
 constexpr int kProdShare = VISFS_WS_PROD_SHARE;
 
-__global__ void __maxnreg__(168) k_build_ws(Batch B, int cluster_size) {
+template <bool BAND>
+__device__ __forceinline__ void build_ws_body(const Batch &B, int cluster_size, const Band &bd) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
     const int tid = threadIdx.x;
-    const Chunk ck = B.chunks[blockIdx.x];
-    const WinDesc &wd = B.win[ck.win];
-    const LMState &st = B.st[ck.win];
+    const int win = BAND ? 0 : B.chunks[blockIdx.x].win;
+    const WinDesc &wd = B.win[win];
+    const LMState &st = B.st[win];
     if (st.done) return;   // uniform over the cluster: all its chunks belong to one window
+    BandChunk bc{0, 0, 0, 0};
+    if (BAND) { bc = bd.chunk[blockIdx.x]; if (bc.n_pose < 0) return; }
+    const int *__restrict__ cpose = BAND ? bd.chunk_pose + (size_t)blockIdx.x * kBandPoses : nullptr;
     const int cur = st.cur;
-    const int F = st.F;
+    const int F = BAND ? bc.F : st.F;
     const double lambda = (wd.trust == 0) ? (B.dbg_lambda >= 0.0 ? B.dbg_lambda : st.lambda) : 0.0;
     const Intr K = load_intr(wd);
-    const int pose_off = wd.pose_off, n_pose = wd.n_pose;
+    const int pose_off = wd.pose_off, n_pose = BAND ? bc.n_pose : wd.n_pose;
     const double *__restrict__ gpose = B.pose + ((size_t)cur * B.tot_pose + pose_off) * kPoseStride;
     const double *__restrict__ gpoint = B.point + (size_t)cur * B.tot_point * 3;
-    const int tile0 = B.chunk_tile_off[blockIdx.x], ntiles = B.chunk_tile_off[blockIdx.x + 1] - tile0;
-    const Tile *__restrict__ tiles = B.tiles + tile0;
+    const int *__restrict__ tile_off = BAND ? bd.chunk_tile_off : B.chunk_tile_off;
+    const int *__restrict__ lm_off = BAND ? bd.sorted_off : B.lm_edge_off;
+    const int tile0 = tile_off[blockIdx.x], ntiles = tile_off[blockIdx.x + 1] - tile0;
+    const Tile *__restrict__ tiles = (BAND ? bd.tiles : B.tiles) + tile0;
 
-    for (int i = tid; i < n_pose * kPoseStride; i += kThreadsWs) sm.pose[(i >> 4) * kPoseSm + (i & 15)] = gpose[i];
-    for (int i = tid; i < n_pose; i += kThreadsWs) sm.hidx[i] = B.pose_hidx[pose_off + i];
+    if (BAND) {   // the chunk's poses, numbered 0 .. n_pose - 1 in ascending pose order; the free ones 0 .. F - 1 in that order
+        for (int i = tid; i < n_pose * kPoseStride; i += kThreadsWs) sm.pose[(i >> 4) * kPoseSm + (i & 15)] = gpose[(size_t)cpose[i >> 4] * kPoseStride + (i & 15)];
+        if (tid < 32) {   // free poses of the chunk numbered by a ballot over their global hessian indices
+            const bool fr = tid < n_pose && B.pose_hidx[pose_off + cpose[tid]] >= 0;
+            const unsigned m = __ballot_sync(0xffffffffu, fr);
+            if (tid < n_pose) sm.hidx[tid] = fr ? __popc(m & ((1u << tid) - 1u)) : -1;
+        }
+    } else {
+        for (int i = tid; i < n_pose * kPoseStride; i += kThreadsWs) sm.pose[(i >> 4) * kPoseSm + (i & 15)] = gpose[i];
+        for (int i = tid; i < n_pose; i += kThreadsWs) sm.hidx[i] = B.pose_hidx[pose_off + i];
+    }
     for (int i = tid; i < kMaxFreeWs * kHStride; i += kThreadsWs) sm.pacc[i] = 0.0;
     __syncthreads();
 
@@ -167,17 +227,17 @@ __global__ void __maxnreg__(168) k_build_ws(Batch B, int cluster_size) {
         Tile T, Tn;
         if (ntiles > 0) {
             T = tiles[0];
-            load_edge_l1(B, wd, T, tid, rec);
-            load_edge_l2(B, wd, T, tid, gpoint, rec);
+            load_edge_l1_t<BAND>(B, wd, bd, T, tid, rec);
+            load_edge_l2_t<BAND>(B, wd, cpose, T, tid, gpoint, rec);
         }
         for (int t = 0; t < ntiles; ++t) {
             Stage &S = sm.st[t & 1];
             const bool more = t + 1 < ntiles;
-            if (more) { Tn = tiles[t + 1]; load_edge_l1(B, wd, Tn, tid, nxt); }   // prefetch, level 1
+            if (more) { Tn = tiles[t + 1]; load_edge_l1_t<BAND>(B, wd, bd, Tn, tid, nxt); }   // prefetch, level 1
             if (t >= 2) bar_sync(BAR_EMPTY + (t & 1), kThreadsWs);
             const int ne = T.ne, ntl = T.ntl, lt = T.lt;
             for (int i = tid; i < ntl * kMaxSmallPoses; i += kEdgeThreads) S.slot[i] = -1;
-            if (tid <= ntl) sm.lmoff[tid] = min(B.lm_edge_off[lt + tid] - T.e0, kTileEdges);
+            if (tid <= ntl) sm.lmoff[tid] = min(lm_off[lt + tid] - T.e0, kTileEdges);
 
             // stage A, everything that needs this edge only: residual, Jacobians, Huber weight; the H_ll / b_l terms go to
             // the (still unused) Yn rows as scratch, W, H_pp_e and b_p_e to their final place.  Nothing of the
@@ -187,7 +247,7 @@ __global__ void __maxnreg__(168) k_build_ws(Batch B, int cluster_size) {
             int slot_idx = -1;
             if (tid < ne) {
                 const int p = rec.pw & kPoseMask;
-                const int tl = rec.gl - lt;
+                const int tl = (BAND ? rec.sl : rec.gl) - lt;
                 const bool act = !(rec.pw & kCulledBit) && !((rec.lf & kFixed) && (rec.pf & kFixed));
                 const bool lmfree = (rec.lf & kInHessian) != 0;
                 double *hl = S.Yn + tid * 18;
@@ -240,7 +300,7 @@ __global__ void __maxnreg__(168) k_build_ws(Batch B, int cluster_size) {
                 }
             }
             S.emeta[tid] = meta;
-            if (more) load_edge_l2(B, wd, Tn, tid, gpoint, nxt);                  // prefetch, level 2
+            if (more) load_edge_l2_t<BAND>(B, wd, cpose, Tn, tid, gpoint, nxt);     // prefetch, level 2
             bar_sync(BAR_PROD, kEdgeThreads);
             if (slot_idx >= 0) S.slot[slot_idx] = (short)tid;   // (after the barrier: other threads cleared the table above)
             // per-landmark H_ll (6) / b_l (3): one owner thread per (landmark, entry), edges added in edge order
@@ -332,8 +392,9 @@ __global__ void __maxnreg__(168) k_build_ws(Batch B, int cluster_size) {
     const int NP = offd + F * kHStride;
     for (int task = tid; task < F * kHStride; task += kThreadsWs) vec[offd + task] = sm.pacc[task];
     __syncthreads();
-    double *part = B.part + wd.part_off + (size_t)((blockIdx.x - wd.chunk_off) / cluster_size) * wd.part_stride;
-    if (cluster_size == 1) {
+    double *part = BAND ? bd.part + (size_t)blockIdx.x * kBandPartStride
+                        : B.part + wd.part_off + (size_t)((blockIdx.x - wd.chunk_off) / cluster_size) * wd.part_stride;
+    if (BAND || cluster_size == 1) {
         for (int idx = tid; idx < NP; idx += kThreadsWs) part[idx] = vec[idx];
     } else {
         cg::cluster_group cluster = cg::this_cluster();
@@ -347,6 +408,11 @@ __global__ void __maxnreg__(168) k_build_ws(Batch B, int cluster_size) {
         cluster.sync();
     }
 }
+
+__global__ void __maxnreg__(168) k_build_ws(Batch B, int cluster_size) { build_ws_body<false>(B, cluster_size, Band{}); }
+
+// the same kernel on the band chunks of a large window (ba_band.cuh); one CTA per chunk, no clusters
+__global__ void __maxnreg__(168) k_build_band(Batch B, Band bd) { build_ws_body<true>(B, 1, bd); }
 
 }  // namespace ws
 }  // namespace visfs

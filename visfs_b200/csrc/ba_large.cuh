@@ -337,7 +337,7 @@ struct RunWarp {
 };
 struct RunSmem { RunWarp w[kWarpsL]; };
 
-__global__ void __launch_bounds__(kThreadsL, 1) k_build_large_run(Batch B, const int4 *__restrict__ lm_rec) {
+__global__ void __launch_bounds__(kThreadsL, 1) k_build_large_run(Batch B, const int4 *__restrict__ lm_rec, int n_lm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RunSmem &sm = *reinterpret_cast<RunSmem *>(smem_raw);
     const WinDesc &wd = B.win[0];
@@ -356,8 +356,8 @@ __global__ void __launch_bounds__(kThreadsL, 1) k_build_large_run(Batch B, const
 
     // this warp's piece of the order
     const int nwarp = gridDim.x * kWarpsL, gw = blockIdx.x * kWarpsL + warp;
-    const int per = (wd.n_point + nwarp - 1) / nwarp;
-    const int i0 = min(gw * per, wd.n_point), i1 = min(i0 + per, wd.n_point);
+    const int per = (n_lm + nwarp - 1) / nwarp;   // n_lm records: the whole sorted map, or what the band chunks left over
+    const int i0 = min(gw * per, n_lm), i1 = min(i0 + per, n_lm);
 
     double acc0[36], acc1[36];
 #pragma unroll
@@ -414,7 +414,8 @@ __global__ void __launch_bounds__(kThreadsL, 1) k_build_large_run(Batch B, const
         if (idx >= i1) return;
         if (idx >= blk0 + 32) { blk0 = idx; rblk = (idx + lane < i1) ? lm_rec[idx + lane] : make_int4(0, 0, 0, 0); }
         const int j = idx - blk0;
-        const int l = __shfl_sync(0xffffffffu, rblk.x, j), e0 = __shfl_sync(0xffffffffu, rblk.y, j), d = __shfl_sync(0xffffffffu, rblk.z, j);
+        const int l = __shfl_sync(0xffffffffu, rblk.x, j), e0 = __shfl_sync(0xffffffffu, rblk.y, j);
+        const int d = __shfl_sync(0xffffffffu, rblk.z, j);
         if (lane < d) {
             const int e = e0 + lane;
             n_pw = B.edge_pose[e];
@@ -425,7 +426,8 @@ __global__ void __launch_bounds__(kThreadsL, 1) k_build_large_run(Batch B, const
     request(i0);
     for (int idx = i0; idx < i1; ++idx) {
         const int j = idx - blk0;
-        const int l = __shfl_sync(0xffffffffu, rblk.x, j), d = __shfl_sync(0xffffffffu, rblk.z, j);
+        const int l = __shfl_sync(0xffffffffu, rblk.x, j);
+        const int d = __shfl_sync(0xffffffffu, rblk.z, j);
         const uint8_t lf = (uint8_t)__shfl_sync(0xffffffffu, rblk.w, j);
         (void)l;
         const int pw = n_pw;

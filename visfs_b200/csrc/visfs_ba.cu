@@ -22,6 +22,7 @@
 #include "ba_build_ws.cuh"
 #include "ba_build_ds.cuh"
 #include "ba_large.cuh"
+#include "ba_band.cuh"
 #include "ba_dense.cuh"
 #include "ba_mf.cuh"
 #include "ba_window.cuh"
@@ -142,6 +143,14 @@ struct visfs_ba_handle {
     int max_deg = -1;                 // largest landmark degree of the uploaded batch (-1: unknown, unsorted edge list)
     bool use_run = false;             // k_build_large_run: landmarks walked in the order of their first pose
     DevBuf d_lm_key, d_lm_key2, d_lm_idx, d_lm_order, d_sort_tmp, d_lm_rec;
+    // band chunks (ba_band.cuh): the large build through ws::k_build_band + k_band_gather, no atomics
+    bool use_band = false, band_rest = false;   // band_rest: some landmarks are outside the band chunks (k_build_large_run takes them)
+    int band_n_chunk = 0, band_n_seg = 0;
+    DevBuf d_bd_scan, d_bd_edge, d_bd_obs, d_bd_chunk, d_bd_tiles, d_bd_ent, d_bd_val, d_bd_part, d_bd_rest;
+    int band_n_rest = 0;
+    ws::Band band{};
+    const int *band_key = nullptr, *band_seg = nullptr;
+    const unsigned long long *band_val = nullptr;
     DevBuf d_pcg;
     bool use_front = false;
     bool use_dense = false;           // dense DMMA Cholesky (ba_dense.cuh): wide fronts whose envelope is mostly full
@@ -1018,6 +1027,122 @@ int plan_mf(visfs_ba_handle *h, int F) {
     return VISFS_BA_OK;
 }
 
+int dev_scan(visfs_ba_handle *h, const int *in, int *out, int n, bool inclusive) {
+    size_t tb = 0;
+    if (inclusive) cub::DeviceScan::InclusiveSum(nullptr, tb, in, out, n, h->stream);
+    else cub::DeviceScan::ExclusiveSum(nullptr, tb, in, out, n, h->stream);
+    CK(h->d_sort_tmp.reserve(tb));
+    if (inclusive) CK(cub::DeviceScan::InclusiveSum(h->d_sort_tmp.p, tb, in, out, n, h->stream));
+    else CK(cub::DeviceScan::ExclusiveSum(h->d_sort_tmp.p, tb, in, out, n, h->stream));
+    return VISFS_BA_OK;
+}
+
+// Band chunks of a large window (ba_band.cuh), once per pass after the envelope is laid out.  Needs the landmarks sorted by
+// their first pose (d_lm_key2 = sorted keys, d_lm_rec = sorted records).  Leaves use_band = false when the map has no band
+// structure (landmarks seen from all over the trajectory: C5).
+int prep_band(visfs_ba_handle *h) {
+    cudaStream_t s = h->stream;
+    Batch &B = h->batch;
+    h->use_band = false; h->band_rest = false;
+    const int L = h->tot_point, E = h->tot_edge;
+    const bool force = getenv("VISFS_BA_BAND_FORCE") != nullptr;   // tests: band chunks on maps of any size and shape
+    if ((L < 4096 && !force) || L <= 0 || E <= 0 || h->n_sky >= 0x7fffffffLL / 36) return VISFS_BA_OK;
+    const int g = std::max(1, std::min((L + 256) / 256, 4 * h->sm_count));
+    const size_t n1 = ((size_t)L + 1 + 3) & ~(size_t)3;
+    CK(h->d_bd_scan.reserve(sizeof(int) * 6 * n1));
+    int *deg = h->d_bd_scan.as<int>(), *sorted_off = deg + n1, *newkey = sorted_off + n1, *rank = newkey + n1, *start = rank + n1, *cid = start + n1;
+    int4 *rec = h->d_lm_rec.as<int4>();
+    bd::k_band_deg<<<g, 256, 0, s>>>(rec, h->d_lm_key2.as<int>(), L, deg, newkey);
+    int st;
+    if ((st = dev_scan(h, deg, sorted_off, L + 1, false))) return st;
+    if ((st = dev_scan(h, newkey, rank, L + 1, true))) return st;
+    bd::k_band_flags<<<g, 256, 0, s>>>(rank, L, start);
+    if ((st = dev_scan(h, start, cid, L + 1, true))) return st;
+    int *hs = h->h_small.as<int>() + 16;   // bytes 64 .. 80 of the 128-byte pinned scratch
+    CK(cudaMemcpyAsync(hs, cid + L, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const int nc = hs[0];
+    h->launches += 6;
+    if (nc <= 0 || nc >= (1 << 22)) return VISFS_BA_OK;
+    // per-chunk tables: [chunk (4 ints) | chunk_pose (19) | ntiles | tile_off | npair | pair_off | npose | pose_off] (nc + 1 each) | counts
+    const size_t c1 = ((size_t)nc + 1 + 3) & ~(size_t)3;
+    CK(h->d_bd_chunk.reserve(sizeof(int) * (c1 * (4 + ws::kBandPoses + 6) + 4)));
+    int *cb = h->d_bd_chunk.as<int>();
+    ws::BandChunk *chunk = reinterpret_cast<ws::BandChunk *>(cb);
+    int *chunk_pose = cb + 4 * c1, *ntiles = chunk_pose + ws::kBandPoses * c1, *tile_off = ntiles + c1, *npair = tile_off + c1,
+        *pair_off = npair + c1, *npose = pair_off + c1, *pose_off = npose + c1, *counts = pose_off + c1;
+    CK(cudaMemsetAsync(counts, 0, sizeof(int) * 4, s));
+    CK(h->d_bd_edge.reserve(sizeof(int) * 3 * (size_t)E));
+    CK(h->d_bd_obs.reserve(sizeof(double) * 3 * (size_t)E));
+    int *s_pw = h->d_bd_edge.as<int>(), *s_gl = s_pw + E, *s_sl = s_gl + E;
+    double *s_ou = h->d_bd_obs.as<double>(), *s_ov = s_ou + E, *s_our = s_ov + E;
+    const int gc = std::max(1, (nc + 1 + 127) / 128);
+    bd::k_band_ranges<<<g, 256, 0, s>>>(start, cid, L, chunk);
+    bd::k_band_chunk<<<nc, 256, 0, s>>>(B, rec, sorted_off, chunk, chunk_pose, s_pw, s_gl, s_sl, s_ou, s_ov, s_our, counts);
+    bd::k_band_count_tiles<<<gc, 128, 0, s>>>(chunk, nc, sorted_off, ntiles, npair, npose);
+    if ((st = dev_scan(h, ntiles, tile_off, nc + 1, false))) return st;
+    if ((st = dev_scan(h, npair, pair_off, nc + 1, false))) return st;
+    if ((st = dev_scan(h, npose, pose_off, nc + 1, false))) return st;
+    CK(cudaMemcpyAsync(hs + 0, tile_off + nc, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(hs + 1, pair_off + nc, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(hs + 2, pose_off + nc, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(hs + 3, counts, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const int n_tiles = hs[0], n_pair = hs[1], n_poseent = hs[2], n_in = hs[3];
+    h->launches += 6;
+    if (getenv("VISFS_BA_VERBOSE"))
+        fprintf(stderr, "[visfs_ba] band chunks: %d chunks, %d tiles, %d of %d landmarks inside, %d + %d gather entries\n", nc, n_tiles, n_in, L, n_pair, n_poseent);
+    // worth it when most of the map is inside band chunks of a useful size
+    if (n_tiles <= 0 || n_pair <= 0 || n_in <= 0) return VISFS_BA_OK;
+    if (!force && (n_in * 2 < L || (long long)n_in < 64LL * nc)) return VISFS_BA_OK;
+    const int n_ent = n_pair + n_poseent;
+    CK(h->d_bd_tiles.reserve(sizeof(Tile) * (size_t)n_tiles));
+    CK(h->d_bd_ent.reserve(sizeof(int) * (4 * (size_t)n_ent + 8)));
+    CK(h->d_bd_val.reserve(sizeof(unsigned long long) * 2 * (size_t)n_ent));
+    CK(h->d_bd_part.reserve(sizeof(double) * (size_t)nc * ws::kBandPartStride));
+    int *key = h->d_bd_ent.as<int>(), *key2 = key + n_ent, *flag = key2 + n_ent, *sid = flag + n_ent + 1;
+    // (flag / sid have n_ent + 1 entries; seg_start reuses the unsorted key array afterwards)
+    unsigned long long *val = h->d_bd_val.as<unsigned long long>(), *val2 = val + n_ent;
+    bd::k_band_fill_tiles<<<gc, 128, 0, s>>>(chunk, nc, sorted_off, tile_off, h->d_bd_tiles.as<Tile>());
+    bd::k_band_entries<<<nc, 128, 0, s>>>(B, chunk, nc, chunk_pose, pair_off, n_pair, pose_off, key, val);
+    {
+        size_t tb = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tb, key, key2, val, val2, n_ent, 0, 32, s);
+        CK(h->d_sort_tmp.reserve(tb));
+        CK(cub::DeviceRadixSort::SortPairs(h->d_sort_tmp.p, tb, key, key2, val, val2, n_ent, 0, 32, s));
+    }
+    const int ge = std::max(1, std::min((n_ent + 256) / 256, 4 * h->sm_count));
+    bd::k_band_seg_flags<<<ge, 256, 0, s>>>(key2, n_ent, flag);
+    if ((st = dev_scan(h, flag, sid, n_ent + 1, false))) return st;
+    CK(cudaMemcpyAsync(hs, sid + n_ent, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const int n_seg = hs[0];
+    if (n_seg <= 0 || n_seg > n_ent) return VISFS_BA_OK;
+    int *seg_start = key;   // n_seg + 1 <= n_ent + 1 entries ... the unsorted keys are no longer needed
+    CK(h->d_bd_scan.reserve(sizeof(int) * 6 * n1));   // (no-op: keeps the scan arrays alive for the pass)
+    bd::k_band_seg_starts<<<ge, 256, 0, s>>>(flag, sid, n_ent, seg_start);
+    CK(cudaGetLastError());
+    h->launches += 6;
+    ws::Band &bd_ = h->band;
+    bd_.chunk = chunk; bd_.chunk_pose = chunk_pose; bd_.sorted_off = sorted_off; bd_.s_pw = s_pw; bd_.s_gl = s_gl; bd_.s_sl = s_sl;
+    bd_.s_ou = s_ou; bd_.s_ov = s_ov; bd_.s_our = s_our; bd_.lm_rec = rec; bd_.tiles = h->d_bd_tiles.as<Tile>(); bd_.chunk_tile_off = tile_off;
+    bd_.part = h->d_bd_part.as<double>(); bd_.n_chunk = nc;
+    h->band_key = key2; h->band_val = val2; h->band_seg = seg_start;
+    h->band_n_chunk = nc; h->band_n_seg = n_seg;
+    h->band_rest = n_in < L;
+    h->band_n_rest = L - n_in;
+    if (h->band_rest) {   // what the chunks left over, compacted in sorted order (deg / newkey are free again)
+        CK(h->d_bd_rest.reserve(sizeof(int4) * (size_t)(L - n_in)));
+        bd::k_band_rest_flag<<<g, 256, 0, s>>>(rec, L, newkey);
+        if ((st = dev_scan(h, newkey, deg, L + 1, false))) return st;
+        bd::k_band_rest_fill<<<g, 256, 0, s>>>(rec, newkey, deg, L, h->d_bd_rest.as<int4>());
+        CK(cudaGetLastError());
+        h->launches += 3;
+    }
+    h->use_band = true;
+    return VISFS_BA_OK;
+}
+
 int run_structure_large(visfs_ba_handle *h) {
     Batch &B = h->batch;
     cudaStream_t s = h->stream;
@@ -1066,9 +1191,15 @@ int run_structure_large(visfs_ba_handle *h) {
     CK(cudaStreamSynchronize(s));
     h->n_sky = info[0];
     h->max_front = (int)info[2];
+    const bool sorted_lm = h->use_run;
     if (h->use_run) {   // worth it only when landmarks that touch the same poses follow each other: runs of >= 4 on average
         const long long n_runs = (long long)(int)(info[3] & 0xffffffffLL);
         if (n_runs * 4 > h->tot_point) h->use_run = false;
+    }
+    h->use_band = false;
+    if (sorted_lm && !getenv("VISFS_BA_NO_BAND")) {
+        const int st2 = prep_band(h);
+        if (st2) return st2;
     }
     const long long F = info[1];
     h->st_F_hint = (int)F;
@@ -1129,9 +1260,16 @@ size_t red_doubles(const visfs_ba_handle *h) { return (size_t)h->batch.red_bp_of
 int enqueue_build_large(visfs_ba_handle *h) {
     int ev = ev_begin(h, EV_BUILD);
     CK(cudaMemsetAsync(h->d_red.p, 0, sizeof(double) * red_doubles(h), h->stream));
-    if (h->use_run)
+    if (h->use_band) {
+        ws::k_build_band<<<h->band_n_chunk, ws::kThreadsWs, sizeof(ws::Smem), h->stream>>>(h->batch, h->band);
+        bd::k_band_gather<<<(h->band_n_seg + 6) / 7, 252, 0, h->stream>>>(h->batch, h->band, h->band_key, h->band_val, h->band_seg, h->band_n_seg);
+        if (h->band_rest)
+            lg::k_build_large_run<<<std::max(1, std::min(h->sm_count, (h->band_n_rest + 63) / 64)), lg::kThreadsL, sizeof(lg::RunSmem), h->stream>>>(
+                h->batch, h->d_bd_rest.as<int4>(), h->band_n_rest);
+        h->launches += h->band_rest ? 2 : 1;
+    } else if (h->use_run)
         lg::k_build_large_run<<<std::max(1, std::min(h->sm_count, (h->tot_point + 63) / 64)), lg::kThreadsL, sizeof(lg::RunSmem), h->stream>>>(
-            h->batch, h->d_lm_rec.as<int4>());
+            h->batch, h->d_lm_rec.as<int4>(), h->tot_point);
     else
         lg::k_build_large<false><<<h->grid_build_l, lg::kThreadsL, sizeof(lg::BuildSmemL), h->stream>>>(h->batch);
     if (h->tot_link > 0) {   // odometry links: every rank evaluates them (identical poses), ONE rank adds them to the sums
@@ -1292,7 +1430,7 @@ int run_pass(visfs_ba_handle *h, int pass) {
 int run_resident(visfs_ba_handle *h) {
     if (!h->resident) return h->fail(VISFS_BA_ERR_INVALID, "no batch uploaded");
     CK(cudaSetDevice(h->device));
-    CK(h->h_small.reserve(64));
+    CK(h->h_small.reserve(128));
     h->ev_next = 0;
     for (auto &v : h->ev_used) v.clear();
     h->launches = 0;
@@ -1551,6 +1689,7 @@ int visfs_ba_create(const visfs_ba_config *cfg, visfs_ba_handle **out) {
     cudaFuncSetAttribute(k_update, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_update);
     e = cudaFuncSetAttribute(ws::k_build_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ws::Smem));
     cudaFuncSetAttribute(ds::k_build_ds, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ds::Smem));
+    cudaFuncSetAttribute(ws::k_build_band, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ws::Smem));
     if (getenv("VISFS_BA_VERBOSE")) {
         cudaFuncAttributes fa{};
         cudaFuncGetAttributes(&fa, ws::k_build_ws);
@@ -1823,7 +1962,7 @@ int visfs_ba_structure_build(visfs_ba_handle *h, const visfs_ba_problem *problem
         k_mark_levels<<<grid2(h->tot_edge, 1), 256, 0, s>>>(h->batch, h->d_out_level.as<uint8_t>());
     }
     k_begin_pass<<<1, 128, 0, s>>>(h->batch, 0);
-    CK(h->h_small.reserve(64));
+    CK(h->h_small.reserve(128));
     st = h->large ? run_structure_large(h) : run_structure(h, true);
     if (st) return st;
     // landmark hessian indices: exclusive scan of the in-Hessian flags
@@ -1941,7 +2080,7 @@ int visfs_ba_debug_trial(visfs_ba_handle *h, const visfs_ba_problem *problem, do
     if (st) return st;
     cudaStream_t s = h->stream;
     k_begin_pass<<<1, 128, 0, s>>>(h->batch, 0);
-    CK(h->h_small.reserve(64));
+    CK(h->h_small.reserve(128));
     LMState before;
     DevBuf dbg;
     struct DbgGuard {   // the damping / capture overrides never outlive this call, whichever way it returns
