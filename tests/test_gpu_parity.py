@@ -482,7 +482,7 @@ def test_tensor_pipe_build_variant_matches_oracle(ba, monkeypatch):
         "C1": synth.config_c1(),
         "C1 30% fixed points": synth.config_c1(fixed_point_frac=0.3),
         "consecutive views": synth.make_window(8, 500, layout="consecutive", views=3, seed=77),
-        "rejected steps": rejecting_window(5, 0.08),
+        "rejected steps": rejecting_window(102, (0.3, np.deg2rad(6.0))),
         "chain of links": synth.make_window(7, 400, layout="all", seed=403, links="chain"),
         "no fixed pose": synth.make_window(5, 200, layout="all", seed=12, root=None),
     }

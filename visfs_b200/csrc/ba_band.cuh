@@ -24,8 +24,11 @@ using ws::BandChunk;
 using ws::kBandPartStride;
 using ws::kBandPoses;
 
-constexpr int kBandKeys = 4;          // first-pose values per chunk: with 10 views per landmark a chunk touches 13 poses
-constexpr int kBandMaxLm = 608;       // landmarks per chunk (32 tiles of 19 landmarks x 10 edges)
+constexpr int kBandKeys = 1;          // first-pose values per chunk.  Measured on C4 (ms per build launch): 1 -> 0.90, 2 -> 1.00, 3 -> 1.08,
+                                      // 4 -> 1.15: inside a tile all landmarks start at the same frame, so the pose pairs that
+                                      // no landmark of the tile covers leave their owner threads idle
+constexpr int kBandMaxLm = 2048;      // landmarks per chunk
+constexpr int kChunkCache = 12032;    // edges of a chunk whose pose indices k_band_chunk keeps in shared memory
 constexpr int kBandFlag = 0x80;       // lm_rec.w: this landmark is NOT in a band chunk (lg::k_build_large_run takes it)
 
 // degree of the landmarks in the sorted order (-> exclusive scan = sorted_off) and "a new first pose starts here"
@@ -37,9 +40,9 @@ __global__ void k_band_deg(const int4 *__restrict__ rec, const int *__restrict__
 }
 
 // chunk starts: rank = inclusive scan of newkey (1-based number of the landmark's first-pose value)
-__global__ void k_band_flags(const int *__restrict__ rank, int L, int *start) {
+__global__ void k_band_flags(const int *__restrict__ rank, int L, int *start, int keys, int max_lm) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= L; i += gridDim.x * blockDim.x)
-        start[i] = (i < L && (i == 0 || (rank[i] - 1) / kBandKeys != (rank[i - 1] - 1) / kBandKeys || i % kBandMaxLm == 0)) ? 1 : 0;
+        start[i] = (i < L && (i == 0 || (rank[i] - 1) / keys != (rank[i - 1] - 1) / keys || i % max_lm == 0)) ? 1 : 0;
 }
 
 // cid = INCLUSIVE scan of start: landmark i belongs to chunk cid[i] - 1; the chunk's range
@@ -57,17 +60,32 @@ __global__ void __launch_bounds__(256) k_band_chunk(Batch B, int4 *rec, const in
                                                     int *counts /* [0] landmarks in band chunks */) {
     __shared__ int s_min[8];
     __shared__ int s_list[kBandPoses + 1];
+    __shared__ int s_p[kChunkCache];
     const int c = blockIdx.x, tid = threadIdx.x;
     const int lm0 = chunk[c].lm0, lm1 = chunk[c].lm1;
     const WinDesc &wd = B.win[0];
+    const int eb = sorted_off[lm0], ne = sorted_off[lm1] - eb;
+    const bool cached = ne <= kChunkCache;
+    if (cached) {
+        for (int i = lm0 + tid; i < lm1; i += 256) {
+            const int4 r = rec[i];
+            const int base = sorted_off[i] - eb;
+            for (int k = 0; k < r.z; ++k) s_p[base + k] = B.edge_pose[r.y + k] & kPoseMask;
+        }
+        __syncthreads();
+    }
     int last = -1, n = 0;
     for (;;) {
         int mn = 0x7fffffff;
-        for (int i = lm0 + tid; i < lm1; i += 256) {
-            const int4 r = rec[i];
-            for (int k = 0; k < r.z; ++k) {
-                const int p = B.edge_pose[r.y + k] & kPoseMask;
-                if (p > last) mn = min(mn, p);
+        if (cached) {
+            for (int k = tid; k < ne; k += 256) { const int p = s_p[k]; if (p > last) mn = min(mn, p); }
+        } else {
+            for (int i = lm0 + tid; i < lm1; i += 256) {
+                const int4 r = rec[i];
+                for (int k = 0; k < r.z; ++k) {
+                    const int p = B.edge_pose[r.y + k] & kPoseMask;
+                    if (p > last) mn = min(mn, p);
+                }
             }
         }
 #pragma unroll

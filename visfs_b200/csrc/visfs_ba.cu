@@ -1056,7 +1056,10 @@ int prep_band(visfs_ba_handle *h) {
     int st;
     if ((st = dev_scan(h, deg, sorted_off, L + 1, false))) return st;
     if ((st = dev_scan(h, newkey, rank, L + 1, true))) return st;
-    bd::k_band_flags<<<g, 256, 0, s>>>(rank, L, start);
+    int keys = bd::kBandKeys, max_lm = bd::kBandMaxLm;
+    if (const char *e = getenv("VISFS_BA_BAND_KEYS")) keys = std::max(1, atoi(e));
+    if (const char *e = getenv("VISFS_BA_BAND_MAXLM")) max_lm = std::max(32, atoi(e));
+    bd::k_band_flags<<<g, 256, 0, s>>>(rank, L, start, keys, max_lm);
     if ((st = dev_scan(h, start, cid, L + 1, true))) return st;
     int *hs = h->h_small.as<int>() + 16;   // bytes 64 .. 80 of the 128-byte pinned scratch
     CK(cudaMemcpyAsync(hs, cid + L, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -1264,7 +1267,7 @@ int enqueue_build_large(visfs_ba_handle *h) {
         ws::k_build_band<<<h->band_n_chunk, ws::kThreadsWs, sizeof(ws::Smem), h->stream>>>(h->batch, h->band);
         bd::k_band_gather<<<(h->band_n_seg + 6) / 7, 252, 0, h->stream>>>(h->batch, h->band, h->band_key, h->band_val, h->band_seg, h->band_n_seg);
         if (h->band_rest)
-            lg::k_build_large_run<<<std::max(1, std::min(h->sm_count, (h->band_n_rest + 63) / 64)), lg::kThreadsL, sizeof(lg::RunSmem), h->stream>>>(
+            lg::k_build_large_run<<<std::max(1, std::min(h->sm_count, (h->band_n_rest + 15) / 16)), lg::kThreadsL, sizeof(lg::RunSmem), h->stream>>>(
                 h->batch, h->d_bd_rest.as<int4>(), h->band_n_rest);
         h->launches += h->band_rest ? 2 : 1;
     } else if (h->use_run)
