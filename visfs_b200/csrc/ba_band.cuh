@@ -30,6 +30,7 @@ constexpr int kBandKeys = 1;          // first-pose values per chunk.  Measured 
 constexpr int kBandMaxLm = 2048;      // landmarks per chunk
 constexpr int kChunkCache = 12032;    // edges of a chunk whose pose indices k_band_chunk keeps in shared memory
 constexpr int kBandFlag = 0x80;       // lm_rec.w: this landmark is NOT in a band chunk (lg::k_build_large_run takes it)
+constexpr uint8_t kInBand = 0x40;     // lm_flags: this landmark IS in a band chunk (lg::k_update_large skips it); rewritten every pass by k_struct_lm
 
 // degree of the landmarks in the sorted order (-> exclusive scan = sorted_off) and "a new first pose starts here"
 __global__ void k_band_deg(const int4 *__restrict__ rec, const int *__restrict__ key, int L, int *deg, int *newkey) {
@@ -126,6 +127,7 @@ __global__ void __launch_bounds__(256) k_band_chunk(Batch B, int4 *rec, const in
             s_ou[base + k] = B.obs_u[e]; s_ov[base + k] = B.obs_v[e]; s_our[base + k] = B.obs_r[e];
         }
         if (n < 0) { r.w |= kBandFlag; rec[i] = r; }
+        else B.lm_flags[wd.point_off + r.x] |= kInBand;
     }
 }
 
@@ -242,6 +244,170 @@ __global__ void __launch_bounds__(252) k_band_gather(Batch B, Band bd, const int
         double *dst = B.red + (q < 6 ? B.red_g_off : B.red_bp_off);
         dst[6 * (size_t)h + (q < 6 ? q : q - 6)] += accv;
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_update_band: lg::k_update_large on the band chunks — landmark back-substitution, point oplus, chi2 of the trial state —
+// with the chunk's poses (accepted and trial), pose steps and flags in shared memory under their chunk-local numbers and
+// the edge records read from the sorted copies.  One CTA per chunk, every warp walks a contiguous piece of the chunk's
+// landmarks in warp tiles (whole landmarks, <= 32 edges); offsets and records of the NEXT tile are requested while the
+// current one is computed.  part2[2 c], part2[2 c + 1] = chi2 / scale partials of chunk c.
+// ------------------------------------------------------------------------------------------------
+struct UpdBandSmem {
+    double pose[ws::kMaxPosesWs * kPoseSm];
+    double poseT[ws::kMaxPosesWs * kPoseSm];
+    double xp[ws::kMaxPosesWs * 6];
+    double H[kUpdWarps][32 * kHs];
+    double lm[kUpdWarps][kWtLm * 12];
+    double red[32];
+    int lmoff[kUpdWarps][kWtLm + 1];
+    int hidx[ws::kMaxPosesWs];
+    unsigned char pflag[ws::kMaxPosesWs];
+};
+
+__global__ void __launch_bounds__(kUpdThreads, 2) k_update_band(Batch B, Band bd, double *part2) {
+    __shared__ UpdBandSmem sm;
+    const WinDesc &wd = B.win[0];
+    const LMState &st = B.st[0];
+    if (st.done) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const BandChunk bc = bd.chunk[blockIdx.x];
+    if (bc.n_pose < 0) {
+        if (tid == 0) { part2[2 * (size_t)blockIdx.x] = 0.0; part2[2 * (size_t)blockIdx.x + 1] = 0.0; }
+        return;
+    }
+    const int *__restrict__ cpose = bd.chunk_pose + (size_t)blockIdx.x * kBandPoses;
+    const int cur = st.cur;
+    const double lambda = (wd.trust == 0) ? (B.dbg_lambda >= 0.0 ? B.dbg_lambda : st.lambda) : 0.0;
+    const Intr K = load_intr(wd);
+    const double *__restrict__ gpose = B.pose + ((size_t)cur * B.tot_pose + wd.pose_off) * kPoseStride;
+    const double *__restrict__ gposeT = B.pose + ((size_t)(1 - cur) * B.tot_pose + wd.pose_off) * kPoseStride;
+    const double *__restrict__ gpoint = B.point + (size_t)cur * B.tot_point * 3;
+    double *__restrict__ gpointT = B.point + (size_t)(1 - cur) * B.tot_point * 3;
+    for (int i = tid; i < bc.n_pose * kPoseStride; i += kUpdThreads) {
+        const int j = (i >> 4) * kPoseSm + (i & 15);
+        const size_t g = (size_t)cpose[i >> 4] * kPoseStride + (i & 15);
+        sm.pose[j] = gpose[g]; sm.poseT[j] = gposeT[g];
+    }
+    if (tid < 32) {
+        const int h = (tid < bc.n_pose) ? B.pose_hidx[wd.pose_off + cpose[tid]] : -1;
+        if (tid < bc.n_pose) {
+            sm.hidx[tid] = h;
+            sm.pflag[tid] = B.pose_flags[wd.pose_off + cpose[tid]];
+#pragma unroll
+            for (int a = 0; a < 6; ++a) sm.xp[tid * 6 + a] = (h >= 0) ? B.xp[(size_t)wd.pose_off * 6 + 6 * (size_t)h + a] : 0.0;
+        }
+    }
+    __syncthreads();
+    double *Hs = sm.H[warp], *Ls = sm.lm[warp];
+    int *lmoff = sm.lmoff[warp];
+    double chi_acc = 0.0, scale_acc = 0.0;
+
+    const int n_lm = bc.lm1 - bc.lm0, per = (n_lm + kUpdWarps - 1) / kUpdWarps;
+    const int l_beg = min(bc.lm0 + warp * per, bc.lm1), l_end = min(l_beg + per, bc.lm1);
+    // lane l: offset of landmark lt + l (lanes 0 .. 8) and its record (landmark, first edge, degree, flags)
+    auto req_off = [&](int lt) { return (lt + lane <= l_end && lane <= kWtLm) ? bd.sorted_off[lt + lane] : 0x7fffffff; };
+    auto req_rec = [&](int lt) { return (lt + lane < l_end && lane < kWtLm) ? bd.lm_rec[lt + lane] : make_int4(0, 0, 0, 0); };
+    int off_abs = req_off(l_beg);
+    int4 rec = req_rec(l_beg);
+    for (int lt = l_beg; lt < l_end;) {
+        const int navail = min(kWtLm, l_end - lt);
+        const int e0 = __shfl_sync(0xffffffffu, off_abs, 0);
+        const int off_l = (lane <= navail) ? off_abs - e0 : 0x7fff;
+        int ntl = 1;
+#pragma unroll
+        for (int l = 2; l <= kWtLm; ++l) {
+            const int v = __shfl_sync(0xffffffffu, off_l, l);
+            ntl += (l <= navail && v <= 32) ? 1 : 0;
+        }
+        const int ne = min(__shfl_sync(0xffffffffu, off_l, ntl), 32);
+        const int lf_l = (lane < ntl) ? rec.w : 0;
+        const int gl_l = rec.x;
+        const int g_of = __shfl_sync(0xffffffffu, gl_l, min(lane / 3, kWtLm - 1));
+        const double pt = (lane < 3 * ntl) ? gpoint[3 * (size_t)g_of + (lane - 3 * (lane / 3))] : 0.0;
+        int pw = 0;
+        double ou = 0, ov = 0, our = 0;
+        if (lane < ne) {
+            const int k = e0 + lane;
+            pw = bd.s_pw[k];
+            ou = bd.s_ou[k]; ov = bd.s_ov[k]; our = bd.s_our[k];
+        }
+        // the next tile's offsets and records: requested now, used in the next iteration
+        const int off_next = req_off(lt + ntl);
+        const int4 rec_next = req_rec(lt + ntl);
+        if (lane <= ntl) lmoff[lane] = min(off_l, 32);
+        int tl = 0;
+#pragma unroll
+        for (int l = 1; l < kWtLm; ++l) {
+            const int v = __shfl_sync(0xffffffffu, off_l, l);
+            tl += (l < ntl && v <= lane) ? 1 : 0;
+        }
+        const int lf = __shfl_sync(0xffffffffu, lf_l, tl);
+        const int gl = __shfl_sync(0xffffffffu, gl_l, tl);
+        const double px = __shfl_sync(0xffffffffu, pt, 3 * tl), py = __shfl_sync(0xffffffffu, pt, 3 * tl + 1),
+                     pz = __shfl_sync(0xffffffffu, pt, 3 * tl + 2);
+        bool act = false, mono = false, lmfree = false;
+        int p = 0;
+        double hl[12];
+#pragma unroll
+        for (int q = 0; q < 12; ++q) hl[q] = 0.0;
+        if (lane < ne) {
+            p = pw & kPoseMask;
+            mono = (pw & kMonoBit) != 0;
+            lmfree = (lf & kInHessian) != 0;
+            act = !(pw & kCulledBit) && !((lf & kFixed) && (sm.pflag[p] & kFixed));
+            if (act && lmfree)
+                upd_edge_terms(sm.pose + p * kPoseSm, px, py, pz, ou, ov, our, mono, K, sm.hidx[p] >= 0 ? sm.xp + p * 6 : nullptr, hl);
+#pragma unroll
+            for (int q = 0; q < 12; ++q) Hs[lane * kHs + q] = hl[q];
+        }
+        __syncwarp();
+        for (int task = lane; task < ntl * 12; task += 32) {
+            const int l = task / 12, q = task - l * 12;
+            double sacc = 0.0;
+            for (int e = lmoff[l]; e < lmoff[l + 1]; ++e) sacc += Hs[e * kHs + q];
+            Ls[task] = sacc;
+        }
+        __syncwarp();
+        if (lane < ne) {
+            double np0 = px, np1 = py, np2 = pz;
+            if (lmfree) {
+                double xl[3];
+                const double sc = upd_point_step(Ls + tl * 12, lambda, xl);
+                np0 = px + xl[0]; np1 = py + xl[1]; np2 = pz + xl[2];
+                if (lane == lmoff[tl]) {      // first edge of the landmark: owner of the point
+                    gpointT[3 * (size_t)gl] = np0; gpointT[3 * (size_t)gl + 1] = np1; gpointT[3 * (size_t)gl + 2] = np2;
+                    scale_acc += sc;
+                }
+            }
+            if (act) {
+                double r0, r1, r2, rho, wgt;
+                edge_residual(sm.poseT + p * kPoseSm, np0, np1, np2, ou, ov, our, mono, K, r0, r1, r2);
+                huber((r0 * r0 + r1 * r1 + r2 * r2) * K.inv_pv, K.delta, rho, wgt);
+                chi_acc += rho;
+            }
+        }
+        __syncwarp();
+        lt += ntl;
+        off_abs = off_next; rec = rec_next;
+    }
+    const double chi = block_sum(chi_acc, sm.red);
+    const double sc = block_sum(scale_acc, sm.red);
+    if (tid == 0) { part2[2 * (size_t)blockIdx.x] = chi; part2[2 * (size_t)blockIdx.x + 1] = sc; }
+}
+
+// chi2 / scale partials of lg::k_update_large (na CTAs, may be 0) and of k_update_band (nb chunks), in that order -> out[0], out[1]
+__global__ void k_band_fold(Batch B, const double *__restrict__ a, int na, const double *__restrict__ b, int nb, double *out) {
+    __shared__ double red[32];
+    if (B.st[0].done) return;
+    double x = 0.0, y = 0.0;
+    for (int i = threadIdx.x; i < na + nb; i += blockDim.x) {
+        const double *src = (i < na) ? a + 2 * (size_t)i : b + 2 * (size_t)(i - na);
+        x += src[0]; y += src[1];
+    }
+    const double sx = block_sum(x, red);
+    const double sy = block_sum(y, red);
+    if (threadIdx.x == 0) { out[0] = sx; out[1] = sy; }
 }
 
 }  // namespace bd

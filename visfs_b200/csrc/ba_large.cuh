@@ -1386,7 +1386,7 @@ __global__ void __launch_bounds__(kPcgThreads) k_solve_pcg(Batch B, double *work
 // ------------------------------------------------------------------------------------------------
 // k_update_large: landmark back-substitution, point oplus, chi2 of the trial state
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreadsL) k_update_large(Batch B) {
+__global__ void __launch_bounds__(kThreadsL) k_update_large(Batch B, int skip_band) {
     // Several whole landmarks per warp step, one edge per lane (the warp tiles of the small-window k_update, formed on
     // the fly): the warp takes the next landmarks of its block whose edges fit 32 lanes (<= 8 landmarks).  Per-landmark
     // sums go through the warp's shared-memory slab in edge order.
@@ -1453,8 +1453,9 @@ __global__ void __launch_bounds__(kThreadsL) k_update_large(Batch B) {
         if (lane < ne) {
             p = pw & kPoseMask;
             mono = (pw & kMonoBit) != 0;
-            lmfree = (lf & kInHessian) != 0;
-            act = !(pw & kCulledBit) && !((lf & kFixed) && (B.pose_flags[p] & kFixed));
+            const bool skip = skip_band && (lf & 0x40);   // a landmark of the band chunks: bd::k_update_band owns it (ba_band.cuh)
+            lmfree = (lf & kInHessian) != 0 && !skip;
+            act = !(pw & kCulledBit) && !((lf & kFixed) && (B.pose_flags[p] & kFixed)) && !skip;
             if (act && lmfree) {
                 const int hi = B.pose_hidx[p];
                 upd_edge_terms(gpose + (size_t)p * kPoseStride, px, py, pz, ou, ov, our, mono, K, hi >= 0 ? B.xp + 6 * (size_t)hi : nullptr, hl);

@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(Batch B) {
     const int npairs = all_pairs ? F * (F + 1) / 2 : F * (F - 1) / 2;
     const int offd = npairs * 36;
     const double *part = B.part + wd.part_off;
-    const int nparts = B.parts_reduced ? 1 : wd.n_parts;
+    const int nparts = B.parts_reduced ? min(1, wd.n_parts) : wd.n_parts;
     const size_t stride = (size_t)wd.part_stride;
     // up to 32 independent loads in flight per entry (one CTA has to pull every partial through its own SM),
     // added in part order

@@ -146,7 +146,7 @@ struct visfs_ba_handle {
     // band chunks (ba_band.cuh): the large build through ws::k_build_band + k_band_gather, no atomics
     bool use_band = false, band_rest = false;   // band_rest: some landmarks are outside the band chunks (k_build_large_run takes them)
     int band_n_chunk = 0, band_n_seg = 0;
-    DevBuf d_bd_scan, d_bd_edge, d_bd_obs, d_bd_chunk, d_bd_tiles, d_bd_ent, d_bd_val, d_bd_part, d_bd_rest;
+    DevBuf d_bd_part2, d_bd_scan, d_bd_edge, d_bd_obs, d_bd_chunk, d_bd_tiles, d_bd_ent, d_bd_val, d_bd_part, d_bd_rest;
     int band_n_rest = 0;
     ws::Band band{};
     const int *band_key = nullptr, *band_seg = nullptr;
@@ -1103,6 +1103,7 @@ int prep_band(visfs_ba_handle *h) {
     CK(h->d_bd_ent.reserve(sizeof(int) * (4 * (size_t)n_ent + 8)));
     CK(h->d_bd_val.reserve(sizeof(unsigned long long) * 2 * (size_t)n_ent));
     CK(h->d_bd_part.reserve(sizeof(double) * (size_t)nc * ws::kBandPartStride));
+    CK(h->d_bd_part2.reserve(sizeof(double) * 2 * (size_t)nc));
     int *key = h->d_bd_ent.as<int>(), *key2 = key + n_ent, *flag = key2 + n_ent, *sid = flag + n_ent + 1;
     // (flag / sid have n_ent + 1 entries; seg_start reuses the unsorted key array afterwards)
     unsigned long long *val = h->d_bd_val.as<unsigned long long>(), *val2 = val + n_ent;
@@ -1347,10 +1348,20 @@ int enqueue_rest_large(visfs_ba_handle *h) {
     ev_end(h, ev);
     DBG_SYNC("solve kernel");
     ev = ev_begin(h, EV_UPDATE);
-    lg::k_update_large<<<h->grid_update_l, lg::kThreadsL, 0, h->stream>>>(h->batch);
-    ev_end(h, ev);
-    ev = ev_begin(h, EV_OTHER);
-    lg::k_fold_part2<<<1, 256, 0, h->stream>>>(h->batch, h->grid_update_l, 0, h->d_scal.as<double>() + 2);
+    if (h->use_band && !getenv("VISFS_BA_NO_BAND_UPDATE")) {
+        if (h->band_rest) lg::k_update_large<<<h->grid_update_l, lg::kThreadsL, 0, h->stream>>>(h->batch, 1);
+        bd::k_update_band<<<h->band_n_chunk, kUpdThreads, 0, h->stream>>>(h->batch, h->band, h->d_bd_part2.as<double>());
+        ev_end(h, ev);
+        ev = ev_begin(h, EV_OTHER);
+        bd::k_band_fold<<<1, 256, 0, h->stream>>>(h->batch, h->batch.part2, h->band_rest ? h->grid_update_l : 0, h->d_bd_part2.as<double>(),
+                                                 h->band_n_chunk, h->d_scal.as<double>() + 2);
+        h->launches += h->band_rest ? 1 : 0;
+    } else {
+        lg::k_update_large<<<h->grid_update_l, lg::kThreadsL, 0, h->stream>>>(h->batch, 0);
+        ev_end(h, ev);
+        ev = ev_begin(h, EV_OTHER);
+        lg::k_fold_part2<<<1, 256, 0, h->stream>>>(h->batch, h->grid_update_l, 0, h->d_scal.as<double>() + 2);
+    }
     if ((st = allreduce(h, h->d_scal.as<double>() + 2, 2, ncclFloat64, ncclSum))) return st;
     k_control<<<1, 32, 0, h->stream>>>(h->batch_ctl);
     ev_end(h, ev);
