@@ -27,7 +27,7 @@ using ws::kBandPoses;
 constexpr int kBandKeys = 1;          // first-pose values per chunk.  Measured on C4 (ms per build launch): 1 -> 0.90, 2 -> 1.00, 3 -> 1.08,
                                       // 4 -> 1.15: inside a tile all landmarks start at the same frame, so the pose pairs that
                                       // no landmark of the tile covers leave their owner threads idle
-constexpr int kBandMaxLm = 2048;      // landmarks per chunk
+constexpr int kBandMaxLm = 608;       // landmarks per chunk (32 tiles of 19 landmarks x 10 edges): bounds the longest chunk of a launch
 constexpr int kChunkCache = 12032;    // edges of a chunk whose pose indices k_band_chunk keeps in shared memory
 constexpr int kBandFlag = 0x80;       // lm_rec.w: this landmark is NOT in a band chunk (lg::k_build_large_run takes it)
 constexpr uint8_t kInBand = 0x40;     // lm_flags: this landmark IS in a band chunk (lg::k_update_large skips it); rewritten every pass by k_struct_lm
@@ -40,10 +40,16 @@ __global__ void k_band_deg(const int4 *__restrict__ rec, const int *__restrict__
     }
 }
 
-// chunk starts: rank = inclusive scan of newkey (1-based number of the landmark's first-pose value)
-__global__ void k_band_flags(const int *__restrict__ rank, int L, int *start, int keys, int max_lm) {
+// chunk starts: rank = inclusive scan of newkey (1-based number of the landmark's first-pose value).  A group = `keys`
+// consecutive values; gstart[i] = i where a group starts, else 0 -> an inclusive MAX scan gives every landmark the start of its
+// group, and groups longer than max_lm are cut every max_lm landmarks counted from there.
+__global__ void k_band_gstart(const int *__restrict__ rank, int L, int keys, int *gstart) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= L; i += gridDim.x * blockDim.x)
-        start[i] = (i < L && (i == 0 || (rank[i] - 1) / keys != (rank[i - 1] - 1) / keys || i % max_lm == 0)) ? 1 : 0;
+        gstart[i] = (i < L && i > 0 && (rank[i] - 1) / keys != (rank[i - 1] - 1) / keys) ? i : 0;
+}
+__global__ void k_band_flags(const int *__restrict__ gpos, int L, int *start, int max_lm) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= L; i += gridDim.x * blockDim.x)
+        start[i] = (i < L && (i - gpos[i]) % max_lm == 0) ? 1 : 0;
 }
 
 // cid = INCLUSIVE scan of start: landmark i belongs to chunk cid[i] - 1; the chunk's range
@@ -140,11 +146,14 @@ __global__ void k_band_rest_fill(const int4 *__restrict__ rec, const int *__rest
         if (flag[i]) rest[pos[i]] = rec[i];
 }
 
-__global__ void k_band_count_tiles(const BandChunk *__restrict__ chunk, int n_chunk, const int *__restrict__ sorted_off, int *ntiles, int *npair, int *npose) {
+__global__ void k_band_count_tiles(const BandChunk *__restrict__ chunk, int n_chunk, const int *__restrict__ sorted_off, int *ntiles, int *npair, int *npose,
+                                   int *cost, int *cidx) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c > n_chunk) return;
     const bool ok = c < n_chunk && chunk[c].n_pose >= 0;
     ntiles[c] = ok ? walk_tiles<false>(sorted_off, chunk[c].lm0, chunk[c].lm1, nullptr, kTileLm, kTileEdges) : 0;
+    // launch order: longest first.  A tile costs more the more block pairs its chunk has (fewer landmark groups in stage C).
+    if (c < n_chunk) { cost[c] = 0x7fffffff - (ok ? ntiles[c] * (64 + chunk[c].F * (chunk[c].F + 1) / 2) : 0); cidx[c] = c; }
     npair[c] = ok ? chunk[c].F * (chunk[c].F + 1) / 2 : 0;   // gather entries: pair blocks ...
     npose[c] = ok ? chunk[c].F : 0;                           // ... and per-pose sums
 }
@@ -271,12 +280,13 @@ __global__ void __launch_bounds__(kUpdThreads, 2) k_update_band(Batch B, Band bd
     const LMState &st = B.st[0];
     if (st.done) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const BandChunk bc = bd.chunk[blockIdx.x];
+    const int c = bd.order[blockIdx.x];   // longest chunks first
+    const BandChunk bc = bd.chunk[c];
     if (bc.n_pose < 0) {
-        if (tid == 0) { part2[2 * (size_t)blockIdx.x] = 0.0; part2[2 * (size_t)blockIdx.x + 1] = 0.0; }
+        if (tid == 0) { part2[2 * (size_t)c] = 0.0; part2[2 * (size_t)c + 1] = 0.0; }
         return;
     }
-    const int *__restrict__ cpose = bd.chunk_pose + (size_t)blockIdx.x * kBandPoses;
+    const int *__restrict__ cpose = bd.chunk_pose + (size_t)c * kBandPoses;
     const int cur = st.cur;
     const double lambda = (wd.trust == 0) ? (B.dbg_lambda >= 0.0 ? B.dbg_lambda : st.lambda) : 0.0;
     const Intr K = load_intr(wd);
@@ -393,7 +403,7 @@ __global__ void __launch_bounds__(kUpdThreads, 2) k_update_band(Batch B, Band bd
     }
     const double chi = block_sum(chi_acc, sm.red);
     const double sc = block_sum(scale_acc, sm.red);
-    if (tid == 0) { part2[2 * (size_t)blockIdx.x] = chi; part2[2 * (size_t)blockIdx.x + 1] = sc; }
+    if (tid == 0) { part2[2 * (size_t)c] = chi; part2[2 * (size_t)c + 1] = sc; }
 }
 
 // chi2 / scale partials of lg::k_update_large (na CTAs, may be 0) and of k_update_band (nb chunks), in that order -> out[0], out[1]

@@ -83,6 +83,7 @@ struct Band {
     const int4 *lm_rec;                        // [L] sorted landmark -> (landmark, first edge, degree, flags)
     const Tile *tiles;
     const int *chunk_tile_off;
+    const int *order;                          // [n_chunk] launch order: chunks by decreasing cost (tiles x block pairs)
     double *part;                              // [n_chunk][kBandPartStride]
     int n_chunk;
 };
@@ -172,13 +173,14 @@ __device__ __forceinline__ void build_ws_body(const Batch &B, int cluster_size, 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
     const int tid = threadIdx.x;
-    const int win = BAND ? 0 : B.chunks[blockIdx.x].win;
+    const int cidx = BAND ? bd.order[blockIdx.x] : (int)blockIdx.x;   // band chunks are launched longest first
+    const int win = BAND ? 0 : B.chunks[cidx].win;
     const WinDesc &wd = B.win[win];
     const LMState &st = B.st[win];
     if (st.done) return;   // uniform over the cluster: all its chunks belong to one window
     BandChunk bc{0, 0, 0, 0};
-    if (BAND) { bc = bd.chunk[blockIdx.x]; if (bc.n_pose < 0) return; }
-    const int *__restrict__ cpose = BAND ? bd.chunk_pose + (size_t)blockIdx.x * kBandPoses : nullptr;
+    if (BAND) { bc = bd.chunk[cidx]; if (bc.n_pose < 0) return; }
+    const int *__restrict__ cpose = BAND ? bd.chunk_pose + (size_t)cidx * kBandPoses : nullptr;
     const int cur = st.cur;
     const int F = BAND ? bc.F : st.F;
     const double lambda = (wd.trust == 0) ? (B.dbg_lambda >= 0.0 ? B.dbg_lambda : st.lambda) : 0.0;
@@ -188,7 +190,7 @@ __device__ __forceinline__ void build_ws_body(const Batch &B, int cluster_size, 
     const double *__restrict__ gpoint = B.point + (size_t)cur * B.tot_point * 3;
     const int *__restrict__ tile_off = BAND ? bd.chunk_tile_off : B.chunk_tile_off;
     const int *__restrict__ lm_off = BAND ? bd.sorted_off : B.lm_edge_off;
-    const int tile0 = tile_off[blockIdx.x], ntiles = tile_off[blockIdx.x + 1] - tile0;
+    const int tile0 = tile_off[cidx], ntiles = tile_off[cidx + 1] - tile0;
     const Tile *__restrict__ tiles = (BAND ? bd.tiles : B.tiles) + tile0;
 
     if (BAND) {   // the chunk's poses, numbered 0 .. n_pose - 1 in ascending pose order; the free ones 0 .. F - 1 in that order
@@ -392,7 +394,7 @@ __device__ __forceinline__ void build_ws_body(const Batch &B, int cluster_size, 
     const int NP = offd + F * kHStride;
     for (int task = tid; task < F * kHStride; task += kThreadsWs) vec[offd + task] = sm.pacc[task];
     __syncthreads();
-    double *part = BAND ? bd.part + (size_t)blockIdx.x * kBandPartStride
+    double *part = BAND ? bd.part + (size_t)cidx * kBandPartStride
                         : B.part + wd.part_off + (size_t)((blockIdx.x - wd.chunk_off) / cluster_size) * wd.part_stride;
     if (BAND || cluster_size == 1) {
         for (int idx = tid; idx < NP; idx += kThreadsWs) part[idx] = vec[idx];

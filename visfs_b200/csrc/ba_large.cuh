@@ -569,12 +569,14 @@ __global__ void __launch_bounds__(kThreadsL, 1) k_build_large_run(Batch B, const
 __global__ void k_lm_first(Batch B, int *key, int *idx) {
     const WinDesc &wd = B.win[0];
     for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < wd.n_point; l += gridDim.x * blockDim.x) {
-        int mn = 0x7fffffff;
+        int mn = 0x7fffffff, mx = -1;
         for (int e = B.lm_edge_off[l]; e < B.lm_edge_off[l + 1]; ++e) {
             const int hi = B.pose_hidx[B.edge_pose[e] & kPoseMask];
-            if (hi >= 0) mn = min(mn, hi);
+            if (hi >= 0) { mn = min(mn, hi); mx = max(mx, hi); }
         }
-        key[l] = mn;
+        // landmarks that span more poses than a band chunk holds (loop closures) sort behind all others, again by first pose:
+        // together with their neighbours they would push every chunk they land in over the pose limit (ba_band.cuh)
+        key[l] = (mx - mn >= 19 && mn < (1 << 24)) ? mn + (1 << 24) : mn;
         idx[l] = l;
     }
 }

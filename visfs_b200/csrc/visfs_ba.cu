@@ -1056,12 +1056,26 @@ int prep_band(visfs_ba_handle *h) {
     int st;
     if ((st = dev_scan(h, deg, sorted_off, L + 1, false))) return st;
     if ((st = dev_scan(h, newkey, rank, L + 1, true))) return st;
-    int keys = bd::kBandKeys, max_lm = bd::kBandMaxLm;
+    int *hs = h->h_small.as<int>() + 16;   // bytes 64 .. 80 of the 128-byte pinned scratch
+    // first-pose values per chunk: one when a value has >= ~256 landmarks (measured best on C4, ba_band.cuh); a rank of a
+    // partitioned run holds 1 / N of every value's landmarks, so it takes N values per chunk to keep the chunks at a size
+    // where the per-chunk prologue / epilogue does not dominate (bounded by the 19 poses a chunk may touch)
+    CK(cudaMemcpyAsync(hs, rank + (L - 1), sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const int n_keys = std::max(hs[0], 1);
+    int keys = (int)std::lround(256.0 * n_keys / L), max_lm = bd::kBandMaxLm;
+    keys = std::max(bd::kBandKeys, std::min(keys, std::max(1, ws::kBandPoses - std::max(h->max_deg, 1))));
     if (const char *e = getenv("VISFS_BA_BAND_KEYS")) keys = std::max(1, atoi(e));
     if (const char *e = getenv("VISFS_BA_BAND_MAXLM")) max_lm = std::max(32, atoi(e));
-    bd::k_band_flags<<<g, 256, 0, s>>>(rank, L, start, keys, max_lm);
+    bd::k_band_gstart<<<g, 256, 0, s>>>(rank, L, keys, start);
+    {   // cid (free until the chunk ids are formed) = start of every landmark's group: inclusive max scan
+        size_t tb = 0;
+        cub::DeviceScan::InclusiveScan(nullptr, tb, start, cid, cub::Max(), L + 1, s);
+        CK(h->d_sort_tmp.reserve(tb));
+        CK(cub::DeviceScan::InclusiveScan(h->d_sort_tmp.p, tb, start, cid, cub::Max(), L + 1, s));
+    }
+    bd::k_band_flags<<<g, 256, 0, s>>>(cid, L, start, max_lm);
     if ((st = dev_scan(h, start, cid, L + 1, true))) return st;
-    int *hs = h->h_small.as<int>() + 16;   // bytes 64 .. 80 of the 128-byte pinned scratch
     CK(cudaMemcpyAsync(hs, cid + L, sizeof(int), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     const int nc = hs[0];
@@ -1069,11 +1083,12 @@ int prep_band(visfs_ba_handle *h) {
     if (nc <= 0 || nc >= (1 << 22)) return VISFS_BA_OK;
     // per-chunk tables: [chunk (4 ints) | chunk_pose (19) | ntiles | tile_off | npair | pair_off | npose | pose_off] (nc + 1 each) | counts
     const size_t c1 = ((size_t)nc + 1 + 3) & ~(size_t)3;
-    CK(h->d_bd_chunk.reserve(sizeof(int) * (c1 * (4 + ws::kBandPoses + 6) + 4)));
+    CK(h->d_bd_chunk.reserve(sizeof(int) * (c1 * (4 + ws::kBandPoses + 10) + 4)));
     int *cb = h->d_bd_chunk.as<int>();
     ws::BandChunk *chunk = reinterpret_cast<ws::BandChunk *>(cb);
     int *chunk_pose = cb + 4 * c1, *ntiles = chunk_pose + ws::kBandPoses * c1, *tile_off = ntiles + c1, *npair = tile_off + c1,
-        *pair_off = npair + c1, *npose = pair_off + c1, *pose_off = npose + c1, *counts = pose_off + c1;
+        *pair_off = npair + c1, *npose = pair_off + c1, *pose_off = npose + c1, *cost = pose_off + c1, *cidx = cost + c1,
+        *cost2 = cidx + c1, *order = cost2 + c1, *counts = order + c1;
     CK(cudaMemsetAsync(counts, 0, sizeof(int) * 4, s));
     CK(h->d_bd_edge.reserve(sizeof(int) * 3 * (size_t)E));
     CK(h->d_bd_obs.reserve(sizeof(double) * 3 * (size_t)E));
@@ -1082,7 +1097,13 @@ int prep_band(visfs_ba_handle *h) {
     const int gc = std::max(1, (nc + 1 + 127) / 128);
     bd::k_band_ranges<<<g, 256, 0, s>>>(start, cid, L, chunk);
     bd::k_band_chunk<<<nc, 256, 0, s>>>(B, rec, sorted_off, chunk, chunk_pose, s_pw, s_gl, s_sl, s_ou, s_ov, s_our, counts);
-    bd::k_band_count_tiles<<<gc, 128, 0, s>>>(chunk, nc, sorted_off, ntiles, npair, npose);
+    bd::k_band_count_tiles<<<gc, 128, 0, s>>>(chunk, nc, sorted_off, ntiles, npair, npose, cost, cidx);
+    {
+        size_t tb = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tb, cost, cost2, cidx, order, nc, 0, 32, s);
+        CK(h->d_sort_tmp.reserve(tb));
+        CK(cub::DeviceRadixSort::SortPairs(h->d_sort_tmp.p, tb, cost, cost2, cidx, order, nc, 0, 32, s));
+    }
     if ((st = dev_scan(h, ntiles, tile_off, nc + 1, false))) return st;
     if ((st = dev_scan(h, npair, pair_off, nc + 1, false))) return st;
     if ((st = dev_scan(h, npose, pose_off, nc + 1, false))) return st;
@@ -1094,10 +1115,10 @@ int prep_band(visfs_ba_handle *h) {
     const int n_tiles = hs[0], n_pair = hs[1], n_poseent = hs[2], n_in = hs[3];
     h->launches += 6;
     if (getenv("VISFS_BA_VERBOSE"))
-        fprintf(stderr, "[visfs_ba] band chunks: %d chunks, %d tiles, %d of %d landmarks inside, %d + %d gather entries\n", nc, n_tiles, n_in, L, n_pair, n_poseent);
+        fprintf(stderr, "[visfs_ba] band chunks: %d first-pose values per chunk, %d chunks, %d tiles, %d of %d landmarks inside, %d + %d gather entries\n", keys, nc, n_tiles, n_in, L, n_pair, n_poseent);
     // worth it when most of the map is inside band chunks of a useful size
     if (n_tiles <= 0 || n_pair <= 0 || n_in <= 0) return VISFS_BA_OK;
-    if (!force && (n_in * 2 < L || (long long)n_in < 64LL * nc)) return VISFS_BA_OK;
+    if (!force && (n_in * 2 < L || (long long)n_in < 32LL * nc)) return VISFS_BA_OK;
     const int n_ent = n_pair + n_poseent;
     CK(h->d_bd_tiles.reserve(sizeof(Tile) * (size_t)n_tiles));
     CK(h->d_bd_ent.reserve(sizeof(int) * (4 * (size_t)n_ent + 8)));
@@ -1129,7 +1150,7 @@ int prep_band(visfs_ba_handle *h) {
     h->launches += 6;
     ws::Band &bd_ = h->band;
     bd_.chunk = chunk; bd_.chunk_pose = chunk_pose; bd_.sorted_off = sorted_off; bd_.s_pw = s_pw; bd_.s_gl = s_gl; bd_.s_sl = s_sl;
-    bd_.s_ou = s_ou; bd_.s_ov = s_ov; bd_.s_our = s_our; bd_.lm_rec = rec; bd_.tiles = h->d_bd_tiles.as<Tile>(); bd_.chunk_tile_off = tile_off;
+    bd_.s_ou = s_ou; bd_.s_ov = s_ov; bd_.s_our = s_our; bd_.lm_rec = rec; bd_.tiles = h->d_bd_tiles.as<Tile>(); bd_.chunk_tile_off = tile_off; bd_.order = order;
     bd_.part = h->d_bd_part.as<double>(); bd_.n_chunk = nc;
     h->band_key = key2; h->band_val = val2; h->band_seg = seg_start;
     h->band_n_chunk = nc; h->band_n_seg = n_seg;
