@@ -412,7 +412,10 @@ def global_ba_numbers(ba, dist, world, rank, local, barrier, reduce_max, reduce_
         elif use_oracle:
             from tests import oracle_api as O
             cores = os.cpu_count() or 1
+            t_cpu = time.perf_counter()
             ref = O.solve(w, threads=cores, omp=True)
+            out["cpu_oracle_s"] = time.perf_counter() - t_cpu
+            out["cpu_oracle_threads"] = cores
             what = f"CPU oracle (OpenMP, {cores} threads) solving the same C4"
             same = same_decisions(r, ref, r["edge_level"], ref["edge_level"])
             chi_rel = max(abs(r[k] - ref[k]) / max(abs(ref[k]), 1e-300) for k in ("chi2_initial", "chi2_pass1", "chi2_final"))
