@@ -80,7 +80,7 @@
 extern "C" {
 #endif
 
-#define VISFS_BA_ABI_VERSION 4
+#define VISFS_BA_ABI_VERSION 5
 
 typedef enum visfs_ba_status {
     VISFS_BA_OK = 0,
@@ -319,6 +319,12 @@ int  visfs_ba_window_remove_frame(visfs_ba_window *w, int64_t frame_id);
 int  visfs_ba_window_remove_points(visfs_ba_window *w, int32_t n, const int64_t *point_id);
 int  visfs_ba_window_remove_observations(visfs_ba_window *w, int32_t n, const int64_t *point_id, const int64_t *frame_id);
 int  visfs_ba_window_set_poses(visfs_ba_window *w, int32_t n, const int64_t *frame_id, const double *pose_tq);
+/* Odometry links between frames of the map (LocalMap::getSignatureLinks, LocalMap.cpp:238-272 -> Optimizer.cpp:116-150): REPLACES
+ * the link set.  link_tq as visfs_ba_problem::link_tq (T_c1c2 as t, q); a link whose frames are not both in the window at the
+ * time of a solve takes no part in it, so links may be declared before their frames arrive and need not be withdrawn when a
+ * frame leaves.  odometry_variance as visfs_ba_problem::odometry_variance (> 0 when n > 0). */
+int  visfs_ba_window_set_links(visfs_ba_window *w, int32_t n, const int64_t *from_frame_id, const int64_t *to_frame_id,
+                               const double *link_tq /* [n][7] */, double odometry_variance);
 /* root_frame_id: the fixed pose (Estimator.cpp:252: newest id - 1); a value that is not in the window fixes none */
 int  visfs_ba_window_solve(visfs_ba_window *w, int64_t root_frame_id, visfs_ba_window_result *result);
 int  visfs_ba_window_get_points(visfs_ba_window *w, int32_t n, const int64_t *point_id, double *xyz_out);

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol(built):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/visfs_ba.h but not exported"
     assert sorted(capi.EXPORTS) == names
-    assert lib.visfs_ba_abi_version() == 4
+    assert lib.visfs_ba_abi_version() == 5
 
 
 def test_struct_layouts_match_the_header(built):

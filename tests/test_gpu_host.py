@@ -72,11 +72,12 @@ def test_local_optimize_repeated_calls_reuse_their_buffers(built, tmp_path):
     assert 0.0 < t["marshal_ms"] < t["local_optimize_ms_best"] < 50.0
 
 
-def test_resident_local_map_class_equals_local_optimize(built, tmp_path):
+@pytest.mark.parametrize("links", [None, "chain"])
+def test_resident_local_map_class_equals_local_optimize(built, tmp_path, links):
     # VISFS::Optimizer::ResidentLocalMap: the same window fed signature by signature as LocalMap's deltas,
     # then one localOptimize on the resident map, must return what Optimizer::localOptimize returns for the maps the reference
     # would have built: poses, culled (feature, signature) pairs, and the points after the 5 m write-back rule
-    w = synth.make_window(6, 300, layout="consecutive", views=4, seed=84, mono_frac=0.2, fixed_point_frac=0.1, first_id=5)
+    w = synth.make_window(6, 300, layout="consecutive", views=4, seed=84, mono_frac=0.2, fixed_point_frac=0.1, first_id=5, links=links)
     fin, f1, f2 = str(tmp_path / "w.bin"), str(tmp_path / "o1.bin"), str(tmp_path / "o2.bin")
     host_io.write_window(fin, w, feature_id_offset=40)
     a = host_io.run_solve(fin, f1, mode="solve")

@@ -20,7 +20,7 @@ class Mirror:
     """LocalMap's bookkeeping in Python; solve() = getSignaturePoses + getFeaturePosesAndObservations + localOptimize (oracle)."""
 
     def __init__(self, seq):
-        self.seq, self.frames, self.points, self.obs = seq, {}, {}, {}
+        self.seq, self.frames, self.points, self.obs, self.links = seq, {}, {}, {}, []
 
     def window(self, root):
         fids = sorted(self.frames)
@@ -41,6 +41,11 @@ class Mirror:
                  edge_pose=np.array([fidx[k[1]] for k in keys], dtype=np.int32),
                  edge_point=np.array([pidx[k[0]] for k in keys], dtype=np.int32),
                  edge_kind=np.array([self.obs[k][1] for k in keys], dtype=np.uint8))
+        if self.links:                                           # LocalMap::getSignatureLinks: consecutive signatures of the map
+            lk = [(a, b, tq) for (a, b, tq) in self.links if a in fidx and b in fidx]
+            w.update(n_links=len(lk), link_from=np.array([fidx[a] for a, _, _ in lk], dtype=np.int32),
+                     link_to=np.array([fidx[b] for _, b, _ in lk], dtype=np.int32),
+                     link_tq=np.array([tq for _, _, tq in lk], dtype=np.float64).reshape(-1, 7), odometry_variance=self.seq["odometry_variance"])
         return w, fids, pids, keys
 
     def solve(self, root):
@@ -58,8 +63,8 @@ class Mirror:
         return r
 
 
-def replay(ba, seed, stable_after=None):
-    seq = synth.make_window(36, 700, views=5, layout="consecutive", seed=seed, outlier_frac=0.08)
+def replay(ba, seed, stable_after=None, links=False):
+    seq = synth.make_window(36, 700, views=5, layout="consecutive", seed=seed, outlier_frac=0.08, links="chain" if links else None)
     first_seen = {}
     for e in range(seq["n_edges"]):
         p, f = int(seq["edge_point"][e]), int(seq["edge_pose"][e])
@@ -67,6 +72,10 @@ def replay(ba, seed, stable_after=None):
     win = capi.ResidentWindow(ba, WINDOW + 1, 600, 6000, fx=seq["fx"], fy=seq["fy"], cx=seq["cx"], cy=seq["cy"], bf=seq["bf"],
                               pixel_variance=seq["pixel_variance"], huber_delta=seq["huber_delta"], iterations=seq["iterations"])
     mir = Mirror(seq)
+    if links:   # declared once, before any frame exists: a solve uses the links whose two frames are in the window at that time
+        a, b = seq["pose_id"][seq["link_from"]], seq["pose_id"][seq["link_to"]]
+        win.set_links(a, b, seq["link_tq"], seq["odometry_variance"])
+        mir.links = [(int(x), int(y), tq.copy()) for x, y, tq in zip(a, b, seq["link_tq"])]
     solved, h2d_solves, full_bytes = 0, 0, 0
     for f in range(seq["n_poses"]):
         fid = int(seq["pose_id"][f])
@@ -134,6 +143,12 @@ def test_sliding_window_equals_resolving_from_scratch_every_frame(ba):
     assert solved >= 30
     # a solve sends the frame table and the batch descriptors only: far less than the window the reference re-marshals
     assert h2d < 0.25 * full, (h2d, full)
+
+
+def test_sliding_window_with_odometry_links(ba):
+    # Optimizer.cpp:116-150 on the resident map: EdgePoseConstraint between consecutive frames of the window
+    solved, _, _ = replay(ba, seed=503, links=True)
+    assert solved >= 30
 
 
 def test_sliding_window_with_stable_features(ba):

@@ -98,7 +98,7 @@ EXPORTS = ["visfs_ba_abi_version", "visfs_ba_create", "visfs_ba_destroy", "visfs
            "visfs_ba_host_alloc", "visfs_ba_host_free", "visfs_ba_debug_pose_oplus", "visfs_ba_debug_link_linearize",
            "visfs_ba_window_create", "visfs_ba_window_destroy", "visfs_ba_window_set_points", "visfs_ba_window_insert_frame",
            "visfs_ba_window_remove_frame", "visfs_ba_window_remove_points", "visfs_ba_window_remove_observations",
-           "visfs_ba_window_set_poses", "visfs_ba_window_solve", "visfs_ba_window_get_points", "visfs_ba_window_h2d_bytes_total"]
+           "visfs_ba_window_set_poses", "visfs_ba_window_set_links", "visfs_ba_window_solve", "visfs_ba_window_get_points", "visfs_ba_window_h2d_bytes_total"]
 
 
 def _ptr(a, typ):
@@ -253,6 +253,7 @@ def load_library(path=LIB_PATH):
     lib.visfs_ba_window_remove_points.argtypes = [C.c_void_p, C.c_int32, _i64p]
     lib.visfs_ba_window_remove_observations.argtypes = [C.c_void_p, C.c_int32, _i64p, _i64p]
     lib.visfs_ba_window_set_poses.argtypes = [C.c_void_p, C.c_int32, _i64p, _dp]
+    lib.visfs_ba_window_set_links.argtypes = [C.c_void_p, C.c_int32, _i64p, _i64p, _dp, C.c_double]
     lib.visfs_ba_window_solve.argtypes = [C.c_void_p, C.c_int64, C.POINTER(WindowResult)]
     lib.visfs_ba_window_get_points.argtypes = [C.c_void_p, C.c_int32, _i64p, _dp]
     lib.visfs_ba_window_h2d_bytes_total.argtypes = [C.c_void_p]
@@ -528,6 +529,14 @@ class ResidentWindow:
         a = np.ascontiguousarray(frame_ids, dtype=np.int64)
         tq = np.ascontiguousarray(pose_tq, dtype=np.float64)
         self.ba._check(self.lib.visfs_ba_window_set_poses(self.w, len(a), _ptr(a, _i64p), _ptr(tq, _dp)))
+
+    def set_links(self, from_ids, to_ids, link_tq, odometry_variance):
+        """Replace the odometry links of the map (by frame id); links whose frames are not both present are skipped by a solve."""
+        a = np.ascontiguousarray(from_ids, dtype=np.int64)
+        b = np.ascontiguousarray(to_ids, dtype=np.int64)
+        tq = np.ascontiguousarray(link_tq, dtype=np.float64).reshape(-1, 7)
+        assert len(a) == len(b) == len(tq)
+        self.ba._check(self.lib.visfs_ba_window_set_links(self.w, len(a), _ptr(a, _i64p), _ptr(b, _i64p), _ptr(tq, _dp), float(odometry_variance)))
 
     def get_points(self, ids):
         ids = np.ascontiguousarray(ids, dtype=np.int64)

@@ -1628,6 +1628,9 @@ struct visfs_ba_window {
     std::unordered_map<uint64_t, int> ob_index;        // (feature slot, frame slot) -> pool index of the live observation
     std::vector<std::vector<int>> frame_obs, point_obs;   // pool indices per slot
     std::vector<int64_t> point_id_of_slot, frame_id_of_slot;
+    struct Link { int64_t from, to; double tq[7]; };
+    std::vector<Link> links;                           // odometry links by frame id (visfs_ba_window_set_links)
+    double odometry_variance = 0.0;
     int64_t h2d_total = 0;
     // device
     DevBuf d_frame_tq, d_frame_pose, d_pose_slot, d_point_xyz, d_point_fixed, d_point_id, d_order, d_ob_point, d_ob_frame, d_ob_obs,
@@ -2501,6 +2504,29 @@ int visfs_ba_window_set_poses(visfs_ba_window *w, int32_t n, const int64_t *fram
     return VISFS_BA_OK;
 }
 
+int visfs_ba_window_set_links(visfs_ba_window *w, int32_t n, const int64_t *from_frame_id, const int64_t *to_frame_id, const double *link_tq,
+                              double odometry_variance) {
+    if (!w) return VISFS_BA_ERR_INVALID;
+    if (n < 0 || (n > 0 && (!from_frame_id || !to_frame_id || !link_tq))) return win_fail(w, VISFS_BA_ERR_INVALID, "set_links: null arrays");
+    if (n > 0 && !(odometry_variance > 0.0)) return win_fail(w, VISFS_BA_ERR_INVALID, "set_links: odometry_variance must be positive");
+    for (int k = 0; k < n; ++k) {
+        if (from_frame_id[k] == to_frame_id[k]) return win_fail(w, VISFS_BA_ERR_INVALID, "set_links: a link from a frame to itself");
+        double nq = 0.0;
+        for (int a = 0; a < 7; ++a) {
+            if (!std::isfinite(link_tq[7 * (size_t)k + a])) return win_fail(w, VISFS_BA_ERR_INVALID, "set_links: non-finite measurement");
+            if (a >= 3) nq += link_tq[7 * (size_t)k + a] * link_tq[7 * (size_t)k + a];
+        }
+        if (!(nq > 0.0)) return win_fail(w, VISFS_BA_ERR_INVALID, "set_links: zero quaternion");
+    }
+    w->links.resize((size_t)n);
+    for (int k = 0; k < n; ++k) {
+        w->links[(size_t)k].from = from_frame_id[k]; w->links[(size_t)k].to = to_frame_id[k];
+        memcpy(w->links[(size_t)k].tq, link_tq + 7 * (size_t)k, 56);
+    }
+    w->odometry_variance = odometry_variance;
+    return VISFS_BA_OK;
+}
+
 int visfs_ba_window_get_points(visfs_ba_window *w, int32_t n, const int64_t *point_id, double *xyz_out) {
     if (!w) return VISFS_BA_ERR_INVALID;
     visfs_ba_handle *h = w->h;
@@ -2527,13 +2553,23 @@ int visfs_ba_window_solve(visfs_ba_window *w, int64_t root_frame_id, visfs_ba_wi
     int *tab = w->h_small.as<int>();
     int root_pose = -1;
     for (int i = 0; i < maxF; ++i) tab[i] = -1;
+    std::vector<int32_t> link_from, link_to;
+    std::vector<double> link_tq;
     {
         int k = 0;
+        std::unordered_map<int64_t, int> pose_of;
         for (const auto &kv : w->frame_slot) {
             tab[kv.second] = k; tab[maxF + k] = kv.second;
             if (kv.first == root_frame_id) root_pose = k;
             if (res->frame_id) res->frame_id[k] = kv.first;
+            pose_of[kv.first] = k;
             ++k;
+        }
+        for (const auto &lk : w->links) {   // the links whose two frames are in the window (Optimizer.cpp:130: uContains(_poses, ...))
+            const auto a = pose_of.find(lk.from), b = pose_of.find(lk.to);
+            if (a == pose_of.end() || b == pose_of.end()) continue;
+            link_from.push_back(a->second); link_to.push_back(b->second);
+            link_tq.insert(link_tq.end(), lk.tq, lk.tq + 7);
         }
     }
     CK(cudaMemcpyAsync(w->d_frame_pose.p, tab, 4 * (size_t)maxF, cudaMemcpyHostToDevice, s));
@@ -2588,6 +2624,9 @@ int visfs_ba_window_solve(visfs_ba_window *w, int64_t root_frame_id, visfs_ba_wi
     pb.fx = w->cfg.fx; pb.fy = w->cfg.fy; pb.cx = w->cfg.cx; pb.cy = w->cfg.cy; pb.bf = w->cfg.bf;
     pb.pixel_variance = w->cfg.pixel_variance; pb.huber_delta = w->cfg.huber_delta;
     pb.iterations = w->cfg.iterations; pb.solver = w->cfg.solver; pb.trust_region = w->cfg.trust_region;
+    pb.n_links = (int32_t)link_from.size();   // (the links travel from the host like in a full call: a few dozen bytes each)
+    pb.link_from = link_from.data(); pb.link_to = link_to.data(); pb.link_tq = link_tq.data();
+    pb.odometry_variance = w->odometry_variance;
     DevInput dev;
     dev.max_degree = std::max(P, 1); dev.n_fixed = root_pose >= 0 ? 1 : 0;
     dev.emit = [&](visfs_ba_handle *hh) -> int {

@@ -379,7 +379,8 @@ std::map<std::size_t, Eigen::Isometry3d> Optimizer::localOptimize(
 // ================================================================================================
 ResidentLocalMap::ResidentLocalMap(const ParametersMap & _parameters, const std::vector<std::shared_ptr<GeometricCamera>> & _cameraModels,
                                    int _maxSignatures, int _maxFeatures) :
-    handle_(nullptr), window_(nullptr), fx_(0.0), baseLine_(0.0), maxSignatures_(_maxSignatures),
+    handle_(nullptr), window_(nullptr), fx_(0.0), baseLine_(0.0), odometryCovariance_(Parameters::defaultOptimizerOdometryCovariance()),
+    maxSignatures_(_maxSignatures),
     maxObservations_(4 * _maxSignatures * _maxFeatures) {
     // the same parameters, with the same defaults, as Optimizer (corelib/src/Optimizer/Optimizer.cpp:37-56)
     int solver = Parameters::defaultOptimizerSolver(), trust = Parameters::defaultOptimizerTrustRegion(), iterations = Parameters::defaultOptimizerIterations();
@@ -389,6 +390,7 @@ ResidentLocalMap::ResidentLocalMap(const ParametersMap & _parameters, const std:
     Parameters::parse(_parameters, Parameters::kOptimizerIterations(), iterations);
     Parameters::parse(_parameters, Parameters::kOptimizerPixelVariance(), pixelVariance);
     Parameters::parse(_parameters, Parameters::kOptimizerRobustKernelDelta(), delta);
+    Parameters::parse(_parameters, Parameters::kOptimizerOdometryCovariance(), odometryCovariance_);
     if (_cameraModels.empty() || !_cameraModels.front()) { fail("ResidentLocalMap: no camera model"); return; }
     const GeometricCamera & cameraModel = *_cameraModels.front();
     Trc_ = cameraModel.getTansformImageToRobot();
@@ -482,6 +484,26 @@ bool ResidentLocalMap::setSignaturePose(std::size_t _id, const Eigen::Isometry3d
     cameraState(_pose, Trc_, tq);
     const int64_t id = static_cast<int64_t>(_id);
     return visfs_ba_window_set_poses(window_, 1, &id, tq) == VISFS_BA_OK || fail("ResidentLocalMap::setSignaturePose");
+}
+
+bool ResidentLocalMap::setLinks(const std::map<std::size_t, std::tuple<std::size_t, std::size_t, Eigen::Isometry3d>> & _links) {
+    if (!window_) return false;
+    std::vector<int64_t> from, to;
+    std::vector<double> tq;
+    const Eigen::Isometry3d TriInv = Trc_.inverse();
+    for (auto iter = _links.begin(); iter != _links.end(); ++iter) {
+        const std::size_t fromId = std::get<0>(iter->second), toId = std::get<1>(iter->second);
+        if (!(fromId > 0 && toId > 0) || fromId == toId) continue;                   // Optimizer.cpp:126-129
+        const Eigen::Isometry3d Tc1c2 = TriInv * std::get<2>(iter->second) * Trc_;   // :133
+        double q[4];
+        rotationToQuaternion(Tc1c2.linear(), q);
+        const Eigen::Vector3d & t = Tc1c2.translation();
+        const double rec[7] = {t[0], t[1], t[2], q[0], q[1], q[2], q[3]};
+        from.push_back(static_cast<int64_t>(fromId)); to.push_back(static_cast<int64_t>(toId));
+        tq.insert(tq.end(), rec, rec + 7);
+    }
+    return visfs_ba_window_set_links(window_, static_cast<int32_t>(from.size()), from.data(), to.data(), tq.data(), odometryCovariance_) == VISFS_BA_OK ||
+           fail("ResidentLocalMap::setLinks");
 }
 
 bool ResidentLocalMap::getFeaturePose(std::size_t _featureId, Eigen::Vector3d & _pose) {

@@ -199,6 +199,9 @@ public:
     bool removeFeature(std::size_t _featureId);
     bool removeObservation(std::size_t _featureId, std::size_t _signatureId);
     bool setSignaturePose(std::size_t _id, const Eigen::Isometry3d & _pose);
+    /** \brief LocalMap::getSignatureLinks' result (<link id, <from, to, T_r1r2>>): replaces the odometry links of the map.
+      * A link takes part in a solve when both its signatures are in the map then (Optimizer.cpp:126-131). */
+    bool setLinks(const std::map<std::size_t, std::tuple<std::size_t, std::size_t, Eigen::Isometry3d>> & _links);
     bool getFeaturePose(std::size_t _featureId, Eigen::Vector3d & _pose);
 
     /** \brief Optimizer::localOptimize on the resident map.  \return optimised poses (T_world<-robot); EMPTY on failure. */
@@ -211,7 +214,7 @@ private:
     visfs_ba_handle * handle_;
     visfs_ba_window * window_;
     Eigen::Isometry3d Trc_;
-    double fx_, baseLine_;
+    double fx_, baseLine_, odometryCovariance_;
     int maxSignatures_, maxObservations_;
     std::string message_;
     std::vector<int64_t> ids_, outlierPoint_, outlierFrame_;

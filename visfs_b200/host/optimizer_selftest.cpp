@@ -119,6 +119,7 @@ int main(int argc, char **argv) {
             }
             ok = ok && map.insertSignature(pk.first, pk.second, obs);
         }
+        ok = ok && map.setLinks(links);   // LocalMap::getSignatureLinks -> the resident map's link set
         if (!ok) { std::fprintf(stderr, "ResidentLocalMap: %s\n", map.lastMessage().c_str()); return 1; }
         std::vector<std::tuple<std::size_t, std::size_t>> outliers;
         auto result = map.localOptimize((std::size_t)rootId, outliers);
