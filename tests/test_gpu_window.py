@@ -63,13 +63,13 @@ class Mirror:
         return r
 
 
-def replay(ba, seed, stable_after=None, links=False):
+def replay(ba, seed, stable_after=None, links=False, max_obs=6000):
     seq = synth.make_window(36, 700, views=5, layout="consecutive", seed=seed, outlier_frac=0.08, links="chain" if links else None)
     first_seen = {}
     for e in range(seq["n_edges"]):
         p, f = int(seq["edge_point"][e]), int(seq["edge_pose"][e])
         first_seen[p] = min(first_seen.get(p, 10**9), f)
-    win = capi.ResidentWindow(ba, WINDOW + 1, 600, 6000, fx=seq["fx"], fy=seq["fy"], cx=seq["cx"], cy=seq["cy"], bf=seq["bf"],
+    win = capi.ResidentWindow(ba, WINDOW + 1, 600, max_obs, fx=seq["fx"], fy=seq["fy"], cx=seq["cx"], cy=seq["cy"], bf=seq["bf"],
                               pixel_variance=seq["pixel_variance"], huber_delta=seq["huber_delta"], iterations=seq["iterations"])
     mir = Mirror(seq)
     if links:   # declared once, before any frame exists: a solve uses the links whose two frames are in the window at that time
@@ -143,6 +143,12 @@ def test_sliding_window_equals_resolving_from_scratch_every_frame(ba):
     assert solved >= 30
     # a solve sends the frame table and the batch descriptors only: far less than the window the reference re-marshals
     assert h2d < 0.25 * full, (h2d, full)
+
+
+def test_sliding_window_with_a_small_observation_pool(ba):
+    # the append-only pool holds 900 observations, the map about 600 live ones: the pool is compacted on the device every few frames
+    solved, _, _ = replay(ba, seed=504, max_obs=900)
+    assert solved >= 30
 
 
 def test_sliding_window_with_odometry_links(ba):

@@ -141,8 +141,32 @@ __global__ void k_win_scatter_points(int n, const int *slot, const double *xyz, 
     }
 }
 
-__global__ void k_win_kill_list(uint8_t *ob_dead, const int *list, int n) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) ob_dead[list[i]] = 1;
+// Removing features / single observations without a host copy of the pool: the delta sets bits in mask[feature slot] (bit f =
+// frame slot f, all bits = the whole feature), one pass over the pool marks what the masks cover, the masks are cleared again.
+__global__ void k_win_mask_set(unsigned *mask, const int *pslot, const int *fslot /* or null: all frames */, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        atomicOr(&mask[pslot[i]], fslot ? (1u << fslot[i]) : 0xffffffffu);
+}
+__global__ void k_win_mask_kill(const unsigned *mask, const int *ob_point, const int *ob_frame, uint8_t *ob_dead, int n_pool) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pool; i += gridDim.x * blockDim.x)
+        if ((mask[ob_point[i]] >> ob_frame[i]) & 1u) ob_dead[i] = 1;
+}
+__global__ void k_win_mask_clear(unsigned *mask, const int *pslot, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) mask[pslot[i]] = 0u;
+}
+
+// Compaction of the append-only pool on the device: pos = exclusive scan of the live flags
+__global__ void k_win_live(const uint8_t *ob_dead, int n_pool, int *live) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= n_pool; i += gridDim.x * blockDim.x) live[i] = (i < n_pool && !ob_dead[i]) ? 1 : 0;
+}
+__global__ void k_win_compact(const int *live, const int *pos, int n_pool, const int *ob_point, const int *ob_frame, const float *ob_obs,
+                              const uint8_t *ob_kind, int *t_point, int *t_frame, float *t_obs, uint8_t *t_kind) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pool; i += gridDim.x * blockDim.x) {
+        if (!live[i]) continue;
+        const int d = pos[i];
+        t_point[d] = ob_point[i]; t_frame[d] = ob_frame[i]; t_kind[d] = ob_kind[i];
+        t_obs[3 * d] = ob_obs[3 * i]; t_obs[3 * d + 1] = ob_obs[3 * i + 1]; t_obs[3 * d + 2] = ob_obs[3 * i + 2];
+    }
 }
 
 }  // namespace wn

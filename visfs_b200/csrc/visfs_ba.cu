@@ -1623,10 +1623,10 @@ struct visfs_ba_window {
     std::map<int64_t, int> point_order;                // ascending feature id -> slot (std::map order of Optimizer.cpp:156)
     std::vector<int> free_points;
     bool order_dirty = true;
-    struct Ob { int pslot, fslot; float o[3]; uint8_t kind, dead; };
-    std::vector<Ob> pool;                              // mirror of the device pool (for compaction and duplicate checks)
-    std::unordered_map<uint64_t, int> ob_index;        // (feature slot, frame slot) -> pool index of the live observation
-    std::vector<std::vector<int>> frame_obs, point_obs;   // pool indices per slot
+    // the observation pool lives on the device only (append-only, tombstones); the host knows how many entries it holds
+    int n_pool = 0;
+    std::vector<int> stamp;                            // per feature slot: the insert_frame call that last saw it (duplicate check)
+    int stamp_now = 0;
     std::vector<int64_t> point_id_of_slot, frame_id_of_slot;
     struct Link { int64_t from, to; double tq[7]; };
     std::vector<Link> links;                           // odometry links by frame id (visfs_ba_window_set_links)
@@ -1635,7 +1635,7 @@ struct visfs_ba_window {
     // device
     DevBuf d_frame_tq, d_frame_pose, d_pose_slot, d_point_xyz, d_point_fixed, d_point_id, d_order, d_ob_point, d_ob_frame, d_ob_obs,
         d_ob_kind, d_ob_dead, d_cnt, d_act, d_rank, d_rank_of_slot, d_slot_of_rank, d_key, d_key2, d_val, d_val2, d_counters, d_scan_tmp,
-        d_sort_tmp, d_pose_out, d_outliers, d_list;
+        d_sort_tmp, d_pose_out, d_outliers, d_list, d_mask, d_compact;
     PinBuf h_small, h_stage;
     DevBuf d_stage;
     cudaEvent_t stage_done = nullptr;              // the last asynchronous copy out of h_stage
@@ -1645,43 +1645,45 @@ struct visfs_ba_window {
         if (h_stage.reserve(bytes) != cudaSuccess || d_stage.reserve(bytes) != cudaSuccess) return nullptr;
         return h_stage.as<char>();
     }
-    static uint64_t okey(int pslot, int fslot) { return ((uint64_t)(uint32_t)pslot << 8) | (uint32_t)fslot; }
 };
 
 namespace {
 
 int win_fail(visfs_ba_window *w, int st, const std::string &msg) { return w->h->fail(st, "window: " + msg); }
 
-// the device pool is append-only; when it is full the live observations are re-packed from the host mirror
+// the device pool is append-only; when it is full the live observations are packed to its front on the device
 int win_compact(visfs_ba_window *w) {
     visfs_ba_handle *h = w->h;
-    std::vector<visfs_ba_window::Ob> live;
-    live.reserve(w->pool.size());
-    for (const auto &o : w->pool) if (!o.dead) live.push_back(o);
-    w->pool.swap(live);
-    w->ob_index.clear();
-    for (auto &v : w->frame_obs) v.clear();
-    for (auto &v : w->point_obs) v.clear();
-    const size_t n = w->pool.size();
-    std::vector<int> op(n), of(n);
-    std::vector<float> oo(3 * n);
-    std::vector<uint8_t> ok(n);
-    for (size_t i = 0; i < n; ++i) {
-        const auto &o = w->pool[i];
-        op[i] = o.pslot; of[i] = o.fslot; oo[3 * i] = o.o[0]; oo[3 * i + 1] = o.o[1]; oo[3 * i + 2] = o.o[2]; ok[i] = o.kind;
-        w->ob_index[visfs_ba_window::okey(o.pslot, o.fslot)] = (int)i;
-        w->frame_obs[(size_t)o.fslot].push_back((int)i); w->point_obs[(size_t)o.pslot].push_back((int)i);
-    }
     cudaStream_t s = h->stream;
-    if (n) {
-        CK(cudaMemcpyAsync(w->d_ob_point.p, op.data(), 4 * n, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(w->d_ob_frame.p, of.data(), 4 * n, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(w->d_ob_obs.p, oo.data(), 12 * n, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(w->d_ob_kind.p, ok.data(), n, cudaMemcpyHostToDevice, s));
+    const int n = w->n_pool;
+    if (n == 0) return VISFS_BA_OK;
+    const size_t N = (size_t)n;
+    // scratch: live (n + 1) | pos (n + 1) | point | frame | obs (3 n floats) | kind
+    const size_t o_live = 0, o_pos = o_live + 4 * (N + 1), o_p = o_pos + 4 * (N + 1), o_f = o_p + 4 * N, o_o = o_f + 4 * N, o_k = o_o + 12 * N;
+    CK(w->d_compact.reserve(o_k + N + 16));
+    char *base = w->d_compact.as<char>();
+    int *live = reinterpret_cast<int *>(base + o_live), *pos = reinterpret_cast<int *>(base + o_pos);
+    const int g = std::max(1, std::min((n + 256) / 256, 1024));
+    wn::k_win_live<<<g, 256, 0, s>>>(w->d_ob_dead.as<uint8_t>(), n, live);
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, live, pos, n + 1, s);
+    CK(w->d_scan_tmp.reserve(tb));
+    CK(cub::DeviceScan::ExclusiveSum(w->d_scan_tmp.p, tb, live, pos, n + 1, s));
+    wn::k_win_compact<<<g, 256, 0, s>>>(live, pos, n, w->d_ob_point.as<int>(), w->d_ob_frame.as<int>(), w->d_ob_obs.as<float>(), w->d_ob_kind.as<uint8_t>(),
+                                        reinterpret_cast<int *>(base + o_p), reinterpret_cast<int *>(base + o_f), reinterpret_cast<float *>(base + o_o),
+                                        reinterpret_cast<uint8_t *>(base + o_k));
+    int *cnt_h = w->h_small.as<int>() + 2 * w->cfg.max_frames;
+    CK(cudaMemcpyAsync(cnt_h, pos + n, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const size_t m = (size_t)cnt_h[0];
+    if (m) {
+        CK(cudaMemcpyAsync(w->d_ob_point.p, base + o_p, 4 * m, cudaMemcpyDeviceToDevice, s));
+        CK(cudaMemcpyAsync(w->d_ob_frame.p, base + o_f, 4 * m, cudaMemcpyDeviceToDevice, s));
+        CK(cudaMemcpyAsync(w->d_ob_obs.p, base + o_o, 12 * m, cudaMemcpyDeviceToDevice, s));
+        CK(cudaMemcpyAsync(w->d_ob_kind.p, base + o_k, m, cudaMemcpyDeviceToDevice, s));
     }
     CK(cudaMemsetAsync(w->d_ob_dead.p, 0, (size_t)w->cfg.max_observations, s));
-    CK(cudaStreamSynchronize(s));
-    w->h2d_total += (int64_t)(21 * n);
+    w->n_pool = (int)m;
     return VISFS_BA_OK;
 }
 
@@ -2290,7 +2292,7 @@ int visfs_ba_window_create(visfs_ba_handle *h, const visfs_ba_window_config *cfg
     const size_t F = (size_t)cfg->max_frames, L = (size_t)cfg->max_points, E = (size_t)cfg->max_observations;
     for (int i = (int)F - 1; i >= 0; --i) w->free_frames.push_back(i);
     for (int i = (int)L - 1; i >= 0; --i) w->free_points.push_back(i);
-    w->frame_obs.resize(F); w->point_obs.resize(L);
+    w->stamp.assign(L, 0);
     w->point_id_of_slot.assign(L, -1); w->frame_id_of_slot.assign(F, -1);
     cudaError_t e = cudaSuccess;
     auto R = [&](DevBuf &b, size_t bytes) { if (e == cudaSuccess) e = b.reserve(bytes); };
@@ -2298,10 +2300,11 @@ int visfs_ba_window_create(visfs_ba_handle *h, const visfs_ba_window_config *cfg
     R(w->d_point_id, 8 * L); R(w->d_order, 4 * L); R(w->d_ob_point, 4 * E); R(w->d_ob_frame, 4 * E); R(w->d_ob_obs, 12 * E);
     R(w->d_ob_kind, E); R(w->d_ob_dead, E); R(w->d_cnt, 4 * L); R(w->d_act, 4 * L); R(w->d_rank, 4 * L); R(w->d_rank_of_slot, 4 * L);
     R(w->d_slot_of_rank, 4 * L); R(w->d_key, 4 * E); R(w->d_key2, 4 * E); R(w->d_val, 4 * E); R(w->d_val2, 4 * E); R(w->d_counters, 16);
-    R(w->d_pose_out, 56 * F); R(w->d_outliers, 8 * E); R(w->d_list, 4 * E);
+    R(w->d_pose_out, 56 * F); R(w->d_outliers, 8 * E); R(w->d_list, 8 * E); R(w->d_mask, 4 * L);
     if (e == cudaSuccess) e = w->h_small.reserve(4096 + 56 * F + 8 * E);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&w->stage_done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMemsetAsync(w->d_ob_dead.p, 0, E, h->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(w->d_mask.p, 0, 4 * L, h->stream);
     if (e != cudaSuccess) { const int st = h->cuda_fail(e, "window allocation"); delete w; return st; }
     *out = w;
     return VISFS_BA_OK;
@@ -2365,42 +2368,37 @@ int visfs_ba_window_insert_frame(visfs_ba_window *w, int64_t frame_id, const dou
     if (w->free_frames.empty()) return win_fail(w, VISFS_BA_ERR_INVALID, "insert_frame: window full (remove a frame first, LocalMap::removeSignature)");
     CK(cudaSetDevice(h->device));
     const int fslot = w->free_frames.back();
-    // validate before anything changes
-    std::vector<int> pslots((size_t)n_obs);
-    {
-        std::unordered_map<int, int> seen;
-        for (int i = 0; i < n_obs; ++i) {
-            auto it = w->point_slot.find(point_id[i]);
-            if (it == w->point_slot.end()) return win_fail(w, VISFS_BA_ERR_INVALID, "insert_frame: observation of a feature that was never set (visfs_ba_window_set_points)");
-            pslots[(size_t)i] = it->second;
-            if (!seen.emplace(it->second, i).second) return win_fail(w, VISFS_BA_ERR_INVALID, "insert_frame: two observations of one feature in one frame");
-        }
+    const size_t n = (size_t)n_obs;
+    // one packed delta [pose | feature slots | frame slots | observations | kinds] -> one staging buffer, contiguous appends.
+    // The feature slots are looked up straight into it; nothing of the window changes before the whole list has been validated.
+    const size_t o_pose = 0, o_ps = 64, o_fs = o_ps + 4 * n, o_obs = o_fs + 4 * n, o_kind = o_obs + 12 * n, bytes = o_kind + n;
+    char *sg = w->stage(bytes);
+    if (!sg) return win_fail(w, VISFS_BA_ERR_CUDA, "insert_frame: staging allocation failed");
+    int *ps = reinterpret_cast<int *>(sg + o_ps), *fs = reinterpret_cast<int *>(sg + o_fs);
+    const int now = ++w->stamp_now;
+    for (size_t i = 0; i < n; ++i) {
+        auto it = w->point_slot.find(point_id[i]);
+        if (it == w->point_slot.end()) return win_fail(w, VISFS_BA_ERR_INVALID, "insert_frame: observation of a feature that was never set (visfs_ba_window_set_points)");
+        const int slot = it->second;
+        if (w->stamp[(size_t)slot] == now) return win_fail(w, VISFS_BA_ERR_INVALID, "insert_frame: two observations of one feature in one frame");
+        w->stamp[(size_t)slot] = now;
+        ps[i] = slot; fs[i] = fslot;
     }
-    if ((int)w->pool.size() + n_obs > w->cfg.max_observations) {
+    if (w->n_pool + n_obs > w->cfg.max_observations) {
         const int st = win_compact(w);
         if (st) return st;
-        if ((int)w->pool.size() + n_obs > w->cfg.max_observations) return win_fail(w, VISFS_BA_ERR_INVALID, "insert_frame: observation pool full (max_observations)");
+        if (w->n_pool + n_obs > w->cfg.max_observations) return win_fail(w, VISFS_BA_ERR_INVALID, "insert_frame: observation pool full (max_observations)");
     }
     w->free_frames.pop_back();
     w->frame_slot.emplace(frame_id, fslot);
     w->frame_id_of_slot[(size_t)fslot] = frame_id;
     cudaStream_t s = h->stream;
-    const size_t at = w->pool.size(), n = (size_t)n_obs;
-    // one packed delta [pose | feature slots | frame slots | observations | kinds] -> one copy, the pieces are contiguous appends
-    const size_t o_pose = 0, o_ps = 64, o_fs = o_ps + 4 * n, o_obs = o_fs + 4 * n, o_kind = o_obs + 12 * n, bytes = o_kind + n;
-    char *sg = w->stage(bytes);
-    if (!sg) return win_fail(w, VISFS_BA_ERR_CUDA, "insert_frame: staging allocation failed");
+    const size_t at = (size_t)w->n_pool;
     memcpy(sg + o_pose, pose_tq, 56);
-    for (size_t i = 0; i < n; ++i) {
-        visfs_ba_window::Ob o{pslots[i], fslot, {obs_uvr[3 * i], obs_uvr[3 * i + 1], obs_uvr[3 * i + 2]}, (uint8_t)(kind ? kind[i] : 0), 0};
-        reinterpret_cast<int *>(sg + o_ps)[i] = o.pslot;
-        reinterpret_cast<int *>(sg + o_fs)[i] = fslot;
-        sg[o_kind + i] = (char)o.kind;
-        w->ob_index[visfs_ba_window::okey(o.pslot, fslot)] = (int)(at + i);
-        w->frame_obs[(size_t)fslot].push_back((int)(at + i)); w->point_obs[(size_t)o.pslot].push_back((int)(at + i));
-        w->pool.push_back(o);
+    if (n) {
+        memcpy(sg + o_obs, obs_uvr, 12 * n);
+        if (kind) memcpy(sg + o_kind, kind, n); else memset(sg + o_kind, 0, n);
     }
-    if (n) memcpy(sg + o_obs, obs_uvr, 12 * n);
     CK(cudaMemcpyAsync(w->d_frame_tq.as<double>() + 7 * (size_t)fslot, sg + o_pose, 56, cudaMemcpyHostToDevice, s));
     if (n) {
         CK(cudaMemcpyAsync(w->d_ob_point.as<int>() + at, sg + o_ps, 4 * n, cudaMemcpyHostToDevice, s));
@@ -2409,6 +2407,7 @@ int visfs_ba_window_insert_frame(visfs_ba_window *w, int64_t frame_id, const dou
         CK(cudaMemcpyAsync(w->d_ob_kind.as<uint8_t>() + at, sg + o_kind, n, cudaMemcpyHostToDevice, s));
     }
     CK(cudaEventRecord(w->stage_done, s));
+    w->n_pool += n_obs;
     w->h2d_total += 56 + (int64_t)(21 * n);
     return VISFS_BA_OK;
 }
@@ -2420,13 +2419,8 @@ int visfs_ba_window_remove_frame(visfs_ba_window *w, int64_t frame_id) {
     if (it == w->frame_slot.end()) return win_fail(w, VISFS_BA_ERR_INVALID, "remove_frame: no such frame");
     CK(cudaSetDevice(h->device));
     const int fslot = it->second;
-    for (int i : w->frame_obs[(size_t)fslot]) {
-        auto &o = w->pool[(size_t)i];
-        if (!o.dead) { o.dead = 1; w->ob_index.erase(visfs_ba_window::okey(o.pslot, o.fslot)); }
-    }
-    w->frame_obs[(size_t)fslot].clear();
-    if (!w->pool.empty())
-        wn::k_win_kill_frame<<<std::max(1, std::min(((int)w->pool.size() + 255) / 256, 256)), 256, 0, h->stream>>>(w->d_ob_frame.as<int>(), w->d_ob_dead.as<uint8_t>(), (int)w->pool.size(), fslot);
+    if (w->n_pool > 0)
+        wn::k_win_kill_frame<<<std::max(1, std::min((w->n_pool + 255) / 256, 256)), 256, 0, h->stream>>>(w->d_ob_frame.as<int>(), w->d_ob_dead.as<uint8_t>(), w->n_pool, fslot);
     CK(cudaGetLastError());
     w->frame_slot.erase(it);
     w->frame_id_of_slot[(size_t)fslot] = -1;
@@ -2434,17 +2428,26 @@ int visfs_ba_window_remove_frame(visfs_ba_window *w, int64_t frame_id) {
     return VISFS_BA_OK;
 }
 
-static int win_kill(visfs_ba_window *w, const std::vector<int> &list) {
+// (feature slot [, frame slot]) pairs -> tombstones in the pool: masks set, one pass over the pool, masks cleared (ba_window.cuh)
+static int win_kill(visfs_ba_window *w, const std::vector<int> &pslots, const std::vector<int> *fslots) {
     visfs_ba_handle *h = w->h;
-    if (list.empty()) return VISFS_BA_OK;
-    char *sg = w->stage(4 * list.size());
+    const size_t n = pslots.size();
+    if (n == 0 || w->n_pool == 0) return VISFS_BA_OK;
+    const size_t bytes = 4 * n * (fslots ? 2 : 1);
+    char *sg = w->stage(bytes);
     if (!sg) return win_fail(w, VISFS_BA_ERR_CUDA, "staging allocation failed");
-    memcpy(sg, list.data(), 4 * list.size());
-    CK(cudaMemcpyAsync(w->d_list.p, sg, 4 * list.size(), cudaMemcpyHostToDevice, h->stream));
-    wn::k_win_kill_list<<<std::max(1, std::min(((int)list.size() + 255) / 256, 64)), 256, 0, h->stream>>>(w->d_ob_dead.as<uint8_t>(), w->d_list.as<int>(), (int)list.size());
+    memcpy(sg, pslots.data(), 4 * n);
+    if (fslots) memcpy(sg + 4 * n, fslots->data(), 4 * n);
+    cudaStream_t s = h->stream;
+    CK(cudaMemcpyAsync(w->d_list.p, sg, bytes, cudaMemcpyHostToDevice, s));
+    const int *dp = w->d_list.as<int>(), *df = fslots ? dp + n : nullptr;
+    const int gl = std::max(1, std::min(((int)n + 255) / 256, 64)), gp = std::max(1, std::min((w->n_pool + 255) / 256, 256));
+    wn::k_win_mask_set<<<gl, 256, 0, s>>>(w->d_mask.as<unsigned>(), dp, df, (int)n);
+    wn::k_win_mask_kill<<<gp, 256, 0, s>>>(w->d_mask.as<unsigned>(), w->d_ob_point.as<int>(), w->d_ob_frame.as<int>(), w->d_ob_dead.as<uint8_t>(), w->n_pool);
+    wn::k_win_mask_clear<<<gl, 256, 0, s>>>(w->d_mask.as<unsigned>(), dp, (int)n);
     CK(cudaGetLastError());
-    CK(cudaEventRecord(w->stage_done, h->stream));
-    w->h2d_total += (int64_t)(4 * list.size());
+    CK(cudaEventRecord(w->stage_done, s));
+    w->h2d_total += (int64_t)bytes;
     return VISFS_BA_OK;
 }
 
@@ -2452,41 +2455,39 @@ int visfs_ba_window_remove_points(visfs_ba_window *w, int32_t n, const int64_t *
     if (!w) return VISFS_BA_ERR_INVALID;
     if (n < 0 || (n > 0 && !point_id)) return win_fail(w, VISFS_BA_ERR_INVALID, "remove_points: null array");
     if (cudaSetDevice(w->h->device) != cudaSuccess) return VISFS_BA_ERR_CUDA;
+    for (int k = 0; k < n; ++k)
+        if (w->point_slot.find(point_id[k]) == w->point_slot.end()) return win_fail(w, VISFS_BA_ERR_INVALID, "remove_points: no such feature");
     std::vector<int> list;
+    list.reserve((size_t)n);
     for (int k = 0; k < n; ++k) {
         auto it = w->point_slot.find(point_id[k]);
-        if (it == w->point_slot.end()) return win_fail(w, VISFS_BA_ERR_INVALID, "remove_points: no such feature");
+        if (it == w->point_slot.end()) continue;   // listed twice
         const int slot = it->second;
-        for (int i : w->point_obs[(size_t)slot]) {
-            auto &o = w->pool[(size_t)i];
-            if (!o.dead) { o.dead = 1; w->ob_index.erase(visfs_ba_window::okey(o.pslot, o.fslot)); list.push_back(i); }
-        }
-        w->point_obs[(size_t)slot].clear();
+        list.push_back(slot);
         w->point_order.erase(point_id[k]);
         w->point_slot.erase(it);
         w->point_id_of_slot[(size_t)slot] = -1;
-        w->free_points.push_back(slot);
         w->order_dirty = true;
     }
-    return win_kill(w, list);
+    // the tombstones are set before the slots can be handed out again (same stream)
+    const int st = win_kill(w, list, nullptr);
+    for (int slot : list) w->free_points.push_back(slot);
+    return st;
 }
 
 int visfs_ba_window_remove_observations(visfs_ba_window *w, int32_t n, const int64_t *point_id, const int64_t *frame_id) {
     if (!w) return VISFS_BA_ERR_INVALID;
     if (n < 0 || (n > 0 && (!point_id || !frame_id))) return win_fail(w, VISFS_BA_ERR_INVALID, "remove_observations: null arrays");
     if (cudaSetDevice(w->h->device) != cudaSuccess) return VISFS_BA_ERR_CUDA;
-    std::vector<int> list;
+    std::vector<int> ps, fs;
+    ps.reserve((size_t)n); fs.reserve((size_t)n);
     for (int k = 0; k < n; ++k) {
         auto ip = w->point_slot.find(point_id[k]);
         auto jf = w->frame_slot.find(frame_id[k]);
         if (ip == w->point_slot.end() || jf == w->frame_slot.end()) continue;      // LocalMap.cpp:219-224 logs and goes on
-        auto io = w->ob_index.find(visfs_ba_window::okey(ip->second, jf->second));
-        if (io == w->ob_index.end()) continue;
-        w->pool[(size_t)io->second].dead = 1;
-        list.push_back(io->second);
-        w->ob_index.erase(io);
+        ps.push_back(ip->second); fs.push_back(jf->second);
     }
-    return win_kill(w, list);
+    return win_kill(w, ps, &fs);
 }
 
 int visfs_ba_window_set_poses(visfs_ba_window *w, int32_t n, const int64_t *frame_id, const double *pose_tq) {
@@ -2546,7 +2547,11 @@ int visfs_ba_window_solve(visfs_ba_window *w, int64_t root_frame_id, visfs_ba_wi
     visfs_ba_handle *h = w->h;
     CK(cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
-    const int P = (int)w->frame_slot.size(), n_pool = (int)w->pool.size(), n_order = (int)w->point_order.size();
+    const bool wtrace = getenv("VISFS_BA_WIN_TRACE") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](std::chrono::steady_clock::time_point a2, std::chrono::steady_clock::time_point b2) { return std::chrono::duration<double, std::milli>(b2 - a2).count(); };
+    const auto tw0 = now();
+    const int P = (int)w->frame_slot.size(), n_pool = w->n_pool, n_order = (int)w->point_order.size();
     const int maxF = w->cfg.max_frames;
     int64_t h2d = 0;
     // ---- the one table a solve sends: frame slot -> pose index (ascending signature id), pose index -> slot
@@ -2618,6 +2623,7 @@ int visfs_ba_window_solve(visfs_ba_window *w, int64_t root_frame_id, visfs_ba_wi
         CK(cudaStreamSynchronize(s));
     }
     w->order_dirty = false;
+    const auto tw1 = now();
     // ---- the window as one problem whose arrays are already on the device
     visfs_ba_problem pb{};
     pb.n_poses = P; pb.n_points = L; pb.n_edges = E;
@@ -2642,8 +2648,10 @@ int visfs_ba_window_solve(visfs_ba_window *w, int64_t root_frame_id, visfs_ba_wi
     int st = upload(h, 1, &pb, &dev);
     if (st) return st;
     h2d += h->h2d_bytes;
+    const auto tw2 = now();
     st = run_resident(h);
     if (st) return st;
+    const auto tw3 = now();
     // ---- results: poses back, write-back into the resident state, outlier list
     const int cap = std::max(0, std::min(res->outlier_capacity, w->cfg.max_observations));
     const int items = std::max(std::max(P * 7, L), E);
@@ -2679,6 +2687,7 @@ int visfs_ba_window_solve(visfs_ba_window *w, int64_t root_frame_id, visfs_ba_wi
     res->h2d_bytes = h2d;
     res->d2h_bytes = 56 * (int64_t)P + 8 * (int64_t)n_copy + 20 + (int64_t)sizeof(LMState);
     w->h2d_total += h2d;
+    if (wtrace) fprintf(stderr, "[visfs_ba] window solve: prep %.3f upload %.3f run %.3f finish %.3f ms\n", ms(tw0, tw1), ms(tw1, tw2), ms(tw2, tw3), ms(tw3, now()));
     return ls.status;
 }
 
