@@ -11,7 +11,10 @@ ws = synth.config_c3_windows(n)
 ba = capi.BundleAdjuster(0)
 packed = ba.prepare_batch(ws, pinned=True, float_obs=True)
 for rep in range(2):
-    for ramp, flat, g in ((1.22, 99, 16), (1.22, 12, 16), (1.22, 10, 20), (1.22, 10, 24), (1.3, 8, 20), (1.15, 99, 16), (1.22, 99, 20)):
+    sweep = ((1.22, 99, 16), (1.22, 12, 16), (1.22, 10, 20), (1.22, 10, 24), (1.3, 8, 20), (1.15, 99, 16), (1.22, 99, 20))
+    if len(sys.argv) > 2 and sys.argv[2] == "big":   # large batches: more, flatter groups
+        sweep = ((1.22, 10, 20), (1.22, 14, 20), (1.22, 20, 20), (1.3, 10, 20), (1.15, 10, 20), (1.22, 12, 24), (1.22, 9, 18), (1.22, 11, 22), (1.4, 10, 20))
+    for ramp, flat, g in sweep:
         os.environ["VISFS_BA_RAMP"] = str(ramp)
         os.environ["VISFS_BA_RAMP_FLAT"] = str(flat)
         os.environ["VISFS_BA_GROUPS"] = str(g)

@@ -437,37 +437,52 @@ __global__ void __launch_bounds__(kThreadsD) k_dense_chol(Batch B, DenseMat M) {
     if (M.prof && c_id == 0 && tid == 0) M.prof[2530] = gtime() - tb;
 }
 
-// the epilogue shared with the other direct solvers: solution checks, pose step, trial poses, pose part of computeScale
+// the epilogue shared with the other direct solvers: solution checks, pose step, trial poses, pose part of computeScale.
+// One thread-block cluster of kBackCluster CTAs (a single CTA took 41 us for C4's 2 000 poses, on every rank, every trial): every
+// CTA takes a slice, the two reductions go through distributed shared memory and are added in rank order by every CTA, so all of
+// them reach the same verdict and the sums do not depend on the schedule.
+constexpr int kBackCluster = 8;
 __global__ void __launch_bounds__(kBackThreads) k_dense_back(Batch B, DenseMat M) {
+    namespace cg = cooperative_groups;
     __shared__ double s_red[32];
+    __shared__ double s_part[2];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int nc = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
     const WinDesc &wd = B.win[0];
     LMState &st = B.st[0];
-    if (st.done) return;
-    const int tid = threadIdx.x;
+    if (st.done) return;   // uniform over the cluster
+    const int tid = threadIdx.x, gt = rank * kBackThreads + tid, stride = nc * kBackThreads;
     const int n = M.n;
     const double *__restrict__ x = M.x;
     const double lambda = (wd.trust == 0) ? (B.dbg_lambda >= 0.0 ? B.dbg_lambda : st.lambda) : 0.0;
     if (n == 0) {
-        if (tid == 0) { st.ok = 1; st.scale_p = 0.0; }
+        if (gt == 0) { st.ok = 1; st.scale_p = 0.0; }
         return;
     }
     const double *__restrict__ braw = B.red + B.red_bp_off;
-    double bad = 0.0;
-    for (int i = tid; i < n; i += kBackThreads) if (!isfinite(x[i])) bad = 1.0;
-    const double anybad = block_sum(bad, s_red);
-    const bool ok = (*M.flag == 0) && (anybad == 0.0);
-    __syncthreads();
-    double sc = 0.0;
-    for (int i = tid; i < n; i += kBackThreads) {
-        const double xi = ok ? x[i] : 0.0;
-        B.xp[i] = xi;
-        sc += xi * (lambda * xi + braw[i]);
+    double bad = 0.0, sc = 0.0;
+    for (int i = gt; i < n; i += stride) {
+        const double xi = x[i];
+        if (!isfinite(xi)) bad = 1.0;
+        sc += xi * (lambda * xi + braw[i]);   // (only used when every entry is finite and the factorisation succeeded)
     }
-    const double scale = block_sum(sc, s_red);
+    const double my_bad = block_sum(bad, s_red);
+    __syncthreads();
+    const double my_sc = block_sum(sc, s_red);
+    if (tid == 0) { s_part[0] = my_bad; s_part[1] = my_sc; }
+    cluster.sync();
+    double anybad = 0.0, scale = 0.0;
+    for (int r = 0; r < nc; ++r) {
+        const double *p = cluster.map_shared_rank(s_part, r);
+        anybad += p[0]; scale += p[1];
+    }
+    cluster.sync();   // nobody leaves while its shared memory is still being read
+    const bool ok = (*M.flag == 0) && (anybad == 0.0);
+    for (int i = gt; i < n; i += stride) B.xp[i] = ok ? x[i] : 0.0;
     const int cur = st.cur;
     const double *src = B.pose + (size_t)cur * B.tot_pose * kPoseStride;
     double *dst = B.pose + (size_t)(1 - cur) * B.tot_pose * kPoseStride;
-    for (int p = tid; p < wd.n_pose; p += kBackThreads) {
+    for (int p = gt; p < wd.n_pose; p += stride) {
         const int hi = B.pose_hidx[p];
         if (hi >= 0) {
             double dlt[6];
@@ -475,7 +490,7 @@ __global__ void __launch_bounds__(kBackThreads) k_dense_back(Batch B, DenseMat M
             pose_oplus(src + (size_t)p * kPoseStride, dlt, dst + (size_t)p * kPoseStride);
         }
     }
-    if (tid == 0) { st.ok = ok ? 1 : 0; st.scale_p = scale; }
+    if (gt == 0) { st.ok = ok ? 1 : 0; st.scale_p = ok ? scale : 0.0; }
 }
 
 }  // namespace dn

@@ -1321,6 +1321,20 @@ int enqueue_build_large(visfs_ba_handle *h) {
         }                                                                                           \
     } while (0)
 
+// dn::k_dense_back as one cluster of dn::kBackCluster CTAs
+int launch_dense_back(visfs_ba_handle *h, const dn::DenseMat &M) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)dn::kBackCluster);
+    cfg.blockDim = dim3(dn::kBackThreads);
+    cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)dn::kBackCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    CK(cudaLaunchKernelEx(&cfg, dn::k_dense_back, h->batch, M));
+    return VISFS_BA_OK;
+}
+
 int enqueue_rest_large(visfs_ba_handle *h) {
     int st;
     DBG_SYNC("before solve (build / allreduce)");
@@ -1339,7 +1353,7 @@ int enqueue_rest_large(visfs_ba_handle *h) {
         dn::k_dense_fill<<<std::max(1, std::min(M.n / 6, 4 * h->sm_count)), 256, 0, h->stream>>>(h->batch, M);
         void *args[] = {(void *)&h->batch, (void *)&h->dense};
         CK(cudaLaunchCooperativeKernel((const void *)dn::k_dense_chol, dim3((unsigned)h->dense_grid), dim3(dn::kThreadsD), args, h->dense_smem, h->stream));
-        dn::k_dense_back<<<1, dn::kBackThreads, 0, h->stream>>>(h->batch, M);
+        { const int stb = launch_dense_back(h, M); if (stb) return stb; }
         h->launches += 2;
     } else if (h->use_mf) {
         // long banded system: nested-dissection multifrontal Cholesky, one launch per tree level (ba_mf.cuh)
@@ -1352,7 +1366,7 @@ int enqueue_rest_large(visfs_ba_handle *h) {
             mf::k_mf_back<<<h->mf_level_off[l + 1] - h->mf_level_off[l], dn::kThreadsD, smem_b, h->stream>>>(h->batch, h->mf_plan, h->mf_level_off[l]);
         dn::DenseMat M{};
         M.n = 6 * h->st_F_hint; M.x = h->mf_plan.x; M.flag = h->mf_plan.flag;
-        dn::k_dense_back<<<1, dn::kBackThreads, 0, h->stream>>>(h->batch, M);
+        { const int stb = launch_dense_back(h, M); if (stb) return stb; }
         h->launches += 2 * nl;
     } else if (h->use_front) {
         lg::k_solve_front<<<1, lg::kSolveThreadsL, sizeof(lg::FrontSmem), h->stream>>>(h->batch, h->front_plan);
