@@ -311,6 +311,7 @@ __device__ __forceinline__ void build_ws_body(const Batch &B, int cluster_size, 
                 double s = 0.0;
                 for (int e = sm.lmoff[l]; e < sm.lmoff[l + 1]; ++e) s += S.Yn[e * 18 + q];
                 S.lm[l * 12 + q] = s;
+                if (!BAND && B.lm_sum) B.lm_sum[(size_t)(lt + l) * 9 + q] = s;   // k_update needs the same sums: it reads them instead of forming them again
             }
             if (kProdShare > 0) {
                 bar_sync(BAR_PROD, kEdgeThreads);

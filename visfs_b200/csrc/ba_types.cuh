@@ -86,6 +86,7 @@ struct Batch {
     unsigned *covis;                 // [tot_pose] row i: bit j set if S block (i,j), i<=j exists (small path)
     double *part;                    // per-chunk partial sums
     double *part2;                   // [n_chunks][2] chi2 / scale partials of the update kernel
+    double *lm_sum;                  // [tot_point][9] H_ll (6) b_l (3) of the current trial, left by k_build_ws for k_update (null: k_update forms them itself)
     double *xp;                      // [tot_pose][6] pose step per hessian index (window-local)
     int *n_running;                  // windows still running in the current pass
     int *ctl_count;                  // [n_win] CTAs of k_update that have finished this trial: the last one runs the LM controller

@@ -121,6 +121,18 @@ __device__ __forceinline__ void upd_edge_terms(const double *ps, double px, doub
     hl[11] = fma(J[2], v0, fma(J[5], v1, J[8] * v2));
 }
 
+// only the last 3 of those terms (W^T x_p): H_ll and b_l come from k_build_ws's per-landmark sums (Batch::lm_sum)
+__device__ __forceinline__ void upd_edge_wx(const double *ps, double px, double py, double pz, double ou, double ov, double our,
+                                            bool mono, const Intr &K, const double *xp, double *hw) {
+    double r[3], J[9], v[3], w;
+    edge_linearize_jx(ps, px, py, pz, ou, ov, our, mono, K, xp, r, J, v, w);
+    const double wo = w * K.inv_pv;
+    const double v0 = wo * v[0], v1 = wo * v[1], v2 = wo * v[2];   // W^T x_p = wo * Jl^T (Jp x_p)
+    hw[0] = fma(J[0], v0, fma(J[3], v1, J[6] * v2));
+    hw[1] = fma(J[1], v0, fma(J[4], v1, J[7] * v2));
+    hw[2] = fma(J[2], v0, fma(J[5], v1, J[8] * v2));
+}
+
 // x_l = (H_ll + lambda I)^-1 (b_l - sum W^T x_p) from the 12 landmark sums; returns the landmark's part of computeScale()
 __device__ __forceinline__ double upd_point_step(const double *ls, double lambda, double *xl) {
     const double A[6] = {ls[0] + lambda, ls[1], ls[2], ls[3] + lambda, ls[4], ls[5] + lambda};
@@ -190,6 +202,39 @@ __global__ void __launch_bounds__(kUpdThreads, 2) k_update(Batch B) {
                          pz = __shfl_sync(0xffffffffu, pt, 3 * tl + 2);
             bool act = false, mono = false, lmfree = false;
             int p = 0;
+            if (B.lm_sum) {
+                // H_ll / b_l of the tile's landmarks as k_build_ws summed them (9 per landmark, contiguous: one coalesced load,
+                // issued with the other loads of the tile); only W^T x_p is formed per edge and summed per landmark here
+                const double *gs = B.lm_sum + 9 * (size_t)T.lt;
+                double s0 = (lane < 9 * T.ntl) ? gs[lane] : 0.0, s1 = (lane + 32 < 9 * T.ntl) ? gs[lane + 32] : 0.0,
+                       s2 = (lane + 64 < 9 * T.ntl) ? gs[lane + 64] : 0.0;
+                double hw[3] = {0.0, 0.0, 0.0};
+                if (lane < T.ne) {
+                    p = pw & kPoseMask;
+                    mono = (pw & kMonoBit) != 0;
+                    lmfree = (lf & kInHessian) != 0;
+                    act = !(pw & kCulledBit) && !((lf & kFixed) && (sm.pflag[p] & kFixed));
+                    const int hi = sm.hidx[p];
+                    if (act && lmfree && hi >= 0) upd_edge_wx(sm.pose + p * kPoseSm, px, py, pz, ou, ov, our, mono, K, sm.xp + hi * 6, hw);
+                    W.H[lane * kHs] = hw[0]; W.H[lane * kHs + 1] = hw[1]; W.H[lane * kHs + 2] = hw[2];
+                }
+                {   // scatter the loaded sums: global entry g = 9 l + q  ->  W.lm[12 l + q]
+                    int g = lane;
+                    if (g < 9 * T.ntl) W.lm[(g / 9) * 12 + g % 9] = s0;
+                    g += 32;
+                    if (g < 9 * T.ntl) W.lm[(g / 9) * 12 + g % 9] = s1;
+                    g += 32;
+                    if (g < 9 * T.ntl) W.lm[(g / 9) * 12 + g % 9] = s2;
+                }
+                __syncwarp();
+                if (lane < T.ntl * 3) {
+                    const int l = lane / 3, q = lane - l * 3;
+                    double s = 0.0;
+                    for (int e = W.lmoff[l]; e < W.lmoff[l + 1]; ++e) s += W.H[e * kHs + q];
+                    W.lm[l * 12 + 9 + q] = s;
+                }
+                __syncwarp();
+            } else {
             double hl[12];
 #pragma unroll
             for (int q = 0; q < 12; ++q) hl[q] = 0.0;
@@ -213,6 +258,7 @@ __global__ void __launch_bounds__(kUpdThreads, 2) k_update(Batch B) {
                 W.lm[task] = s;
             }
             __syncwarp();
+            }
             if (lane < T.ne) {
                 double np0 = px, np1 = py, np2 = pz;
                 if (lmfree) {

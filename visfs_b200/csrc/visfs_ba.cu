@@ -103,7 +103,7 @@ struct visfs_ba_handle {
     // device memory
     DevBuf d_st, d_pose, d_point, d_pose_flags, d_lm_flags, d_pose_hidx, d_pose_active, d_point_hidx,
         d_lm_edge_off, d_obs_u, d_obs_v, d_obs_r, d_edge_pose, d_edge_point, d_edge_orig, d_covis, d_part, d_part2, d_xp,
-        d_n_running, d_ctl_count, d_tiles, d_tile_off, d_tile_cnt, d_wtiles, d_wtile_off;
+        d_n_running, d_ctl_count, d_lm_sum, d_tiles, d_tile_off, d_tile_cnt, d_wtiles, d_wtile_off;
     // the caller's arrays, window and chunk descriptors: ONE device buffer with the layout of the pinned staging buffer,
     // filled by ONE H2D copy (a single-window call is latency-bound: ten small copies cost ~50 us)
     DevBuf d_in;
@@ -281,6 +281,7 @@ Batch make_batch(visfs_ba_handle *h) {
     b.edge_pose = h->d_edge_pose.as<int>(); b.edge_point = h->d_edge_point.as<int>();
     b.edge_orig = h->sorted ? nullptr : h->d_edge_orig.as<int>();
     b.covis = h->d_covis.as<unsigned>(); b.part = h->d_part.as<double>(); b.part2 = h->d_part2.as<double>();
+    b.lm_sum = (h->use_ws && !h->use_ds && !getenv("VISFS_BA_NO_LMSUM")) ? h->d_lm_sum.as<double>() : nullptr;
     b.xp = h->d_xp.as<double>(); b.n_running = h->d_n_running.as<int>(); b.ctl_count = h->d_ctl_count.as<int>();
     b.dbg = nullptr; b.dbg_lambda = -1.0;
     b.tot_link = h->tot_link;
@@ -443,6 +444,7 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs, const DevIn
         CK(h->d_info.reserve(sizeof(long long) * 4)); CK(h->d_cnt.reserve(sizeof(int) * 4));
     }
     CK(h->d_part2.reserve(sizeof(double) * 2 * std::max(std::max(h->n_chunks, 1), std::max(h->grid_build_l, h->grid_update_l))));
+    if (h->use_ws) CK(h->d_lm_sum.reserve(sizeof(double) * 9 * L));
     CK(h->d_xp.reserve(sizeof(double) * 6 * P)); CK(h->d_n_running.reserve(sizeof(int) * 4)); CK(h->d_ctl_count.reserve(sizeof(int) * (size_t)n));
     const size_t max_tiles = 2 * E / (ds::kEdges + 1) + L / ds::kLm + 2 * (size_t)h->n_chunks + 8;   // (bound for either tile shape)
     CK(h->d_tiles.reserve(sizeof(Tile) * max_tiles));
