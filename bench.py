@@ -282,6 +282,9 @@ def resident_window_numbers(ba, quick, size="c0", _warm=True):
     np.minimum.at(first_seen, seq["edge_point"], seq["edge_pose"])
     win = capi.ResidentWindow(ba, views + 1, max_pts, max_obs, fx=seq["fx"], fy=seq["fy"], cx=seq["cx"], cy=seq["cy"], bf=seq["bf"],
                               pixel_variance=seq["pixel_variance"], huber_delta=seq["huber_delta"], iterations=seq["iterations"])
+    # the full-call arm has a handle of its own, like the resident map has (Optimizer and ResidentLocalMap each create theirs):
+    # the two arms do not take turns on one set of device buffers
+    ba_full = capi.BundleAdjuster(device=ba.device, profile_kernels=False)
     # every array a frame hands over is converted BEFORE the clock starts (the harness' numpy work is not the product's)
     import ctypes as C
     lib, W = ba.lib, win.w
@@ -338,13 +341,14 @@ def resident_window_numbers(ba, quick, size="c0", _warm=True):
                  edge_point=remap[seq["edge_point"][keep]].astype(np.int32), edge_kind=seq["edge_kind"][keep])
         for k in ("link_from", "link_to", "link_tq", "n_links"):
             w.pop(k, None)
-        packed = ba.prepare_batch([w], pinned=True, float_obs=True)
-        ba.solve_packed(packed)
+        packed = ba_full.prepare_batch([w], pinned=True, float_obs=True)
+        ba_full.solve_packed(packed)
         t1 = time.perf_counter()
-        ba.solve_packed(packed)
+        ba_full.solve_packed(packed)
         t_full += time.perf_counter() - t1
-        h2d_full += int(ba.timing()["h2d_bytes"])
+        h2d_full += int(ba_full.timing()["h2d_bytes"])
     win.close()
+    ba_full.close()
     n = max(solves, 1)
     return {"workload": f"{n_frames}-frame sequence through a {views}-frame local map, ~{edges // n} edges per solve, root = newest - 1",
             "solves": solves, "per_frame_ms_resident": 1e3 * t_res / n, "per_frame_ms_full_call": 1e3 * t_full / n,

@@ -316,6 +316,7 @@ class BundleAdjuster:
             msg = self.lib.visfs_ba_last_error(None)
             raise BAError(f"visfs_ba_create failed ({st}): {msg.decode() if msg else ''}")
         self.h = h
+        self.device = int(device)
         self._resident = None
 
     def close(self):
