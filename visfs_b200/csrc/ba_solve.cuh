@@ -38,7 +38,10 @@ __global__ void k_reduce_parts(Batch B) {
     }
 }
 
-__global__ void __launch_bounds__(kSolveThreads) k_solve(Batch B) {
+// k_solve: all registers to one CTA (single windows: latency); k_solve2: 128 registers, two CTAs per SM (batches: the kernel is a
+// chain of dependent steps per window, a second resident window hides them; C3 x 1024 step 42.85 -> 42.13 ms, but one C1 window
+// 0.717 -> 0.743 ms, hence the choice by batch size at launch)
+__device__ __forceinline__ void solve_body(const Batch &B) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *S = reinterpret_cast<double *>(smem_raw);
     const int w = blockIdx.x;
@@ -401,5 +404,8 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(Batch B) {
         for (int k = 0; k < 6; ++k) st.t_solve[k] = tclk[k] - tclk[0];
     }
 }
+
+__global__ void __launch_bounds__(kSolveThreads) k_solve(Batch B) { solve_body(B); }
+__global__ void __launch_bounds__(kSolveThreads, 2) k_solve2(Batch B) { solve_body(B); }
 
 }  // namespace visfs

@@ -706,7 +706,8 @@ int enqueue_body(visfs_ba_handle *h) {
         k_reduce_parts<<<dim3((unsigned)h->reduce_grid, (unsigned)h->n_win), 256, 0, h->stream>>>(h->batch);
         h->launches += 1;
     }
-    k_solve<<<h->n_win, kSolveThreads, h->solve_smem, h->stream>>>(h->batch);
+    if (h->n_win >= 2 * h->sm_count) k_solve2<<<h->n_win, kSolveThreads, h->solve_smem, h->stream>>>(h->batch);
+    else k_solve<<<h->n_win, kSolveThreads, h->solve_smem, h->stream>>>(h->batch);
     LAUNCH_CHECK("k_solve");
     ev_end(h, ev);
     ev = ev_begin(h, EV_UPDATE);
@@ -1798,6 +1799,7 @@ int visfs_ba_create(const visfs_ba_config *cfg, visfs_ba_handle **out) {
     cudaFuncSetAttribute(lg::k_build_large<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(lg::BuildSmemL));
     cudaFuncSetAttribute(lg::k_build_large<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(lg::BuildSmemL));
     e = cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_solve2, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) {
         g_create_error = std::string("kernel image not usable on this device (built for sm_100a): ") + cudaGetErrorString(e);
         cudaStreamDestroy(h->stream);
