@@ -709,17 +709,41 @@ __global__ void k_cull(Batch B) {
     const double *gpose = B.pose + ((size_t)cur * B.tot_pose + wd.pose_off) * kPoseStride;
     const double *gpoint = B.point + ((size_t)cur * B.tot_point + wd.point_off) * 3;
     int cnt = 0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < wd.n_edge; i += gridDim.x * blockDim.x) {
-        const int e = wd.edge_off + i;
-        const int pw = B.edge_pose[e];
-        const int p = pw & kPoseMask, l = B.edge_point[e];
-        if (pw & kCulledBit) continue;
-        if ((B.lm_flags[wd.point_off + l] & kFixed) && (B.pose_flags[wd.pose_off + p] & kFixed)) continue;  // never active
-        double r0, r1, r2;
-        edge_residual(gpose + p * kPoseStride, gpoint[3 * l], gpoint[3 * l + 1], gpoint[3 * l + 2], B.obs_u[e], B.obs_v[e],
-                      B.obs_r[e], (pw & kMonoBit) != 0, K, r0, r1, r2);
-        const double chi2 = (r0 * r0 + r1 * r1 + r2 * r2) * K.inv_pv;
-        if (chi2 > wd.delta) { B.edge_pose[e] = pw | kCulledBit; ++cnt; }
+    // four edges per thread and step: the loads of one level (edge words -> flags / point / pose / observation) are issued for all
+    // four before any is used — with one edge per thread the kernel is a chain of three dependent memory round trips per CTA
+    constexpr int U = 4;
+    const int stride = gridDim.x * blockDim.x;
+    for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < wd.n_edge; i0 += U * stride) {
+        int pw[U], l[U];
+        bool live[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * stride;
+            live[u] = i < wd.n_edge;
+            pw[u] = live[u] ? B.edge_pose[wd.edge_off + i] : kCulledBit;
+            l[u] = live[u] ? B.edge_point[wd.edge_off + i] : 0;
+        }
+        double px[U], py[U], pz[U], ou[U], ov[U], our[U];
+        uint8_t lf[U], pf[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            live[u] = live[u] && !(pw[u] & kCulledBit);
+            const int e = wd.edge_off + i0 + u * stride;
+            if (live[u]) {
+                lf[u] = B.lm_flags[wd.point_off + l[u]]; pf[u] = B.pose_flags[wd.pose_off + (pw[u] & kPoseMask)];
+                px[u] = gpoint[3 * l[u]]; py[u] = gpoint[3 * l[u] + 1]; pz[u] = gpoint[3 * l[u] + 2];
+                ou[u] = B.obs_u[e]; ov[u] = B.obs_v[e]; our[u] = B.obs_r[e];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (!live[u]) continue;
+            if ((lf[u] & kFixed) && (pf[u] & kFixed)) continue;  // never active
+            double r0, r1, r2;
+            edge_residual(gpose + (pw[u] & kPoseMask) * kPoseStride, px[u], py[u], pz[u], ou[u], ov[u], our[u], (pw[u] & kMonoBit) != 0, K, r0, r1, r2);
+            const double chi2 = (r0 * r0 + r1 * r1 + r2 * r2) * K.inv_pv;
+            if (chi2 > wd.delta) { B.edge_pose[wd.edge_off + i0 + u * stride] = pw[u] | kCulledBit; ++cnt; }
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);

@@ -1472,7 +1472,7 @@ int run_pass(visfs_ba_handle *h, int pass) {
     }
     ev = ev_begin(h, EV_OTHER);
     k_end_pass<<<gw, 128, 0, s>>>(B, pass);
-    if (pass == 0 && h->tot_edge > 0) k_cull<<<dim3((unsigned)h->grid_edge_x, (unsigned)h->n_win), 256, 0, s>>>(B);
+    if (pass == 0 && h->tot_edge > 0) k_cull<<<dim3((unsigned)((h->grid_edge_x + 3) / 4), (unsigned)h->n_win), 256, 0, s>>>(B);   // (four edges per thread)
     ev_end(h, ev);
     h->launches += (pass == 0 && h->tot_edge > 0) ? 2 : 1;
     CK(cudaGetLastError());
