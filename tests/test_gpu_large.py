@@ -168,10 +168,19 @@ def test_small_window_through_large_path(ba, monkeypatch):
     small = ba.solve(w)
     monkeypatch.setenv("VISFS_BA_FORCE_LARGE", "1")
     big = ba.solve(w)
+    # ... and through the band chunks of the large path: every landmark starts at the same frame, so the whole map is ONE chunk
+    # and every skyline block has exactly one source in the gather list
+    monkeypatch.setenv("VISFS_BA_BAND_FORCE", "1")
+    band = ba.solve(w)
+    got_sys, ref_sys = ba.debug_trial(w, 0.8), O.reduced_system(w, 0.8)
+    monkeypatch.delenv("VISFS_BA_BAND_FORCE")
     monkeypatch.delenv("VISFS_BA_FORCE_LARGE")
     ref = O.solve(w)
     check_solution(small, ref, "small path")
     check_solution(big, ref, "large path")
+    check_solution(band, ref, "large path, one band chunk")
+    rel_close(got_sys["S"], ref_sys["S"], 1e-10, "one band chunk: reduced camera system")
+    rel_close(got_sys["b_s"], ref_sys["b_s"], 1e-10, "one band chunk: reduced rhs")
 
 
 def test_partitioned_single_rank_equals_unpartitioned(ba):

@@ -1124,12 +1124,12 @@ int prep_band(visfs_ba_handle *h) {
     if (!force && (n_in * 2 < L || (long long)n_in < 32LL * nc)) return VISFS_BA_OK;
     const int n_ent = n_pair + n_poseent;
     CK(h->d_bd_tiles.reserve(sizeof(Tile) * (size_t)n_tiles));
-    CK(h->d_bd_ent.reserve(sizeof(int) * (4 * (size_t)n_ent + 8)));
+    CK(h->d_bd_ent.reserve(sizeof(int) * (5 * (size_t)n_ent + 12)));
     CK(h->d_bd_val.reserve(sizeof(unsigned long long) * 2 * (size_t)n_ent));
     CK(h->d_bd_part.reserve(sizeof(double) * (size_t)nc * ws::kBandPartStride));
     CK(h->d_bd_part2.reserve(sizeof(double) * 2 * (size_t)nc));
-    int *key = h->d_bd_ent.as<int>(), *key2 = key + n_ent, *flag = key2 + n_ent, *sid = flag + n_ent + 1;
-    // (flag / sid have n_ent + 1 entries; seg_start reuses the unsorted key array afterwards)
+    int *key = h->d_bd_ent.as<int>(), *key2 = key + n_ent, *flag = key2 + n_ent, *sid = flag + n_ent + 1, *seg_start = sid + n_ent + 1;
+    // (flag / sid / seg_start have n_ent + 1 entries: every key may be a segment of its own)
     unsigned long long *val = h->d_bd_val.as<unsigned long long>(), *val2 = val + n_ent;
     bd::k_band_fill_tiles<<<gc, 128, 0, s>>>(chunk, nc, sorted_off, tile_off, h->d_bd_tiles.as<Tile>());
     bd::k_band_entries<<<nc, 128, 0, s>>>(B, chunk, nc, chunk_pose, pair_off, n_pair, pose_off, key, val);
@@ -1146,7 +1146,6 @@ int prep_band(visfs_ba_handle *h) {
     CK(cudaStreamSynchronize(s));
     const int n_seg = hs[0];
     if (n_seg <= 0 || n_seg > n_ent) return VISFS_BA_OK;
-    int *seg_start = key;   // n_seg + 1 <= n_ent + 1 entries ... the unsorted keys are no longer needed
     CK(h->d_bd_scan.reserve(sizeof(int) * 6 * n1));   // (no-op: keeps the scan arrays alive for the pass)
     bd::k_band_seg_starts<<<ge, 256, 0, s>>>(flag, sid, n_ent, seg_start);
     CK(cudaGetLastError());
