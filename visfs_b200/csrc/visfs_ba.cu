@@ -1083,7 +1083,7 @@ int prep_band(visfs_ba_handle *h) {
     CK(cudaStreamSynchronize(s));
     const int nc = hs[0];
     h->launches += 6;
-    if (nc <= 0 || nc >= (1 << 22)) return VISFS_BA_OK;
+    if (nc <= 0 || nc >= (1 << 22) || (size_t)nc * ws::kBandPartStride * sizeof(double) > ((size_t)8 << 30)) return VISFS_BA_OK;   // (partials <= 8 GB)
     // per-chunk tables: [chunk (4 ints) | chunk_pose (19) | ntiles | tile_off | npair | pair_off | npose | pose_off] (nc + 1 each) | counts
     const size_t c1 = ((size_t)nc + 1 + 3) & ~(size_t)3;
     CK(h->d_bd_chunk.reserve(sizeof(int) * (c1 * (4 + ws::kBandPoses + 10) + 4)));
