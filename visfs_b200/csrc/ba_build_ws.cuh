@@ -54,6 +54,7 @@ struct Smem {
     double pacc[kMaxFreeWs * kHStride];
     int hidx[kMaxSmallPoses];
     int lmoff[kTileLm + 1];
+    short slot_pose[kTileEdges];               // regular chunks: hessian index of the pose of edge slot t (-1: fixed pose / no edge)
 };
 constexpr int kStageDoubles = (int)(sizeof(Stage) / sizeof(double));
 static_assert(sizeof(Smem) <= 232448, "k_build_ws: shared memory over the 227 KB a CTA may use");
@@ -161,6 +162,40 @@ __device__ __forceinline__ void stage_b_edge(Stage &S, int e, double lambda) {
     }
 }
 
+// Regular chunks (k_chunk_regular): edge slot e belongs to the same pose in every tile, so the per-pose sums need no slot table.
+// The producers ADD H_pp_e (21) and b_p_e (6) into the H row of the slot (it persists over the tiles of its stage) and leave this
+// tile's b_p_e in entries 21..26; stage B reads it there and adds g = b_p_e - W Dinv b_l into the consumer thread's registers.
+constexpr int kRegScratch = 5760;              // doubles of stage 0 the group partials may use; the g accumulators follow (192 x 6)
+constexpr int kRegMaxFree = 16;                // the CTA's partial system must stay inside the W / Yn part of stage 1: F <= 16
+__device__ __forceinline__ void stage_b_edge_reg(Stage &S, int e, double lambda, double *gacc) {
+    const int meta = S.emeta[e];
+    if (meta < 0) return;
+    double *ys = S.Yn + e * 18;
+    const double *hs = S.H + e * kHStride;
+    if (meta & 64) {
+        const double *ls = S.lm + (meta & 63) * 12;
+        double A[6] = {ls[0] + lambda, ls[1], ls[2], ls[3] + lambda, ls[4], ls[5] + lambda};
+        const double bl[3] = {ls[6], ls[7], ls[8]};
+        double Di[6], db[3];
+        inv_sym3(A, Di);
+        sym3_mul(Di, bl, db);
+        const double *wsrc = S.W + e * 18;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            const double w0 = wsrc[a * 3], w1 = wsrc[a * 3 + 1], w2 = wsrc[a * 3 + 2];
+            ys[a * 3 + 0] = -fma(w0, Di[0], fma(w1, Di[1], w2 * Di[2]));
+            ys[a * 3 + 1] = -fma(w0, Di[1], fma(w1, Di[3], w2 * Di[4]));
+            ys[a * 3 + 2] = -fma(w0, Di[2], fma(w1, Di[4], w2 * Di[5]));
+            gacc[a] += hs[21 + a] - fma(w0, db[0], fma(w1, db[1], w2 * db[2]));
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 18; ++q) ys[q] = 0.0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) gacc[a] += hs[21 + a];
+    }
+}
+
 // Of every 4 edges of a tile, how many get their stage B from the producers (after one more producer barrier) instead of
 // the consumers.  Measured on C3 x 512 (ms per step): 0 -> 22.7, 1 -> 23.7, 2 -> 23.7; the old all-producer design 23.1.
 #ifndef VISFS_WS_PROD_SHARE
@@ -205,6 +240,9 @@ __device__ __forceinline__ void build_ws_body(const Batch &B, int cluster_size, 
         for (int i = tid; i < n_pose; i += kThreadsWs) sm.hidx[i] = B.pose_hidx[pose_off + i];
     }
     for (int i = tid; i < kMaxFreeWs * kHStride; i += kThreadsWs) sm.pacc[i] = 0.0;
+    const bool reg = !BAND && kProdShare == 0 && B.chunk_regular != nullptr && B.chunk_regular[blockIdx.x] != 0 && F <= kRegMaxFree;
+    if (reg)
+        for (int i = tid; i < kTileEdges * kHStride; i += kThreadsWs) { sm.st[0].H[i] = 0.0; sm.st[1].H[i] = 0.0; }
     __syncthreads();
 
     const int npairs = F * (F + 1) / 2;
@@ -212,7 +250,7 @@ __device__ __forceinline__ void build_ws_body(const Batch &B, int cluster_size, 
     if (npairs > 0) {
         G = kPairThreads / npairs;
         if (G > kTileLm) G = kTileLm;
-        const int cap = 1 + kStageDoubles / (npairs * 36);
+        const int cap = 1 + (reg ? kRegScratch : kStageDoubles) / (npairs * 36);
         if (G > cap) G = cap;
         if (G < 1) G = 1;
     }
@@ -290,16 +328,31 @@ __device__ __forceinline__ void build_ws_body(const Batch &B, int cluster_size, 
                         for (int q = 0; q < 18; ++q) ws[q] = 0.0;
                     }
                     const double wr0 = wo * lin.r[0], wr1 = wo * lin.r[1], wr2 = wo * lin.r[2];
+                    if (reg) {
 #pragma unroll
-                    for (int a = 0; a < 6; ++a) {
-                        hs[27 + a] = -fma(lin.Jp[a], wr0, fma(lin.Jp[6 + a], wr1, lin.Jp[12 + a] * wr2));
+                        for (int a = 0; a < 6; ++a) {
+                            const double bp = -fma(lin.Jp[a], wr0, fma(lin.Jp[6 + a], wr1, lin.Jp[12 + a] * wr2));
+                            hs[21 + a] = bp;
+                            hs[27 + a] += bp;
 #pragma unroll
-                        for (int c = a; c < 6; ++c)
-                            hs[hd_index(a, c)] = wo * fma(lin.Jp[a], lin.Jp[c], fma(lin.Jp[6 + a], lin.Jp[6 + c], lin.Jp[12 + a] * lin.Jp[12 + c]));
+                            for (int c = a; c < 6; ++c)
+                                hs[hd_index(a, c)] += wo * fma(lin.Jp[a], lin.Jp[c], fma(lin.Jp[6 + a], lin.Jp[6 + c], lin.Jp[12 + a] * lin.Jp[12 + c]));
+                        }
+                    } else {
+#pragma unroll
+                        for (int a = 0; a < 6; ++a) {
+                            hs[27 + a] = -fma(lin.Jp[a], wr0, fma(lin.Jp[6 + a], wr1, lin.Jp[12 + a] * wr2));
+#pragma unroll
+                            for (int c = a; c < 6; ++c)
+                                hs[hd_index(a, c)] = wo * fma(lin.Jp[a], lin.Jp[c], fma(lin.Jp[6 + a], lin.Jp[6 + c], lin.Jp[12 + a] * lin.Jp[12 + c]));
+                        }
                     }
                     slot_idx = tl * kMaxSmallPoses + hi;
                     meta = (short)(tl | (lmfree ? 64 : 0));
                 }
+                if (reg && t == 0) sm.slot_pose[tid] = (short)sm.hidx[p];   // structure, not activity: the same in every tile
+            } else if (reg && t == 0) {
+                sm.slot_pose[tid] = (short)-1;
             }
             S.emeta[tid] = meta;
             if (more) load_edge_l2_t<BAND>(B, wd, cpose, Tn, tid, gpoint, nxt);     // prefetch, level 2
@@ -328,6 +381,7 @@ __device__ __forceinline__ void build_ws_body(const Batch &B, int cluster_size, 
         double acc[36];   // lives only in the consumer branch: never competes with the producers' registers
 #pragma unroll
         for (int q = 0; q < 36; ++q) acc[q] = 0.0;
+        double gacc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};   // regular chunks: g of this thread's edge slot, summed over the tiles
         int pi = -1, pj = -1;
         if (grp < G && pt < npairs) {
             int i = 0, base = 0;
@@ -338,8 +392,10 @@ __device__ __forceinline__ void build_ws_body(const Batch &B, int cluster_size, 
             Stage &S = sm.st[t & 1];
             bar_sync(BAR_FULL + (t & 1), kThreadsWs);
             const int ntl = S.ntl;
-            if ((ctid & 3) >= kProdShare) stage_b_edge(S, ctid, lambda);
+            if (reg) stage_b_edge_reg(S, ctid, lambda, gacc);
+            else if ((ctid & 3) >= kProdShare) stage_b_edge(S, ctid, lambda);
             bar_sync(BAR_CONS, kPairThreads);
+            if (!reg)
             for (int task = ctid; task < F * kHStride; task += kPairThreads) {
                 const int i = task / kHStride, k = task - i * kHStride;
                 double s = 0.0;
@@ -372,6 +428,10 @@ __device__ __forceinline__ void build_ws_body(const Batch &B, int cluster_size, 
         }
         // groups -> one block per owner (consumer-only barriers; the stages are no longer written)
         bar_sync(BAR_CONS, kPairThreads);
+        if (reg) {
+#pragma unroll
+            for (int a = 0; a < 6; ++a) scratch[kRegScratch + ctid * 6 + a] = gacc[a];
+        }
         if (G > 1 && grp > 0 && grp < G && pt < npairs) {
             double *dst = scratch + ((size_t)(grp - 1) * npairs + pt) * 36;
 #pragma unroll
@@ -393,6 +453,20 @@ __device__ __forceinline__ void build_ws_body(const Batch &B, int cluster_size, 
     // ---- epilogue: one vector per CTA -> (cluster sum through DSMEM) -> global partial
     const int offd = npairs * 36;
     const int NP = offd + F * kHStride;
+    if (reg) {
+        // per-pose sums from the slot accumulators: both stages, slots in order; g from the consumers' registers
+        for (int task = tid; task < F * kHStride; task += kThreadsWs) {
+            const int i = task / kHStride, k = task - i * kHStride;
+            double s = 0.0;
+            if (k >= 21 && k < 27) {
+                for (int t = 0; t < kTileEdges; ++t) if (sm.slot_pose[t] == i) s += scratch[kRegScratch + t * 6 + (k - 21)];
+            } else {
+                for (int t = 0; t < kTileEdges; ++t) if (sm.slot_pose[t] == i) s += sm.st[0].H[t * kHStride + k] + sm.st[1].H[t * kHStride + k];
+            }
+            sm.pacc[task] = s;
+        }
+        __syncthreads();
+    }
     for (int task = tid; task < F * kHStride; task += kThreadsWs) vec[offd + task] = sm.pacc[task];
     __syncthreads();
     double *part = BAND ? bd.part + (size_t)cidx * kBandPartStride

@@ -521,6 +521,24 @@ __global__ void k_fill_tiles(Batch B, const int *tile_off, Tile *tiles, int max_
     walk_tiles<true>(B.lm_edge_off, B.chunks[c].lm0, B.chunks[c].lm1, tiles + tile_off[c], max_lm, max_edges);
 }
 
+// A chunk is REGULAR when all its landmarks are seen by the same poses in the same order (a fully covisible window: C1 / C3).
+// Then edge slot t of every tile of the chunk belongs to the same pose, and k_build_ws keeps the per-pose sums in per-slot
+// accumulators instead of summing them through the slot table tile by tile.  Structure only (pose indices): once per upload.
+__global__ void k_chunk_regular(Batch B, int *out) {
+    const Chunk ck = B.chunks[blockIdx.x];
+    const int *__restrict__ off = B.lm_edge_off;
+    const int e0 = off[ck.lm0], d0 = (ck.lm1 > ck.lm0) ? off[ck.lm0 + 1] - e0 : 0;
+    bool ok = d0 > 0 && d0 <= kMaxSmallPoses;
+    for (int l = ck.lm0 + 1 + (int)threadIdx.x; l < ck.lm1 && ok; l += blockDim.x) {
+        const int el = off[l];
+        if (off[l + 1] - el != d0) { ok = false; break; }
+        for (int k = 0; k < d0; ++k)
+            if ((B.edge_pose[el + k] ^ B.edge_pose[e0 + k]) & kPoseMask) { ok = false; break; }
+    }
+    ok = __syncthreads_and(ok);
+    if (threadIdx.x == 0) out[blockIdx.x] = ok ? 1 : 0;
+}
+
 // per landmark: active flag, pose_active marks, degree check
 __global__ void k_struct_lm(Batch B) {
     const int w = blockIdx.y;

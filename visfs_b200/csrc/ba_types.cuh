@@ -92,6 +92,7 @@ struct Batch {
     int *ctl_count;                  // [n_win] CTAs of k_update that have finished this trial: the last one runs the LM controller
     const Tile *tiles;               // tile table, chunk c owns tiles [chunk_tile_off[c], chunk_tile_off[c + 1])
     const int *chunk_tile_off;       // [n_chunks + 1]
+    const int *chunk_regular;        // [n_chunks] 1: all landmarks of the chunk are seen by the same poses in the same order (or null)
     const Tile *wtiles;              // warp tiles of k_update (<= 32 edges, whole landmarks), same indexing
     const int *chunk_wtile_off;      // [n_chunks + 1]
     // large-window path (ba_large.cuh): block-skyline reduced camera system in the reduce buffer

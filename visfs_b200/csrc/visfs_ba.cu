@@ -103,7 +103,7 @@ struct visfs_ba_handle {
     // device memory
     DevBuf d_st, d_pose, d_point, d_pose_flags, d_lm_flags, d_pose_hidx, d_pose_active, d_point_hidx,
         d_lm_edge_off, d_obs_u, d_obs_v, d_obs_r, d_edge_pose, d_edge_point, d_edge_orig, d_covis, d_part, d_part2, d_xp,
-        d_n_running, d_ctl_count, d_lm_sum, d_tiles, d_tile_off, d_tile_cnt, d_wtiles, d_wtile_off;
+        d_n_running, d_ctl_count, d_lm_sum, d_chunk_regular, d_tiles, d_tile_off, d_tile_cnt, d_wtiles, d_wtile_off;
     // the caller's arrays, window and chunk descriptors: ONE device buffer with the layout of the pinned staging buffer,
     // filled by ONE H2D copy (a single-window call is latency-bound: ten small copies cost ~50 us)
     DevBuf d_in;
@@ -288,6 +288,7 @@ Batch make_batch(visfs_ba_handle *h) {
     b.link_win = h->d_link_win.as<int>(); b.link_from = h->d_link_from.as<int>(); b.link_to = h->d_link_to.as<int>();
     b.link_m = h->d_link_m.as<double>(); b.link_lin = h->d_link_lin.as<double>();
     b.tiles = h->d_tiles.as<Tile>(); b.chunk_tile_off = h->d_tile_off.as<int>();
+    b.chunk_regular = (h->use_ws && !h->use_ds && !getenv("VISFS_BA_NO_REGULAR")) ? h->d_chunk_regular.as<int>() : nullptr;
     b.wtiles = h->d_wtiles.as<Tile>(); b.chunk_wtile_off = h->d_wtile_off.as<int>();
     b.sky_first = h->d_sky_first.as<int>(); b.sky_off = h->d_sky_off.as<long long>();
     b.col_ptr = h->d_col_ptr.as<int>(); b.col_rows = h->d_col_rows.as<int>();
@@ -445,6 +446,7 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs, const DevIn
     }
     CK(h->d_part2.reserve(sizeof(double) * 2 * std::max(std::max(h->n_chunks, 1), std::max(h->grid_build_l, h->grid_update_l))));
     if (h->use_ws) CK(h->d_lm_sum.reserve(sizeof(double) * 9 * L));
+    if (h->use_ws) CK(h->d_chunk_regular.reserve(sizeof(int) * (size_t)std::max(h->n_chunks, 1)));
     CK(h->d_xp.reserve(sizeof(double) * 6 * P)); CK(h->d_n_running.reserve(sizeof(int) * 4)); CK(h->d_ctl_count.reserve(sizeof(int) * (size_t)n));
     const size_t max_tiles = 2 * E / (ds::kEdges + 1) + L / ds::kLm + 2 * (size_t)h->n_chunks + 8;   // (bound for either tile shape)
     CK(h->d_tiles.reserve(sizeof(Tile) * max_tiles));
@@ -628,6 +630,7 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs, const DevIn
         CK(h->d_tmp2.reserve(tmp_bytes));
         CK(cub::DeviceScan::ExclusiveSum(h->d_tmp2.p, tmp_bytes, h->d_tile_cnt.as<int>(), h->d_tile_off.as<int>(), nc1, s));
         if (h->n_chunks) k_fill_tiles<<<(h->n_chunks + 127) / 128, 128, 0, s>>>(B, h->d_tile_off.as<int>(), h->d_tiles.as<Tile>(), tile_lm, tile_edges);
+        if (h->n_chunks && B.chunk_regular) k_chunk_regular<<<h->n_chunks, 128, 0, s>>>(B, h->d_chunk_regular.as<int>());
         // warp tiles of k_update (d_tile_cnt is reused: the scan above has consumed it)
         k_count_wtiles<<<(nc1 + 127) / 128, 128, 0, s>>>(B, h->d_tile_cnt.as<int>());
         CK(cub::DeviceScan::ExclusiveSum(h->d_tmp2.p, tmp_bytes, h->d_tile_cnt.as<int>(), h->d_wtile_off.as<int>(), nc1, s));
