@@ -460,9 +460,11 @@ def dense_window_numbers(ba, quick):
     """BASELINE config C5: 200 key frames orbiting one scene, 200 000 landmarks x 10 random views (dense reduced system)."""
     w = synth.config_c5(n_poses=200, n_points=50000 if quick else 200000)
     ba.upload([w])
-    ba.run_resident()
-    ba.run_resident()
-    t = ba.timing()
+    runs = []
+    for _ in range(4):          # one warm-up, then the median of three (the build adds with L2 atomics: 10-20 % run-to-run spread
+        ba.run_resident()       # was observed right after the GPU had idled through the CPU oracle of C4)
+        runs.append(ba.timing())
+    t = sorted(runs[1:], key=lambda x: x["total_ms"])[1]
     r = ba.download()[0]
     return {"workload": f"C5 dense window: {w['n_poses']} key frames, {w['n_points']} landmarks, {w['n_edges']} edges, one GPU",
             "lm_iterations": int(t["lm_iterations"]), "lm_trials": int(t["lm_trials"]), "ms_per_solve": t["total_ms"],

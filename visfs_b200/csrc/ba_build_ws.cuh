@@ -240,7 +240,8 @@ __device__ __forceinline__ void build_ws_body(const Batch &B, int cluster_size, 
         for (int i = tid; i < n_pose; i += kThreadsWs) sm.hidx[i] = B.pose_hidx[pose_off + i];
     }
     for (int i = tid; i < kMaxFreeWs * kHStride; i += kThreadsWs) sm.pacc[i] = 0.0;
-    const bool reg = !BAND && kProdShare == 0 && B.chunk_regular != nullptr && B.chunk_regular[blockIdx.x] != 0 && F <= kRegMaxFree;
+    // (from 4 tiles up: clearing the accumulators and reducing them by pose costs about as much as two tiles' worth of slot-table sums)
+    const bool reg = !BAND && kProdShare == 0 && ntiles >= 4 && B.chunk_regular != nullptr && B.chunk_regular[blockIdx.x] != 0 && F <= kRegMaxFree;
     if (reg)
         for (int i = tid; i < kTileEdges * kHStride; i += kThreadsWs) { sm.st[0].H[i] = 0.0; sm.st[1].H[i] = 0.0; }
     __syncthreads();
