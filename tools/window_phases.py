@@ -16,6 +16,9 @@ max_pts, max_obs = (32768, 262144) if big else (4096, 32768)
 first_seen = np.full(seq["n_points"], 10**9)
 np.minimum.at(first_seen, seq["edge_point"], seq["edge_pose"])
 ba = capi.BundleAdjuster(0)
+if 'ctx' in sys.argv:   # the handle first runs a pipelined batch (20 sub-handles, streams, page-locked staging)
+    _p = ba.prepare_batch(synth.config_c3_windows(512), pinned=True, float_obs=True)
+    ba.solve_packed(_p); ba.solve_packed(_p)
 win = capi.ResidentWindow(ba, views + 1, max_pts, max_obs, fx=seq["fx"], fy=seq["fy"], cx=seq["cx"], cy=seq["cy"], bf=seq["bf"],
                           pixel_variance=seq["pixel_variance"], huber_delta=seq["huber_delta"], iterations=seq["iterations"])
 lib, W = ba.lib, win.w

@@ -43,7 +43,8 @@ struct DevBuf {
         if (bytes <= cap) return cudaSuccess;
         if (p) cudaFree(p);
         p = nullptr; cap = 0;
-        const size_t want = bytes + bytes / 4 + 256;
+        const size_t want = bytes + bytes / 2 + 256;   // (x 1.5: a map that grows frame by frame re-allocates every ~5 frames instead of every 2;
+                                                       //  cudaFree + cudaMalloc cost milliseconds in a process with many streams and page-locked buffers)
         cudaError_t e = cudaMalloc(&p, want);
         if (e == cudaSuccess) cap = want;
         return e;
@@ -63,7 +64,8 @@ struct PinBuf {
         if (bytes <= cap) return cudaSuccess;
         if (p) cudaFreeHost(p);
         p = nullptr; cap = 0;
-        const size_t want = bytes + bytes / 4 + 256;
+        const size_t want = bytes + bytes / 2 + 256;   // (x 1.5: a map that grows frame by frame re-allocates every ~5 frames instead of every 2;
+                                                       //  cudaFree + cudaMalloc cost milliseconds in a process with many streams and page-locked buffers)
         cudaError_t e = cudaMallocHost(&p, want);
         if (e == cudaSuccess) cap = want;
         return e;
@@ -2322,6 +2324,19 @@ int visfs_ba_window_create(visfs_ba_handle *h, const visfs_ba_window_config *cfg
     R(w->d_slot_of_rank, 4 * L); R(w->d_key, 4 * E); R(w->d_key2, 4 * E); R(w->d_val, 4 * E); R(w->d_val2, 4 * E); R(w->d_counters, 16);
     R(w->d_pose_out, 56 * F); R(w->d_outliers, 8 * E); R(w->d_list, 8 * E); R(w->d_mask, 4 * L);
     if (e == cudaSuccess) e = w->h_small.reserve(4096 + 56 * F + 8 * E);
+    // everything a solve or a delta may need later is allocated now: cudaMalloc / cudaFree / cudaMallocHost in the middle of a
+    // session cost milliseconds once the process holds many streams and large page-locked buffers
+    if (e == cudaSuccess) {
+        size_t tb_scan = 0, tb_sort = 0, tb_scan2 = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tb_scan, (const int *)nullptr, (int *)nullptr, (int)L, h->stream);
+        cub::DeviceScan::ExclusiveSum(nullptr, tb_scan2, (const int *)nullptr, (int *)nullptr, (int)E + 1, h->stream);
+        cub::DeviceRadixSort::SortPairs(nullptr, tb_sort, (const unsigned *)nullptr, (unsigned *)nullptr, (const int *)nullptr, (int *)nullptr, (int)E, 0, 32, h->stream);
+        R(w->d_scan_tmp, std::max(tb_scan, tb_scan2)); R(w->d_sort_tmp, tb_sort);
+        R(w->d_compact, 25 * E + 64);
+        const size_t stage_bytes = 64 + 21 * std::max<size_t>(E / 4, 1024) + 37 * std::min<size_t>(L, 16384);
+        R(w->d_stage, stage_bytes);
+        if (e == cudaSuccess) e = w->h_stage.reserve(stage_bytes);
+    }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&w->stage_done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMemsetAsync(w->d_ob_dead.p, 0, E, h->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(w->d_mask.p, 0, 4 * L, h->stream);
