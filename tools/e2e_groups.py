@@ -13,11 +13,17 @@ packed = ba.prepare_batch(ws, pinned=True, float_obs=True)
 for rep in range(2):
     sweep = ((1.22, 99, 16), (1.22, 12, 16), (1.22, 10, 20), (1.22, 10, 24), (1.3, 8, 20), (1.15, 99, 16), (1.22, 99, 20))
     if len(sys.argv) > 2 and sys.argv[2] == "big":   # large batches: more, flatter groups
-        sweep = ((1.22, 10, 20), (1.22, 14, 20), (1.22, 20, 20), (1.3, 10, 20), (1.15, 10, 20), (1.22, 12, 24), (1.22, 9, 18), (1.22, 11, 22), (1.4, 10, 20))
+        sweep = ((1.22, 10, 20), (1.22, 10, 16), (1.22, 12, 24), (1.3, 10, 20), (1.22, 8, 20), (1.22, 10, 28), (1.18, 12, 20))
+    if len(sys.argv) > 3:   # explicit group counts: default ramp, plus 0 = the library's own choice
+        sweep = tuple((1.22, max(4, int(x) // 2), int(x)) for x in sys.argv[3].split(','))
     for ramp, flat, g in sweep:
         os.environ["VISFS_BA_RAMP"] = str(ramp)
         os.environ["VISFS_BA_RAMP_FLAT"] = str(flat)
-        os.environ["VISFS_BA_GROUPS"] = str(g)
+        if g > 0:
+            os.environ["VISFS_BA_GROUPS"] = str(g)
+            os.environ["VISFS_BA_RAMP_FLAT"] = str(flat)
+        else:
+            os.environ.pop("VISFS_BA_GROUPS", None); os.environ.pop("VISFS_BA_RAMP_FLAT", None)
         for _ in range(2):
             ba.solve_packed(packed)
         t0 = time.perf_counter()
