@@ -152,14 +152,16 @@ bool Optimizer::marshal(std::size_t _rootId,
     const Eigen::Isometry3d Trc = cameraModel.getTansformImageToRobot();
     m.clear();
 
-    std::map<std::size_t, int> poseIndex;
+    // pose ids in ascending order with their indices: the observations of a feature are keyed by signature id in ascending
+    // order too (std::map), so both lookups below are merge walks instead of tree searches
+    std::vector<std::size_t> poseKey;
     for (auto iter = _poses.begin(); iter != _poses.end(); ++iter) {
         if (iter->first > 0) {                                            // :101
             Eigen::Isometry3d cameraPose = iter->second * Trc;           // :104  Twc = Twr * Trc
             cameraPose = cameraPose.inverse();                            // :108  Tcw
             double q[4];
             rotationToQuaternion(cameraPose.linear(), q);                 // :109  CameraPose(R, t)
-            poseIndex.emplace(iter->first, static_cast<int>(m.pose_id.size()));
+            poseKey.push_back(iter->first);
             m.pose_id.push_back(static_cast<int64_t>(iter->first));
             m.pose_fixed.push_back(iter->first == _rootId ? 1 : 0);       // :111
             const Eigen::Vector3d & t = cameraPose.translation();
@@ -167,38 +169,43 @@ bool Optimizer::marshal(std::size_t _rootId,
             m.pose_tq.append(rec, rec + 7);
         }
     }
+    const std::size_t nPose = poseKey.size();
 
     const Eigen::Matrix3d K = cameraModel.eigenKdouble();                 // :176
     double baseLine = 0.0;
     if (_cameraModels.size() > 1) baseLine = cameraModel.getBaseLine();   // :181-183 (float -> double)
     m.fx = K(0, 0); m.fy = K(1, 1); m.cx = K(0, 2); m.cy = K(1, 2);
     m.bf = baseLine * m.fx;                                               // :195
+    const double bfx = baseLine * K(0, 0);
 
+    auto pit = _points3D.begin();
     for (auto iter = _wordReferences.begin(); iter != _wordReferences.end(); ++iter) {   // :156
         const std::size_t id = iter->first;
-        auto pit = _points3D.find(id);
-        if (pit == _points3D.end()) continue;                             // :158
+        while (pit != _points3D.end() && pit->first < id) ++pit;          // _points3D.find(id), both maps ascend
+        if (pit == _points3D.end() || pit->first != id) continue;         // :158
         const int pointIndex = static_cast<int>(m.point_id.size());
         const Eigen::Vector3d & pointPose = std::get<0>(pit->second);
         m.point_id.push_back(static_cast<int64_t>(id));
         m.point_fixed.push_back(std::get<1>(pit->second) ? 1 : 0);        // :165
         m.point_xyz.push_back(pointPose[0]); m.point_xyz.push_back(pointPose[1]); m.point_xyz.push_back(pointPose[2]);
+        std::size_t pk = 0;
         for (auto jter = iter->second.begin(); jter != iter->second.end(); ++jter) {     // :169
-            auto cit = poseIndex.find(jter->first);
-            if (cit == poseIndex.end()) continue;                         // :172
+            while (pk < nPose && poseKey[pk] < jter->first) ++pk;         // uContains(_poses, jter->first)
+            if (pk == nPose) break;                                       // (every later signature id is larger still)
+            if (poseKey[pk] != jter->first) continue;                     // :172
             const FeatureBA & pt = jter->second;
             const double depth = pt.depth;                                // :174
             float obs[3] = {pt.kpt.pt.x, pt.kpt.pt.y, 0.0f};
             uint8_t kind = VISFS_BA_EDGE_MONO;
             if (std::isfinite(depth) && depth > 0.0 && baseLine > 0.0) {  // :184
-                const float disparity = static_cast<float>(baseLine * K(0, 0) / depth);   // :187
+                const float disparity = static_cast<float>(bfx / depth);  // :187
                 obs[2] = pt.kpt.pt.x - disparity;                         // :188  (float - float; the device widens it)
                 kind = VISFS_BA_EDGE_STEREO;
             }
             // else: the reference's mono branch is commented out (:197-208) and its live code is undefined
             // behaviour; this build defines the mono edge as rows 0-1 of EdgeStereo.
             m.edge_obs.append(obs, obs + 3);
-            m.edge_pose.push_back(cit->second);
+            m.edge_pose.push_back(static_cast<int32_t>(pk));
             m.edge_point.push_back(pointIndex);
             m.edge_kind.push_back(kind);
         }

@@ -32,7 +32,7 @@ template <typename T> void wrv(std::ostream &os, const Optimizer::detail::HostAr
 }  // namespace
 
 int main(int argc, char **argv) {
-    if (argc != 4) { std::fprintf(stderr, "usage: %s marshal|solve|time|resident <in> <out>\n", argv[0]); return 2; }
+    if (argc != 4) { std::fprintf(stderr, "usage: %s marshal|marshaltime|solve|time|resident <in> <out>\n", argv[0]); return 2; }
     const std::string mode = argv[1];
     std::ifstream in(argv[2], std::ios::binary);
     if (!in) { std::fprintf(stderr, "cannot open %s\n", argv[2]); return 2; }
@@ -86,6 +86,15 @@ int main(int argc, char **argv) {
         cameraModels.push_back(std::make_shared<GeometricCamera>(std::vector<double>{fx, fy, cx, cy, baseline}));
 
     std::ofstream out(argv[3], std::ios::binary);
+    if (mode == "marshaltime") {   // the map walk alone, no device needed: ms per call over 50 calls
+        Optimizer::detail::MarshalledWindow m;
+        Optimizer::Optimizer::marshal((std::size_t)rootId, poses, cameraModels, points3D, wordReferences, m);
+        const auto t0 = std::chrono::steady_clock::now();
+        for (int r = 0; r < 50; ++r) Optimizer::Optimizer::marshal((std::size_t)rootId, poses, cameraModels, points3D, wordReferences, m);
+        std::printf("{\"marshal_ms\": %.4f, \"edges\": %lld}\n",
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() / 50, (long long)m.edge_pose.size());
+        return 0;
+    }
     if (mode == "marshal") {
         Optimizer::detail::MarshalledWindow m;
         const bool ok = Optimizer::Optimizer::marshal((std::size_t)rootId, poses, cameraModels, points3D, wordReferences, m);
