@@ -355,7 +355,7 @@ def resident_window_numbers(ba, quick, size="c0", _warm=True):
             "h2d_bytes_per_frame_resident": h2d_res // n, "h2d_bytes_per_frame_full_call": h2d_full // n,
             "note": "resident: set_points + insert_frame + remove_frame + solve + remove_observations per frame; full call: one visfs_ba_solve "
                     "on a pre-marshalled page-locked window.  Neither clock contains host marshalling: the reference's std::map walk that the "
-                    "resident map makes unnecessary is single_window.*.local_optimize_marshal_ms (c0: 0.02 ms, c2: 2.2 ms per call).  At the "
+                    "resident map makes unnecessary is single_window.*.local_optimize_marshal_ms (c0: 0.02 ms, c2: 1.3 ms per call).  At the "
                     "c0 size both are bound by the ~58 launches of the two-pass LM and the resident path adds ~10 short launches that build "
                     "the window on the device; it pays off from C2-sized maps up, where the map walk is more than the whole GPU call"}
 
