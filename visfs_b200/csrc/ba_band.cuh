@@ -110,6 +110,7 @@ __global__ void __launch_bounds__(256) k_band_chunk(Batch B, int4 *rec, const in
         last = mn;
     }
     __syncthreads();
+    __shared__ int s_ref[kMaxSmallPoses + 1];   // degree and local pose numbers of the chunk's first landmark: the others are compared with it
     if (tid == 0) {
         int F = 0;
         for (int i = 0; i < n; ++i) {
@@ -119,14 +120,26 @@ __global__ void __launch_bounds__(256) k_band_chunk(Batch B, int4 *rec, const in
         chunk[c].n_pose = n;
         chunk[c].F = (n >= 0) ? F : 0;
         if (n >= 0) atomicAdd(&counts[0], lm1 - lm0);
+        const int4 r0 = rec[lm0];
+        s_ref[0] = (n >= 0 && r0.z <= kMaxSmallPoses) ? r0.z : -1;
+        for (int k = 0; k < r0.z && s_ref[0] >= 0; ++k) {
+            const int p = B.edge_pose[r0.y + k] & kPoseMask;
+            int loc = 0;
+            while (loc < n - 1 && s_list[loc] != p) ++loc;
+            s_ref[1 + k] = loc;
+        }
     }
+    __syncthreads();
+    bool same = s_ref[0] > 0;
     for (int i = lm0 + tid; i < lm1; i += 256) {
         int4 r = rec[i];
         const int base = sorted_off[i];
+        if (r.z != s_ref[0]) same = false;
         for (int k = 0; k < r.z && n >= 0; ++k) {
             const int e = r.y + k, pw = B.edge_pose[e], p = pw & kPoseMask;
             int loc = 0;
             while (loc < n - 1 && s_list[loc] != p) ++loc;
+            if (same && loc != s_ref[1 + k]) same = false;
             s_pw[base + k] = (pw & ~kPoseMask) | loc;
             s_gl[base + k] = wd.point_off + B.edge_point[e];
             s_sl[base + k] = i;
@@ -135,6 +148,8 @@ __global__ void __launch_bounds__(256) k_band_chunk(Batch B, int4 *rec, const in
         if (n < 0) { r.w |= kBandFlag; rec[i] = r; }
         else B.lm_flags[wd.point_off + r.x] |= kInBand;
     }
+    same = __syncthreads_and(same);
+    if (tid == 0) { chunk[c].regular = (same && n >= 0) ? 1 : 0; chunk[c].pad = 0; }
 }
 
 // the landmarks outside the band chunks, compacted in sorted order for lg::k_build_large_run (pos = exclusive scan of flag)

@@ -71,6 +71,7 @@ constexpr int kBandPartStride = 7472;          // doubles per chunk slot >= part
 struct BandChunk {
     int lm0, lm1;                              // landmark range in the sorted order
     int n_pose, F;                             // poses the chunk touches / the free ones among them; n_pose < 0: not a band chunk
+    int regular, pad;                          // 1: all landmarks of the chunk are seen by the same poses in the same order
 };
 struct Band {
     const BandChunk *chunk;
@@ -213,7 +214,7 @@ __device__ __forceinline__ void build_ws_body(const Batch &B, int cluster_size, 
     const WinDesc &wd = B.win[win];
     const LMState &st = B.st[win];
     if (st.done) return;   // uniform over the cluster: all its chunks belong to one window
-    BandChunk bc{0, 0, 0, 0};
+    BandChunk bc{0, 0, 0, 0, 0, 0};
     if (BAND) { bc = bd.chunk[cidx]; if (bc.n_pose < 0) return; }
     const int *__restrict__ cpose = BAND ? bd.chunk_pose + (size_t)cidx * kBandPoses : nullptr;
     const int cur = st.cur;
@@ -241,7 +242,8 @@ __device__ __forceinline__ void build_ws_body(const Batch &B, int cluster_size, 
     }
     for (int i = tid; i < kMaxFreeWs * kHStride; i += kThreadsWs) sm.pacc[i] = 0.0;
     // (from 4 tiles up: clearing the accumulators and reducing them by pose costs about as much as two tiles' worth of slot-table sums)
-    const bool reg = !BAND && kProdShare == 0 && ntiles >= 4 && B.chunk_regular != nullptr && B.chunk_regular[blockIdx.x] != 0 && F <= kRegMaxFree;
+    const bool reg = kProdShare == 0 && ntiles >= 4 && F <= kRegMaxFree &&
+                     (BAND ? bc.regular != 0 : (B.chunk_regular != nullptr && B.chunk_regular[blockIdx.x] != 0));
     if (reg)
         for (int i = tid; i < kTileEdges * kHStride; i += kThreadsWs) { sm.st[0].H[i] = 0.0; sm.st[1].H[i] = 0.0; }
     __syncthreads();

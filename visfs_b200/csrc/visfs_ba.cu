@@ -1091,10 +1091,10 @@ int prep_band(visfs_ba_handle *h) {
     if (nc <= 0 || nc >= (1 << 22) || (size_t)nc * ws::kBandPartStride * sizeof(double) > ((size_t)8 << 30)) return VISFS_BA_OK;   // (partials <= 8 GB)
     // per-chunk tables: [chunk (4 ints) | chunk_pose (19) | ntiles | tile_off | npair | pair_off | npose | pose_off] (nc + 1 each) | counts
     const size_t c1 = ((size_t)nc + 1 + 3) & ~(size_t)3;
-    CK(h->d_bd_chunk.reserve(sizeof(int) * (c1 * (4 + ws::kBandPoses + 10) + 4)));
+    CK(h->d_bd_chunk.reserve(sizeof(int) * (c1 * (6 + ws::kBandPoses + 10) + 4)));
     int *cb = h->d_bd_chunk.as<int>();
     ws::BandChunk *chunk = reinterpret_cast<ws::BandChunk *>(cb);
-    int *chunk_pose = cb + 4 * c1, *ntiles = chunk_pose + ws::kBandPoses * c1, *tile_off = ntiles + c1, *npair = tile_off + c1,
+    int *chunk_pose = cb + 6 * c1, *ntiles = chunk_pose + ws::kBandPoses * c1, *tile_off = ntiles + c1, *npair = tile_off + c1,
         *pair_off = npair + c1, *npose = pair_off + c1, *pose_off = npose + c1, *cost = pose_off + c1, *cidx = cost + c1,
         *cost2 = cidx + c1, *order = cost2 + c1, *counts = order + c1;
     CK(cudaMemsetAsync(counts, 0, sizeof(int) * 4, s));
