@@ -93,6 +93,7 @@ struct visfs_ba_handle {
     int n_win = 0, n_chunks = 0, tot_pose = 0, tot_point = 0, tot_edge = 0, max_pose = 0, max_iter = 0, tot_link = 0;
     DevBuf d_link_win, d_link_from, d_link_to, d_link_m, d_link_lin;
     bool resident = false, has_run = false, sorted = true, use_ws = false;
+    int max_clusters8 = 0;            // resident clusters of 8 k_build_ws CTAs (cudaOccupancyMaxActiveClusters)
     bool use_ds = false;              // k_build_ds (Schur products on the FP64 tensor pipe): windows of <= 10 poses; opt-in
                                       // (VISFS_BA_USE_DS=1) -- measured 19 % slower per C3 step than k_build_ws, DESIGN.md §5
     int cluster = 1;
@@ -378,8 +379,13 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs, const DevIn
     h->use_ds = h->use_ws && max_pose <= ds::kMaxPosesDs && getenv("VISFS_BA_USE_DS") != nullptr;
     const int sms = std::max(h->sm_count, 8);
     int per_window = 1;
+    bool wide_clusters = false;
     if (n == 1) {
-        per_window = std::max(1, std::min((max_point + kTileLm / 2 - 1) / (kTileLm / 2), (sms * 7 / 8) / 4 * 4));
+        int cap_pw = (sms * 7 / 8) / 4 * 4;
+        // one wave of clusters of 8 when the device holds >= 12 of them at once (B200: 15 -> 120 chunks; C1 0.754 -> 0.724 ms)
+        if (h->use_ws && h->max_clusters8 >= 12 && !getenv("VISFS_BA_CLUSTER") && !getenv("VISFS_BA_NO_CLUSTER")) { cap_pw = h->max_clusters8 * 8; wide_clusters = true; }
+        if (const char *e = getenv("VISFS_BA_PERWINDOW")) cap_pw = std::max(1, atoi(e));   // (experiments)
+        per_window = std::max(1, std::min((max_point + kTileLm / 2 - 1) / (kTileLm / 2), cap_pw));
         if (const char *e = getenv("VISFS_BA_CHUNKS")) per_window = std::max(1, atoi(e));   // experiments
     } else {
         double best = -1.0;
@@ -393,7 +399,7 @@ int upload(visfs_ba_handle *h, int n, const visfs_ba_problem *probs, const DevIn
     int cl = 1;
     // clusters only for the single-window latency case: 4 CTAs per cluster still fit one wave (33 clusters of 4 are
     // co-resident at 195 KB of shared memory per CTA; clusters of 8 drop that to 15) and cut k_solve's input 4x
-    int cl_max = 4;
+    int cl_max = wide_clusters ? 8 : 4;
     if (const char *e = getenv("VISFS_BA_CLUSTER")) cl_max = std::max(1, std::min(atoi(e), 8));
     if (h->use_ws && n == 1 && !getenv("VISFS_BA_NO_CLUSTER")) while (cl < cl_max && cl * 2 <= per_window) cl *= 2;
     h->cluster = cl;
@@ -1751,6 +1757,18 @@ int visfs_ba_create(const visfs_ba_config *cfg, visfs_ba_handle **out) {
     e = cudaFuncSetAttribute(ws::k_build_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ws::Smem));
     cudaFuncSetAttribute(ds::k_build_ds, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ds::Smem));
     cudaFuncSetAttribute(ws::k_build_band, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ws::Smem));
+    {   // how many clusters of 8 k_build_ws CTAs the device keeps resident at once (B200: 15): the single-window decomposition
+        // uses clusters of 8 when one wave of them covers the window (k_solve then reads half as many partial systems)
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(8 * 16); cfg.blockDim = dim3(ws::kThreadsWs); cfg.dynamicSmemBytes = sizeof(ws::Smem);
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 8; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        int nc = 0;
+        if (cudaOccupancyMaxActiveClusters(&nc, ws::k_build_ws, &cfg) != cudaSuccess) { nc = 0; cudaGetLastError(); }
+        h->max_clusters8 = nc;
+    }
     if (getenv("VISFS_BA_VERBOSE")) {
         cudaFuncAttributes fa{};
         cudaFuncGetAttributes(&fa, ws::k_build_ws);
